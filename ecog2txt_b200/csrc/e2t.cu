@@ -1,0 +1,894 @@
+// e2t.cu -- C-ABI (include/e2t.h) and host orchestration of the seq2seq hot path.
+//
+// Data layout in HBM (all fp32, row-major, time-major activations so that one time step of every
+// utterance is one contiguous [B, F] matrix -- the A operand of the recurrent GEMM):
+//   x           [B, T, C]        caller's ECoG batch (read once, by the fused reverse+conv GEMM)
+//   conv_out    [T', B, E]       T' = ceil(T/W)
+//   hs[l]       [T', B, 2H]      BiLSTM outputs, fwd in [:H], bwd in [H:]; hd[l] = dropped copy
+//   gates[l][d] [T', B, 4H]      x-projection -> gate activations (fwd) -> dz (bwd), in place
+//   cs[l][d]    [T', B, H]       cell states
+//   decoder: demb [L,B,Dp], dgates [L,B,4Hd], dcs/hdec [L,B,Hd], logits [L,B,Vp] (-> dlogits in place)
+// Parameters: one flat fp32 buffer per kind (value / grad / adam m / adam v / EMA) in TF-checkpoint
+// layout and order (subject-private tensors first), see e2t.h.
+#include "../../include/e2t.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_simt.cuh"
+#ifndef E2T_EMU
+#include "gemm_tc.cuh"
+#endif
+
+static thread_local std::string g_err;
+extern "C" const char* e2t_last_error(void) { return g_err.c_str(); }
+extern "C" int e2t_abi_version(void) { return 1; }
+
+namespace {
+
+struct TensorInfo {
+  std::string name;
+  std::vector<int64_t> shape;
+  i64 off = 0, n = 0;
+  int subnet = -1;  // -1 = shared
+  bool trainable = true;
+};
+
+struct EncLayer {
+  int In, H;
+  i64 K[2], b[2];           // offsets into the flat parameter buffers
+  float *hs = nullptr, *hd = nullptr, *dhs = nullptr;
+  float* gates[2] = {nullptr, nullptr};
+  float* cs[2] = {nullptr, nullptr};
+  float* KT[2] = {nullptr, nullptr};   // packed [4H, ldkt] transposed kernels (K-major B operand)
+  int ldkt = 0;
+};
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static inline i64 cdiv(i64 a, i64 b) { return (a + b - 1) / b; }
+
+}  // namespace
+
+struct e2t_handle {
+  e2t_config cfg;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::vector<TensorInfo> tensors;
+  std::map<std::string, int> by_name;
+  i64 n_params = 0;
+  float *P = nullptr, *G = nullptr, *M = nullptr, *Vv = nullptr, *S = nullptr;
+  const float* Wc = nullptr;  // weights used by the current forward pass (P or S)
+  int64_t step = 0;
+  int64_t n_launch = 0, n_launch_tc = 0;
+  bool packed_dirty = true;
+  int packed_src = -1;
+
+  // parameter offsets
+  i64 conv_w[E2T_MAX_SUBNETS], conv_b[E2T_MAX_SUBNETS];
+  std::vector<EncLayer> enc;
+  i64 demb_w, demb_b, dec_K, dec_b, proj_w, proj_b;
+
+  // capacities
+  int Bm, Tm, Lm, T2m, Cmax, Dp, Vp, beam_m;
+  // packed decoder weights
+  float* dec_KT = nullptr; int ld_dec_kt = 0;   // [4Hd, D+Hd (padded)]
+  float* proj_wT = nullptr;                      // [Hd, Vp]
+  float* conv_wT[E2T_MAX_SUBNETS];               // [E, W*C]
+
+  // workspace
+  std::vector<void*> allocs;
+  float *d_x, *conv_out, *dconv;
+  int *d_lens_in, *d_lens, *d_lens2, *d_tlast, *d_y, *d_prev, *d_tgt;
+  float *h0, *c0, *dh0, *dc0, *dh_rec, *dc_rec;
+  float *demb, *ddemb, *dgates, *dcs, *hdec, *dhdec, *logits, *loss_rows, *d_loss;
+  int* d_ntok;
+  // decode workspace
+  float *g_h[2], *g_c[2], *g_e, *g_z, *g_logits, *g_logp, *g_score[2], *g_lse;
+  int *g_prev[2], *g_done[2], *g_tokens[2], *g_src, *g_tok;
+  // last-forward bookkeeping for e2t_get_activation
+  int last_B = 0, last_T2 = 0, last_L = 0, last_subnet = 0;
+
+  template <typename T>
+  T* alloc(i64 n) {
+    void* p = nullptr;
+    E2T_CHECK(cudaMalloc(&p, (size_t)std::max<i64>(n, 1) * sizeof(T)));
+    E2T_CHECK(cudaMemset(p, 0, (size_t)std::max<i64>(n, 1) * sizeof(T)));
+    allocs.push_back(p);
+    return static_cast<T*>(p);
+  }
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// launches
+// ------------------------------------------------------------------------------------------------
+#define LAUNCH(h, kern, grid, block, smem, ...)                       \
+  do {                                                                \
+    E2T_LAUNCH(kern, grid, block, smem, (h)->stream, __VA_ARGS__);    \
+    ++(h)->n_launch;                                                  \
+  } while (0)
+
+inline dim3 grid1(i64 n, int block = 256) { return dim3((unsigned)cdiv(n, block)); }
+
+// C[M,N] = A(m,k) B(k,n) + bias + beta*C with arbitrary strides; dispatches to tcgen05 when possible.
+void gemm(e2t_handle* h, const float* A, i64 sam, i64 sak, const float* B, i64 sbk, i64 sbn, float* C, i64 ldc,
+          int M, int N, int K, const float* bias, float beta) {
+  if (M <= 0 || N <= 0) return;
+  if (K <= 0) {
+    E2T_REQUIRE(beta == 1.f && !bias, "empty-K gemm must be a no-op");
+    return;
+  }
+#ifndef E2T_EMU
+  if (h->cfg.gemm_backend != E2T_GEMM_SIMT && sak == 1 && sbk == 1 &&
+      tc_gemm_nt_supported(A, sam, B, sbn, C, ldc, M, N, K)) {
+    tc_gemm_nt(h->stream, A, sam, B, sbn, C, ldc, M, N, K, bias, beta);
+    ++h->n_launch;
+    ++h->n_launch_tc;
+    return;
+  }
+#endif
+  GemmP p{};
+  p.A = A; p.sam = sam; p.sak = sak;
+  p.B = B; p.sbk = sbk; p.sbn = sbn;
+  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.beta = beta;
+  dim3 grid((unsigned)cdiv(N, 64), (unsigned)cdiv(M, 64));
+  auto kfn = k_gemm<0>;
+  LAUNCH(h, kfn, grid, dim3(256), 0, p);
+}
+
+// conv-gather GEMMs (A3+A4 fused). mode 1: Y[T2*B, E] = gather(x) Wc + b ; mode 2: dWc[W*C, E] = gather(x)^T dY
+void gemm_conv(e2t_handle* h, int mode, const float* x, const int* lens, int Bsz, int T, int Cch, int Wd, int T2,
+               const float* Bmat, i64 sbk, i64 sbn, float* C, i64 ldc, int N, const float* bias, float beta) {
+  GemmP p{};
+  p.x = x; p.lens = lens; p.Bsz = Bsz; p.T = T; p.Cch = Cch; p.Wd = Wd;
+  p.B = Bmat; p.sbk = sbk; p.sbn = sbn; p.C = C; p.ldc = ldc; p.N = N; p.bias = bias; p.beta = beta;
+  if (mode == 1) { p.M = T2 * Bsz; p.K = Wd * Cch; } else { p.M = Wd * Cch; p.K = T2 * Bsz; }
+  if (p.M <= 0 || p.K <= 0) return;
+  dim3 grid((unsigned)cdiv(N, 64), (unsigned)cdiv(p.M, 64));
+  if (mode == 1) { auto kfn = k_gemm<1>; LAUNCH(h, kfn, grid, dim3(256), 0, p); }
+  else           { auto kfn = k_gemm<2>; LAUNCH(h, kfn, grid, dim3(256), 0, p); }
+}
+
+DropP make_drop(uint32_t seed, uint32_t stream, float p) {
+  DropP d;
+  d.key = e2t_stream_key(seed, stream);
+  d.thresh = p > 0.f ? e2t_thresh(p) : 0u;
+  d.inv = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// construction
+// ------------------------------------------------------------------------------------------------
+void add_tensor(e2t_handle* h, const std::string& name, std::vector<int64_t> shape, int subnet) {
+  TensorInfo t;
+  t.name = name; t.shape = shape; t.subnet = subnet;
+  t.n = 1;
+  for (auto s : shape) t.n *= s;
+  t.off = h->n_params;
+  // keep every tensor 16-byte aligned inside the flat buffers (TMA / float4)
+  h->n_params += (t.n + 3) / 4 * 4;
+  h->by_name[name] = (int)h->tensors.size();
+  h->tensors.push_back(t);
+}
+
+void build_params(e2t_handle* h) {
+  const e2t_config& c = h->cfg;
+  char buf[256];
+  for (int s = 0; s < c.n_subnets; ++s) {
+    snprintf(buf, sizeof buf, "seq2seq/subnet_%d/encoder_embedding_%d_%d_0", c.subnet_id[s], c.subnet_C[s], c.E);
+    h->conv_w[s] = h->n_params;
+    add_tensor(h, std::string(buf) + "/weights", {1, c.subnet_W[s], c.subnet_C[s], c.E}, s);
+    h->conv_b[s] = h->n_params;
+    add_tensor(h, std::string(buf) + "/biases", {c.E}, s);
+  }
+  int n_in = c.E;
+  h->enc.resize(c.n_enc_layers);
+  for (int l = 0; l < c.n_enc_layers; ++l) {
+    EncLayer& L = h->enc[l];
+    L.In = n_in; L.H = c.H[l];
+    for (int d = 0; d < 2; ++d) {
+      snprintf(buf, sizeof buf, "seq2seq/encoder_rnn_%d/bidirectional_rnn/%s/multi_rnn_cell/cell_0/lstm_cell", l,
+               d ? "bw" : "fw");
+      L.K[d] = h->n_params;
+      add_tensor(h, std::string(buf) + "/kernel", {n_in + L.H, 4 * L.H}, -1);
+      L.b[d] = h->n_params;
+      add_tensor(h, std::string(buf) + "/bias", {4 * L.H}, -1);
+    }
+    n_in = 2 * L.H;
+  }
+  snprintf(buf, sizeof buf, "seq2seq/decoder_embedding_%d_%d_0", c.V, c.D);
+  h->demb_w = h->n_params; add_tensor(h, std::string(buf) + "/weights", {c.V, c.D}, -1);
+  h->demb_b = h->n_params; add_tensor(h, std::string(buf) + "/biases", {c.D}, -1);
+  const char* rb = "seq2seq/decoder_rnn/multi_rnn_cell/cell_0/lstm_cell";
+  h->dec_K = h->n_params; add_tensor(h, std::string(rb) + "/kernel", {c.D + c.Hd, 4 * c.Hd}, -1);
+  h->dec_b = h->n_params; add_tensor(h, std::string(rb) + "/bias", {4 * c.Hd}, -1);
+  snprintf(buf, sizeof buf, "seq2seq/decoder_projection_%d_%d_0", c.Hd, c.V);
+  h->proj_w = h->n_params; add_tensor(h, std::string(buf) + "/weights", {c.V, c.Hd}, -1);
+  h->proj_b = h->n_params; add_tensor(h, std::string(buf) + "/biases", {c.V}, -1);
+}
+
+void validate(const e2t_config& c) {
+  E2T_REQUIRE(c.n_subnets >= 1 && c.n_subnets <= E2T_MAX_SUBNETS, "n_subnets out of range");
+  E2T_REQUIRE(c.n_enc_layers >= 1 && c.n_enc_layers <= E2T_MAX_LAYERS, "n_enc_layers out of range");
+  for (int s = 0; s < c.n_subnets; ++s)
+    E2T_REQUIRE(c.subnet_C[s] > 0 && c.subnet_W[s] > 0, "subnet C/W must be positive");
+  for (int l = 0; l < c.n_enc_layers; ++l) E2T_REQUIRE(c.H[l] > 0, "encoder_rnn size must be positive");
+  E2T_REQUIRE(c.E > 0 && c.D > 0 && c.Hd > 0 && c.V > 2, "layer sizes must be positive");
+  E2T_REQUIRE(c.Hd == 2 * c.H[c.n_enc_layers - 1], "decoder_rnn must equal 2*encoder_rnn[-1] (state bridge)");
+  E2T_REQUIRE(c.pad_id >= 0 && c.pad_id < c.V && c.eos_id >= 0 && c.eos_id < c.V && c.start_id >= 0 &&
+              c.start_id < c.V, "special token ids out of range");
+  E2T_REQUIRE(c.max_B > 0 && c.max_T > 0 && c.max_L > 0, "capacities must be positive");
+  E2T_REQUIRE(c.ff_dropout >= 0.f && c.ff_dropout < 1.f && c.rnn_dropout >= 0.f && c.rnn_dropout < 1.f,
+              "dropout must be in [0,1)");
+  E2T_REQUIRE(c.max_beam >= 1 && c.max_beam <= 32, "max_beam must be in [1,32]");
+}
+
+void build_workspace(e2t_handle* h) {
+  const e2t_config& c = h->cfg;
+  int minW = c.subnet_W[0];
+  h->Cmax = 0;
+  for (int s = 0; s < c.n_subnets; ++s) { minW = std::min(minW, c.subnet_W[s]); h->Cmax = std::max(h->Cmax, c.subnet_C[s]); }
+  h->Bm = c.max_B; h->Tm = c.max_T; h->Lm = c.max_L; h->beam_m = c.max_beam;
+  h->T2m = (int)cdiv(c.max_T, minW);
+  h->Dp = round_up(c.D, 4); h->Vp = round_up(c.V, 4);
+  const i64 Bm = h->Bm, T2 = h->T2m, Lm = h->Lm;
+  h->P = h->alloc<float>(h->n_params); h->G = h->alloc<float>(h->n_params);
+  h->M = h->alloc<float>(h->n_params); h->Vv = h->alloc<float>(h->n_params);
+  h->S = h->alloc<float>(h->n_params);
+  h->d_x = h->alloc<float>(Bm * h->Tm * h->Cmax);
+  h->conv_out = h->alloc<float>(T2 * Bm * c.E);
+  h->dconv = h->alloc<float>(T2 * Bm * c.E);
+  h->d_lens_in = h->alloc<int>(Bm); h->d_lens = h->alloc<int>(Bm); h->d_lens2 = h->alloc<int>(Bm);
+  h->d_tlast = h->alloc<int>(Bm);
+  h->d_y = h->alloc<int>(Bm * Lm); h->d_prev = h->alloc<int>(Bm * Lm); h->d_tgt = h->alloc<int>(Bm * Lm);
+  int Hmax = c.Hd;
+  for (int l = 0; l < c.n_enc_layers; ++l) {
+    EncLayer& L = h->enc[l];
+    Hmax = std::max(Hmax, L.H);
+    L.hs = h->alloc<float>(T2 * Bm * 2 * L.H);
+    L.dhs = h->alloc<float>(T2 * Bm * 2 * L.H);
+    L.hd = (l + 1 < c.n_enc_layers && c.rnn_dropout > 0.f) ? h->alloc<float>(T2 * Bm * 2 * L.H) : nullptr;
+    L.ldkt = round_up(L.In + L.H, 4);
+    for (int d = 0; d < 2; ++d) {
+      L.gates[d] = h->alloc<float>(T2 * Bm * 4 * L.H);
+      L.cs[d] = h->alloc<float>(T2 * Bm * L.H);
+      L.KT[d] = h->alloc<float>((i64)4 * L.H * L.ldkt);
+    }
+  }
+  h->h0 = h->alloc<float>(Bm * c.Hd); h->c0 = h->alloc<float>(Bm * c.Hd);
+  h->dh0 = h->alloc<float>(Bm * c.Hd); h->dc0 = h->alloc<float>(Bm * c.Hd);
+  h->dh_rec = h->alloc<float>(Bm * Hmax); h->dc_rec = h->alloc<float>(Bm * Hmax);
+  h->demb = h->alloc<float>(Lm * Bm * h->Dp); h->ddemb = h->alloc<float>(Lm * Bm * h->Dp);
+  h->dgates = h->alloc<float>(Lm * Bm * 4 * c.Hd);
+  h->dcs = h->alloc<float>(Lm * Bm * c.Hd); h->hdec = h->alloc<float>(Lm * Bm * c.Hd);
+  h->dhdec = h->alloc<float>(Lm * Bm * c.Hd);
+  h->logits = h->alloc<float>(Lm * Bm * h->Vp);
+  h->loss_rows = h->alloc<float>(Lm * Bm);
+  h->d_loss = h->alloc<float>(4); h->d_ntok = h->alloc<int>(4);
+  h->ld_dec_kt = round_up(c.D + c.Hd, 4);
+  h->dec_KT = h->alloc<float>((i64)4 * c.Hd * h->ld_dec_kt);
+  h->proj_wT = h->alloc<float>((i64)c.Hd * h->Vp);
+  for (int s = 0; s < c.n_subnets; ++s)
+    h->conv_wT[s] = h->alloc<float>((i64)c.E * round_up(c.subnet_W[s] * c.subnet_C[s], 4));
+  // decode workspace (rows = B*beam)
+  const i64 R = Bm * h->beam_m;
+  for (int i = 0; i < 2; ++i) {
+    h->g_h[i] = h->alloc<float>(R * c.Hd); h->g_c[i] = h->alloc<float>(R * c.Hd);
+    h->g_score[i] = h->alloc<float>(R);
+    h->g_prev[i] = h->alloc<int>(R); h->g_done[i] = h->alloc<int>(R);
+    h->g_tokens[i] = h->alloc<int>(R * Lm);
+  }
+  h->g_e = h->alloc<float>(R * h->Dp); h->g_z = h->alloc<float>(R * 4 * c.Hd);
+  h->g_logits = h->alloc<float>(R * h->Vp); h->g_logp = h->alloc<float>(R * Lm);
+  h->g_lse = h->alloc<float>(R); h->g_src = h->alloc<int>(R); h->g_tok = h->alloc<int>(R);
+}
+
+// Re-pack the derived (transposed) weight copies from `src` (P for training, S for EMA decoding).
+void repack(e2t_handle* h, const float* src, int src_id) {
+  if (!h->packed_dirty && h->packed_src == src_id) return;
+  const e2t_config& c = h->cfg;
+  auto tr = [&](const float* in, i64 ldi, float* out, i64 ldo, int K, int N) {
+    dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(K, 32));
+    LAUNCH(h, k_transpose, grid, dim3(256), 0, in, ldi, out, ldo, K, N);
+  };
+  for (auto& L : h->enc)
+    for (int d = 0; d < 2; ++d) tr(src + L.K[d], 4 * L.H, L.KT[d], L.ldkt, L.In + L.H, 4 * L.H);
+  tr(src + h->dec_K, 4 * c.Hd, h->dec_KT, h->ld_dec_kt, c.D + c.Hd, 4 * c.Hd);
+  tr(src + h->proj_w, c.Hd, h->proj_wT, h->Vp, c.V, c.Hd);
+  for (int s = 0; s < c.n_subnets; ++s) {
+    int WC = c.subnet_W[s] * c.subnet_C[s];
+    tr(src + h->conv_w[s], c.E, h->conv_wT[s], round_up(WC, 4), WC, c.E);
+  }
+  h->packed_dirty = false;
+  h->packed_src = src_id;
+}
+
+void use_weights(e2t_handle* h, bool ema) {
+  bool e = ema && h->cfg.ema_decay > 0.f;
+  h->Wc = e ? h->S : h->P;
+  repack(h, h->Wc, e ? 1 : 0);
+}
+
+// stage inputs; returns device pointers
+struct Inputs { const float* x; const int* lens_in; const int* y; };
+Inputs stage(e2t_handle* h, int subnet, const float* x, const int32_t* lens, const int32_t* y, int loc, int B,
+             int T, int L) {
+  const e2t_config& c = h->cfg;
+  E2T_REQUIRE(subnet >= 0 && subnet < c.n_subnets, "subnet index out of range");
+  E2T_REQUIRE(B >= 1 && B <= h->Bm, "B exceeds max_B");
+  E2T_REQUIRE(T >= 1 && T <= h->Tm, "T exceeds max_T");
+  E2T_REQUIRE(L >= 0 && L <= h->Lm, "L exceeds max_L");
+  E2T_REQUIRE(x != nullptr, "x is NULL");
+  Inputs in{};
+  if (loc == E2T_HOST) {
+    size_t nx = (size_t)B * T * c.subnet_C[subnet];
+    E2T_CHECK(cudaMemcpyAsync(h->d_x, x, nx * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    in.x = h->d_x;
+    if (lens) {
+      E2T_CHECK(cudaMemcpyAsync(h->d_lens_in, lens, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      in.lens_in = h->d_lens_in;
+    }
+    if (y) {
+      E2T_CHECK(cudaMemcpyAsync(h->d_y, y, (size_t)B * L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      in.y = h->d_y;
+    }
+  } else {
+    E2T_REQUIRE(loc == E2T_DEVICE, "loc must be E2T_HOST or E2T_DEVICE");
+    in.x = x; in.lens_in = lens; in.y = y;
+  }
+  return in;
+}
+
+// ------------------------------------------------------------------------------------------------
+// encoder forward (A2-A5)
+// ------------------------------------------------------------------------------------------------
+void lstm_layer_forward(e2t_handle* h, const float* in, int ld_in, int In, int H, const float* KT, int ldkt,
+                        const float* bias, float* gates, float* cs, float* hs, float* hd, int ldh, int col0, const int* lens2,
+                        int steps, int B, bool reverse, const float* h_init, const float* c_init, DropP dp,
+                        int drop_F) {
+  // input projection for every step at once: gates[steps*B, 4H] = in Wx + b
+  // KT [4H, ldkt] = kernel^T: column block [0,In) is Wx^T, [In,In+H) is Wh^T (both K-major B operands)
+  gemm(h, in, ld_in, 1, KT, 1, ldkt, gates, 4 * H, steps * B, 4 * H, In, bias, 0.f);
+  const float* WhT = KT + In;
+  for (int s = 0; s < steps; ++s) {
+    int t = reverse ? steps - 1 - s : s;
+    int tp = reverse ? t + 1 : t - 1;
+    const float* hprev = s == 0 ? h_init : hs + (i64)tp * B * ldh + col0;
+    i64 ldp = s == 0 ? H : ldh;
+    const float* cprev = s == 0 ? c_init : cs + (i64)tp * B * H;
+    float* z = gates + (i64)t * B * 4 * H;
+    if (hprev) gemm(h, hprev, ldp, 1, WhT, 1, ldkt, z, 4 * H, B, 4 * H, H, nullptr, 1.f);
+    LstmFwdP p{};
+    p.z = z; p.c_prev = cprev; p.c_out = cs + (i64)t * B * H;
+    p.h_out = hs + (i64)t * B * ldh + col0;
+    p.h_drop = hd ? hd + (i64)t * B * ldh + col0 : nullptr;
+    p.ldh = ldh; p.lens2 = lens2; p.t = t; p.B = B; p.H = H;
+    p.dp = dp; p.drop_F = drop_F; p.drop_col0 = col0;
+    LAUNCH(h, k_lstm_fwd, grid1((i64)B * H), dim3(256), 0, p);
+  }
+}
+
+void encoder_forward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, bool train, uint32_t seed) {
+  const e2t_config& c = h->cfg;
+  const int C = c.subnet_C[subnet], W = c.subnet_W[subnet];
+  const int T2 = (int)cdiv(T, W);
+  const float* Wc = h->Wc;
+  LAUNCH(h, k_lengths, dim3(B), dim3(32), 0, in.x, in.lens_in, h->d_lens, h->d_lens2, h->d_tlast, B, T, C, W);
+  gemm_conv(h, 1, in.x, h->d_lens, B, T, C, W, T2, h->conv_wT[subnet], 1, round_up(W * C, 4), h->conv_out, c.E, c.E,
+            Wc + h->conv_b[subnet], 0.f);
+  DropP dpc = make_drop(seed, E2T_STREAM_CONV, train ? c.ff_dropout : 0.f);
+  if (c.conv_act != E2T_ACT_LINEAR || dpc.thresh)
+    LAUNCH(h, k_act_dropout, grid1((i64)T2 * B * c.E), dim3(256), 0, h->conv_out, (i64)T2 * B, c.E, c.E,
+           c.conv_act, dpc);
+  const float* inp = h->conv_out;
+  int ld_in = c.E;
+  for (int l = 0; l < c.n_enc_layers; ++l) {
+    EncLayer& L = h->enc[l];
+    bool drop = train && c.rnn_dropout > 0.f && l + 1 < c.n_enc_layers;
+    DropP dp = make_drop(seed, E2T_STREAM_ENC0 + l, drop ? c.rnn_dropout : 0.f);
+    for (int d = 0; d < 2; ++d)
+      lstm_layer_forward(h, inp, ld_in, L.In, L.H, L.KT[d], L.ldkt, Wc + L.b[d], L.gates[d], L.cs[d], L.hs,
+                         drop ? L.hd : nullptr, 2 * L.H, d * L.H, h->d_lens2, T2, B, d == 1, nullptr, nullptr, dp,
+                         2 * L.H);
+    inp = drop ? L.hd : L.hs;
+    ld_in = 2 * L.H;
+  }
+  EncLayer& top = h->enc.back();
+  LAUNCH(h, k_gather_final, grid1((i64)B * 2 * top.H), dim3(256), 0, top.hs, top.cs[0], top.cs[1], h->d_lens2,
+         h->h0, h->c0, B, top.H);
+  h->last_B = B; h->last_T2 = T2; h->last_subnet = subnet;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoder forward, teacher forced (A8-A9)
+// ------------------------------------------------------------------------------------------------
+void decoder_forward(e2t_handle* h, const Inputs& in, int B, int L, bool train, uint32_t seed, bool with_grad) {
+  const e2t_config& c = h->cfg;
+  const float* Wc = h->Wc;
+  const i64 rows = (i64)L * B;
+  LAUNCH(h, k_shift_targets, grid1(rows), dim3(256), 0, in.y, h->d_prev, h->d_tgt, B, L, c.start_id, c.V);
+  DropP dpe = make_drop(seed, E2T_STREAM_DEMB, train ? c.ff_dropout : 0.f);
+  LAUNCH(h, k_embed_fwd, grid1(rows * c.D), dim3(256), 0, h->d_prev, Wc + h->demb_w, Wc + h->demb_b, h->demb, rows,
+         c.D, h->Dp, c.emb_act, dpe);
+  DropP none = make_drop(0, 0, 0.f);
+  lstm_layer_forward(h, h->demb, h->Dp, c.D, c.Hd, h->dec_KT, h->ld_dec_kt, Wc + h->dec_b, h->dgates, h->dcs, h->hdec, nullptr,
+                     c.Hd, 0, nullptr, L, B, false, h->h0, h->c0, none, 0);
+  // logits = hdec Wp^T + b ; Wp canonical [V,Hd] is already the K-major B operand
+  gemm(h, h->hdec, c.Hd, 1, Wc + h->proj_w, 1, c.Hd, h->logits, h->Vp, (int)rows, c.V, c.Hd, Wc + h->proj_b, 0.f);
+  LAUNCH(h, k_softmax_ce, dim3((unsigned)rows), dim3(128), 0, h->logits, h->Vp, c.V, h->d_tgt, c.pad_id,
+         c.penalty_scale, h->loss_rows, with_grad ? 1 : 0);
+  LAUNCH(h, k_reduce_loss, dim3(1), dim3(256), 0, h->loss_rows, h->d_tgt, c.pad_id, (int)rows, h->d_loss, h->d_ntok);
+  h->last_L = L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward (A10)
+// ------------------------------------------------------------------------------------------------
+// BPTT through one LSTM direction whose forward was produced by lstm_layer_forward.
+// On exit gates holds dz for every step; returns nothing (dh_rec/dc_rec hold the grads wrt the initial state).
+void lstm_layer_backward(e2t_handle* h, int H, const float* K, int In, float* gates, const float* cs, const float* dhs,
+                         int ldh, int col0, const int* lens2, int steps, int B, bool reverse, const float* c_init,
+                         const float* dc_inject, int ldi, const int* inject_t, int inject_const) {
+  const float* Wh = K + (i64)In * 4 * H;  // canonical rows [H, 4H] = K-major B operand of dz Wh^T
+  E2T_CHECK(cudaMemsetAsync(h->dc_rec, 0, (size_t)B * H * sizeof(float), h->stream));
+  for (int s = steps - 1; s >= 0; --s) {
+    int t = reverse ? steps - 1 - s : s;
+    int tn = reverse ? t - 1 : t + 1;   // the step processed after t in the forward pass
+    int tp = reverse ? t + 1 : t - 1;   // the step processed before t
+    bool have_rec = s != steps - 1;
+    if (have_rec)
+      gemm(h, gates + (i64)tn * B * 4 * H, 4 * H, 1, Wh, 1, 4 * H, h->dh_rec, H, B, H, 4 * H, nullptr, 0.f);
+    LstmBwdP p{};
+    p.gz = gates + (i64)t * B * 4 * H;
+    p.c_t = cs + (i64)t * B * H;
+    p.c_prev = s == 0 ? c_init : cs + (i64)tp * B * H;
+    p.dh_out = dhs ? dhs + (i64)t * B * ldh + col0 : nullptr;
+    p.ldh = ldh;
+    p.dh_rec = have_rec ? h->dh_rec : nullptr;
+    p.dc_rec = h->dc_rec;
+    p.dc_inject = dc_inject; p.ldi = ldi; p.inject_t = inject_t; p.inject_const = inject_const;
+    p.lens2 = lens2; p.t = t; p.B = B; p.H = H;
+    LAUNCH(h, k_lstm_bwd, grid1((i64)B * H), dim3(256), 0, p);
+  }
+}
+
+// weight / bias / input gradients of one LSTM direction after its dz is known.
+void lstm_layer_wgrads(e2t_handle* h, const float* in, int ld_in, int In, int H, const float* K, float* dK, float* db,
+                       const float* dz, const float* hs, int ldh, int col0, int steps, int B, bool reverse,
+                       const float* h_init, float* d_in, int ld_din, float beta_din) {
+  const i64 rows = (i64)steps * B;
+  // dWx [In,4H] = in^T dz
+  gemm(h, in, 1, ld_in, dz, 4 * H, 1, dK, 4 * H, In, 4 * H, (int)rows, nullptr, 0.f);
+  // dWh [H,4H] = hprev^T dz : forward direction pairs hs[t-1] with dz[t]; backward pairs hs[t+1] with dz[t]
+  float* dWh = dK + (i64)In * 4 * H;
+  if (steps > 1) {
+    const float* hp = reverse ? hs + (i64)B * ldh + col0 : hs + col0;
+    const float* dzp = reverse ? dz : dz + (i64)B * 4 * H;
+    gemm(h, hp, 1, ldh, dzp, 4 * H, 1, dWh, 4 * H, H, 4 * H, (int)((i64)(steps - 1) * B), nullptr, 0.f);
+  } else {
+    E2T_CHECK(cudaMemsetAsync(dWh, 0, (size_t)H * 4 * H * sizeof(float), h->stream));
+  }
+  if (h_init) {  // decoder: first step's previous state is the bridge state
+    const float* dz0 = reverse ? dz + (i64)(steps - 1) * B * 4 * H : dz;
+    gemm(h, h_init, 1, H, dz0, 4 * H, 1, dWh, 4 * H, H, 4 * H, B, nullptr, 1.f);
+  }
+  LAUNCH(h, k_colsum, dim3((unsigned)cdiv(4 * H, 32)), dim3(256), 0, dz, rows, 4 * H, 4 * H, db, 0);
+  // d_in [rows, In] (+)= dz Wx^T ; canonical K rows [In,4H] are the K-major B operand
+  if (d_in) gemm(h, dz, 4 * H, 1, K, 1, 4 * H, d_in, ld_din, (int)rows, In, 4 * H, nullptr, beta_din);
+}
+
+void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, uint32_t seed) {
+  const e2t_config& c = h->cfg;
+  const float* P = h->P;
+  float* G = h->G;
+  const int C = c.subnet_C[subnet], W = c.subnet_W[subnet];
+  const int T2 = (int)cdiv(T, W);
+  const i64 rows = (i64)L * B;
+  E2T_CHECK(cudaMemsetAsync(G, 0, (size_t)h->n_params * sizeof(float), h->stream));
+  // ---- projection: logits already hold dlogits
+  gemm(h, h->logits, 1, h->Vp, h->hdec, c.Hd, 1, G + h->proj_w, c.Hd, c.V, c.Hd, (int)rows, nullptr, 0.f);
+  LAUNCH(h, k_colsum, dim3((unsigned)cdiv(c.V, 32)), dim3(256), 0, h->logits, rows, c.V, h->Vp, G + h->proj_b, 0);
+  // dhdec [rows,Hd] = dlogits Wp ; B operand (k=v, n=u) = Wp[v*Hd+u] -> packed transpose is the K-major form
+  gemm(h, h->logits, h->Vp, 1, h->proj_wT, 1, h->Vp, h->dhdec, c.Hd, (int)rows, c.Hd, c.V, nullptr, 0.f);
+  // ---- decoder recurrence
+  lstm_layer_backward(h, c.Hd, P + h->dec_K, c.D, h->dgates, h->dcs, h->dhdec, c.Hd, 0, nullptr, L, B, false, h->c0,
+                      nullptr, 0, nullptr, -1);
+  // grads wrt the bridge state: dh0 = dz[0] Wh^T, dc0 = dc_rec
+  gemm(h, h->dgates, 4 * c.Hd, 1, P + h->dec_K + (i64)c.D * 4 * c.Hd, 1, 4 * c.Hd, h->dh0, c.Hd, B, c.Hd, 4 * c.Hd,
+       nullptr, 0.f);
+  E2T_CHECK(cudaMemcpyAsync(h->dc0, h->dc_rec, (size_t)B * c.Hd * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  lstm_layer_wgrads(h, h->demb, h->Dp, c.D, c.Hd, P + h->dec_K, G + h->dec_K, G + h->dec_b, h->dgates, h->hdec, c.Hd, 0,
+                    L, B, false, h->h0, h->ddemb, h->Dp, 0.f);
+  // ---- decoder embedding
+  DropP dpe = make_drop(seed, E2T_STREAM_DEMB, c.ff_dropout);
+  LAUNCH(h, k_act_dropout_bwd, grid1(rows * c.D), dim3(256), 0, h->ddemb, h->demb, rows, c.D, h->Dp, c.emb_act, dpe);
+  LAUNCH(h, k_embed_bwd, grid1(rows * c.D), dim3(256), 0, h->d_prev, h->ddemb, G + h->demb_w, rows, c.D, h->Dp);
+  LAUNCH(h, k_colsum, dim3((unsigned)cdiv(c.D, 32)), dim3(256), 0, h->ddemb, rows, c.D, h->Dp, G + h->demb_b, 0);
+  // ---- encoder, top layer first
+  const int nl = c.n_enc_layers;
+  for (int l = nl - 1; l >= 0; --l) {
+    EncLayer& Ly = h->enc[l];
+    const i64 n_out = (i64)T2 * B * 2 * Ly.H;
+    if (l == nl - 1) {
+      E2T_CHECK(cudaMemsetAsync(Ly.dhs, 0, (size_t)n_out * sizeof(float), h->stream));
+      LAUNCH(h, k_scatter_final, grid1((i64)B * 2 * Ly.H), dim3(256), 0, Ly.dhs, h->dh0, h->d_lens2, B, Ly.H);
+    } else if (c.rnn_dropout > 0.f) {
+      DropP dp = make_drop(seed, E2T_STREAM_ENC0 + l, c.rnn_dropout);
+      LAUNCH(h, k_dropout_bwd, grid1(n_out), dim3(256), 0, Ly.dhs, n_out, dp);
+    }
+    const float* inp; int ld_in; float* d_in; int ld_din;
+    if (l == 0) { inp = h->conv_out; ld_in = c.E; d_in = h->dconv; ld_din = c.E; }
+    else {
+      EncLayer& Lb = h->enc[l - 1];
+      inp = (c.rnn_dropout > 0.f) ? Lb.hd : Lb.hs; ld_in = 2 * Lb.H; d_in = Lb.dhs; ld_din = 2 * Lb.H;
+    }
+    for (int d = 0; d < 2; ++d) {
+      bool top = l == nl - 1;
+      lstm_layer_backward(h, Ly.H, P + Ly.K[d], Ly.In, Ly.gates[d], Ly.cs[d], Ly.dhs, 2 * Ly.H, d * Ly.H, h->d_lens2,
+                          T2, B, d == 1, nullptr, top ? h->dc0 + d * Ly.H : nullptr, c.Hd,
+                          (top && d == 0) ? h->d_tlast : nullptr, 0);
+      lstm_layer_wgrads(h, inp, ld_in, Ly.In, Ly.H, P + Ly.K[d], G + Ly.K[d], G + Ly.b[d], Ly.gates[d], Ly.hs, 2 * Ly.H,
+                        d * Ly.H, T2, B, d == 1, nullptr, d_in, ld_din, d == 0 ? 0.f : 1.f);
+    }
+  }
+  // ---- temporal conv
+  DropP dpc = make_drop(seed, E2T_STREAM_CONV, c.ff_dropout);
+  LAUNCH(h, k_act_dropout_bwd, grid1((i64)T2 * B * c.E), dim3(256), 0, h->dconv, h->conv_out, (i64)T2 * B, c.E, c.E,
+         c.conv_act, dpc);
+  gemm_conv(h, 2, in.x, h->d_lens, B, T, C, W, T2, h->dconv, c.E, 1, G + h->conv_w[subnet], c.E, c.E, nullptr, 0.f);
+  LAUNCH(h, k_colsum, dim3((unsigned)cdiv(c.E, 32)), dim3(256), 0, h->dconv, (i64)T2 * B, c.E, c.E,
+         G + h->conv_b[subnet], 0);
+}
+
+void read_loss(e2t_handle* h, float* loss_sum, int32_t* ntok) {
+  if (!loss_sum && !ntok) return;
+  float l = 0.f; int n = 0;
+  E2T_CHECK(cudaMemcpyAsync(&l, h->d_loss, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  E2T_CHECK(cudaMemcpyAsync(&n, h->d_ntok, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  E2T_CHECK(cudaStreamSynchronize(h->stream));
+  if (loss_sum) *loss_sum = l;
+  if (ntok) *ntok = n;
+}
+
+// one decoder step for `rows` state rows (greedy: rows = B, beam: rows = B*beam)
+void decode_step(e2t_handle* h, int rows, const int* prev, const float* h_in, const float* c_in, float* h_out,
+                 float* c_out) {
+  const e2t_config& c = h->cfg;
+  const float* Wc = h->Wc;
+  DropP none = make_drop(0, 0, 0.f);
+  LAUNCH(h, k_embed_fwd, grid1((i64)rows * c.D), dim3(256), 0, prev, Wc + h->demb_w, Wc + h->demb_b, h->g_e, (i64)rows,
+         c.D, h->Dp, c.emb_act, none);
+  const float* KT = h->dec_KT;
+  gemm(h, h->g_e, h->Dp, 1, KT, 1, h->ld_dec_kt, h->g_z, 4 * c.Hd, rows, 4 * c.Hd, c.D, Wc + h->dec_b, 0.f);
+  gemm(h, h_in, c.Hd, 1, KT + c.D, 1, h->ld_dec_kt, h->g_z, 4 * c.Hd, rows, 4 * c.Hd, c.Hd, nullptr, 1.f);
+  LstmFwdP p{};
+  p.z = h->g_z; p.c_prev = c_in; p.c_out = c_out; p.h_out = h_out; p.h_drop = nullptr; p.ldh = c.Hd;
+  p.lens2 = nullptr; p.t = 0; p.B = rows; p.H = c.Hd; p.dp = none;
+  LAUNCH(h, k_lstm_fwd, grid1((i64)rows * c.Hd), dim3(256), 0, p);
+  gemm(h, h_out, c.Hd, 1, Wc + h->proj_w, 1, c.Hd, h->g_logits, h->Vp, rows, c.V, c.Hd, Wc + h->proj_b, 0.f);
+}
+
+TensorInfo& find_tensor(e2t_handle* h, const char* name) {
+  E2T_REQUIRE(name != nullptr, "tensor name is NULL");
+  auto it = h->by_name.find(name);
+  if (it == h->by_name.end()) throw std::runtime_error(std::string("e2t: no tensor named '") + name + "'");
+  return h->tensors[it->second];
+}
+float* flat_of(e2t_handle* h, int which) {
+  switch (which) {
+    case E2T_VALUE: return h->P;
+    case E2T_GRAD: return h->G;
+    case E2T_ADAM_M: return h->M;
+    case E2T_ADAM_V: return h->Vv;
+    case E2T_EMA: return h->S;
+  }
+  throw std::runtime_error("e2t: bad `which`");
+}
+
+}  // namespace
+
+#define API_BEGIN try {
+#define API_END                                   \
+  return 0;                                       \
+  }                                               \
+  catch (const std::exception& e) {               \
+    g_err = e.what();                             \
+    return -1;                                    \
+  }                                               \
+  catch (...) {                                   \
+    g_err = "e2t: unknown error";                 \
+    return -1;                                    \
+  }
+#define NEED_H E2T_REQUIRE(h != nullptr, "handle is NULL")
+
+extern "C" int e2t_create(const e2t_config* cfg, e2t_handle** out) {
+  e2t_handle* h = nullptr;
+  try {
+    E2T_REQUIRE(cfg && out, "NULL argument");
+    validate(*cfg);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+      throw std::runtime_error("e2t: no CUDA device available -- this library has no CPU fallback");
+    E2T_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "device ordinal out of range");
+    E2T_CHECK(cudaSetDevice(cfg->device));
+    h = new e2t_handle();
+    h->cfg = *cfg;
+    E2T_CHECK(cudaStreamCreate(&h->own_stream));
+    h->stream = h->own_stream;
+    build_params(h);
+    build_workspace(h);
+    h->Wc = h->P;
+    E2T_CHECK(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    if (h) e2t_destroy(h);
+    return -1;
+  }
+}
+
+extern "C" int e2t_destroy(e2t_handle* h) {
+  if (!h) return 0;
+  cudaDeviceSynchronize();
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return 0;
+}
+
+extern "C" int e2t_set_stream(e2t_handle* h, void* s) {
+  API_BEGIN NEED_H;
+  E2T_CHECK(cudaStreamSynchronize(h->stream));
+  h->stream = s ? static_cast<cudaStream_t>(s) : h->own_stream;
+  API_END
+}
+extern "C" int e2t_sync(e2t_handle* h) {
+  API_BEGIN NEED_H;
+  E2T_CHECK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+extern "C" int e2t_param_count(e2t_handle* h) { return h ? (int)h->tensors.size() : -1; }
+extern "C" int64_t e2t_param_total(e2t_handle* h) { return h ? (int64_t)h->n_params : -1; }
+
+extern "C" int e2t_param_info(e2t_handle* h, int index, char* name, int name_cap, int64_t* shape, int* ndim,
+                              int64_t* offset) {
+  API_BEGIN NEED_H;
+  E2T_REQUIRE(index >= 0 && index < (int)h->tensors.size(), "tensor index out of range");
+  const TensorInfo& t = h->tensors[index];
+  if (name && name_cap > 0) { strncpy(name, t.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (shape) for (size_t i = 0; i < t.shape.size(); ++i) shape[i] = t.shape[i];
+  if (ndim) *ndim = (int)t.shape.size();
+  if (offset) *offset = t.off;
+  API_END
+}
+
+extern "C" int e2t_get_tensor(e2t_handle* h, const char* name, int which, float* host_out) {
+  API_BEGIN NEED_H;
+  E2T_REQUIRE(host_out, "host_out is NULL");
+  TensorInfo& t = find_tensor(h, name);
+  E2T_CHECK(cudaStreamSynchronize(h->stream));
+  E2T_CHECK(cudaMemcpy(host_out, flat_of(h, which) + t.off, (size_t)t.n * sizeof(float), cudaMemcpyDeviceToHost));
+  API_END
+}
+
+extern "C" int e2t_set_tensor(e2t_handle* h, const char* name, int which, const float* host_in) {
+  API_BEGIN NEED_H;
+  E2T_REQUIRE(host_in, "host_in is NULL");
+  TensorInfo& t = find_tensor(h, name);
+  E2T_CHECK(cudaStreamSynchronize(h->stream));
+  E2T_CHECK(cudaMemcpy(flat_of(h, which) + t.off, host_in, (size_t)t.n * sizeof(float), cudaMemcpyHostToDevice));
+  if (which == E2T_VALUE)  // a fresh variable value also (re)initialises its EMA shadow, as TF does
+    E2T_CHECK(cudaMemcpy(h->S + t.off, host_in, (size_t)t.n * sizeof(float), cudaMemcpyHostToDevice));
+  if (which == E2T_VALUE || which == E2T_EMA) h->packed_dirty = true;
+  API_END
+}
+
+extern "C" int e2t_flat_buffer(e2t_handle* h, int which, void** dev_ptr, int64_t* n) {
+  API_BEGIN NEED_H;
+  if (dev_ptr) *dev_ptr = flat_of(h, which);
+  if (n) *n = h->n_params;
+  API_END
+}
+
+extern "C" int e2t_set_trainable(e2t_handle* h, const char* name, int trainable) {
+  API_BEGIN NEED_H;
+  find_tensor(h, name).trainable = trainable != 0;
+  API_END
+}
+extern "C" int e2t_get_step(e2t_handle* h, int64_t* step) { API_BEGIN NEED_H; if (step) *step = h->step; API_END }
+extern "C" int e2t_set_step(e2t_handle* h, int64_t step) { API_BEGIN NEED_H; h->step = step; API_END }
+
+extern "C" int e2t_train_step_grads(e2t_handle* h, int subnet, const float* x, const int32_t* lens, const int32_t* y,
+                                    int loc, int B, int T, int L, uint32_t dropout_seed, float* loss_sum,
+                                    int32_t* ntok) {
+  API_BEGIN NEED_H;
+  E2T_REQUIRE(y != nullptr && L >= 1, "training needs targets");
+  Inputs in = stage(h, subnet, x, lens, y, loc, B, T, L);
+  use_weights(h, false);
+  encoder_forward(h, subnet, in, B, T, true, dropout_seed);
+  decoder_forward(h, in, B, L, true, dropout_seed, true);
+  backward(h, subnet, in, B, T, L, dropout_seed);
+  E2T_CHECK(cudaGetLastError());
+  read_loss(h, loss_sum, ntok);
+  API_END
+}
+
+extern "C" int e2t_adam_ema_step(e2t_handle* h, int subnet, float grad_scale) {
+  API_BEGIN NEED_H;
+  const e2t_config& c = h->cfg;
+  h->step += 1;
+  double t = (double)h->step;
+  float lr_t = (float)(c.lr * std::sqrt(1.0 - std::pow((double)c.beta2, t)) / (1.0 - std::pow((double)c.beta1, t)));
+  // merge adjacent selected tensors into ranges
+  i64 start = -1, end = -1;
+  auto flush = [&]() {
+    if (start < 0) return;
+    i64 n = end - start;
+    LAUNCH(h, k_adam_ema, grid1(n), dim3(256), 0, h->P + start, h->G + start, h->M + start, h->Vv + start,
+           h->S + start, n, grad_scale, lr_t, c.beta1, c.beta2, c.eps, c.ema_decay);
+    start = -1;
+  };
+  for (const TensorInfo& ti : h->tensors) {
+    bool sel = ti.trainable && (ti.subnet < 0 || subnet < 0 || ti.subnet == subnet);
+    i64 padded = (ti.n + 3) / 4 * 4;
+    if (sel) {
+      if (start >= 0 && end == ti.off) end = ti.off + padded;
+      else { flush(); start = ti.off; end = ti.off + padded; }
+    } else flush();
+  }
+  flush();
+  h->packed_dirty = true;
+  E2T_CHECK(cudaGetLastError());
+  API_END
+}
+
+extern "C" int e2t_eval_loss(e2t_handle* h, int subnet, const float* x, const int32_t* lens, const int32_t* y, int loc,
+                             int B, int T, int L, int use_ema, float* loss_sum, int32_t* ntok) {
+  API_BEGIN NEED_H;
+  E2T_REQUIRE(y != nullptr && L >= 1, "eval_loss needs targets");
+  Inputs in = stage(h, subnet, x, lens, y, loc, B, T, L);
+  use_weights(h, use_ema != 0);
+  encoder_forward(h, subnet, in, B, T, false, 0);
+  decoder_forward(h, in, B, L, false, 0, false);
+  E2T_CHECK(cudaGetLastError());
+  read_loss(h, loss_sum, ntok);
+  API_END
+}
+
+extern "C" int e2t_greedy_decode(e2t_handle* h, int subnet, const float* x, const int32_t* lens, int loc, int B, int T,
+                                 int max_len, int use_ema, float temperature, int32_t* tokens, float* logp) {
+  API_BEGIN NEED_H;
+  const e2t_config& c = h->cfg;
+  E2T_REQUIRE(max_len >= 1 && max_len <= h->Lm, "max_len exceeds max_L");
+  E2T_REQUIRE(tokens != nullptr, "tokens is NULL");
+  E2T_REQUIRE(temperature > 0.f, "temperature must be positive");
+  Inputs in = stage(h, subnet, x, lens, nullptr, loc, B, T, 0);
+  use_weights(h, use_ema != 0);
+  encoder_forward(h, subnet, in, B, T, false, 0);
+  LAUNCH(h, k_fill_int, grid1(B), dim3(256), 0, h->g_prev[0], c.start_id, (i64)B);
+  E2T_CHECK(cudaMemsetAsync(h->g_done[0], 0, (size_t)B * sizeof(int), h->stream));
+  const float* hin = h->h0; const float* cin = h->c0;
+  for (int k = 0; k < max_len; ++k) {
+    float* ho = h->g_h[k & 1]; float* co = h->g_c[k & 1];
+    decode_step(h, B, h->g_prev[0], hin, cin, ho, co);
+    LAUNCH(h, k_greedy_pick, dim3(B), dim3(128), 0, h->g_logits, h->Vp, c.V, 1.0f / temperature, k, max_len, c.pad_id,
+           c.eos_id, h->g_prev[0], h->g_done[0], h->g_tokens[0], h->g_logp);
+    hin = ho; cin = co;
+  }
+  E2T_CHECK(cudaGetLastError());
+  E2T_CHECK(cudaMemcpyAsync(tokens, h->g_tokens[0], (size_t)B * max_len * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (logp)
+    E2T_CHECK(cudaMemcpyAsync(logp, h->g_logp, (size_t)B * max_len * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  E2T_CHECK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+extern "C" int e2t_beam_decode(e2t_handle* h, int subnet, const float* x, const int32_t* lens, int loc, int B, int T,
+                               int beam, int max_len, int use_ema, float temperature, int32_t* tokens, float* scores) {
+  API_BEGIN NEED_H;
+  const e2t_config& c = h->cfg;
+  E2T_REQUIRE(beam >= 1 && beam <= h->beam_m, "beam exceeds max_beam");
+  E2T_REQUIRE(beam <= c.V, "beam wider than the vocabulary");
+  E2T_REQUIRE(max_len >= 1 && max_len <= h->Lm, "max_len exceeds max_L");
+  E2T_REQUIRE(tokens != nullptr, "tokens is NULL");
+  E2T_REQUIRE(temperature > 0.f, "temperature must be positive");
+  Inputs in = stage(h, subnet, x, lens, nullptr, loc, B, T, 0);
+  use_weights(h, use_ema != 0);
+  encoder_forward(h, subnet, in, B, T, false, 0);
+  const int R = B * beam;
+  // state buffers: cur (index a) holds the live beams; decode_step writes the candidates into slot 2 = g_z-adjacent
+  // we use g_h[0]/g_c[0] as current, g_h[1]/g_c[1] as new, and reorder back into [0] through a temporary swap.
+  LAUNCH(h, k_beam_init, grid1((i64)R * c.Hd), dim3(256), 0, h->h0, h->c0, h->g_h[0], h->g_c[0], h->g_score[0], B, beam,
+         c.Hd);
+  LAUNCH(h, k_fill_int, grid1(R), dim3(256), 0, h->g_prev[0], c.start_id, (i64)R);
+  E2T_CHECK(cudaMemsetAsync(h->g_done[0], 0, (size_t)R * sizeof(int), h->stream));
+  LAUNCH(h, k_fill_int, grid1((i64)R * max_len), dim3(256), 0, h->g_tokens[0], c.pad_id, (i64)R * max_len);
+  // a third state buffer for the reordered result (reuse dh0/dc0-sized scratch is too small -> use hdec/dhdec heads)
+  E2T_REQUIRE((i64)R * c.Hd <= (i64)h->Lm * h->Bm * c.Hd, "beam workspace too small (max_L*max_B < B*beam)");
+  float* h_re = h->hdec; float* c_re = h->dhdec;
+  int cur = 0;
+  for (int k = 0; k < max_len; ++k) {
+    int nxt = cur ^ 1;
+    decode_step(h, R, h->g_prev[cur], h->g_h[cur], h->g_c[cur], h->g_h[nxt], h->g_c[nxt]);
+    LAUNCH(h, k_beam_topk, dim3(B), dim3(256), 0, h->g_logits, h->Vp, c.V, 1.0f / temperature, beam, h->g_score[cur],
+           h->g_done[cur], c.pad_id, h->g_lse, h->g_score[nxt], h->g_src, h->g_tok);
+    BeamStepP p{};
+    p.h_new = h->g_h[nxt]; p.c_new = h->g_c[nxt]; p.h_old = h->g_h[cur]; p.c_old = h->g_c[cur];
+    p.h_out = h_re; p.c_out = c_re; p.Hd = c.Hd;
+    p.src = h->g_src; p.tok = h->g_tok; p.done_in = h->g_done[cur]; p.prev_in = h->g_prev[cur];
+    p.done_out = h->g_done[nxt]; p.prev_out = h->g_prev[nxt];
+    p.toks_in = h->g_tokens[cur]; p.toks_out = h->g_tokens[nxt];
+    p.beam = beam; p.k = k; p.max_len = max_len; p.pad_id = c.pad_id; p.eos_id = c.eos_id; p.rows = R;
+    LAUNCH(h, k_beam_reorder, grid1((i64)R * c.Hd), dim3(256), 0, p);
+    E2T_CHECK(cudaMemcpyAsync(h->g_h[nxt], h_re, (size_t)R * c.Hd * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    E2T_CHECK(cudaMemcpyAsync(h->g_c[nxt], c_re, (size_t)R * c.Hd * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    cur = nxt;
+  }
+  E2T_CHECK(cudaGetLastError());
+  E2T_CHECK(cudaMemcpyAsync(tokens, h->g_tokens[cur], (size_t)R * max_len * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (scores)
+    E2T_CHECK(cudaMemcpyAsync(scores, h->g_score[cur], (size_t)R * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  E2T_CHECK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+extern "C" int e2t_get_activation(e2t_handle* h, const char* name, void* host_out, int64_t n_cap, int64_t* n_out) {
+  API_BEGIN NEED_H;
+  E2T_REQUIRE(name && host_out, "NULL argument");
+  const e2t_config& c = h->cfg;
+  const i64 B = h->last_B, T2 = h->last_T2, L = h->last_L;
+  const void* src = nullptr; i64 n = 0; size_t esz = 4;
+  std::string s(name);
+  if (s == "lens") { src = h->d_lens; n = B; }
+  else if (s == "lens2") { src = h->d_lens2; n = B; }
+  else if (s == "conv_out") { src = h->conv_out; n = T2 * B * c.E; }
+  else if (s == "final_h") { src = h->h0; n = B * c.Hd; }
+  else if (s == "final_c") { src = h->c0; n = B * c.Hd; }
+  else if (s == "logits") {
+    // stored with leading dim Vp: copy row by row
+    n = L * B * c.V;
+    E2T_REQUIRE(n <= n_cap, "host buffer too small");
+    E2T_CHECK(cudaStreamSynchronize(h->stream));
+    for (i64 r = 0; r < L * B; ++r)
+      E2T_CHECK(cudaMemcpy((float*)host_out + r * c.V, h->logits + r * h->Vp, (size_t)c.V * 4, cudaMemcpyDeviceToHost));
+    if (n_out) *n_out = n;
+    return 0;
+  } else if (s.rfind("enc", 0) == 0 && s.size() >= 8 && s.substr(s.size() - 4) == "_out") {
+    int l = atoi(s.c_str() + 3);
+    E2T_REQUIRE(l >= 0 && l < c.n_enc_layers, "encoder layer out of range");
+    src = h->enc[l].hs; n = T2 * B * 2 * h->enc[l].H;
+  } else throw std::runtime_error("e2t: unknown activation '" + s + "'");
+  E2T_REQUIRE(n <= n_cap, "host buffer too small");
+  E2T_CHECK(cudaStreamSynchronize(h->stream));
+  E2T_CHECK(cudaMemcpy(host_out, src, (size_t)n * esz, cudaMemcpyDeviceToHost));
+  if (n_out) *n_out = n;
+  API_END
+}
+
+extern "C" int e2t_launch_counts(e2t_handle* h, int64_t* total, int64_t* tensor_core) {
+  API_BEGIN NEED_H;
+  if (total) *total = h->n_launch;
+  if (tensor_core) *tensor_core = h->n_launch_tc;
+  API_END
+}
+
+extern "C" int e2t_selftest_gemm(e2t_handle* h, int M, int N, int K, float* max_abs_diff) {
+  API_BEGIN NEED_H;
+#ifdef E2T_EMU
+  (void)M; (void)N; (void)K; (void)max_abs_diff;
+  throw std::runtime_error("e2t: tcgen05 self-test is not available in the emulation build");
+#else
+  float d = tc_gemm_selftest(h->stream, M, N, K);
+  if (max_abs_diff) *max_abs_diff = d;
+#endif
+  API_END
+}

@@ -1,0 +1,576 @@
+// kernels_simt.cuh -- fp32 CUDA-core kernels of the seq2seq hot path (every op of SURVEY.md §8a).
+// These are the validation / small-shape path; the tcgen05 kernels in gemm_tc.cuh replace the GEMMs
+// and the recurrence at production shapes.  Written against the CUDA subset that tests/emu can run.
+#pragma once
+#include "common.cuh"
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide reductions for blockDim.x == 128 or 256 (multiple of 32, <= 1024); `red` = 32 floats smem
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int i = 0; i < nw; ++i) r += red[i];
+  return r;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < nw; ++i) r = fmaxf(r, red[i]);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A2: lengths.  One warp per utterance; scans frames from the tail for the last non-zero frame
+// (nn.sequences_tools, trainers.py:806-807) unless lens_in is given; lens2 = ceil(len/W).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_lengths(const float* __restrict__ x, const int* __restrict__ lens_in, int* lens,
+                          int* lens2, int* tlast, int B, int T, int C, int W) {
+  int b = blockIdx.x;
+  int lane = threadIdx.x;
+  int len = 0;
+  if (lens_in) {
+    len = lens_in[b];
+    len = len < 0 ? 0 : (len > T ? T : len);
+  } else {
+    for (int t = T - 1; t >= 0; --t) {
+      const float* row = x + ((i64)b * T + t) * C;
+      int any = 0;
+      for (int c = lane; c < C; c += 32) any |= (row[c] != 0.0f);
+      for (int o = 16; o > 0; o >>= 1) any |= __shfl_xor_sync(0xffffffffu, any, o);
+      if (any) { len = t + 1; break; }
+    }
+  }
+  if (lane == 0) {
+    lens[b] = len;
+    int l2 = (len + W - 1) / W;
+    lens2[b] = l2;
+    tlast[b] = l2 - 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic strided fp32 GEMM  C[m,n] = sum_k A(m,k) B(k,n) (+bias[n]) (+beta*C)
+//   A(m,k) = A[m*sam + k*sak]   B(k,n) = B[k*sbk + n*sbn]
+// CONV=1: A(m,k) gathers the reversed, zero-padded ECoG window (A3+A4 fused): row m = t2*Bsz+b,
+//         k = w*C+c  ->  x[b, len_b-1-(t2*W+w), c]   (tf.reverse_sequence + stride-W conv)
+// CONV=2: the transpose of that gather (m = w*C+c, k = t2*Bsz+b), for dW_conv = A^T dY.
+// 64x64x16 tiles, 256 threads, 4x4 register micro-tile.
+// ------------------------------------------------------------------------------------------------
+struct GemmP {
+  const float* A; i64 sam, sak;
+  const float* B; i64 sbk, sbn;
+  float* C; i64 ldc;
+  int M, N, K;
+  const float* bias; float beta;
+  const float* x; const int* lens; int Bsz, T, Cch, Wd;
+};
+
+template <int CONV>
+__device__ __forceinline__ float gemm_load_a(const GemmP& p, int m, int k) {
+  if (CONV == 0) return p.A[(i64)m * p.sam + (i64)k * p.sak];
+  int row = CONV == 1 ? m : k, col = CONV == 1 ? k : m;
+  int t2 = row / p.Bsz, b = row - t2 * p.Bsz;
+  int w = col / p.Cch, c = col - w * p.Cch;
+  int s = t2 * p.Wd + w, len = p.lens[b];
+  if (s >= len) return 0.0f;
+  return p.x[((i64)b * p.T + (len - 1 - s)) * p.Cch + c];
+}
+
+template <int CONV>
+__global__ void __launch_bounds__(256) k_gemm(GemmP p) {
+  __shared__ float As[16][65];
+  __shared__ float Bs[16][65];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const bool a_kfast = (CONV == 1) || (CONV == 0 && p.sak == 1);
+  const bool b_nfast = p.sbn == 1;
+  for (int k0 = 0; k0 < p.K; k0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = tid + i * 256;
+      int kk, mm;
+      if (a_kfast) { kk = e & 15; mm = e >> 4; } else { mm = e & 63; kk = e >> 6; }
+      int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < p.M && k < p.K) ? gemm_load_a<CONV>(p, m, k) : 0.f;
+      int nn;
+      if (b_nfast) { nn = e & 63; kk = e >> 6; } else { kk = e & 15; nn = e >> 4; }
+      int n = n0 + nn;
+      k = k0 + kk;
+      Bs[kk][nn] = (n < p.N && k < p.K) ? p.B[(i64)k * p.sbk + (i64)n * p.sbn] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (p.bias) v += p.bias[n];
+      float* c = p.C + (i64)m * p.ldc + n;
+      if (p.beta != 0.f) v += p.beta * (*c);
+      *c = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// activation + dropout over X[rows, F] (leading dim ld), in place.  Hash index = row*F + f.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_act_dropout(float* X, i64 rows, int F, int ld, int act, DropP dp) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * F) return;
+  i64 r = i / F;
+  int f = (int)(i - r * F);
+  float v = X[r * ld + f];
+  if (act == 1) v = fmaxf(v, 0.f);
+  if (dp.thresh) v = e2t_keep(dp.key, (uint32_t)i, dp.thresh) ? v * dp.inv : 0.f;
+  X[r * ld + f] = v;
+}
+// backward of the above: dX <- dX * d(out)/d(pre); `out` is the stored forward output.
+__global__ void k_act_dropout_bwd(float* dX, const float* out, i64 rows, int F, int ld, int act, DropP dp) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * F) return;
+  i64 r = i / F;
+  int f = (int)(i - r * F);
+  float g = dX[r * ld + f];
+  if (dp.thresh) g = e2t_keep(dp.key, (uint32_t)i, dp.thresh) ? g * dp.inv : 0.f;
+  if (act == 1 && !(out[r * ld + f] > 0.f)) g = 0.f;
+  dX[r * ld + f] = g;
+}
+// dropout-only backward for RNN layer outputs: dX[r, f] *= keep/(1-p)
+__global__ void k_dropout_bwd(float* dX, i64 n, DropP dp) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dX[i] = e2t_keep(dp.key, (uint32_t)i, dp.thresh) ? dX[i] * dp.inv : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A5/A8: LSTM cell, one time step (TF1 LSTMCell: gates i,j,f,o; forget_bias 1; App. D item 4).
+// z [B,4H] holds pre-activations on entry and (sig i, tanh j, sig(f+1), sig o) on exit.
+// Rows with t >= lens2[b] (dynamic_rnn past the length): output 0, cell 0, gates untouched.
+// ------------------------------------------------------------------------------------------------
+struct LstmFwdP {
+  float* z; const float* c_prev; float* c_out;
+  float* h_out; float* h_drop; int ldh;
+  const int* lens2; int t, B, H;
+  DropP dp; int drop_F, drop_col0;   // hash index = (t*B+b)*drop_F + drop_col0 + u
+};
+__global__ void k_lstm_fwd(LstmFwdP p) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.B * p.H) return;
+  int b = i / p.H, u = i - b * p.H;
+  bool valid = p.lens2 ? (p.t < p.lens2[b]) : true;
+  float* hrow = p.h_out + (i64)b * p.ldh + u;
+  if (!valid) {
+    *hrow = 0.f;
+    if (p.h_drop) p.h_drop[(i64)b * p.ldh + u] = 0.f;
+    p.c_out[i] = 0.f;
+    return;
+  }
+  float* z = p.z + (i64)b * 4 * p.H + u;
+  float gi = sigmoidf_(z[0]);
+  float gj = tanhf(z[p.H]);
+  float gf = sigmoidf_(z[2 * p.H] + 1.0f);
+  float go = sigmoidf_(z[3 * p.H]);
+  float cp = p.c_prev ? p.c_prev[i] : 0.f;
+  float c = gf * cp + gi * gj;
+  float h = go * tanhf(c);
+  z[0] = gi; z[p.H] = gj; z[2 * p.H] = gf; z[3 * p.H] = go;
+  p.c_out[i] = c;
+  *hrow = h;
+  if (p.h_drop) {
+    uint32_t idx = (uint32_t)(((i64)p.t * p.B + b) * p.drop_F + p.drop_col0 + u);
+    p.h_drop[(i64)b * p.ldh + u] = e2t_keep(p.dp.key, idx, p.dp.thresh) ? h * p.dp.inv : 0.f;
+  }
+}
+
+// Backward of one step.  gz: gate activations in, dz (d loss / d pre-activations) out.
+struct LstmBwdP {
+  float* gz; const float* c_t; const float* c_prev;
+  const float* dh_out; int ldh;        // grad wrt this step's output (nullable)
+  const float* dh_rec;                 // [B,H] grad through the recurrence (nullable)
+  float* dc_rec;                       // [B,H] in/out
+  const float* dc_inject; int ldi;     // final-state cell grad, added when t == inject_t[b] (nullable)
+  const int* inject_t; int inject_const;  // inject_t nullable -> use inject_const
+  const int* lens2; int t, B, H;
+};
+__global__ void k_lstm_bwd(LstmBwdP p) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.B * p.H) return;
+  int b = i / p.H, u = i - b * p.H;
+  float* z = p.gz + (i64)b * 4 * p.H + u;
+  bool valid = p.lens2 ? (p.t < p.lens2[b]) : true;
+  if (!valid) {
+    z[0] = 0.f; z[p.H] = 0.f; z[2 * p.H] = 0.f; z[3 * p.H] = 0.f;
+    p.dc_rec[i] = 0.f;
+    return;
+  }
+  float dh = 0.f;
+  if (p.dh_out) dh += p.dh_out[(i64)b * p.ldh + u];
+  if (p.dh_rec) dh += p.dh_rec[i];
+  float dc = p.dc_rec[i];
+  if (p.dc_inject) {
+    int ti = p.inject_t ? p.inject_t[b] : p.inject_const;
+    if (ti == p.t) dc += p.dc_inject[(i64)b * p.ldi + u];
+  }
+  float gi = z[0], gj = z[p.H], gf = z[2 * p.H], go = z[3 * p.H];
+  float c = p.c_t[i];
+  float cp = p.c_prev ? p.c_prev[i] : 0.f;
+  float tc = tanhf(c);
+  float d_o = dh * tc * go * (1.f - go);
+  dc += dh * go * (1.f - tc * tc);
+  float d_i = dc * gj * gi * (1.f - gi);
+  float d_j = dc * gi * (1.f - gj * gj);
+  float d_f = dc * cp * gf * (1.f - gf);
+  p.dc_rec[i] = dc * gf;
+  z[0] = d_i; z[p.H] = d_j; z[2 * p.H] = d_f; z[3 * p.H] = d_o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bridge (App. D item 5): decoder (c,h)_0 = concat(fwd final, bwd final) of the last encoder layer.
+// hs [T',B,2H]; c_fw, c_bw [T',B,H]; fwd final sits at t = lens2-1, bwd final at t = 0.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_gather_final(const float* hs, const float* c_fw, const float* c_bw, const int* lens2,
+                               float* h0, float* c0, int B, int H) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 2 * H) return;
+  int b = i / (2 * H), j = i - b * 2 * H;
+  int d = j >= H, u = j - d * H;
+  int l2 = lens2[b];
+  if (l2 <= 0) { h0[i] = 0.f; c0[i] = 0.f; return; }
+  int t = d ? 0 : l2 - 1;
+  h0[i] = hs[((i64)t * B + b) * 2 * H + j];
+  c0[i] = (d ? c_bw : c_fw)[((i64)t * B + b) * H + u];
+}
+// transpose of the gather for h: dhs[t_final, b, j] += dh0[b, j]  (dhs zeroed beforehand)
+__global__ void k_scatter_final(float* dhs, const float* dh0, const int* lens2, int B, int H) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 2 * H) return;
+  int b = i / (2 * H), j = i - b * 2 * H;
+  int d = j >= H;
+  int l2 = lens2[b];
+  if (l2 <= 0) return;
+  int t = d ? 0 : l2 - 1;
+  dhs[((i64)t * B + b) * 2 * H + j] += dh0[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// A8: decoder inputs.  y [B,L] -> time-major prev[k,b] (teacher forcing, start token first) and tgt[k,b]
+// ------------------------------------------------------------------------------------------------
+__global__ void k_shift_targets(const int* y, int* prev, int* tgt, int B, int L, int start_id, int V) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * L) return;
+  int k = i / B, b = i - k * B;
+  int t = y[b * L + k];
+  t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+  tgt[i] = t;
+  int pv = k == 0 ? start_id : y[b * L + k - 1];
+  prev[i] = pv < 0 ? 0 : (pv >= V ? V - 1 : pv);
+}
+// e[r, :] = dropout(act(Emb[tok[r], :] + bias)); rows r = k*B+b; out leading dim ld
+__global__ void k_embed_fwd(const int* tok, const float* emb, const float* bias, float* out, i64 rows,
+                            int D, int ld, int act, DropP dp) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * D) return;
+  i64 r = i / D;
+  int j = (int)(i - r * D);
+  float v = emb[(i64)tok[r] * D + j] + bias[j];
+  if (act == 1) v = fmaxf(v, 0.f);
+  if (dp.thresh) v = e2t_keep(dp.key, (uint32_t)i, dp.thresh) ? v * dp.inv : 0.f;
+  out[r * ld + j] = v;
+}
+// dEmb[tok[r], j] += dpre[r, j]  (dpre already passed through k_act_dropout_bwd)
+__global__ void k_embed_bwd(const int* tok, const float* dpre, float* demb, i64 rows, int D, int ld) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * D) return;
+  i64 r = i / D;
+  int j = (int)(i - r * D);
+  atomicAdd(demb + (i64)tok[r] * D + j, dpre[r * ld + j]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// A9: masked softmax cross-entropy, one block (128 threads) per row r = k*B+b of logits [rows, V].
+// loss_row[r] = scale * (lse - logit[tgt]) (0 where tgt == pad); with_grad: logits <- dlogits.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_softmax_ce(float* logits, int ld, int V, const int* tgt,
+                                                    int pad_id, float scale, float* loss_row, int with_grad) {
+  __shared__ float red[32];
+  i64 r = blockIdx.x;
+  float* row = logits + r * ld;
+  int t = tgt[r];
+  if (t == pad_id) {
+    if (with_grad)
+      for (int j = threadIdx.x; j < V; j += blockDim.x) row[j] = 0.f;
+    if (threadIdx.x == 0) loss_row[r] = 0.f;
+    return;
+  }
+  float mx = -3.0e38f;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) mx = fmaxf(mx, row[j]);
+  mx = block_max(mx, red);
+  float s = 0.f;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) s += expf(row[j] - mx);
+  s = block_sum(s, red);
+  float lse = mx + logf(s);
+  if (threadIdx.x == 0) loss_row[r] = scale * (lse - row[t]);
+  if (with_grad) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < V; j += blockDim.x) {
+      float g = expf(row[j] - lse);
+      if (j == t) g -= 1.f;
+      row[j] = scale * g;
+    }
+  }
+}
+// deterministic single-block reduction of the per-row losses and the unmasked-token count
+__global__ void __launch_bounds__(256) k_reduce_loss(const float* loss_row, const int* tgt, int pad_id, int rows,
+                                                     float* loss_out, int* ntok_out) {
+  __shared__ float red[32];
+  float s = 0.f, n = 0.f;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+    s += loss_row[i];
+    n += (tgt[i] != pad_id) ? 1.f : 0.f;
+  }
+  s = block_sum(s, red);
+  n = block_sum(n, red);
+  if (threadIdx.x == 0) { *loss_out = s; *ntok_out = (int)(n + 0.5f); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums (bias gradients): out[n] (+)= sum_m X[m*ld + n].  block = 32 columns x 8 row lanes.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_colsum(const float* X, i64 rows, int N, int ld, float* out, int accumulate) {
+  __shared__ float part[8][33];
+  int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  int n = blockIdx.x * 32 + cx;
+  float s = 0.f;
+  if (n < N)
+    for (i64 m = ry; m < rows; m += 8) s += X[m * ld + n];
+  part[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && n < N) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += part[i][cx];
+    out[n] = accumulate ? out[n] + t : t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// A10: TF1 Adam (lr_t folds the bias corrections) + ExponentialMovingAverage, fused, elementwise.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_adam_ema(float* p, const float* g, float* m, float* v, float* s, i64 n, float grad_scale,
+                           float lr_t, float b1, float b2, float eps, float ema_decay) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i] * grad_scale;
+  float mi = b1 * m[i] + (1.f - b1) * gi;
+  float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+  m[i] = mi; v[i] = vi; p[i] = pi;
+  if (ema_decay > 0.f) s[i] = ema_decay * s[i] + (1.f - ema_decay) * pi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A11 greedy: one block (128 threads) per row: argmax (lowest index on ties) + log-prob of it under
+// softmax(logits / temperature); appends to tokens[b, k]; finished rows emit pad and keep `prev`.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_greedy_pick(const float* logits, int ld, int V, float inv_temp, int k,
+                                                     int max_len, int pad_id, int eos_id, int* prev, int* done,
+                                                     int* tokens, float* logp) {
+  __shared__ float red[32];
+  __shared__ int best_idx_s;
+  int b = blockIdx.x;
+  const float* row = logits + (i64)b * ld;
+  float mx = -3.0e38f;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) mx = fmaxf(mx, row[j]);
+  mx = block_max(mx, red);
+  // lowest index attaining the max: encode as -index and take the max
+  float bi = -3.0e38f;
+  for (int j = threadIdx.x; j < V; j += blockDim.x)
+    if (row[j] == mx) bi = fmaxf(bi, -(float)j);
+  bi = block_max(bi, red);
+  float s = 0.f;
+  for (int j = threadIdx.x; j < V; j += blockDim.x) s += expf((row[j] - mx) * inv_temp);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    int best = (int)(-bi + 0.5f);
+    best_idx_s = best;
+    int was_done = done[b];
+    tokens[(i64)b * max_len + k] = was_done ? pad_id : best;
+    if (logp) logp[(i64)b * max_len + k] = was_done ? 0.f : -logf(s);  // (mx-mx)*inv_temp - log(sum)
+    if (!was_done) prev[b] = best;
+    done[b] = was_done | (best == eos_id);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tiled transpose: out[n*ldo + k] = in[k*ldi + n] for k < K, n < N  (weight re-packing)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_transpose(const float* in, i64 ldi, float* out, i64 ldo, int K, int N) {
+  __shared__ float tile[32][33];
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  for (int i = ty; i < 32; i += 8) {
+    int k = k0 + i, n = n0 + tx;
+    tile[i][tx] = (k < K && n < N) ? in[(i64)k * ldi + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    int n = n0 + i, k = k0 + tx;
+    if (n < N && k < K) out[(i64)n * ldo + k] = tile[tx][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// A11 beam search helpers (width <= 32).  State rows are r = b*beam + j.
+// k_beam_topk: one block per utterance.  For each live beam the candidates are
+//   score[j] + log_softmax(logits[r]/T)[v]; finished beams contribute only (score[j], pad).
+// Selects the `beam` best (score desc, then flat index j*V+v asc) by repeated block arg-max.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_beam_topk(const float* logits, int ld, int V, float inv_temp, int beam,
+                                                   const float* score_in, const int* done_in, int pad_id,
+                                                   float* lse_ws, float* score_out, int* src_out, int* tok_out) {
+  __shared__ float red[32];
+  __shared__ float sel_score[32];
+  __shared__ int sel_flat[32];
+  int b = blockIdx.x;
+  // log-sum-exp per beam row at temperature
+  for (int j = 0; j < beam; ++j) {
+    const float* row = logits + ((i64)b * beam + j) * ld;
+    float mx = -3.0e38f;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) mx = fmaxf(mx, row[v] * inv_temp);
+    mx = block_max(mx, red);
+    float s = 0.f;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) s += expf(row[v] * inv_temp - mx);
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) lse_ws[b * beam + j] = mx + logf(s);
+  }
+  __syncthreads();
+  for (int n = 0; n < beam; ++n) {
+    float best = -3.0e38f;
+    int best_flat = 0x7fffffff;
+    for (int j = 0; j < beam; ++j) {
+      int r = b * beam + j;
+      float sc = score_in[r];
+      if (done_in[r]) {
+        if (threadIdx.x == 0) {
+          int flat = j * V + pad_id;
+          bool taken = false;
+          for (int q = 0; q < n; ++q) taken |= (sel_flat[q] == flat);
+          if (!taken && (sc > best || (sc == best && flat < best_flat))) { best = sc; best_flat = flat; }
+        }
+        continue;
+      }
+      const float* row = logits + (i64)r * ld;
+      float lse = lse_ws[r];
+      for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        float cand = sc + (row[v] * inv_temp - lse);
+        int flat = j * V + v;
+        if (cand > best || (cand == best && flat < best_flat)) {
+          bool taken = false;
+          for (int q = 0; q < n; ++q) taken |= (sel_flat[q] == flat);
+          if (!taken) { best = cand; best_flat = flat; }
+        }
+      }
+    }
+    // block arg-max with lowest-flat tie-break: first the max score, then the min flat among holders
+    float bm = block_max(best, red);
+    float cand_flat = (best == bm) ? -(float)best_flat : -3.0e38f;
+    float bf = block_max(cand_flat, red);
+    if (threadIdx.x == 0) {
+      sel_score[n] = bm;
+      sel_flat[n] = (int)(-bf + 0.5f);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < beam) {
+    int n = threadIdx.x;
+    score_out[b * beam + n] = sel_score[n];
+    src_out[b * beam + n] = sel_flat[n] / V;
+    tok_out[b * beam + n] = sel_flat[n] % V;
+  }
+}
+// reorder beam state after top-k: rows of (h,c) gathered from src; finished sources keep their old state
+struct BeamStepP {
+  const float* h_new; const float* c_new; const float* h_old; const float* c_old;
+  float* h_out; float* c_out; int Hd;
+  const int* src; const int* tok; const int* done_in; const int* prev_in;
+  int* done_out; int* prev_out; const int* toks_in; int* toks_out;
+  int beam, k, max_len, pad_id, eos_id, rows;
+};
+__global__ void k_beam_reorder(BeamStepP p) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (i64)p.rows * p.Hd) return;
+  int r = (int)(i / p.Hd), u = (int)(i - (i64)r * p.Hd);
+  int b = r / p.beam;
+  int sr = b * p.beam + p.src[r];
+  bool was_done = p.done_in[sr] != 0;
+  p.h_out[i] = was_done ? p.h_old[(i64)sr * p.Hd + u] : p.h_new[(i64)sr * p.Hd + u];
+  p.c_out[i] = was_done ? p.c_old[(i64)sr * p.Hd + u] : p.c_new[(i64)sr * p.Hd + u];
+  if (u == 0) {
+    int tk = p.tok[r];
+    for (int q = 0; q < p.max_len; ++q) {
+      int v = q < p.k ? p.toks_in[(i64)sr * p.max_len + q] : p.pad_id;
+      if (q == p.k) v = was_done ? p.pad_id : tk;
+      p.toks_out[(i64)r * p.max_len + q] = v;
+    }
+    p.prev_out[r] = was_done ? p.prev_in[sr] : tk;
+    p.done_out[r] = was_done | (tk == p.eos_id);
+  }
+}
+__global__ void k_fill_int(int* p, int v, i64 n) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void k_fill_float(float* p, float v, i64 n) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+// beam init: scores[b,0]=0, others -1e30; h/c rows replicated from [B,Hd] to [B*beam,Hd]
+__global__ void k_beam_init(const float* h0, const float* c0, float* h, float* c, float* score, int B, int beam, int Hd) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (i64)B * beam * Hd) return;
+  int r = (int)(i / Hd), u = (int)(i - (i64)r * Hd);
+  int b = r / beam, j = r - b * beam;
+  h[i] = h0[(i64)b * Hd + u];
+  c[i] = c0[(i64)b * Hd + u];
+  if (u == 0) score[r] = j == 0 ? 0.f : -1.0e30f;
+}

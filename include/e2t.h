@@ -1,0 +1,149 @@
+/* e2t.h -- C-ABI of the B200-native ECoG->text seq2seq engine (libe2t.so).
+ *
+ * This is the drop-in boundary for the hot path of jgmakin/ecog2txt: everything the reference
+ * reaches through `machine_learning.neural_networks.sequence_networks.SequenceNetwork`
+ * (imported at /root/reference/ecog2txt/trainers.py:33, constructed :126-135, driven
+ * :318,355,367 (fit), :379 (restore_and_assess), :699,750 (get_weights_as_numpy_array),
+ * :813-823 (_convolve_sequences/_encode_sequences), :933-937 (online predictor)).
+ * The reference has no FFI of its own (pure Python on TF1.15); the Python class
+ * ecog2txt_b200.SequenceNetwork binds these symbols through ctypes.
+ *
+ * Conventions
+ *   - every call returns int: 0 = OK, <0 = error; text via e2t_last_error() (thread-local).
+ *   - plain pointers and sizes only.  `loc` says where x / lens / y live: E2T_HOST (the library
+ *     stages them to the device on its stream) or E2T_DEVICE (used in place).
+ *   - the caller owns every buffer it passes; the library owns all device memory behind the
+ *     opaque handle.  One handle <-> one GPU <-> one CUDA stream; not thread-safe per handle.
+ *   - all floats are fp32, all indices int32, all arrays C-contiguous.
+ *   - tensor names / shapes follow the TF checkpoint convention the reference parses in
+ *     MultiSubjectTrainer.recover_model_sizes (/root/reference/ecog2txt/trainers.py:444-554).
+ */
+#ifndef E2T_H_
+#define E2T_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define E2T_MAX_SUBNETS 16
+#define E2T_MAX_LAYERS 8
+#define E2T_HOST 0
+#define E2T_DEVICE 1
+
+/* which copy of a parameter tensor */
+#define E2T_VALUE 0   /* trained variable                                      */
+#define E2T_GRAD 1    /* gradient of the summed loss (before 1/ntok)           */
+#define E2T_ADAM_M 2
+#define E2T_ADAM_V 3
+#define E2T_EMA 4     /* .../ExponentialMovingAverage shadow (trainers.py:466) */
+
+/* activations */
+#define E2T_ACT_LINEAR 0
+#define E2T_ACT_RELU 1
+
+/* GEMM backends */
+#define E2T_GEMM_AUTO 0     /* tcgen05 where shapes allow, SIMT otherwise */
+#define E2T_GEMM_SIMT 1     /* fp32 CUDA-core tiles only (validation path) */
+#define E2T_GEMM_TCGEN05 2  /* same as AUTO but reports an error if nothing could use tensor cores */
+
+typedef struct e2t_handle e2t_handle;
+
+/* Model geometry + optimiser constants; mirrors the manifest keys SequenceNetwork consumes
+ * (layer_sizes, FF_dropout, RNN_dropout, EMA_decay: mochastar_word_sequence.yaml:3-4,11,62-75). */
+typedef struct e2t_config {
+  int32_t n_subnets;                     /* subjects; private conv weights (trainers.py:337-338) */
+  int32_t subnet_id[E2T_MAX_SUBNETS];    /* ECoGSubject.subnet_id, subjects.py:106-108 */
+  int32_t subnet_C[E2T_MAX_SUBNETS];     /* encoder_inputs num_features */
+  int32_t subnet_W[E2T_MAX_SUBNETS];     /* decimation_factor = conv width = stride, subjects.py:144-157 */
+  int32_t E;                             /* layer_sizes['encoder_embedding'][0] */
+  int32_t n_enc_layers;
+  int32_t H[E2T_MAX_LAYERS];             /* layer_sizes['encoder_rnn'] (per direction) */
+  int32_t D;                             /* layer_sizes['decoder_embedding'][0] */
+  int32_t Hd;                            /* layer_sizes['decoder_rnn'][0]; must equal 2*H[last] */
+  int32_t V;                             /* decoder_targets num_features (vocabulary) */
+  int32_t conv_act, emb_act;             /* E2T_ACT_* */
+  int32_t pad_id, eos_id, start_id;      /* indices of <pad>, <EOS>; first decoder input */
+  int32_t max_B, max_T, max_L;           /* workspace capacity: utterances/call, frames, target len */
+  int32_t max_beam;                      /* capacity for beam search (>=1) */
+  float ff_dropout, rnn_dropout;         /* training only */
+  float lr, beta1, beta2, eps;           /* TF1 AdamOptimizer */
+  float ema_decay;                       /* 0 disables the shadow copy */
+  float penalty_scale;                   /* decoder_targets penalty_scale, subjects.py:289 */
+  int32_t gemm_backend;                  /* E2T_GEMM_* */
+  int32_t device;                        /* CUDA device ordinal */
+} e2t_config;
+
+const char* e2t_last_error(void);
+/* ABI version of this header; bump on any signature change. */
+int e2t_abi_version(void);
+
+/* replaces SequenceNetwork.__init__ (trainers.py:126-135) */
+int e2t_create(const e2t_config* cfg, e2t_handle** out);
+int e2t_destroy(e2t_handle* h);
+/* run on the caller's CUDA stream (cudaStream_t as void*; NULL = the library's own stream) */
+int e2t_set_stream(e2t_handle* h, void* cuda_stream);
+int e2t_sync(e2t_handle* h);
+
+/* ---- parameters: replaces get_weights_as_numpy_array / the TF Saver (trainers.py:699-700,240-252) */
+int e2t_param_count(e2t_handle* h);
+int64_t e2t_param_total(e2t_handle* h); /* number of fp32 elements in the flat buffer */
+/* name (NUL-terminated, truncated to name_cap), shape[<=4], ndim, offset into the flat buffer */
+int e2t_param_info(e2t_handle* h, int index, char* name, int name_cap, int64_t* shape, int* ndim,
+                   int64_t* offset);
+int e2t_get_tensor(e2t_handle* h, const char* name, int which, float* host_out);
+int e2t_set_tensor(e2t_handle* h, const char* name, int which, const float* host_in);
+/* device pointer + length of one flat buffer (E2T_GRAD for the data-parallel all-reduce) */
+int e2t_flat_buffer(e2t_handle* h, int which, void** dev_ptr, int64_t* n);
+/* train_vars_scope (trainers.py:312,352,366): per-tensor trainable flag, default 1 */
+int e2t_set_trainable(e2t_handle* h, const char* name, int trainable);
+/* Adam step counter (for checkpoint/resume) */
+int e2t_get_step(e2t_handle* h, int64_t* step);
+int e2t_set_step(e2t_handle* h, int64_t step);
+
+/* ---- training: replaces one sess.run(train_op) inside SequenceNetwork.fit (trainers.py:318) ----
+ * x [B,T,C_subnet] fp32 zero-padded at the tail; lens [B] or NULL (inferred from the zero padding,
+ * trainers.py:806-807); y [B,L] int32 targets with <EOS> appended and pad_id after it.
+ * Runs forward + backward; gradients of  penalty_scale * sum_tokens CE  are left in the E2T_GRAD
+ * buffer (zeroed first).  loss_sum / ntok (nullable, host) receive the summed loss and the number
+ * of unmasked target tokens; reading them synchronises the stream. */
+int e2t_train_step_grads(e2t_handle* h, int subnet, const float* x, const int32_t* lens,
+                         const int32_t* y, int loc, int B, int T, int L, uint32_t dropout_seed,
+                         float* loss_sum, int32_t* ntok);
+/* Adam + EMA on the trainable tensors of `subnet` (private) and the shared ones, using
+ * grad * grad_scale (1 / global token count).  subnet < 0: every subnet. */
+int e2t_adam_ema_step(e2t_handle* h, int subnet, float grad_scale);
+/* forward only (assessment loss): same inputs, no dropout, weights = value or EMA */
+int e2t_eval_loss(e2t_handle* h, int subnet, const float* x, const int32_t* lens, const int32_t* y,
+                  int loc, int B, int T, int L, int use_ema, float* loss_sum, int32_t* ntok);
+
+/* ---- decoding: replaces restore_and_assess's decode and the online predictor
+ * ('decoder_outputs:0', 'decoder_probs:0'; trainers.py:379,933-937) ----
+ * tokens [B,max_len] int32: argmax tokens up to and including <EOS>, then pad_id.
+ * logp   [B,max_len] fp32 (nullable): log softmax(logits/temperature) of each emitted token. */
+int e2t_greedy_decode(e2t_handle* h, int subnet, const float* x, const int32_t* lens, int loc, int B,
+                      int T, int max_len, int use_ema, float temperature, int32_t* tokens,
+                      float* logp);
+/* tokens [B,beam,max_len] best-first (trainers.py:952-963); scores [B,beam] summed log-probs. */
+int e2t_beam_decode(e2t_handle* h, int subnet, const float* x, const int32_t* lens, int loc, int B,
+                    int T, int beam, int max_len, int use_ema, float temperature, int32_t* tokens,
+                    float* scores);
+
+/* ---- introspection (get_internal_activations, trainers.py:757-859) -------------------------
+ * Copies an activation of the most recent forward pass to the host.  names: "lens", "lens2"
+ * (int32 [B]), "conv_out" [T',B,E], "enc<l>_out" [T',B,2H], "final_h", "final_c" [B,Hd],
+ * "logits" [L,B,V].  n_cap = capacity of host_out in elements; *n_out = elements written. */
+int e2t_get_activation(e2t_handle* h, const char* name, void* host_out, int64_t n_cap,
+                       int64_t* n_out);
+
+/* ---- accounting -------------------------------------------------------------------------- */
+/* kernels launched by this handle since creation (all / those that used tcgen05) */
+int e2t_launch_counts(e2t_handle* h, int64_t* total, int64_t* tensor_core);
+/* self-test of the tcgen05 GEMM against the SIMT GEMM on random data; returns max |diff| */
+int e2t_selftest_gemm(e2t_handle* h, int M, int N, int K, float* max_abs_diff);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* E2T_H_ */
