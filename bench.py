@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- training throughput (utterances/s) and greedy-decode latency of the seq2seq hot path.
+
+Contract: `python bench.py --gpus N --steps K --warmup W` (under torchrun for N>1) prints ONE JSON line
+on rank 0.  A "step" = one full training step (forward + backward + all-reduce (N>1) + Adam + EMA)
+over one synthetic batch of the config-2 workload of BASELINE.json: T=400 frames x C=256 channels,
+3x400 BiLSTM encoder, 800 LSTM decoder, V=1806, per-GPU batch 256 (weak scaling).
+  value : whole-job utterances/s with the batch pool already resident in HBM (pool > L2)
+  e2e   : same metric through the public API with HOST (pinned) buffers: H2D of x/y and D2H of the loss
+          inside the timed region, every step
+  roofline     : recurrent-step kernels (the dominant category), algorithmic FLOPs / CUDA-event time
+  cpu_baseline : the oracle (torch CPU port; the reference's TF1.15 path cannot run here) on a bounded sample
+`--impl reference` times that CPU port alone on the same config / metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+GEO = dict(subnet_ids=(400,), subnet_C=(256,), subnet_W=(12,), E=100, H=(400, 400, 400), D=150, Hd=800, V=1806)
+T_FRAMES, L_TGT = 400, 11
+FF_DROPOUT, RNN_DROPOUT = 0.1, 0.5   # mochastar_word_sequence.yaml:4,11
+METRIC, UNIT = "train_utterances_per_sec", "utt/s"
+
+
+def flops_per_utt(L):
+    """BASELINE.md section 4 (multiply-add = 2 FLOP)."""
+    W, C, E, H, D, Hd, V, T2 = 12, 256, 100, 400, 150, 800, 1806, 34
+    conv = 2 * T2 * W * C * E
+    enc = 2 * 2 * T2 * (E + H) * 4 * H + 2 * 2 * 2 * T2 * (3 * H) * 4 * H
+    dec = (2 * (D + Hd) * 4 * Hd + 2 * Hd * V) * L
+    fwd = conv + enc + dec
+    rec_fwd = 3 * 2 * 2 * T2 * H * 4 * H + L * 2 * Hd * 4 * Hd     # h Wh products only
+    return dict(forward=fwd, train=3 * fwd, recurrent_train=2 * rec_fwd)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_utt_per_s(B, steps, threads=None, warmup=1):
+    """The oracle's training step (forward, autograd backward, Adam+EMA) on the host cores."""
+    import torch
+    from oracle import seq2seq_oracle as O
+    from ecog2txt_b200.synthetic import SyntheticCorpus, load_vocab
+    if threads:
+        torch.set_num_threads(threads)
+    ocfg = O.OracleConfig(**GEO)
+    P = O.init_params(ocfg, 1)
+    opt = O.AdamEMA(ocfg, P)
+    corpus = SyntheticCorpus(load_vocab(size=GEO["V"]), T=T_FRAMES, C=256, seed=0)
+    times = []
+    for s in range(warmup + steps):
+        b = corpus.batch(B, seed=s, L=L_TGT)
+        x, y = torch.from_numpy(b["encoder_inputs"]), torch.from_numpy(b["decoder_targets"]).long()
+        t0 = time.perf_counter()
+        masks = O.make_masks(ocfg, s, B, 34, L_TGT, FF_DROPOUT, RNN_DROPOUT, torch.float32)
+        _, ntok, g, _ = O.loss_and_grads(ocfg, P, x, None, y, masks=masks)
+        opt.step(P, g, 1.0 / ntok)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    return B / float(np.mean(times)), torch.get_num_threads(), float(np.mean(times))
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    B = args.ref_batch
+    v, cores, dt = cpu_port_utt_per_s(B, args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config2: T=400 C=256 3x400 BiLSTM + 800 LSTM decoder V=1806, L=11, dropout .1/.5",
+                   "batch_per_step": B},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} training steps of {B} utterances (oracle: torch CPU fp32; the reference's "
+                                   "TF1.15 + machine_learning path is not installable here)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="utterances per GPU per step")
+    ap.add_argument("--ref-batch", type=int, default=32)
+    ap.add_argument("--backend", default="auto")
+    ap.add_argument("--cpu-baseline-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decode", action="store_true", help="also report greedy / beam decode numbers")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ecog2txt_b200 import Engine, EngineConfig, _lib
+    from ecog2txt_b200.params import init_engine
+    from ecog2txt_b200.synthetic import SyntheticCorpus, load_vocab
+    from ecog2txt_b200.dist import flat_tensor
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU port"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+    eng = Engine(EngineConfig(**GEO, max_B=B, max_T=T_FRAMES, max_L=20, max_beam=8, ff_dropout=FF_DROPOUT,
+                              rnn_dropout=RNN_DROPOUT, gemm_backend=args.backend, device=local))
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    init_engine(eng, seed=1)
+    grads = flat_tensor(eng, _lib.GRAD)
+
+    # ---- synthetic pool: 4 distinct batches per rank, 105 MB each -> 420 MB > 126 MB L2
+    corpus = SyntheticCorpus(load_vocab(size=GEO["V"]), T=T_FRAMES, C=256, seed=0)
+    NPOOL = 4
+    host, dev = [], []
+    for i in range(NPOOL):
+        b = corpus.batch(B, seed=1000 * rank + i, L=L_TGT)
+        hx = torch.from_numpy(b["encoder_inputs"]).pin_memory()
+        hy = torch.from_numpy(b["decoder_targets"]).pin_memory()
+        host.append((hx, hy))
+        dev.append((hx.cuda(), hy.cuda()))
+    ntok_t = torch.zeros(1, device="cuda")
+
+    def step_device(i):
+        x, y = dev[i % NPOOL]
+        eng.train_step_grads(x, None, y, seed=i, want_loss=False)
+        ntok = float((y != 0).sum()) if world == 1 else None
+        if world > 1:
+            ntok_t[0] = (y != 0).sum()
+            dist.all_reduce(grads)
+            dist.all_reduce(ntok_t)
+            ntok = float(ntok_t.item())
+        eng.adam_ema_step(1.0 / ntok)
+
+    ntok_cache = [float((hy != 0).sum()) for _, hy in host]
+
+    def step_host(i):
+        hx, hy = host[i % NPOOL]
+        loss, ntok = eng.train_step_grads(hx.numpy(), None, hy.numpy(), seed=i, want_loss=True)  # H2D x,y ; D2H loss
+        if world > 1:
+            ntok_t[0] = ntok
+            dist.all_reduce(grads)
+            dist.all_reduce(ntok_t)
+            ntok = float(ntok_t.item())
+        eng.adam_ema_step(1.0 / ntok)
+        return loss
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    l0, _ = eng.launch_counts()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_device, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    l1, tc1 = eng.launch_counts()
+    launches = (l1 - l0) * args.steps // (args.steps + max(args.warmup, 3))
+    ms_e2e = timed(step_host, args.steps, 3)
+    value = B * world * args.steps / (ms * 1e-3)
+    e2e = B * world * args.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline leg: recurrent-step kernels, CUDA events around every launch of the category
+    fl = flops_per_utt(L_TGT)
+    roof = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained", 1590.0 * 0.88)
+        psrc = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback"
+        eng.profile_enable(True)
+        nprof = 3
+        for i in range(nprof):
+            step_device(i)
+        cat_ms = {c: eng.profile_read(c) for c in range(4)}
+        eng.profile_enable(False)
+        rec_ms, rec_n = cat_ms[0]
+        tot = sum(v[0] for v in cat_ms.values())
+        achieved = fl["recurrent_train"] * B * nprof / (rec_ms * 1e-3) / 1e12 if rec_ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "recurrent LSTM steps (h Wh GEMM + gate kernel, fwd+bwd)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "peak_source": psrc + "; operands are tf32/fp32 (nominal tf32 peak is half the bf16 figure)",
+                "launches_per_step": rec_n // nprof, "avg_launch_us": 1e3 * rec_ms / max(rec_n, 1),
+                "share_of_step": rec_ms / tot if tot > 0 else None,
+                "category_ms_per_step": {k: cat_ms[i][0] / nprof for i, k in enumerate(("recurrent", "bulk_gemm", "conv", "other"))},
+                "whole_step_frac_of_peak": (fl["train"] * value / world / 1e12) / peak_tf}
+
+    decode = None
+    if args.decode and rank == 0:
+        x, _ = dev[0]
+        for _ in range(2):
+            eng.greedy_decode(x, None, max_len=20, want_logp=False)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            eng.greedy_decode(x, None, max_len=20, want_logp=False)
+        g256 = (time.perf_counter() - t0) / 5
+        x1 = x[:1].contiguous()
+        for _ in range(2):
+            eng.greedy_decode(x1, None, max_len=20, want_logp=False)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            eng.greedy_decode(x1, None, max_len=20, want_logp=False)
+        g1 = (time.perf_counter() - t0) / 10
+        xb = x[:32].contiguous()
+        eng.beam_decode(xb, None, beam=8, max_len=20)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            eng.beam_decode(xb, None, beam=8, max_len=20)
+        b8 = (time.perf_counter() - t0) / 3
+        decode = {"greedy_ms_per_utt_batch256": 1e3 * g256 / B, "greedy_ms_per_utt_batch1": 1e3 * g1,
+                  "beam8_utt_per_s_batch32": 32 / b8}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, dt = cpu_port_utt_per_s(args.ref_batch, args.cpu_baseline_steps)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_baseline_steps} training steps of {args.ref_batch} utterances of the same workload "
+                         f"({dt:.2f} s/step; oracle = torch CPU fp32 port, reference TF1.15 path not runnable here)"}
+
+    if rank == 0:
+        hx, hy = host[0]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32" if eng.launch_counts()[1] > 0 else "f32", "data": "synthetic",
+            "config": {"workload": "config2: T=400 C=256 3x400 BiLSTM + 800 LSTM decoder V=1806, L=11, dropout .1/.5, "
+                                   "Adam+EMA, per-GPU batch %d" % B,
+                       "global_batch": B * world, "cache": "pool of 4 batches x 105 MB per rank (> 126 MB L2)",
+                       "parallelism": f"dp{world}", "gemm_backend": args.backend},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(hx.numel() * 4 + hy.numel() * 4),
+                    "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "tcgen05_launches_total": int(tc1),
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        }
+        if decode:
+            line["decode"] = decode
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -82,6 +82,8 @@ _SIGNATURES = {
                                   C.c_float, _P, _P]),
     "e2t_get_activation": (C.c_int, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "e2t_launch_counts": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "e2t_profile_enable": (C.c_int, [_P, C.c_int]),
+    "e2t_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "e2t_selftest_gemm": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

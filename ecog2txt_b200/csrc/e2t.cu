@@ -66,6 +66,13 @@ struct e2t_handle {
   int64_t n_launch = 0, n_launch_tc = 0;
   bool packed_dirty = true;
   int packed_src = -1;
+  // per-category event timing (e2t_profile_*)
+  bool prof = false;
+  int cat = E2T_CAT_OTHER;
+#ifndef E2T_EMU
+  struct ProfRec { int cat; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
+#endif
 
   // parameter offsets
   i64 conv_w[E2T_MAX_SUBNETS], conv_b[E2T_MAX_SUBNETS];
@@ -107,9 +114,35 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // launches
 // ------------------------------------------------------------------------------------------------
+#ifndef E2T_EMU
+inline void prof_begin(e2t_handle* h) {
+  if (!h->prof) return;
+  e2t_handle::ProfRec r;
+  r.cat = h->cat;
+  E2T_CHECK(cudaEventCreate(&r.a));
+  E2T_CHECK(cudaEventCreate(&r.b));
+  E2T_CHECK(cudaEventRecord(r.a, h->stream));
+  h->prof_recs.push_back(r);
+}
+inline void prof_end(e2t_handle* h) {
+  if (!h->prof) return;
+  E2T_CHECK(cudaEventRecord(h->prof_recs.back().b, h->stream));
+}
+#else
+inline void prof_begin(e2t_handle*) {}
+inline void prof_end(e2t_handle*) {}
+#endif
+struct CatScope {
+  e2t_handle* h; int old;
+  CatScope(e2t_handle* h_, int c) : h(h_), old(h_->cat) { h->cat = c; }
+  ~CatScope() { h->cat = old; }
+};
+
 #define LAUNCH(h, kern, grid, block, smem, ...)                       \
   do {                                                                \
+    prof_begin(h);                                                    \
     E2T_LAUNCH(kern, grid, block, smem, (h)->stream, __VA_ARGS__);    \
+    prof_end(h);                                                      \
     ++(h)->n_launch;                                                  \
   } while (0)
 
@@ -124,14 +157,18 @@ void gemm(e2t_handle* h, const float* A, i64 sam, i64 sak, const float* B, i64 s
     return;
   }
 #ifndef E2T_EMU
+  CatScope cs0_(h, h->cat == E2T_CAT_RECURRENT ? E2T_CAT_RECURRENT : E2T_CAT_BULK_GEMM);
   if (h->cfg.gemm_backend != E2T_GEMM_SIMT && sak == 1 && sbk == 1 &&
       tc_gemm_nt_supported(A, sam, B, sbn, C, ldc, M, N, K)) {
+    prof_begin(h);
     tc_gemm_nt(h->stream, A, sam, B, sbn, C, ldc, M, N, K, bias, beta);
+    prof_end(h);
     ++h->n_launch;
     ++h->n_launch_tc;
     return;
   }
 #endif
+  CatScope cs_(h, h->cat == E2T_CAT_RECURRENT ? E2T_CAT_RECURRENT : E2T_CAT_BULK_GEMM);
   GemmP p{};
   p.A = A; p.sam = sam; p.sak = sak;
   p.B = B; p.sbk = sbk; p.sbn = sbn;
@@ -144,6 +181,7 @@ void gemm(e2t_handle* h, const float* A, i64 sam, i64 sak, const float* B, i64 s
 // conv-gather GEMMs (A3+A4 fused). mode 1: Y[T2*B, E] = gather(x) Wc + b ; mode 2: dWc[W*C, E] = gather(x)^T dY
 void gemm_conv(e2t_handle* h, int mode, const float* x, const int* lens, int Bsz, int T, int Cch, int Wd, int T2,
                const float* Bmat, i64 sbk, i64 sbn, float* C, i64 ldc, int N, const float* bias, float beta) {
+  CatScope cs_(h, E2T_CAT_CONV);
   GemmP p{};
   p.x = x; p.lens = lens; p.Bsz = Bsz; p.T = T; p.Cch = Cch; p.Wd = Wd;
   p.B = Bmat; p.sbk = sbk; p.sbn = sbn; p.C = C; p.ldc = ldc; p.N = N; p.bias = bias; p.beta = beta;
@@ -356,6 +394,7 @@ void lstm_layer_forward(e2t_handle* h, const float* in, int ld_in, int In, int H
   // KT [4H, ldkt] = kernel^T: column block [0,In) is Wx^T, [In,In+H) is Wh^T (both K-major B operands)
   gemm(h, in, ld_in, 1, KT, 1, ldkt, gates, 4 * H, steps * B, 4 * H, In, bias, 0.f);
   const float* WhT = KT + In;
+  CatScope cs_(h, E2T_CAT_RECURRENT);
   for (int s = 0; s < steps; ++s) {
     int t = reverse ? steps - 1 - s : s;
     int tp = reverse ? t + 1 : t - 1;
@@ -437,6 +476,7 @@ void lstm_layer_backward(e2t_handle* h, int H, const float* K, int In, float* ga
                          const float* dc_inject, int ldi, const int* inject_t, int inject_const) {
   const float* Wh = K + (i64)In * 4 * H;  // canonical rows [H, 4H] = K-major B operand of dz Wh^T
   E2T_CHECK(cudaMemsetAsync(h->dc_rec, 0, (size_t)B * H * sizeof(float), h->stream));
+  CatScope cs_(h, E2T_CAT_RECURRENT);
   for (int s = steps - 1; s >= 0; --s) {
     int t = reverse ? steps - 1 - s : s;
     int tn = reverse ? t - 1 : t + 1;   // the step processed after t in the forward pass
@@ -878,6 +918,33 @@ extern "C" int e2t_launch_counts(e2t_handle* h, int64_t* total, int64_t* tensor_
   API_BEGIN NEED_H;
   if (total) *total = h->n_launch;
   if (tensor_core) *tensor_core = h->n_launch_tc;
+  API_END
+}
+
+extern "C" int e2t_profile_enable(e2t_handle* h, int on) {
+  API_BEGIN NEED_H;
+#ifndef E2T_EMU
+  E2T_CHECK(cudaStreamSynchronize(h->stream));
+  for (auto& r : h->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  h->prof_recs.clear();
+#endif
+  h->prof = on != 0;
+  API_END
+}
+extern "C" int e2t_profile_read(e2t_handle* h, int category, double* ms_total, int64_t* launches) {
+  API_BEGIN NEED_H;
+  double ms = 0.0; int64_t n = 0;
+#ifndef E2T_EMU
+  E2T_CHECK(cudaStreamSynchronize(h->stream));
+  for (auto& r : h->prof_recs) {
+    if (r.cat != category) continue;
+    float t = 0.f;
+    E2T_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t; ++n;
+  }
+#endif
+  if (ms_total) *ms_total = ms;
+  if (launches) *launches = n;
   API_END
 }
 

@@ -247,6 +247,14 @@ class Engine:
         self._ck(self._lib.e2t_launch_counts(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
+    def profile_enable(self, on: bool):
+        self._ck(self._lib.e2t_profile_enable(self._h, int(on)))
+
+    def profile_read(self, category: int) -> Tuple[float, int]:
+        ms, n = C.c_double(), C.c_int64()
+        self._ck(self._lib.e2t_profile_read(self._h, category, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     def selftest_gemm(self, M: int, N: int, K: int) -> float:
         d = C.c_float()
         self._ck(self._lib.e2t_selftest_gemm(self._h, M, N, K, C.byref(d)))

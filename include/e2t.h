@@ -140,6 +140,16 @@ int e2t_get_activation(e2t_handle* h, const char* name, void* host_out, int64_t 
 /* ---- accounting -------------------------------------------------------------------------- */
 /* kernels launched by this handle since creation (all / those that used tcgen05) */
 int e2t_launch_counts(e2t_handle* h, int64_t* total, int64_t* tensor_core);
+/* Per-category device timing (CUDA events around every launch of the category; for bench.py's
+ * roofline leg only -- the events perturb the step, so it is never on during a timed region).
+ * categories: 0 recurrent steps (h Wh GEMM + gate kernel, fwd and bwd), 1 bulk GEMMs (input
+ * projections, output projection, weight/input gradients), 2 temporal conv, 3 everything else. */
+#define E2T_CAT_RECURRENT 0
+#define E2T_CAT_BULK_GEMM 1
+#define E2T_CAT_CONV 2
+#define E2T_CAT_OTHER 3
+int e2t_profile_enable(e2t_handle* h, int on);
+int e2t_profile_read(e2t_handle* h, int category, double* ms_total, int64_t* launches);
 /* self-test of the tcgen05 GEMM against the SIMT GEMM on random data; returns max |diff| */
 int e2t_selftest_gemm(e2t_handle* h, int M, int N, int K, float* max_abs_diff);
 

@@ -1,0 +1,119 @@
+"""Parity checks shared by the CPU (kernel-emulation) and GPU test files: the engine under test is
+driven through the C-ABI and compared with the oracle on the same seeded inputs."""
+import numpy as np
+import torch
+
+from ecog2txt_b200 import Engine, EngineConfig, _lib
+from oracle import seq2seq_oracle as O
+
+TINY = dict(subnet_ids=(7,), subnet_C=(6,), subnet_W=(4,), E=5, H=(8, 8), D=6, Hd=16, V=11)
+SMALL = dict(subnet_ids=(400,), subnet_C=(32,), subnet_W=(12,), E=20, H=(32, 32, 32), D=12, Hd=64, V=60)
+# aligned shapes (multiples of 4 / 16-byte rows) so that the tcgen05 GEMM path is eligible on the GPU
+MEDIUM = dict(subnet_ids=(400,), subnet_C=(64,), subnet_W=(12,), E=32, H=(64, 64), D=24, Hd=128, V=200)
+TWO_SUBJ = dict(subnet_ids=(400, 401), subnet_C=(6, 10), subnet_W=(4, 3), E=5, H=(8,), D=6, Hd=16, V=11)
+
+
+def make_params(ocfg, seed=1, bias_scale=0.1, eos_bias=None):
+    P = O.init_params(ocfg, seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    for k in P:
+        if P[k].ndim == 1:
+            P[k] = (torch.randn(P[k].shape, generator=g) * bias_scale).float()
+    if eos_bias is not None:  # make greedy hypotheses longer than one token
+        pb = f"seq2seq/decoder_projection_{ocfg.Hd}_{ocfg.V}_0/biases"
+        P[pb][ocfg.eos_id] = eos_bias
+        P[pb][ocfg.pad_id] = -20.0
+    return P
+
+
+def make_batch(ocfg, B, T, L, subnet=0, seed=0, ragged=True):
+    rs = np.random.RandomState(seed)
+    C = ocfg.subnet_C[subnet]
+    x = rs.randn(B, T, C).astype(np.float32)
+    lens = rs.randint(max(1, T // 3), T + 1, size=B) if ragged else np.full(B, T)
+    lens[0] = T
+    for b in range(B):
+        x[b, lens[b]:] = 0.0
+    y = np.zeros((B, L), np.int32)
+    for b in range(B):
+        n = rs.randint(1, L) if ragged else L - 1
+        y[b, :n] = rs.randint(3, ocfg.V, size=n)
+        y[b, n] = ocfg.eos_id
+    return x, lens.astype(np.int32), y
+
+
+def engine_for(geo, lib, B, T, L, **kw):
+    ecfg = EngineConfig(**geo, max_B=B, max_T=T, max_L=L, **kw)
+    return Engine(ecfg, lib=lib)
+
+
+def rel_err(a, ref):
+    return float(np.abs(a - ref).max() / max(np.abs(ref).max(), 1e-6))
+
+
+def check_train_step(lib, geo, B, T, L, ff=0.0, rnn=0.0, seed=3, tol=2e-4, backend="simt", give_lens=False,
+                     subnet=0):
+    ocfg = O.OracleConfig(**geo)
+    P = make_params(ocfg)
+    eng = engine_for(geo, lib, B, T, L, ff_dropout=ff, rnn_dropout=rnn, gemm_backend=backend)
+    eng.set_all({k: v.numpy() for k, v in P.items()})
+    x, lens, y = make_batch(ocfg, B, T, L, subnet=subnet)
+    W = ocfg.subnet_W[subnet]
+    T2 = -(-T // W)
+    masks = O.make_masks(ocfg, seed, B, T2, L, ff, rnn, torch.float32) if (ff > 0 or rnn > 0) else None
+    lo, no, g, acts = O.loss_and_grads(ocfg, P, torch.from_numpy(x), None, torch.from_numpy(y).long(),
+                                       subnet=subnet, masks=masks)
+    loss, ntok = eng.train_step_grads(x, lens if give_lens else None, y, subnet=subnet, seed=seed)
+    assert ntok == no
+    assert abs(loss - lo) <= tol * max(abs(lo), 1.0), (loss, lo)
+    assert (eng.activation("lens", (B,), np.int32) == lens).all()
+    e_top = eng.activation("final_h", (B, ocfg.Hd))
+    assert rel_err(e_top, acts["final_h"].numpy()) <= tol
+    G = eng.get_all(_lib.GRAD)
+    worst = 0.0
+    for k, v in G.items():
+        e = rel_err(v, g[k].numpy())
+        worst = max(worst, e)
+        assert e <= 5 * tol, (k, e)
+    eng.close()
+    return worst
+
+
+def check_decode(lib, geo, B, T, max_len, beam=0, backend="simt", temperature=0.7, use_ema=False):
+    ocfg = O.OracleConfig(**geo)
+    P = make_params(ocfg, eos_bias=-1.0)
+    eng = engine_for(geo, lib, B, T, max_len, max_beam=max(beam, 1), gemm_backend=backend)
+    eng.set_all({k: v.numpy() for k, v in P.items()})
+    x, lens, _ = make_batch(ocfg, B, T, 4)
+    xt = torch.from_numpy(x)
+    if beam == 0:
+        t_ref, lp_ref, logits = O.greedy_decode(ocfg, P, xt, None, max_len=max_len, temperature=temperature)
+        toks, logp = eng.greedy_decode(x, None, max_len=max_len, temperature=temperature, use_ema=use_ema)
+        # margin-aware: rows whose oracle top-2 logit gap is tiny at some live step may legitimately differ
+        top2 = logits.topk(2, dim=2).values
+        gap = (top2[..., 0] - top2[..., 1]).numpy()
+        live = np.ones_like(gap, bool)
+        tr = t_ref.numpy()
+        for b in range(B):
+            ends = np.where(tr[b] == ocfg.eos_id)[0]
+            if len(ends):
+                live[b, ends[0] + 1:] = False
+        safe = np.all((gap > 1e-3) | ~live, axis=1)
+        assert safe.mean() > 0.5
+        assert (toks[safe] == tr[safe]).all()
+        assert np.abs(logp[safe] - lp_ref.numpy()[safe]).max() < 2e-3
+        assert (tr != ocfg.pad_id).sum(1).max() > 1, "test params should give multi-token hypotheses"
+    else:
+        t_ref, s_ref = O.beam_decode(ocfg, P, xt, None, beam=beam, max_len=max_len, temperature=temperature)
+        toks, scores = eng.beam_decode(x, None, beam=beam, max_len=max_len, temperature=temperature)
+        s_ref = s_ref.numpy()
+        assert np.abs(scores - s_ref).max() < 5e-3
+        # beams whose score is well separated from their neighbours must hold identical tokens
+        sep = np.ones_like(s_ref, bool)
+        d = np.abs(np.diff(s_ref, axis=1)) > 1e-2
+        sep[:, 1:] &= d
+        sep[:, :-1] &= d
+        assert sep.mean() > 0.5
+        assert (toks[sep] == t_ref.numpy()[sep]).all()
+        assert (np.diff(scores, axis=1) <= 1e-6).all(), "beams must be best-first"
+    eng.close()
