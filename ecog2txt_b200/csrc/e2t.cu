@@ -167,6 +167,14 @@ void gemm(e2t_handle* h, const float* A, i64 sam, i64 sak, const float* B, i64 s
     ++h->n_launch_tc;
     return;
   }
+  if (h->cfg.gemm_backend != E2T_GEMM_SIMT && sam == 1 && sbn == 1 && tc_gemm_tn_supported(A, sak, B, sbk, M, N, K)) {
+    prof_begin(h);
+    tc_gemm_tn(h->stream, A, sak, B, sbk, C, ldc, M, N, K, bias, beta);
+    prof_end(h);
+    ++h->n_launch;
+    ++h->n_launch_tc;
+    return;
+  }
 #endif
   CatScope cs_(h, h->cat == E2T_CAT_RECURRENT ? E2T_CAT_RECURRENT : E2T_CAT_BULK_GEMM);
   GemmP p{};
@@ -954,7 +962,8 @@ extern "C" int e2t_selftest_gemm(e2t_handle* h, int M, int N, int K, float* max_
   (void)M; (void)N; (void)K; (void)max_abs_diff;
   throw std::runtime_error("e2t: tcgen05 self-test is not available in the emulation build");
 #else
-  float d = tc_gemm_selftest(h->stream, M, N, K);
+  // M < 0 selects the TN (A^T B, MN-major operands) variant
+  float d = M < 0 ? tc_gemm_selftest(h->stream, -M, N, K, true) : tc_gemm_selftest(h->stream, M, N, K, false);
   if (max_abs_diff) *max_abs_diff = d;
 #endif
   API_END

@@ -100,10 +100,25 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major tf32 operands: the only legal smem layout is SWIZZLE_128B_BASE32B (cutlass sm100_common.inl:92,
+// UMMA::Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> o (128 B of MN elements) x (4 k rows)): every k row holds
+// 32 consecutive MN elements, 32-byte chunks are XOR-permuted by (row & 3), 4 k rows = one 512 B atom.
+// LBO = byte stride between 32-element MN chunks, SBO = byte stride between 4-row k groups.
+// The matching TMA mode is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;   // SWIZZLE_128B_BASE32B
+  return d;
+}
 // cute::UMMA::InstrDescriptor: c_format F32=1 [4,6) | a_format TF32=2 [7,10) | b_format TF32=2 [10,13)
-// | a_major=b_major=K(0) | N>>3 [17,23) | M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// | a_major [15] b_major [16] (0 = K, 1 = MN) | N>>3 [17,23) | M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int mn_major = 0) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)mn_major << 15) | ((uint32_t)mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 struct TcGemmP {
@@ -112,7 +127,10 @@ struct TcGemmP {
   const float* bias; float beta;
 };
 
-template <int BN>
+// TN = false: A [M,K], B [N,K] row-major (K-major operands).
+// TN = true : A [K,M], B [K,N] row-major (MN-major operands; weight gradients X^T dZ): a stage holds
+//             BM/32 (+ BN/32) sub-tiles of [BK k-rows x 32 MN elements], one TMA box each.
+template <int BN, bool TN>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcGemmP p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -150,13 +168,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const uint32_t fb = smem_u32(&full_bar[s]);
         mbar_expect_tx(fb, STAGE_BYTES);
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        tma_load_2d(sa, &map_a, fb, kb * BK, m0);
-        tma_load_2d(sa + A_BYTES, &map_b, fb, kb * BK, n0);
+        if (!TN) {
+          tma_load_2d(sa, &map_a, fb, kb * BK, m0);
+          tma_load_2d(sa + A_BYTES, &map_b, fb, kb * BK, n0);
+        } else {
+#pragma unroll
+          for (int i = 0; i < BM / 32; ++i) tma_load_2d(sa + i * (BK * 128), &map_a, fb, m0 + i * 32, kb * BK);
+#pragma unroll
+          for (int i = 0; i < BN / 32; ++i) tma_load_2d(sa + A_BYTES + i * (BK * 128), &map_b, fb, n0 + i * 32, kb * BK);
+        }
       }
     }
   } else if (warp == 5) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+      constexpr uint32_t idesc = make_idesc_tf32(BM, BN, TN ? 1 : 0);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
@@ -165,8 +190,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t da = make_smem_desc(sa + k * UMMA_K * 4);
-          const uint64_t db = make_smem_desc(sa + A_BYTES + k * UMMA_K * 4);
+          const uint64_t da = TN ? make_smem_desc_mn(sa + k * 1024, BK * 128, 512) : make_smem_desc(sa + k * UMMA_K * 4);
+          const uint64_t db = TN ? make_smem_desc_mn(sa + A_BYTES + k * 1024, BK * 128, 512)
+                                 : make_smem_desc(sa + A_BYTES + k * UMMA_K * 4);
           umma_tf32(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(smem_u32(&empty_bar[s]));   // frees this smem stage when the MMAs retire
@@ -236,7 +262,8 @@ inline EncodeTiledFn encode_fn() {
 
 // 2-D fp32 tensor map over a row-major [rows, cols] matrix with leading dimension ld (elements);
 // box = [box_rows x 32 cols], 128-byte swizzle, zero OOB fill.
-inline CUtensorMap make_map(const float* ptr, i64 rows, i64 cols, i64 ld, int box_rows) {
+inline CUtensorMap make_map(const float* ptr, i64 rows, i64 cols, i64 ld, int box_rows, bool atom32 = false) {
+  if (rows <= 0 || cols <= 0) throw std::runtime_error("e2t: empty tensor map");
   CUtensorMap m;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
@@ -245,7 +272,8 @@ inline CUtensorMap make_map(const float* ptr, i64 rows, i64 cols, i64 ld, int bo
   EncodeTiledFn fn = encode_fn();
   if (!fn) throw std::runtime_error("e2t: cuTensorMapEncodeTiled entry point not found");
   CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("e2t: cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return m;
@@ -254,10 +282,10 @@ inline CUtensorMap make_map(const float* ptr, i64 rows, i64 cols, i64 ld, int bo
 template <int BN>
 constexpr size_t smem_bytes() { return (size_t)kStages * (BM * BK * 4 + BN * BK * 4) + (2 * kStages + 2) * 8 + 1024; }
 
-template <int BN>
+template <int BN, bool TN>
 inline void launch(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const TcGemmP& p) {
   static bool attr_set = false;
-  auto kfn = k_gemm_tc<BN>;
+  auto kfn = k_gemm_tc<BN, TN>;
   if (!attr_set) {
     E2T_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN>()));
     attr_set = true;
@@ -291,15 +319,39 @@ static inline void tc_gemm_nt(cudaStream_t st, const float* A, i64 lda, const fl
   if (N <= 32) bn = 32; else if (N <= 64 && bn > 64) bn = 64;
   CUtensorMap ma = tc::make_map(A, M, K, lda, tc::BM);
   CUtensorMap mb = tc::make_map(B, N, K, ldb, bn);
-  if (bn == 128) tc::launch<128>(st, ma, mb, p);
-  else if (bn == 64) tc::launch<64>(st, ma, mb, p);
-  else tc::launch<32>(st, ma, mb, p);
+  if (bn == 128) tc::launch<128, false>(st, ma, mb, p);
+  else if (bn == 64) tc::launch<64, false>(st, ma, mb, p);
+  else tc::launch<32, false>(st, ma, mb, p);
+}
+
+// C[M,N] = A[K,M]^T B[K,N]  (A, B row-major with leading dims lda, ldb): weight gradients.
+static inline bool tc_gemm_tn_supported(const float* A, i64 lda, const float* B, i64 ldb, int M, int N, int K) {
+  if (M < 8 || N < 8 || K < 32) return false;
+  if ((lda & 3) || (ldb & 3)) return false;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return false;
+  if ((i64)M * N * K < (i64)64 * 64 * 64) return false;
+  return true;
+}
+static inline void tc_gemm_tn(cudaStream_t st, const float* A, i64 lda, const float* B, i64 ldb, float* C, i64 ldc, int M,
+                              int N, int K, const float* bias, float beta) {
+  tc::TcGemmP p{C, ldc, M, N, K, bias, beta};
+  const int mt = (M + tc::BM - 1) / tc::BM;
+  int bn = 128;
+  if (mt * ((N + 127) / 128) < 96) bn = 64;
+  if (mt * ((N + 63) / 64) < 96) bn = 32;
+  if (N <= 32) bn = 32; else if (N <= 64 && bn > 64) bn = 64;
+  // boxes are [BK k-rows x 32 MN columns] of the [K, M] / [K, N] matrices
+  CUtensorMap ma = tc::make_map(A, K, M, lda, tc::BK, true);
+  CUtensorMap mb = tc::make_map(B, K, N, ldb, tc::BK, true);
+  if (bn == 128) tc::launch<128, true>(st, ma, mb, p);
+  else if (bn == 64) tc::launch<64, true>(st, ma, mb, p);
+  else tc::launch<32, true>(st, ma, mb, p);
 }
 
 // A/B random, C_tc vs fp32 SIMT reference; exercises bias, beta and ragged M/N/K edges. Returns max |diff|.
-static inline float tc_gemm_selftest(cudaStream_t st, int M, int N, int K) {
-  const i64 lda = (K + 3) / 4 * 4, ldb = lda, ldc = (N + 3) / 4 * 4;
-  std::vector<float> hA((size_t)M * lda), hB((size_t)N * ldb), hC((size_t)M * ldc), hbias(N);
+static inline float tc_gemm_selftest(cudaStream_t st, int M, int N, int K, bool tn = false) {
+  const i64 lda = tn ? (M + 3) / 4 * 4 : (K + 3) / 4 * 4, ldb = tn ? (N + 3) / 4 * 4 : (K + 3) / 4 * 4, ldc = (N + 3) / 4 * 4;
+  std::vector<float> hA((size_t)(tn ? K : M) * lda), hB((size_t)(tn ? K : N) * ldb), hC((size_t)M * ldc), hbias(N);
   uint32_t s = 12345u;
   auto rnd = [&]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
   for (auto& v : hA) v = rnd();
@@ -315,9 +367,11 @@ static inline float tc_gemm_selftest(cudaStream_t st, int M, int N, int K) {
   E2T_CHECK(cudaMemcpy(dC1, hC.data(), hC.size() * 4, cudaMemcpyHostToDevice));
   E2T_CHECK(cudaMemcpy(dC2, hC.data(), hC.size() * 4, cudaMemcpyHostToDevice));
   E2T_CHECK(cudaMemcpy(dbias, hbias.data(), hbias.size() * 4, cudaMemcpyHostToDevice));
-  tc_gemm_nt(st, dA, lda, dB, ldb, dC1, ldc, M, N, K, dbias, 1.0f);
+  if (tn) tc_gemm_tn(st, dA, lda, dB, ldb, dC1, ldc, M, N, K, dbias, 1.0f);
+  else tc_gemm_nt(st, dA, lda, dB, ldb, dC1, ldc, M, N, K, dbias, 1.0f);
   GemmP g{};
-  g.A = dA; g.sam = lda; g.sak = 1; g.B = dB; g.sbk = 1; g.sbn = ldb; g.C = dC2; g.ldc = ldc;
+  g.A = dA; g.sam = tn ? 1 : lda; g.sak = tn ? lda : 1; g.B = dB; g.sbk = tn ? ldb : 1; g.sbn = tn ? 1 : ldb;
+  g.C = dC2; g.ldc = ldc;
   g.M = M; g.N = N; g.K = K; g.bias = dbias; g.beta = 1.0f;
   dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
   k_gemm<0><<<grid, 256, 0, st>>>(g);

@@ -21,3 +21,18 @@ def test_tcgen05_gemm_matches_simt(gpu_lib, M, N, K):
     print(f"tcgen05 gemm {M}x{N}x{K}: max|diff| = {d:.3e} (tol {tol:.3e})")
     assert d <= tol, (d, tol)
     eng.close()
+
+
+# weight-gradient shapes C[M,N] = A[K,M]^T B[K,N]: dWx (800x1600 over 8704 rows), dWh, dWp, conv, ragged
+TN_SHAPES = [(800, 1600, 8704), (400, 1600, 8448), (1806, 800, 2816), (100, 1600, 8704), (3072, 100, 8704),
+             (150, 3200, 2816), (130, 72, 100), (32, 32, 64)]
+
+
+@pytest.mark.parametrize("M,N,K", TN_SHAPES)
+def test_tcgen05_gemm_tn_matches_simt(gpu_lib, M, N, K):
+    eng = pc.engine_for(pc.TINY, gpu_lib, 2, 8, 4)
+    d = eng.selftest_gemm(-M, N, K)   # negative M selects the TN variant
+    tol = 4.0 * (K ** 0.5) * 0.25 * 2 * 2 ** -10 + 1e-5
+    print(f"tcgen05 gemm TN {M}x{N}x{K}: max|diff| = {d:.3e} (tol {tol:.3e})")
+    assert d <= tol, (d, tol)
+    eng.close()
