@@ -15,7 +15,7 @@ HOST, DEVICE = 0, 1
 VALUE, GRAD, ADAM_M, ADAM_V, EMA = 0, 1, 2, 3, 4
 ACT = {"linear": 0, "relu": 1}
 GEMM = {"auto": 0, "simt": 1, "tcgen05": 2}
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class E2TConfig(C.Structure):
@@ -82,6 +82,7 @@ _SIGNATURES = {
                                   C.c_float, _P, _P]),
     "e2t_get_activation": (C.c_int, [_P, C.c_char_p, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "e2t_launch_counts": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "e2t_counter": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64)]),
     "e2t_profile_enable": (C.c_int, [_P, C.c_int]),
     "e2t_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "e2t_selftest_gemm": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),

@@ -23,11 +23,12 @@
 #include "kernels_simt.cuh"
 #ifndef E2T_EMU
 #include "gemm_tc.cuh"
+#include "lstm_rec.cuh"
 #endif
 
 static thread_local std::string g_err;
 extern "C" const char* e2t_last_error(void) { return g_err.c_str(); }
-extern "C" int e2t_abi_version(void) { return 1; }
+extern "C" int e2t_abi_version(void) { return 2; }
 
 namespace {
 
@@ -93,6 +94,8 @@ struct e2t_handle {
   float *h0, *c0, *dh0, *dc0, *dh_rec, *dc_rec;
   float *demb, *ddemb, *dgates, *dcs, *hdec, *dhdec, *logits, *loss_rows, *d_loss;
   int* d_ntok;
+  int* rec_counters = nullptr;   // arrival counters of the persistent recurrent kernels [2][n_bt][T2m]
+  int64_t n_launch_rec = 0;
   // decode workspace
   float *g_h[2], *g_c[2], *g_e, *g_z, *g_logits, *g_logp, *g_score[2], *g_lse;
   int *g_prev[2], *g_done[2], *g_tokens[2], *g_src, *g_tok;
@@ -317,6 +320,7 @@ void build_workspace(e2t_handle* h) {
   h->logits = h->alloc<float>(Lm * Bm * h->Vp);
   h->loss_rows = h->alloc<float>(Lm * Bm);
   h->d_loss = h->alloc<float>(4); h->d_ntok = h->alloc<int>(4);
+  h->rec_counters = h->alloc<int>((i64)2 * cdiv(Bm, 128) * std::max<i64>(T2, Lm));
   h->ld_dec_kt = round_up(c.D + c.Hd, 4);
   h->dec_KT = h->alloc<float>((i64)4 * c.Hd * h->ld_dec_kt);
   h->proj_wT = h->alloc<float>((i64)c.Hd * h->Vp);
@@ -394,13 +398,17 @@ Inputs stage(e2t_handle* h, int subnet, const float* x, const int32_t* lens, con
 // ------------------------------------------------------------------------------------------------
 // encoder forward (A2-A5)
 // ------------------------------------------------------------------------------------------------
-void lstm_layer_forward(e2t_handle* h, const float* in, int ld_in, int In, int H, const float* KT, int ldkt,
-                        const float* bias, float* gates, float* cs, float* hs, float* hd, int ldh, int col0, const int* lens2,
-                        int steps, int B, bool reverse, const float* h_init, const float* c_init, DropP dp,
-                        int drop_F) {
+void lstm_xproj(e2t_handle* h, const float* in, int ld_in, int In, int H, const float* KT, int ldkt, const float* bias,
+                float* gates, int steps, int B) {
   // input projection for every step at once: gates[steps*B, 4H] = in Wx + b
   // KT [4H, ldkt] = kernel^T: column block [0,In) is Wx^T, [In,In+H) is Wh^T (both K-major B operands)
   gemm(h, in, ld_in, 1, KT, 1, ldkt, gates, 4 * H, steps * B, 4 * H, In, bias, 0.f);
+}
+
+// the per-step recurrence (one GEMM + one gate kernel per step): small / unaligned shapes and the decoder
+void lstm_layer_steps(e2t_handle* h, int In, int H, const float* KT, int ldkt, float* gates, float* cs, float* hs,
+                      float* hd, int ldh, int col0, const int* lens2, int steps, int B, bool reverse,
+                      const float* h_init, const float* c_init, DropP dp, int drop_F) {
   const float* WhT = KT + In;
   CatScope cs_(h, E2T_CAT_RECURRENT);
   for (int s = 0; s < steps; ++s) {
@@ -419,6 +427,26 @@ void lstm_layer_forward(e2t_handle* h, const float* in, int ld_in, int In, int H
     p.dp = dp; p.drop_F = drop_F; p.drop_col0 = col0;
     LAUNCH(h, k_lstm_fwd, grid1((i64)B * H), dim3(256), 0, p);
   }
+}
+
+void lstm_layer_forward(e2t_handle* h, const float* in, int ld_in, int In, int H, const float* KT, int ldkt,
+                        const float* bias, float* gates, float* cs, float* hs, float* hd, int ldh, int col0, const int* lens2,
+                        int steps, int B, bool reverse, const float* h_init, const float* c_init, DropP dp,
+                        int drop_F) {
+  lstm_xproj(h, in, ld_in, In, H, KT, ldkt, bias, gates, steps, B);
+  lstm_layer_steps(h, In, H, KT, ldkt, gates, cs, hs, hd, ldh, col0, lens2, steps, B, reverse, h_init, c_init, dp, drop_F);
+}
+
+// persistent tcgen05 recurrence usable for a BiLSTM layer of this shape?
+bool use_rec(e2t_handle* h, int B, int H, int In, int steps) {
+#ifndef E2T_EMU
+  if (h->cfg.gemm_backend == E2T_GEMM_SIMT) return false;
+  if (In % 4 != 0) return false;   // Wh^T starts at column In of the packed kernel: 16-byte TMA base
+  return rec::rec_supported(B, H, steps);
+#else
+  (void)h; (void)B; (void)H; (void)In; (void)steps;
+  return false;
+#endif
 }
 
 void encoder_forward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, bool train, uint32_t seed) {
@@ -440,9 +468,21 @@ void encoder_forward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, 
     bool drop = train && c.rnn_dropout > 0.f && l + 1 < c.n_enc_layers;
     DropP dp = make_drop(seed, E2T_STREAM_ENC0 + l, drop ? c.rnn_dropout : 0.f);
     for (int d = 0; d < 2; ++d)
-      lstm_layer_forward(h, inp, ld_in, L.In, L.H, L.KT[d], L.ldkt, Wc + L.b[d], L.gates[d], L.cs[d], L.hs,
-                         drop ? L.hd : nullptr, 2 * L.H, d * L.H, h->d_lens2, T2, B, d == 1, nullptr, nullptr, dp,
-                         2 * L.H);
+      lstm_xproj(h, inp, ld_in, L.In, L.H, L.KT[d], L.ldkt, Wc + L.b[d], L.gates[d], T2, B);
+    if (use_rec(h, B, L.H, L.In, T2)) {
+#ifndef E2T_EMU
+      CatScope cs_(h, E2T_CAT_RECURRENT);
+      prof_begin(h);
+      rec::rec_forward(h->stream, L.gates, L.cs, L.hs, drop ? L.hd : nullptr, L.KT, L.ldkt, L.In, h->d_lens2,
+                       h->rec_counters, T2, B, L.H, dp, 2 * L.H);
+      prof_end(h);
+      ++h->n_launch; ++h->n_launch_tc; ++h->n_launch_rec;
+#endif
+    } else {
+      for (int d = 0; d < 2; ++d)
+        lstm_layer_steps(h, L.In, L.H, L.KT[d], L.ldkt, L.gates[d], L.cs[d], L.hs, drop ? L.hd : nullptr, 2 * L.H,
+                         d * L.H, h->d_lens2, T2, B, d == 1, nullptr, nullptr, dp, 2 * L.H);
+    }
     inp = drop ? L.hd : L.hs;
     ld_in = 2 * L.H;
   }
@@ -576,11 +616,25 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
       EncLayer& Lb = h->enc[l - 1];
       inp = (c.rnn_dropout > 0.f) ? Lb.hd : Lb.hs; ld_in = 2 * Lb.H; d_in = Lb.dhs; ld_din = 2 * Lb.H;
     }
+    const bool top = l == nl - 1;
+    const bool rec_ok = use_rec(h, B, Ly.H, Ly.In, T2);
+    if (rec_ok) {
+#ifndef E2T_EMU
+      CatScope cs_(h, E2T_CAT_RECURRENT);
+      const float* Kd[2] = {P + Ly.K[0], P + Ly.K[1]};
+      const float* csd[2] = {Ly.cs[0], Ly.cs[1]};
+      prof_begin(h);
+      rec::rec_backward(h->stream, Ly.gates, csd, Ly.dhs, Kd, Ly.In, h->d_lens2, top ? h->dc0 : nullptr, c.Hd,
+                        top ? h->d_tlast : nullptr, h->rec_counters, T2, B, Ly.H);
+      prof_end(h);
+      ++h->n_launch; ++h->n_launch_tc; ++h->n_launch_rec;
+#endif
+    }
     for (int d = 0; d < 2; ++d) {
-      bool top = l == nl - 1;
-      lstm_layer_backward(h, Ly.H, P + Ly.K[d], Ly.In, Ly.gates[d], Ly.cs[d], Ly.dhs, 2 * Ly.H, d * Ly.H, h->d_lens2,
-                          T2, B, d == 1, nullptr, top ? h->dc0 + d * Ly.H : nullptr, c.Hd,
-                          (top && d == 0) ? h->d_tlast : nullptr, 0);
+      if (!rec_ok)
+        lstm_layer_backward(h, Ly.H, P + Ly.K[d], Ly.In, Ly.gates[d], Ly.cs[d], Ly.dhs, 2 * Ly.H, d * Ly.H, h->d_lens2,
+                            T2, B, d == 1, nullptr, top ? h->dc0 + d * Ly.H : nullptr, c.Hd,
+                            (top && d == 0) ? h->d_tlast : nullptr, 0);
       lstm_layer_wgrads(h, inp, ld_in, Ly.In, Ly.H, P + Ly.K[d], G + Ly.K[d], G + Ly.b[d], Ly.gates[d], Ly.hs, 2 * Ly.H,
                         d * Ly.H, T2, B, d == 1, nullptr, d_in, ld_din, d == 0 ? 0.f : 1.f);
     }
@@ -926,6 +980,17 @@ extern "C" int e2t_launch_counts(e2t_handle* h, int64_t* total, int64_t* tensor_
   API_BEGIN NEED_H;
   if (total) *total = h->n_launch;
   if (tensor_core) *tensor_core = h->n_launch_tc;
+  API_END
+}
+
+extern "C" int e2t_counter(e2t_handle* h, const char* name, int64_t* value) {
+  API_BEGIN NEED_H;
+  E2T_REQUIRE(name && value, "NULL argument");
+  std::string s(name);
+  if (s == "launches") *value = h->n_launch;
+  else if (s == "tcgen05_launches") *value = h->n_launch_tc;
+  else if (s == "persistent_rnn_launches") *value = h->n_launch_rec;
+  else throw std::runtime_error("e2t: unknown counter '" + s + "'");
   API_END
 }
 

@@ -247,6 +247,11 @@ class Engine:
         self._ck(self._lib.e2t_launch_counts(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
+    def counter(self, name: str) -> int:
+        v = C.c_int64()
+        self._ck(self._lib.e2t_counter(self._h, name.encode(), C.byref(v)))
+        return int(v.value)
+
     def profile_enable(self, on: bool):
         self._ck(self._lib.e2t_profile_enable(self._h, int(on)))
 

@@ -10,6 +10,9 @@ TINY = dict(subnet_ids=(7,), subnet_C=(6,), subnet_W=(4,), E=5, H=(8, 8), D=6, H
 SMALL = dict(subnet_ids=(400,), subnet_C=(32,), subnet_W=(12,), E=20, H=(32, 32, 32), D=12, Hd=64, V=60)
 # aligned shapes (multiples of 4 / 16-byte rows) so that the tcgen05 GEMM path is eligible on the GPU
 MEDIUM = dict(subnet_ids=(400,), subnet_C=(64,), subnet_W=(12,), E=32, H=(64, 64), D=24, Hd=128, V=200)
+# full-width recurrent layers (H = 400 per direction, decoder 800) on a narrow input: exercises the
+# persistent tcgen05 recurrent kernels at the config-2 layer shape while the oracle still runs in seconds
+WIDE = dict(subnet_ids=(400,), subnet_C=(32,), subnet_W=(12,), E=100, H=(400, 400), D=24, Hd=800, V=200)
 TWO_SUBJ = dict(subnet_ids=(400, 401), subnet_C=(6, 10), subnet_W=(4, 3), E=5, H=(8,), D=6, Hd=16, V=11)
 
 
@@ -75,7 +78,10 @@ def check_train_step(lib, geo, B, T, L, ff=0.0, rnn=0.0, seed=3, tol=2e-4, backe
         e = rel_err(v, g[k].numpy())
         worst = max(worst, e)
         assert e <= 5 * tol, (k, e)
+    eng._last_counters = {k: eng.counter(k) for k in ("launches", "tcgen05_launches", "persistent_rnn_launches")}
+    counters = eng._last_counters
     eng.close()
+    check_train_step.last_counters = counters
     return worst
 
 
