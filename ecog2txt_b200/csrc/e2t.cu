@@ -46,8 +46,8 @@ struct EncLayer {
   float *hs = nullptr, *hd = nullptr, *dhs = nullptr;
   float* gates[2] = {nullptr, nullptr};
   float* cs[2] = {nullptr, nullptr};
-  float* KT[2] = {nullptr, nullptr};   // packed [4H, ldkt] transposed kernels (K-major B operand)
-  int ldkt = 0;
+  float* KT[2] = {nullptr, nullptr};   // packed [4H, ldkt] transposed kernels (K-major B operands):
+  int ldkt = 0, In4 = 0;               // Wx^T in columns [0,In), Wh^T in [In4, In4+H), In4 = round_up(In,4)
 };
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -94,6 +94,7 @@ struct e2t_handle {
   float *h0, *c0, *dh0, *dc0, *dh_rec, *dc_rec;
   float *demb, *ddemb, *dgates, *dcs, *hdec, *dhdec, *logits, *loss_rows, *d_loss;
   int* d_ntok;
+  float* colsum_ws = nullptr; i64 colsum_ws_n = 0;   // [64, N] partial column sums
   int* rec_counters = nullptr;   // arrival counters of the persistent recurrent kernels [2][n_bt][T2m]
   int64_t n_launch_rec = 0;
   // decode workspace
@@ -203,6 +204,17 @@ void gemm_conv(e2t_handle* h, int mode, const float* x, const int* lens, int Bsz
   else           { auto kfn = k_gemm<2>; LAUNCH(h, kfn, grid, dim3(256), 0, p); }
 }
 
+// out[n] = sum_m X[m*ld + n]; tall matrices go through a deterministic two-pass partial-sum scratch
+void colsum(e2t_handle* h, const float* X, i64 rows, int N, int ld, float* out) {
+  const int R = 64;
+  if (rows >= 512 && (i64)R * N <= h->colsum_ws_n) {
+    LAUNCH(h, k_colsum, dim3((unsigned)cdiv(N, 32), R), dim3(256), 0, X, rows, N, ld, h->colsum_ws, 0, (i64)N);
+    LAUNCH(h, k_colsum, dim3((unsigned)cdiv(N, 32), 1), dim3(256), 0, h->colsum_ws, (i64)R, N, N, out, 0, (i64)0);
+  } else {
+    LAUNCH(h, k_colsum, dim3((unsigned)cdiv(N, 32), 1), dim3(256), 0, X, rows, N, ld, out, 0, (i64)0);
+  }
+}
+
 DropP make_drop(uint32_t seed, uint32_t stream, float p) {
   DropP d;
   d.key = e2t_stream_key(seed, stream);
@@ -303,7 +315,8 @@ void build_workspace(e2t_handle* h) {
     L.hs = h->alloc<float>(T2 * Bm * 2 * L.H);
     L.dhs = h->alloc<float>(T2 * Bm * 2 * L.H);
     L.hd = (l + 1 < c.n_enc_layers && c.rnn_dropout > 0.f) ? h->alloc<float>(T2 * Bm * 2 * L.H) : nullptr;
-    L.ldkt = round_up(L.In + L.H, 4);
+    L.In4 = round_up(L.In, 4);
+    L.ldkt = L.In4 + round_up(L.H, 4);
     for (int d = 0; d < 2; ++d) {
       L.gates[d] = h->alloc<float>(T2 * Bm * 4 * L.H);
       L.cs[d] = h->alloc<float>(T2 * Bm * L.H);
@@ -320,8 +333,10 @@ void build_workspace(e2t_handle* h) {
   h->logits = h->alloc<float>(Lm * Bm * h->Vp);
   h->loss_rows = h->alloc<float>(Lm * Bm);
   h->d_loss = h->alloc<float>(4); h->d_ntok = h->alloc<int>(4);
+  h->colsum_ws_n = (i64)64 * std::max<i64>(std::max<i64>(4 * Hmax, h->Vp), std::max<i64>(c.E, h->Dp));
+  h->colsum_ws = h->alloc<float>(h->colsum_ws_n);
   h->rec_counters = h->alloc<int>((i64)2 * cdiv(Bm, 128) * std::max<i64>(T2, Lm));
-  h->ld_dec_kt = round_up(c.D + c.Hd, 4);
+  h->ld_dec_kt = h->Dp + round_up(c.Hd, 4);
   h->dec_KT = h->alloc<float>((i64)4 * c.Hd * h->ld_dec_kt);
   h->proj_wT = h->alloc<float>((i64)c.Hd * h->Vp);
   for (int s = 0; s < c.n_subnets; ++s)
@@ -348,8 +363,12 @@ void repack(e2t_handle* h, const float* src, int src_id) {
     LAUNCH(h, k_transpose, grid, dim3(256), 0, in, ldi, out, ldo, K, N);
   };
   for (auto& L : h->enc)
-    for (int d = 0; d < 2; ++d) tr(src + L.K[d], 4 * L.H, L.KT[d], L.ldkt, L.In + L.H, 4 * L.H);
-  tr(src + h->dec_K, 4 * c.Hd, h->dec_KT, h->ld_dec_kt, c.D + c.Hd, 4 * c.Hd);
+    for (int d = 0; d < 2; ++d) {
+      tr(src + L.K[d], 4 * L.H, L.KT[d], L.ldkt, L.In, 4 * L.H);
+      tr(src + L.K[d] + (i64)L.In * 4 * L.H, 4 * L.H, L.KT[d] + L.In4, L.ldkt, L.H, 4 * L.H);
+    }
+  tr(src + h->dec_K, 4 * c.Hd, h->dec_KT, h->ld_dec_kt, c.D, 4 * c.Hd);
+  tr(src + h->dec_K + (i64)c.D * 4 * c.Hd, 4 * c.Hd, h->dec_KT + h->Dp, h->ld_dec_kt, c.Hd, 4 * c.Hd);
   tr(src + h->proj_w, c.Hd, h->proj_wT, h->Vp, c.V, c.Hd);
   for (int s = 0; s < c.n_subnets; ++s) {
     int WC = c.subnet_W[s] * c.subnet_C[s];
@@ -406,10 +425,10 @@ void lstm_xproj(e2t_handle* h, const float* in, int ld_in, int In, int H, const 
 }
 
 // the per-step recurrence (one GEMM + one gate kernel per step): small / unaligned shapes and the decoder
-void lstm_layer_steps(e2t_handle* h, int In, int H, const float* KT, int ldkt, float* gates, float* cs, float* hs,
+void lstm_layer_steps(e2t_handle* h, int In4, int H, const float* KT, int ldkt, float* gates, float* cs, float* hs,
                       float* hd, int ldh, int col0, const int* lens2, int steps, int B, bool reverse,
                       const float* h_init, const float* c_init, DropP dp, int drop_F) {
-  const float* WhT = KT + In;
+  const float* WhT = KT + In4;   // In4 = round_up(In, 4): 16-byte aligned start of Wh^T
   CatScope cs_(h, E2T_CAT_RECURRENT);
   for (int s = 0; s < steps; ++s) {
     int t = reverse ? steps - 1 - s : s;
@@ -434,17 +453,17 @@ void lstm_layer_forward(e2t_handle* h, const float* in, int ld_in, int In, int H
                         int steps, int B, bool reverse, const float* h_init, const float* c_init, DropP dp,
                         int drop_F) {
   lstm_xproj(h, in, ld_in, In, H, KT, ldkt, bias, gates, steps, B);
-  lstm_layer_steps(h, In, H, KT, ldkt, gates, cs, hs, hd, ldh, col0, lens2, steps, B, reverse, h_init, c_init, dp, drop_F);
+  lstm_layer_steps(h, round_up(In, 4), H, KT, ldkt, gates, cs, hs, hd, ldh, col0, lens2, steps, B, reverse, h_init, c_init, dp,
+                   drop_F);
 }
 
 // persistent tcgen05 recurrence usable for a BiLSTM layer of this shape?
-bool use_rec(e2t_handle* h, int B, int H, int In, int steps) {
+bool use_rec(e2t_handle* h, int B, int H, int steps) {
 #ifndef E2T_EMU
   if (h->cfg.gemm_backend == E2T_GEMM_SIMT) return false;
-  if (In % 4 != 0) return false;   // Wh^T starts at column In of the packed kernel: 16-byte TMA base
   return rec::rec_supported(B, H, steps);
 #else
-  (void)h; (void)B; (void)H; (void)In; (void)steps;
+  (void)h; (void)B; (void)H; (void)steps;
   return false;
 #endif
 }
@@ -469,18 +488,18 @@ void encoder_forward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, 
     DropP dp = make_drop(seed, E2T_STREAM_ENC0 + l, drop ? c.rnn_dropout : 0.f);
     for (int d = 0; d < 2; ++d)
       lstm_xproj(h, inp, ld_in, L.In, L.H, L.KT[d], L.ldkt, Wc + L.b[d], L.gates[d], T2, B);
-    if (use_rec(h, B, L.H, L.In, T2)) {
+    if (use_rec(h, B, L.H, T2)) {
 #ifndef E2T_EMU
       CatScope cs_(h, E2T_CAT_RECURRENT);
       prof_begin(h);
-      rec::rec_forward(h->stream, L.gates, L.cs, L.hs, drop ? L.hd : nullptr, L.KT, L.ldkt, L.In, h->d_lens2,
+      rec::rec_forward(h->stream, L.gates, L.cs, L.hs, drop ? L.hd : nullptr, L.KT, L.ldkt, L.In4, h->d_lens2,
                        h->rec_counters, T2, B, L.H, dp, 2 * L.H);
       prof_end(h);
       ++h->n_launch; ++h->n_launch_tc; ++h->n_launch_rec;
 #endif
     } else {
       for (int d = 0; d < 2; ++d)
-        lstm_layer_steps(h, L.In, L.H, L.KT[d], L.ldkt, L.gates[d], L.cs[d], L.hs, drop ? L.hd : nullptr, 2 * L.H,
+        lstm_layer_steps(h, L.In4, L.H, L.KT[d], L.ldkt, L.gates[d], L.cs[d], L.hs, drop ? L.hd : nullptr, 2 * L.H,
                          d * L.H, h->d_lens2, T2, B, d == 1, nullptr, nullptr, dp, 2 * L.H);
     }
     inp = drop ? L.hd : L.hs;
@@ -566,7 +585,7 @@ void lstm_layer_wgrads(e2t_handle* h, const float* in, int ld_in, int In, int H,
     const float* dz0 = reverse ? dz + (i64)(steps - 1) * B * 4 * H : dz;
     gemm(h, h_init, 1, H, dz0, 4 * H, 1, dWh, 4 * H, H, 4 * H, B, nullptr, 1.f);
   }
-  LAUNCH(h, k_colsum, dim3((unsigned)cdiv(4 * H, 32)), dim3(256), 0, dz, rows, 4 * H, 4 * H, db, 0);
+  colsum(h, dz, rows, 4 * H, 4 * H, db);
   // d_in [rows, In] (+)= dz Wx^T ; canonical K rows [In,4H] are the K-major B operand
   if (d_in) gemm(h, dz, 4 * H, 1, K, 1, 4 * H, d_in, ld_din, (int)rows, In, 4 * H, nullptr, beta_din);
 }
@@ -581,7 +600,7 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
   E2T_CHECK(cudaMemsetAsync(G, 0, (size_t)h->n_params * sizeof(float), h->stream));
   // ---- projection: logits already hold dlogits
   gemm(h, h->logits, 1, h->Vp, h->hdec, c.Hd, 1, G + h->proj_w, c.Hd, c.V, c.Hd, (int)rows, nullptr, 0.f);
-  LAUNCH(h, k_colsum, dim3((unsigned)cdiv(c.V, 32)), dim3(256), 0, h->logits, rows, c.V, h->Vp, G + h->proj_b, 0);
+  colsum(h, h->logits, rows, c.V, h->Vp, G + h->proj_b);
   // dhdec [rows,Hd] = dlogits Wp ; B operand (k=v, n=u) = Wp[v*Hd+u] -> packed transpose is the K-major form
   gemm(h, h->logits, h->Vp, 1, h->proj_wT, 1, h->Vp, h->dhdec, c.Hd, (int)rows, c.Hd, c.V, nullptr, 0.f);
   // ---- decoder recurrence
@@ -597,7 +616,7 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
   DropP dpe = make_drop(seed, E2T_STREAM_DEMB, c.ff_dropout);
   LAUNCH(h, k_act_dropout_bwd, grid1(rows * c.D), dim3(256), 0, h->ddemb, h->demb, rows, c.D, h->Dp, c.emb_act, dpe);
   LAUNCH(h, k_embed_bwd, grid1(rows * c.D), dim3(256), 0, h->d_prev, h->ddemb, G + h->demb_w, rows, c.D, h->Dp);
-  LAUNCH(h, k_colsum, dim3((unsigned)cdiv(c.D, 32)), dim3(256), 0, h->ddemb, rows, c.D, h->Dp, G + h->demb_b, 0);
+  colsum(h, h->ddemb, rows, c.D, h->Dp, G + h->demb_b);
   // ---- encoder, top layer first
   const int nl = c.n_enc_layers;
   for (int l = nl - 1; l >= 0; --l) {
@@ -617,7 +636,7 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
       inp = (c.rnn_dropout > 0.f) ? Lb.hd : Lb.hs; ld_in = 2 * Lb.H; d_in = Lb.dhs; ld_din = 2 * Lb.H;
     }
     const bool top = l == nl - 1;
-    const bool rec_ok = use_rec(h, B, Ly.H, Ly.In, T2);
+    const bool rec_ok = use_rec(h, B, Ly.H, T2);
     if (rec_ok) {
 #ifndef E2T_EMU
       CatScope cs_(h, E2T_CAT_RECURRENT);
@@ -644,8 +663,8 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
   LAUNCH(h, k_act_dropout_bwd, grid1((i64)T2 * B * c.E), dim3(256), 0, h->dconv, h->conv_out, (i64)T2 * B, c.E, c.E,
          c.conv_act, dpc);
   gemm_conv(h, 2, in.x, h->d_lens, B, T, C, W, T2, h->dconv, c.E, 1, G + h->conv_w[subnet], c.E, c.E, nullptr, 0.f);
-  LAUNCH(h, k_colsum, dim3((unsigned)cdiv(c.E, 32)), dim3(256), 0, h->dconv, (i64)T2 * B, c.E, c.E,
-         G + h->conv_b[subnet], 0);
+  colsum(h, h->dconv, (i64)T2 * B, c.E, c.E,
+         G + h->conv_b[subnet]);
 }
 
 void read_loss(e2t_handle* h, float* loss_sum, int32_t* ntok) {
@@ -668,7 +687,7 @@ void decode_step(e2t_handle* h, int rows, const int* prev, const float* h_in, co
          c.D, h->Dp, c.emb_act, none);
   const float* KT = h->dec_KT;
   gemm(h, h->g_e, h->Dp, 1, KT, 1, h->ld_dec_kt, h->g_z, 4 * c.Hd, rows, 4 * c.Hd, c.D, Wc + h->dec_b, 0.f);
-  gemm(h, h_in, c.Hd, 1, KT + c.D, 1, h->ld_dec_kt, h->g_z, 4 * c.Hd, rows, 4 * c.Hd, c.Hd, nullptr, 1.f);
+  gemm(h, h_in, c.Hd, 1, KT + h->Dp, 1, h->ld_dec_kt, h->g_z, 4 * c.Hd, rows, 4 * c.Hd, c.Hd, nullptr, 1.f);
   LstmFwdP p{};
   p.z = h->g_z; p.c_prev = c_in; p.c_out = c_out; p.h_out = h_out; p.h_drop = nullptr; p.ldh = c.Hd;
   p.lens2 = nullptr; p.t = 0; p.B = rows; p.H = c.Hd; p.dp = none;

@@ -377,19 +377,27 @@ __global__ void __launch_bounds__(256) k_reduce_loss(const float* loss_row, cons
 // ------------------------------------------------------------------------------------------------
 // column sums (bias gradients): out[n] (+)= sum_m X[m*ld + n].  block = 32 columns x 8 row lanes.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_colsum(const float* X, i64 rows, int N, int ld, float* out, int accumulate) {
+// blockIdx.y splits the rows into gridDim.y contiguous chunks; chunk y writes out[y*out_stride + n]
+// (two deterministic passes for tall matrices: partial sums into a scratch, then a colsum of the scratch).
+__global__ void __launch_bounds__(256) k_colsum(const float* X, i64 rows, int N, int ld, float* out, int accumulate,
+                                                i64 out_stride) {
   __shared__ float part[8][33];
   int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   int n = blockIdx.x * 32 + cx;
+  const i64 chunk = (rows + gridDim.y - 1) / gridDim.y;
+  const i64 m0 = (i64)blockIdx.y * chunk;
+  i64 m1 = m0 + chunk;
+  if (m1 > rows) m1 = rows;
   float s = 0.f;
   if (n < N)
-    for (i64 m = ry; m < rows; m += 8) s += X[m * ld + n];
+    for (i64 m = m0 + ry; m < m1; m += 8) s += X[m * ld + n];
   part[ry][cx] = s;
   __syncthreads();
   if (ry == 0 && n < N) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += part[i][cx];
-    out[n] = accumulate ? out[n] + t : t;
+    float* o = out + (i64)blockIdx.y * out_stride + n;
+    *o = accumulate ? *o + t : t;
   }
 }
 
