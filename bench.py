@@ -246,9 +246,10 @@ def main():
         nprof = 3
         for i in range(nprof):
             step_device(i)
-        cat_ms = {c: eng.profile_read(c) for c in range(4)}
+        cat_ms = {c: eng.profile_read(c) for c in range(6)}
         eng.profile_enable(False)
-        rec_ms, rec_n = cat_ms[0]
+        rec_ms = cat_ms[0][0] + cat_ms[4][0] + cat_ms[5][0]
+        rec_n = cat_ms[0][1] + cat_ms[4][1] + cat_ms[5][1]
         tot = sum(v[0] for v in cat_ms.values())
         achieved = fl["recurrent_train"] * B * nprof / (rec_ms * 1e-3) / 1e12 if rec_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "recurrent LSTM steps (h Wh GEMM + gate kernel, fwd+bwd)",
@@ -256,7 +257,10 @@ def main():
                 "peak_source": psrc + "; operands are tf32/fp32 (nominal tf32 peak is half the bf16 figure)",
                 "launches_per_step": rec_n // nprof, "avg_launch_us": 1e3 * rec_ms / max(rec_n, 1),
                 "share_of_step": rec_ms / tot if tot > 0 else None,
-                "category_ms_per_step": {k: cat_ms[i][0] / nprof for i, k in enumerate(("recurrent", "bulk_gemm", "conv", "other"))},
+                "category_ms_per_step": {k: cat_ms[i][0] / nprof for i, k in enumerate(
+                    ("recurrent_per_step_kernels", "bulk_gemm", "conv", "other", "persistent_rnn_fwd", "persistent_rnn_bwd"))},
+                "persistent_rnn_us_per_launch": {"fwd": 1e3 * cat_ms[4][0] / max(cat_ms[4][1], 1),
+                                                 "bwd": 1e3 * cat_ms[5][0] / max(cat_ms[5][1], 1)},
                 "whole_step_frac_of_peak": (fl["train"] * value / world / 1e12) / peak_tf}
 
     decode = None

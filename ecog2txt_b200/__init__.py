@@ -9,3 +9,4 @@ TOKEN_TYPES = {'phoneme', 'word', 'trial', 'word_sequence', 'word_piece_sequence
 DATA_PARTITIONS = {'training', 'validation', 'testing'}
 
 from .engine import Engine, EngineConfig, E2TError  # noqa: E402,F401
+from .sequence_network import SequenceNetwork  # noqa: E402,F401

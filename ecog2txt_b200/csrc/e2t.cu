@@ -48,6 +48,11 @@ struct EncLayer {
   float* cs[2] = {nullptr, nullptr};
   float* KT[2] = {nullptr, nullptr};   // packed [4H, ldkt] transposed kernels (K-major B operands):
   int ldkt = 0, In4 = 0;               // Wx^T in columns [0,In), Wh^T in [In4, In4+H), In4 = round_up(In,4)
+  // rec = this layer runs on the persistent recurrent kernels: its gate columns are permuted (e2t_gate_perm) in
+  // KT rows, in the packed bias bP and in KP = canonical kernel with permuted columns (backward B operands)
+  bool rec = false;
+  float* KP[2] = {nullptr, nullptr};
+  float* bP[2] = {nullptr, nullptr};
 };
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -95,6 +100,7 @@ struct e2t_handle {
   float *demb, *ddemb, *dgates, *dcs, *hdec, *dhdec, *logits, *loss_rows, *d_loss;
   int* d_ntok;
   float* colsum_ws = nullptr; i64 colsum_ws_n = 0;   // [64, N] partial column sums
+  float* perm_ws = nullptr; i64 perm_ws_n = 0;       // [(In+H+1), 4H] weight + bias gradients in permuted gate order
   int* rec_counters = nullptr;   // arrival counters of the persistent recurrent kernels [2][n_bt][T2m]
   int64_t n_launch_rec = 0;
   // decode workspace
@@ -317,11 +323,19 @@ void build_workspace(e2t_handle* h) {
     L.hd = (l + 1 < c.n_enc_layers && c.rnn_dropout > 0.f) ? h->alloc<float>(T2 * Bm * 2 * L.H) : nullptr;
     L.In4 = round_up(L.In, 4);
     L.ldkt = L.In4 + round_up(L.H, 4);
+#ifndef E2T_EMU
+    L.rec = c.gemm_backend != E2T_GEMM_SIMT && rec::rec_supported((int)Bm, L.H, 1);
+#endif
     for (int d = 0; d < 2; ++d) {
       L.gates[d] = h->alloc<float>(T2 * Bm * 4 * L.H);
       L.cs[d] = h->alloc<float>(T2 * Bm * L.H);
       L.KT[d] = h->alloc<float>((i64)4 * L.H * L.ldkt);
+      if (L.rec) {
+        L.KP[d] = h->alloc<float>((i64)(L.In + L.H) * 4 * L.H);
+        L.bP[d] = h->alloc<float>((i64)4 * L.H);
+      }
     }
+    if (L.rec) h->perm_ws_n = std::max<i64>(h->perm_ws_n, (i64)(L.In + L.H + 1) * 4 * L.H);
   }
   h->h0 = h->alloc<float>(Bm * c.Hd); h->c0 = h->alloc<float>(Bm * c.Hd);
   h->dh0 = h->alloc<float>(Bm * c.Hd); h->dc0 = h->alloc<float>(Bm * c.Hd);
@@ -335,6 +349,7 @@ void build_workspace(e2t_handle* h) {
   h->d_loss = h->alloc<float>(4); h->d_ntok = h->alloc<int>(4);
   h->colsum_ws_n = (i64)64 * std::max<i64>(std::max<i64>(4 * Hmax, h->Vp), std::max<i64>(c.E, h->Dp));
   h->colsum_ws = h->alloc<float>(h->colsum_ws_n);
+  if (h->perm_ws_n) h->perm_ws = h->alloc<float>(h->perm_ws_n);
   h->rec_counters = h->alloc<int>((i64)2 * cdiv(Bm, 128) * std::max<i64>(T2, Lm));
   h->ld_dec_kt = h->Dp + round_up(c.Hd, 4);
   h->dec_KT = h->alloc<float>((i64)4 * c.Hd * h->ld_dec_kt);
@@ -358,14 +373,20 @@ void build_workspace(e2t_handle* h) {
 void repack(e2t_handle* h, const float* src, int src_id) {
   if (!h->packed_dirty && h->packed_src == src_id) return;
   const e2t_config& c = h->cfg;
-  auto tr = [&](const float* in, i64 ldi, float* out, i64 ldo, int K, int N) {
+  auto tr = [&](const float* in, i64 ldi, float* out, i64 ldo, int K, int N, int permH = 0) {
     dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(K, 32));
-    LAUNCH(h, k_transpose, grid, dim3(256), 0, in, ldi, out, ldo, K, N);
+    LAUNCH(h, k_transpose, grid, dim3(256), 0, in, ldi, out, ldo, K, N, permH);
   };
   for (auto& L : h->enc)
     for (int d = 0; d < 2; ++d) {
-      tr(src + L.K[d], 4 * L.H, L.KT[d], L.ldkt, L.In, 4 * L.H);
-      tr(src + L.K[d] + (i64)L.In * 4 * L.H, 4 * L.H, L.KT[d] + L.In4, L.ldkt, L.H, 4 * L.H);
+      const int pH = L.rec ? L.H : 0;
+      tr(src + L.K[d], 4 * L.H, L.KT[d], L.ldkt, L.In, 4 * L.H, pH);
+      tr(src + L.K[d] + (i64)L.In * 4 * L.H, 4 * L.H, L.KT[d] + L.In4, L.ldkt, L.H, 4 * L.H, pH);
+      if (L.rec) {
+        const i64 rows = L.In + L.H;
+        LAUNCH(h, k_permute_cols, grid1(rows * 4 * L.H), dim3(256), 0, src + L.K[d], L.KP[d], rows, 4 * L.H, L.H, 1);
+        LAUNCH(h, k_permute_cols, grid1((i64)4 * L.H), dim3(256), 0, src + L.b[d], L.bP[d], (i64)1, 4 * L.H, L.H, 1);
+      }
     }
   tr(src + h->dec_K, 4 * c.Hd, h->dec_KT, h->ld_dec_kt, c.D, 4 * c.Hd);
   tr(src + h->dec_K + (i64)c.D * 4 * c.Hd, 4 * c.Hd, h->dec_KT + h->Dp, h->ld_dec_kt, c.Hd, 4 * c.Hd);
@@ -458,14 +479,10 @@ void lstm_layer_forward(e2t_handle* h, const float* in, int ld_in, int In, int H
 }
 
 // persistent tcgen05 recurrence usable for a BiLSTM layer of this shape?
-bool use_rec(e2t_handle* h, int B, int H, int steps) {
-#ifndef E2T_EMU
-  if (h->cfg.gemm_backend == E2T_GEMM_SIMT) return false;
-  return rec::rec_supported(B, H, steps);
-#else
-  (void)h; (void)B; (void)H; (void)steps;
-  return false;
-#endif
+bool use_rec(e2t_handle* h, const EncLayer& L, int B, int steps) {
+  (void)h;
+  // decided once per layer at creation (the packed weight layout depends on it); any B <= max_B qualifies
+  return L.rec && B >= 1 && steps >= 1;
 }
 
 void encoder_forward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, bool train, uint32_t seed) {
@@ -487,10 +504,10 @@ void encoder_forward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, 
     bool drop = train && c.rnn_dropout > 0.f && l + 1 < c.n_enc_layers;
     DropP dp = make_drop(seed, E2T_STREAM_ENC0 + l, drop ? c.rnn_dropout : 0.f);
     for (int d = 0; d < 2; ++d)
-      lstm_xproj(h, inp, ld_in, L.In, L.H, L.KT[d], L.ldkt, Wc + L.b[d], L.gates[d], T2, B);
-    if (use_rec(h, B, L.H, T2)) {
+      lstm_xproj(h, inp, ld_in, L.In, L.H, L.KT[d], L.ldkt, L.rec ? L.bP[d] : Wc + L.b[d], L.gates[d], T2, B);
+    if (use_rec(h, L, B, T2)) {
 #ifndef E2T_EMU
-      CatScope cs_(h, E2T_CAT_RECURRENT);
+      CatScope cs_(h, E2T_CAT_REC_FWD);
       prof_begin(h);
       rec::rec_forward(h->stream, L.gates, L.cs, L.hs, drop ? L.hd : nullptr, L.KT, L.ldkt, L.In4, h->d_lens2,
                        h->rec_counters, T2, B, L.H, dp, 2 * L.H);
@@ -636,11 +653,11 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
       inp = (c.rnn_dropout > 0.f) ? Lb.hd : Lb.hs; ld_in = 2 * Lb.H; d_in = Lb.dhs; ld_din = 2 * Lb.H;
     }
     const bool top = l == nl - 1;
-    const bool rec_ok = use_rec(h, B, Ly.H, T2);
+    const bool rec_ok = use_rec(h, Ly, B, T2);
     if (rec_ok) {
 #ifndef E2T_EMU
-      CatScope cs_(h, E2T_CAT_RECURRENT);
-      const float* Kd[2] = {P + Ly.K[0], P + Ly.K[1]};
+      CatScope cs_(h, E2T_CAT_REC_BWD);
+      const float* Kd[2] = {Ly.KP[0], Ly.KP[1]};   // canonical rows, permuted gate columns
       const float* csd[2] = {Ly.cs[0], Ly.cs[1]};
       prof_begin(h);
       rec::rec_backward(h->stream, Ly.gates, csd, Ly.dhs, Kd, Ly.In, h->d_lens2, top ? h->dc0 : nullptr, c.Hd,
@@ -654,8 +671,19 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
         lstm_layer_backward(h, Ly.H, P + Ly.K[d], Ly.In, Ly.gates[d], Ly.cs[d], Ly.dhs, 2 * Ly.H, d * Ly.H, h->d_lens2,
                             T2, B, d == 1, nullptr, top ? h->dc0 + d * Ly.H : nullptr, c.Hd,
                             (top && d == 0) ? h->d_tlast : nullptr, 0);
-      lstm_layer_wgrads(h, inp, ld_in, Ly.In, Ly.H, P + Ly.K[d], G + Ly.K[d], G + Ly.b[d], Ly.gates[d], Ly.hs, 2 * Ly.H,
-                        d * Ly.H, T2, B, d == 1, nullptr, d_in, ld_din, d == 0 ? 0.f : 1.f);
+      if (rec_ok) {
+        // dz is in the permuted gate order: gradients land in a scratch and are un-permuted into the flat buffer
+        float* dKp = h->perm_ws;
+        float* dbp = h->perm_ws + (i64)(Ly.In + Ly.H) * 4 * Ly.H;
+        lstm_layer_wgrads(h, inp, ld_in, Ly.In, Ly.H, Ly.KP[d], dKp, dbp, Ly.gates[d], Ly.hs, 2 * Ly.H, d * Ly.H, T2, B,
+                          d == 1, nullptr, d_in, ld_din, d == 0 ? 0.f : 1.f);
+        const i64 rows = Ly.In + Ly.H;
+        LAUNCH(h, k_permute_cols, grid1(rows * 4 * Ly.H), dim3(256), 0, dKp, G + Ly.K[d], rows, 4 * Ly.H, Ly.H, 0);
+        LAUNCH(h, k_permute_cols, grid1((i64)4 * Ly.H), dim3(256), 0, dbp, G + Ly.b[d], (i64)1, 4 * Ly.H, Ly.H, 0);
+      } else {
+        lstm_layer_wgrads(h, inp, ld_in, Ly.In, Ly.H, P + Ly.K[d], G + Ly.K[d], G + Ly.b[d], Ly.gates[d], Ly.hs, 2 * Ly.H,
+                          d * Ly.H, T2, B, d == 1, nullptr, d_in, ld_din, d == 0 ? 0.f : 1.f);
+      }
     }
   }
   // ---- temporal conv

@@ -452,7 +452,16 @@ __global__ void __launch_bounds__(128) k_greedy_pick(const float* logits, int ld
 // ------------------------------------------------------------------------------------------------
 // tiled transpose: out[n*ldo + k] = in[k*ldi + n] for k < K, n < N  (weight re-packing)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_transpose(const float* in, i64 ldi, float* out, i64 ldo, int K, int N) {
+// Gate-column permutation of the layers run by the persistent recurrent kernels (lstm_rec.cuh): canonical
+// column n = g*H + u  ->  n' = 64*(u/16) + 32*((u%16)/8) + 8*g + (u%8), so that the 4 gates x 8 units one
+// epilogue thread owns are 32 contiguous floats (one 128 B line) of a gates row and 32 contiguous TMEM columns.
+#define E2T_REC_UT 8   /* hidden units per epilogue thread of the persistent kernels */
+__host__ __device__ __forceinline__ int e2t_gate_perm(int n, int H) {
+  int g = n / H, u = n - g * H;
+  return 64 * (u >> 4) + (4 * E2T_REC_UT) * ((u & 15) / E2T_REC_UT) + E2T_REC_UT * g + (u % E2T_REC_UT);
+}
+// permH > 0: output row n is replaced by e2t_gate_perm(n, permH)
+__global__ void __launch_bounds__(256) k_transpose(const float* in, i64 ldi, float* out, i64 ldo, int K, int N, int permH) {
   __shared__ float tile[32][33];
   int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
@@ -463,8 +472,18 @@ __global__ void __launch_bounds__(256) k_transpose(const float* in, i64 ldi, flo
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     int n = n0 + i, k = k0 + tx;
-    if (n < N && k < K) out[(i64)n * ldo + k] = tile[tx][i];
+    if (n < N && k < K) out[(i64)(permH > 0 ? e2t_gate_perm(n, permH) : n) * ldo + k] = tile[tx][i];
   }
+}
+// out[r, perm(n)] = in[r, n] (forward = 1: canonical -> permuted copy) or out[r, n] = in[r, perm(n)] (forward = 0)
+__global__ void k_permute_cols(const float* in, float* out, i64 rows, int N, int permH, int forward) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * N) return;
+  i64 r = i / N;
+  int n = (int)(i - r * N);
+  int np = e2t_gate_perm(n, permH);
+  if (forward) out[r * N + np] = in[i];
+  else out[i] = in[r * N + np];
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -19,6 +19,9 @@
 //
 // warp roles: 0 = TMA producer (+ counter wait), 1 = MMA issuer (+ TMEM owner), 2..5 = epilogue.
 #pragma once
+#include <cstdlib>
+#include <vector>
+
 #include "gemm_tc.cuh"
 
 namespace rec {
@@ -27,18 +30,30 @@ using namespace tc;
 
 constexpr int kU = 16;            // hidden units per CTA
 constexpr int kBM = 128;          // batch rows per CTA
-constexpr int kThreadsRec = 192;
+constexpr int kUT = E2T_REC_UT;   // hidden units per epilogue thread (8: every global access is a full 32 B sector)
+constexpr int kEpiWarps = 4 * (kU / kUT);          // kU/kUT warps per TMEM lane quadrant
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kThreadsRec = 64 + kEpiThreads;      // + TMA producer warp + MMA warp
 constexpr uint32_t A_STAGE_BYTES = kBM * BK * 4;   // 16 KB
 
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
   int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void red_release_gpu(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+// publish the step: make the epilogue's generic-proxy global stores visible (gpu scope, async proxy) and bump the counter
+__device__ __forceinline__ void publish_step(int* ctr, int mode) {
+  if (mode == 0) { fence_proxy_async_all(); red_release_gpu(ctr, 1); }
+  else if (mode == 1) { red_release_gpu(ctr, 1); }
+  else if (mode == 2) { __threadfence(); atomicAdd(ctr, 1); }
+  else { fence_proxy_async_global(); red_release_gpu(ctr, 1); }
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -53,13 +68,48 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 }
 // Bounded wait on a global arrival counter (a lost arrival must trap, not hang the GPU).
 __device__ __forceinline__ void wait_counter(const int* p, int target) {
+  // relaxed polling (an acquire load in the loop costs one L1 invalidation per iteration), one acquire fence after
   const long long t0 = clock64();
-  while (ld_acquire_gpu(p) < target) {
+  while (ld_relaxed_gpu(p) < target) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
+  fence_acq_rel_gpu();
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// n contiguous floats (n % 4 == 0, 16-byte aligned) <-> registers
+template <int N>
+__device__ __forceinline__ void ldv(float* dst, const float* src) {
+#pragma unroll
+  for (int i = 0; i < N / 4; ++i) {
+    const float4 v = *reinterpret_cast<const float4*>(src + 4 * i);
+    dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+  }
+}
+template <int N>
+__device__ __forceinline__ void stv(float* dst, const float* src) {
+#pragma unroll
+  for (int i = 0; i < N / 4; ++i)
+    *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(src[4 * i], src[4 * i + 1], src[4 * i + 2], src[4 * i + 3]);
 }
 template <int NCOL>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v);
+template <>
+__device__ __forceinline__ void tmem_ld_cols<4>(uint32_t taddr, float* v) { tmem_ld4(taddr, v); tmem_ld_wait(); }
+template <>
+__device__ __forceinline__ void tmem_ld_cols<8>(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+  tmem_ld_wait();
+}
+template <>
+__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, float* v) { tmem_ld32(taddr, v); }
 template <>
 __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -78,7 +128,17 @@ __device__ __forceinline__ void tmem_ld_cols<64>(uint32_t taddr, float* v) {
   tmem_ld32(taddr + 32, v + 32);
 }
 
-__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
+// fp32 gate non-linearities on the SFU: ex2.approx + rcp (abs error ~1e-7, far below the tf32 operand rounding)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigm(float x) { return rcp_approx(1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+  // tanh(x) = 1 - 2 / (1 + e^{2x}); saturates cleanly (e^{2x} -> inf gives 1, -> 0 gives -1)
+  return 1.0f - 2.0f * rcp_approx(1.0f + __expf(2.0f * x));
+}
 
 struct RecFwdP {
   float* gates[2];        // [T', B, 4H] x-projection (+bias) in, gate activations out
@@ -89,6 +149,8 @@ struct RecFwdP {
   int* counters;          // [2][n_bt][steps], zeroed before launch
   int steps, B, H, n_bt, n_slices, nkc, stages;
   DropP dp; int drop_F;
+  long long* dbg;         // E2T_REC_DEBUG=1: per-step clock64 stamps of CTA 0 ([steps][8]), else NULL
+  int pub_mode;
 };
 
 struct RecBwdP {
@@ -100,6 +162,8 @@ struct RecBwdP {
   const int* inject_t;                   // fwd direction: time index per row at which to inject (nullable -> 0)
   int* counters;
   int steps, B, H, n_bt, n_slices, nkc, stages;
+  long long* dbg;
+  int pub_mode;
 };
 
 // shared-memory carve (dynamic, 1024-aligned): [W resident: nkc * WCHUNK] [A ring: stages * 16 KB] [barriers]
@@ -137,12 +201,15 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
   const CUtensorMap* map_w = d ? &map_w1 : &map_w0;
   const int steps = p.steps, B = p.B, H = p.H;
   int* counters = p.counters + (size_t)(d * p.n_bt + bt) * steps;
+  const int kc_rot = (int)(((long long)j * p.nkc) / p.n_slices);   // per-CTA starting K chunk
+  long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
+#define REC_STAMP(step, slot) do { if (dbg) dbg[(step) * 8 + (slot)] = clock64(); } while (0)
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     mbar_init(smem_u32(w_bar), 1);
     mbar_init(smem_u32(acc_full), 1);
-    mbar_init(smem_u32(acc_empty), 4);
+    mbar_init(smem_u32(acc_empty), kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -159,8 +226,8 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
       const uint32_t wb = smem_u32(w_bar);
       mbar_expect_tx(wb, (uint32_t)p.nkc * G::WCHUNK);
       for (int kc = 0; kc < p.nkc; ++kc) {
-        if (!BWD) tma_load_3d(smem_u32(smem_w + (size_t)kc * G::WCHUNK), map_w, wb, kc * BK, j * kU, 0);
-        else      tma_load_2d(smem_u32(smem_w + (size_t)kc * G::WCHUNK), map_w, wb, kc * BK, j * kU);
+        // forward: 64 permuted gate rows of Wh^T ; backward: 16 unit rows of Wh (permuted gate columns = K)
+        tma_load_2d(smem_u32(smem_w + (size_t)kc * G::WCHUNK), map_w, wb, kc * BK, j * G::N);
       }
       int it = 0;
       for (int s = 1; s < steps; ++s) {
@@ -171,7 +238,10 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
         else      { const int sf = steps - 1 - s; const int t = reverse ? steps - 1 - sf : sf; t_src = reverse ? t - 1 : t + 1; }
         wait_counter(counters + (s - 1), p.n_slices);
         fence_proxy_async_all();
-        for (int kc = 0; kc < p.nkc; ++kc, ++it) {
+        REC_STAMP(s, 0);
+        for (int kk = 0; kk < p.nkc; ++kk, ++it) {
+          int kc = kk + kc_rot;                       // the K order is free: spread the chain's CTAs over the tile
+          if (kc >= p.nkc) kc -= p.nkc;
           const int st = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(smem_u32(&empty_bar[st]), ph ^ 1);
@@ -179,6 +249,7 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
           mbar_expect_tx(fb, A_STAGE_BYTES);
           tma_load_2d(smem_u32(smem_a + (size_t)st * A_STAGE_BYTES), map_a, fb, kc * BK, t_src * B + bt * kBM);
         }
+        REC_STAMP(s, 1);
       }
     }
   } else if (warp == 1) {
@@ -191,152 +262,149 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
       for (int s = 1; s < steps; ++s) {
         mbar_wait(smem_u32(acc_empty), ((s - 1) & 1) ^ 1);   // epilogue drained the previous accumulator
         fence_after_sync();
-        for (int kc = 0; kc < p.nkc; ++kc, ++it) {
+        for (int kk = 0; kk < p.nkc; ++kk, ++it) {
+          int kc = kk + kc_rot;
+          if (kc >= p.nkc) kc -= p.nkc;
           const int st = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(smem_u32(&full_bar[st]), ph);
           fence_after_sync();
+          if (kk == 0) REC_STAMP(s, 2);
           const uint32_t sa = smem_u32(smem_a + (size_t)st * A_STAGE_BYTES);
           const uint32_t sw = smem_u32(smem_w + (size_t)kc * G::WCHUNK);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
             umma_tf32(tmem_base, make_smem_desc(sa + k * UMMA_K * 4), make_smem_desc(sw + k * UMMA_K * 4), idesc,
-                      (kc > 0 || k > 0) ? 1u : 0u);
+                      (kk > 0 || k > 0) ? 1u : 0u);
           umma_commit(smem_u32(&empty_bar[st]));
         }
         umma_commit(smem_u32(acc_full));
+        REC_STAMP(s, 3);
       }
     }
   } else {
-    // ================= epilogue: thread = batch row, 16 hidden units =================
-    const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
+    // ================= epilogue: thread = (batch row, kUT hidden units) =================
+    // warp w may only read TMEM lanes [32*(w%4), +32): kU/kUT warps per lane quadrant, one per group of kUT units,
+    // so that every scheduler holds several epilogue warps and the gate math (latency-bound in one warp) overlaps.
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int ug = ew >> 2;                          // unit group
     const int r = quad * 32 + lane;
     const int b = bt * kBM + r;
     const bool row_ok = b < B;
-    const int u0 = j * kU;
+    const int u0 = j * kU + ug * kUT;                // first hidden unit of this thread
+    const int z0 = j * 4 * kU + ug * 4 * kUT;        // its 4*kUT contiguous gate columns (permuted layout [ug][gate][kUT])
     const int len2 = row_ok ? (p.lens2 ? p.lens2[b] : steps) : 0;
-    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    float carry[kU];                                 // forward: cell state ; backward: dc through time
+    // TMEM columns follow the B-operand rows: forward [ug][gate][kUT] (4*kUT per thread), backward units (kUT per thread)
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(BWD ? ug * kUT : ug * 4 * kUT);
+    float carry[kUT];                                // forward: cell state ; backward: dc through time
 #pragma unroll
-    for (int i = 0; i < kU; ++i) carry[i] = 0.f;
+    for (int i = 0; i < kUT; ++i) carry[i] = 0.f;
+    const bool publisher = threadIdx.x == 64;
 
     if constexpr (!BWD) {
-      float* gates = p.gates[d];
-      float* cs = p.cs[d];
+      float* gates = d ? p.gates[1] : p.gates[0];
+      float* cs = d ? p.cs[1] : p.cs[0];
       const int col0 = d * H;
       for (int s = 0; s < steps; ++s) {
         const int t = reverse ? steps - 1 - s : s;
         const bool valid = row_ok && t < len2;
-        float* zrow = gates + ((i64)t * B + b) * 4 * H + u0;
-        float4 zx[4][kU / 4];
-        if (valid) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-#pragma unroll
-            for (int q = 0; q < kU / 4; ++q) zx[g][q] = *reinterpret_cast<const float4*>(zrow + (i64)g * H + q * 4);
-        }
-        float acc[4 * kU];
+        float* zrow = gates + ((i64)t * B + b) * 4 * H + z0;   // [gate][kUT] contiguous
+        float z[4 * kUT];
+        if (valid) ldv<4 * kUT>(z, zrow);
+        float acc[4 * kUT];
         if (s > 0) {
           mbar_wait(smem_u32(acc_full), (s - 1) & 1);
           fence_after_sync();
-          tmem_ld_cols<4 * kU>(taddr, acc);
+          if (publisher) REC_STAMP(s, 4);
+          tmem_ld_cols<4 * kUT>(taddr, acc);
           fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(acc_empty));
         } else {
 #pragma unroll
-          for (int i = 0; i < 4 * kU; ++i) acc[i] = 0.f;
+          for (int i = 0; i < 4 * kUT; ++i) acc[i] = 0.f;
         }
+        float hv[kUT];
+        if (valid) {
+#pragma unroll
+          for (int e = 0; e < kUT; ++e) {
+            const float gi = sigm(z[e] + acc[e]);
+            const float gj = tanh_fast(z[kUT + e] + acc[kUT + e]);
+            const float gf = sigm(z[2 * kUT + e] + acc[2 * kUT + e] + 1.0f);
+            const float go = sigm(z[3 * kUT + e] + acc[3 * kUT + e]);
+            const float c = gf * carry[e] + gi * gj;
+            carry[e] = c;
+            hv[e] = go * tanh_fast(c);
+            z[e] = gi; z[kUT + e] = gj; z[2 * kUT + e] = gf; z[3 * kUT + e] = go;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < kUT; ++e) { carry[e] = 0.f; hv[e] = 0.f; }
+        }
+        // 1) the hidden state is all the other CTAs of the chain wait for: store it, then publish
+        if (row_ok) stv<kUT>(p.hs + ((i64)t * B + b) * 2 * H + col0 + u0, hv);
+        if (publisher) REC_STAMP(s, 5);
+        named_bar_sync(1, kEpiThreads);
+        if (publisher) {
+          REC_STAMP(s, 6);
+          // generic-proxy stores of the epilogue warps (ordered by the barrier) -> gpu scope -> async proxy (TMA)
+          publish_step(counters + s, p.pub_mode & 15);
+          REC_STAMP(s, 7);
+        }
+        // 2) everything only the backward pass needs (gate activations, cell state, dropout copy) goes out after
+        //    the release, off the inter-CTA critical path
         if (row_ok) {
-          float hv[kU];
-          if (valid) {
-#pragma unroll
-            for (int q = 0; q < kU / 4; ++q) {
-              float zi[4] = {zx[0][q].x, zx[0][q].y, zx[0][q].z, zx[0][q].w};
-              float zj[4] = {zx[1][q].x, zx[1][q].y, zx[1][q].z, zx[1][q].w};
-              float zf[4] = {zx[2][q].x, zx[2][q].y, zx[2][q].z, zx[2][q].w};
-              float zo[4] = {zx[3][q].x, zx[3][q].y, zx[3][q].z, zx[3][q].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int u = q * 4 + e;
-                const float gi = sigm(zi[e] + acc[u]);
-                const float gj = tanhf(zj[e] + acc[kU + u]);
-                const float gf = sigm(zf[e] + acc[2 * kU + u] + 1.0f);
-                const float go = sigm(zo[e] + acc[3 * kU + u]);
-                const float c = gf * carry[u] + gi * gj;
-                carry[u] = c;
-                hv[u] = go * tanhf(c);
-                zi[e] = gi; zj[e] = gj; zf[e] = gf; zo[e] = go;
-              }
-              *reinterpret_cast<float4*>(zrow + q * 4) = make_float4(zi[0], zi[1], zi[2], zi[3]);
-              *reinterpret_cast<float4*>(zrow + (i64)H + q * 4) = make_float4(zj[0], zj[1], zj[2], zj[3]);
-              *reinterpret_cast<float4*>(zrow + (i64)2 * H + q * 4) = make_float4(zf[0], zf[1], zf[2], zf[3]);
-              *reinterpret_cast<float4*>(zrow + (i64)3 * H + q * 4) = make_float4(zo[0], zo[1], zo[2], zo[3]);
-            }
-          } else {
-#pragma unroll
-            for (int u = 0; u < kU; ++u) { carry[u] = 0.f; hv[u] = 0.f; }
-          }
-          float* crow = cs + ((i64)t * B + b) * H + u0;
-          float* hrow = p.hs + ((i64)t * B + b) * 2 * H + col0 + u0;
-#pragma unroll
-          for (int q = 0; q < kU / 4; ++q) {
-            *reinterpret_cast<float4*>(crow + q * 4) = make_float4(carry[q * 4], carry[q * 4 + 1], carry[q * 4 + 2], carry[q * 4 + 3]);
-            *reinterpret_cast<float4*>(hrow + q * 4) = make_float4(hv[q * 4], hv[q * 4 + 1], hv[q * 4 + 2], hv[q * 4 + 3]);
-          }
+          if (valid) stv<4 * kUT>(zrow, z);
+          stv<kUT>(cs + ((i64)t * B + b) * H + u0, carry);
           if (p.hd) {
-            float* drow = p.hd + ((i64)t * B + b) * 2 * H + col0 + u0;
             const uint32_t idx0 = (uint32_t)(((i64)t * B + b) * p.drop_F + col0 + u0);
+            const uint32_t key = p.dp.key, thresh = p.dp.thresh;
+            const float inv = p.dp.inv;
+            float o[kUT];
 #pragma unroll
-            for (int u = 0; u < kU; ++u)
-              drow[u] = (valid && e2t_keep(p.dp.key, idx0 + u, p.dp.thresh)) ? hv[u] * p.dp.inv : 0.f;
+            for (int e = 0; e < kUT; ++e) o[e] = (valid && e2t_keep(key, idx0 + e, thresh)) ? hv[e] * inv : 0.f;
+            stv<kUT>(p.hd + ((i64)t * B + b) * 2 * H + col0 + u0, o);
           }
-        }
-        // publish: generic-proxy stores -> visible to the async proxy (TMA) of every CTA in the chain
-        fence_proxy_async_all();
-        named_bar_sync(1, 128);
-        if (threadIdx.x == 64) {
-          __threadfence();
-          red_release_gpu(counters + s, 1);
         }
       }
     } else {
-      float* gates = p.gates[d];
-      const float* cs = p.cs[d];
+      float* gates = d ? p.gates[1] : p.gates[0];
+      const float* cs = d ? p.cs[1] : p.cs[0];
       const int col0 = d * H;
       for (int q = 0; q < steps; ++q) {
         const int sf = steps - 1 - q;                       // forward-order step index being differentiated
         const int t = reverse ? steps - 1 - sf : sf;
         const int tp = reverse ? t + 1 : t - 1;             // step processed before t in the forward pass
         const bool valid = row_ok && t < len2;
-        float* zrow = gates + ((i64)t * B + b) * 4 * H + u0;
-        float4 gz[4][kU / 4], cc[kU / 4], cp[kU / 4], dho[kU / 4];
+        float* zrow = gates + ((i64)t * B + b) * 4 * H + z0;
+        float gz[4 * kUT], cv[kUT], cpv[kUT], dhv[kUT];
         if (valid) {
+          ldv<4 * kUT>(gz, zrow);
+          ldv<kUT>(cv, cs + ((i64)t * B + b) * H + u0);
+          if (sf > 0) ldv<kUT>(cpv, cs + ((i64)tp * B + b) * H + u0);
+          else {
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
+            for (int e = 0; e < kUT; ++e) cpv[e] = 0.f;
+          }
+          if (p.dhs) ldv<kUT>(dhv, p.dhs + ((i64)t * B + b) * 2 * H + col0 + u0);
+          else {
 #pragma unroll
-            for (int w = 0; w < kU / 4; ++w) gz[g][w] = *reinterpret_cast<const float4*>(zrow + (i64)g * H + w * 4);
-          const float* crow = cs + ((i64)t * B + b) * H + u0;
-#pragma unroll
-          for (int w = 0; w < kU / 4; ++w) {
-            cc[w] = *reinterpret_cast<const float4*>(crow + w * 4);
-            cp[w] = sf > 0 ? *reinterpret_cast<const float4*>(cs + ((i64)tp * B + b) * H + u0 + w * 4)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-            dho[w] = p.dhs ? *reinterpret_cast<const float4*>(p.dhs + ((i64)t * B + b) * 2 * H + col0 + u0 + w * 4)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int e = 0; e < kUT; ++e) dhv[e] = 0.f;
           }
         }
-        float acc[kU];
+        float acc[kUT];
         if (q > 0) {
           mbar_wait(smem_u32(acc_full), (q - 1) & 1);
           fence_after_sync();
-          tmem_ld_cols<kU>(taddr, acc);
+          if (publisher) REC_STAMP(q, 4);
+          tmem_ld_cols<kUT>(taddr, acc);
           fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(acc_empty));
         } else {
 #pragma unroll
-          for (int i = 0; i < kU; ++i) acc[i] = 0.f;
+          for (int i = 0; i < kUT; ++i) acc[i] = 0.f;
         }
         if (row_ok) {
           if (valid) {
@@ -346,49 +414,33 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
               inject = ti == t;
             }
 #pragma unroll
-            for (int w = 0; w < kU / 4; ++w) {
-              const float gi[4] = {gz[0][w].x, gz[0][w].y, gz[0][w].z, gz[0][w].w};
-              const float gj[4] = {gz[1][w].x, gz[1][w].y, gz[1][w].z, gz[1][w].w};
-              const float gf[4] = {gz[2][w].x, gz[2][w].y, gz[2][w].z, gz[2][w].w};
-              const float go[4] = {gz[3][w].x, gz[3][w].y, gz[3][w].z, gz[3][w].w};
-              const float cv[4] = {cc[w].x, cc[w].y, cc[w].z, cc[w].w};
-              const float cpv[4] = {cp[w].x, cp[w].y, cp[w].z, cp[w].w};
-              const float dhv[4] = {dho[w].x, dho[w].y, dho[w].z, dho[w].w};
-              float di[4], dj[4], df[4], dO[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int u = w * 4 + e;
-                const float dh = dhv[e] + acc[u];
-                float dc = carry[u];
-                if (inject) dc += p.dc_inject[(i64)b * p.ldi + col0 + u0 + u];
-                const float tc_ = tanhf(cv[e]);
-                dO[e] = dh * tc_ * go[e] * (1.f - go[e]);
-                dc += dh * go[e] * (1.f - tc_ * tc_);
-                di[e] = dc * gj[e] * gi[e] * (1.f - gi[e]);
-                dj[e] = dc * gi[e] * (1.f - gj[e] * gj[e]);
-                df[e] = dc * cpv[e] * gf[e] * (1.f - gf[e]);
-                carry[u] = dc * gf[e];
-              }
-              *reinterpret_cast<float4*>(zrow + w * 4) = make_float4(di[0], di[1], di[2], di[3]);
-              *reinterpret_cast<float4*>(zrow + (i64)H + w * 4) = make_float4(dj[0], dj[1], dj[2], dj[3]);
-              *reinterpret_cast<float4*>(zrow + (i64)2 * H + w * 4) = make_float4(df[0], df[1], df[2], df[3]);
-              *reinterpret_cast<float4*>(zrow + (i64)3 * H + w * 4) = make_float4(dO[0], dO[1], dO[2], dO[3]);
+            for (int e = 0; e < kUT; ++e) {
+              const float gi = gz[e], gj = gz[kUT + e], gf = gz[2 * kUT + e], go = gz[3 * kUT + e];
+              const float dh = dhv[e] + acc[e];
+              float dc = carry[e];
+              if (inject) dc += p.dc_inject[(i64)b * p.ldi + col0 + u0 + e];
+              const float tc_ = tanh_fast(cv[e]);
+              gz[3 * kUT + e] = dh * tc_ * go * (1.f - go);
+              dc += dh * go * (1.f - tc_ * tc_);
+              gz[e] = dc * gj * gi * (1.f - gi);
+              gz[kUT + e] = dc * gi * (1.f - gj * gj);
+              gz[2 * kUT + e] = dc * cpv[e] * gf * (1.f - gf);
+              carry[e] = dc * gf;
             }
           } else {
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
+            for (int i = 0; i < 4 * kUT; ++i) gz[i] = 0.f;
 #pragma unroll
-              for (int w = 0; w < kU / 4; ++w) *reinterpret_cast<float4*>(zrow + (i64)g * H + w * 4) = z4;
-#pragma unroll
-            for (int u = 0; u < kU; ++u) carry[u] = 0.f;
+            for (int e = 0; e < kUT; ++e) carry[e] = 0.f;
           }
+          stv<4 * kUT>(zrow, gz);
         }
-        fence_proxy_async_all();
-        named_bar_sync(1, 128);
-        if (threadIdx.x == 64) {
-          __threadfence();
-          red_release_gpu(counters + q, 1);
+        if (publisher) REC_STAMP(q, 5);
+        named_bar_sync(1, kEpiThreads);
+        if (publisher) {
+          REC_STAMP(q, 6);
+          publish_step(counters + q, p.pub_mode & 15);
+          REC_STAMP(q, 7);
         }
       }
     }
@@ -462,9 +514,34 @@ inline void rec_launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap
     attr_smem = smem;
   }
   E2T_CHECK(cudaMemsetAsync(p.counters, 0, (size_t)2 * p.n_bt * p.steps * sizeof(int), st));
+  // diagnostic: E2T_REC_DEBUG=<n> prints the per-step clock64 timeline of CTA 0 for the first n launches
+  static int dbg_left = getenv("E2T_REC_DEBUG") ? atoi(getenv("E2T_REC_DEBUG")) : 0;
+  p.dbg = nullptr;
+  static int pub_mode = getenv("E2T_REC_PUB") ? atoi(getenv("E2T_REC_PUB")) : 3;
+  p.pub_mode = pub_mode;
+  if (dbg_left > 0) {
+    E2T_CHECK(cudaMalloc(&p.dbg, (size_t)p.steps * 8 * sizeof(long long)));
+    E2T_CHECK(cudaMemsetAsync(p.dbg, 0, (size_t)p.steps * 8 * sizeof(long long), st));
+  }
   void* args[] = {(void*)&a0, (void*)&a1, (void*)&w0, (void*)&w1, (void*)&p};
   dim3 grid((unsigned)(2 * p.n_bt * p.n_slices));
   E2T_CHECK(cudaLaunchCooperativeKernel((const void*)kfn, grid, dim3(kThreadsRec), args, smem, st));
+  if (p.dbg) {
+    --dbg_left;
+    std::vector<long long> hst((size_t)p.steps * 8);
+    E2T_CHECK(cudaStreamSynchronize(st));
+    E2T_CHECK(cudaMemcpy(hst.data(), p.dbg, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.dbg);
+    fprintf(stderr, "[rec %s] steps=%d B=%d H=%d nkc=%d stages=%d grid=%u  (cycles rel. to flag-seen of each step)\n"
+                    "  step  flag->tma_issued  ->first_full  ->mma_committed  ->acc_seen  ->h_stored  ->bar_passed  ->released | step_total\n",
+            BWD ? "bwd" : "fwd", p.steps, p.B, p.H, p.nkc, p.stages, grid.x);
+    for (int s = 1; s < p.steps; ++s) {
+      const long long* e = &hst[(size_t)s * 8];
+      const long long prev = s > 1 ? hst[(size_t)(s - 1) * 8] : 0;
+      fprintf(stderr, "  %4d  %8lld %8lld %8lld %8lld %8lld %8lld %8lld | %8lld\n", s, e[1] - e[0], e[2] - e[0], e[3] - e[0],
+              e[4] - e[0], e[5] - e[0], e[6] - e[0], e[7] ? e[7] - e[0] : 0, prev ? e[0] - prev : 0);
+    }
+  }
 }
 
 // Forward of one BiLSTM layer.  KT[d]: packed transposed kernels [4H, ldkt] (Wh^T at column In).
@@ -484,10 +561,10 @@ inline void rec_forward(cudaStream_t st, float* const gates[2], float* const cs[
     const i64 adims[2] = {H, (i64)steps * B}, astr[2] = {1, 2 * (i64)H};
     const int abox[2] = {BK, kBM};
     ma[d] = make_map_nd(hs + (i64)d * H, 2, adims, astr, abox);
-    // W: Wh^T viewed as (k, u, gate): element (k,u,g) at KT[(g*H+u)*ldkt + In + k]
-    const i64 wdims[3] = {H, H, 4}, wstr[3] = {1, (i64)ldkt, (i64)H * ldkt};
-    const int wbox[3] = {BK, kU, 4};
-    mw[d] = make_map_nd(KT[d] + In, 3, wdims, wstr, wbox);
+    // W: Wh^T rows in the permuted gate order (64 consecutive rows = the 4 gates of one CTA's 16 units)
+    const i64 wdims[2] = {H, 4 * (i64)H}, wstr[2] = {1, (i64)ldkt};
+    const int wbox[2] = {BK, 4 * kU};
+    mw[d] = make_map_nd(KT[d] + In, 2, wdims, wstr, wbox);
   }
   rec_launch<false>(st, ma[0], ma[1], mw[0], mw[1], p);
 }

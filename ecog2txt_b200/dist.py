@@ -13,9 +13,14 @@ class _DevBuf:
 
 
 def flat_tensor(engine, which: int = L.GRAD):
-    """torch view (no copy) of one of the engine's flat parameter-sized device buffers."""
+    """torch view (no copy) of one of the engine's flat parameter-sized buffers (device memory; host memory
+    only for the test-only kernel-emulation build, whose "device" buffers are malloc'ed)."""
     import torch
     ptr, n = engine.flat_buffer(which)
+    if getattr(engine, "emulated", False):
+        import ctypes
+        import numpy as np
+        return torch.from_numpy(np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_float)), shape=(n,)))
     return torch.as_tensor(_DevBuf(ptr, n), device=torch.device("cuda", engine.cfg.device))
 
 

@@ -91,6 +91,7 @@ class Engine:
     def __init__(self, cfg: EngineConfig, lib: Optional[C.CDLL] = None):
         self.cfg = cfg
         self._lib = lib if lib is not None else L.load()
+        self.emulated = lib is not None
         self._h = C.c_void_p()
         cc = cfg.to_c()
         if self._lib.e2t_create(C.byref(cc), C.byref(self._h)) != 0:

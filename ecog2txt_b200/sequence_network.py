@@ -1,0 +1,247 @@
+"""``SequenceNetwork`` -- the drop-in class for the slot the reference fills with
+``machine_learning.neural_networks.sequence_networks.SequenceNetwork`` (imported at
+/root/reference/ecog2txt/trainers.py:33).  Same constructor keywords, attributes and methods as observed from
+the reference's call sites:
+
+* ctor                         trainers.py:126-135  (manifest-defaulted keys: yaml :3-5,11-12,25,29,62-75,88)
+* ``fit``                      trainers.py:309-318,341-367 (train_vars_scope / reuse_vars_scope / _restore_epoch)
+* ``restore_and_assess``       trainers.py:379-380 ; plotters.py:631-636
+* ``get_weights_as_numpy_array`` trainers.py:699-700,750-751
+* attributes                   checkpoint_path, N_epochs, layer_sizes, TEMPORALLY_CONVOLVE, EMA_decay, FF_dropout,
+                               RNN_dropout, assessment_epoch_interval, beam_width, temperature
+
+All arithmetic happens in libe2t.so (CUDA, sm_100a) behind the C-ABI; this file is the host-side epoch loop
+(the reference's tfh.GraphBuilder train/assess cadence, trainers.py:852-859), the TFRecord batch assembly and
+the host metrics.  Under torch.distributed every minibatch is sharded across ranks with one all-reduce of the
+flat gradient buffer per step.
+"""
+from __future__ import annotations
+
+import os
+import re
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import EOS_token as _EOS, OOV_token as _OOV, pad_token as _PAD, _lib
+from . import params as prm
+from . import tfrecord
+from .dist import allreduce_grads, flat_tensor, shard_range
+from .engine import Engine, EngineConfig
+from .metrics import target_inds_to_sequences, wer_vector
+
+_MANIFEST_KEYS = dict(layer_sizes=None, FF_dropout=0.0, RNN_dropout=0.0, TEMPORALLY_CONVOLVE=True, EMA_decay=0.99,
+                      N_epochs=800, beam_width=1, temperature=1.0, assessment_epoch_interval=10,
+                      tf_summaries_dir=None)
+
+
+class SequenceNetwork:
+    def __init__(self, manifest, EOS_token=_EOS, pad_token=_PAD, OOV_token=_OOV, training_GPUs=(0,),
+                 TARGETS_ARE_SEQUENCES=True, VERBOSE=True, N_cases=256, max_hyp_length=20, learning_rate=5e-4,
+                 seed=1, gemm_backend="auto", lib=None, **kwargs):
+        # utils_jgm.auto_attribute(CHECK_MANIFEST=True): a keyword wins, else manifest[key] (README.md:42)
+        for key, default in _MANIFEST_KEYS.items():
+            if key in kwargs and kwargs[key] is not None:
+                val = kwargs.pop(key)
+            elif manifest is not None and key in manifest:
+                val = manifest[key]
+            else:
+                val = default
+            setattr(self, key, val)
+        if kwargs:
+            raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
+        if self.layer_sizes is None:
+            raise ValueError("layer_sizes must come from the manifest or a keyword")
+        if not self.TEMPORALLY_CONVOLVE:
+            raise NotImplementedError("this engine implements the temporally-convolving encoder only "
+                                      "(TEMPORALLY_CONVOLVE: true in every shipped manifest)")
+        self.EOS_token, self.pad_token, self.OOV_token = EOS_token, pad_token, OOV_token
+        self.training_GPUs = list(training_GPUs)
+        self.assessment_GPU = self.training_GPUs[0]
+        self.TARGETS_ARE_SEQUENCES = TARGETS_ARE_SEQUENCES
+        self.VERBOSE = VERBOSE
+        self.N_cases, self.max_hyp_length, self.learning_rate, self.seed = N_cases, max_hyp_length, learning_rate, seed
+        self.gemm_backend = gemm_backend
+        self.checkpoint_path: Optional[str] = None
+        self.inputs_to_occlude = None
+        self._lib = lib
+        self._engine: Optional[Engine] = None
+        self._engine_key = None
+
+    # ------------------------------------------------------------------------------------------
+    def vprint(self, *a, **k):
+        if self.VERBOSE:
+            print(*a, **k)
+
+    def _geometry(self, subnets_params):
+        ls = self.layer_sizes
+        first = subnets_params[0].data_manifests
+        V = int(first['decoder_targets'].num_features)
+        flist = first['decoder_targets'].get_feature_list()
+        geo = dict(
+            subnet_ids=tuple(int(s.subnet_id) for s in subnets_params),
+            subnet_C=tuple(int(s.data_manifests['encoder_inputs'].num_features) for s in subnets_params),
+            subnet_W=tuple(int(s.decimation_factor) for s in subnets_params),
+            E=int(ls['encoder_embedding'][0]), H=tuple(int(h) for h in ls['encoder_rnn']),
+            D=int(ls['decoder_embedding'][0]), Hd=int(ls['decoder_rnn'][0]), V=V,
+            pad_id=flist.index(self.pad_token) if self.pad_token in flist else 0,
+            eos_id=flist.index(self.EOS_token), start_id=flist.index(self.EOS_token),
+        )
+        if ls.get('decoder_projection'):
+            raise NotImplementedError("hidden decoder_projection layers are not built (empty in the shipped manifests)")
+        return geo, flist
+
+    def _get_engine(self, subnets_params, max_T, max_L) -> Engine:
+        geo, flist = self._geometry(subnets_params)
+        key = (tuple(sorted(geo.items())), self.FF_dropout, self.RNN_dropout, self.EMA_decay)
+        e = self._engine
+        if e is None or self._engine_key != key or e.cfg.max_T < max_T or e.cfg.max_L < max_L:
+            if e is not None:
+                e.close()
+            dev = self.training_GPUs[0]
+            cfg = EngineConfig(**geo, max_B=self.N_cases, max_T=max_T, max_L=max(max_L, self.max_hyp_length),
+                               max_beam=max(int(self.beam_width), 1), ff_dropout=float(self.FF_dropout),
+                               rnn_dropout=float(self.RNN_dropout), lr=self.learning_rate,
+                               ema_decay=float(self.EMA_decay), gemm_backend=self.gemm_backend, device=dev)
+            self._engine = Engine(cfg, lib=self._lib)
+            prm.init_engine(self._engine, self.seed)
+            self._engine_key = key
+        self._targets_list = flist
+        return self._engine
+
+    # -- data ----------------------------------------------------------------------------------
+    @staticmethod
+    def _load_partition(subject, partition):
+        """[(x [T,C] fp32, y [L] int32)] for every trial of the partition's blocks (trainers.py:891-901)."""
+        mans = {k: subject.data_manifests[k] for k in ('encoder_inputs', 'decoder_targets')}
+        paths = [subject.tf_record_partial_path.format(b) for b in sorted(subject.block_ids[partition])]
+        return [(ex['encoder_inputs'], ex['decoder_targets']) for ex in tfrecord.read_examples(paths, mans)]
+
+    @staticmethod
+    def _batch(examples, idx, T_pad, L_pad, pad_id):
+        x = tfrecord.pad_batch_f32([examples[i][0] for i in idx], T_pad)
+        y = np.full((len(idx), L_pad), pad_id, np.int32)
+        for r, i in enumerate(idx):
+            t = examples[i][1]
+            y[r, :len(t)] = t
+        return x, y
+
+    # -- fit -----------------------------------------------------------------------------------
+    def fit(self, subnets_params, train_vars_scope='seq2seq', reuse_vars_scope=None, _restore_epoch=None):
+        """Train N_epochs on the subjects jointly (one subject per minibatch, App. D item 11); every
+        assessment_epoch_interval epochs decode training / validation data with the EMA weights and checkpoint.
+        Returns {'training'|'validation': struct(.decoder_accuracies, .decoder_word_error_rates, ...)}."""
+        import torch.distributed as dist
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+        data = {s.subnet_id: {p: self._load_partition(s, p) for p in ('training', 'validation')} for s in subnets_params}
+        max_T = max(x.shape[0] for d in data.values() for part in d.values() for x, _ in part)
+        max_L = max(len(y) for d in data.values() for part in d.values() for _, y in part)
+        eng = self._get_engine(subnets_params, max_T, max_L)
+        pad_id = eng.cfg.pad_id
+        start_epoch = 0
+        if _restore_epoch is not None and _restore_epoch > 0:
+            prm.load_checkpoint(eng, self.checkpoint_path, _restore_epoch, reuse_vars_scope=reuse_vars_scope)
+            start_epoch = _restore_epoch
+        pat = re.compile(train_vars_scope or 'seq2seq')
+        for name in eng.tensors():
+            eng.set_trainable(name, bool(pat.match(name)))
+        grads = flat_tensor(eng, _lib.GRAD) if world > 1 else None
+        rs = np.random.RandomState(self.seed + 17 + start_epoch)
+        n_assess = self.N_epochs // self.assessment_epoch_interval
+        assessments = {p: SimpleNamespace(decoder_accuracies=np.zeros(n_assess), decoder_word_error_rates=np.zeros(n_assess),
+                                          decoder_confusions=None, epochs=np.zeros(n_assess, int), losses=np.zeros(n_assess))
+                       for p in ('training', 'validation')}
+        step = eng.step
+        for epoch in range(start_epoch, start_epoch + self.N_epochs):
+            # minibatches: (subject index, example indices); all ranks draw the same order, then shard each batch
+            plan = []
+            for si, s in enumerate(subnets_params):
+                order = rs.permutation(len(data[s.subnet_id]['training']))
+                plan += [(si, order[i:i + self.N_cases]) for i in range(0, len(order), self.N_cases)]
+            order = rs.permutation(len(plan))
+            ep_loss, ep_tok = 0.0, 0
+            for pi in order:
+                si, idx = plan[pi]
+                lo, hi = shard_range(len(idx), rank, world)
+                if hi > lo:
+                    x, y = self._batch(data[subnets_params[si].subnet_id]['training'], idx[lo:hi], max_T, max_L, pad_id)
+                    loss, ntok = eng.train_step_grads(x, None, y, subnet=si, seed=step)
+                else:   # fewer utterances than ranks: contribute zero gradients
+                    flat_tensor(eng, _lib.GRAD).zero_()
+                    loss, ntok = 0.0, 0
+                ntok_g = allreduce_grads(eng, grads, float(ntok)) if world > 1 else float(ntok)
+                eng.adam_ema_step(1.0 / max(ntok_g, 1.0), subnet=si)
+                step += 1
+                ep_loss += loss
+                ep_tok += ntok
+            done = epoch + 1 - start_epoch
+            if done % self.assessment_epoch_interval == 0:
+                k = done // self.assessment_epoch_interval - 1
+                for part in ('training', 'validation'):
+                    res = self._assess(eng, subnets_params, data, part, max_T, max_L)
+                    a = assessments[part]
+                    a.decoder_accuracies[k], a.decoder_word_error_rates[k] = res.accuracy, res.word_error_rate
+                    a.epochs[k], a.losses[k] = epoch + 1, ep_loss / max(ep_tok, 1)
+                self.vprint(f"epoch {epoch + 1}: train loss/token {ep_loss / max(ep_tok, 1):.4f}  "
+                            f"WER train {assessments['training'].decoder_word_error_rates[k]:.3f} "
+                            f"valid {assessments['validation'].decoder_word_error_rates[k]:.3f}")
+                if self.checkpoint_path and rank == 0:
+                    prm.save_checkpoint(eng, self.checkpoint_path, epoch + 1)
+        if self.checkpoint_path and rank == 0 and self.N_epochs % self.assessment_epoch_interval:
+            prm.save_checkpoint(eng, self.checkpoint_path, start_epoch + self.N_epochs)
+        return assessments
+
+    # -- assessment ----------------------------------------------------------------------------
+    def _assess(self, eng, subnets_params, data, partition, max_T, max_L):
+        """Decode (greedy if beam_width == 1, else beam) with the EMA weights; WER over the last subject's trials
+        like the reference's assessor (one subnet's validation data, trainers.py:838-849)."""
+        s = subnets_params[-1]
+        si = len(subnets_params) - 1
+        examples = data[s.subnet_id][partition]
+        pad_id, eos_id = eng.cfg.pad_id, eng.cfg.eos_id
+        refs, hyps, n_ok, n_tok = [], [], 0, 0
+        Lh = max(self.max_hyp_length, max_L)
+        for i in range(0, len(examples), self.N_cases):
+            idx = np.arange(i, min(i + self.N_cases, len(examples)))
+            x, y = self._batch(examples, idx, max_T, max_L, pad_id)
+            if int(self.beam_width) > 1:
+                toks, _ = eng.beam_decode(x, None, beam=int(self.beam_width), max_len=Lh, subnet=si, use_ema=True,
+                                          temperature=float(self.temperature))
+            else:
+                t, _ = eng.greedy_decode(x, None, max_len=Lh, subnet=si, use_ema=True,
+                                         temperature=float(self.temperature), want_logp=False)
+                toks = t[:, None, :]
+            for r in range(len(idx)):
+                refs.append(target_inds_to_sequences(y[r][None, None, :], self._targets_list)[0])
+                hyps.append(target_inds_to_sequences(toks[r:r + 1], self._targets_list)[0])
+                m = y[r] != pad_id
+                n_ok += int((toks[r, 0, :max_L][m] == y[r][m]).sum())
+                n_tok += int(m.sum())
+        wers = wer_vector(refs, hyps) if refs else np.zeros(0)
+        return SimpleNamespace(word_error_rate=float(wers.mean()) if len(wers) else float('nan'),
+                               accuracy=n_ok / max(n_tok, 1), references=refs, hypotheses=hyps,
+                               word_error_rates=wers)
+
+    def restore_and_assess(self, subnets_params, restore_epoch, WRITE=False, data_partitions=('training', 'validation')):
+        data = {s.subnet_id: {p: self._load_partition(s, p) for p in data_partitions} for s in subnets_params}
+        max_T = max(x.shape[0] for d in data.values() for part in d.values() for x, _ in part)
+        max_L = max(len(y) for d in data.values() for part in d.values() for _, y in part)
+        eng = self._get_engine(subnets_params, max_T, max_L)
+        prm.load_checkpoint(eng, self.checkpoint_path, restore_epoch, reuse_vars_scope='seq2seq')
+        return {p: self._assess(eng, subnets_params, data, p, max_T, max_L) for p in data_partitions}
+
+    def get_weights_as_numpy_array(self, full_var_name, restore_epoch):
+        """The stored variable (or its `/ExponentialMovingAverage` shadow) from checkpoint `restore_epoch`."""
+        with np.load(f"{self.checkpoint_path}-{restore_epoch}.npz") as z:
+            return np.array(z[full_var_name])
+
+    # -- online predictor (construct_online_predictor, trainers.py:925-949) ---------------------------
+    def predict(self, inputs: np.ndarray, subnet: int = 0) -> str:
+        """One utterance [T, C] -> decoded sentence with the EMA weights (greedy)."""
+        eng = self._engine
+        if eng is None:
+            raise RuntimeError("fit or restore_and_assess first")
+        x = np.ascontiguousarray(inputs[None], np.float32)
+        toks, _ = eng.greedy_decode(x, None, max_len=self.max_hyp_length, subnet=subnet, use_ema=True, want_logp=False)
+        return target_inds_to_sequences(toks[:, None, :], self._targets_list)[0]

@@ -150,6 +150,8 @@ int e2t_counter(e2t_handle* h, const char* name, int64_t* value);
 #define E2T_CAT_BULK_GEMM 1
 #define E2T_CAT_CONV 2
 #define E2T_CAT_OTHER 3
+#define E2T_CAT_REC_FWD 4   /* whole-layer persistent recurrent kernel, forward (both directions) */
+#define E2T_CAT_REC_BWD 5   /* whole-layer persistent recurrent kernel, BPTT */
 int e2t_profile_enable(e2t_handle* h, int on);
 int e2t_profile_read(e2t_handle* h, int category, double* ms_total, int64_t* launches);
 /* self-test of the tcgen05 GEMM against the SIMT GEMM on random data; returns max |diff| */
