@@ -19,6 +19,7 @@
 //
 // warp roles: 0 = TMA producer (+ counter wait), 1 = MMA issuer (+ TMEM owner), 2..5 = epilogue.
 #pragma once
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -65,6 +66,27 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load delivered to the same smem offset (and signalling the same mbarrier offset) of every CTA in cta_mask
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at this smem offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
 }
 // Bounded wait on a global arrival counter (a lost arrival must trap, not hang the GPU).
 __device__ __forceinline__ void wait_counter(const int* p, int target) {
@@ -148,6 +170,7 @@ struct RecFwdP {
   const int* lens2;       // [B] (nullable: all steps valid)
   int* counters;          // [2][n_bt][steps], zeroed before launch
   int steps, B, H, n_bt, n_slices, nkc, stages;
+  int csz;                // cluster size: consecutive unit slices of one chain share every A tile by TMA multicast
   DropP dp; int drop_F;
   long long* dbg;         // E2T_REC_DEBUG=1: per-step clock64 stamps of CTA 0 ([steps][8]), else NULL
   int pub_mode;
@@ -162,6 +185,7 @@ struct RecBwdP {
   const int* inject_t;                   // fwd direction: time index per row at which to inject (nullable -> 0)
   int* counters;
   int steps, B, H, n_bt, n_slices, nkc, stages;
+  int csz;
   long long* dbg;
   int pub_mode;
 };
@@ -201,12 +225,17 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
   const CUtensorMap* map_w = d ? &map_w1 : &map_w0;
   const int steps = p.steps, B = p.B, H = p.H;
   int* counters = p.counters + (size_t)(d * p.n_bt + bt) * steps;
-  const int kc_rot = (int)(((long long)j * p.nkc) / p.n_slices);   // per-CTA starting K chunk
+  const int csz = p.csz;                                   // cluster = csz consecutive slices of this chain
+  const int crank = csz > 1 ? (int)cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << csz) - 1);
+  // per-cluster starting K chunk (the K order is free; spreads the chain's clusters over the tile)
+  const int kc_rot = (int)(((long long)(j / csz) * p.nkc) / ((p.n_slices + csz - 1) / csz));
   long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
 #define REC_STAMP(step, slot) do { if (dbg) dbg[(step) * 8 + (slot)] = clock64(); } while (0)
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    // a stage is free once the MMA warps of ALL csz CTAs of the cluster have consumed it (multicast commit)
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), csz); }
     mbar_init(smem_u32(w_bar), 1);
     mbar_init(smem_u32(acc_full), 1);
     mbar_init(smem_u32(acc_empty), kEpiWarps);
@@ -216,6 +245,7 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), G::TMEM_COLS);
   fence_before_sync();
   __syncthreads();
+  if (csz > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -247,7 +277,12 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
           mbar_wait(smem_u32(&empty_bar[st]), ph ^ 1);
           const uint32_t fb = smem_u32(&full_bar[st]);
           mbar_expect_tx(fb, A_STAGE_BYTES);
-          tma_load_2d(smem_u32(smem_a + (size_t)st * A_STAGE_BYTES), map_a, fb, kc * BK, t_src * B + bt * kBM);
+          if (csz == 1) {
+            tma_load_2d(smem_u32(smem_a + (size_t)st * A_STAGE_BYTES), map_a, fb, kc * BK, t_src * B + bt * kBM);
+          } else if (kk % csz == crank) {
+            // one L2 read per cluster: the chunks are dealt round-robin to the cluster's CTAs, each multicast to all
+            tma_load_2d_mc(smem_u32(smem_a + (size_t)st * A_STAGE_BYTES), map_a, fb, kc * BK, t_src * B + bt * kBM, cmask);
+          }
         }
         REC_STAMP(s, 1);
       }
@@ -276,7 +311,8 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
           for (int k = 0; k < BK / UMMA_K; ++k)
             umma_tf32(tmem_base, make_smem_desc(sa + k * UMMA_K * 4), make_smem_desc(sw + k * UMMA_K * 4), idesc,
                       (kk > 0 || k > 0) ? 1u : 0u);
-          umma_commit(smem_u32(&empty_bar[st]));
+          if (csz == 1) umma_commit(smem_u32(&empty_bar[st]));
+          else umma_commit_mc(smem_u32(&empty_bar[st]), cmask);
         }
         umma_commit(smem_u32(acc_full));
         REC_STAMP(s, 3);
@@ -447,6 +483,7 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
   }
   fence_before_sync();
   __syncthreads();
+  if (csz > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into / signal this CTA
   if (warp == 1) {
     fence_after_sync();
     tmem_dealloc(tmem_base, G::TMEM_COLS);
@@ -523,18 +560,34 @@ inline void rec_launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap
     E2T_CHECK(cudaMalloc(&p.dbg, (size_t)p.steps * 8 * sizeof(long long)));
     E2T_CHECK(cudaMemsetAsync(p.dbg, 0, (size_t)p.steps * 8 * sizeof(long long), st));
   }
-  void* args[] = {(void*)&a0, (void*)&a1, (void*)&w0, (void*)&w1, (void*)&p};
   dim3 grid((unsigned)(2 * p.n_bt * p.n_slices));
-  E2T_CHECK(cudaLaunchCooperativeKernel((const void*)kfn, grid, dim3(kThreadsRec), args, smem, st));
+  // optional cluster (E2T_REC_CLUSTER=<max size>): the largest divisor of n_slices <= max shares every A tile by TMA
+  // multicast (H=400 -> clusters of 5).  Measured on B200 (profiles/README.md): no gain -- L2 already de-duplicates the
+  // chain's concurrent reads of one line and the bound is the aggregate L2->SM delivery rate -- so the default is 1.
+  static int cs_cap = getenv("E2T_REC_CLUSTER") ? atoi(getenv("E2T_REC_CLUSTER")) : 1;
+  p.csz = 1;
+  for (int c = std::min(cs_cap, 8); c >= 2; --c)
+    if (p.n_slices % c == 0) { p.csz = c; break; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(kThreadsRec); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  attrs[na].id = cudaLaunchAttributeCooperative; attrs[na].val.cooperative = 1; ++na;   // all CTAs co-resident
+  if (p.csz > 1) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = (unsigned)p.csz; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1; ++na;
+  }
+  cfg.attrs = attrs; cfg.numAttrs = na;
+  E2T_CHECK(cudaLaunchKernelEx(&cfg, kfn, a0, a1, w0, w1, p));
   if (p.dbg) {
     --dbg_left;
     std::vector<long long> hst((size_t)p.steps * 8);
     E2T_CHECK(cudaStreamSynchronize(st));
     E2T_CHECK(cudaMemcpy(hst.data(), p.dbg, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(p.dbg);
-    fprintf(stderr, "[rec %s] steps=%d B=%d H=%d nkc=%d stages=%d grid=%u  (cycles rel. to flag-seen of each step)\n"
+    fprintf(stderr, "[rec %s] steps=%d B=%d H=%d nkc=%d stages=%d cluster=%d grid=%u  (cycles rel. to flag-seen of each step)\n"
                     "  step  flag->tma_issued  ->first_full  ->mma_committed  ->acc_seen  ->h_stored  ->bar_passed  ->released | step_total\n",
-            BWD ? "bwd" : "fwd", p.steps, p.B, p.H, p.nkc, p.stages, grid.x);
+            BWD ? "bwd" : "fwd", p.steps, p.B, p.H, p.nkc, p.stages, p.csz, grid.x);
     for (int s = 1; s < p.steps; ++s) {
       const long long* e = &hst[(size_t)s * 8];
       const long long prev = s > 1 ? hst[(size_t)(s - 1) * 8] : 0;
