@@ -94,7 +94,7 @@ class SequenceNetwork:
 
     def _get_engine(self, subnets_params, max_T, max_L) -> Engine:
         geo, flist = self._geometry(subnets_params)
-        key = (tuple(sorted(geo.items())), self.FF_dropout, self.RNN_dropout, self.EMA_decay)
+        key = (tuple(sorted(geo.items())), self.FF_dropout, self.RNN_dropout, self.EMA_decay, int(self.beam_width), self.N_cases)
         e = self._engine
         if e is None or self._engine_key != key or e.cfg.max_T < max_T or e.cfg.max_L < max_L:
             if e is not None:

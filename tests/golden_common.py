@@ -1,0 +1,44 @@
+"""Checks an engine build (emulated on CPU, CUDA on the GPU) against tests/golden/seq2seq_tiny.npz."""
+import os
+
+import numpy as np
+
+import parity_common as pc
+from ecog2txt_b200 import _lib
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "seq2seq_tiny.npz")
+
+
+def load():
+    z = np.load(GOLD)
+    P = {k[2:].replace("|", "/"): z[k] for k in z.files if k.startswith("P|")}
+    return z, P
+
+
+def check_engine_against_golden(lib, backend="simt", tol=2e-4):
+    z, P = load()
+    B, T, L = z["x"].shape[0], z["x"].shape[1], z["y"].shape[1]
+    eng = pc.engine_for(pc.TINY, lib, B, T, 6, max_beam=3, gemm_backend=backend)
+    eng.set_all(P)
+    loss, ntok = eng.train_step_grads(z["x"], None, z["y"], seed=0)
+    assert ntok == int(z["ntok"])
+    assert abs(loss - float(z["loss"])) <= tol * abs(float(z["loss"]))
+    assert (eng.activation("lens", (B,), np.int32) == z["lens"]).all()
+    assert pc.rel_err(eng.activation("final_h", z["final_h"].shape), z["final_h"]) <= tol
+    assert pc.rel_err(eng.activation("final_c", z["final_c"].shape), z["final_c"]) <= tol
+    for k, v in eng.get_all(_lib.GRAD).items():
+        assert pc.rel_err(v, z["G|" + k.replace("/", "|")]) <= 5 * tol, k
+    eng.adam_ema_step(1.0 / ntok)
+    for k, v in eng.get_all(_lib.VALUE).items():
+        assert np.allclose(v, z["W1|" + k.replace("/", "|")], rtol=1e-4, atol=1e-6), k
+    for k, v in eng.get_all(_lib.EMA).items():
+        assert np.allclose(v, z["S1|" + k.replace("/", "|")], rtol=1e-4, atol=1e-6), k
+    # decoding with the ORIGINAL weights
+    eng.set_all(P)
+    toks, logp = eng.greedy_decode(z["x"], None, max_len=6, temperature=0.7)
+    assert (toks == z["greedy_tokens"]).all()
+    assert np.abs(logp - z["greedy_logp"]).max() < 2e-3
+    bt, bs = eng.beam_decode(z["x"], None, beam=3, max_len=6, temperature=0.7)
+    assert np.abs(bs - z["beam_scores"]).max() < 5e-3
+    assert (bt[:, 0] == z["beam_tokens"][:, 0]).all()
+    eng.close()

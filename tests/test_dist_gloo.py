@@ -1,0 +1,80 @@
+"""CPU, world_size 2, gloo: the data-parallel plumbing of SURVEY.md section 8e -- shard the minibatch, ONE all-reduce of
+the engine's flat gradient buffer (+ the token count), identical Adam+EMA on every rank -- must reproduce the
+single-process step on the whole batch.  Engines run on the kernel-emulation build (TEST-ONLY)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import parity_common as pc
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import ctypes
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    import __graft_entry__ as ge
+    from ecog2txt_b200 import _lib
+    from ecog2txt_b200.dist import allreduce_grads, flat_tensor, shard_range
+    from oracle import seq2seq_oracle as O
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = _lib.bind(ctypes.CDLL(ge.EMU_LIB))
+    geo = pc.TINY
+    ocfg = O.OracleConfig(**geo)
+    P = pc.make_params(ocfg)
+    B, T, L = 7, 19, 5          # 7 utterances over 2 ranks: shards of 4 and 3
+    x, lens, y = pc.make_batch(ocfg, B, T, L)
+    eng = pc.engine_for(geo, lib, B, T, L, gemm_backend="simt")
+    eng.set_all({k: v.numpy() for k, v in P.items()})
+    lo, hi = shard_range(B, rank, world)
+    loss, ntok = eng.train_step_grads(np.ascontiguousarray(x[lo:hi]), None, np.ascontiguousarray(y[lo:hi]), seed=0)
+    g = flat_tensor(eng, _lib.GRAD)
+    ntok_g = allreduce_grads(eng, g, float(ntok))
+    eng.adam_ema_step(1.0 / ntok_g)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ntok=ntok_g, lo=lo, hi=hi,
+             **{k.replace("/", "|"): v for k, v in eng.get_all(_lib.VALUE).items()},
+             **{"G|" + k.replace("/", "|"): v for k, v in eng.get_all(_lib.GRAD).items()})
+    eng.close()
+    dist.destroy_process_group()
+
+
+def test_two_rank_step_equals_single_process(tmp_path, emu_lib):
+    from ecog2txt_b200 import _lib
+    from ecog2txt_b200.dist import shard_range
+    from oracle import seq2seq_oracle as O
+    assert [shard_range(7, r, 2) for r in range(2)] == [(0, 4), (4, 7)]
+    assert [shard_range(5, r, 8) for r in range(8)] == [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 5), (5, 5), (5, 5)]
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    # single process, whole batch
+    geo = pc.TINY
+    ocfg = O.OracleConfig(**geo)
+    P = pc.make_params(ocfg)
+    x, lens, y = pc.make_batch(ocfg, 7, 19, 5)
+    eng = pc.engine_for(geo, emu_lib, 7, 19, 5, gemm_backend="simt")
+    eng.set_all({k: v.numpy() for k, v in P.items()})
+    loss, ntok = eng.train_step_grads(x, None, y, seed=0)
+    G = eng.get_all(_lib.GRAD)
+    eng.adam_ema_step(1.0 / ntok)
+    W = eng.get_all(_lib.VALUE)
+    assert float(r0["ntok"]) == float(r1["ntok"]) == float(ntok)
+    for k in W:
+        kk = k.replace("/", "|")
+        assert np.array_equal(r0[kk], r1[kk]), k                      # replicas stay bit-identical
+        assert np.allclose(r0["G|" + kk], G[k], rtol=1e-5, atol=1e-6), k   # summed shard grads == full-batch grads
+        assert np.allclose(r0[kk], W[k], rtol=1e-5, atol=1e-6), k
+    eng.close()
