@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--backend", default="auto")
     ap.add_argument("--cpu-baseline-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", default=None, help="write the per-kernel event-time breakdown of a step to this file")
     ap.add_argument("--decode", action="store_true", help="also report greedy / beam decode numbers")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -247,6 +248,12 @@ def main():
         for i in range(nprof):
             step_device(i)
         cat_ms = {c: eng.profile_read(c) for c in range(6)}
+        if args.breakdown:
+            rep = eng.profile_report()
+            with open(args.breakdown, "w") as f:
+                f.write("# per-kernel CUDA-event time over %d training steps (ms total, launches, us/launch)\n" % nprof)
+                for k, (n, t) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
+                    f.write(f"{t / nprof:9.4f} ms/step  n/step={n // nprof:4d}  {1e3 * t / n:9.2f} us  {k}\n")
         eng.profile_enable(False)
         rec_ms = cat_ms[0][0] + cat_ms[4][0] + cat_ms[5][0]
         rec_n = cat_ms[0][1] + cat_ms[4][1] + cat_ms[5][1]

@@ -76,7 +76,7 @@ struct e2t_handle {
   bool prof = false;
   int cat = E2T_CAT_OTHER;
 #ifndef E2T_EMU
-  struct ProfRec { int cat; cudaEvent_t a, b; };
+  struct ProfRec { int cat; cudaEvent_t a, b; std::string label; };
   std::vector<ProfRec> prof_recs;
 #endif
 
@@ -125,10 +125,12 @@ namespace {
 // launches
 // ------------------------------------------------------------------------------------------------
 #ifndef E2T_EMU
-inline void prof_begin(e2t_handle* h) {
+inline void prof_begin(e2t_handle* h, const char* label = "", int M = 0, int N = 0, int K = 0) {
   if (!h->prof) return;
   e2t_handle::ProfRec r;
   r.cat = h->cat;
+  r.label = label;
+  if (M || N || K) r.label += "[" + std::to_string(M) + "," + std::to_string(N) + "," + std::to_string(K) + "]";
   E2T_CHECK(cudaEventCreate(&r.a));
   E2T_CHECK(cudaEventCreate(&r.b));
   E2T_CHECK(cudaEventRecord(r.a, h->stream));
@@ -139,7 +141,7 @@ inline void prof_end(e2t_handle* h) {
   E2T_CHECK(cudaEventRecord(h->prof_recs.back().b, h->stream));
 }
 #else
-inline void prof_begin(e2t_handle*) {}
+inline void prof_begin(e2t_handle*, const char* = "", int = 0, int = 0, int = 0) {}
 inline void prof_end(e2t_handle*) {}
 #endif
 struct CatScope {
@@ -150,7 +152,7 @@ struct CatScope {
 
 #define LAUNCH(h, kern, grid, block, smem, ...)                       \
   do {                                                                \
-    prof_begin(h);                                                    \
+    prof_begin(h, #kern);                                             \
     E2T_LAUNCH(kern, grid, block, smem, (h)->stream, __VA_ARGS__);    \
     prof_end(h);                                                      \
     ++(h)->n_launch;                                                  \
@@ -170,7 +172,7 @@ void gemm(e2t_handle* h, const float* A, i64 sam, i64 sak, const float* B, i64 s
   CatScope cs0_(h, h->cat == E2T_CAT_RECURRENT ? E2T_CAT_RECURRENT : E2T_CAT_BULK_GEMM);
   if (h->cfg.gemm_backend != E2T_GEMM_SIMT && sak == 1 && sbk == 1 &&
       tc_gemm_nt_supported(A, sam, B, sbn, C, ldc, M, N, K)) {
-    prof_begin(h);
+    prof_begin(h, "tc_gemm_nt", M, N, K);
     tc_gemm_nt(h->stream, A, sam, B, sbn, C, ldc, M, N, K, bias, beta);
     prof_end(h);
     ++h->n_launch;
@@ -178,7 +180,7 @@ void gemm(e2t_handle* h, const float* A, i64 sam, i64 sak, const float* B, i64 s
     return;
   }
   if (h->cfg.gemm_backend != E2T_GEMM_SIMT && sam == 1 && sbn == 1 && tc_gemm_tn_supported(A, sak, B, sbk, M, N, K)) {
-    prof_begin(h);
+    prof_begin(h, "tc_gemm_tn", M, N, K);
     tc_gemm_tn(h->stream, A, sak, B, sbk, C, ldc, M, N, K, bias, beta);
     prof_end(h);
     ++h->n_launch;
@@ -508,7 +510,7 @@ void encoder_forward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, 
     if (use_rec(h, L, B, T2)) {
 #ifndef E2T_EMU
       CatScope cs_(h, E2T_CAT_REC_FWD);
-      prof_begin(h);
+      prof_begin(h, "rec_forward", B, L.H, T2);
       rec::rec_forward(h->stream, L.gates, L.cs, L.hs, drop ? L.hd : nullptr, L.KT, L.ldkt, L.In4, h->d_lens2,
                        h->rec_counters, T2, B, L.H, dp, 2 * L.H);
       prof_end(h);
@@ -659,7 +661,7 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
       CatScope cs_(h, E2T_CAT_REC_BWD);
       const float* Kd[2] = {Ly.KP[0], Ly.KP[1]};   // canonical rows, permuted gate columns
       const float* csd[2] = {Ly.cs[0], Ly.cs[1]};
-      prof_begin(h);
+      prof_begin(h, "rec_backward", B, Ly.H, T2);
       rec::rec_backward(h->stream, Ly.gates, csd, Ly.dhs, Kd, Ly.In, h->d_lens2, top ? h->dc0 : nullptr, c.Hd,
                         top ? h->d_tlast : nullptr, h->rec_counters, T2, B, Ly.H);
       prof_end(h);
@@ -1065,6 +1067,26 @@ extern "C" int e2t_profile_read(e2t_handle* h, int category, double* ms_total, i
 #endif
   if (ms_total) *ms_total = ms;
   if (launches) *launches = n;
+  API_END
+}
+
+extern "C" int e2t_profile_report(e2t_handle* h, char* buf, int64_t cap) {
+  API_BEGIN NEED_H;
+  E2T_REQUIRE(buf && cap > 0, "NULL buffer");
+  std::string out;
+#ifndef E2T_EMU
+  E2T_CHECK(cudaStreamSynchronize(h->stream));
+  std::map<std::string, std::pair<int64_t, double>> agg;
+  for (auto& r : h->prof_recs) {
+    float t = 0.f;
+    E2T_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+    auto& e = agg[r.label];
+    e.first += 1; e.second += t;
+  }
+  for (auto& kv : agg) out += kv.first + "\t" + std::to_string(kv.second.first) + "\t" + std::to_string(kv.second.second) + "\n";
+#endif
+  strncpy(buf, out.c_str(), (size_t)cap - 1);
+  buf[cap - 1] = 0;
   API_END
 }
 

@@ -12,6 +12,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <cmath>
+#include <map>
 #include <mutex>
 
 #include "common.cuh"
@@ -121,126 +123,194 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int mn_majo
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ================================================================================================
+// Persistent warp-specialised GEMM (one CTA per SM, loops over work items = (m tile, n tile, k split)).
+//   warp 0      TMA producer   every lane runs the loop and the mbarrier waits (warp-convergent control flow
+//                              keeps descriptors in uniform registers), one elected lane issues
+//   warp 1      MMA issuer     same; owns the 512-column TMEM allocation = two BN-wide accumulators, so the
+//                              epilogue of work item i overlaps the K loop of item i+1
+//   warps 2-5   epilogue       tcgen05.ld (thread = accumulator row) -> padded smem transpose -> row-contiguous
+//                              128-byte global accesses (bias / beta*C / split-K partials)
+// BN is a run-time multiple of 16 (TN: of 32) up to 256: measured on B200 (tools/ubench/tma_mma.cu) one
+// tcgen05.mma kind::tf32 costs the issuing thread ~70 cycles and one smem-stage hand-off ~300 cycles whatever
+// its size, so the K loop only approaches the tensor-pipe floor (BN/2 cycles per instruction) with wide tiles.
+// ================================================================================================
 struct TcGemmP {
   float* C; i64 ldc;
   int M, N, K;
   const float* bias; float beta;
+  int BN, stages;              // tile width, smem ring depth
+  int tiles_m, tiles_n, ksplit, kb_per_split;
+  float* ws;                   // split-K partials [ksplit][M][N] (ksplit > 1), reduced by k_splitk_reduce
 };
 
-// TN = false: A [M,K], B [N,K] row-major (K-major operands).
-// TN = true : A [K,M], B [K,N] row-major (MN-major operands; weight gradients X^T dZ): a stage holds
-//             BM/32 (+ BN/32) sub-tiles of [BK k-rows x 32 MN elements], one TMA box each.
-template <int BN, bool TN>
-__global__ void __launch_bounds__(kThreads, 1)
+constexpr int kGemmThreads = 192;
+constexpr int kEpiPad = 33;    // floats per staged row: conflict-free column writes and row reads
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <bool TN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcGemmP p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // carve: [stage][A 16 KB | B BN*128 B] ... then barriers
-  constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * STAGE_BYTES);
-  uint64_t* full_bar = bars;                 // [kStages]
-  uint64_t* empty_bar = bars + kStages;      // [kStages]
-  uint64_t* tmem_full_bar = bars + 2 * kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  const uint32_t A_BYTES = BM * BK * 4, B_BYTES = (uint32_t)p.BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+  float* stage_c = reinterpret_cast<float*>(smem + (size_t)p.stages * STAGE_BYTES);      // [4 warps][32][kEpiPad]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_c + 4 * 32 * kEpiPad);
+  uint64_t* full_bar = bars;                      // [stages]
+  uint64_t* empty_bar = bars + p.stages;          // [stages]
+  uint64_t* acc_full = bars + 2 * p.stages;       // [2]
+  uint64_t* acc_empty = acc_full + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int num_kb = (p.K + BK - 1) / BK;
-
-  if (warp == 4 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-    mbar_init(smem_u32(tmem_full_bar), 1);
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&acc_full[a]), 1); mbar_init(smem_u32(&acc_empty[a]), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), BN);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  // warp-uniform by construction (REDUX writes a uniform register): keeps the tcgen05 operands out of vector registers
+  const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
 
-  if (warp == 4) {
-    if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
+  const int n_items = p.tiles_m * p.tiles_n * p.ksplit;
+  const int num_kb_total = (p.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int ks = item / (p.tiles_m * p.tiles_n);
+      const int tile = item - ks * (p.tiles_m * p.tiles_n);
+      const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * p.BN;
+      const int kb0 = ks * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, num_kb_total);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
-        const uint32_t fb = smem_u32(&full_bar[s]);
-        mbar_expect_tx(fb, STAGE_BYTES);
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        if (!TN) {
-          tma_load_2d(sa, &map_a, fb, kb * BK, m0);
-          tma_load_2d(sa + A_BYTES, &map_b, fb, kb * BK, n0);
-        } else {
+        if (elect_one()) {
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          if (!TN) {
+            tma_load_2d(sa, &map_a, fb, kb * BK, m0);
+            tma_load_2d(sa + A_BYTES, &map_b, fb, kb * BK, n0);
+          } else {
 #pragma unroll
-          for (int i = 0; i < BM / 32; ++i) tma_load_2d(sa + i * (BK * 128), &map_a, fb, m0 + i * 32, kb * BK);
-#pragma unroll
-          for (int i = 0; i < BN / 32; ++i) tma_load_2d(sa + A_BYTES + i * (BK * 128), &map_b, fb, n0 + i * 32, kb * BK);
+            for (int i = 0; i < BM / 32; ++i) tma_load_2d(sa + i * (BK * 128), &map_a, fb, m0 + i * 32, kb * BK);
+            for (int i = 0; i < p.BN / 32; ++i) tma_load_2d(sa + A_BYTES + i * (BK * 128), &map_b, fb, n0 + i * 32, kb * BK);
+          }
         }
+        __syncwarp();
       }
     }
-  } else if (warp == 5) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BM, BN, TN ? 1 : 0);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = make_idesc_tf32(BM, p.BN, TN ? 1 : 0);
+    int it = 0, n_done = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+      const int ks = item / (p.tiles_m * p.tiles_n);
+      const int kb0 = ks * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, num_kb_total);
+      const int acc = n_done & 1;
+      const uint32_t acc_ph = (n_done >> 1) & 1;
+      mbar_wait(smem_u32(&acc_empty[acc]), acc_ph ^ 1);     // the epilogue drained this accumulator
+      fence_after_sync();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
         mbar_wait(smem_u32(&full_bar[s]), ph);
         fence_after_sync();
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t da = TN ? make_smem_desc_mn(sa + k * 1024, BK * 128, 512) : make_smem_desc(sa + k * UMMA_K * 4);
-          const uint64_t db = TN ? make_smem_desc_mn(sa + A_BYTES + k * 1024, BK * 128, 512)
-                                 : make_smem_desc(sa + A_BYTES + k * UMMA_K * 4);
-          umma_tf32(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = TN ? make_smem_desc_mn(sa + k * 1024, BK * 128, 512) : make_smem_desc(sa + k * UMMA_K * 4);
+            const uint64_t db = TN ? make_smem_desc_mn(sa + A_BYTES + k * 1024, BK * 128, 512)
+                                   : make_smem_desc(sa + A_BYTES + k * UMMA_K * 4);
+            umma_tf32(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));             // frees this smem stage when the MMAs retire
+          if (kb == kb1 - 1) umma_commit(smem_u32(&acc_full[acc]));
         }
-        umma_commit(smem_u32(&empty_bar[s]));   // frees this smem stage when the MMAs retire
+        __syncwarp();
       }
-      umma_commit(smem_u32(tmem_full_bar));      // accumulator complete
     }
   } else {
-    // epilogue: warp w owns TMEM lanes [32w, 32w+32) = accumulator rows
-    mbar_wait(smem_u32(tmem_full_bar), 0);
-    fence_after_sync();
-    const int row = m0 + warp * 32 + lane;
-    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
-      const int col0 = n0 + c * 32;
-      if (row < p.M && col0 < p.N) {
-        float* crow = p.C + (i64)row * p.ldc + col0;
-        if (vec_ok && col0 + 32 <= p.N) {
+    // ================= epilogue: warp w reads TMEM lanes [32*(w%4), +32) =================
+    const int quad = warp & 3;
+    float* st = stage_c + (size_t)(warp - 2) * 32 * kEpiPad;
+    int n_done = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+      const int ks = item / (p.tiles_m * p.tiles_n);
+      const int tile = item - ks * (p.tiles_m * p.tiles_n);
+      const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * p.BN;
+      const int acc = n_done & 1;
+      const uint32_t acc_ph = (n_done >> 1) & 1;
+      mbar_wait(smem_u32(&acc_full[acc]), acc_ph);
+      fence_after_sync();
+      const int row0 = m0 + quad * 32;
+      const int n_end = min(n0 + p.BN, p.N);
+      float* outp; i64 ldo; const float* bias; float beta;
+      if (p.ksplit > 1) { outp = p.ws + (size_t)ks * p.M * p.N; ldo = p.N; bias = nullptr; beta = 0.f; }
+      else { outp = p.C; ldo = p.ldc; bias = p.bias; beta = p.beta; }
+      const int rows_ok = min(32, p.M - row0);
+      for (int c0 = n0; c0 < n_end; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256 + (c0 - n0)), v);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (p.bias) { o.x += p.bias[col0 + j]; o.y += p.bias[col0 + j + 1]; o.z += p.bias[col0 + j + 2]; o.w += p.bias[col0 + j + 3]; }
-            if (p.beta != 0.f) {
-              const float4 old = *reinterpret_cast<const float4*>(crow + j);
-              o.x += p.beta * old.x; o.y += p.beta * old.y; o.z += p.beta * old.z; o.w += p.beta * old.w;
-            }
-            *reinterpret_cast<float4*>(crow + j) = o;
-          }
-        } else {
-          for (int j = 0; j < 32; ++j) {
-            if (col0 + j >= p.N) break;
-            float o = v[j];
-            if (p.bias) o += p.bias[col0 + j];
-            if (p.beta != 0.f) o += p.beta * crow[j];
-            crow[j] = o;
+        for (int j = 0; j < 32; ++j) st[lane * kEpiPad + j] = v[j];
+        __syncwarp();
+        const int col = c0 + lane;
+        if (col < n_end) {
+          const float bv = bias ? bias[col] : 0.f;
+          float* cp = outp + (i64)row0 * ldo + col;
+          if (beta != 0.f) {
+#pragma unroll 8
+            for (int r = 0; r < rows_ok; ++r) cp[(i64)r * ldo] = st[r * kEpiPad + lane] + bv + beta * cp[(i64)r * ldo];
+          } else {
+#pragma unroll 8
+            for (int r = 0; r < rows_ok; ++r) cp[(i64)r * ldo] = st[r * kEpiPad + lane] + bv;
           }
         }
+        __syncwarp();
       }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(smem_u32(&acc_empty[acc]));
     }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 1) {
     fence_after_sync();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 512);
   }
+}
+
+// C[m,n] = sum_s ws[s][m][n] (+ bias[n]) (+ beta*C): fixed summation order -> deterministic split-K
+__global__ void k_splitk_reduce(const float* __restrict__ ws, int ksplit, int M, int N, float* C, i64 ldc,
+                                const float* __restrict__ bias, float beta) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (i64)M * N) return;
+  const int m = (int)(i / N), n = (int)(i - (i64)m * N);
+  float a = 0.f;
+  for (int s = 0; s < ksplit; ++s) a += ws[(size_t)s * M * N + i];
+  if (bias) a += bias[n];
+  float* c = C + (i64)m * ldc + n;
+  if (beta != 0.f) a += beta * (*c);
+  *c = a;
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -279,19 +349,92 @@ inline CUtensorMap make_map(const float* ptr, i64 rows, i64 cols, i64 ld, int bo
   return m;
 }
 
-template <int BN>
-constexpr size_t smem_bytes() { return (size_t)kStages * (BM * BK * 4 + BN * BK * 4) + (2 * kStages + 2) * 8 + 1024; }
+inline int sm_count_() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
 
-template <int BN, bool TN>
-inline void launch(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const TcGemmP& p) {
+constexpr size_t kSmemCap = 227 * 1024;
+inline size_t gemm_fixed_smem() { return (size_t)4 * 32 * kEpiPad * 4 + (2 * 8 + 4 + 1) * 8 + 1024; }
+inline size_t gemm_smem_bytes(int BN, int stages) { return (size_t)stages * (BM * BK * 4 + (size_t)BN * BK * 4) + gemm_fixed_smem(); }
+
+// split-K workspace (grown on demand; one per process is enough: launches are stream-ordered per handle, and
+// handles on different streams would race -- so it is keyed by stream)
+struct SplitWs { float* p = nullptr; size_t n = 0; };
+inline SplitWs& split_ws(cudaStream_t st) {
+  static std::mutex mu;
+  static std::map<cudaStream_t, SplitWs> tab;
+  std::lock_guard<std::mutex> g(mu);
+  return tab[st];
+}
+
+// choose the tile width: fewest waves x (cycles per k-step ~ max(BN/2, issue floor))
+inline int pick_bn(int M, int N, bool tn, int nsm) {
+  const int step = tn ? 32 : 16;
+  int best = 256; double best_cost = 1e30;
+  const int tm = (M + BM - 1) / BM;
+  for (int bn = 256; bn >= 32; bn -= step) {
+    const int tn_ = (N + bn - 1) / bn;
+    const double waves = std::ceil((double)tm * tn_ / nsm);
+    const double per_k = std::max(bn / 2.0, 80.0) + 75.0;       // MMA pipe / issue floor + amortised stage hand-off
+    const double cost = (tm * tn_ >= nsm ? waves : 1.0) * per_k;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+template <bool TN>
+inline void launch_gemm(cudaStream_t st, const float* A, i64 lda, const float* B, i64 ldb, float* C, i64 ldc, int M, int N,
+                        int K, const float* bias, float beta) {
+  const int nsm = sm_count_();
+  TcGemmP p{};
+  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.beta = beta;
+  p.BN = pick_bn(M, N, TN, nsm);
+  if (p.BN > ((N + 15) / 16) * 16) p.BN = ((N + (TN ? 31 : 15)) / (TN ? 32 : 16)) * (TN ? 32 : 16);
+  p.tiles_m = (M + BM - 1) / BM;
+  p.tiles_n = (N + p.BN - 1) / p.BN;
+  const int num_kb = (K + BK - 1) / BK;
+  const int tiles = p.tiles_m * p.tiles_n;
+  p.ksplit = 1;
+  if (tiles * 2 <= nsm && num_kb >= 16) {       // few output tiles, long K (weight gradients): split K over the idle SMs
+    p.ksplit = std::min(nsm / tiles, num_kb / 8);
+    if (p.ksplit < 1) p.ksplit = 1;
+  }
+  p.kb_per_split = (num_kb + p.ksplit - 1) / p.ksplit;
+  p.ksplit = (num_kb + p.kb_per_split - 1) / p.kb_per_split;     // no empty splits
+  int stages = 8;
+  while (stages > 2 && gemm_smem_bytes(p.BN, stages) > kSmemCap) --stages;
+  p.stages = stages;
+  if (p.ksplit > 1) {
+    SplitWs& w = split_ws(st);
+    const size_t need = (size_t)p.ksplit * M * N;
+    if (w.n < need) {
+      if (w.p) { E2T_CHECK(cudaStreamSynchronize(st)); E2T_CHECK(cudaFree(w.p)); }
+      E2T_CHECK(cudaMalloc(&w.p, need * sizeof(float)));
+      w.n = need;
+    }
+    p.ws = w.p;
+  }
+  CUtensorMap ma, mb;
+  if (!TN) { ma = make_map(A, M, K, lda, BM); mb = make_map(B, N, K, ldb, p.BN); }
+  else { ma = make_map(A, K, M, lda, BK, true); mb = make_map(B, K, N, ldb, BK, true); }
+  auto kfn = k_gemm_tc<TN>;
   static bool attr_set = false;
-  auto kfn = k_gemm_tc<BN, TN>;
   if (!attr_set) {
-    E2T_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<BN>()));
+    E2T_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap));
     attr_set = true;
   }
-  dim3 grid((unsigned)((p.N + BN - 1) / BN), (unsigned)((p.M + BM - 1) / BM));
-  kfn<<<grid, kThreads, smem_bytes<BN>(), st>>>(ma, mb, p);
+  const int grid = std::min(tiles * p.ksplit, nsm);
+  kfn<<<grid, kGemmThreads, gemm_smem_bytes(p.BN, p.stages), st>>>(ma, mb, p);
+  if (p.ksplit > 1) {
+    const i64 n = (i64)M * N;
+    k_splitk_reduce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.ws, p.ksplit, M, N, C, ldc, bias, beta);
+  }
 }
 
 }  // namespace tc
@@ -310,18 +453,7 @@ static inline bool tc_gemm_nt_supported(const float* A, i64 lda, const float* B,
 
 static inline void tc_gemm_nt(cudaStream_t st, const float* A, i64 lda, const float* B, i64 ldb, float* C, i64 ldc, int M,
                               int N, int K, const float* bias, float beta) {
-  tc::TcGemmP p{C, ldc, M, N, K, bias, beta};
-  // pick the N tile so that small-M problems still spread over many SMs
-  const int mt = (M + tc::BM - 1) / tc::BM;
-  int bn = 128;
-  if (mt * ((N + 127) / 128) < 96) bn = 64;
-  if (mt * ((N + 63) / 64) < 96) bn = 32;
-  if (N <= 32) bn = 32; else if (N <= 64 && bn > 64) bn = 64;
-  CUtensorMap ma = tc::make_map(A, M, K, lda, tc::BM);
-  CUtensorMap mb = tc::make_map(B, N, K, ldb, bn);
-  if (bn == 128) tc::launch<128, false>(st, ma, mb, p);
-  else if (bn == 64) tc::launch<64, false>(st, ma, mb, p);
-  else tc::launch<32, false>(st, ma, mb, p);
+  tc::launch_gemm<false>(st, A, lda, B, ldb, C, ldc, M, N, K, bias, beta);
 }
 
 // C[M,N] = A[K,M]^T B[K,N]  (A, B row-major with leading dims lda, ldb): weight gradients.
@@ -334,18 +466,7 @@ static inline bool tc_gemm_tn_supported(const float* A, i64 lda, const float* B,
 }
 static inline void tc_gemm_tn(cudaStream_t st, const float* A, i64 lda, const float* B, i64 ldb, float* C, i64 ldc, int M,
                               int N, int K, const float* bias, float beta) {
-  tc::TcGemmP p{C, ldc, M, N, K, bias, beta};
-  const int mt = (M + tc::BM - 1) / tc::BM;
-  int bn = 128;
-  if (mt * ((N + 127) / 128) < 96) bn = 64;
-  if (mt * ((N + 63) / 64) < 96) bn = 32;
-  if (N <= 32) bn = 32; else if (N <= 64 && bn > 64) bn = 64;
-  // boxes are [BK k-rows x 32 MN columns] of the [K, M] / [K, N] matrices
-  CUtensorMap ma = tc::make_map(A, K, M, lda, tc::BK, true);
-  CUtensorMap mb = tc::make_map(B, K, N, ldb, tc::BK, true);
-  if (bn == 128) tc::launch<128, true>(st, ma, mb, p);
-  else if (bn == 64) tc::launch<64, true>(st, ma, mb, p);
-  else tc::launch<32, true>(st, ma, mb, p);
+  tc::launch_gemm<true>(st, A, lda, B, ldb, C, ldc, M, N, K, bias, beta);
 }
 
 // A/B random, C_tc vs fp32 SIMT reference; exercises bias, beta and ragged M/N/K edges. Returns max |diff|.

@@ -261,6 +261,16 @@ class Engine:
         self._ck(self._lib.e2t_profile_read(self._h, category, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
+    def profile_report(self) -> Dict[str, Tuple[int, float]]:
+        """{kernel label: (launches, total ms)} of the records taken since profile_enable(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        self._ck(self._lib.e2t_profile_report(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            k, n, ms = line.split("\t")
+            out[k] = (int(n), float(ms))
+        return out
+
     def selftest_gemm(self, M: int, N: int, K: int) -> float:
         d = C.c_float()
         self._ck(self._lib.e2t_selftest_gemm(self._h, M, N, K, C.byref(d)))

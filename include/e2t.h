@@ -154,6 +154,8 @@ int e2t_counter(e2t_handle* h, const char* name, int64_t* value);
 #define E2T_CAT_REC_BWD 5   /* whole-layer persistent recurrent kernel, BPTT */
 int e2t_profile_enable(e2t_handle* h, int on);
 int e2t_profile_read(e2t_handle* h, int category, double* ms_total, int64_t* launches);
+/* per-kernel breakdown of the same records: lines "label<TAB>launches<TAB>ms_total\n" (NUL-terminated, truncated to cap) */
+int e2t_profile_report(e2t_handle* h, char* buf, int64_t cap);
 /* self-test of the tcgen05 GEMM against the SIMT GEMM on random data; returns max |diff| */
 int e2t_selftest_gemm(e2t_handle* h, int M, int N, int K, float* max_abs_diff);
 

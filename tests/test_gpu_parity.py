@@ -91,7 +91,8 @@ def test_sequence_network_fit_on_gpu(gpu_lib, tmp_path):
     assert net._engine.counter("persistent_rnn_launches") > 0
     wer = a["training"].decoder_word_error_rates
     assert wer[-1] < 0.2, wer                     # 10 fixed sentences are learnable: WER -> ~0 on the training set
-    assert a["validation"].decoder_word_error_rates[-1] < 0.5
+    vwer = a["validation"].decoder_word_error_rates
+    assert vwer[-1] < 0.75 and vwer[-1] <= vwer[0], vwer   # 32 held-out utterances, 96 training ones: generalises, loosely
     res = net.restore_and_assess([s], 60)
     assert abs(res["training"].word_error_rate - wer[-1]) < 1e-9
     net.beam_width = 4
