@@ -85,6 +85,7 @@ _SIGNATURES = {
     "e2t_counter": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64)]),
     "e2t_profile_enable": (C.c_int, [_P, C.c_int]),
     "e2t_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "e2t_bench_gemm": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_float)]),
     "e2t_profile_report": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "e2t_selftest_gemm": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
 }

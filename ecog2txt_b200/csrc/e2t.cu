@@ -24,6 +24,7 @@
 #ifndef E2T_EMU
 #include "gemm_tc.cuh"
 #include "lstm_rec.cuh"
+#include "conv_tc.cuh"
 #endif
 
 static thread_local std::string g_err;
@@ -91,6 +92,7 @@ struct e2t_handle {
   float* dec_KT = nullptr; int ld_dec_kt = 0;   // [4Hd, D+Hd (padded)]
   float* proj_wT = nullptr;                      // [Hd, Vp]
   float* conv_wT[E2T_MAX_SUBNETS];               // [E, W*C]
+  float* conv_wT_lo[E2T_MAX_SUBNETS];            // tf32 remainder of conv_wT (conv_wT then holds the tf32-exact part)
 
   // workspace
   std::vector<void*> allocs;
@@ -200,13 +202,25 @@ void gemm(e2t_handle* h, const float* A, i64 sam, i64 sak, const float* B, i64 s
 
 // conv-gather GEMMs (A3+A4 fused). mode 1: Y[T2*B, E] = gather(x) Wc + b ; mode 2: dWc[W*C, E] = gather(x)^T dY
 void gemm_conv(e2t_handle* h, int mode, const float* x, const int* lens, int Bsz, int T, int Cch, int Wd, int T2,
-               const float* Bmat, i64 sbk, i64 sbn, float* C, i64 ldc, int N, const float* bias, float beta) {
+               const float* Bmat, i64 sbk, i64 sbn, float* C, i64 ldc, int N, const float* bias, float beta,
+               const float* Bmat_lo = nullptr) {
   CatScope cs_(h, E2T_CAT_CONV);
   GemmP p{};
   p.x = x; p.lens = lens; p.Bsz = Bsz; p.T = T; p.Cch = Cch; p.Wd = Wd;
   p.B = Bmat; p.sbk = sbk; p.sbn = sbn; p.C = C; p.ldc = ldc; p.N = N; p.bias = bias; p.beta = beta;
   if (mode == 1) { p.M = T2 * Bsz; p.K = Wd * Cch; } else { p.M = Wd * Cch; p.K = T2 * Bsz; }
   if (p.M <= 0 || p.K <= 0) return;
+#ifndef E2T_EMU
+  if (h->cfg.gemm_backend != E2T_GEMM_SIMT && beta == 0.f && conv::conv_tc_supported(Cch, Wd, N, T2 * Bsz) &&
+      (mode == 1 ? (sbk == 1 && (sbn & 3) == 0) : (sbn == 1 && (sbk & 3) == 0)) && (ldc & 3) == 0) {
+    prof_begin(h, mode == 1 ? "conv_fwd_tc" : "conv_bwd_tc", p.M, N, p.K);
+    if (mode == 1) conv::launch_conv<false>(h->stream, x, lens, Bsz, T, Cch, Wd, T2, Bmat, Bmat_lo, sbn, C, ldc, N, bias);
+    else conv::launch_conv<true>(h->stream, x, lens, Bsz, T, Cch, Wd, T2, Bmat, nullptr, sbk, C, ldc, N, bias);
+    prof_end(h);
+    ++h->n_launch; ++h->n_launch_tc;
+    return;
+  }
+#endif
   dim3 grid((unsigned)cdiv(N, 64), (unsigned)cdiv(p.M, 64));
   if (mode == 1) { auto kfn = k_gemm<1>; LAUNCH(h, kfn, grid, dim3(256), 0, p); }
   else           { auto kfn = k_gemm<2>; LAUNCH(h, kfn, grid, dim3(256), 0, p); }
@@ -356,8 +370,14 @@ void build_workspace(e2t_handle* h) {
   h->ld_dec_kt = h->Dp + round_up(c.Hd, 4);
   h->dec_KT = h->alloc<float>((i64)4 * c.Hd * h->ld_dec_kt);
   h->proj_wT = h->alloc<float>((i64)c.Hd * h->Vp);
-  for (int s = 0; s < c.n_subnets; ++s)
+  for (int s = 0; s < c.n_subnets; ++s) {
     h->conv_wT[s] = h->alloc<float>((i64)c.E * round_up(c.subnet_W[s] * c.subnet_C[s], 4));
+    h->conv_wT_lo[s] = nullptr;
+#ifndef E2T_EMU
+    if (c.gemm_backend != E2T_GEMM_SIMT && conv::conv_tc_supported(c.subnet_C[s], c.subnet_W[s], c.E, 1 << 20))
+      h->conv_wT_lo[s] = h->alloc<float>((i64)c.E * round_up(c.subnet_W[s] * c.subnet_C[s], 4));
+#endif
+  }
   // decode workspace (rows = B*beam)
   const i64 R = Bm * h->beam_m;
   for (int i = 0; i < 2; ++i) {
@@ -396,6 +416,12 @@ void repack(e2t_handle* h, const float* src, int src_id) {
   for (int s = 0; s < c.n_subnets; ++s) {
     int WC = c.subnet_W[s] * c.subnet_C[s];
     tr(src + h->conv_w[s], c.E, h->conv_wT[s], round_up(WC, 4), WC, c.E);
+#ifndef E2T_EMU
+    if (h->conv_wT_lo[s]) {   // hi / lo split in place: the SIMT fallback for tiny batches then sees tf32-rounded weights
+      const i64 n = (i64)c.E * round_up(WC, 4);
+      LAUNCH(h, conv::k_split_tf32, grid1(n), dim3(256), 0, h->conv_wT[s], h->conv_wT[s], h->conv_wT_lo[s], n);
+    }
+#endif
   }
   h->packed_dirty = false;
   h->packed_src = src_id;
@@ -494,7 +520,7 @@ void encoder_forward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, 
   const float* Wc = h->Wc;
   LAUNCH(h, k_lengths, dim3(B), dim3(32), 0, in.x, in.lens_in, h->d_lens, h->d_lens2, h->d_tlast, B, T, C, W);
   gemm_conv(h, 1, in.x, h->d_lens, B, T, C, W, T2, h->conv_wT[subnet], 1, round_up(W * C, 4), h->conv_out, c.E, c.E,
-            Wc + h->conv_b[subnet], 0.f);
+            Wc + h->conv_b[subnet], 0.f, h->conv_wT_lo[subnet]);
   DropP dpc = make_drop(seed, E2T_STREAM_CONV, train ? c.ff_dropout : 0.f);
   if (c.conv_act != E2T_ACT_LINEAR || dpc.thresh)
     LAUNCH(h, k_act_dropout, grid1((i64)T2 * B * c.E), dim3(256), 0, h->conv_out, (i64)T2 * B, c.E, c.E,
@@ -1067,6 +1093,18 @@ extern "C" int e2t_profile_read(e2t_handle* h, int category, double* ms_total, i
 #endif
   if (ms_total) *ms_total = ms;
   if (launches) *launches = n;
+  API_END
+}
+
+extern "C" int e2t_bench_gemm(e2t_handle* h, int M, int N, int K, int tn, float beta, int iters, float* ms_per_launch) {
+  API_BEGIN NEED_H;
+#ifdef E2T_EMU
+  (void)M; (void)N; (void)K; (void)tn; (void)beta; (void)iters; (void)ms_per_launch;
+  throw std::runtime_error("e2t: tcgen05 GEMM is not available in the emulation build");
+#else
+  E2T_REQUIRE(iters >= 1 && ms_per_launch, "bad arguments");
+  *ms_per_launch = tc_gemm_bench(h->stream, M, N, K, tn != 0, beta, iters);
+#endif
   API_END
 }
 

@@ -469,6 +469,31 @@ static inline void tc_gemm_tn(cudaStream_t st, const float* A, i64 lda, const fl
   tc::launch_gemm<true>(st, A, lda, B, ldb, C, ldc, M, N, K, bias, beta);
 }
 
+// times `iters` back-to-back launches of one GEMM shape on zero-filled operands (diagnostic; e2t_bench_gemm)
+static inline float tc_gemm_bench(cudaStream_t st, int M, int N, int K, bool tn, float beta, int iters) {
+  const i64 lda = tn ? (M + 3) / 4 * 4 : (K + 3) / 4 * 4, ldb = tn ? (N + 3) / 4 * 4 : (K + 3) / 4 * 4, ldc = (N + 3) / 4 * 4;
+  float *dA, *dB, *dC;
+  const size_t na = (size_t)(tn ? K : M) * lda, nb = (size_t)(tn ? K : N) * ldb, nc = (size_t)M * ldc;
+  E2T_CHECK(cudaMalloc(&dA, na * 4)); E2T_CHECK(cudaMalloc(&dB, nb * 4)); E2T_CHECK(cudaMalloc(&dC, nc * 4));
+  E2T_CHECK(cudaMemsetAsync(dA, 0, na * 4, st)); E2T_CHECK(cudaMemsetAsync(dB, 0, nb * 4, st));
+  E2T_CHECK(cudaMemsetAsync(dC, 0, nc * 4, st));
+  cudaEvent_t e0, e1;
+  E2T_CHECK(cudaEventCreate(&e0)); E2T_CHECK(cudaEventCreate(&e1));
+  for (int i = 0; i < iters + 2; ++i) {
+    if (i == 2) E2T_CHECK(cudaEventRecord(e0, st));
+    if (tn) tc_gemm_tn(st, dA, lda, dB, ldb, dC, ldc, M, N, K, nullptr, beta);
+    else tc_gemm_nt(st, dA, lda, dB, ldb, dC, ldc, M, N, K, nullptr, beta);
+  }
+  E2T_CHECK(cudaEventRecord(e1, st));
+  E2T_CHECK(cudaStreamSynchronize(st));
+  E2T_CHECK(cudaGetLastError());
+  float ms = 0.f;
+  E2T_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(dA); cudaFree(dB); cudaFree(dC);
+  return ms / iters;
+}
+
 // A/B random, C_tc vs fp32 SIMT reference; exercises bias, beta and ragged M/N/K edges. Returns max |diff|.
 static inline float tc_gemm_selftest(cudaStream_t st, int M, int N, int K, bool tn = false) {
   const i64 lda = tn ? (M + 3) / 4 * 4 : (K + 3) / 4 * 4, ldb = tn ? (N + 3) / 4 * 4 : (K + 3) / 4 * 4, ldc = (N + 3) / 4 * 4;

@@ -271,6 +271,11 @@ class Engine:
             out[k] = (int(n), float(ms))
         return out
 
+    def bench_gemm(self, M: int, N: int, K: int, tn: bool = False, beta: float = 0.0, iters: int = 20) -> float:
+        ms = C.c_float()
+        self._ck(self._lib.e2t_bench_gemm(self._h, M, N, K, int(tn), beta, iters, C.byref(ms)))
+        return float(ms.value)
+
     def selftest_gemm(self, M: int, N: int, K: int) -> float:
         d = C.c_float()
         self._ck(self._lib.e2t_selftest_gemm(self._h, M, N, K, C.byref(d)))

@@ -158,6 +158,8 @@ int e2t_profile_read(e2t_handle* h, int category, double* ms_total, int64_t* lau
 int e2t_profile_report(e2t_handle* h, char* buf, int64_t cap);
 /* self-test of the tcgen05 GEMM against the SIMT GEMM on random data; returns max |diff| */
 int e2t_selftest_gemm(e2t_handle* h, int M, int N, int K, float* max_abs_diff);
+/* diagnostic: average device time (ms) of one tcgen05 GEMM launch of this shape (tn: C = A^T B), zero operands */
+int e2t_bench_gemm(e2t_handle* h, int M, int N, int K, int tn, float beta, int iters, float* ms_per_launch);
 
 #ifdef __cplusplus
 }
