@@ -103,6 +103,7 @@ struct e2t_handle {
   int* d_ntok;
   float* colsum_ws = nullptr; i64 colsum_ws_n = 0;   // [64, N] partial column sums
   float* perm_ws = nullptr; i64 perm_ws_n = 0;       // [(In+H+1), 4H] weight + bias gradients in permuted gate order
+  float* rec_pws = nullptr; i64 rec_pws_n = 0;       // partial-dh workspace of the reduce-scatter BPTT kernel
   int* rec_counters = nullptr;   // arrival counters of the persistent recurrent kernels [2][n_bt][T2m]
   int64_t n_launch_rec = 0;
   // decode workspace
@@ -352,6 +353,9 @@ void build_workspace(e2t_handle* h) {
       }
     }
     if (L.rec) h->perm_ws_n = std::max<i64>(h->perm_ws_n, (i64)(L.In + L.H + 1) * 4 * L.H);
+#ifndef E2T_EMU
+    if (L.rec && rec::bptt_supported((int)Bm, L.H)) h->rec_pws_n = std::max<i64>(h->rec_pws_n, (i64)rec::bptt_ws_floats((int)Bm, L.H));
+#endif
   }
   h->h0 = h->alloc<float>(Bm * c.Hd); h->c0 = h->alloc<float>(Bm * c.Hd);
   h->dh0 = h->alloc<float>(Bm * c.Hd); h->dc0 = h->alloc<float>(Bm * c.Hd);
@@ -366,6 +370,7 @@ void build_workspace(e2t_handle* h) {
   h->colsum_ws_n = (i64)64 * std::max<i64>(std::max<i64>(4 * Hmax, h->Vp), std::max<i64>(c.E, h->Dp));
   h->colsum_ws = h->alloc<float>(h->colsum_ws_n);
   if (h->perm_ws_n) h->perm_ws = h->alloc<float>(h->perm_ws_n);
+  if (h->rec_pws_n) h->rec_pws = h->alloc<float>(h->rec_pws_n);
   h->rec_counters = h->alloc<int>((i64)2 * cdiv(Bm, 128) * std::max<i64>(T2, Lm));
   h->ld_dec_kt = h->Dp + round_up(c.Hd, 4);
   h->dec_KT = h->alloc<float>((i64)4 * c.Hd * h->ld_dec_kt);
@@ -688,8 +693,13 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
       const float* Kd[2] = {Ly.KP[0], Ly.KP[1]};   // canonical rows, permuted gate columns
       const float* csd[2] = {Ly.cs[0], Ly.cs[1]};
       prof_begin(h, "rec_backward", B, Ly.H, T2);
-      rec::rec_backward(h->stream, Ly.gates, csd, Ly.dhs, Kd, Ly.In, h->d_lens2, top ? h->dc0 : nullptr, c.Hd,
-                        top ? h->d_tlast : nullptr, h->rec_counters, T2, B, Ly.H);
+      static const bool use_allgather = getenv("E2T_REC_BWD_ALLGATHER") != nullptr;
+      if (!use_allgather && h->rec_pws && rec::bptt_supported(h->Bm, Ly.H))
+        rec::rec_backward_rs(h->stream, Ly.gates, csd, Ly.dhs, Kd, Ly.In, h->d_lens2, top ? h->dc0 : nullptr, c.Hd,
+                             top ? h->d_tlast : nullptr, h->rec_counters, h->rec_pws, T2, B, Ly.H);
+      else
+        rec::rec_backward(h->stream, Ly.gates, csd, Ly.dhs, Kd, Ly.In, h->d_lens2, top ? h->dc0 : nullptr, c.Hd,
+                          top ? h->d_tlast : nullptr, h->rec_counters, T2, B, Ly.H);
       prof_end(h);
       ++h->n_launch; ++h->n_launch_tc; ++h->n_launch_rec;
 #endif

@@ -113,6 +113,14 @@ __device__ __forceinline__ void ldv(float* dst, const float* src) {
   }
 }
 template <int N>
+__device__ __forceinline__ void ldv_cg(float* dst, const float* src) {
+#pragma unroll
+  for (int i = 0; i < N / 4; ++i) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(src + 4 * i));
+    dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+  }
+}
+template <int N>
 __device__ __forceinline__ void stv(float* dst, const float* src) {
 #pragma unroll
   for (int i = 0; i < N / 4; ++i)
@@ -225,17 +233,14 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
   const CUtensorMap* map_w = d ? &map_w1 : &map_w0;
   const int steps = p.steps, B = p.B, H = p.H;
   int* counters = p.counters + (size_t)(d * p.n_bt + bt) * steps;
-  const int csz = p.csz;                                   // cluster = csz consecutive slices of this chain
-  const int crank = csz > 1 ? (int)cluster_ctarank() : 0;
-  const uint16_t cmask = (uint16_t)((1u << csz) - 1);
-  // per-cluster starting K chunk (the K order is free; spreads the chain's clusters over the tile)
-  const int kc_rot = (int)(((long long)(j / csz) * p.nkc) / ((p.n_slices + csz - 1) / csz));
+  // per-CTA starting K chunk (the K order is free; spreads the chain's CTAs over the tile)
+  const int kc_rot = (int)(((long long)j * p.nkc) / p.n_slices);
   long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
 #define REC_STAMP(step, slot) do { if (dbg) dbg[(step) * 8 + (slot)] = clock64(); } while (0)
 
   if (warp == 0 && lane == 0) {
     // a stage is free once the MMA warps of ALL csz CTAs of the cluster have consumed it (multicast commit)
-    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), csz); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     mbar_init(smem_u32(w_bar), 1);
     mbar_init(smem_u32(acc_full), 1);
     mbar_init(smem_u32(acc_empty), kEpiWarps);
@@ -245,13 +250,12 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), G::TMEM_COLS);
   fence_before_sync();
   __syncthreads();
-  if (csz > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
   fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);   // warp-uniform: tcgen05 operands stay in uniform registers
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
+    // ================= TMA producer (warp-convergent: every lane polls / waits, one elected lane issues) =========
+    if (elect_one()) {
       // resident weights, once
       const uint32_t wb = smem_u32(w_bar);
       mbar_expect_tx(wb, (uint32_t)p.nkc * G::WCHUNK);
@@ -259,64 +263,66 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
         // forward: 64 permuted gate rows of Wh^T ; backward: 16 unit rows of Wh (permuted gate columns = K)
         tma_load_2d(smem_u32(smem_w + (size_t)kc * G::WCHUNK), map_w, wb, kc * BK, j * G::N);
       }
-      int it = 0;
-      for (int s = 1; s < steps; ++s) {
-        // forward pass : step s (forward order) consumes h of step s-1
-        // backward pass: q-th processed step (q = s) consumes dz of the (q-1)-th processed step
-        int t_src;
-        if (!BWD) { const int t = reverse ? steps - 1 - s : s; t_src = reverse ? t + 1 : t - 1; }
-        else      { const int sf = steps - 1 - s; const int t = reverse ? steps - 1 - sf : sf; t_src = reverse ? t - 1 : t + 1; }
-        wait_counter(counters + (s - 1), p.n_slices);
-        fence_proxy_async_all();
-        REC_STAMP(s, 0);
-        for (int kk = 0; kk < p.nkc; ++kk, ++it) {
-          int kc = kk + kc_rot;                       // the K order is free: spread the chain's CTAs over the tile
-          if (kc >= p.nkc) kc -= p.nkc;
-          const int st = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(smem_u32(&empty_bar[st]), ph ^ 1);
+    }
+    __syncwarp();
+    int it = 0;
+    for (int s = 1; s < steps; ++s) {
+      // forward pass : step s (forward order) consumes h of step s-1
+      // backward pass: q-th processed step (q = s) consumes dz of the (q-1)-th processed step
+      int t_src;
+      if (!BWD) { const int t = reverse ? steps - 1 - s : s; t_src = reverse ? t + 1 : t - 1; }
+      else      { const int sf = steps - 1 - s; const int t = reverse ? steps - 1 - sf : sf; t_src = reverse ? t - 1 : t + 1; }
+      wait_counter(counters + (s - 1), p.n_slices);     // all lanes poll the same word: one L2 request per round
+      fence_proxy_async_all();
+      if (lane == 0) REC_STAMP(s, 0);
+      for (int kk = 0; kk < p.nkc; ++kk, ++it) {
+        int kc = kk + kc_rot;                       // the K order is free: spread the chain's CTAs over the tile
+        if (kc >= p.nkc) kc -= p.nkc;
+        const int st = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(smem_u32(&empty_bar[st]), ph ^ 1);
+        if (elect_one()) {
           const uint32_t fb = smem_u32(&full_bar[st]);
           mbar_expect_tx(fb, A_STAGE_BYTES);
-          if (csz == 1) {
-            tma_load_2d(smem_u32(smem_a + (size_t)st * A_STAGE_BYTES), map_a, fb, kc * BK, t_src * B + bt * kBM);
-          } else if (kk % csz == crank) {
-            // one L2 read per cluster: the chunks are dealt round-robin to the cluster's CTAs, each multicast to all
-            tma_load_2d_mc(smem_u32(smem_a + (size_t)st * A_STAGE_BYTES), map_a, fb, kc * BK, t_src * B + bt * kBM, cmask);
-          }
+          tma_load_2d(smem_u32(smem_a + (size_t)st * A_STAGE_BYTES), map_a, fb, kc * BK, t_src * B + bt * kBM);
         }
-        REC_STAMP(s, 1);
+        __syncwarp();
       }
+      if (lane == 0) REC_STAMP(s, 1);
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(kBM, G::N, 0);
-      mbar_wait(smem_u32(w_bar), 0);
+    // ================= MMA issuer (warp-convergent) =================
+    constexpr uint32_t idesc = make_idesc_tf32(kBM, G::N, 0);
+    mbar_wait(smem_u32(w_bar), 0);
+    fence_after_sync();
+    // K-major SWIZZLE_128B descriptors advance linearly with the byte offset (>> 4) as long as bits [0,14) do not wrap
+    const uint64_t desc_a0 = make_smem_desc(smem_u32(smem_a));
+    const uint64_t desc_w0 = make_smem_desc(smem_u32(smem_w));
+    int it = 0;
+    for (int s = 1; s < steps; ++s) {
+      mbar_wait(smem_u32(acc_empty), ((s - 1) & 1) ^ 1);   // epilogue drained the previous accumulator
       fence_after_sync();
-      int it = 0;
-      for (int s = 1; s < steps; ++s) {
-        mbar_wait(smem_u32(acc_empty), ((s - 1) & 1) ^ 1);   // epilogue drained the previous accumulator
+      for (int kk = 0; kk < p.nkc; ++kk, ++it) {
+        int kc = kk + kc_rot;
+        if (kc >= p.nkc) kc -= p.nkc;
+        const int st = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(smem_u32(&full_bar[st]), ph);
         fence_after_sync();
-        for (int kk = 0; kk < p.nkc; ++kk, ++it) {
-          int kc = kk + kc_rot;
-          if (kc >= p.nkc) kc -= p.nkc;
-          const int st = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(smem_u32(&full_bar[st]), ph);
-          fence_after_sync();
-          if (kk == 0) REC_STAMP(s, 2);
-          const uint32_t sa = smem_u32(smem_a + (size_t)st * A_STAGE_BYTES);
-          const uint32_t sw = smem_u32(smem_w + (size_t)kc * G::WCHUNK);
+        if (kk == 0 && lane == 0) REC_STAMP(s, 2);
+        if (elect_one()) {
+          const uint64_t da = desc_a0 + (uint64_t)(((uint32_t)st * A_STAGE_BYTES) >> 4);
+          const uint64_t dw = desc_w0 + (uint64_t)(((uint32_t)kc * G::WCHUNK) >> 4);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_tf32(tmem_base, make_smem_desc(sa + k * UMMA_K * 4), make_smem_desc(sw + k * UMMA_K * 4), idesc,
+            umma_tf32(tmem_base, da + (uint64_t)(k * UMMA_K * 4 >> 4), dw + (uint64_t)(k * UMMA_K * 4 >> 4), idesc,
                       (kk > 0 || k > 0) ? 1u : 0u);
-          if (csz == 1) umma_commit(smem_u32(&empty_bar[st]));
-          else umma_commit_mc(smem_u32(&empty_bar[st]), cmask);
+          umma_commit(smem_u32(&empty_bar[st]));
+          if (kk == p.nkc - 1) umma_commit(smem_u32(acc_full));
         }
-        umma_commit(smem_u32(acc_full));
-        REC_STAMP(s, 3);
+        __syncwarp();
       }
+      if (lane == 0) REC_STAMP(s, 3);
     }
   } else {
     // ================= epilogue: thread = (batch row, kUT hidden units) =================
@@ -389,7 +395,9 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
           REC_STAMP(s, 7);
         }
         // 2) everything only the backward pass needs (gate activations, cell state, dropout copy) goes out after
-        //    the release, off the inter-CTA critical path
+        //    the release, off the inter-CTA critical path -- and only once the release has been issued: a gpu-scope
+        //    release waits for the SM's outstanding stores, so 48 KB of them issued meanwhile would sit in front of it
+        named_bar_sync(3, kEpiThreads);
         if (row_ok) {
           if (valid) stv<4 * kUT>(zrow, z);
           stv<kUT>(cs + ((i64)t * B + b) * H + u0, carry);
@@ -483,10 +491,261 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
   }
   fence_before_sync();
   __syncthreads();
-  if (csz > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into / signal this CTA
   if (warp == 1) {
     fence_after_sync();
     tmem_dealloc(tmem_base, G::TMEM_COLS);
+  }
+}
+
+// ================================================================================================
+// BPTT, reduce-scatter formulation (k_lstm_bptt).  The all-gather kernel above must stream dz_{t+1}[128 x 4H] into every
+// CTA each step (819 KB, 200 tcgen05.mma of K = 8: ~23 us per step at H = 400).  Here every CTA multiplies ONLY ITS OWN
+// 64 gate columns of dz (already in its registers) with the matching 64 columns of Wh for ALL H units:
+//     partial_j[128 x H] = dz[:, G_j] (128 x 64, written by the epilogue threads into a swizzled smem tile)
+//                          x Wh[:, G_j]^T (H x 64, resident in smem for the whole sequence)        -- 16 MMAs per step
+// and stores the partial to an L2-resident workspace; the owner of units U_i sums the n_slices partials of its 16
+// columns in a fixed order (deterministic) when it differentiates the next step.  Per step and CTA: 205 KB written,
+// 205 KB read, no TMA on the critical path (writer and readers all use the generic proxy, so the hand-off is a plain
+// release / acquire on the per-step counter), the recurrent weights are read from HBM once per layer.
+// warps: 0 = weight loader (TMA, once), 1 = MMA issuer (+TMEM owner), 2..9 = compute (thread = batch row x 8 units).
+// ================================================================================================
+struct RecBptt {
+  float* gates[2];        // gate activations in, dz out (in place), permuted gate columns
+  const float* cs[2];
+  const float* dhs;       // [T', B, 2H] grad wrt layer outputs (nullable)
+  const int* lens2;
+  const float* dc_inject; int ldi;
+  const int* inject_t;
+  int* counters;          // [2][n_bt][steps], zeroed before launch
+  float* pws;             // [2 parity][2 dir][n_bt][writer slice][H/4 unit quads][128 rows][4 units] partial dh:
+                          // every warp-wide 16-byte access (32 rows of one unit quad) is 512 contiguous bytes
+  int steps, B, H, n_bt, n_slices;
+  int n_parts, part;      // the H accumulator columns are produced by n_parts MMAs of N <= 256 (multiples of 16)
+  int wbox_rows;          // rows per weight TMA box (H or H/2)
+  long long* dbg;
+};
+static_assert(kUT == 8 && kU == 16, "k_lstm_bptt maps one 32-column k-chunk of the dz tile to one unit group");
+
+constexpr int kBUT = 4;                               // hidden units per compute thread
+constexpr int kBGroups = kU / kBUT;                   // 4 unit sub-groups per slice -> 4 warps per TMEM lane quadrant
+constexpr int kBComputeThreads = 32 * 4 * kBGroups;   // 512
+constexpr int kBpttThreads = 64 + kBComputeThreads;
+
+__global__ void __launch_bounds__(kBpttThreads, 1)
+k_lstm_bptt(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1, RecBptt p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int H = p.H, steps = p.steps, B = p.B;
+  const uint32_t WCH = (uint32_t)H * 128;                 // one 32-column chunk of the resident weights [H rows x 128 B]
+  unsigned char* smem_w = smem;                           // [2 chunks][H][32] K-major, 128B swizzle
+  unsigned char* smem_a = smem + 2 * (size_t)WCH;         // [2 chunks][128][32]  (2 * WCH is a multiple of 1024: H % 16 == 0)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + 2 * A_STAGE_BYTES);
+  uint64_t* w_bar = bars;
+  uint64_t* a_full = bars + 1;     // compute threads -> MMA warp: the dz tile is in smem
+  uint64_t* acc_full = bars + 2;   // MMA warp -> compute threads: partial is in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x % p.n_slices;
+  const int bt = (blockIdx.x / p.n_slices) % p.n_bt;
+  const int d = blockIdx.x / (p.n_slices * p.n_bt);
+  const bool reverse = d == 1;
+  const CUtensorMap* map_w = d ? &map_w1 : &map_w0;
+  int* counters = p.counters + (size_t)(d * p.n_bt + bt) * steps;
+  long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(smem_u32(w_bar), 1);
+    mbar_init(smem_u32(a_full), 1);
+    mbar_init(smem_u32(acc_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // Wh[u, G_j]: rows = all H units, columns = this CTA's 64 permuted gate columns (two 32-column chunks)
+      const uint32_t wb = smem_u32(w_bar);
+      mbar_expect_tx(wb, 2 * WCH);
+      for (int c = 0; c < 2; ++c)
+        for (int r0 = 0; r0 < H; r0 += p.wbox_rows)    // box rows <= 256, a multiple of 8 (every piece 1024-aligned)
+          tma_load_2d(smem_u32(smem_w + (size_t)c * WCH + (size_t)r0 * 128), map_w, wb, j * 64 + c * 32, r0);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    mbar_wait(smem_u32(w_bar), 0);
+    fence_after_sync();
+    const uint64_t desc_a0 = make_smem_desc(smem_u32(smem_a));
+    const uint64_t desc_w0 = make_smem_desc(smem_u32(smem_w));
+    for (int q = 0; q + 1 < steps; ++q) {
+      mbar_wait(smem_u32(a_full), q & 1);
+      fence_after_sync();
+      if (elect_one()) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = desc_a0 + (uint64_t)((c * A_STAGE_BYTES + k * UMMA_K * 4) >> 4);
+            for (int pt = 0; pt < p.n_parts; ++pt) {
+              const int n = min(p.part, H - pt * p.part);
+              const uint64_t dw = desc_w0 + (uint64_t)((c * WCH + (uint32_t)(pt * p.part) * 128 + k * UMMA_K * 4) >> 4);
+              umma_tf32(tmem_base + (uint32_t)(pt * p.part), da, dw, make_idesc_tf32(kBM, n, 0), (c > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+        umma_commit(smem_u32(acc_full));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= compute threads: (batch row, kBUT hidden units) =================
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int sg = ew >> 2;                          // unit sub-group (kBUT units) of this thread
+    const int ug = sg >> 1, sub = sg & 1;            // 8-unit group of the permuted gate layout / which half of it
+    const int r = quad * 32 + lane;
+    const int b = bt * kBM + r;
+    const bool row_ok = b < B;
+    const int u0 = j * kU + sg * kBUT;
+    const int z0 = j * 4 * kU + ug * 4 * kUT + sub * kBUT;   // gate g of these units: z0 + g * kUT .. + kBUT
+    const int len2 = row_ok ? (p.lens2 ? p.lens2[b] : steps) : 0;
+    float* gates = d ? p.gates[1] : p.gates[0];
+    const float* cs = d ? p.cs[1] : p.cs[0];
+    const int col0 = d * H;
+    const bool publisher = threadIdx.x == 64;
+    const size_t chain_sz = (size_t)p.n_slices * kBM * H;                 // one (parity, dir, bt) block of the workspace
+    float* pws_chain = p.pws + (size_t)(d * p.n_bt + bt) * chain_sz;      // + parity * 2 * n_bt * chain_sz
+    const size_t par_stride = (size_t)2 * p.n_bt * chain_sz;
+    // this thread's dz pieces inside the swizzled A tile: chunk ug, row r, 16-byte piece (gate * 2 + sub) XOR (r & 7)
+    const uint32_t a_row = smem_u32(smem_a) + (uint32_t)ug * A_STAGE_BYTES + (uint32_t)r * 128;
+    // TMEM -> workspace: this thread copies columns [hcol0, hcol0 + H / kBGroups) of its row
+    const int ncol = H / kBGroups;
+    const int hcol0 = sg * ncol;
+    float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int q = 0; q < steps; ++q) {
+      const int sf = steps - 1 - q;
+      const int t = reverse ? steps - 1 - sf : sf;
+      const int tp = reverse ? t + 1 : t - 1;
+      const bool valid = row_ok && t < len2;
+      float* zrow = gates + ((i64)t * B + b) * 4 * H + z0;
+      float4 gz[4], cv, cpv, dhv;
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      cv = cpv = dhv = zero4;
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) gz[g] = *reinterpret_cast<const float4*>(zrow + g * kUT);
+        cv = *reinterpret_cast<const float4*>(cs + ((i64)t * B + b) * H + u0);
+        if (sf > 0) cpv = *reinterpret_cast<const float4*>(cs + ((i64)tp * B + b) * H + u0);
+        if (p.dhs) dhv = *reinterpret_cast<const float4*>(p.dhs + ((i64)t * B + b) * 2 * H + col0 + u0);
+      }
+      float4 acc = zero4;
+      if (q > 0) {
+        // every CTA of the chain has stored its partial of step q-1
+        if (publisher) wait_counter(counters + (q - 1), p.n_slices);
+        named_bar_sync(1, kBComputeThreads);
+        if (publisher && dbg) dbg[q * 8 + 0] = clock64();
+        if (valid) {
+          // L2-only loads (the buffer is rewritten by other SMs every two steps); kBatch independent 16-byte loads in
+          // flight per thread, summed in slice order (deterministic)
+          const float* src = pws_chain + (size_t)((q - 1) & 1) * par_stride + ((size_t)(u0 / 4) * kBM + r) * 4;
+          constexpr int kBatch = 9;
+          for (int i0 = 0; i0 < p.n_slices; i0 += kBatch) {
+            float4 v[kBatch];
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i)
+              if (i0 + i < p.n_slices) v[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(i0 + i) * kBM * H));
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i)
+              if (i0 + i < p.n_slices) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }
+          }
+        }
+        if (publisher && dbg) dbg[q * 8 + 1] = clock64();
+      }
+      if (valid) {
+        float4 inj = zero4;
+        if (p.dc_inject) {
+          const int ti = (d == 0 && p.inject_t) ? p.inject_t[b] : 0;
+          if (ti == t) inj = *reinterpret_cast<const float4*>(p.dc_inject + (i64)b * p.ldi + col0 + u0);
+        }
+        auto cell = [](float gi, float gj, float gf, float go, float cvv, float cpp, float dh, float& dc, float& di, float& dj,
+                       float& df, float& dgo) {
+          const float tc_ = tanh_fast(cvv);
+          dgo = dh * tc_ * go * (1.f - go);
+          dc += dh * go * (1.f - tc_ * tc_);
+          di = dc * gj * gi * (1.f - gi);
+          dj = dc * gi * (1.f - gj * gj);
+          df = dc * cpp * gf * (1.f - gf);
+          dc = dc * gf;
+        };
+        float dcx = carry.x + inj.x, dcy = carry.y + inj.y, dcz = carry.z + inj.z, dcw = carry.w + inj.w;
+        float4 di, dj, df, dgo;
+        cell(gz[0].x, gz[1].x, gz[2].x, gz[3].x, cv.x, cpv.x, dhv.x + acc.x, dcx, di.x, dj.x, df.x, dgo.x);
+        cell(gz[0].y, gz[1].y, gz[2].y, gz[3].y, cv.y, cpv.y, dhv.y + acc.y, dcy, di.y, dj.y, df.y, dgo.y);
+        cell(gz[0].z, gz[1].z, gz[2].z, gz[3].z, cv.z, cpv.z, dhv.z + acc.z, dcz, di.z, dj.z, df.z, dgo.z);
+        cell(gz[0].w, gz[1].w, gz[2].w, gz[3].w, cv.w, cpv.w, dhv.w + acc.w, dcw, di.w, dj.w, df.w, dgo.w);
+        carry = make_float4(dcx, dcy, dcz, dcw);
+        gz[0] = di; gz[1] = dj; gz[2] = df; gz[3] = dgo;
+      } else {
+        gz[0] = gz[1] = gz[2] = gz[3] = zero4;
+        carry = zero4;
+      }
+      if (q + 1 < steps) {
+        // dz -> swizzled A tile (rows past B are zero), visible to the tensor core, then hand over to the MMA warp
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t addr = a_row + (uint32_t)(((g * 2 + sub) ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(gz[g].x), "f"(gz[g].y), "f"(gz[g].z),
+                       "f"(gz[g].w) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        named_bar_sync(2, kBComputeThreads);
+        if (publisher) mbar_arrive(smem_u32(a_full));
+        if (publisher && dbg) dbg[q * 8 + 2] = clock64();
+      }
+      // dz to HBM for the weight-gradient GEMMs (off the inter-CTA critical path: overlaps the MMA)
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(zrow + g * kUT) = gz[g];
+      }
+      if (q + 1 < steps) {
+        mbar_wait(smem_u32(acc_full), q & 1);
+        fence_after_sync();
+        if (publisher && dbg) dbg[q * 8 + 3] = clock64();
+        // unit quad (column / 4) of writer slice j lives at ((j * H/4 + quad) * 128 + row) * 4
+        float* dst = pws_chain + (size_t)(q & 1) * par_stride + (size_t)j * kBM * H + ((size_t)(hcol0 / 4) * kBM + r) * 4;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)hcol0;
+        int c = 0;
+        for (; c + 32 <= ncol; c += 32) {
+          float v[32];
+          tmem_ld32(taddr + (uint32_t)c, v);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) stv<4>(dst + (size_t)(c / 4 + g) * kBM * 4, v + g * 4);
+        }
+        for (; c < ncol; c += 4) {
+          float v[4];
+          tmem_ld_cols<4>(taddr + (uint32_t)c, v);
+          stv<4>(dst + (size_t)(c / 4) * kBM * 4, v);
+        }
+        fence_before_sync();
+        if (publisher && dbg) dbg[q * 8 + 4] = clock64();
+        named_bar_sync(1, kBComputeThreads);     // all partial stores of this CTA are ordered before the release below
+        if (publisher) {
+          red_release_gpu(counters + q, 1);
+          if (dbg) dbg[q * 8 + 5] = clock64();
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -561,22 +820,14 @@ inline void rec_launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap
     E2T_CHECK(cudaMemsetAsync(p.dbg, 0, (size_t)p.steps * 8 * sizeof(long long), st));
   }
   dim3 grid((unsigned)(2 * p.n_bt * p.n_slices));
-  // optional cluster (E2T_REC_CLUSTER=<max size>): the largest divisor of n_slices <= max shares every A tile by TMA
-  // multicast (H=400 -> clusters of 5).  Measured on B200 (profiles/README.md): no gain -- L2 already de-duplicates the
-  // chain's concurrent reads of one line and the bound is the aggregate L2->SM delivery rate -- so the default is 1.
-  static int cs_cap = getenv("E2T_REC_CLUSTER") ? atoi(getenv("E2T_REC_CLUSTER")) : 1;
+  // (a cluster sharing every A tile by TMA multicast was measured slower than unicast -- tools/ubench/ingest.cu: the
+  // per-SM ingest of a 208 KB tile is ~2300 cycles alone or hot-shared by 100 CTAs, ~3200 with multicast -- and removed)
   p.csz = 1;
-  for (int c = std::min(cs_cap, 8); c >= 2; --c)
-    if (p.n_slices % c == 0) { p.csz = c; break; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(kThreadsRec); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attrs[2];
   int na = 0;
   attrs[na].id = cudaLaunchAttributeCooperative; attrs[na].val.cooperative = 1; ++na;   // all CTAs co-resident
-  if (p.csz > 1) {
-    attrs[na].id = cudaLaunchAttributeClusterDimension;
-    attrs[na].val.clusterDim.x = (unsigned)p.csz; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = 1; ++na;
-  }
   cfg.attrs = attrs; cfg.numAttrs = na;
   E2T_CHECK(cudaLaunchKernelEx(&cfg, kfn, a0, a1, w0, w1, p));
   if (p.dbg) {
@@ -643,6 +894,76 @@ inline void rec_backward(cudaStream_t st, float* const gates[2], const float* co
     mw[d] = make_map_nd(K[d] + (i64)In * 4 * H, 2, wdims, wstr, wbox);
   }
   rec_launch<true>(st, ma[0], ma[1], mw[0], mw[1], p);
+}
+
+inline size_t bptt_smem_bytes(int H) { return (size_t)2 * H * 128 + 2 * A_STAGE_BYTES + 8 * 8 + 1024; }
+inline size_t bptt_ws_floats(int B, int H) {
+  const int n_bt = (B + kBM - 1) / kBM, n_slices = H / kU;
+  return (size_t)2 * 2 * n_bt * n_slices * kBM * H;
+}
+inline bool bptt_supported(int B, int H) {
+  if (H % kU != 0 || H < kU || H > 512) return false;
+  const int n_bt = (B + kBM - 1) / kBM, n_slices = H / kU;
+  if (2 * n_bt * n_slices > sm_count()) return false;
+  return bptt_smem_bytes(H) <= 227 * 1024;
+}
+
+// BPTT of one BiLSTM layer, reduce-scatter formulation.  K[d]: canonical kernels [In+H, 4H] with permuted gate columns.
+inline void rec_backward_rs(cudaStream_t st, float* const gates[2], const float* const cs[2], const float* dhs,
+                            const float* const K[2], int In, const int* lens2, const float* dc_inject, int ldi,
+                            const int* inject_t, int* counters, float* pws, int steps, int B, int H) {
+  RecBptt p{};
+  for (int d = 0; d < 2; ++d) { p.gates[d] = gates[d]; p.cs[d] = cs[d]; }
+  p.dhs = dhs; p.lens2 = lens2; p.dc_inject = dc_inject; p.ldi = ldi; p.inject_t = inject_t; p.counters = counters;
+  p.pws = pws; p.steps = steps; p.B = B; p.H = H;
+  p.n_bt = (B + kBM - 1) / kBM; p.n_slices = H / kU;
+  p.n_parts = (H + 255) / 256;
+  p.part = (((H + p.n_parts - 1) / p.n_parts) + 15) / 16 * 16;
+  CUtensorMap mw[2];
+  for (int d = 0; d < 2; ++d) {
+    // Wh = rows [In, In+H) of the canonical kernel: [H rows (units), 4H permuted gate columns]; box = 32 columns x 200 rows
+    const i64 wdims[2] = {4 * (i64)H, H}, wstr[2] = {1, 4 * (i64)H};
+    p.wbox_rows = H <= 256 ? H : H / 2;
+    const int wbox[2] = {BK, p.wbox_rows};
+    mw[d] = make_map_nd(K[d] + (i64)In * 4 * H, 2, wdims, wstr, wbox);
+  }
+  auto kfn = k_lstm_bptt;
+  const size_t smem = bptt_smem_bytes(H);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    E2T_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  E2T_CHECK(cudaMemsetAsync(p.counters, 0, (size_t)2 * p.n_bt * p.steps * sizeof(int), st));
+  static int dbg_left = getenv("E2T_REC_DEBUG") ? atoi(getenv("E2T_REC_DEBUG")) : 0;
+  p.dbg = nullptr;
+  if (dbg_left > 0) {
+    E2T_CHECK(cudaMalloc(&p.dbg, (size_t)p.steps * 8 * sizeof(long long)));
+    E2T_CHECK(cudaMemsetAsync(p.dbg, 0, (size_t)p.steps * 8 * sizeof(long long), st));
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * p.n_bt * p.n_slices)); cfg.blockDim = dim3(kBpttThreads);
+  cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeCooperative; attrs[0].val.cooperative = 1;   // all CTAs co-resident
+  cfg.attrs = attrs; cfg.numAttrs = 1;
+  E2T_CHECK(cudaLaunchKernelEx(&cfg, kfn, mw[0], mw[1], p));
+  if (p.dbg) {
+    --dbg_left;
+    std::vector<long long> hst((size_t)p.steps * 8);
+    E2T_CHECK(cudaStreamSynchronize(st));
+    E2T_CHECK(cudaMemcpy(hst.data(), p.dbg, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.dbg);
+    fprintf(stderr, "[rec bptt] steps=%d B=%d H=%d grid=%u (cycles rel. to flag-seen)\n"
+                    "  step  ->partials_summed  ->dz_in_smem  ->acc_seen  ->partial_stored  ->released | step_total\n",
+            p.steps, p.B, p.H, cfg.gridDim.x);
+    for (int q = 1; q + 1 < p.steps; ++q) {
+      const long long* e = &hst[(size_t)q * 8];
+      const long long prev = q > 1 ? hst[(size_t)(q - 1) * 8] : 0;
+      fprintf(stderr, "  %4d  %8lld %8lld %8lld %8lld %8lld | %8lld\n", q, e[1] - e[0], e[2] - e[0], e[3] - e[0], e[4] - e[0],
+              e[5] - e[0], prev ? e[0] - prev : 0);
+    }
+  }
 }
 
 }  // namespace rec

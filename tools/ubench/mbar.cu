@@ -21,8 +21,22 @@ __device__ __forceinline__ void wait_test(uint32_t bar, uint32_t parity) {
   while (!done)
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void wait_hint(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity), "r"(10000000u) : "memory");
+}
+__device__ __forceinline__ void wait_test_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(20);
+  }
+}
 template <int W> __device__ __forceinline__ void wait(uint32_t bar, uint32_t parity) {
-  if (W == 0) wait_bounded(bar, parity); else if (W == 1) wait_loop(bar, parity); else wait_test(bar, parity);
+  if (W == 0) wait_bounded(bar, parity); else if (W == 1) wait_loop(bar, parity); else if (W == 2) wait_test(bar, parity);
+  else if (W == 3) wait_hint(bar, parity); else wait_test_sleep(bar, parity);
 }
 // variant: 0 = two threads in different warps ping-pong over `stages` barriers; 1 = + tcgen05 fence in consumer;
 // 2 = single thread arrive+wait on its own barrier; 3 = producer/consumer in same warp? (n/a)
@@ -63,7 +77,7 @@ __global__ void k(int n, int stages, int variant, long long* out, int stride) {
   }
 }
 template <int W> void run(const char* name, long long* d) {
-  for (int stride : {1, 2, 16})
+  for (int stride : {1})
   for (int variant = 0; variant < 3; variant += 2)
     for (int stages : {1, 6}) {
       if (variant == 2 && stages != 1) continue;
@@ -78,6 +92,6 @@ template <int W> void run(const char* name, long long* d) {
 }
 int main() {
   long long* d; cudaMalloc(&d, 148 * 8);
-  run<0>("bounded", d); run<1>("loop", d); run<2>("test", d);
+  run<1>("loop", d); run<3>("hint", d); run<4>("testsleep", d);
   return 0;
 }
