@@ -201,6 +201,25 @@ void gemm(e2t_handle* h, const float* A, i64 sam, i64 sak, const float* B, i64 s
   LAUNCH(h, kfn, grid, dim3(256), 0, p);
 }
 
+// C[M,N] = A0 B0^T + A1 B1^T (+bias) (+beta C), all operands K-major (row-major [M,K] / [N,K]).  One pass over C on the
+// tensor cores when both halves are eligible, else two plain GEMMs.
+void gemm2(e2t_handle* h, const float* A0, i64 lda0, const float* B0, i64 ldb0, int K0, const float* A1, i64 lda1,
+           const float* B1, i64 ldb1, int K1, float* C, i64 ldc, int M, int N, const float* bias, float beta) {
+#ifndef E2T_EMU
+  if (h->cfg.gemm_backend != E2T_GEMM_SIMT && tc_gemm_nt_supported(A0, lda0, B0, ldb0, C, ldc, M, N, K0) &&
+      tc_gemm_nt_supported(A1, lda1, B1, ldb1, C, ldc, M, N, K1)) {
+    CatScope cs0_(h, h->cat == E2T_CAT_RECURRENT ? E2T_CAT_RECURRENT : E2T_CAT_BULK_GEMM);
+    prof_begin(h, "tc_gemm_nt2", M, N, K0 + K1);
+    tc_gemm_nt2(h->stream, A0, lda0, B0, ldb0, K0, A1, lda1, B1, ldb1, K1, C, ldc, M, N, bias, beta);
+    prof_end(h);
+    ++h->n_launch; ++h->n_launch_tc;
+    return;
+  }
+#endif
+  gemm(h, A0, lda0, 1, B0, 1, ldb0, C, ldc, M, N, K0, bias, beta);
+  gemm(h, A1, lda1, 1, B1, 1, ldb1, C, ldc, M, N, K1, nullptr, 1.f);
+}
+
 // conv-gather GEMMs (A3+A4 fused). mode 1: Y[T2*B, E] = gather(x) Wc + b ; mode 2: dWc[W*C, E] = gather(x)^T dY
 void gemm_conv(e2t_handle* h, int mode, const float* x, const int* lens, int Bsz, int T, int Cch, int Wd, int T2,
                const float* Bmat, i64 sbk, i64 sbn, float* C, i64 ldc, int N, const float* bias, float beta,
@@ -479,9 +498,12 @@ void lstm_xproj(e2t_handle* h, const float* in, int ld_in, int In, int H, const 
 }
 
 // the per-step recurrence (one GEMM + one gate kernel per step): small / unaligned shapes and the decoder
+// xin != NULL: the x-projection is fused into every step's GEMM (z_t = [x_t, h_{t-1}] [Wx; Wh] + b, one pass over z_t);
+// needs h_init.  xin == NULL: gates already hold the x-projection (+bias) and the step GEMM accumulates onto it.
 void lstm_layer_steps(e2t_handle* h, int In4, int H, const float* KT, int ldkt, float* gates, float* cs, float* hs,
                       float* hd, int ldh, int col0, const int* lens2, int steps, int B, bool reverse,
-                      const float* h_init, const float* c_init, DropP dp, int drop_F) {
+                      const float* h_init, const float* c_init, DropP dp, int drop_F, const float* xin = nullptr,
+                      int ld_x = 0, int In = 0, const float* bias = nullptr) {
   const float* WhT = KT + In4;   // In4 = round_up(In, 4): 16-byte aligned start of Wh^T
   CatScope cs_(h, E2T_CAT_RECURRENT);
   for (int s = 0; s < steps; ++s) {
@@ -491,7 +513,8 @@ void lstm_layer_steps(e2t_handle* h, int In4, int H, const float* KT, int ldkt, 
     i64 ldp = s == 0 ? H : ldh;
     const float* cprev = s == 0 ? c_init : cs + (i64)tp * B * H;
     float* z = gates + (i64)t * B * 4 * H;
-    if (hprev) gemm(h, hprev, ldp, 1, WhT, 1, ldkt, z, 4 * H, B, 4 * H, H, nullptr, 1.f);
+    if (xin) gemm2(h, xin + (i64)t * B * ld_x, ld_x, KT, ldkt, In, hprev, ldp, WhT, ldkt, H, z, 4 * H, B, 4 * H, bias, 0.f);
+    else if (hprev) gemm(h, hprev, ldp, 1, WhT, 1, ldkt, z, 4 * H, B, 4 * H, H, nullptr, 1.f);
     LstmFwdP p{};
     p.z = z; p.c_prev = cprev; p.c_out = cs + (i64)t * B * H;
     p.h_out = hs + (i64)t * B * ldh + col0;
@@ -506,6 +529,11 @@ void lstm_layer_forward(e2t_handle* h, const float* in, int ld_in, int In, int H
                         const float* bias, float* gates, float* cs, float* hs, float* hd, int ldh, int col0, const int* lens2,
                         int steps, int B, bool reverse, const float* h_init, const float* c_init, DropP dp,
                         int drop_F) {
+  if (h_init) {   // decoder: x-projection fused into the step GEMMs
+    lstm_layer_steps(h, round_up(In, 4), H, KT, ldkt, gates, cs, hs, hd, ldh, col0, lens2, steps, B, reverse, h_init, c_init, dp,
+                     drop_F, in, ld_in, In, bias);
+    return;
+  }
   lstm_xproj(h, in, ld_in, In, H, KT, ldkt, bias, gates, steps, B);
   lstm_layer_steps(h, round_up(In, 4), H, KT, ldkt, gates, cs, hs, hd, ldh, col0, lens2, steps, B, reverse, h_init, c_init, dp,
                    drop_F);
@@ -714,15 +742,18 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
         float* dKp = h->perm_ws;
         float* dbp = h->perm_ws + (i64)(Ly.In + Ly.H) * 4 * Ly.H;
         lstm_layer_wgrads(h, inp, ld_in, Ly.In, Ly.H, Ly.KP[d], dKp, dbp, Ly.gates[d], Ly.hs, 2 * Ly.H, d * Ly.H, T2, B,
-                          d == 1, nullptr, d_in, ld_din, d == 0 ? 0.f : 1.f);
+                          d == 1, nullptr, nullptr, ld_din, 0.f);
         const i64 rows = Ly.In + Ly.H;
         LAUNCH(h, k_permute_cols, grid1(rows * 4 * Ly.H), dim3(256), 0, dKp, G + Ly.K[d], rows, 4 * Ly.H, Ly.H, 0);
         LAUNCH(h, k_permute_cols, grid1((i64)4 * Ly.H), dim3(256), 0, dbp, G + Ly.b[d], (i64)1, 4 * Ly.H, Ly.H, 0);
       } else {
         lstm_layer_wgrads(h, inp, ld_in, Ly.In, Ly.H, P + Ly.K[d], G + Ly.K[d], G + Ly.b[d], Ly.gates[d], Ly.hs, 2 * Ly.H,
-                          d * Ly.H, T2, B, d == 1, nullptr, d_in, ld_din, d == 0 ? 0.f : 1.f);
+                          d * Ly.H, T2, B, d == 1, nullptr, nullptr, ld_din, 0.f);
       }
     }
+    // d_in [rows, In] = dz_fw Wx_fw^T + dz_bw Wx_bw^T in one pass (canonical K rows [In, 4H] are the K-major B operands)
+    gemm2(h, Ly.gates[0], 4 * Ly.H, rec_ok ? Ly.KP[0] : P + Ly.K[0], 4 * Ly.H, 4 * Ly.H, Ly.gates[1], 4 * Ly.H,
+          rec_ok ? Ly.KP[1] : P + Ly.K[1], 4 * Ly.H, 4 * Ly.H, d_in, ld_din, (int)((i64)T2 * B), Ly.In, nullptr, 0.f);
   }
   // ---- temporal conv
   DropP dpc = make_drop(seed, E2T_STREAM_CONV, c.ff_dropout);
@@ -752,8 +783,8 @@ void decode_step(e2t_handle* h, int rows, const int* prev, const float* h_in, co
   LAUNCH(h, k_embed_fwd, grid1((i64)rows * c.D), dim3(256), 0, prev, Wc + h->demb_w, Wc + h->demb_b, h->g_e, (i64)rows,
          c.D, h->Dp, c.emb_act, none);
   const float* KT = h->dec_KT;
-  gemm(h, h->g_e, h->Dp, 1, KT, 1, h->ld_dec_kt, h->g_z, 4 * c.Hd, rows, 4 * c.Hd, c.D, Wc + h->dec_b, 0.f);
-  gemm(h, h_in, c.Hd, 1, KT + h->Dp, 1, h->ld_dec_kt, h->g_z, 4 * c.Hd, rows, 4 * c.Hd, c.Hd, nullptr, 1.f);
+  gemm2(h, h->g_e, h->Dp, KT, h->ld_dec_kt, c.D, h_in, c.Hd, KT + h->Dp, h->ld_dec_kt, c.Hd, h->g_z, 4 * c.Hd, rows, 4 * c.Hd,
+        Wc + h->dec_b, 0.f);
   LstmFwdP p{};
   p.z = h->g_z; p.c_prev = c_in; p.c_out = c_out; p.h_out = h_out; p.h_drop = nullptr; p.ldh = c.Hd;
   p.lens2 = nullptr; p.t = 0; p.B = rows; p.H = c.Hd; p.dp = none;

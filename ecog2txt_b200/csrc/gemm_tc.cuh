@@ -145,6 +145,8 @@ struct TcGemmP {
   int BN, stages;              // tile width, smem ring depth
   int tiles_m, tiles_n, ksplit, kb_per_split;
   float* ws;                   // split-K partials [ksplit][M][N] (ksplit > 1), reduced by k_splitk_reduce
+  int nkb0;                    // K-concatenated product C = A0 B0^T + A1 B1^T: k-blocks [0, nkb0) come from the first
+  int nkb_total;               // operand pair, [nkb0, nkb_total) from the second (nkb0 == nkb_total: single pair)
 };
 
 constexpr int kGemmThreads = 192;
@@ -161,7 +163,8 @@ __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
 
 template <bool TN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcGemmP p) {
+k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+          const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2, TcGemmP p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t A_BYTES = BM * BK * 4, B_BYTES = (uint32_t)p.BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
@@ -188,7 +191,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
 
   const int n_items = p.tiles_m * p.tiles_n * p.ksplit;
-  const int num_kb_total = (p.K + BK - 1) / BK;
+  const int num_kb_total = p.nkb_total;
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -206,13 +209,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           const uint32_t fb = smem_u32(&full_bar[s]);
           mbar_expect_tx(fb, STAGE_BYTES);
           const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const bool second = kb >= p.nkb0;
+          const CUtensorMap* ma = second ? &map_a2 : &map_a;
+          const CUtensorMap* mb = second ? &map_b2 : &map_b;
+          const int kc = (second ? kb - p.nkb0 : kb) * BK;
           if (!TN) {
-            tma_load_2d(sa, &map_a, fb, kb * BK, m0);
-            tma_load_2d(sa + A_BYTES, &map_b, fb, kb * BK, n0);
+            tma_load_2d(sa, ma, fb, kc, m0);
+            tma_load_2d(sa + A_BYTES, mb, fb, kc, n0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BM / 32; ++i) tma_load_2d(sa + i * (BK * 128), &map_a, fb, m0 + i * 32, kb * BK);
-            for (int i = 0; i < p.BN / 32; ++i) tma_load_2d(sa + A_BYTES + i * (BK * 128), &map_b, fb, n0 + i * 32, kb * BK);
+            for (int i = 0; i < BM / 32; ++i) tma_load_2d(sa + i * (BK * 128), ma, fb, m0 + i * 32, kc);
+            for (int i = 0; i < p.BN / 32; ++i) tma_load_2d(sa + A_BYTES + i * (BK * 128), mb, fb, n0 + i * 32, kc);
           }
         }
         __syncwarp();
@@ -391,9 +398,12 @@ inline int pick_bn(int M, int N, bool tn, int nsm) {
   return best;
 }
 
+// Optional second operand pair (A2, B2, K2): C = A B^T + A2 B2^T (+bias, +beta C) in ONE pass over C -- the two LSTM
+// directions' contributions to d(input), or [x_t, h_{t-1}] [Wx; Wh] of a decoder step, without a read-modify-write of C.
 template <bool TN>
 inline void launch_gemm(cudaStream_t st, const float* A, i64 lda, const float* B, i64 ldb, float* C, i64 ldc, int M, int N,
-                        int K, const float* bias, float beta) {
+                        int K, const float* bias, float beta, const float* A2 = nullptr, i64 lda2 = 0,
+                        const float* B2 = nullptr, i64 ldb2 = 0, int K2 = 0) {
   const int nsm = sm_count_();
   TcGemmP p{};
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.beta = beta;
@@ -401,7 +411,9 @@ inline void launch_gemm(cudaStream_t st, const float* A, i64 lda, const float* B
   if (p.BN > ((N + 15) / 16) * 16) p.BN = ((N + (TN ? 31 : 15)) / (TN ? 32 : 16)) * (TN ? 32 : 16);
   p.tiles_m = (M + BM - 1) / BM;
   p.tiles_n = (N + p.BN - 1) / p.BN;
-  const int num_kb = (K + BK - 1) / BK;
+  p.nkb0 = (K + BK - 1) / BK;
+  const int num_kb = p.nkb0 + (A2 ? (K2 + BK - 1) / BK : 0);
+  p.nkb_total = num_kb;
   const int tiles = p.tiles_m * p.tiles_n;
   p.ksplit = 1;
   if (tiles * 2 <= nsm && num_kb >= 16) {       // few output tiles, long K (weight gradients): split K over the idle SMs
@@ -423,9 +435,14 @@ inline void launch_gemm(cudaStream_t st, const float* A, i64 lda, const float* B
     }
     p.ws = w.p;
   }
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, ma2, mb2;
   if (!TN) { ma = make_map(A, M, K, lda, BM); mb = make_map(B, N, K, ldb, p.BN); }
   else { ma = make_map(A, K, M, lda, BK, true); mb = make_map(B, K, N, ldb, BK, true); }
+  ma2 = ma; mb2 = mb;
+  if (A2) {
+    if (!TN) { ma2 = make_map(A2, M, K2, lda2, BM); mb2 = make_map(B2, N, K2, ldb2, p.BN); }
+    else { ma2 = make_map(A2, K2, M, lda2, BK, true); mb2 = make_map(B2, K2, N, ldb2, BK, true); }
+  }
   auto kfn = k_gemm_tc<TN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -433,7 +450,7 @@ inline void launch_gemm(cudaStream_t st, const float* A, i64 lda, const float* B
     attr_set = true;
   }
   const int grid = std::min(tiles * p.ksplit, nsm);
-  kfn<<<grid, kGemmThreads, gemm_smem_bytes(p.BN, p.stages), st>>>(ma, mb, p);
+  kfn<<<grid, kGemmThreads, gemm_smem_bytes(p.BN, p.stages), st>>>(ma, mb, ma2, mb2, p);
   if (p.ksplit > 1) {
     const i64 n = (i64)M * N;
     k_splitk_reduce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.ws, p.ksplit, M, N, C, ldc, bias, beta);
@@ -457,6 +474,12 @@ static inline bool tc_gemm_nt_supported(const float* A, i64 lda, const float* B,
 static inline void tc_gemm_nt(cudaStream_t st, const float* A, i64 lda, const float* B, i64 ldb, float* C, i64 ldc, int M,
                               int N, int K, const float* bias, float beta) {
   tc::launch_gemm<false>(st, A, lda, B, ldb, C, ldc, M, N, K, bias, beta);
+}
+// C = A B^T + A2 B2^T (+bias) (+beta C): all four operands K-major
+static inline void tc_gemm_nt2(cudaStream_t st, const float* A, i64 lda, const float* B, i64 ldb, int K, const float* A2,
+                               i64 lda2, const float* B2, i64 ldb2, int K2, float* C, i64 ldc, int M, int N,
+                               const float* bias, float beta) {
+  tc::launch_gemm<false>(st, A, lda, B, ldb, C, ldc, M, N, K, bias, beta, A2, lda2, B2, ldb2, K2);
 }
 
 // C[M,N] = A[K,M]^T B[K,N]  (A, B row-major with leading dims lda, ldb): weight gradients.

@@ -126,6 +126,16 @@ __device__ __forceinline__ void stv(float* dst, const float* src) {
   for (int i = 0; i < N / 4; ++i)
     *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(src[4 * i], src[4 * i + 1], src[4 * i + 2], src[4 * i + 3]);
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 template <int NCOL>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v);
 template <>
@@ -236,7 +246,10 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
   // per-CTA starting K chunk (the K order is free; spreads the chain's CTAs over the tile)
   const int kc_rot = (int)(((long long)j * p.nkc) / p.n_slices);
   long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
-#define REC_STAMP(step, slot) do { if (dbg) dbg[(step) * 8 + (slot)] = clock64(); } while (0)
+  // every CTA also stamps one probe step with the device-wide timer ([steps*8 + blockIdx*8 + slot]): who is late?
+  long long* dbgx = p.dbg ? p.dbg + (size_t)p.steps * 8 + (size_t)blockIdx.x * 8 : nullptr;
+#define REC_STAMP(step, slot) do { if (dbg) dbg[(step) * 8 + (slot)] = clock64(); \
+    if (dbgx && (step) == 10) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); dbgx[slot] = (long long)gt_; } } while (0)
 
   if (warp == 0 && lane == 0) {
     // a stage is free once the MMA warps of ALL csz CTAs of the cluster have consumed it (multicast commit)
@@ -529,7 +542,7 @@ static_assert(kUT == 8 && kU == 16, "k_lstm_bptt maps one 32-column k-chunk of t
 constexpr int kBUT = 4;                               // hidden units per compute thread
 constexpr int kBGroups = kU / kBUT;                   // 4 unit sub-groups per slice -> 4 warps per TMEM lane quadrant
 constexpr int kBComputeThreads = 32 * 4 * kBGroups;   // 512
-constexpr int kBpttThreads = 64 + kBComputeThreads;
+constexpr int kBpttThreads = kBComputeThreads;          // no dedicated issue warps: 512 threads -> 128 registers each
 
 __global__ void __launch_bounds__(kBpttThreads, 1)
 k_lstm_bptt(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1, RecBptt p) {
@@ -561,7 +574,7 @@ k_lstm_bptt(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -577,35 +590,14 @@ k_lstm_bptt(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ 
           tma_load_2d(smem_u32(smem_w + (size_t)c * WCH + (size_t)r0 * 128), map_w, wb, j * 64 + c * 32, r0);
     }
     __syncwarp();
-  } else if (warp == 1) {
     mbar_wait(smem_u32(w_bar), 0);
-    fence_after_sync();
-    const uint64_t desc_a0 = make_smem_desc(smem_u32(smem_a));
-    const uint64_t desc_w0 = make_smem_desc(smem_u32(smem_w));
-    for (int q = 0; q + 1 < steps; ++q) {
-      mbar_wait(smem_u32(a_full), q & 1);
-      fence_after_sync();
-      if (elect_one()) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = desc_a0 + (uint64_t)((c * A_STAGE_BYTES + k * UMMA_K * 4) >> 4);
-            for (int pt = 0; pt < p.n_parts; ++pt) {
-              const int n = min(p.part, H - pt * p.part);
-              const uint64_t dw = desc_w0 + (uint64_t)((c * WCH + (uint32_t)(pt * p.part) * 128 + k * UMMA_K * 4) >> 4);
-              umma_tf32(tmem_base + (uint32_t)(pt * p.part), da, dw, make_idesc_tf32(kBM, n, 0), (c > 0 || k > 0) ? 1u : 0u);
-            }
-          }
-        umma_commit(smem_u32(acc_full));
-      }
-      __syncwarp();
-    }
-  } else {
+  }
+  const uint64_t desc_a0 = make_smem_desc(smem_u32(smem_a));
+  const uint64_t desc_w0 = make_smem_desc(smem_u32(smem_w));
+  {
     // ================= compute threads: (batch row, kBUT hidden units) =================
-    const int ew = warp - 2;
     const int quad = warp & 3;
-    const int sg = ew >> 2;                          // unit sub-group (kBUT units) of this thread
+    const int sg = warp >> 2;                        // unit sub-group (kBUT units) of this thread
     const int ug = sg >> 1, sub = sg & 1;            // 8-unit group of the permuted gate layout / which half of it
     const int r = quad * 32 + lane;
     const int b = bt * kBM + r;
@@ -616,7 +608,7 @@ k_lstm_bptt(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ 
     float* gates = d ? p.gates[1] : p.gates[0];
     const float* cs = d ? p.cs[1] : p.cs[0];
     const int col0 = d * H;
-    const bool publisher = threadIdx.x == 64;
+    const bool publisher = threadIdx.x == 0;
     const size_t chain_sz = (size_t)p.n_slices * kBM * H;                 // one (parity, dir, bt) block of the workspace
     float* pws_chain = p.pws + (size_t)(d * p.n_bt + bt) * chain_sz;      // + parity * 2 * n_bt * chain_sz
     const size_t par_stride = (size_t)2 * p.n_bt * chain_sz;
@@ -703,9 +695,27 @@ k_lstm_bptt(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ 
                        "f"(gz[g].w) : "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        fence_before_sync();                 // this thread's tcgen05.ld of the previous step precede the next MMAs
         named_bar_sync(2, kBComputeThreads);
-        if (publisher) mbar_arrive(smem_u32(a_full));
-        if (publisher && dbg) dbg[q * 8 + 2] = clock64();
+        if (warp == 0) {
+          fence_after_sync();
+          if (publisher && dbg) dbg[q * 8 + 2] = clock64();
+          if (elect_one()) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t da = desc_a0 + (uint64_t)((c * A_STAGE_BYTES + k * UMMA_K * 4) >> 4);
+                for (int pt = 0; pt < p.n_parts; ++pt) {
+                  const int n = min(p.part, H - pt * p.part);
+                  const uint64_t dw = desc_w0 + (uint64_t)((c * WCH + (uint32_t)(pt * p.part) * 128 + k * UMMA_K * 4) >> 4);
+                  umma_tf32(tmem_base + (uint32_t)(pt * p.part), da, dw, make_idesc_tf32(kBM, n, 0), (c > 0 || k > 0) ? 1u : 0u);
+                }
+              }
+            umma_commit(smem_u32(acc_full));
+          }
+          __syncwarp();
+        }
       }
       // dz to HBM for the weight-gradient GEMMs (off the inter-CTA critical path: overlaps the MMA)
       if (row_ok) {
@@ -719,13 +729,23 @@ k_lstm_bptt(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ 
         // unit quad (column / 4) of writer slice j lives at ((j * H/4 + quad) * 128 + row) * 4
         float* dst = pws_chain + (size_t)(q & 1) * par_stride + (size_t)j * kBM * H + ((size_t)(hcol0 / 4) * kBM + r) * 4;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)hcol0;
+        // TMEM reads (64 B/clk) and the global stores overlap: the next 16 columns are in flight while these are stored
         int c = 0;
-        for (; c + 32 <= ncol; c += 32) {
-          float v[32];
-          tmem_ld32(taddr + (uint32_t)c, v);
+        float va[16], vb[16];
+        if (ncol >= 16) tmem_ld16_nowait(taddr, va);
+        for (; c + 16 <= ncol; c += 32) {
+          tmem_ld_wait();
+          if (c + 32 <= ncol) tmem_ld16_nowait(taddr + (uint32_t)(c + 16), vb);
 #pragma unroll
-          for (int g = 0; g < 8; ++g) stv<4>(dst + (size_t)(c / 4 + g) * kBM * 4, v + g * 4);
+          for (int g = 0; g < 4; ++g) stv<4>(dst + (size_t)(c / 4 + g) * kBM * 4, va + g * 4);
+          if (c + 32 <= ncol) {
+            tmem_ld_wait();
+            if (c + 48 <= ncol) tmem_ld16_nowait(taddr + (uint32_t)(c + 32), va);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) stv<4>(dst + (size_t)((c + 16) / 4 + g) * kBM * 4, vb + g * 4);
+          }
         }
+        c = ncol / 16 * 16;
         for (; c < ncol; c += 4) {
           float v[4];
           tmem_ld_cols<4>(taddr + (uint32_t)c, v);
@@ -743,7 +763,7 @@ k_lstm_bptt(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ 
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 0) {
     fence_after_sync();
     tmem_dealloc(tmem_base, 512);
   }
@@ -815,11 +835,12 @@ inline void rec_launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap
   p.dbg = nullptr;
   static int pub_mode = getenv("E2T_REC_PUB") ? atoi(getenv("E2T_REC_PUB")) : 3;
   p.pub_mode = pub_mode;
-  if (dbg_left > 0) {
-    E2T_CHECK(cudaMalloc(&p.dbg, (size_t)p.steps * 8 * sizeof(long long)));
-    E2T_CHECK(cudaMemsetAsync(p.dbg, 0, (size_t)p.steps * 8 * sizeof(long long), st));
-  }
   dim3 grid((unsigned)(2 * p.n_bt * p.n_slices));
+  const size_t dbg_n = ((size_t)p.steps + grid.x) * 8;
+  if (dbg_left > 0) {
+    E2T_CHECK(cudaMalloc(&p.dbg, dbg_n * sizeof(long long)));
+    E2T_CHECK(cudaMemsetAsync(p.dbg, 0, dbg_n * sizeof(long long), st));
+  }
   // (a cluster sharing every A tile by TMA multicast was measured slower than unicast -- tools/ubench/ingest.cu: the
   // per-SM ingest of a 208 KB tile is ~2300 cycles alone or hot-shared by 100 CTAs, ~3200 with multicast -- and removed)
   p.csz = 1;
@@ -832,10 +853,22 @@ inline void rec_launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap
   E2T_CHECK(cudaLaunchKernelEx(&cfg, kfn, a0, a1, w0, w1, p));
   if (p.dbg) {
     --dbg_left;
-    std::vector<long long> hst((size_t)p.steps * 8);
+    std::vector<long long> hst(dbg_n);
     E2T_CHECK(cudaStreamSynchronize(st));
     E2T_CHECK(cudaMemcpy(hst.data(), p.dbg, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(p.dbg);
+    if (p.steps > 11) {
+      // probe step 10, all CTAs, ns relative to the earliest flag-seen
+      long long t0 = -1;
+      for (unsigned c = 0; c < grid.x; ++c) { const long long v = hst[((size_t)p.steps + c) * 8]; if (v && (t0 < 0 || v < t0)) t0 = v; }
+      fprintf(stderr, "[rec %s probe step 10] cta: flag_seen tma_issued first_full mma_committed acc_seen h_stored bar released (ns)\n", BWD ? "bwd" : "fwd");
+      for (unsigned c = 0; c < grid.x; ++c) {
+        const long long* e = &hst[((size_t)p.steps + c) * 8];
+        fprintf(stderr, "  cta %3u:", c);
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %6lld", e[k] ? e[k] - t0 : -1);
+        fprintf(stderr, "\n");
+      }
+    }
     fprintf(stderr, "[rec %s] steps=%d B=%d H=%d nkc=%d stages=%d cluster=%d grid=%u  (cycles rel. to flag-seen of each step)\n"
                     "  step  flag->tma_issued  ->first_full  ->mma_committed  ->acc_seen  ->h_stored  ->bar_passed  ->released | step_total\n",
             BWD ? "bwd" : "fwd", p.steps, p.B, p.H, p.nkc, p.stages, p.csz, grid.x);

@@ -8,11 +8,6 @@
 #include "gemm_tc.cuh"
 using namespace tc;
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
 template <int BN>
 __global__ void __launch_bounds__(192, 1)
 k_ub(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int num_kb, int kb_wrap, int mode,
@@ -36,7 +31,49 @@ k_ub(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensor
   const int m0 = (blockIdx.x % m_tiles) * BM;
   const int n0 = 0;
   long long t0 = clock64();
-  if (mode == 8 || mode == 9) {
+  if (mode == 10 || mode == 11) {
+    // like 8/9 but only lane 0 polls the mbarrier, then the warp reconverges
+    if (warp == 4) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % stages; const uint32_t ph = (kb / stages) & 1;
+        if (lane == 0) mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+        __syncwarp();
+        const uint32_t fb = smem_u32(&full_bar[s]);
+        if (elect_one()) {
+          if (mode == 10) {
+            mbar_expect_tx(fb, STAGE_BYTES);
+            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+            tma_load_2d(sa, &map_a, fb, (kb % kb_wrap) * BK, m0);
+            tma_load_2d(sa + A_BYTES, &map_b, fb, (kb % kb_wrap) * BK, n0);
+          } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fb) : "memory");
+          }
+        }
+        __syncwarp();
+      }
+    } else if (warp == 5) {
+      constexpr uint32_t idesc = make_idesc_tf32(BM, BN, 0);
+      const uint32_t tb = __reduce_max_sync(0xffffffffu, tmem_base);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % stages; const uint32_t ph = (kb / stages) & 1;
+        if (lane == 0) mbar_wait(smem_u32(&full_bar[s]), ph);
+        __syncwarp();
+        fence_after_sync();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_tf32(tb, make_smem_desc(sa + k * UMMA_K * 4), make_smem_desc(sa + A_BYTES + k * UMMA_K * 4), idesc, 1u);
+          umma_commit(smem_u32(&empty_bar[s]));
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(smem_u32(done_bar));
+      __syncwarp();
+      mbar_wait(smem_u32(done_bar), 0);
+      if (lane == 0) out_cycles[blockIdx.x] = clock64() - t0;
+    }
+  } else if (mode == 8 || mode == 9) {
     // warp-convergent roles: every lane runs the loop and the waits, one elected lane issues (mode 9: MMA only)
     if (warp == 4) {
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -224,7 +261,7 @@ int main() {
   cudaMemset(dA, 0, (size_t)M * K * 4); cudaMemset(dB, 0, (size_t)256 * K * 4);
   const int nkb = 2000;
   for (int grid : {148}) {
-    for (int mode : {8, 9}) for (int R : {1}) {
+    for (int mode : {8, 10, 11}) for (int R : {1}) {
       run<64>(mode, 6, grid, dA, dB, M, K, nkb, dcy, R);
       run<128>(mode, 6, grid, dA, dB, M, K, nkb, dcy, R);
       run<256>(mode, 4, grid, dA, dB, M, K, nkb, dcy, R);
