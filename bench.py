@@ -190,9 +190,18 @@ def main():
 
     ntok_cache = [float((hy != 0).sum()) for _, hy in host]
 
+    staged = {"next": None}
+
     def step_host(i):
-        hx, hy = host[i % NPOOL]
-        loss, ntok = eng.train_step_grads(hx.numpy(), None, hy.numpy(), seed=i, want_loss=True)  # H2D x,y ; D2H loss
+        # end to end through the public API with HOST buffers: the H2D copy of THIS step's batch was started (pinned
+        # memory, library copy stream) while the previous step computed; every step copies its inputs and reads its loss
+        if staged["next"] != i:
+            hx, hy = host[i % NPOOL]
+            eng.stage_inputs(i & 1, hx.numpy(), None, hy.numpy())
+        hx, hy = host[(i + 1) % NPOOL]
+        eng.stage_inputs((i + 1) & 1, hx.numpy(), None, hy.numpy())
+        staged["next"] = i + 1
+        loss, ntok = eng.train_step_grads_staged(i & 1, seed=i, want_loss=True)   # D2H loss, ntok
         if world > 1:
             ntok_t[0] = ntok
             dist.all_reduce(grads)

@@ -11,7 +11,7 @@ import os
 
 E2T_MAX_SUBNETS = 16
 E2T_MAX_LAYERS = 8
-HOST, DEVICE = 0, 1
+HOST, DEVICE, STAGED0, STAGED1 = 0, 1, 2, 3
 VALUE, GRAD, ADAM_M, ADAM_V, EMA = 0, 1, 2, 3, 4
 ACT = {"linear": 0, "relu": 1}
 GEMM = {"auto": 0, "simt": 1, "tcgen05": 2}
@@ -73,6 +73,7 @@ _SIGNATURES = {
     "e2t_set_step": (C.c_int, [_P, C.c_int64]),
     "e2t_train_step_grads": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                        C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "e2t_stage_inputs": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
     "e2t_adam_ema_step": (C.c_int, [_P, C.c_int, C.c_float]),
     "e2t_eval_loss": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.POINTER(C.c_float), C.POINTER(C.c_int32)]),

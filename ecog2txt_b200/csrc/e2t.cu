@@ -106,6 +106,14 @@ struct e2t_handle {
   float* rec_pws = nullptr; i64 rec_pws_n = 0;       // partial-dh workspace of the reduce-scatter BPTT kernel
   int* rec_counters = nullptr;   // arrival counters of the persistent recurrent kernels [2][n_bt][T2m]
   int64_t n_launch_rec = 0;
+  // double-buffered input staging (e2t_stage_inputs): slot 0 aliases d_x / d_lens_in / d_y
+  cudaStream_t copy_stream = nullptr;
+  float* st_x[2] = {nullptr, nullptr}; int* st_lens[2] = {nullptr, nullptr}; int* st_y[2] = {nullptr, nullptr};
+  bool st_has_lens[2] = {false, false}, st_has_y[2] = {false, false};
+  int st_B[2] = {0, 0}, st_T[2] = {0, 0}, st_L[2] = {0, 0}, st_subnet[2] = {0, 0};
+#ifndef E2T_EMU
+  cudaEvent_t st_ready[2] = {nullptr, nullptr}, st_done[2] = {nullptr, nullptr};
+#endif
   // decode workspace
   float *g_h[2], *g_c[2], *g_e, *g_z, *g_logits, *g_logp, *g_score[2], *g_lse;
   int *g_prev[2], *g_done[2], *g_tokens[2], *g_src, *g_tok;
@@ -466,7 +474,7 @@ Inputs stage(e2t_handle* h, int subnet, const float* x, const int32_t* lens, con
   E2T_REQUIRE(B >= 1 && B <= h->Bm, "B exceeds max_B");
   E2T_REQUIRE(T >= 1 && T <= h->Tm, "T exceeds max_T");
   E2T_REQUIRE(L >= 0 && L <= h->Lm, "L exceeds max_L");
-  E2T_REQUIRE(x != nullptr, "x is NULL");
+  E2T_REQUIRE(x != nullptr || loc == E2T_STAGED0 || loc == E2T_STAGED1, "x is NULL");
   Inputs in{};
   if (loc == E2T_HOST) {
     size_t nx = (size_t)B * T * c.subnet_C[subnet];
@@ -480,11 +488,33 @@ Inputs stage(e2t_handle* h, int subnet, const float* x, const int32_t* lens, con
       E2T_CHECK(cudaMemcpyAsync(h->d_y, y, (size_t)B * L * sizeof(int), cudaMemcpyHostToDevice, h->stream));
       in.y = h->d_y;
     }
+  } else if (loc == E2T_STAGED0 || loc == E2T_STAGED1) {
+#ifdef E2T_EMU
+    throw std::runtime_error("e2t: staged inputs are not available in the emulation build");
+#else
+    const int slot = loc - E2T_STAGED0;
+    E2T_REQUIRE(h->st_ready[slot] != nullptr, "slot was never staged (e2t_stage_inputs)");
+    E2T_REQUIRE(h->st_B[slot] == B && h->st_T[slot] == T && h->st_L[slot] == L && h->st_subnet[slot] == subnet,
+                "staged slot holds a batch of another shape / subject");
+    E2T_CHECK(cudaStreamWaitEvent(h->stream, h->st_ready[slot], 0));
+    in.x = h->st_x[slot];
+    in.lens_in = h->st_has_lens[slot] ? h->st_lens[slot] : nullptr;
+    in.y = h->st_has_y[slot] ? h->st_y[slot] : nullptr;
+#endif
   } else {
-    E2T_REQUIRE(loc == E2T_DEVICE, "loc must be E2T_HOST or E2T_DEVICE");
+    E2T_REQUIRE(loc == E2T_DEVICE, "loc must be E2T_HOST, E2T_DEVICE or E2T_STAGED0/1");
     in.x = x; in.lens_in = lens; in.y = y;
   }
   return in;
+}
+
+// after the last kernel that reads a staged slot has been enqueued: the copy stream may overwrite it
+void release_slot(e2t_handle* h, int loc) {
+#ifndef E2T_EMU
+  if (loc == E2T_STAGED0 || loc == E2T_STAGED1) E2T_CHECK(cudaEventRecord(h->st_done[loc - E2T_STAGED0], h->stream));
+#else
+  (void)h; (void)loc;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -857,6 +887,10 @@ extern "C" int e2t_destroy(e2t_handle* h) {
   if (!h) return 0;
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
+#ifndef E2T_EMU
+  for (int i = 0; i < 2; ++i) { if (h->st_ready[i]) cudaEventDestroy(h->st_ready[i]); if (h->st_done[i]) cudaEventDestroy(h->st_done[i]); }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+#endif
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return 0;
@@ -929,14 +963,53 @@ extern "C" int e2t_train_step_grads(e2t_handle* h, int subnet, const float* x, c
                                     int loc, int B, int T, int L, uint32_t dropout_seed, float* loss_sum,
                                     int32_t* ntok) {
   API_BEGIN NEED_H;
-  E2T_REQUIRE(y != nullptr && L >= 1, "training needs targets");
+  E2T_REQUIRE((y != nullptr || loc == E2T_STAGED0 || loc == E2T_STAGED1) && L >= 1, "training needs targets");
   Inputs in = stage(h, subnet, x, lens, y, loc, B, T, L);
+  E2T_REQUIRE(in.y != nullptr, "training needs targets");
   use_weights(h, false);
   encoder_forward(h, subnet, in, B, T, true, dropout_seed);
   decoder_forward(h, in, B, L, true, dropout_seed, true);
   backward(h, subnet, in, B, T, L, dropout_seed);
   E2T_CHECK(cudaGetLastError());
+  release_slot(h, loc);
   read_loss(h, loss_sum, ntok);
+  API_END
+}
+
+extern "C" int e2t_stage_inputs(e2t_handle* h, int slot, int subnet, const float* x, const int32_t* lens, const int32_t* y,
+                                int B, int T, int L) {
+  API_BEGIN NEED_H;
+#ifdef E2T_EMU
+  (void)slot; (void)subnet; (void)x; (void)lens; (void)y; (void)B; (void)T; (void)L;
+  throw std::runtime_error("e2t: staged inputs are not available in the emulation build");
+#else
+  const e2t_config& c = h->cfg;
+  E2T_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+  E2T_REQUIRE(subnet >= 0 && subnet < c.n_subnets, "subnet index out of range");
+  E2T_REQUIRE(x != nullptr && B >= 1 && B <= h->Bm && T >= 1 && T <= h->Tm && L >= 0 && L <= h->Lm, "bad staging arguments");
+  if (!h->copy_stream) E2T_CHECK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  if (!h->st_ready[slot]) {
+    E2T_CHECK(cudaEventCreateWithFlags(&h->st_ready[slot], cudaEventDisableTiming));
+    E2T_CHECK(cudaEventCreateWithFlags(&h->st_done[slot], cudaEventDisableTiming));
+    if (slot == 0) { h->st_x[0] = h->d_x; h->st_lens[0] = h->d_lens_in; h->st_y[0] = h->d_y; }
+    else {
+      h->st_x[1] = h->alloc<float>((i64)h->Bm * h->Tm * h->Cmax);
+      h->st_lens[1] = h->alloc<int>(h->Bm);
+      h->st_y[1] = h->alloc<int>((i64)h->Bm * h->Lm);
+      E2T_CHECK(cudaDeviceSynchronize());   // alloc() zero-fills on the legacy stream
+    }
+    E2T_CHECK(cudaEventRecord(h->st_done[slot], h->stream));
+  }
+  // the previous consumer of this slot must have finished with it
+  E2T_CHECK(cudaStreamWaitEvent(h->copy_stream, h->st_done[slot], 0));
+  const size_t nx = (size_t)B * T * c.subnet_C[subnet];
+  E2T_CHECK(cudaMemcpyAsync(h->st_x[slot], x, nx * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
+  if (lens) E2T_CHECK(cudaMemcpyAsync(h->st_lens[slot], lens, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, h->copy_stream));
+  if (y) E2T_CHECK(cudaMemcpyAsync(h->st_y[slot], y, (size_t)B * L * sizeof(int), cudaMemcpyHostToDevice, h->copy_stream));
+  h->st_has_lens[slot] = lens != nullptr; h->st_has_y[slot] = y != nullptr;
+  h->st_B[slot] = B; h->st_T[slot] = T; h->st_L[slot] = L; h->st_subnet[slot] = subnet;
+  E2T_CHECK(cudaEventRecord(h->st_ready[slot], h->copy_stream));
+#endif
   API_END
 }
 
@@ -978,6 +1051,7 @@ extern "C" int e2t_eval_loss(e2t_handle* h, int subnet, const float* x, const in
   encoder_forward(h, subnet, in, B, T, false, 0);
   decoder_forward(h, in, B, L, false, 0, false);
   E2T_CHECK(cudaGetLastError());
+  release_slot(h, loc);
   read_loss(h, loss_sum, ntok);
   API_END
 }
@@ -992,6 +1066,7 @@ extern "C" int e2t_greedy_decode(e2t_handle* h, int subnet, const float* x, cons
   Inputs in = stage(h, subnet, x, lens, nullptr, loc, B, T, 0);
   use_weights(h, use_ema != 0);
   encoder_forward(h, subnet, in, B, T, false, 0);
+  release_slot(h, loc);
   LAUNCH(h, k_fill_int, grid1(B), dim3(256), 0, h->g_prev[0], c.start_id, (i64)B);
   E2T_CHECK(cudaMemsetAsync(h->g_done[0], 0, (size_t)B * sizeof(int), h->stream));
   const float* hin = h->h0; const float* cin = h->c0;
@@ -1022,6 +1097,7 @@ extern "C" int e2t_beam_decode(e2t_handle* h, int subnet, const float* x, const 
   Inputs in = stage(h, subnet, x, lens, nullptr, loc, B, T, 0);
   use_weights(h, use_ema != 0);
   encoder_forward(h, subnet, in, B, T, false, 0);
+  release_slot(h, loc);
   const int R = B * beam;
   // state buffers: cur (index a) holds the live beams; decode_step writes the candidates into slot 2 = g_z-adjacent
   // we use g_h[0]/g_c[0] as current, g_h[1]/g_c[1] as new, and reorder back into [0] through a temporary swap.

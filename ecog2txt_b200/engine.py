@@ -206,6 +206,28 @@ class Engine:
         self._ck(self._lib.e2t_train_step_grads(self._h, subnet, px, pl, py, loc, B, T, Lk, seed & 0xFFFFFFFF, None, None))
         return None
 
+    def stage_inputs(self, slot: int, x: np.ndarray, lens, y, subnet: int = 0):
+        """Start the host->device copy of a minibatch into staging slot 0/1 on the library's copy stream (returns at once
+        when the arrays are page-locked); consume it with train_step_grads_staged(slot, ...)."""
+        if not isinstance(x, np.ndarray):
+            raise TypeError("stage_inputs takes host (numpy) arrays")
+        px, pl, py, _, B, T = self._inputs(x, lens, y)
+        Lk = int(y.shape[1]) if y is not None else 0
+        self._ck(self._lib.e2t_stage_inputs(self._h, slot, subnet, px, pl, py, B, T, Lk))
+        self._staged_shape = getattr(self, "_staged_shape", {})
+        self._staged_shape[slot] = (B, T, Lk, subnet)
+
+    def train_step_grads_staged(self, slot: int, seed: int = 0, want_loss: bool = True):
+        B, T, Lk, subnet = self._staged_shape[slot]
+        loc = L.STAGED0 + slot
+        if want_loss:
+            loss, ntok = C.c_float(), C.c_int32()
+            self._ck(self._lib.e2t_train_step_grads(self._h, subnet, None, None, None, loc, B, T, Lk, seed & 0xFFFFFFFF,
+                                                    C.byref(loss), C.byref(ntok)))
+            return float(loss.value), int(ntok.value)
+        self._ck(self._lib.e2t_train_step_grads(self._h, subnet, None, None, None, loc, B, T, Lk, seed & 0xFFFFFFFF, None, None))
+        return None
+
     def adam_ema_step(self, grad_scale: float, subnet: int = -1):
         self._ck(self._lib.e2t_adam_ema_step(self._h, subnet, float(grad_scale)))
 

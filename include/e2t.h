@@ -31,6 +31,8 @@ extern "C" {
 #define E2T_MAX_LAYERS 8
 #define E2T_HOST 0
 #define E2T_DEVICE 1
+#define E2T_STAGED0 2   /* inputs were copied ahead of time into staging slot 0 / 1 by e2t_stage_inputs */
+#define E2T_STAGED1 3
 
 /* which copy of a parameter tensor */
 #define E2T_VALUE 0   /* trained variable                                      */
@@ -111,6 +113,12 @@ int e2t_set_step(e2t_handle* h, int64_t step);
 int e2t_train_step_grads(e2t_handle* h, int subnet, const float* x, const int32_t* lens,
                          const int32_t* y, int loc, int B, int T, int L, uint32_t dropout_seed,
                          float* loss_sum, int32_t* ntok);
+/* Input pipeline (the tf.data prefetch of the reference, trainers.py:891-901): copy the NEXT minibatch host -> device on
+ * the library's copy stream while the current step computes.  Two slots; a slot is overwritten only after the step that
+ * consumed it has finished (event-ordered, no host synchronisation).  Consume with loc = E2T_STAGED0 + slot and the same
+ * subnet / B / T / L (x, lens, y arguments are then ignored).  Host buffers should be page-locked for the copy to overlap. */
+int e2t_stage_inputs(e2t_handle* h, int slot, int subnet, const float* x, const int32_t* lens,
+                     const int32_t* y, int B, int T, int L);
 /* Adam + EMA on the trainable tensors of `subnet` (private) and the shared ones, using
  * grad * grad_scale (1 / global token count).  subnet < 0: every subnet. */
 int e2t_adam_ema_step(e2t_handle* h, int subnet, float grad_scale);
