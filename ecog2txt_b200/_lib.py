@@ -15,7 +15,8 @@ HOST, DEVICE, STAGED0, STAGED1 = 0, 1, 2, 3
 VALUE, GRAD, ADAM_M, ADAM_V, EMA = 0, 1, 2, 3, 4
 ACT = {"linear": 0, "relu": 1}
 GEMM = {"auto": 0, "simt": 1, "tcgen05": 2}
-ABI_VERSION = 2
+ATTN = {"none": 0, "luong": 1}
+ABI_VERSION = 3
 
 
 class E2TConfig(C.Structure):
@@ -49,6 +50,7 @@ class E2TConfig(C.Structure):
         ("penalty_scale", C.c_float),
         ("gemm_backend", C.c_int32),
         ("device", C.c_int32),
+        ("attention", C.c_int32),
     ]
 
 

@@ -29,7 +29,7 @@
 
 static thread_local std::string g_err;
 extern "C" const char* e2t_last_error(void) { return g_err.c_str(); }
-extern "C" int e2t_abi_version(void) { return 2; }
+extern "C" int e2t_abi_version(void) { return 3; }
 
 namespace {
 
@@ -85,6 +85,11 @@ struct e2t_handle {
   i64 conv_w[E2T_MAX_SUBNETS], conv_b[E2T_MAX_SUBNETS];
   std::vector<EncLayer> enc;
   i64 demb_w, demb_b, dec_K, dec_b, proj_w, proj_b;
+  i64 at_wq = 0, at_wc = 0, at_bc = 0;          // attention parameters (cfg.attention != NONE)
+  float *at_q = nullptr, *at_ctx = nullptr, *at_ht = nullptr, *at_alpha = nullptr, *at_dscore = nullptr;
+  float *at_dht = nullptr, *at_dctx = nullptr, *at_dq = nullptr;
+  float *at_combT = nullptr, *at_queryT = nullptr;   // packed transposes for the backward GEMMs
+  float *g_q = nullptr, *g_ctx = nullptr, *g_ht = nullptr, *g_alpha = nullptr;
 
   // capacities
   int Bm, Tm, Lm, T2m, Cmax, Dp, Vp, beam_m;
@@ -322,6 +327,12 @@ void build_params(e2t_handle* h) {
   snprintf(buf, sizeof buf, "seq2seq/decoder_projection_%d_%d_0", c.Hd, c.V);
   h->proj_w = h->n_params; add_tensor(h, std::string(buf) + "/weights", {c.V, c.Hd}, -1);
   h->proj_b = h->n_params; add_tensor(h, std::string(buf) + "/biases", {c.V}, -1);
+  if (c.attention == E2T_ATTN_LUONG) {
+    // stored [out, in] like the projection (trainers.py:513-520), i.e. already the K-major B operand of the forward GEMMs
+    h->at_wq = h->n_params; add_tensor(h, "seq2seq/decoder_attention/query/weights", {c.Hd, c.Hd}, -1);
+    h->at_wc = h->n_params; add_tensor(h, "seq2seq/decoder_attention/combine/weights", {c.Hd, 2 * c.Hd}, -1);
+    h->at_bc = h->n_params; add_tensor(h, "seq2seq/decoder_attention/combine/biases", {c.Hd}, -1);
+  }
 }
 
 void validate(const e2t_config& c) {
@@ -338,6 +349,7 @@ void validate(const e2t_config& c) {
   E2T_REQUIRE(c.ff_dropout >= 0.f && c.ff_dropout < 1.f && c.rnn_dropout >= 0.f && c.rnn_dropout < 1.f,
               "dropout must be in [0,1)");
   E2T_REQUIRE(c.max_beam >= 1 && c.max_beam <= 32, "max_beam must be in [1,32]");
+  E2T_REQUIRE(c.attention == E2T_ATTN_NONE || c.attention == E2T_ATTN_LUONG, "attention must be E2T_ATTN_NONE or E2T_ATTN_LUONG");
 }
 
 void build_workspace(e2t_handle* h) {
@@ -410,6 +422,17 @@ void build_workspace(e2t_handle* h) {
       h->conv_wT_lo[s] = h->alloc<float>((i64)c.E * round_up(c.subnet_W[s] * c.subnet_C[s], 4));
 #endif
   }
+  if (c.attention != E2T_ATTN_NONE) {
+    const i64 n = Lm * Bm * c.Hd;
+    h->at_q = h->alloc<float>(n); h->at_ctx = h->alloc<float>(n); h->at_ht = h->alloc<float>(n);
+    h->at_dht = h->alloc<float>(n); h->at_dctx = h->alloc<float>(n); h->at_dq = h->alloc<float>(n);
+    h->at_alpha = h->alloc<float>(Lm * Bm * T2); h->at_dscore = h->alloc<float>(Lm * Bm * T2);
+    h->at_combT = h->alloc<float>((i64)2 * c.Hd * c.Hd); h->at_queryT = h->alloc<float>((i64)c.Hd * c.Hd);
+    const i64 Rr = Bm * h->beam_m;
+    h->g_q = h->alloc<float>(Rr * c.Hd); h->g_ctx = h->alloc<float>(Rr * c.Hd); h->g_ht = h->alloc<float>(Rr * c.Hd);
+    h->g_alpha = h->alloc<float>(Rr * T2);
+    h->colsum_ws_n = std::max<i64>(h->colsum_ws_n, (i64)64 * c.Hd);
+  }
   // decode workspace (rows = B*beam)
   const i64 R = Bm * h->beam_m;
   for (int i = 0; i < 2; ++i) {
@@ -445,6 +468,10 @@ void repack(e2t_handle* h, const float* src, int src_id) {
   tr(src + h->dec_K, 4 * c.Hd, h->dec_KT, h->ld_dec_kt, c.D, 4 * c.Hd);
   tr(src + h->dec_K + (i64)c.D * 4 * c.Hd, 4 * c.Hd, h->dec_KT + h->Dp, h->ld_dec_kt, c.Hd, 4 * c.Hd);
   tr(src + h->proj_w, c.Hd, h->proj_wT, h->Vp, c.V, c.Hd);
+  if (c.attention != E2T_ATTN_NONE) {
+    tr(src + h->at_wc, 2 * c.Hd, h->at_combT, c.Hd, c.Hd, 2 * c.Hd);      // [Hd, 2Hd] -> [2Hd, Hd]
+    tr(src + h->at_wq, c.Hd, h->at_queryT, c.Hd, c.Hd, c.Hd);
+  }
   for (int s = 0; s < c.n_subnets; ++s) {
     int WC = c.subnet_W[s] * c.subnet_C[s];
     tr(src + h->conv_w[s], c.E, h->conv_wT[s], round_up(WC, 4), WC, c.E);
@@ -633,8 +660,21 @@ void decoder_forward(e2t_handle* h, const Inputs& in, int B, int L, bool train, 
   DropP none = make_drop(0, 0, 0.f);
   lstm_layer_forward(h, h->demb, h->Dp, c.D, c.Hd, h->dec_KT, h->ld_dec_kt, Wc + h->dec_b, h->dgates, h->dcs, h->hdec, nullptr,
                      c.Hd, 0, nullptr, L, B, false, h->h0, h->c0, none, 0);
-  // logits = hdec Wp^T + b ; Wp canonical [V,Hd] is already the K-major B operand
-  gemm(h, h->hdec, c.Hd, 1, Wc + h->proj_w, 1, c.Hd, h->logits, h->Vp, (int)rows, c.V, c.Hd, Wc + h->proj_b, 0.f);
+  const float* proj_in = h->hdec;
+  if (c.attention != E2T_ATTN_NONE) {
+    // A7: q = hdec Wq^T ; fused score/softmax/context over the last encoder layer ; h~ = tanh([ctx, hdec] Wc^T + bc)
+    const EncLayer& top = h->enc.back();
+    const int T2 = h->last_T2;
+    gemm(h, h->hdec, c.Hd, 1, Wc + h->at_wq, 1, c.Hd, h->at_q, c.Hd, (int)rows, c.Hd, c.Hd, nullptr, 0.f);
+    LAUNCH(h, k_attn_fwd, dim3((unsigned)rows), dim3(128), (size_t)T2 * sizeof(float), h->at_q, top.hs, h->d_lens2,
+           h->at_alpha, h->at_ctx, B, B, 1, T2, c.Hd, h->T2m);
+    gemm2(h, h->at_ctx, c.Hd, Wc + h->at_wc, 2 * c.Hd, c.Hd, h->hdec, c.Hd, Wc + h->at_wc + c.Hd, 2 * c.Hd, c.Hd, h->at_ht,
+          c.Hd, (int)rows, c.Hd, Wc + h->at_bc, 0.f);
+    LAUNCH(h, k_tanh_fwd, grid1(rows * c.Hd), dim3(256), 0, h->at_ht, rows * c.Hd);
+    proj_in = h->at_ht;
+  }
+  // logits = h Wp^T + b ; Wp canonical [V,Hd] is already the K-major B operand
+  gemm(h, proj_in, c.Hd, 1, Wc + h->proj_w, 1, c.Hd, h->logits, h->Vp, (int)rows, c.V, c.Hd, Wc + h->proj_b, 0.f);
   LAUNCH(h, k_softmax_ce, dim3((unsigned)rows), dim3(128), 0, h->logits, h->Vp, c.V, h->d_tgt, c.pad_id,
          c.penalty_scale, h->loss_rows, with_grad ? 1 : 0);
   LAUNCH(h, k_reduce_loss, dim3(1), dim3(256), 0, h->loss_rows, h->d_tgt, c.pad_id, (int)rows, h->d_loss, h->d_ntok);
@@ -707,10 +747,29 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
   const i64 rows = (i64)L * B;
   E2T_CHECK(cudaMemsetAsync(G, 0, (size_t)h->n_params * sizeof(float), h->stream));
   // ---- projection: logits already hold dlogits
-  gemm(h, h->logits, 1, h->Vp, h->hdec, c.Hd, 1, G + h->proj_w, c.Hd, c.V, c.Hd, (int)rows, nullptr, 0.f);
+  const bool attn = c.attention != E2T_ATTN_NONE;
+  const float* proj_in = attn ? h->at_ht : h->hdec;
+  gemm(h, h->logits, 1, h->Vp, proj_in, c.Hd, 1, G + h->proj_w, c.Hd, c.V, c.Hd, (int)rows, nullptr, 0.f);
   colsum(h, h->logits, rows, c.V, h->Vp, G + h->proj_b);
-  // dhdec [rows,Hd] = dlogits Wp ; B operand (k=v, n=u) = Wp[v*Hd+u] -> packed transpose is the K-major form
-  gemm(h, h->logits, h->Vp, 1, h->proj_wT, 1, h->Vp, h->dhdec, c.Hd, (int)rows, c.Hd, c.V, nullptr, 0.f);
+  // d(proj input) [rows,Hd] = dlogits Wp ; B operand (k=v, n=u) = Wp[v*Hd+u] -> packed transpose is the K-major form
+  gemm(h, h->logits, h->Vp, 1, h->proj_wT, 1, h->Vp, attn ? h->at_dht : h->dhdec, c.Hd, (int)rows, c.Hd, c.V, nullptr, 0.f);
+  if (attn) {
+    const EncLayer& top = h->enc.back();
+    LAUNCH(h, k_tanh_bwd, grid1(rows * c.Hd), dim3(256), 0, h->at_dht, h->at_ht, rows * c.Hd);      // -> d(pre-tanh)
+    // dWc [Hd, 2Hd] = dpre^T [ctx, hdec] ; dbc
+    gemm(h, h->at_dht, 1, c.Hd, h->at_ctx, c.Hd, 1, G + h->at_wc, 2 * c.Hd, c.Hd, c.Hd, (int)rows, nullptr, 0.f);
+    gemm(h, h->at_dht, 1, c.Hd, h->hdec, c.Hd, 1, G + h->at_wc + c.Hd, 2 * c.Hd, c.Hd, c.Hd, (int)rows, nullptr, 0.f);
+    colsum(h, h->at_dht, rows, c.Hd, c.Hd, G + h->at_bc);
+    // dctx = dpre Wc[:, :Hd]
+    gemm(h, h->at_dht, c.Hd, 1, h->at_combT, 1, c.Hd, h->at_dctx, c.Hd, (int)rows, c.Hd, c.Hd, nullptr, 0.f);
+    LAUNCH(h, k_attn_bwd_q, dim3((unsigned)rows), dim3(128), (size_t)T2 * sizeof(float), h->at_dctx, top.hs, h->d_lens2,
+           h->at_alpha, h->at_dscore, h->at_dq, B, B, T2, c.Hd, h->T2m);
+    // dWq [Hd, Hd] = dq^T hdec
+    gemm(h, h->at_dq, 1, c.Hd, h->hdec, c.Hd, 1, G + h->at_wq, c.Hd, c.Hd, c.Hd, (int)rows, nullptr, 0.f);
+    // dhdec = dpre Wc[:, Hd:] + dq Wq   (one pass)
+    gemm2(h, h->at_dht, c.Hd, h->at_combT + (i64)c.Hd * c.Hd, c.Hd, c.Hd, h->at_dq, c.Hd, h->at_queryT, c.Hd, c.Hd, h->dhdec,
+          c.Hd, (int)rows, c.Hd, nullptr, 0.f);
+  }
   // ---- decoder recurrence
   lstm_layer_backward(h, c.Hd, P + h->dec_K, c.D, h->dgates, h->dcs, h->dhdec, c.Hd, 0, nullptr, L, B, false, h->c0,
                       nullptr, 0, nullptr, -1);
@@ -733,6 +792,9 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
     if (l == nl - 1) {
       E2T_CHECK(cudaMemsetAsync(Ly.dhs, 0, (size_t)n_out * sizeof(float), h->stream));
       LAUNCH(h, k_scatter_final, grid1((i64)B * 2 * Ly.H), dim3(256), 0, Ly.dhs, h->dh0, h->d_lens2, B, Ly.H);
+      if (attn)   // the attention's gradient wrt the encoder outputs joins the bridge's
+        LAUNCH(h, k_attn_bwd_enc, dim3((unsigned)B), dim3(256), (size_t)2 * L * T2 * sizeof(float), h->at_dctx, h->at_q,
+               h->at_alpha, h->at_dscore, h->d_lens2, Ly.dhs, L, B, T2, c.Hd, h->T2m);
     } else if (c.rnn_dropout > 0.f) {
       DropP dp = make_drop(seed, E2T_STREAM_ENC0 + l, c.rnn_dropout);
       LAUNCH(h, k_dropout_bwd, grid1(n_out), dim3(256), 0, Ly.dhs, n_out, dp);
@@ -806,7 +868,7 @@ void read_loss(e2t_handle* h, float* loss_sum, int32_t* ntok) {
 
 // one decoder step for `rows` state rows (greedy: rows = B, beam: rows = B*beam)
 void decode_step(e2t_handle* h, int rows, const int* prev, const float* h_in, const float* c_in, float* h_out,
-                 float* c_out) {
+                 float* c_out, int B, int beam) {
   const e2t_config& c = h->cfg;
   const float* Wc = h->Wc;
   DropP none = make_drop(0, 0, 0.f);
@@ -819,7 +881,19 @@ void decode_step(e2t_handle* h, int rows, const int* prev, const float* h_in, co
   p.z = h->g_z; p.c_prev = c_in; p.c_out = c_out; p.h_out = h_out; p.h_drop = nullptr; p.ldh = c.Hd;
   p.lens2 = nullptr; p.t = 0; p.B = rows; p.H = c.Hd; p.dp = none;
   LAUNCH(h, k_lstm_fwd, grid1((i64)rows * c.Hd), dim3(256), 0, p);
-  gemm(h, h_out, c.Hd, 1, Wc + h->proj_w, 1, c.Hd, h->g_logits, h->Vp, rows, c.V, c.Hd, Wc + h->proj_b, 0.f);
+  const float* proj_in = h_out;
+  if (c.attention != E2T_ATTN_NONE) {
+    const EncLayer& top = h->enc.back();
+    const int T2 = h->last_T2;
+    gemm(h, h_out, c.Hd, 1, Wc + h->at_wq, 1, c.Hd, h->g_q, c.Hd, rows, c.Hd, c.Hd, nullptr, 0.f);
+    LAUNCH(h, k_attn_fwd, dim3((unsigned)rows), dim3(128), (size_t)T2 * sizeof(float), h->g_q, top.hs, h->d_lens2,
+           h->g_alpha, h->g_ctx, rows, B, beam, T2, c.Hd, h->T2m);
+    gemm2(h, h->g_ctx, c.Hd, Wc + h->at_wc, 2 * c.Hd, c.Hd, h_out, c.Hd, Wc + h->at_wc + c.Hd, 2 * c.Hd, c.Hd, h->g_ht, c.Hd,
+          rows, c.Hd, Wc + h->at_bc, 0.f);
+    LAUNCH(h, k_tanh_fwd, grid1((i64)rows * c.Hd), dim3(256), 0, h->g_ht, (i64)rows * c.Hd);
+    proj_in = h->g_ht;
+  }
+  gemm(h, proj_in, c.Hd, 1, Wc + h->proj_w, 1, c.Hd, h->g_logits, h->Vp, rows, c.V, c.Hd, Wc + h->proj_b, 0.f);
 }
 
 TensorInfo& find_tensor(e2t_handle* h, const char* name) {
@@ -1072,7 +1146,7 @@ extern "C" int e2t_greedy_decode(e2t_handle* h, int subnet, const float* x, cons
   const float* hin = h->h0; const float* cin = h->c0;
   for (int k = 0; k < max_len; ++k) {
     float* ho = h->g_h[k & 1]; float* co = h->g_c[k & 1];
-    decode_step(h, B, h->g_prev[0], hin, cin, ho, co);
+    decode_step(h, B, h->g_prev[0], hin, cin, ho, co, B, 1);
     LAUNCH(h, k_greedy_pick, dim3(B), dim3(128), 0, h->g_logits, h->Vp, c.V, 1.0f / temperature, k, max_len, c.pad_id,
            c.eos_id, h->g_prev[0], h->g_done[0], h->g_tokens[0], h->g_logp);
     hin = ho; cin = co;
@@ -1112,7 +1186,7 @@ extern "C" int e2t_beam_decode(e2t_handle* h, int subnet, const float* x, const 
   int cur = 0;
   for (int k = 0; k < max_len; ++k) {
     int nxt = cur ^ 1;
-    decode_step(h, R, h->g_prev[cur], h->g_h[cur], h->g_c[cur], h->g_h[nxt], h->g_c[nxt]);
+    decode_step(h, R, h->g_prev[cur], h->g_h[cur], h->g_c[cur], h->g_h[nxt], h->g_c[nxt], B, beam);
     LAUNCH(h, k_beam_topk, dim3(B), dim3(256), 0, h->g_logits, h->Vp, c.V, 1.0f / temperature, beam, h->g_score[cur],
            h->g_done[cur], c.pad_id, h->g_lse, h->g_score[nxt], h->g_src, h->g_tok);
     BeamStepP p{};

@@ -294,6 +294,126 @@ __global__ void k_scatter_final(float* dhs, const float* dh0, const int* lens2, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// A7: Luong ("general") attention over the last encoder layer's outputs, fused score / masked softmax / context.
+// The reference model has no attention; north_star asks for it, so it is an optional module
+// (e2t_config.attention) whose normative spec is oracle/seq2seq_oracle.py: decoder_step (parity unpinned).
+//   q = h Wq^T (GEMM, outside) ; score[s] = q . enc[s] for s < lens2[b] ; alpha = softmax(score) ; ctx = sum_s alpha[s] enc[s]
+// One block per decoder row r (time-major rows r = k*R + j of q / ctx / alpha; encoder batch index b = j / bdiv, so that the
+// beam rows of one utterance share its encoder outputs).  enc [T2, Benc, F] time-major.  Scores live in shared memory
+// (T2 floats); each thread keeps its F/blockDim query elements in registers; nothing but alpha and ctx goes to HBM.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_attn_fwd(const float* __restrict__ q, const float* __restrict__ enc, const int* __restrict__ lens2, float* alpha,
+           float* ctx, int R, int Benc, int bdiv, int T2, int F, int ld_alpha) {
+  E2T_DYN_SMEM(float, sc);                 // [T2] scores -> probabilities
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  const int j = r % R;
+  const int b = j / bdiv;
+  const int len = min(lens2[b], T2);
+  const float* qr = q + (i64)r * F;
+  for (int s = 0; s < len; ++s) {
+    const float* er = enc + ((i64)s * Benc + b) * F;
+    float a = 0.f;
+    for (int u = threadIdx.x; u < F; u += blockDim.x) a = fmaf(qr[u], er[u], a);
+    a = block_sum(a, red);
+    if (threadIdx.x == 0) sc[s] = a;
+  }
+  __syncthreads();
+  float m = -3.0e38f;
+  for (int s = threadIdx.x; s < len; s += blockDim.x) m = fmaxf(m, sc[s]);
+  m = block_max(m, red);
+  float z = 0.f;
+  for (int s = threadIdx.x; s < len; s += blockDim.x) { const float e = expf(sc[s] - m); sc[s] = e; z += e; }
+  z = block_sum(z, red);
+  const float inv = len > 0 ? 1.0f / z : 0.f;
+  __syncthreads();
+  for (int s = threadIdx.x; s < T2; s += blockDim.x) {
+    const float pv = s < len ? sc[s] * inv : 0.f;
+    if (s < len) sc[s] = pv;
+    alpha[(i64)r * ld_alpha + s] = pv;
+  }
+  __syncthreads();
+  for (int u = threadIdx.x; u < F; u += blockDim.x) {
+    float a = 0.f;
+    for (int s = 0; s < len; ++s) a = fmaf(sc[s], enc[((i64)s * Benc + b) * F + u], a);
+    ctx[(i64)r * F + u] = a;
+  }
+}
+// backward, phase 1 (one block per decoder row): dalpha[s] = dctx . enc[s] ; dscore = alpha * (dalpha - sum alpha dalpha)
+// (written over alpha's companion buffer dscore) ; dq[u] = sum_s dscore[s] enc[s][u]
+__global__ void __launch_bounds__(128)
+k_attn_bwd_q(const float* __restrict__ dctx, const float* __restrict__ enc, const int* __restrict__ lens2,
+             const float* __restrict__ alpha, float* dscore, float* dq, int R, int Benc, int T2, int F, int ld_alpha) {
+  E2T_DYN_SMEM(float, sc);                 // [T2] dalpha -> dscore
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  const int b = r % R;
+  const int len = min(lens2[b], T2);
+  const float* dr = dctx + (i64)r * F;
+  const float* ar = alpha + (i64)r * ld_alpha;
+  for (int s = 0; s < len; ++s) {
+    const float* er = enc + ((i64)s * Benc + b) * F;
+    float a = 0.f;
+    for (int u = threadIdx.x; u < F; u += blockDim.x) a = fmaf(dr[u], er[u], a);
+    a = block_sum(a, red);
+    if (threadIdx.x == 0) sc[s] = a;
+  }
+  __syncthreads();
+  float t = 0.f;
+  for (int s = threadIdx.x; s < len; s += blockDim.x) t = fmaf(ar[s], sc[s], t);
+  t = block_sum(t, red);
+  __syncthreads();
+  for (int s = threadIdx.x; s < T2; s += blockDim.x) {
+    const float v = s < len ? ar[s] * (sc[s] - t) : 0.f;
+    if (s < len) sc[s] = v;
+    dscore[(i64)r * ld_alpha + s] = v;
+  }
+  __syncthreads();
+  for (int u = threadIdx.x; u < F; u += blockDim.x) {
+    float a = 0.f;
+    for (int s = 0; s < len; ++s) a = fmaf(sc[s], enc[((i64)s * Benc + b) * F + u], a);
+    dq[(i64)r * F + u] = a;
+  }
+}
+// backward, phase 2 (one block per utterance b; thread = feature u): denc[s,b,u] += sum_k alpha[k,b,s] dctx[k,b,u]
+// + dscore[k,b,s] q[k,b,u], the L decoder steps summed in order (deterministic, no atomics).
+__global__ void __launch_bounds__(256)
+k_attn_bwd_enc(const float* __restrict__ dctx, const float* __restrict__ q, const float* __restrict__ alpha,
+               const float* __restrict__ dscore, const int* __restrict__ lens2, float* denc, int L, int B, int T2, int F,
+               int ld_alpha) {
+  E2T_DYN_SMEM(float, sm);                 // [2][L][T2]: alpha, dscore of this utterance
+  const int b = blockIdx.x;
+  const int len = min(lens2[b], T2);
+  for (int i = threadIdx.x; i < L * T2; i += blockDim.x) {
+    const int k = i / T2, s = i - k * T2;
+    sm[i] = alpha[((i64)k * B + b) * ld_alpha + s];
+    sm[L * T2 + i] = dscore[((i64)k * B + b) * ld_alpha + s];
+  }
+  __syncthreads();
+  for (int u = threadIdx.x; u < F; u += blockDim.x) {
+    for (int s = 0; s < len; ++s) {
+      float a = 0.f;
+      for (int k = 0; k < L; ++k) {
+        const i64 row = ((i64)k * B + b) * F + u;
+        a = fmaf(sm[k * T2 + s], dctx[row], a);
+        a = fmaf(sm[L * T2 + k * T2 + s], q[row], a);
+      }
+      denc[((i64)s * B + b) * F + u] += a;
+    }
+  }
+}
+// X <- tanh(X) in place ; and its backward dX <- dX * (1 - out^2)
+__global__ void k_tanh_fwd(float* X, i64 n) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) X[i] = tanhf(X[i]);
+}
+__global__ void k_tanh_bwd(float* dX, const float* out, i64 n) {
+  i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const float o = out[i]; dX[i] *= 1.f - o * o; }
+}
+
+// ------------------------------------------------------------------------------------------------
 // A8: decoder inputs.  y [B,L] -> time-major prev[k,b] (teacher forcing, start token first) and tgt[k,b]
 // ------------------------------------------------------------------------------------------------
 __global__ void k_shift_targets(const int* y, int* prev, int* tgt, int B, int L, int start_id, int V) {

@@ -41,6 +41,7 @@ class EngineConfig:
     penalty_scale: float = 1.0
     gemm_backend: str = "auto"
     device: int = 0
+    attention: str = "none"    # "luong": optional A7 module (not in the reference model)
 
     def to_c(self) -> L.E2TConfig:
         c = L.E2TConfig()
@@ -63,6 +64,7 @@ class EngineConfig:
         c.lr, c.beta1, c.beta2, c.eps = self.lr, self.beta1, self.beta2, self.eps
         c.ema_decay, c.penalty_scale = self.ema_decay, self.penalty_scale
         c.gemm_backend, c.device = L.GEMM[self.gemm_backend], self.device
+        c.attention = L.ATTN[self.attention]
         return c
 
 

@@ -39,7 +39,7 @@ _MANIFEST_KEYS = dict(layer_sizes=None, FF_dropout=0.0, RNN_dropout=0.0, TEMPORA
 class SequenceNetwork:
     def __init__(self, manifest, EOS_token=_EOS, pad_token=_PAD, OOV_token=_OOV, training_GPUs=(0,),
                  TARGETS_ARE_SEQUENCES=True, VERBOSE=True, N_cases=256, max_hyp_length=20, learning_rate=5e-4,
-                 seed=1, gemm_backend="auto", lib=None, **kwargs):
+                 seed=1, gemm_backend="auto", attention="none", lib=None, **kwargs):
         # utils_jgm.auto_attribute(CHECK_MANIFEST=True): a keyword wins, else manifest[key] (README.md:42)
         for key, default in _MANIFEST_KEYS.items():
             if key in kwargs and kwargs[key] is not None:
@@ -63,6 +63,7 @@ class SequenceNetwork:
         self.VERBOSE = VERBOSE
         self.N_cases, self.max_hyp_length, self.learning_rate, self.seed = N_cases, max_hyp_length, learning_rate, seed
         self.gemm_backend = gemm_backend
+        self.attention = attention       # "luong": optional A7 module (default "none" = the reference model)
         self.checkpoint_path: Optional[str] = None
         self.inputs_to_occlude = None
         self._lib = lib
@@ -94,7 +95,7 @@ class SequenceNetwork:
 
     def _get_engine(self, subnets_params, max_T, max_L) -> Engine:
         geo, flist = self._geometry(subnets_params)
-        key = (tuple(sorted(geo.items())), self.FF_dropout, self.RNN_dropout, self.EMA_decay, int(self.beam_width), self.N_cases)
+        key = (tuple(sorted(geo.items())), self.attention, self.FF_dropout, self.RNN_dropout, self.EMA_decay, int(self.beam_width), self.N_cases)
         e = self._engine
         if e is None or self._engine_key != key or e.cfg.max_T < max_T or e.cfg.max_L < max_L:
             if e is not None:
@@ -103,7 +104,8 @@ class SequenceNetwork:
             cfg = EngineConfig(**geo, max_B=self.N_cases, max_T=max_T, max_L=max(max_L, self.max_hyp_length),
                                max_beam=max(int(self.beam_width), 1), ff_dropout=float(self.FF_dropout),
                                rnn_dropout=float(self.RNN_dropout), lr=self.learning_rate,
-                               ema_decay=float(self.EMA_decay), gemm_backend=self.gemm_backend, device=dev)
+                               ema_decay=float(self.EMA_decay), gemm_backend=self.gemm_backend, device=dev,
+                               attention=self.attention)
             self._engine = Engine(cfg, lib=self._lib)
             prm.init_engine(self._engine, self.seed)
             self._engine_key = key

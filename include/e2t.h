@@ -45,6 +45,10 @@ extern "C" {
 #define E2T_ACT_LINEAR 0
 #define E2T_ACT_RELU 1
 
+/* decoder attention (A7) */
+#define E2T_ATTN_NONE 0
+#define E2T_ATTN_LUONG 1    /* q = h Wq^T; alpha = softmax_s(q . enc_s); h~ = tanh(Wc [ctx; h] + bc); logits from h~ */
+
 /* GEMM backends */
 #define E2T_GEMM_AUTO 0     /* tcgen05 where shapes allow, SIMT otherwise */
 #define E2T_GEMM_SIMT 1     /* fp32 CUDA-core tiles only (validation path) */
@@ -75,6 +79,8 @@ typedef struct e2t_config {
   float penalty_scale;                   /* decoder_targets penalty_scale, subjects.py:289 */
   int32_t gemm_backend;                  /* E2T_GEMM_* */
   int32_t device;                        /* CUDA device ordinal */
+  int32_t attention;                     /* E2T_ATTN_*: optional Luong attention over the encoder outputs (not in the
+                                          * reference model; default NONE = reference behaviour) */
 } e2t_config;
 
 const char* e2t_last_error(void);

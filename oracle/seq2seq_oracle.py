@@ -60,6 +60,7 @@ class OracleConfig:
     beta2: float = 0.999
     eps: float = 1e-8
     ema_decay: float = 0.99                   # yaml:3
+    attention: str = "none"                   # "luong": optional A7 module [CHOICE; absent from the reference, SURVEY 0.5]
 
     def __post_init__(self):
         assert self.Hd == 2 * self.H[-1], "bridge needs decoder_rnn == 2*encoder_rnn[-1]"
@@ -90,6 +91,11 @@ def param_shapes(cfg: OracleConfig) -> "Dict[str, Tuple[int, ...]]":
     base = f"seq2seq/decoder_projection_{cfg.Hd}_{cfg.V}_0"
     shapes[base + "/weights"] = (cfg.V, cfg.Hd)            # transposed, trainers.py:513-520
     shapes[base + "/biases"] = (cfg.V,)
+    if cfg.attention == "luong":
+        # stored [out, in] like the projection; q = h Wq^T, h~ = tanh(Wc [ctx; h] + bc)
+        shapes["seq2seq/decoder_attention/query/weights"] = (cfg.Hd, cfg.Hd)
+        shapes["seq2seq/decoder_attention/combine/weights"] = (cfg.Hd, 2 * cfg.Hd)
+        shapes["seq2seq/decoder_attention/combine/biases"] = (cfg.Hd,)
     return shapes
 
 
@@ -248,8 +254,22 @@ def encoder(cfg, P, x, lens, subnet, train_masks=None):
     return acts
 
 
-def decoder_step(cfg, P, y_prev, h, c, emb_mask=None):
-    """One decoder step: Emb[y_prev] (+bias, act) -> LSTM(Hd) -> logits = h Wp^T + b."""
+def luong_attention(cfg, P, h, enc, lens2):
+    """A7 [CHOICE, not in the reference]: Luong 'general' attention on the decoder OUTPUT (no input feeding, so the
+    recurrence is untouched): q = h Wq^T; score_s = q . enc_s for s < lens2 (else masked); alpha = softmax(score);
+    ctx = sum_s alpha_s enc_s; h~ = tanh(Wc [ctx; h] + bc).  enc [B,T',Hd] = outputs of the last encoder layer."""
+    q = h @ P["seq2seq/decoder_attention/query/weights"].T
+    score = torch.einsum("bf,bsf->bs", q, enc)
+    mask = torch.arange(enc.shape[1]).unsqueeze(0) < lens2.unsqueeze(1)
+    score = score.masked_fill(~mask, -1e30)
+    alpha = torch.softmax(score, dim=1) * mask.to(h.dtype)
+    ctx = torch.einsum("bs,bsf->bf", alpha, enc)
+    return torch.tanh(torch.cat([ctx, h], dim=1) @ P["seq2seq/decoder_attention/combine/weights"].T
+                      + P["seq2seq/decoder_attention/combine/biases"])
+
+
+def decoder_step(cfg, P, y_prev, h, c, emb_mask=None, enc=None, lens2=None):
+    """One decoder step: Emb[y_prev] (+bias, act) -> LSTM(Hd) [-> attention] -> logits = h Wp^T + b."""
     eb = f"seq2seq/decoder_embedding_{cfg.V}_{cfg.D}_0"
     e = _act(P[eb + "/weights"][y_prev] + P[eb + "/biases"], cfg.emb_act)
     if emb_mask is not None:
@@ -259,7 +279,8 @@ def decoder_step(cfg, P, y_prev, h, c, emb_mask=None):
     z = e @ K[:cfg.D] + h @ K[cfg.D:] + bias
     h, c = lstm_cell(z, c)
     pb = f"seq2seq/decoder_projection_{cfg.Hd}_{cfg.V}_0"
-    logits = h @ P[pb + "/weights"].T + P[pb + "/biases"]
+    ho = luong_attention(cfg, P, h, enc, lens2) if cfg.attention == "luong" else h
+    logits = ho @ P[pb + "/weights"].T + P[pb + "/biases"]
     return logits, h, c
 
 
@@ -290,7 +311,7 @@ def train_loss(cfg, P, x, lens, y, subnet=0, masks=None):
     logits_all = []
     for k in range(L):
         em = None if masks is None or "demb" not in masks else masks["demb"][:, k]
-        logits, h, c = decoder_step(cfg, P, prev, h, c, em)
+        logits, h, c = decoder_step(cfg, P, prev, h, c, em, acts[f"enc{len(cfg.H) - 1}_out"], acts["lens2"])
         logits_all.append(logits)
         lp = torch.log_softmax(logits, dim=1)
         m = (y[:, k] != cfg.pad_id).to(x.dtype)
@@ -351,7 +372,7 @@ def greedy_decode(cfg, P, x, lens, max_len=20, subnet=0, temperature=1.0):
     logp = torch.zeros(B, max_len, dtype=x.dtype)
     all_logits = torch.zeros(B, max_len, cfg.V, dtype=x.dtype)
     for k in range(max_len):
-        logits, h, c = decoder_step(cfg, P, prev, h, c)
+        logits, h, c = decoder_step(cfg, P, prev, h, c, None, acts[f"enc{len(cfg.H) - 1}_out"], acts["lens2"])
         all_logits[:, k] = logits
         nxt = logits.argmax(dim=1)
         lp = torch.log_softmax(logits / temperature, dim=1).gather(1, nxt[:, None]).squeeze(1)
@@ -378,7 +399,9 @@ def beam_decode(cfg, P, x, lens, beam=8, max_len=20, subnet=0, temperature=1.0):
     prev = torch.full((B, beam), cfg.start_id, dtype=torch.int64)
     done = torch.zeros(B, beam, dtype=torch.bool)
     for k in range(max_len):
-        logits, hn, cn = decoder_step(cfg, P, prev.reshape(-1), h.reshape(B * beam, -1), c.reshape(B * beam, -1))
+        enc_top = acts[f"enc{len(cfg.H) - 1}_out"]
+        logits, hn, cn = decoder_step(cfg, P, prev.reshape(-1), h.reshape(B * beam, -1), c.reshape(B * beam, -1), None,
+                                      enc_top.repeat_interleave(beam, dim=0), acts["lens2"].repeat_interleave(beam))
         lp = torch.log_softmax(logits / temperature, dim=1).reshape(B, beam, V)
         hn, cn = hn.reshape(B, beam, -1), cn.reshape(B, beam, -1)
         cand = scores[:, :, None] + lp

@@ -13,6 +13,9 @@ MEDIUM = dict(subnet_ids=(400,), subnet_C=(64,), subnet_W=(12,), E=32, H=(64, 64
 # full-width recurrent layers (H = 400 per direction, decoder 800) on a narrow input: exercises the
 # persistent tcgen05 recurrent kernels at the config-2 layer shape while the oracle still runs in seconds
 WIDE = dict(subnet_ids=(400,), subnet_C=(32,), subnet_W=(12,), E=100, H=(400, 400), D=24, Hd=800, V=200)
+# optional Luong attention (A7) on top of the same geometries
+TINY_ATTN = dict(TINY, attention="luong")
+MEDIUM_ATTN = dict(MEDIUM, attention="luong")
 TWO_SUBJ = dict(subnet_ids=(400, 401), subnet_C=(6, 10), subnet_W=(4, 3), E=5, H=(8,), D=6, Hd=16, V=11)
 
 

@@ -64,6 +64,16 @@ def test_persistent_kernels_are_deterministic(gpu_lib):
         assert np.array_equal(outs[0][k], outs[1][k]), k
 
 
+@pytest.mark.parametrize("backend,tol", [("simt", 2e-4), ("auto", 1e-2)])
+def test_attention_train_and_decode(gpu_lib, backend, tol):
+    """A7 (optional Luong attention): training step (loss, every gradient incl. the attention tensors and the encoder
+    path through the attention), greedy and beam decode, CUDA-core and tensor-core GEMM backends."""
+    pc.check_train_step(gpu_lib, pc.MEDIUM_ATTN, 16, 96, 6, backend=backend, tol=tol)
+    pc.check_train_step(gpu_lib, pc.MEDIUM_ATTN, 16, 96, 6, ff=0.1, rnn=0.5, backend=backend, tol=tol)
+    pc.check_decode(gpu_lib, pc.MEDIUM_ATTN, 8, 96, 6, backend=backend)
+    pc.check_decode(gpu_lib, pc.MEDIUM_ATTN, 4, 96, 6, beam=4, backend=backend)
+
+
 @pytest.mark.parametrize("backend,tol", [("simt", 2e-4), ("auto", 2e-4)])
 def test_golden_vectors(gpu_lib, backend, tol):
     """The committed golden vectors (tests/golden/make_golden.py) through the CUDA path; TINY shapes stay on the fp32

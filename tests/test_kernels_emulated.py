@@ -43,3 +43,14 @@ def test_beam_width_one_equals_greedy(emu_lib):
     b, sc = eng.beam_decode(x, None, beam=1, max_len=6, temperature=0.5)
     assert (b[:, 0] == g).all()
     assert np.allclose(sc[:, 0], lp.sum(1), atol=1e-5)
+
+
+def test_attention_train_step(emu_lib):
+    """A7: fused score / masked softmax / context kernels + their backward against autograd of the oracle."""
+    pc.check_train_step(emu_lib, pc.TINY_ATTN, 3, 19, 5)
+    pc.check_train_step(emu_lib, pc.TINY_ATTN, 3, 19, 5, ff=0.1, rnn=0.5)
+
+
+def test_attention_decode(emu_lib):
+    pc.check_decode(emu_lib, pc.TINY_ATTN, 6, 21, 6)
+    pc.check_decode(emu_lib, pc.TINY_ATTN, 4, 21, 6, beam=4)
