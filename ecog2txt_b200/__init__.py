@@ -10,3 +10,4 @@ DATA_PARTITIONS = {'training', 'validation', 'testing'}
 
 from .engine import Engine, EngineConfig, E2TError  # noqa: E402,F401
 from .sequence_network import SequenceNetwork  # noqa: E402,F401
+from .trainers import MultiSubjectTrainer  # noqa: E402,F401

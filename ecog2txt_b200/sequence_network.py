@@ -239,11 +239,24 @@ class SequenceNetwork:
             return np.array(z[full_var_name])
 
     # -- online predictor (construct_online_predictor, trainers.py:925-949) ---------------------------
-    def predict(self, inputs: np.ndarray, subnet: int = 0) -> str:
-        """One utterance [T, C] -> decoded sentence with the EMA weights (greedy)."""
+    def prepare_for_prediction(self, subnets_params, restore_epoch, max_T: int = 1250):
+        """Build the engine for these subjects and restore checkpoint `restore_epoch` (EMA weights are used to decode).
+        max_T: longest utterance the predictor accepts (data_generators.py:38,157 clips trials at 1250 samples)."""
+        eng = self._get_engine(subnets_params, max_T, self.max_hyp_length)
+        prm.load_checkpoint(eng, self.checkpoint_path, restore_epoch, reuse_vars_scope='seq2seq')
+        return eng
+
+    def predict_tokens(self, inputs: np.ndarray, subnet: int = 0) -> np.ndarray:
+        """One utterance [T, C] -> token indices [max_hyp_length] (greedy, EMA weights).  Calls of one shape are replayed
+        as a single CUDA graph by the library from the second call on (e2t.h: e2t_greedy_decode)."""
         eng = self._engine
         if eng is None:
-            raise RuntimeError("fit or restore_and_assess first")
+            raise RuntimeError("fit, restore_and_assess or prepare_for_prediction first")
         x = np.ascontiguousarray(inputs[None], np.float32)
-        toks, _ = eng.greedy_decode(x, None, max_len=self.max_hyp_length, subnet=subnet, use_ema=True, want_logp=False)
-        return target_inds_to_sequences(toks[:, None, :], self._targets_list)[0]
+        toks, _ = eng.greedy_decode(x, None, max_len=self.max_hyp_length, subnet=subnet, use_ema=True,
+                                    temperature=float(self.temperature), want_logp=False)
+        return toks[0]
+
+    def predict(self, inputs: np.ndarray, subnet: int = 0) -> str:
+        """One utterance [T, C] -> decoded sentence with the EMA weights (greedy)."""
+        return target_inds_to_sequences(self.predict_tokens(inputs, subnet)[None, None, :], self._targets_list)[0]

@@ -154,7 +154,8 @@ int e2t_get_activation(e2t_handle* h, const char* name, void* host_out, int64_t 
 /* ---- accounting -------------------------------------------------------------------------- */
 /* kernels launched by this handle since creation (all / those that used tcgen05) */
 int e2t_launch_counts(e2t_handle* h, int64_t* total, int64_t* tensor_core);
-/* named counters: "launches", "tcgen05_launches", "persistent_rnn_launches" (whole-layer recurrent kernels) */
+/* named counters: "launches", "tcgen05_launches", "persistent_rnn_launches" (whole-layer recurrent kernels),
+ * "decode_graph_replays" (greedy decodes of <= 8 host utterances replayed as one CUDA graph) */
 int e2t_counter(e2t_handle* h, const char* name, int64_t* value);
 /* Per-category device timing (CUDA events around every launch of the category; for bench.py's
  * roofline leg only -- the events perturb the step, so it is never on during a timed region).

@@ -108,3 +108,25 @@ def test_sequence_network_fit_on_gpu(gpu_lib, tmp_path):
     net.beam_width = 4
     res_b = net.restore_and_assess([s], 60)
     assert res_b["training"].word_error_rate <= wer[-1] + 0.05
+
+
+def test_online_predictor_graph_replay(gpu_lib):
+    """N3: one-utterance greedy decodes of a fixed shape are replayed as a CUDA graph from the third call on and return
+    exactly what the eager path returns (also after the weights change: the graph reads the live buffers)."""
+    from oracle import seq2seq_oracle as O
+    ocfg = O.OracleConfig(**pc.WIDE)
+    P = pc.make_params(ocfg, eos_bias=-1.0)
+    eng = pc.engine_for(pc.WIDE, gpu_lib, 1, 100, 8, gemm_backend="auto")
+    eng.set_all({k: v.numpy() for k, v in P.items()})
+    x, _, _ = pc.make_batch(ocfg, 1, 100, 4)
+    outs = [eng.greedy_decode(x, None, max_len=8, temperature=0.5) for _ in range(4)]
+    assert eng.counter("decode_graph_replays") >= 2
+    for t, lp in outs[1:]:
+        assert (t == outs[0][0]).all() and np.array_equal(lp, outs[0][1])
+    x2, _, _ = pc.make_batch(ocfg, 1, 100, 4, seed=5)
+    t_graph, _ = eng.greedy_decode(x2, None, max_len=8, temperature=0.5)
+    eng2 = pc.engine_for(pc.WIDE, gpu_lib, 1, 100, 8, gemm_backend="auto")
+    eng2.set_all({k: v.numpy() for k, v in P.items()})
+    t_eager, _ = eng2.greedy_decode(x2, None, max_len=8, temperature=0.5)
+    assert (t_graph == t_eager).all()
+    eng.close(); eng2.close()

@@ -1,0 +1,65 @@
+"""CPU: MultiSubjectTrainer (the caller of the hot path) on the kernel-emulation build:
+sequential / parallel transfer-learning schedules (trainers.py:303-374), checkpoint discovery (:240-252),
+recover_model_sizes on our checkpoints (:444-554) and the online predictor (:925-963)."""
+import os
+
+import numpy as np
+
+from ecog2txt_b200 import MultiSubjectTrainer
+from ecog2txt_b200 import params as prm
+from test_sequence_network import MANIFEST, VOCAB, _subject
+
+
+def _trainer(tmp_path, emu_lib, ids=(400, 401), **sn):
+    subjects = [_subject(tmp_path, sid, seed=i) for i, sid in enumerate(ids)]
+    for s in subjects:
+        s.write_tf_records_maybe()
+    manifest = {sid: dict(MANIFEST, token_type="word_sequence", decoder_targets_penalty_scale=1.0) for sid in ids}
+    sn_kwargs = dict(N_cases=6, max_hyp_length=5, learning_rate=1e-2, lib=emu_lib, gemm_backend="simt", **sn)
+    return MultiSubjectTrainer(manifest, list(ids), checkpoint_dir=str(tmp_path / "ckpt"), SN_kwargs=sn_kwargs,
+                               VERBOSE=False, subjects=subjects)
+
+
+def test_sequential_transfer_learn(tmp_path, emu_lib):
+    tr = _trainer(tmp_path, emu_lib, assessment_epoch_interval=5)
+    assert tr.ecog_subjects[0].pretrain_all_blocks and not tr.ecog_subjects[1].pretrain_all_blocks
+    assert tr.ecog_subjects[0].block_ids["training"] == {1, 2, 3}      # first subject pre-trains on all its blocks
+    assert tr.restore_epoch is None
+    a = tr.sequential_transfer_learn(pretraining_epochs=5, training_epochs=10, posttraining_epochs=5)
+    # epochs: subject 400: 10 ; subject 401: 5 (subnet only) + 10 + 5
+    assert tr.restore_epoch == 30
+    assert a["training"].decoder_word_error_rates.shape == (3,)
+    tr._restore_epoch = None
+    assert tr.restore_epoch == 30                                       # discovered from model.ckpt-<epoch>.index
+    # the pre-training phase of subject 401 (epochs 10 -> 15) must not have touched the shared tensors
+    shared = "seq2seq/decoder_rnn/multi_rnn_cell/cell_0/lstm_cell/kernel"
+    w10 = tr.net.get_weights_as_numpy_array(shared, 10)
+    w15 = tr.net.get_weights_as_numpy_array(shared, 15)
+    w30 = tr.net.get_weights_as_numpy_array(shared, 30)
+    assert np.array_equal(w10, w15) and not np.array_equal(w15, w30)
+    # recover_model_sizes reads our checkpoints with the reference's parsing rules
+    layer_sizes, data_sizes, strides, EMA = tr.recover_model_sizes()
+    assert layer_sizes["encoder_embedding"] == [5] and layer_sizes["encoder_rnn"] == [8, 8]
+    assert layer_sizes["decoder_embedding"] == [6] and layer_sizes["decoder_rnn"] == [16]
+    assert layer_sizes["decoder_projection"] == []
+    assert strides[401] == [4] and data_sizes[401]["encoder_inputs"] == 6
+    assert data_sizes[None]["decoder_targets"] == len(VOCAB) and EMA == 1
+    res = tr.assess_saved_model()
+    assert abs(res["training"].word_error_rate - a["training"].decoder_word_error_rates[-1]) < 1e-9
+    # online predictor: one utterance at a time -> sentence
+    predict = tr.construct_online_predictor()
+    x, _ = tr.net._load_partition(tr.ecog_subjects[-1], "validation")[0]
+    s1 = predict(x)
+    assert isinstance(s1, str) and s1 == predict(x)
+
+
+def test_parallel_transfer_learn_and_resume(tmp_path, emu_lib):
+    tr = _trainer(tmp_path, emu_lib, N_epochs=10, assessment_epoch_interval=5)
+    a = tr.parallel_transfer_learn()
+    assert a["training"].decoder_word_error_rates.shape == (2,)
+    assert os.path.exists(os.path.join(tr.checkpoint_dir, "model.ckpt-10.index"))
+    shapes = prm.variable_to_shape_map(tr.net.checkpoint_path, 10)
+    assert "seq2seq/subnet_400/encoder_embedding_6_5_0/weights" in shapes     # both private subnets live in one model
+    assert "seq2seq/subnet_401/encoder_embedding_6_5_0/weights" in shapes
+    tr.parallel_transfer_learn(RESUME=True)                                   # last subject only, from the latest epoch
+    assert tr.restore_epoch == 20
