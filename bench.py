@@ -254,8 +254,10 @@ def main():
         psrc = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback"
         eng.profile_enable(True)
         nprof = 3
-        for i in range(nprof):
-            step_device(i)
+        for i in range(nprof):     # rank-local steps: no collective may be issued by rank 0 alone
+            x, y = dev[i % NPOOL]
+            eng.train_step_grads(x, None, y, seed=i, want_loss=False)
+            eng.adam_ema_step(1.0 / ntok_cache[i % NPOOL])
         cat_ms = {c: eng.profile_read(c) for c in range(6)}
         if args.breakdown:
             rep = eng.profile_report()
