@@ -54,6 +54,7 @@ struct EncLayer {
   bool rec = false;
   float* KP[2] = {nullptr, nullptr};
   float* bP[2] = {nullptr, nullptr};
+  float* dKP[2] = {nullptr, nullptr};  // [(In+H+1), 4H] weight + bias gradients in permuted gate order (un-permuted in one batch)
 };
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -108,6 +109,12 @@ struct e2t_handle {
   int* d_ntok;
   float* colsum_ws = nullptr; i64 colsum_ws_n = 0;   // [64, N] partial column sums
   float* perm_ws = nullptr; i64 perm_ws_n = 0;       // [(In+H+1), 4H] weight + bias gradients in permuted gate order
+  // batched small jobs (k_batch): pending list + device table
+  std::vector<BatchJob> batch;
+  BatchJob* d_batch = nullptr; int d_batch_cap = 0;
+  float* colsum_pool = nullptr; i64 colsum_pool_n = 0, colsum_pool_used = 0;   // [64][N] partial sums of deferred colsums
+  std::vector<BatchJob> batch2;       // second pass of the two-pass column sums (runs after `batch`)
+  std::vector<BatchJob> batch3;       // un-permutes that consume column sums (run after `batch2`)
   float* rec_pws = nullptr; i64 rec_pws_n = 0;       // partial-dh workspace of the reduce-scatter BPTT kernel
   int* rec_counters = nullptr;   // arrival counters of the persistent recurrent kernels [2][n_bt][T2m]
   int64_t n_launch_rec = 0, n_graph_replays = 0;
@@ -279,6 +286,55 @@ void colsum(e2t_handle* h, const float* X, i64 rows, int N, int ld, float* out) 
   }
 }
 
+// ---- batched small jobs ----------------------------------------------------------------------------
+void batch_flush_list(e2t_handle* h, std::vector<BatchJob>& jobs) {
+  if (jobs.empty()) return;
+  int blk = 0;
+  for (auto& j : jobs) { j.blk0 = blk; blk += j.nblk; }
+  if ((int)jobs.size() > h->d_batch_cap) throw std::runtime_error("e2t: batch job table overflow");
+  // pageable source: the runtime stages the bytes before returning, so `jobs` may be reused at once
+  E2T_CHECK(cudaMemcpyAsync(h->d_batch, jobs.data(), jobs.size() * sizeof(BatchJob), cudaMemcpyHostToDevice, h->stream));
+  LAUNCH(h, k_batch, dim3((unsigned)blk), dim3(256), 0, h->d_batch, (int)jobs.size());
+  jobs.clear();
+}
+void batch_flush(e2t_handle* h) {
+  batch_flush_list(h, h->batch);
+  batch_flush_list(h, h->batch2);
+  batch_flush_list(h, h->batch3);
+  h->colsum_pool_used = 0;
+}
+void batch_transpose(e2t_handle* h, const float* in, i64 ldi, float* out, i64 ldo, int K, int N, int permH = 0,
+                     float* out_lo = nullptr) {
+  BatchJob j{};
+  j.type = E2T_JOB_TRANSPOSE; j.in = in; j.ldi = ldi; j.out = out; j.out2 = out_lo; j.ldo = ldo; j.K = K; j.N = N; j.permH = permH;
+  j.nblk = (int)(cdiv(N, 32) * cdiv(K, 32));
+  h->batch.push_back(j);
+}
+void batch_permute(e2t_handle* h, std::vector<BatchJob>& list, const float* in, float* out, i64 rows, int N, int permH, int forward) {
+  BatchJob j{};
+  j.type = E2T_JOB_PERMUTE; j.in = in; j.out = out; j.rows = rows; j.N = N; j.permH = permH; j.flag = forward;
+  j.nblk = (int)cdiv(rows * N, 256);
+  list.push_back(j);
+}
+// deferred deterministic column sum: out[n] = sum_m X[m*ld + n]; runs at the next batch_flush
+void batch_colsum(e2t_handle* h, const float* X, i64 rows, int N, int ld, float* out) {
+  const int R = 64;
+  BatchJob j{};
+  j.type = E2T_JOB_COLSUM; j.in = X; j.ldi = ld; j.rows = rows; j.N = N;
+  if (rows >= 512 && h->colsum_pool_used + (i64)R * N <= h->colsum_pool_n) {
+    float* ws = h->colsum_pool + h->colsum_pool_used;
+    h->colsum_pool_used += (i64)R * N;
+    j.out = ws; j.ldo = N; j.flag = R; j.nblk = (int)cdiv(N, 32) * R;
+    h->batch.push_back(j);
+    BatchJob k{};
+    k.type = E2T_JOB_COLSUM; k.in = ws; k.ldi = N; k.rows = R; k.N = N; k.out = out; k.ldo = 0; k.flag = 1; k.nblk = (int)cdiv(N, 32);
+    h->batch2.push_back(k);
+  } else {
+    j.out = out; j.ldo = 0; j.flag = 1; j.nblk = (int)cdiv(N, 32);
+    h->batch2.push_back(j);
+  }
+}
+
 DropP make_drop(uint32_t seed, uint32_t stream, float p) {
   DropP d;
   d.key = e2t_stream_key(seed, stream);
@@ -398,6 +454,7 @@ void build_workspace(e2t_handle* h) {
       if (L.rec) {
         L.KP[d] = h->alloc<float>((i64)(L.In + L.H) * 4 * L.H);
         L.bP[d] = h->alloc<float>((i64)4 * L.H);
+        L.dKP[d] = h->alloc<float>((i64)(L.In + L.H + 1) * 4 * L.H);
       }
     }
     if (L.rec) h->perm_ws_n = std::max<i64>(h->perm_ws_n, (i64)(L.In + L.H + 1) * 4 * L.H);
@@ -418,6 +475,14 @@ void build_workspace(e2t_handle* h) {
   h->colsum_ws_n = (i64)64 * std::max<i64>(std::max<i64>(4 * Hmax, h->Vp), std::max<i64>(c.E, h->Dp));
   h->colsum_ws = h->alloc<float>(h->colsum_ws_n);
   if (h->perm_ws_n) h->perm_ws = h->alloc<float>(h->perm_ws_n);
+  {
+    i64 ncols = h->Vp + 4 * c.Hd + h->Dp + c.E + 2 * c.Hd;
+    for (auto& L : h->enc) ncols += 2 * 4 * L.H;
+    h->colsum_pool_n = 64 * ncols;
+    h->colsum_pool = h->alloc<float>(h->colsum_pool_n);
+    h->d_batch_cap = 256;
+    h->d_batch = reinterpret_cast<BatchJob*>(h->alloc<char>((i64)h->d_batch_cap * sizeof(BatchJob)));
+  }
   if (h->rec_pws_n) h->rec_pws = h->alloc<float>(h->rec_pws_n);
   h->rec_counters = h->alloc<int>((i64)2 * cdiv(Bm, 128) * std::max<i64>(T2, Lm));
   h->ld_dec_kt = h->Dp + round_up(c.Hd, 4);
@@ -459,9 +524,9 @@ void build_workspace(e2t_handle* h) {
 void repack(e2t_handle* h, const float* src, int src_id) {
   if (!h->packed_dirty && h->packed_src == src_id) return;
   const e2t_config& c = h->cfg;
-  auto tr = [&](const float* in, i64 ldi, float* out, i64 ldo, int K, int N, int permH = 0) {
-    dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(K, 32));
-    LAUNCH(h, k_transpose, grid, dim3(256), 0, in, ldi, out, ldo, K, N, permH);
+  // all re-packs of a step go out as ONE k_batch launch
+  auto tr = [&](const float* in, i64 ldi, float* out, i64 ldo, int K, int N, int permH = 0, float* out_lo = nullptr) {
+    batch_transpose(h, in, ldi, out, ldo, K, N, permH, out_lo);
   };
   for (auto& L : h->enc)
     for (int d = 0; d < 2; ++d) {
@@ -470,8 +535,8 @@ void repack(e2t_handle* h, const float* src, int src_id) {
       tr(src + L.K[d] + (i64)L.In * 4 * L.H, 4 * L.H, L.KT[d] + L.In4, L.ldkt, L.H, 4 * L.H, pH);
       if (L.rec) {
         const i64 rows = L.In + L.H;
-        LAUNCH(h, k_permute_cols, grid1(rows * 4 * L.H), dim3(256), 0, src + L.K[d], L.KP[d], rows, 4 * L.H, L.H, 1);
-        LAUNCH(h, k_permute_cols, grid1((i64)4 * L.H), dim3(256), 0, src + L.b[d], L.bP[d], (i64)1, 4 * L.H, L.H, 1);
+        batch_permute(h, h->batch, src + L.K[d], L.KP[d], rows, 4 * L.H, L.H, 1);
+        batch_permute(h, h->batch, src + L.b[d], L.bP[d], (i64)1, 4 * L.H, L.H, 1);
       }
     }
   tr(src + h->dec_K, 4 * c.Hd, h->dec_KT, h->ld_dec_kt, c.D, 4 * c.Hd);
@@ -483,14 +548,10 @@ void repack(e2t_handle* h, const float* src, int src_id) {
   }
   for (int s = 0; s < c.n_subnets; ++s) {
     int WC = c.subnet_W[s] * c.subnet_C[s];
-    tr(src + h->conv_w[s], c.E, h->conv_wT[s], round_up(WC, 4), WC, c.E);
-#ifndef E2T_EMU
-    if (h->conv_wT_lo[s]) {   // hi / lo split in place: the SIMT fallback for tiny batches then sees tf32-rounded weights
-      const i64 n = (i64)c.E * round_up(WC, 4);
-      LAUNCH(h, conv::k_split_tf32, grid1(n), dim3(256), 0, h->conv_wT[s], h->conv_wT[s], h->conv_wT_lo[s], n);
-    }
-#endif
+    // tensor-core conv: Wc^T split into its tf32-exact part and the remainder (3xTF32 forward, conv_tc.cuh)
+    tr(src + h->conv_w[s], c.E, h->conv_wT[s], round_up(WC, 4), WC, c.E, 0, h->conv_wT_lo[s]);
   }
+  batch_flush(h);
   h->packed_dirty = false;
   h->packed_src = src_id;
 }
@@ -742,7 +803,7 @@ void lstm_layer_wgrads(e2t_handle* h, const float* in, int ld_in, int In, int H,
     const float* dz0 = reverse ? dz + (i64)(steps - 1) * B * 4 * H : dz;
     gemm(h, h_init, 1, H, dz0, 4 * H, 1, dWh, 4 * H, H, 4 * H, B, nullptr, 1.f);
   }
-  colsum(h, dz, rows, 4 * H, 4 * H, db);
+  batch_colsum(h, dz, rows, 4 * H, 4 * H, db);
   // d_in [rows, In] (+)= dz Wx^T ; canonical K rows [In,4H] are the K-major B operand
   if (d_in) gemm(h, dz, 4 * H, 1, K, 1, 4 * H, d_in, ld_din, (int)rows, In, 4 * H, nullptr, beta_din);
 }
@@ -759,7 +820,7 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
   const bool attn = c.attention != E2T_ATTN_NONE;
   const float* proj_in = attn ? h->at_ht : h->hdec;
   gemm(h, h->logits, 1, h->Vp, proj_in, c.Hd, 1, G + h->proj_w, c.Hd, c.V, c.Hd, (int)rows, nullptr, 0.f);
-  colsum(h, h->logits, rows, c.V, h->Vp, G + h->proj_b);
+  batch_colsum(h, h->logits, rows, c.V, h->Vp, G + h->proj_b);
   // d(proj input) [rows,Hd] = dlogits Wp ; B operand (k=v, n=u) = Wp[v*Hd+u] -> packed transpose is the K-major form
   gemm(h, h->logits, h->Vp, 1, h->proj_wT, 1, h->Vp, attn ? h->at_dht : h->dhdec, c.Hd, (int)rows, c.Hd, c.V, nullptr, 0.f);
   if (attn) {
@@ -768,7 +829,7 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
     // dWc [Hd, 2Hd] = dpre^T [ctx, hdec] ; dbc
     gemm(h, h->at_dht, 1, c.Hd, h->at_ctx, c.Hd, 1, G + h->at_wc, 2 * c.Hd, c.Hd, c.Hd, (int)rows, nullptr, 0.f);
     gemm(h, h->at_dht, 1, c.Hd, h->hdec, c.Hd, 1, G + h->at_wc + c.Hd, 2 * c.Hd, c.Hd, c.Hd, (int)rows, nullptr, 0.f);
-    colsum(h, h->at_dht, rows, c.Hd, c.Hd, G + h->at_bc);
+    batch_colsum(h, h->at_dht, rows, c.Hd, c.Hd, G + h->at_bc);
     // dctx = dpre Wc[:, :Hd]
     gemm(h, h->at_dht, c.Hd, 1, h->at_combT, 1, c.Hd, h->at_dctx, c.Hd, (int)rows, c.Hd, c.Hd, nullptr, 0.f);
     LAUNCH(h, k_attn_bwd_q, dim3((unsigned)rows), dim3(128), (size_t)T2 * sizeof(float), h->at_dctx, top.hs, h->d_lens2,
@@ -792,7 +853,7 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
   DropP dpe = make_drop(seed, E2T_STREAM_DEMB, c.ff_dropout);
   LAUNCH(h, k_act_dropout_bwd, grid1(rows * c.D), dim3(256), 0, h->ddemb, h->demb, rows, c.D, h->Dp, c.emb_act, dpe);
   LAUNCH(h, k_embed_bwd, grid1(rows * c.D), dim3(256), 0, h->d_prev, h->ddemb, G + h->demb_w, rows, c.D, h->Dp);
-  colsum(h, h->ddemb, rows, c.D, h->Dp, G + h->demb_b);
+  batch_colsum(h, h->ddemb, rows, c.D, h->Dp, G + h->demb_b);
   // ---- encoder, top layer first
   const int nl = c.n_enc_layers;
   for (int l = nl - 1; l >= 0; --l) {
@@ -840,13 +901,13 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
                             (top && d == 0) ? h->d_tlast : nullptr, 0);
       if (rec_ok) {
         // dz is in the permuted gate order: gradients land in a scratch and are un-permuted into the flat buffer
-        float* dKp = h->perm_ws;
-        float* dbp = h->perm_ws + (i64)(Ly.In + Ly.H) * 4 * Ly.H;
+        float* dKp = Ly.dKP[d];
+        float* dbp = Ly.dKP[d] + (i64)(Ly.In + Ly.H) * 4 * Ly.H;
         lstm_layer_wgrads(h, inp, ld_in, Ly.In, Ly.H, Ly.KP[d], dKp, dbp, Ly.gates[d], Ly.hs, 2 * Ly.H, d * Ly.H, T2, B,
                           d == 1, nullptr, nullptr, ld_din, 0.f);
         const i64 rows = Ly.In + Ly.H;
-        LAUNCH(h, k_permute_cols, grid1(rows * 4 * Ly.H), dim3(256), 0, dKp, G + Ly.K[d], rows, 4 * Ly.H, Ly.H, 0);
-        LAUNCH(h, k_permute_cols, grid1((i64)4 * Ly.H), dim3(256), 0, dbp, G + Ly.b[d], (i64)1, 4 * Ly.H, Ly.H, 0);
+        batch_permute(h, h->batch3, dKp, G + Ly.K[d], rows, 4 * Ly.H, Ly.H, 0);
+        batch_permute(h, h->batch3, dbp, G + Ly.b[d], (i64)1, 4 * Ly.H, Ly.H, 0);
       } else {
         lstm_layer_wgrads(h, inp, ld_in, Ly.In, Ly.H, P + Ly.K[d], G + Ly.K[d], G + Ly.b[d], Ly.gates[d], Ly.hs, 2 * Ly.H,
                           d * Ly.H, T2, B, d == 1, nullptr, nullptr, ld_din, 0.f);
@@ -861,8 +922,8 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
   LAUNCH(h, k_act_dropout_bwd, grid1((i64)T2 * B * c.E), dim3(256), 0, h->dconv, h->conv_out, (i64)T2 * B, c.E, c.E,
          c.conv_act, dpc);
   gemm_conv(h, 2, in.x, h->d_lens, B, T, C, W, T2, h->dconv, c.E, 1, G + h->conv_w[subnet], c.E, c.E, nullptr, 0.f);
-  colsum(h, h->dconv, (i64)T2 * B, c.E, c.E,
-         G + h->conv_b[subnet]);
+  batch_colsum(h, h->dconv, (i64)T2 * B, c.E, c.E, G + h->conv_b[subnet]);
+  batch_flush(h);    // every bias-gradient column sum and gate-order un-permute of the step: three launches
 }
 
 void read_loss(e2t_handle* h, float* loss_sum, int32_t* ntok) {

@@ -607,6 +607,80 @@ __global__ void k_permute_cols(const float* in, float* out, i64 rows, int N, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// Batched small jobs.  A training step needs ~60 tiny weight re-packs (transposes, gate-column permutations, tf32
+// splits) and bias-gradient column sums; launched one by one each costs a launch + a tail of a few microseconds on an
+// otherwise idle GPU.  k_batch runs a whole list of them in ONE launch (block -> job by a scan of the job table).
+//   E2T_JOB_TRANSPOSE   out[perm(n)][k] = in[k][n]   (permH > 0: row n -> e2t_gate_perm(n); out2 != NULL: tf32 hi -> out, lo -> out2)
+//   E2T_JOB_PERMUTE     out[r][perm(n)] = in[r][n] (flag = 1) or out[r][n] = in[r][perm(n)] (flag = 0)
+//   E2T_JOB_COLSUM      out[y][n] = sum over the y-th of `flag` row chunks of in[m][n]   (deterministic partial sums;
+//                       flag = 1: the final sum; a second job over the partials finishes the two-pass reduction)
+// ------------------------------------------------------------------------------------------------
+enum { E2T_JOB_TRANSPOSE = 0, E2T_JOB_PERMUTE = 1, E2T_JOB_COLSUM = 2 };
+struct BatchJob {
+  int type, blk0, nblk;
+  int K, N, permH, flag;
+  long long ldi, ldo, rows;
+  const float* in;
+  float* out;
+  float* out2;
+};
+__global__ void __launch_bounds__(256) k_batch(const BatchJob* __restrict__ jobs, int n_jobs) {
+  __shared__ float tile[32][33];
+  int ji = 0;
+  while (ji + 1 < n_jobs && (int)blockIdx.x >= jobs[ji + 1].blk0) ++ji;
+  const BatchJob J = jobs[ji];
+  const int lb = blockIdx.x - J.blk0;
+  if (J.type == E2T_JOB_TRANSPOSE) {
+    const int tiles_n = (J.N + 31) / 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int k0 = (lb / tiles_n) * 32, n0 = (lb % tiles_n) * 32;
+    for (int i = ty; i < 32; i += 8) {
+      const int k = k0 + i, n = n0 + tx;
+      tile[i][tx] = (k < J.K && n < J.N) ? J.in[(i64)k * J.ldi + n] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+      const int n = n0 + i, k = k0 + tx;
+      if (n < J.N && k < J.K) {
+        const i64 o = (i64)(J.permH > 0 ? e2t_gate_perm(n, J.permH) : n) * J.ldo + k;
+        const float a = tile[tx][i];
+        if (J.out2) {
+          const float hi = __uint_as_float(__float_as_uint(a) & 0xffffe000u);
+          J.out[o] = hi; J.out2[o] = a - hi;
+        } else J.out[o] = a;
+      }
+    }
+  } else if (J.type == E2T_JOB_PERMUTE) {
+    const i64 i = (i64)lb * blockDim.x + threadIdx.x;
+    if (i < J.rows * J.N) {
+      const i64 r = i / J.N;
+      const int n = (int)(i - r * J.N);
+      const int np = e2t_gate_perm(n, J.permH);
+      if (J.flag) J.out[r * J.N + np] = J.in[i];
+      else J.out[i] = J.in[r * J.N + np];
+    }
+  } else {
+    const int nx = (J.N + 31) / 32;
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int n = (lb % nx) * 32 + cx, y = lb / nx;
+    const i64 chunk = (J.rows + J.flag - 1) / J.flag;
+    const i64 m0 = (i64)y * chunk;
+    i64 m1 = m0 + chunk;
+    if (m1 > J.rows) m1 = J.rows;
+    float sacc = 0.f;
+    if (n < J.N)
+      for (i64 m = m0 + ry; m < m1; m += 8) sacc += J.in[m * J.ldi + n];
+    tile[ry][cx] = sacc;
+    __syncthreads();
+    if (ry == 0 && n < J.N) {
+      float t = 0.f;
+      for (int i = 0; i < 8; ++i) t += tile[i][cx];
+      J.out[(i64)y * J.ldo + n] = t;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // A11 beam search helpers (width <= 32).  State rows are r = b*beam + j.
 // k_beam_topk: one block per utterance.  For each live beam the candidates are
 //   score[j] + log_softmax(logits[r]/T)[v]; finished beams contribute only (score[j], pad).

@@ -36,6 +36,7 @@ constexpr int kEpiWarps = 4 * (kU / kUT);          // kU/kUT warps per TMEM lane
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kThreadsRec = 64 + kEpiThreads;      // + TMA producer warp + MMA warp
 constexpr uint32_t A_STAGE_BYTES = kBM * BK * 4;   // 16 KB
+constexpr int kGroup = 3;                          // k-chunks per mbarrier phase of the A-tile ring
 
 __device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
   int v;
@@ -111,6 +112,25 @@ __device__ __forceinline__ void ldv(float* dst, const float* src) {
     const float4 v = *reinterpret_cast<const float4*>(src + 4 * i);
     dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
   }
+}
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a thread's 32 contiguous bytes are one full sector per request,
+// half the L1 wavefronts of two 128-bit accesses.  n % 8 == 0, 32-byte aligned.
+template <int N>
+__device__ __forceinline__ void ldv8(float* d, const float* src) {
+#pragma unroll
+  for (int i = 0; i < N / 8; ++i)
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(d[8 * i]), "=f"(d[8 * i + 1]), "=f"(d[8 * i + 2]), "=f"(d[8 * i + 3]), "=f"(d[8 * i + 4]),
+                   "=f"(d[8 * i + 5]), "=f"(d[8 * i + 6]), "=f"(d[8 * i + 7])
+                 : "l"(src + 8 * i));
+}
+template <int N>
+__device__ __forceinline__ void stv8(float* dst, const float* v) {
+#pragma unroll
+  for (int i = 0; i < N / 8; ++i)
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 8 * i), "f"(v[8 * i]), "f"(v[8 * i + 1]),
+                 "f"(v[8 * i + 2]), "f"(v[8 * i + 3]), "f"(v[8 * i + 4]), "f"(v[8 * i + 5]), "f"(v[8 * i + 6]), "f"(v[8 * i + 7])
+                 : "memory");
 }
 template <int N>
 __device__ __forceinline__ void ldv_cg(float* dst, const float* src) {
@@ -225,7 +245,7 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* smem_w = smem;
   unsigned char* smem_a = smem + (size_t)p.nkc * G::WCHUNK;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages * A_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages * kGroup * A_STAGE_BYTES);
   uint64_t* full_bar = bars;                       // [stages]
   uint64_t* empty_bar = bars + p.stages;           // [stages]
   uint64_t* w_bar = bars + 2 * p.stages;
@@ -288,16 +308,21 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
       wait_counter(counters + (s - 1), p.n_slices);     // all lanes poll the same word: one L2 request per round
       fence_proxy_async_all();
       if (lane == 0) REC_STAMP(s, 0);
-      for (int kk = 0; kk < p.nkc; ++kk, ++it) {
-        int kc = kk + kc_rot;                       // the K order is free: spread the chain's CTAs over the tile
-        if (kc >= p.nkc) kc -= p.nkc;
-        const int st = it % p.stages;
+      // the A tile arrives in groups of kGroup k-chunks per mbarrier phase: one producer/consumer hand-off costs about as
+      // much as the four MMAs of a chunk (tools/ubench/tma_mma.cu), so fewer, larger phases shorten the step
+      for (int kk0 = 0; kk0 < p.nkc; kk0 += kGroup, ++it) {
+        const int st = it % p.stages;                 // ring slot = group of kGroup chunk buffers
         const uint32_t ph = (it / p.stages) & 1;
+        const int n = min(kGroup, p.nkc - kk0);
         mbar_wait(smem_u32(&empty_bar[st]), ph ^ 1);
         if (elect_one()) {
           const uint32_t fb = smem_u32(&full_bar[st]);
-          mbar_expect_tx(fb, A_STAGE_BYTES);
-          tma_load_2d(smem_u32(smem_a + (size_t)st * A_STAGE_BYTES), map_a, fb, kc * BK, t_src * B + bt * kBM);
+          mbar_expect_tx(fb, (uint32_t)n * A_STAGE_BYTES);
+          for (int i = 0; i < n; ++i) {
+            int kc = kk0 + i + kc_rot;                // the K order is free: spread the chain's CTAs over the tile
+            if (kc >= p.nkc) kc -= p.nkc;
+            tma_load_2d(smem_u32(smem_a + (size_t)(st * kGroup + i) * A_STAGE_BYTES), map_a, fb, kc * BK, t_src * B + bt * kBM);
+          }
         }
         __syncwarp();
       }
@@ -315,23 +340,26 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
     for (int s = 1; s < steps; ++s) {
       mbar_wait(smem_u32(acc_empty), ((s - 1) & 1) ^ 1);   // epilogue drained the previous accumulator
       fence_after_sync();
-      for (int kk = 0; kk < p.nkc; ++kk, ++it) {
-        int kc = kk + kc_rot;
-        if (kc >= p.nkc) kc -= p.nkc;
+      for (int kk0 = 0; kk0 < p.nkc; kk0 += kGroup, ++it) {
         const int st = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1;
+        const int n = min(kGroup, p.nkc - kk0);
         mbar_wait(smem_u32(&full_bar[st]), ph);
         fence_after_sync();
-        if (kk == 0 && lane == 0) REC_STAMP(s, 2);
+        if (kk0 == 0 && lane == 0) REC_STAMP(s, 2);
         if (elect_one()) {
-          const uint64_t da = desc_a0 + (uint64_t)(((uint32_t)st * A_STAGE_BYTES) >> 4);
-          const uint64_t dw = desc_w0 + (uint64_t)(((uint32_t)kc * G::WCHUNK) >> 4);
+          for (int i = 0; i < n; ++i) {
+            int kc = kk0 + i + kc_rot;
+            if (kc >= p.nkc) kc -= p.nkc;
+            const uint64_t da = desc_a0 + (uint64_t)(((uint32_t)(st * kGroup + i) * A_STAGE_BYTES) >> 4);
+            const uint64_t dw = desc_w0 + (uint64_t)(((uint32_t)kc * G::WCHUNK) >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_tf32(tmem_base, da + (uint64_t)(k * UMMA_K * 4 >> 4), dw + (uint64_t)(k * UMMA_K * 4 >> 4), idesc,
-                      (kk > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_tf32(tmem_base, da + (uint64_t)(k * UMMA_K * 4 >> 4), dw + (uint64_t)(k * UMMA_K * 4 >> 4), idesc,
+                        (kk0 + i > 0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(smem_u32(&empty_bar[st]));
-          if (kk == p.nkc - 1) umma_commit(smem_u32(acc_full));
+          if (kk0 + kGroup >= p.nkc) umma_commit(smem_u32(acc_full));
         }
         __syncwarp();
       }
@@ -366,7 +394,7 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
         const bool valid = row_ok && t < len2;
         float* zrow = gates + ((i64)t * B + b) * 4 * H + z0;   // [gate][kUT] contiguous
         float z[4 * kUT];
-        if (valid) ldv<4 * kUT>(z, zrow);
+        if (valid) ldv8<4 * kUT>(z, zrow);
         float acc[4 * kUT];
         if (s > 0) {
           mbar_wait(smem_u32(acc_full), (s - 1) & 1);
@@ -398,7 +426,7 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
           for (int e = 0; e < kUT; ++e) { carry[e] = 0.f; hv[e] = 0.f; }
         }
         // 1) the hidden state is all the other CTAs of the chain wait for: store it, then publish
-        if (row_ok) stv<kUT>(p.hs + ((i64)t * B + b) * 2 * H + col0 + u0, hv);
+        if (row_ok) stv8<kUT>(p.hs + ((i64)t * B + b) * 2 * H + col0 + u0, hv);
         if (publisher) REC_STAMP(s, 5);
         named_bar_sync(1, kEpiThreads);
         if (publisher) {
@@ -412,8 +440,8 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
         //    release waits for the SM's outstanding stores, so 48 KB of them issued meanwhile would sit in front of it
         named_bar_sync(3, kEpiThreads);
         if (row_ok) {
-          if (valid) stv<4 * kUT>(zrow, z);
-          stv<kUT>(cs + ((i64)t * B + b) * H + u0, carry);
+          if (valid) stv8<4 * kUT>(zrow, z);
+          stv8<kUT>(cs + ((i64)t * B + b) * H + u0, carry);
           if (p.hd) {
             const uint32_t idx0 = (uint32_t)(((i64)t * B + b) * p.drop_F + col0 + u0);
             const uint32_t key = p.dp.key, thresh = p.dp.thresh;
@@ -421,7 +449,7 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
             float o[kUT];
 #pragma unroll
             for (int e = 0; e < kUT; ++e) o[e] = (valid && e2t_keep(key, idx0 + e, thresh)) ? hv[e] * inv : 0.f;
-            stv<kUT>(p.hd + ((i64)t * B + b) * 2 * H + col0 + u0, o);
+            stv8<kUT>(p.hd + ((i64)t * B + b) * 2 * H + col0 + u0, o);
           }
         }
       }
@@ -787,14 +815,14 @@ inline CUtensorMap make_map_nd(const float* ptr, int nd, const i64* dims, const 
 
 template <bool BWD>
 inline size_t rec_smem_bytes(int nkc, int stages) {
-  return (size_t)nkc * Geo<BWD>::WCHUNK + (size_t)stages * A_STAGE_BYTES + (2 * stages + 4) * 8 + 1024;
+  return (size_t)nkc * Geo<BWD>::WCHUNK + (size_t)stages * kGroup * A_STAGE_BYTES + (2 * stages + 4) * 8 + 1024;
 }
 
 // picks the A-ring depth that fits; returns 0 if the resident weights do not fit at all
 template <bool BWD>
 inline int rec_pick_stages(int nkc) {
   const size_t cap = 227 * 1024;
-  for (int s = 8; s >= 2; --s)
+  for (int s = 4; s >= 2; --s)     // ring depth in groups of kGroup chunks
     if (rec_smem_bytes<BWD>(nkc, s) <= cap) return s;
   return 0;
 }
