@@ -56,7 +56,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.idx), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -234,10 +234,10 @@ def main():
     if rank == 0:
         sampler.start()
     ms = timed(step_device, args.steps, max(args.warmup, 3))
-    clocks = sampler.stop() if rank == 0 else None
     l1, tc1 = eng.launch_counts()
     launches = (l1 - l0) * args.steps // (args.steps + max(args.warmup, 3))
     ms_e2e = timed(step_host, args.steps, 3)
+    clocks = sampler.stop() if rank == 0 else None     # sampled over both timed regions
     value = B * world * args.steps / (ms * 1e-3)
     e2e = B * world * args.steps / (ms_e2e * 1e-3)
 
@@ -266,20 +266,37 @@ def main():
                 for k, (n, t) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
                     f.write(f"{t / nprof:9.4f} ms/step  n/step={n // nprof:4d}  {1e3 * t / n:9.2f} us  {k}\n")
         eng.profile_enable(False)
-        rec_ms = cat_ms[0][0] + cat_ms[4][0] + cat_ms[5][0]
-        rec_n = cat_ms[0][1] + cat_ms[4][1] + cat_ms[5][1]
+        # dominant kernels: the whole-layer persistent recurrent kernels (forward + BPTT) -- a latency chain of T' = 34
+        # dependent steps per launch, so the tensor roofline is an upper bound they cannot approach
+        T2, H = 34, 400
+        flops_launch = 2 * 2 * T2 * B * H * 4 * H            # both directions, h Wh (or dz Wh^T) products of one layer
+        n_f, n_b = cat_ms[4][1], cat_ms[5][1]
+        rec_ms = cat_ms[4][0] + cat_ms[5][0]
         tot = sum(v[0] for v in cat_ms.values())
-        achieved = fl["recurrent_train"] * B * nprof / (rec_ms * 1e-3) / 1e12 if rec_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "recurrent LSTM steps (h Wh GEMM + gate kernel, fwd+bwd)",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
-                "peak_source": psrc + "; operands are tf32/fp32 (nominal tf32 peak is half the bf16 figure)",
-                "launches_per_step": rec_n // nprof, "avg_launch_us": 1e3 * rec_ms / max(rec_n, 1),
-                "share_of_step": rec_ms / tot if tot > 0 else None,
+        peak_tf32 = peak_tf / 2.0
+        achieved = flops_launch * (n_f + n_b) / (rec_ms * 1e-3) / 1e12 if rec_ms > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_lstm_rec_fwd"]["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        conv_bytes = B * T_FRAMES * 256 * 4
+        conv_gbs = 2 * conv_bytes * nprof / (cat_ms[2][0] * 1e-3) / 1e9 if cat_ms[2][0] > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "k_lstm_rec<fwd> + k_lstm_bptt (persistent whole-layer recurrent kernels, tcgen05 kind::tf32)",
+                "achieved": achieved, "peak": peak_tf32, "unit": "TFLOP/s", "frac": achieved / peak_tf32, "traffic": traffic,
+                "peak_source": psrc + " / 2: operands are tf32 (fp32 in HBM, 10-bit mantissa in the tensor core); dense tf32 "
+                               "runs at half the bf16 rate",
+                "algorithmic_flops_per_launch": flops_launch, "launches_per_step": (n_f + n_b) // nprof,
+                "avg_launch_us": 1e3 * rec_ms / max(n_f + n_b, 1), "share_of_step": rec_ms / tot if tot > 0 else None,
+                "us_per_launch": {"fwd": 1e3 * cat_ms[4][0] / max(n_f, 1), "bptt": 1e3 * cat_ms[5][0] / max(n_b, 1)},
+                "us_per_recurrent_step": {"fwd": 1e3 * cat_ms[4][0] / max(n_f, 1) / T2, "bptt": 1e3 * cat_ms[5][0] / max(n_b, 1) / T2},
                 "category_ms_per_step": {k: cat_ms[i][0] / nprof for i, k in enumerate(
-                    ("recurrent_per_step_kernels", "bulk_gemm", "conv", "other", "persistent_rnn_fwd", "persistent_rnn_bwd"))},
-                "persistent_rnn_us_per_launch": {"fwd": 1e3 * cat_ms[4][0] / max(cat_ms[4][1], 1),
-                                                 "bwd": 1e3 * cat_ms[5][0] / max(cat_ms[5][1], 1)},
-                "whole_step_frac_of_peak": (fl["train"] * value / world / 1e12) / peak_tf}
+                    ("decoder_per_step_kernels", "bulk_gemm", "conv", "other", "persistent_rnn_fwd", "persistent_rnn_bwd"))},
+                "hbm_kernel": {"kernel": "k_conv_tc fwd + bwd (gather-GEMM over the ECoG tensor)", "bound": "hbm",
+                               "achieved": conv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": conv_gbs / hbm_peak,
+                               "algorithmic_bytes_per_launch": conv_bytes},
+                "whole_step_frac_of_tf32_peak": (fl["train"] * value / world / 1e12) / peak_tf32}
 
     decode = None
     if args.decode and rank == 0:
