@@ -13,6 +13,7 @@
 #include <cuda.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 
@@ -383,19 +384,28 @@ inline SplitWs& split_ws(cudaStream_t st) {
   return tab[st];
 }
 
-// choose the tile width: fewest waves x (cycles per k-step ~ max(BN/2, issue floor))
-inline int pick_bn(int M, int N, bool tn, int nsm) {
+// Tile width and split-K from a small cost model fitted to B200 measurements (tools/sweep_gemm.py): a k-block costs
+// ~650 cycles up to BN = 128 (stage hand-off + MMA issue, not the tensor pipe) and ~1.1 more per extra column; a CTA pays
+// ~6000 cycles of prologue / drain, a split-K reduction ~8000 cycles plus its traffic.
+inline void pick_tiling(int M, int N, int num_kb, bool tn, int nsm, int* bn_out, int* ks_out) {
   const int step = tn ? 32 : 16;
-  int best = 256; double best_cost = 1e30;
   const int tm = (M + BM - 1) / BM;
-  for (int bn = 256; bn >= 32; bn -= step) {
-    const int tn_ = (N + bn - 1) / bn;
-    const double waves = std::ceil((double)tm * tn_ / nsm);
-    const double per_k = std::max(bn / 2.0, 80.0) + 75.0;       // MMA pipe / issue floor + amortised stage hand-off
-    const double cost = (tm * tn_ >= nsm ? waves : 1.0) * per_k;
-    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  const int n_cap = (N + step - 1) / step * step;
+  double best = 1e30;
+  int best_bn = std::min(256, n_cap), best_ks = 1;
+  for (int bn = std::min(256, n_cap); bn >= std::min(32, n_cap); bn -= step) {
+    const int tiles = tm * ((N + bn - 1) / bn);
+    const double per_kb = 650.0 + std::max(0, bn - 128) * 1.1;
+    const int ks_max = tiles >= nsm ? 1 : std::max(1, std::min(8, num_kb / 8));
+    for (int ks = 1; ks <= ks_max; ++ks) {
+      const int kb = (num_kb + ks - 1) / ks;
+      const double waves = std::ceil((double)tiles * ks / nsm);
+      double cost = 6000.0 + waves * (kb * per_kb + bn / 32.0 * 500.0);
+      if (ks > 1) cost += 8000.0 + (double)ks * M * N * 4.0 / 3.0e12 * 1.965e9;
+      if (cost < best - 1.0) { best = cost; best_bn = bn; best_ks = ks; }
+    }
   }
-  return best;
+  *bn_out = best_bn; *ks_out = best_ks;
 }
 
 // Optional second operand pair (A2, B2, K2): C = A B^T + A2 B2^T (+bias, +beta C) in ONE pass over C -- the two LSTM
@@ -407,18 +417,21 @@ inline void launch_gemm(cudaStream_t st, const float* A, i64 lda, const float* B
   const int nsm = sm_count_();
   TcGemmP p{};
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.beta = beta;
-  p.BN = pick_bn(M, N, TN, nsm);
-  if (p.BN > ((N + 15) / 16) * 16) p.BN = ((N + (TN ? 31 : 15)) / (TN ? 32 : 16)) * (TN ? 32 : 16);
-  p.tiles_m = (M + BM - 1) / BM;
-  p.tiles_n = (N + p.BN - 1) / p.BN;
   p.nkb0 = (K + BK - 1) / BK;
   const int num_kb = p.nkb0 + (A2 ? (K2 + BK - 1) / BK : 0);
   p.nkb_total = num_kb;
-  const int tiles = p.tiles_m * p.tiles_n;
-  p.ksplit = 1;
-  if (tiles * 2 <= nsm && num_kb >= 16) {       // few output tiles, long K (weight gradients): split K over the idle SMs
-    p.ksplit = std::min(nsm / tiles, num_kb / 8);
-    if (p.ksplit < 1) p.ksplit = 1;
+  pick_tiling(M, N, num_kb, TN, nsm, &p.BN, &p.ksplit);
+  p.tiles_m = (M + BM - 1) / BM;
+  p.tiles_n = (N + p.BN - 1) / p.BN;
+  int tiles = p.tiles_m * p.tiles_n;
+  {  // diagnostic overrides for shape sweeps (tools/sweep_gemm.py)
+    const char* e_bn = getenv("E2T_GEMM_BN");
+    const char* e_ks = getenv("E2T_GEMM_KSPLIT");
+    if (e_bn && atoi(e_bn) > 0) {
+      p.BN = atoi(e_bn);
+      p.tiles_n = (N + p.BN - 1) / p.BN;
+    }
+    if (e_ks && atoi(e_ks) > 0) p.ksplit = std::min(atoi(e_ks), num_kb);
   }
   p.kb_per_split = (num_kb + p.ksplit - 1) / p.ksplit;
   p.ksplit = (num_kb + p.kb_per_split - 1) / p.kb_per_split;     // no empty splits
@@ -449,6 +462,7 @@ inline void launch_gemm(cudaStream_t st, const float* A, i64 lda, const float* B
     E2T_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap));
     attr_set = true;
   }
+  tiles = p.tiles_m * p.tiles_n;
   const int grid = std::min(tiles * p.ksplit, nsm);
   kfn<<<grid, kGemmThreads, gemm_smem_bytes(p.BN, p.stages), st>>>(ma, mb, ma2, mb2, p);
   if (p.ksplit > 1) {

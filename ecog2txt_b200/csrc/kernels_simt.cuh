@@ -651,13 +651,15 @@ __global__ void __launch_bounds__(256) k_batch(const BatchJob* __restrict__ jobs
       }
     }
   } else if (J.type == E2T_JOB_PERMUTE) {
-    const i64 i = (i64)lb * blockDim.x + threadIdx.x;
-    if (i < J.rows * J.N) {
-      const i64 r = i / J.N;
-      const int n = (int)(i - r * J.N);
+    // block = 256 consecutive columns of one row (no 64-bit division per element); nblk = rows * ceil(N / 256)
+    const int bpr = (J.N + 255) / 256;
+    const int r = lb / bpr;
+    const int n = (lb - r * bpr) * 256 + threadIdx.x;
+    if (n < J.N) {
       const int np = e2t_gate_perm(n, J.permH);
-      if (J.flag) J.out[r * J.N + np] = J.in[i];
-      else J.out[i] = J.in[r * J.N + np];
+      const i64 base = (i64)r * J.N;
+      if (J.flag) J.out[base + np] = J.in[base + n];
+      else J.out[base + n] = J.in[base + np];
     }
   } else {
     const int nx = (J.N + 31) / 32;
