@@ -792,16 +792,28 @@ void lstm_layer_wgrads(e2t_handle* h, const float* in, int ld_in, int In, int H,
   gemm(h, in, 1, ld_in, dz, 4 * H, 1, dK, 4 * H, In, 4 * H, (int)rows, nullptr, 0.f);
   // dWh [H,4H] = hprev^T dz : forward direction pairs hs[t-1] with dz[t]; backward pairs hs[t+1] with dz[t]
   float* dWh = dK + (i64)In * 4 * H;
-  if (steps > 1) {
-    const float* hp = reverse ? hs + (i64)B * ldh + col0 : hs + col0;
-    const float* dzp = reverse ? dz : dz + (i64)B * 4 * H;
-    gemm(h, hp, 1, ldh, dzp, 4 * H, 1, dWh, 4 * H, H, 4 * H, (int)((i64)(steps - 1) * B), nullptr, 0.f);
-  } else {
-    E2T_CHECK(cudaMemsetAsync(dWh, 0, (size_t)H * 4 * H * sizeof(float), h->stream));
+  const float* hp = reverse ? hs + (i64)B * ldh + col0 : hs + col0;
+  const float* dzp = reverse ? dz : dz + (i64)B * 4 * H;
+  const float* dz0 = reverse ? dz + (i64)(steps - 1) * B * 4 * H : dz;
+  const int Krec = (int)((i64)(steps - 1) * B);
+  bool fused = false;
+#ifndef E2T_EMU
+  if (h_init && steps > 1 && h->cfg.gemm_backend != E2T_GEMM_SIMT && tc_gemm_tn_supported(hp, ldh, dzp, 4 * H, H, 4 * H, Krec) &&
+      tc_gemm_tn_supported(h_init, H, dz0, 4 * H, H, 4 * H, B)) {
+    // decoder: the first step pairs the bridge state with dz[0]; both row ranges in one pass over dWh
+    CatScope cs0_(h, E2T_CAT_BULK_GEMM);
+    prof_begin(h, "tc_gemm_tn2", H, 4 * H, Krec + B);
+    tc_gemm_tn2(h->stream, hp, ldh, dzp, 4 * H, Krec, h_init, H, dz0, 4 * H, B, dWh, 4 * H, H, 4 * H);
+    prof_end(h);
+    ++h->n_launch; ++h->n_launch_tc;
+    fused = true;
   }
-  if (h_init) {  // decoder: first step's previous state is the bridge state
-    const float* dz0 = reverse ? dz + (i64)(steps - 1) * B * 4 * H : dz;
-    gemm(h, h_init, 1, H, dz0, 4 * H, 1, dWh, 4 * H, H, 4 * H, B, nullptr, 1.f);
+#endif
+  if (!fused) {
+    if (steps > 1) gemm(h, hp, 1, ldh, dzp, 4 * H, 1, dWh, 4 * H, H, 4 * H, Krec, nullptr, 0.f);
+    else E2T_CHECK(cudaMemsetAsync(dWh, 0, (size_t)H * 4 * H * sizeof(float), h->stream));
+    if (h_init)   // decoder: first step's previous state is the bridge state
+      gemm(h, h_init, 1, H, dz0, 4 * H, 1, dWh, 4 * H, H, 4 * H, B, nullptr, 1.f);
   }
   batch_colsum(h, dz, rows, 4 * H, 4 * H, db);
   // d_in [rows, In] (+)= dz Wx^T ; canonical K rows [In,4H] are the K-major B operand

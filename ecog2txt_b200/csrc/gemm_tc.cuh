@@ -277,22 +277,45 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       if (p.ksplit > 1) { outp = p.ws + (size_t)ks * p.M * p.N; ldo = p.N; bias = nullptr; beta = 0.f; }
       else { outp = p.C; ldo = p.ldc; bias = p.bias; beta = p.beta; }
       const int rows_ok = min(32, p.M - row0);
+      // TMEM (thread = row, 32 columns) -> swizzled float4 staging -> 16-byte global accesses, 4 rows x 128 B per warp
+      // instruction.  Slot (j ^ (row & 7)) keeps both the row-wise writes and the 8-lanes-per-row reads conflict-free.
+      float4* st4 = reinterpret_cast<float4*>(st);
+      const bool vec_ok = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(outp) & 15) == 0);
+      const int rsub = lane >> 3, slot = lane & 7;
       for (int c0 = n0; c0 < n_end; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 256 + (c0 - n0)), v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) st[lane * kEpiPad + j] = v[j];
+        for (int j = 0; j < 8; ++j) st4[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
-        const int col = c0 + lane;
+        const int col = c0 + 4 * slot;
         if (col < n_end) {
-          const float bv = bias ? bias[col] : 0.f;
-          float* cp = outp + (i64)row0 * ldo + col;
-          if (beta != 0.f) {
-#pragma unroll 8
-            for (int r = 0; r < rows_ok; ++r) cp[(i64)r * ldo] = st[r * kEpiPad + lane] + bv + beta * cp[(i64)r * ldo];
-          } else {
-#pragma unroll 8
-            for (int r = 0; r < rows_ok; ++r) cp[(i64)r * ldo] = st[r * kEpiPad + lane] + bv;
+          float bv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (bias) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (col + e < n_end) bv[e] = bias[col + e];
+          }
+          const bool full4 = vec_ok && col + 4 <= n_end;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + rsub;
+            if (r < rows_ok) {
+              float4 o = st4[r * 8 + (slot ^ (r & 7))];
+              o.x += bv[0]; o.y += bv[1]; o.z += bv[2]; o.w += bv[3];
+              float* cp = outp + (i64)(row0 + r) * ldo + col;
+              if (full4) {
+                if (beta != 0.f) {
+                  const float4 old = *reinterpret_cast<const float4*>(cp);
+                  o.x += beta * old.x; o.y += beta * old.y; o.z += beta * old.z; o.w += beta * old.w;
+                }
+                *reinterpret_cast<float4*>(cp) = o;
+              } else {
+                const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (col + e < n_end) cp[e] = beta != 0.f ? ov[e] + beta * cp[e] : ov[e];
+              }
+            }
           }
         }
         __syncwarp();
@@ -532,6 +555,12 @@ static inline float tc_gemm_bench(cudaStream_t st, int M, int N, int K, bool tn,
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(dA); cudaFree(dB); cudaFree(dC);
   return ms / iters;
+}
+
+// C[M,N] = A[K,M]^T B[K,N] + A2[K2,M]^T B2[K2,N]: two row ranges of a weight gradient in one pass
+static inline void tc_gemm_tn2(cudaStream_t st, const float* A, i64 lda, const float* B, i64 ldb, int K, const float* A2,
+                               i64 lda2, const float* B2, i64 ldb2, int K2, float* C, i64 ldc, int M, int N) {
+  tc::launch_gemm<true>(st, A, lda, B, ldb, C, ldc, M, N, K, nullptr, 0.f, A2, lda2, B2, ldb2, K2);
 }
 
 // A/B random, C_tc vs fp32 SIMT reference; exercises bias, beta and ragged M/N/K edges. Returns max |diff|.
