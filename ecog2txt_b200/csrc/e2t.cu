@@ -313,7 +313,7 @@ void batch_transpose(e2t_handle* h, const float* in, i64 ldi, float* out, i64 ld
 void batch_permute(e2t_handle* h, std::vector<BatchJob>& list, const float* in, float* out, i64 rows, int N, int permH, int forward) {
   BatchJob j{};
   j.type = E2T_JOB_PERMUTE; j.in = in; j.out = out; j.rows = rows; j.N = N; j.permH = permH; j.flag = forward;
-  j.nblk = (int)(rows * cdiv(N, 256));
+  j.nblk = (int)(rows * cdiv(N, 1024));
   list.push_back(j);
 }
 // deferred deterministic column sum: out[n] = sum_m X[m*ld + n]; runs at the next batch_flush

@@ -626,8 +626,10 @@ struct BatchJob {
 };
 __global__ void __launch_bounds__(256) k_batch(const BatchJob* __restrict__ jobs, int n_jobs) {
   __shared__ float tile[32][33];
-  int ji = 0;
-  while (ji + 1 < n_jobs && (int)blockIdx.x >= jobs[ji + 1].blk0) ++ji;
+  // job of this block = number of jobs whose first block is <= blockIdx.x, minus one: one parallel probe instead of a
+  // serial scan of the table (n_jobs <= blockDim.x)
+  const int pred = (int)threadIdx.x < n_jobs && jobs[threadIdx.x].blk0 <= (int)blockIdx.x;
+  const int ji = __syncthreads_count(pred) - 1;
   const BatchJob J = jobs[ji];
   const int lb = blockIdx.x - J.blk0;
   if (J.type == E2T_JOB_TRANSPOSE) {
@@ -651,15 +653,18 @@ __global__ void __launch_bounds__(256) k_batch(const BatchJob* __restrict__ jobs
       }
     }
   } else if (J.type == E2T_JOB_PERMUTE) {
-    // block = 256 consecutive columns of one row (no 64-bit division per element); nblk = rows * ceil(N / 256)
-    const int bpr = (J.N + 255) / 256;
+    // block = 1024 consecutive columns of one row (no 64-bit division per element); nblk = rows * ceil(N / 1024)
+    const int bpr = (J.N + 1023) / 1024;
     const int r = lb / bpr;
-    const int n = (lb - r * bpr) * 256 + threadIdx.x;
-    if (n < J.N) {
-      const int np = e2t_gate_perm(n, J.permH);
-      const i64 base = (i64)r * J.N;
-      if (J.flag) J.out[base + np] = J.in[base + n];
-      else J.out[base + n] = J.in[base + np];
+    const i64 base = (i64)r * J.N;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int n = (lb - r * bpr) * 1024 + q * 256 + threadIdx.x;
+      if (n < J.N) {
+        const int np = e2t_gate_perm(n, J.permH);
+        if (J.flag) J.out[base + np] = J.in[base + n];
+        else J.out[base + n] = J.in[base + np];
+      }
     }
   } else {
     const int nx = (J.N + 31) / 32;

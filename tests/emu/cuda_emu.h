@@ -60,6 +60,17 @@ float shfl_f(float v, int src_lane);
 
 static inline void __syncthreads() { emu::sync_block(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::sync_warp(); }
+// blocks run one after another and fibers only switch at sync points, so a plain static counter is race-free
+static inline int __syncthreads_count(int pred) {
+  static int count = 0, result = 0;
+  if (threadIdx.x == 0) count = 0;
+  emu::sync_block();
+  count += pred ? 1 : 0;
+  emu::sync_block();
+  if (threadIdx.x == 0) result = count;
+  emu::sync_block();
+  return result;
+}
 static inline float __shfl_xor_sync(unsigned, float v, int m) { return emu::shfl_f(v, emu::lane() ^ m); }
 static inline float __shfl_down_sync(unsigned, float v, int d) {
   int s = emu::lane() + d;
