@@ -132,9 +132,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="utterances per GPU per step")
-    ap.add_argument("--ref-batch", type=int, default=32)
+    ap.add_argument("--ref-batch", type=int, default=256, help="utterances per CPU step (the GPU arm's per-GPU batch)")
     ap.add_argument("--backend", default="auto")
-    ap.add_argument("--cpu-baseline-steps", type=int, default=2)
+    ap.add_argument("--cpu-baseline-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write the per-kernel event-time breakdown of a step to this file")
     ap.add_argument("--decode", action="store_true", help="also report greedy / beam decode numbers")
