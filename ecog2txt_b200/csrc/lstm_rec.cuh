@@ -567,10 +567,10 @@ struct RecBptt {
 };
 static_assert(kUT == 8 && kU == 16, "k_lstm_bptt maps one 32-column k-chunk of the dz tile to one unit group");
 
-constexpr int kBUT = 4;                               // hidden units per compute thread
-constexpr int kBGroups = kU / kBUT;                   // 4 unit sub-groups per slice -> 4 warps per TMEM lane quadrant
-constexpr int kBComputeThreads = 32 * 4 * kBGroups;   // 512
-constexpr int kBpttThreads = kBComputeThreads;          // no dedicated issue warps: 512 threads -> 128 registers each
+constexpr int kBUT = 8;                               // hidden units per compute thread
+constexpr int kBGroups = kU / kBUT;                   // 2 unit groups per slice -> 2 warps per TMEM lane quadrant
+constexpr int kBComputeThreads = 32 * 4 * kBGroups;   // 256
+constexpr int kBpttThreads = kBComputeThreads;          // no dedicated issue warps: 256 threads -> 255 registers each
 
 __global__ void __launch_bounds__(kBpttThreads, 1)
 k_lstm_bptt(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1, RecBptt p) {
@@ -625,13 +625,12 @@ k_lstm_bptt(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ 
   {
     // ================= compute threads: (batch row, kBUT hidden units) =================
     const int quad = warp & 3;
-    const int sg = warp >> 2;                        // unit sub-group (kBUT units) of this thread
-    const int ug = sg >> 1, sub = sg & 1;            // 8-unit group of the permuted gate layout / which half of it
+    const int sg = warp >> 2;                        // unit sub-group (kBUT = 8 units = one group of the permuted gate layout)
     const int r = quad * 32 + lane;
     const int b = bt * kBM + r;
     const bool row_ok = b < B;
     const int u0 = j * kU + sg * kBUT;
-    const int z0 = j * 4 * kU + ug * 4 * kUT + sub * kBUT;   // gate g of these units: z0 + g * kUT .. + kBUT
+    const int z0 = j * 4 * kU + sg * 4 * kBUT;       // this thread's 32 contiguous gate columns [gate][8]
     const int len2 = row_ok ? (p.lens2 ? p.lens2[b] : steps) : 0;
     float* gates = d ? p.gates[1] : p.gates[0];
     const float* cs = d ? p.cs[1] : p.cs[0];
@@ -640,12 +639,14 @@ k_lstm_bptt(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ 
     const size_t chain_sz = (size_t)p.n_slices * kBM * H;                 // one (parity, dir, bt) block of the workspace
     float* pws_chain = p.pws + (size_t)(d * p.n_bt + bt) * chain_sz;      // + parity * 2 * n_bt * chain_sz
     const size_t par_stride = (size_t)2 * p.n_bt * chain_sz;
-    // this thread's dz pieces inside the swizzled A tile: chunk ug, row r, 16-byte piece (gate * 2 + sub) XOR (r & 7)
-    const uint32_t a_row = smem_u32(smem_a) + (uint32_t)ug * A_STAGE_BYTES + (uint32_t)r * 128;
+    // this thread's dz row inside the swizzled A tile: chunk sg (its 32 contiguous k), row r, 16-byte pieces XOR (r & 7)
+    const uint32_t a_row = smem_u32(smem_a) + (uint32_t)sg * A_STAGE_BYTES + (uint32_t)r * 128;
     // TMEM -> workspace: this thread copies columns [hcol0, hcol0 + H / kBGroups) of its row
     const int ncol = H / kBGroups;
     const int hcol0 = sg * ncol;
-    float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
+    float carry[kBUT];
+#pragma unroll
+    for (int i = 0; i < kBUT; ++i) carry[i] = 0.f;
 
     for (int q = 0; q < steps; ++q) {
       const int sf = steps - 1 - q;
@@ -653,74 +654,82 @@ k_lstm_bptt(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ 
       const int tp = reverse ? t + 1 : t - 1;
       const bool valid = row_ok && t < len2;
       float* zrow = gates + ((i64)t * B + b) * 4 * H + z0;
-      float4 gz[4], cv, cpv, dhv;
-      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      cv = cpv = dhv = zero4;
-      if (valid) {
+      float gz[4 * kBUT], cv[kBUT], cpv[kBUT], dhv[kBUT];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) gz[g] = *reinterpret_cast<const float4*>(zrow + g * kUT);
-        cv = *reinterpret_cast<const float4*>(cs + ((i64)t * B + b) * H + u0);
-        if (sf > 0) cpv = *reinterpret_cast<const float4*>(cs + ((i64)tp * B + b) * H + u0);
-        if (p.dhs) dhv = *reinterpret_cast<const float4*>(p.dhs + ((i64)t * B + b) * 2 * H + col0 + u0);
+      for (int e = 0; e < kBUT; ++e) { cv[e] = 0.f; cpv[e] = 0.f; dhv[e] = 0.f; }
+      if (valid) {
+        ldv8<4 * kBUT>(gz, zrow);                    // 256-bit accesses: half the L1 wavefronts of 128-bit ones
+        ldv8<kBUT>(cv, cs + ((i64)t * B + b) * H + u0);
+        if (sf > 0) ldv8<kBUT>(cpv, cs + ((i64)tp * B + b) * H + u0);
+        if (p.dhs) ldv8<kBUT>(dhv, p.dhs + ((i64)t * B + b) * 2 * H + col0 + u0);
       }
-      float4 acc = zero4;
+      float acc[kBUT];
+#pragma unroll
+      for (int i = 0; i < kBUT; ++i) acc[i] = 0.f;
       if (q > 0) {
         // every CTA of the chain has stored its partial of step q-1
         if (publisher) wait_counter(counters + (q - 1), p.n_slices);
         named_bar_sync(1, kBComputeThreads);
         if (publisher && dbg) dbg[q * 8 + 0] = clock64();
         if (valid) {
-          // L2-only loads (the buffer is rewritten by other SMs every two steps); kBatch independent 16-byte loads in
-          // flight per thread, summed in slice order (deterministic)
+          // L2-only loads (the buffer is rewritten by other SMs every two steps); kBatch slices = 2 kBatch independent
+          // 16-byte loads in flight per thread, summed in slice order (deterministic)
           const float* src = pws_chain + (size_t)((q - 1) & 1) * par_stride + ((size_t)(u0 / 4) * kBM + r) * 4;
-          constexpr int kBatch = 9;
+          constexpr int kBatch = 13;
           for (int i0 = 0; i0 < p.n_slices; i0 += kBatch) {
-            float4 v[kBatch];
+            float4 v[kBatch][kBUT / 4];
 #pragma unroll
             for (int i = 0; i < kBatch; ++i)
-              if (i0 + i < p.n_slices) v[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(i0 + i) * kBM * H));
+              if (i0 + i < p.n_slices) {
+#pragma unroll
+                for (int h4 = 0; h4 < kBUT / 4; ++h4)
+                  v[i][h4] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(i0 + i) * kBM * H + (size_t)h4 * kBM * 4));
+              }
 #pragma unroll
             for (int i = 0; i < kBatch; ++i)
-              if (i0 + i < p.n_slices) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }
+              if (i0 + i < p.n_slices) {
+#pragma unroll
+                for (int h4 = 0; h4 < kBUT / 4; ++h4) {
+                  acc[4 * h4] += v[i][h4].x; acc[4 * h4 + 1] += v[i][h4].y; acc[4 * h4 + 2] += v[i][h4].z; acc[4 * h4 + 3] += v[i][h4].w;
+                }
+              }
           }
         }
         if (publisher && dbg) dbg[q * 8 + 1] = clock64();
       }
       if (valid) {
-        float4 inj = zero4;
+        bool inject = false;
         if (p.dc_inject) {
           const int ti = (d == 0 && p.inject_t) ? p.inject_t[b] : 0;
-          if (ti == t) inj = *reinterpret_cast<const float4*>(p.dc_inject + (i64)b * p.ldi + col0 + u0);
+          inject = ti == t;
         }
-        auto cell = [](float gi, float gj, float gf, float go, float cvv, float cpp, float dh, float& dc, float& di, float& dj,
-                       float& df, float& dgo) {
-          const float tc_ = tanh_fast(cvv);
-          dgo = dh * tc_ * go * (1.f - go);
+#pragma unroll
+        for (int e = 0; e < kBUT; ++e) {
+          const float gi = gz[e], gj = gz[kBUT + e], gf = gz[2 * kBUT + e], go = gz[3 * kBUT + e];
+          const float dh = dhv[e] + acc[e];
+          float dc = carry[e];
+          if (inject) dc += p.dc_inject[(i64)b * p.ldi + col0 + u0 + e];
+          const float tc_ = tanh_fast(cv[e]);
+          gz[3 * kBUT + e] = dh * tc_ * go * (1.f - go);
           dc += dh * go * (1.f - tc_ * tc_);
-          di = dc * gj * gi * (1.f - gi);
-          dj = dc * gi * (1.f - gj * gj);
-          df = dc * cpp * gf * (1.f - gf);
-          dc = dc * gf;
-        };
-        float dcx = carry.x + inj.x, dcy = carry.y + inj.y, dcz = carry.z + inj.z, dcw = carry.w + inj.w;
-        float4 di, dj, df, dgo;
-        cell(gz[0].x, gz[1].x, gz[2].x, gz[3].x, cv.x, cpv.x, dhv.x + acc.x, dcx, di.x, dj.x, df.x, dgo.x);
-        cell(gz[0].y, gz[1].y, gz[2].y, gz[3].y, cv.y, cpv.y, dhv.y + acc.y, dcy, di.y, dj.y, df.y, dgo.y);
-        cell(gz[0].z, gz[1].z, gz[2].z, gz[3].z, cv.z, cpv.z, dhv.z + acc.z, dcz, di.z, dj.z, df.z, dgo.z);
-        cell(gz[0].w, gz[1].w, gz[2].w, gz[3].w, cv.w, cpv.w, dhv.w + acc.w, dcw, di.w, dj.w, df.w, dgo.w);
-        carry = make_float4(dcx, dcy, dcz, dcw);
-        gz[0] = di; gz[1] = dj; gz[2] = df; gz[3] = dgo;
+          gz[e] = dc * gj * gi * (1.f - gi);
+          gz[kBUT + e] = dc * gi * (1.f - gj * gj);
+          gz[2 * kBUT + e] = dc * cpv[e] * gf * (1.f - gf);
+          carry[e] = dc * gf;
+        }
       } else {
-        gz[0] = gz[1] = gz[2] = gz[3] = zero4;
-        carry = zero4;
+#pragma unroll
+        for (int i = 0; i < 4 * kBUT; ++i) gz[i] = 0.f;
+#pragma unroll
+        for (int e = 0; e < kBUT; ++e) carry[e] = 0.f;
       }
       if (q + 1 < steps) {
         // dz -> swizzled A tile (rows past B are zero), visible to the tensor core, then hand over to the MMA warp
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t addr = a_row + (uint32_t)(((g * 2 + sub) ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(gz[g].x), "f"(gz[g].y), "f"(gz[g].z),
-                       "f"(gz[g].w) : "memory");
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t addr = a_row + (uint32_t)((c ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(gz[4 * c]), "f"(gz[4 * c + 1]),
+                       "f"(gz[4 * c + 2]), "f"(gz[4 * c + 3]) : "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         fence_before_sync();                 // this thread's tcgen05.ld of the previous step precede the next MMAs
@@ -746,10 +755,7 @@ k_lstm_bptt(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ 
         }
       }
       // dz to HBM for the weight-gradient GEMMs (off the inter-CTA critical path: overlaps the MMA)
-      if (row_ok) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(zrow + g * kUT) = gz[g];
-      }
+      if (row_ok) stv8<4 * kBUT>(zrow, gz);
       if (q + 1 < steps) {
         mbar_wait(smem_u32(acc_full), q & 1);
         fence_after_sync();
