@@ -2,7 +2,10 @@
 import numpy as np
 import pytest
 
+import torch
+
 import parity_common as pc
+from ecog2txt_b200 import Engine, EngineConfig, _lib
 
 pytestmark = pytest.mark.gpu
 
@@ -130,3 +133,94 @@ def test_online_predictor_graph_replay(gpu_lib):
     t_eager, _ = eng2.greedy_decode(x2, None, max_len=8, temperature=0.5)
     assert (t_graph == t_eager).all()
     eng.close(); eng2.close()
+
+
+def _full_size_engine(gpu_lib, B, T=400, **kw):
+    """BASELINE.json config 2 at full size: 256-channel ECoG, 3x400 BiLSTM, 800 LSTM decoder, V = 1806."""
+    from ecog2txt_b200.params import init_engine
+    geo = dict(subnet_ids=(400,), subnet_C=(256,), subnet_W=(12,), E=100, H=(400, 400, 400), D=150, Hd=800, V=1806)
+    eng = Engine(EngineConfig(**geo, max_B=B, max_T=T, max_L=12, **kw), lib=gpu_lib)
+    init_engine(eng, seed=1)
+    return eng
+
+
+def _full_size_batch(B, T=400, L=11, seed=0, ragged=True):
+    rs = np.random.RandomState(seed)
+    x = rs.randn(B, T, 256).astype(np.float32)
+    lens = rs.randint(T // 2, T + 1, size=B) if ragged else np.full(B, T)
+    lens[0] = T
+    for b in range(B):
+        x[b, lens[b]:] = 0.0
+    y = np.zeros((B, L), np.int32)
+    for b in range(B):
+        n = rs.randint(3, L)
+        y[b, :n] = rs.randint(3, 1806, size=n)
+        y[b, n] = 1
+    return x, lens.astype(np.int32), y
+
+
+def test_full_size_properties(gpu_lib):
+    """Config-2 shapes are far beyond what the oracle finishes in seconds, so the full-size path is pinned through
+    size-independent properties: (1) bit-identical gradients run to run, (2) zero-padding invariance (T = 400 vs the
+    same utterances padded to T = 436: lengths are inferred from the padding), (3) batch additivity (the gradient of the
+    summed loss over 256 utterances = the sum over its two halves), (4) the forward-only loss equals the training loss
+    without dropout."""
+    B = 256
+    x, lens, y = _full_size_batch(B)
+    eng = _full_size_engine(gpu_lib, B, T=436)
+    loss, ntok = eng.train_step_grads(x, None, y, seed=3)
+    g1 = eng.get_all(_lib.GRAD)
+    loss_b, _ = eng.train_step_grads(x, None, y, seed=3)
+    g2 = eng.get_all(_lib.GRAD)
+    assert loss == loss_b and np.isfinite(loss) and ntok == int((y != 0).sum())
+    emb = "seq2seq/decoder_embedding_1806_150_0/weights"      # atomicAdd scatter: order-dependent rounding
+    for k in g1:
+        if k != emb:
+            assert np.array_equal(g1[k], g2[k]), k
+    le, ne = eng.eval_loss(x, None, y)
+    assert ne == ntok and abs(le - loss) <= 1e-5 * abs(loss)
+    # (2) padding invariance
+    xp = np.zeros((B, 436, 256), np.float32)
+    xp[:, :400] = x
+    loss_p, ntok_p = eng.train_step_grads(xp, None, y, seed=3)
+    gp = eng.get_all(_lib.GRAD)
+    assert ntok_p == ntok and abs(loss_p - loss) <= 1e-5 * abs(loss)
+    for k in g1:
+        assert pc.rel_err(gp[k], g1[k]) <= 1e-4, k
+    # (3) batch additivity: different batch tiling (one 128-row tile instead of two) and summation order
+    acc = None
+    ltot = 0.0
+    for lo in (0, 128):
+        l_h, _ = eng.train_step_grads(np.ascontiguousarray(x[lo:lo + 128]), None, np.ascontiguousarray(y[lo:lo + 128]), seed=3)
+        gh = eng.get_all(_lib.GRAD)
+        ltot += l_h
+        acc = gh if acc is None else {k: acc[k] + gh[k] for k in gh}
+    assert abs(ltot - loss) <= 2e-4 * abs(loss)
+    for k in g1:
+        assert pc.rel_err(acc[k], g1[k]) <= 5e-3, (k, pc.rel_err(acc[k], g1[k]))
+    eng.close()
+
+
+def test_degenerate_inputs(gpu_lib):
+    """Edge cases of the reference's data: an all-zero (empty) utterance inside a batch, a single frame, a single
+    utterance, targets that are EOS only -- against the oracle, tensor-core backend."""
+    from oracle import seq2seq_oracle as O
+    ocfg = O.OracleConfig(**pc.MEDIUM)
+    P = pc.make_params(ocfg)
+    x, lens, y = pc.make_batch(ocfg, 5, 40, 4)
+    x[2] = 0.0                      # empty utterance: length 0, encoder states zero
+    x[3, 1:] = 0.0                  # one frame
+    y[4] = 0
+    y[4, 0] = ocfg.eos_id           # EOS-only target
+    eng = pc.engine_for(pc.MEDIUM, gpu_lib, 5, 40, 4, gemm_backend="auto")
+    eng.set_all({k: v.numpy() for k, v in P.items()})
+    lo, no, g, _ = O.loss_and_grads(ocfg, P, torch.from_numpy(x), None, torch.from_numpy(y).long())
+    loss, ntok = eng.train_step_grads(x, None, y, seed=0)
+    assert ntok == no and abs(loss - lo) <= 1e-2 * abs(lo)
+    G = eng.get_all(_lib.GRAD)
+    for k, v in G.items():
+        assert pc.rel_err(v, g[k].numpy()) <= 5e-2, k
+    t_ref, _, _ = O.greedy_decode(ocfg, P, torch.from_numpy(x[:1]), None, max_len=4)
+    toks, _ = eng.greedy_decode(np.ascontiguousarray(x[:1]), None, max_len=4)      # B = 1
+    assert toks.shape == (1, 4)
+    eng.close()
