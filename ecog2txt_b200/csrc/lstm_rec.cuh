@@ -11,13 +11,14 @@
 //   forward : CTA owns hidden units [16j, 16j+16) -> its 64 gate columns (i|j|f|o x 16 units), K = H.
 //             D[128 x 64] = h_prev[128 x H] * WhT_slice[64 x H]^T ; epilogue thread = one batch row,
 //             keeps its 16 cell values in registers across all steps.
-//   backward: CTA owns the same 16 units -> N = 16 columns of dh_rec, K = 4H.
-//             D[128 x 16] = dz_next[128 x 4H] * Wh_slice[16 x 4H]^T ; dc carried in registers.
-// CTAs of one (direction, batch tile) chain exchange h / dz through L2 (their natural HBM buffers) and
-// a per-step arrival counter: epilogue stores -> fence -> red.release ; producer ld.acquire spin ->
-// fence.proxy.async -> TMA.  All CTAs must be co-resident: cooperative launch, grid <= #SMs.
+//   backward: k_lstm_bptt (below), reduce-scatter: every CTA multiplies only its own 64 dz columns for all H units and the
+//             partial dh goes through an L2 workspace.  The older all-gather form k_lstm_rec<true> (N = 16 columns of
+//             dh_rec, K = 4H: 819 KB of dz per CTA per step) is kept as the fallback for H > 512 only.
+// CTAs of one (direction, batch tile) chain exchange h / partial dh through L2 and a per-step arrival counter:
+// epilogue stores -> fence -> red.release ; waiter ld.relaxed spin -> fence.acq_rel (-> fence.proxy.async -> TMA).
+// All CTAs must be co-resident: cooperative launch, grid <= #SMs.
 //
-// warp roles: 0 = TMA producer (+ counter wait), 1 = MMA issuer (+ TMEM owner), 2..5 = epilogue.
+// warp roles (k_lstm_rec): 0 = TMA producer (+ counter wait), 1 = MMA issuer (+ TMEM owner), 2..9 = epilogue.
 #pragma once
 #include <algorithm>
 #include <cstdlib>
@@ -67,27 +68,6 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// TMA load delivered to the same smem offset (and signalling the same mbarrier offset) of every CTA in cta_mask
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
-      : "memory");
-}
-// tcgen05.commit arriving on the mbarrier at this smem offset in every CTA of cta_mask
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(cta_mask) : "memory");
 }
 // Bounded wait on a global arrival counter (a lost arrival must trap, not hang the GPU).
 __device__ __forceinline__ void wait_counter(const int* p, int target) {
@@ -208,7 +188,6 @@ struct RecFwdP {
   const int* lens2;       // [B] (nullable: all steps valid)
   int* counters;          // [2][n_bt][steps], zeroed before launch
   int steps, B, H, n_bt, n_slices, nkc, stages;
-  int csz;                // cluster size: consecutive unit slices of one chain share every A tile by TMA multicast
   DropP dp; int drop_F;
   long long* dbg;         // E2T_REC_DEBUG=1: per-step clock64 stamps of CTA 0 ([steps][8]), else NULL
   int pub_mode;
@@ -223,7 +202,6 @@ struct RecBwdP {
   const int* inject_t;                   // fwd direction: time index per row at which to inject (nullable -> 0)
   int* counters;
   int steps, B, H, n_bt, n_slices, nkc, stages;
-  int csz;
   long long* dbg;
   int pub_mode;
 };
@@ -272,7 +250,6 @@ k_lstm_rec(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ C
     if (dbgx && (step) == 10) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); dbgx[slot] = (long long)gt_; } } while (0)
 
   if (warp == 0 && lane == 0) {
-    // a stage is free once the MMA warps of ALL csz CTAs of the cluster have consumed it (multicast commit)
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     mbar_init(smem_u32(w_bar), 1);
     mbar_init(smem_u32(acc_full), 1);
@@ -877,7 +854,6 @@ inline void rec_launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap
   }
   // (a cluster sharing every A tile by TMA multicast was measured slower than unicast -- tools/ubench/ingest.cu: the
   // per-SM ingest of a 208 KB tile is ~2300 cycles alone or hot-shared by 100 CTAs, ~3200 with multicast -- and removed)
-  p.csz = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(kThreadsRec); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attrs[2];
@@ -903,9 +879,9 @@ inline void rec_launch(cudaStream_t st, const CUtensorMap& a0, const CUtensorMap
         fprintf(stderr, "\n");
       }
     }
-    fprintf(stderr, "[rec %s] steps=%d B=%d H=%d nkc=%d stages=%d cluster=%d grid=%u  (cycles rel. to flag-seen of each step)\n"
+    fprintf(stderr, "[rec %s] steps=%d B=%d H=%d nkc=%d ring=%dx%d grid=%u  (cycles rel. to flag-seen of each step)\n"
                     "  step  flag->tma_issued  ->first_full  ->mma_committed  ->acc_seen  ->h_stored  ->bar_passed  ->released | step_total\n",
-            BWD ? "bwd" : "fwd", p.steps, p.B, p.H, p.nkc, p.stages, p.csz, grid.x);
+            BWD ? "bwd" : "fwd", p.steps, p.B, p.H, p.nkc, p.stages, kGroup, grid.x);
     for (int s = 1; s < p.steps; ++s) {
       const long long* e = &hst[(size_t)s * 8];
       const long long prev = s > 1 ? hst[(size_t)(s - 1) * 8] : 0;
