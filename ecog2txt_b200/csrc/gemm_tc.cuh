@@ -162,13 +162,49 @@ __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <bool TN>
+// ---- cta_group::2 (CTA pair) primitives: the pair computes a 256 x BN tile, each SM holds its 128 rows of A and HALF of B,
+// so the operand ingest per SM and k-block drops from (128 + BN) to (128 + BN/2) rows -- measured 596 vs 790 cycles per
+// 256-wide k-block (tools/ubench/mma2cta.cu).  Only the leader CTA (cluster rank 0) issues MMAs; both load and drain.
+__device__ __forceinline__ uint32_t cluster_rank_() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all_() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load into this CTA's smem whose completion is signalled on the LEADER's mbarrier (peer bit of the address cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+// commit arriving on the mbarrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+// arrive on the barrier at this smem offset in the leader CTA (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t local_bar) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(0));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+template <bool TN, bool TWO>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
           const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2, TcGemmP p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t A_BYTES = BM * BK * 4, B_BYTES = (uint32_t)p.BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+  // TWO: this CTA stages its own 128 rows of A and BN/2 rows of B
+  const int bn_local = TWO ? p.BN / 2 : p.BN;
+  const uint32_t A_BYTES = BM * BK * 4, B_BYTES = (uint32_t)bn_local * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+  const uint32_t rank = TWO ? cluster_rank_() : 0u;
+  const int tile_rows = TWO ? 2 * BM : BM;
+  const int cta0 = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // work-item index / stride in CTAs or CTA pairs
+  const int ncta = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   float* stage_c = reinterpret_cast<float*>(smem + (size_t)p.stages * STAGE_BYTES);      // [4 warps][32][kEpiPad]
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_c + 4 * 32 * kEpiPad);
   uint64_t* full_bar = bars;                      // [stages]
@@ -180,13 +216,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&acc_full[a]), 1); mbar_init(smem_u32(&acc_empty[a]), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&acc_full[a]), 1); mbar_init(smem_u32(&acc_empty[a]), TWO ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == 1) {
+    if (!TWO) tmem_alloc(smem_u32(tmem_slot), 512);
+    else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  }
   fence_before_sync();
   __syncthreads();
+  if (TWO) cluster_sync_all_();      // the peer's barriers are initialised before anything is signalled across the pair
   fence_after_sync();
   // warp-uniform by construction (REDUX writes a uniform register): keeps the tcgen05 operands out of vector registers
   const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
@@ -197,10 +240,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   if (warp == 0) {
     // ================= TMA producer =================
     int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = cta0; item < n_items; item += ncta) {
       const int ks = item / (p.tiles_m * p.tiles_n);
       const int tile = item - ks * (p.tiles_m * p.tiles_n);
-      const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * p.BN;
+      const int m0 = (tile / p.tiles_n) * tile_rows + (int)rank * BM;              // this CTA's 128 rows of A
+      const int n0 = (tile % p.tiles_n) * p.BN + (int)rank * bn_local;             // its rows of B
       const int kb0 = ks * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, num_kb_total);
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % p.stages;
@@ -208,29 +252,38 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
         if (elect_one()) {
           const uint32_t fb = smem_u32(&full_bar[s]);
-          mbar_expect_tx(fb, STAGE_BYTES);
+          // TWO: both CTAs' loads complete on the leader's barrier, which therefore expects twice the bytes
+          if (!TWO) mbar_expect_tx(fb, STAGE_BYTES);
+          else if (rank == 0) mbar_expect_tx(fb, 2 * STAGE_BYTES);
           const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
           const bool second = kb >= p.nkb0;
           const CUtensorMap* ma = second ? &map_a2 : &map_a;
           const CUtensorMap* mb = second ? &map_b2 : &map_b;
           const int kc = (second ? kb - p.nkb0 : kb) * BK;
           if (!TN) {
-            tma_load_2d(sa, ma, fb, kc, m0);
-            tma_load_2d(sa + A_BYTES, mb, fb, kc, n0);
+            if (!TWO) { tma_load_2d(sa, ma, fb, kc, m0); tma_load_2d(sa + A_BYTES, mb, fb, kc, n0); }
+            else { tma_load_2d_2sm(sa, ma, fb, kc, m0); tma_load_2d_2sm(sa + A_BYTES, mb, fb, kc, n0); }
           } else {
 #pragma unroll
-            for (int i = 0; i < BM / 32; ++i) tma_load_2d(sa + i * (BK * 128), ma, fb, m0 + i * 32, kc);
-            for (int i = 0; i < p.BN / 32; ++i) tma_load_2d(sa + A_BYTES + i * (BK * 128), mb, fb, n0 + i * 32, kc);
+            for (int i = 0; i < BM / 32; ++i) {
+              if (!TWO) tma_load_2d(sa + i * (BK * 128), ma, fb, m0 + i * 32, kc);
+              else tma_load_2d_2sm(sa + i * (BK * 128), ma, fb, m0 + i * 32, kc);
+            }
+            for (int i = 0; i < bn_local / 32; ++i) {
+              if (!TWO) tma_load_2d(sa + A_BYTES + i * (BK * 128), mb, fb, n0 + i * 32, kc);
+              else tma_load_2d_2sm(sa + A_BYTES + i * (BK * 128), mb, fb, n0 + i * 32, kc);
+            }
           }
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    const uint32_t idesc = make_idesc_tf32(BM, p.BN, TN ? 1 : 0);
+    // ================= MMA issuer (TWO: the leader CTA only) =================
+    const uint32_t idesc = make_idesc_tf32(tile_rows, p.BN, TN ? 1 : 0);
     int it = 0, n_done = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+    if (!TWO || rank == 0)
+    for (int item = cta0; item < n_items; item += ncta, ++n_done) {
       const int ks = item / (p.tiles_m * p.tiles_n);
       const int kb0 = ks * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, num_kb_total);
       const int acc = n_done & 1;
@@ -250,10 +303,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             const uint64_t da = TN ? make_smem_desc_mn(sa + k * 1024, BK * 128, 512) : make_smem_desc(sa + k * UMMA_K * 4);
             const uint64_t db = TN ? make_smem_desc_mn(sa + A_BYTES + k * 1024, BK * 128, 512)
                                    : make_smem_desc(sa + A_BYTES + k * UMMA_K * 4);
-            umma_tf32(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (!TWO) umma_tf32(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_tf32_2sm(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(smem_u32(&empty_bar[s]));             // frees this smem stage when the MMAs retire
-          if (kb == kb1 - 1) umma_commit(smem_u32(&acc_full[acc]));
+          if (!TWO) {
+            umma_commit(smem_u32(&empty_bar[s]));             // frees this smem stage when the MMAs retire
+            if (kb == kb1 - 1) umma_commit(smem_u32(&acc_full[acc]));
+          } else {
+            umma_commit_2sm(smem_u32(&empty_bar[s]));         // ... in both CTAs of the pair
+            if (kb == kb1 - 1) umma_commit_2sm(smem_u32(&acc_full[acc]));
+          }
         }
         __syncwarp();
       }
@@ -263,10 +322,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     const int quad = warp & 3;
     float* st = stage_c + (size_t)(warp - 2) * 32 * kEpiPad;
     int n_done = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+    for (int item = cta0; item < n_items; item += ncta, ++n_done) {
       const int ks = item / (p.tiles_m * p.tiles_n);
       const int tile = item - ks * (p.tiles_m * p.tiles_n);
-      const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * p.BN;
+      const int m0 = (tile / p.tiles_n) * tile_rows + (int)rank * BM, n0 = (tile % p.tiles_n) * p.BN;   // own rows, all BN columns
       const int acc = n_done & 1;
       const uint32_t acc_ph = (n_done >> 1) & 1;
       mbar_wait(smem_u32(&acc_full[acc]), acc_ph);
@@ -322,14 +381,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       }
       fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cta(smem_u32(&acc_empty[acc]));
+      if (lane == 0) {
+        if (!TWO) mbar_arrive_cta(smem_u32(&acc_empty[acc]));
+        else mbar_arrive_leader(smem_u32(&acc_empty[acc]));     // the leader's MMA warp waits for both CTAs' epilogues
+      }
     }
   }
   fence_before_sync();
   __syncthreads();
+  if (TWO) cluster_sync_all_();      // nobody frees TMEM / leaves while the peer may still signal or read across the pair
   if (warp == 1) {
     fence_after_sync();
-    tmem_dealloc(tmem_base, 512);
+    if (!TWO) tmem_dealloc(tmem_base, 512);
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -410,25 +474,31 @@ inline SplitWs& split_ws(cudaStream_t st) {
 // Tile width and split-K from a small cost model fitted to B200 measurements (tools/sweep_gemm.py): a k-block costs
 // ~650 cycles up to BN = 128 (stage hand-off + MMA issue, not the tensor pipe) and ~1.1 more per extra column; a CTA pays
 // ~6000 cycles of prologue / drain, a split-K reduction ~8000 cycles plus its traffic.
-inline void pick_tiling(int M, int N, int num_kb, bool tn, int nsm, int* bn_out, int* ks_out) {
-  const int step = tn ? 32 : 16;
-  const int tm = (M + BM - 1) / BM;
-  const int n_cap = (N + step - 1) / step * step;
+inline void pick_tiling(int M, int N, int num_kb, bool tn, int nsm, int* bn_out, int* ks_out, int* two_out) {
   double best = 1e30;
-  int best_bn = std::min(256, n_cap), best_ks = 1;
-  for (int bn = std::min(256, n_cap); bn >= std::min(32, n_cap); bn -= step) {
-    const int tiles = tm * ((N + bn - 1) / bn);
-    const double per_kb = 650.0 + std::max(0, bn - 128) * 1.1;
-    const int ks_max = tiles >= nsm ? 1 : std::max(1, std::min(8, num_kb / 8));
-    for (int ks = 1; ks <= ks_max; ++ks) {
-      const int kb = (num_kb + ks - 1) / ks;
-      const double waves = std::ceil((double)tiles * ks / nsm);
-      double cost = 6000.0 + waves * (kb * per_kb + bn / 32.0 * 500.0);
-      if (ks > 1) cost += 8000.0 + (double)ks * M * N * 4.0 / 3.0e12 * 1.965e9;
-      if (cost < best - 1.0) { best = cost; best_bn = bn; best_ks = ks; }
+  int best_bn = 0, best_ks = 1, best_two = 0;
+  static const bool allow_two = getenv("E2T_GEMM_NO_2SM") == nullptr;
+  for (int two = 0; two <= ((allow_two && M > BM) ? 1 : 0); ++two) {
+    // single CTA: BN multiple of 16 (TN: 32); CTA pair: each SM stages BN/2 rows of B -> multiples of 32 (TN: 64)
+    const int step = (tn ? 32 : 16) * (two ? 2 : 1);
+    const int tm = two ? (M + 2 * BM - 1) / (2 * BM) : (M + BM - 1) / BM;
+    const int units = two ? nsm / 2 : nsm;
+    const int n_cap = (N + step - 1) / step * step;
+    for (int bn = std::min(256, n_cap); bn >= std::min(2 * step, n_cap); bn -= step) {
+      const int tiles = tm * ((N + bn - 1) / bn);
+      // cycles per 32-deep k-block (tools/sweep_gemm.py, tools/ubench/mma2cta.cu)
+      const double per_kb = two ? 520.0 + std::max(0, bn - 128) * 0.6 : 650.0 + std::max(0, bn - 128) * 1.1;
+      const int ks_max = tiles >= units ? 1 : std::max(1, std::min(8, num_kb / 8));
+      for (int ks = 1; ks <= ks_max; ++ks) {
+        const int kb = (num_kb + ks - 1) / ks;
+        const double waves = std::ceil((double)tiles * ks / units);
+        double cost = (two ? 7000.0 : 6000.0) + waves * (kb * per_kb + bn / 32.0 * 500.0);
+        if (ks > 1) cost += 8000.0 + (double)ks * M * N * 4.0 / 3.0e12 * 1.965e9;
+        if (cost < best - 1.0) { best = cost; best_bn = bn; best_ks = ks; best_two = two; }
+      }
     }
   }
-  *bn_out = best_bn; *ks_out = best_ks;
+  *bn_out = best_bn; *ks_out = best_ks; *two_out = best_two;
 }
 
 // Optional second operand pair (A2, B2, K2): C = A B^T + A2 B2^T (+bias, +beta C) in ONE pass over C -- the two LSTM
@@ -443,8 +513,9 @@ inline void launch_gemm(cudaStream_t st, const float* A, i64 lda, const float* B
   p.nkb0 = (K + BK - 1) / BK;
   const int num_kb = p.nkb0 + (A2 ? (K2 + BK - 1) / BK : 0);
   p.nkb_total = num_kb;
-  pick_tiling(M, N, num_kb, TN, nsm, &p.BN, &p.ksplit);
-  p.tiles_m = (M + BM - 1) / BM;
+  int two = 0;
+  pick_tiling(M, N, num_kb, TN, nsm, &p.BN, &p.ksplit, &two);
+  p.tiles_m = two ? (M + 2 * BM - 1) / (2 * BM) : (M + BM - 1) / BM;
   p.tiles_n = (N + p.BN - 1) / p.BN;
   int tiles = p.tiles_m * p.tiles_n;
   {  // diagnostic overrides for shape sweeps (tools/sweep_gemm.py)
@@ -458,8 +529,9 @@ inline void launch_gemm(cudaStream_t st, const float* A, i64 lda, const float* B
   }
   p.kb_per_split = (num_kb + p.ksplit - 1) / p.ksplit;
   p.ksplit = (num_kb + p.kb_per_split - 1) / p.kb_per_split;     // no empty splits
+  const int bn_local = two ? p.BN / 2 : p.BN;      // B rows staged per SM
   int stages = 8;
-  while (stages > 2 && gemm_smem_bytes(p.BN, stages) > kSmemCap) --stages;
+  while (stages > 2 && gemm_smem_bytes(bn_local, stages) > kSmemCap) --stages;
   p.stages = stages;
   if (p.ksplit > 1) {
     SplitWs& w = split_ws(st);
@@ -472,22 +544,34 @@ inline void launch_gemm(cudaStream_t st, const float* A, i64 lda, const float* B
     p.ws = w.p;
   }
   CUtensorMap ma, mb, ma2, mb2;
-  if (!TN) { ma = make_map(A, M, K, lda, BM); mb = make_map(B, N, K, ldb, p.BN); }
+  if (!TN) { ma = make_map(A, M, K, lda, BM); mb = make_map(B, N, K, ldb, bn_local); }
   else { ma = make_map(A, K, M, lda, BK, true); mb = make_map(B, K, N, ldb, BK, true); }
   ma2 = ma; mb2 = mb;
   if (A2) {
-    if (!TN) { ma2 = make_map(A2, M, K2, lda2, BM); mb2 = make_map(B2, N, K2, ldb2, p.BN); }
+    if (!TN) { ma2 = make_map(A2, M, K2, lda2, BM); mb2 = make_map(B2, N, K2, ldb2, bn_local); }
     else { ma2 = make_map(A2, K2, M, lda2, BK, true); mb2 = make_map(B2, K2, N, ldb2, BK, true); }
   }
-  auto kfn = k_gemm_tc<TN>;
   static bool attr_set = false;
   if (!attr_set) {
-    E2T_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap));
+    E2T_CHECK(cudaFuncSetAttribute(k_gemm_tc<TN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap));
+    E2T_CHECK(cudaFuncSetAttribute(k_gemm_tc<TN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap));
     attr_set = true;
   }
   tiles = p.tiles_m * p.tiles_n;
-  const int grid = std::min(tiles * p.ksplit, nsm);
-  kfn<<<grid, kGemmThreads, gemm_smem_bytes(p.BN, p.stages), st>>>(ma, mb, ma2, mb2, p);
+  const size_t smem_bytes = gemm_smem_bytes(bn_local, p.stages);
+  if (!two) {
+    const int grid = std::min(tiles * p.ksplit, nsm);
+    k_gemm_tc<TN, false><<<grid, kGemmThreads, smem_bytes, st>>>(ma, mb, ma2, mb2, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * std::min(tiles * p.ksplit, nsm / 2)));
+    cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    E2T_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tc<TN, true>, ma, mb, ma2, mb2, p));
+  }
   if (p.ksplit > 1) {
     const i64 n = (i64)M * N;
     k_splitk_reduce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.ws, p.ksplit, M, N, C, ldc, bias, beta);
