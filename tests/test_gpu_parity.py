@@ -224,3 +224,34 @@ def test_degenerate_inputs(gpu_lib):
     toks, _ = eng.greedy_decode(np.ascontiguousarray(x[:1]), None, max_len=4)      # B = 1
     assert toks.shape == (1, 4)
     eng.close()
+
+
+def test_staged_inputs_match_host_path(gpu_lib):
+    """e2t_stage_inputs (the prefetch pipeline bench.py's e2e leg and SequenceNetwork.fit use): staging batch i+1 while batch i
+    trains gives exactly the loss / gradients of the plain host path, in both slots, and guards against shape mix-ups."""
+    from oracle import seq2seq_oracle as O
+    from ecog2txt_b200 import E2TError
+    ocfg = O.OracleConfig(**pc.MEDIUM)
+    P = pc.make_params(ocfg)
+    eng = pc.engine_for(pc.MEDIUM, gpu_lib, 16, 96, 6, gemm_backend="auto")
+    eng.set_all({k: v.numpy() for k, v in P.items()})
+    batches = [pc.make_batch(ocfg, 16, 96, 6, seed=s) for s in range(3)]
+    ref = []
+    for x, _, y in batches:
+        loss, ntok = eng.train_step_grads(x, None, y, seed=7)
+        ref.append((loss, ntok, eng.get_all(_lib.GRAD)))
+    eng.stage_inputs(0, batches[0][0], None, batches[0][2])
+    for i, (x, _, y) in enumerate(batches):
+        if i + 1 < len(batches):
+            eng.stage_inputs((i + 1) & 1, batches[i + 1][0], None, batches[i + 1][2])     # overlaps the step below
+        loss, ntok = eng.train_step_grads_staged(i & 1, seed=7)
+        assert (loss, ntok) == ref[i][:2]
+        g = eng.get_all(_lib.GRAD)
+        for k in g:
+            if "decoder_embedding" in k and k.endswith("weights"):
+                continue   # atomicAdd scatter
+            assert np.array_equal(g[k], ref[i][2][k]), k
+    with pytest.raises(E2TError):
+        eng._staged_shape[0] = (8, 96, 6, 0)        # a slot holds what was staged, not what the caller claims
+        eng.train_step_grads_staged(0, seed=7)
+    eng.close()
