@@ -163,12 +163,32 @@ class SequenceNetwork:
                 plan += [(si, order[i:i + self.N_cases]) for i in range(0, len(order), self.N_cases)]
             order = rs.permutation(len(plan))
             ep_loss, ep_tok = 0.0, 0
+            # this rank's shard of every minibatch of the epoch; the host->device copy of minibatch k+1 is started
+            # (e2t_stage_inputs, library copy stream) before minibatch k is trained -- the tf.data prefetch of the reference
+            shards = []
             for pi in order:
                 si, idx = plan[pi]
                 lo, hi = shard_range(len(idx), rank, world)
-                if hi > lo:
-                    x, y = self._batch(data[subnets_params[si].subnet_id]['training'], idx[lo:hi], max_T, max_L, pad_id)
-                    loss, ntok = eng.train_step_grads(x, None, y, subnet=si, seed=step)
+                shards.append((si, idx[lo:hi]))
+            pipelined = not eng.emulated
+
+            def host_batch(k):
+                si, ids = shards[k]
+                return self._batch(data[subnets_params[si].subnet_id]['training'], ids, max_T, max_L, pad_id) if len(ids) else None
+
+            nxt = host_batch(0) if shards else None
+            if pipelined and nxt is not None:
+                eng.stage_inputs(0, nxt[0], None, nxt[1], subnet=shards[0][0])
+            for k, (si, ids) in enumerate(shards):
+                cur = nxt
+                nxt = host_batch(k + 1) if k + 1 < len(shards) else None
+                if pipelined and nxt is not None:
+                    eng.stage_inputs((k + 1) & 1, nxt[0], None, nxt[1], subnet=shards[k + 1][0])
+                if cur is not None:
+                    if pipelined:
+                        loss, ntok = eng.train_step_grads_staged(k & 1, seed=step)
+                    else:
+                        loss, ntok = eng.train_step_grads(cur[0], None, cur[1], subnet=si, seed=step)
                 else:   # fewer utterances than ranks: contribute zero gradients
                     flat_tensor(eng, _lib.GRAD).zero_()
                     loss, ntok = 0.0, 0
