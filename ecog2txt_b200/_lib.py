@@ -15,8 +15,9 @@ HOST, DEVICE, STAGED0, STAGED1 = 0, 1, 2, 3
 VALUE, GRAD, ADAM_M, ADAM_V, EMA = 0, 1, 2, 3, 4
 ACT = {"linear": 0, "relu": 1}
 GEMM = {"auto": 0, "simt": 1, "tcgen05": 2}
-ATTN = {"none": 0, "luong": 1}
-ABI_VERSION = 3
+ATTN = {"none": 0, "luong": 1, "bahdanau": 2}
+AUX_KIND = {"gaussian": 0, "categorical": 1}
+ABI_VERSION = 4
 
 
 class E2TConfig(C.Structure):
@@ -51,6 +52,11 @@ class E2TConfig(C.Structure):
         ("gemm_backend", C.c_int32),
         ("device", C.c_int32),
         ("attention", C.c_int32),
+        ("aux_layer", C.c_int32),
+        ("aux_hidden", C.c_int32),
+        ("aux_F", C.c_int32),
+        ("aux_kind", C.c_int32),
+        ("aux_penalty", C.c_float),
     ]
 
 
@@ -76,6 +82,10 @@ _SIGNATURES = {
     "e2t_train_step_grads": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                        C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "e2t_stage_inputs": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
+    "e2t_set_encoder_targets": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
+    "e2t_last_losses": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "e2t_input_saliency": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                     C.c_float, _P, _P]),
     "e2t_adam_ema_step": (C.c_int, [_P, C.c_int, C.c_float]),
     "e2t_eval_loss": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.POINTER(C.c_float), C.POINTER(C.c_int32)]),

@@ -29,7 +29,7 @@
 
 static thread_local std::string g_err;
 extern "C" const char* e2t_last_error(void) { return g_err.c_str(); }
-extern "C" int e2t_abi_version(void) { return 3; }
+extern "C" int e2t_abi_version(void) { return 4; }
 
 namespace {
 
@@ -87,10 +87,26 @@ struct e2t_handle {
   std::vector<EncLayer> enc;
   i64 demb_w, demb_b, dec_K, dec_b, proj_w, proj_b;
   i64 at_wq = 0, at_wc = 0, at_bc = 0;          // attention parameters (cfg.attention != NONE)
+  i64 at_wk = 0, at_v = 0;                      // Bahdanau only: key projection [Hd, Hd], score vector [1, Hd]
+  float *at_kp = nullptr, *at_dkp = nullptr, *at_dvrow = nullptr, *at_keysT = nullptr;
   float *at_q = nullptr, *at_ctx = nullptr, *at_ht = nullptr, *at_alpha = nullptr, *at_dscore = nullptr;
   float *at_dht = nullptr, *at_dctx = nullptr, *at_dq = nullptr;
   float *at_combT = nullptr, *at_queryT = nullptr;   // packed transposes for the backward GEMMs
   float *g_q = nullptr, *g_ctx = nullptr, *g_ht = nullptr, *g_alpha = nullptr;
+
+  // A6 encoder-targets head: parameter offsets (w1/b1 only with a hidden layer), activations, targets of the next step
+  bool aux = false;
+  i64 aux_w1 = 0, aux_b1 = 0, aux_w2 = 0, aux_b2 = 0;
+  int aux_In = 0, aux_Pp = 0, aux_Fp = 0;
+  float *aux_w1T_lo = nullptr, *aux_hs_hi = nullptr, *aux_hs_lo = nullptr;   // 3xTF32 operands of the hidden GEMM (tensor-core backend)
+  float *aux_w1T = nullptr, *aux_z1 = nullptr, *aux_dz1 = nullptr, *aux_out = nullptr, *aux_loss_rows = nullptr;
+  int* aux_cnt_rows = nullptr;
+  void* aux_tgt = nullptr;          // device copy of the caller's [B,T,F] float / [B,T] int targets
+  bool aux_ready = false, aux_ran = false;
+  int aux_tgt_B = 0, aux_tgt_T = 0;
+  float pen_dec = 1.f, pen_aux = 1.f;   // penalty scales in force (e2t_input_saliency overrides them for one call)
+  // A13 saliency workspace (allocated on first use)
+  float *sal_tmp = nullptr, *sal_dx = nullptr, *sal_sq = nullptr;
 
   // capacities
   int Bm, Tm, Lm, T2m, Cmax, Dp, Vp, beam_m;
@@ -392,11 +408,30 @@ void build_params(e2t_handle* h) {
   snprintf(buf, sizeof buf, "seq2seq/decoder_projection_%d_%d_0", c.Hd, c.V);
   h->proj_w = h->n_params; add_tensor(h, std::string(buf) + "/weights", {c.V, c.Hd}, -1);
   h->proj_b = h->n_params; add_tensor(h, std::string(buf) + "/biases", {c.V}, -1);
-  if (c.attention == E2T_ATTN_LUONG) {
+  if (c.attention != E2T_ATTN_NONE) {
     // stored [out, in] like the projection (trainers.py:513-520), i.e. already the K-major B operand of the forward GEMMs
     h->at_wq = h->n_params; add_tensor(h, "seq2seq/decoder_attention/query/weights", {c.Hd, c.Hd}, -1);
+    if (c.attention == E2T_ATTN_BAHDANAU) {
+      h->at_wk = h->n_params; add_tensor(h, "seq2seq/decoder_attention/keys/weights", {c.Hd, c.Hd}, -1);
+      h->at_v = h->n_params; add_tensor(h, "seq2seq/decoder_attention/score/weights", {1, c.Hd}, -1);
+    }
     h->at_wc = h->n_params; add_tensor(h, "seq2seq/decoder_attention/combine/weights", {c.Hd, 2 * c.Hd}, -1);
     h->at_bc = h->n_params; add_tensor(h, "seq2seq/decoder_attention/combine/biases", {c.Hd}, -1);
+  }
+  h->aux = c.aux_F > 0;
+  if (h->aux) {
+    // A6: '<x>_projection' scopes number their layers; the last layer's weight is stored transposed (trainers.py:488-520)
+    int n_feat = 2 * c.H[c.aux_layer], k = 0;
+    h->aux_In = n_feat;
+    if (c.aux_hidden > 0) {
+      snprintf(buf, sizeof buf, "seq2seq/encoder_%d_projection_%d_%d_0", c.aux_layer, n_feat, c.aux_hidden);
+      h->aux_w1 = h->n_params; add_tensor(h, std::string(buf) + "/weights", {n_feat, c.aux_hidden}, -1);
+      h->aux_b1 = h->n_params; add_tensor(h, std::string(buf) + "/biases", {c.aux_hidden}, -1);
+      n_feat = c.aux_hidden; k = 1;
+    }
+    snprintf(buf, sizeof buf, "seq2seq/encoder_%d_projection_%d_%d_%d", c.aux_layer, n_feat, c.aux_F, k);
+    h->aux_w2 = h->n_params; add_tensor(h, std::string(buf) + "/weights", {c.aux_F, n_feat}, -1);
+    h->aux_b2 = h->n_params; add_tensor(h, std::string(buf) + "/biases", {c.aux_F}, -1);
   }
 }
 
@@ -414,7 +449,14 @@ void validate(const e2t_config& c) {
   E2T_REQUIRE(c.ff_dropout >= 0.f && c.ff_dropout < 1.f && c.rnn_dropout >= 0.f && c.rnn_dropout < 1.f,
               "dropout must be in [0,1)");
   E2T_REQUIRE(c.max_beam >= 1 && c.max_beam <= 32, "max_beam must be in [1,32]");
-  E2T_REQUIRE(c.attention == E2T_ATTN_NONE || c.attention == E2T_ATTN_LUONG, "attention must be E2T_ATTN_NONE or E2T_ATTN_LUONG");
+  E2T_REQUIRE(c.attention == E2T_ATTN_NONE || c.attention == E2T_ATTN_LUONG || c.attention == E2T_ATTN_BAHDANAU,
+              "attention must be E2T_ATTN_NONE, E2T_ATTN_LUONG or E2T_ATTN_BAHDANAU");
+  E2T_REQUIRE(c.aux_F >= 0 && c.aux_hidden >= 0, "aux_F / aux_hidden must be >= 0");
+  if (c.aux_F > 0) {
+    E2T_REQUIRE(c.aux_layer >= 0 && c.aux_layer < c.n_enc_layers, "aux_layer must name an encoder layer");
+    E2T_REQUIRE(c.aux_kind == E2T_AUX_GAUSSIAN || c.aux_kind == E2T_AUX_CATEGORICAL, "aux_kind must be E2T_AUX_*");
+    E2T_REQUIRE(c.aux_kind == E2T_AUX_GAUSSIAN || c.aux_F >= 2, "a categorical head needs >= 2 classes");
+  }
 }
 
 void build_workspace(e2t_handle* h) {
@@ -476,7 +518,7 @@ void build_workspace(e2t_handle* h) {
   h->colsum_ws = h->alloc<float>(h->colsum_ws_n);
   if (h->perm_ws_n) h->perm_ws = h->alloc<float>(h->perm_ws_n);
   {
-    i64 ncols = h->Vp + 4 * c.Hd + h->Dp + c.E + 2 * c.Hd;
+    i64 ncols = h->Vp + 4 * c.Hd + h->Dp + c.E + 3 * c.Hd + round_up(c.aux_F, 4) + round_up(c.aux_hidden, 4);
     for (auto& L : h->enc) ncols += 2 * 4 * L.H;
     h->colsum_pool_n = 64 * ncols;
     h->colsum_pool = h->alloc<float>(h->colsum_pool_n);
@@ -506,7 +548,31 @@ void build_workspace(e2t_handle* h) {
     h->g_q = h->alloc<float>(Rr * c.Hd); h->g_ctx = h->alloc<float>(Rr * c.Hd); h->g_ht = h->alloc<float>(Rr * c.Hd);
     h->g_alpha = h->alloc<float>(Rr * T2);
     h->colsum_ws_n = std::max<i64>(h->colsum_ws_n, (i64)64 * c.Hd);
+    if (c.attention == E2T_ATTN_BAHDANAU) {
+      h->at_kp = h->alloc<float>(T2 * Bm * c.Hd); h->at_dkp = h->alloc<float>(T2 * Bm * c.Hd);
+      h->at_dvrow = h->alloc<float>(n);
+      h->at_keysT = h->alloc<float>((i64)c.Hd * c.Hd);
+    }
   }
+  if (h->aux) {
+    const i64 rows = T2 * Bm;
+    h->aux_Pp = round_up(c.aux_hidden, 4); h->aux_Fp = round_up(c.aux_F, 4);
+    if (c.aux_hidden > 0) {
+      h->aux_w1T = h->alloc<float>((i64)c.aux_hidden * h->aux_In);
+#ifndef E2T_EMU
+      if (c.gemm_backend != E2T_GEMM_SIMT && (h->aux_In & 3) == 0) {
+        h->aux_w1T_lo = h->alloc<float>((i64)c.aux_hidden * h->aux_In);
+        h->aux_hs_hi = h->alloc<float>(rows * h->aux_In); h->aux_hs_lo = h->alloc<float>(rows * h->aux_In);
+      }
+#endif
+      h->aux_z1 = h->alloc<float>(rows * h->aux_Pp); h->aux_dz1 = h->alloc<float>(rows * h->aux_Pp);
+    }
+    h->aux_out = h->alloc<float>(rows * h->aux_Fp);
+    h->aux_loss_rows = h->alloc<float>(rows); h->aux_cnt_rows = h->alloc<int>(rows);
+    const i64 per_frame = c.aux_kind == E2T_AUX_GAUSSIAN ? c.aux_F : 1;
+    h->aux_tgt = h->alloc<float>(Bm * h->Tm * per_frame);   // int32 and fp32 are both 4 bytes
+  }
+  h->pen_dec = c.penalty_scale; h->pen_aux = c.aux_penalty;
   // decode workspace (rows = B*beam)
   const i64 R = Bm * h->beam_m;
   for (int i = 0; i < 2; ++i) {
@@ -545,7 +611,10 @@ void repack(e2t_handle* h, const float* src, int src_id) {
   if (c.attention != E2T_ATTN_NONE) {
     tr(src + h->at_wc, 2 * c.Hd, h->at_combT, c.Hd, c.Hd, 2 * c.Hd);      // [Hd, 2Hd] -> [2Hd, Hd]
     tr(src + h->at_wq, c.Hd, h->at_queryT, c.Hd, c.Hd, c.Hd);
+    if (c.attention == E2T_ATTN_BAHDANAU) tr(src + h->at_wk, c.Hd, h->at_keysT, c.Hd, c.Hd, c.Hd);
   }
+  if (h->aux && c.aux_hidden > 0)   // W1 [In, P] -> W1^T [P, In]: the K-major B operand of the head's first GEMM
+    tr(src + h->aux_w1, c.aux_hidden, h->aux_w1T, h->aux_In, h->aux_In, c.aux_hidden, 0, h->aux_w1T_lo);
   for (int s = 0; s < c.n_subnets; ++s) {
     int WC = c.subnet_W[s] * c.subnet_C[s];
     // tensor-core conv: Wc^T split into its tf32-exact part and the remainder (3xTF32 forward, conv_tc.cuh)
@@ -713,6 +782,8 @@ void encoder_forward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, 
   EncLayer& top = h->enc.back();
   LAUNCH(h, k_gather_final, grid1((i64)B * 2 * top.H), dim3(256), 0, top.hs, top.cs[0], top.cs[1], h->d_lens2,
          h->h0, h->c0, B, top.H);
+  if (c.attention == E2T_ATTN_BAHDANAU)   // keys of the additive attention, once per batch: kp = enc Wk^T
+    gemm(h, top.hs, c.Hd, 1, Wc + h->at_wk, 1, c.Hd, h->at_kp, c.Hd, T2 * B, c.Hd, c.Hd, nullptr, 0.f);
   h->last_B = B; h->last_T2 = T2; h->last_subnet = subnet;
 }
 
@@ -736,8 +807,9 @@ void decoder_forward(e2t_handle* h, const Inputs& in, int B, int L, bool train, 
     const EncLayer& top = h->enc.back();
     const int T2 = h->last_T2;
     gemm(h, h->hdec, c.Hd, 1, Wc + h->at_wq, 1, c.Hd, h->at_q, c.Hd, (int)rows, c.Hd, c.Hd, nullptr, 0.f);
+    const bool bah = c.attention == E2T_ATTN_BAHDANAU;
     LAUNCH(h, k_attn_fwd, dim3((unsigned)rows), dim3(128), (size_t)T2 * sizeof(float), h->at_q, top.hs, h->d_lens2,
-           h->at_alpha, h->at_ctx, B, B, 1, T2, c.Hd, h->T2m);
+           h->at_alpha, h->at_ctx, B, B, 1, T2, c.Hd, h->T2m, bah ? h->at_kp : nullptr, bah ? Wc + h->at_v : nullptr);
     gemm2(h, h->at_ctx, c.Hd, Wc + h->at_wc, 2 * c.Hd, c.Hd, h->hdec, c.Hd, Wc + h->at_wc + c.Hd, 2 * c.Hd, c.Hd, h->at_ht,
           c.Hd, (int)rows, c.Hd, Wc + h->at_bc, 0.f);
     LAUNCH(h, k_tanh_fwd, grid1(rows * c.Hd), dim3(256), 0, h->at_ht, rows * c.Hd);
@@ -746,9 +818,84 @@ void decoder_forward(e2t_handle* h, const Inputs& in, int B, int L, bool train, 
   // logits = h Wp^T + b ; Wp canonical [V,Hd] is already the K-major B operand
   gemm(h, proj_in, c.Hd, 1, Wc + h->proj_w, 1, c.Hd, h->logits, h->Vp, (int)rows, c.V, c.Hd, Wc + h->proj_b, 0.f);
   LAUNCH(h, k_softmax_ce, dim3((unsigned)rows), dim3(128), 0, h->logits, h->Vp, c.V, h->d_tgt, c.pad_id,
-         c.penalty_scale, h->loss_rows, with_grad ? 1 : 0);
+         h->pen_dec, h->loss_rows, with_grad ? 1 : 0);
   LAUNCH(h, k_reduce_loss, dim3(1), dim3(256), 0, h->loss_rows, h->d_tgt, c.pad_id, (int)rows, h->d_loss, h->d_ntok);
   h->last_L = L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A6: encoder-targets head on the outputs of encoder layer cfg.aux_layer (trainers.py:798-799; App. D item 12)
+// ------------------------------------------------------------------------------------------------
+void aux_forward(e2t_handle* h, int subnet, int B, int T, bool train, uint32_t seed, bool with_grad) {
+  h->aux_ran = false;
+  if (!h->aux || !h->aux_ready) return;
+  h->aux_ready = false;            // the targets belong to this step only
+  const e2t_config& c = h->cfg;
+  E2T_REQUIRE(h->aux_tgt_B == B && h->aux_tgt_T == T, "encoder targets were set for another batch shape");
+  const float* Wc = h->Wc;
+  const int W = c.subnet_W[subnet], T2 = (int)cdiv(T, W);
+  const int rows = T2 * B;
+  const EncLayer& Ly = h->enc[c.aux_layer];
+  const float* feat = Ly.hs; int ldf = h->aux_In, nf = h->aux_In;
+  if (c.aux_hidden > 0) {
+    if (h->aux_w1T_lo) {
+      // tensor-core backend: these pre-activations feed a ReLU, and with plain tf32 products the ones within ~1e-3 of zero
+      // flip sides (measured: up to 8 % error on the head's and the lower layers' gradients, 0.3 % with fp32 products).
+      // 3xTF32, like the conv forward: hs = hi + lo, W1^T = hi + lo (split at re-pack), three tensor-core products.
+      const i64 n = (i64)rows * h->aux_In;
+      LAUNCH(h, k_split_tf32, grid1(n), dim3(256), 0, Ly.hs, h->aux_hs_hi, h->aux_hs_lo, n);
+      gemm2(h, h->aux_hs_hi, h->aux_In, h->aux_w1T, h->aux_In, h->aux_In, h->aux_hs_lo, h->aux_In, h->aux_w1T, h->aux_In,
+            h->aux_In, h->aux_z1, h->aux_Pp, rows, c.aux_hidden, Wc + h->aux_b1, 0.f);
+      gemm(h, h->aux_hs_hi, h->aux_In, 1, h->aux_w1T_lo, 1, h->aux_In, h->aux_z1, h->aux_Pp, rows, c.aux_hidden, h->aux_In,
+           nullptr, 1.f);
+    } else {
+      gemm(h, Ly.hs, h->aux_In, 1, h->aux_w1T, 1, h->aux_In, h->aux_z1, h->aux_Pp, rows, c.aux_hidden, h->aux_In,
+           Wc + h->aux_b1, 0.f);
+    }
+    DropP dp = make_drop(seed, E2T_STREAM_AUX, train ? c.ff_dropout : 0.f);
+    if (c.conv_act != E2T_ACT_LINEAR || dp.thresh)
+      LAUNCH(h, k_act_dropout, grid1((i64)rows * c.aux_hidden), dim3(256), 0, h->aux_z1, (i64)rows, c.aux_hidden, h->aux_Pp,
+             c.conv_act, dp);
+    feat = h->aux_z1; ldf = h->aux_Pp; nf = c.aux_hidden;
+  }
+  // out = feat W2^T + b2 ; W2 canonical [F, nf] is already the K-major B operand
+  gemm(h, feat, ldf, 1, Wc + h->aux_w2, 1, nf, h->aux_out, h->aux_Fp, rows, c.aux_F, nf, Wc + h->aux_b2, 0.f);
+  AuxP p{};
+  p.out = h->aux_out; p.ld = h->aux_Fp; p.F = c.aux_F; p.tgt = h->aux_tgt; p.kind = c.aux_kind;
+  p.lens = h->d_lens; p.lens2 = h->d_lens2; p.B = B; p.T = T; p.W = W; p.rows = rows;
+  p.scale = h->pen_aux; p.loss_row = h->aux_loss_rows; p.cnt_row = h->aux_cnt_rows; p.with_grad = with_grad ? 1 : 0;
+  LAUNCH(h, k_aux_loss, dim3((unsigned)rows), dim3(32), 0, p);
+  LAUNCH(h, k_reduce_aux, dim3(1), dim3(256), 0, h->aux_loss_rows, h->aux_cnt_rows, rows, h->d_loss + 1, h->d_ntok + 1);
+  h->aux_ran = true;
+}
+
+// gradients of the head's parameters; its gradient wrt the layer outputs is ADDED to that layer's dhs
+void aux_backward(e2t_handle* h, int B, int T2, bool train, uint32_t seed) {
+  const e2t_config& c = h->cfg;
+  const float* Wc = h->Wc;
+  float* G = h->G;
+  const int rows = T2 * B, In = h->aux_In, F = c.aux_F, Ph = c.aux_hidden;
+  EncLayer& Ly = h->enc[c.aux_layer];
+  const float* dout = h->aux_out;
+  const float* feat = Ph > 0 ? h->aux_z1 : Ly.hs;
+  const int ldf = Ph > 0 ? h->aux_Pp : In, nf = Ph > 0 ? Ph : In;
+  // dW2 [F, nf] = dout^T feat ; db2
+  gemm(h, dout, 1, h->aux_Fp, feat, ldf, 1, G + h->aux_w2, nf, F, nf, rows, nullptr, 0.f);
+  batch_colsum(h, dout, rows, F, h->aux_Fp, G + h->aux_b2);
+  if (Ph > 0) {
+    // dz1 [rows, P] = dout W2 ; B(k = f, n = p) = W2[f*P + p]
+    gemm(h, dout, h->aux_Fp, 1, Wc + h->aux_w2, Ph, 1, h->aux_dz1, h->aux_Pp, rows, Ph, F, nullptr, 0.f);
+    DropP dp = make_drop(seed, E2T_STREAM_AUX, train ? c.ff_dropout : 0.f);
+    LAUNCH(h, k_act_dropout_bwd, grid1((i64)rows * Ph), dim3(256), 0, h->aux_dz1, h->aux_z1, (i64)rows, Ph, h->aux_Pp,
+           c.conv_act, dp);
+    // dW1 [In, P] = hs^T dz1 ; db1 ; dhs += dz1 W1^T with B(k = p, n = i) = W1[i*P + p]
+    gemm(h, Ly.hs, 1, In, h->aux_dz1, h->aux_Pp, 1, G + h->aux_w1, Ph, In, Ph, rows, nullptr, 0.f);
+    batch_colsum(h, h->aux_dz1, rows, Ph, h->aux_Pp, G + h->aux_b1);
+    gemm(h, h->aux_dz1, h->aux_Pp, 1, Wc + h->aux_w1, 1, Ph, Ly.dhs, In, rows, In, Ph, nullptr, 1.f);
+  } else {
+    // dhs += dout W2 ; B(k = f, n = i) = W2[f*In + i]
+    gemm(h, dout, h->aux_Fp, 1, Wc + h->aux_w2, In, 1, Ly.dhs, In, rows, In, F, nullptr, 1.f);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -820,9 +967,11 @@ void lstm_layer_wgrads(e2t_handle* h, const float* in, int ld_in, int In, int H,
   if (d_in) gemm(h, dz, 4 * H, 1, K, 1, 4 * H, d_in, ld_din, (int)rows, In, 4 * H, nullptr, beta_din);
 }
 
-void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, uint32_t seed) {
+// train = false: the forward pass ran without dropout (saliency), possibly on the EMA weights
+void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, uint32_t seed, bool train = true) {
   const e2t_config& c = h->cfg;
-  const float* P = h->P;
+  const float* P = h->Wc;
+  const bool rnn_drop = train && c.rnn_dropout > 0.f;
   float* G = h->G;
   const int C = c.subnet_C[subnet], W = c.subnet_W[subnet];
   const int T2 = (int)cdiv(T, W);
@@ -844,8 +993,11 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
     batch_colsum(h, h->at_dht, rows, c.Hd, c.Hd, G + h->at_bc);
     // dctx = dpre Wc[:, :Hd]
     gemm(h, h->at_dht, c.Hd, 1, h->at_combT, 1, c.Hd, h->at_dctx, c.Hd, (int)rows, c.Hd, c.Hd, nullptr, 0.f);
+    const bool bah = c.attention == E2T_ATTN_BAHDANAU;
     LAUNCH(h, k_attn_bwd_q, dim3((unsigned)rows), dim3(128), (size_t)T2 * sizeof(float), h->at_dctx, top.hs, h->d_lens2,
-           h->at_alpha, h->at_dscore, h->at_dq, B, B, T2, c.Hd, h->T2m);
+           h->at_alpha, h->at_dscore, h->at_dq, B, B, T2, c.Hd, h->T2m, bah ? h->at_kp : nullptr, bah ? P + h->at_v : nullptr,
+           h->at_q, h->at_dvrow);
+    if (bah) batch_colsum(h, h->at_dvrow, rows, c.Hd, c.Hd, G + h->at_v);
     // dWq [Hd, Hd] = dq^T hdec
     gemm(h, h->at_dq, 1, c.Hd, h->hdec, c.Hd, 1, G + h->at_wq, c.Hd, c.Hd, c.Hd, (int)rows, nullptr, 0.f);
     // dhdec = dpre Wc[:, Hd:] + dq Wq   (one pass)
@@ -862,7 +1014,7 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
   lstm_layer_wgrads(h, h->demb, h->Dp, c.D, c.Hd, P + h->dec_K, G + h->dec_K, G + h->dec_b, h->dgates, h->hdec, c.Hd, 0,
                     L, B, false, h->h0, h->ddemb, h->Dp, 0.f);
   // ---- decoder embedding
-  DropP dpe = make_drop(seed, E2T_STREAM_DEMB, c.ff_dropout);
+  DropP dpe = make_drop(seed, E2T_STREAM_DEMB, train ? c.ff_dropout : 0.f);
   LAUNCH(h, k_act_dropout_bwd, grid1(rows * c.D), dim3(256), 0, h->ddemb, h->demb, rows, c.D, h->Dp, c.emb_act, dpe);
   LAUNCH(h, k_embed_bwd, grid1(rows * c.D), dim3(256), 0, h->d_prev, h->ddemb, G + h->demb_w, rows, c.D, h->Dp);
   batch_colsum(h, h->ddemb, rows, c.D, h->Dp, G + h->demb_b);
@@ -874,18 +1026,27 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
     if (l == nl - 1) {
       E2T_CHECK(cudaMemsetAsync(Ly.dhs, 0, (size_t)n_out * sizeof(float), h->stream));
       LAUNCH(h, k_scatter_final, grid1((i64)B * 2 * Ly.H), dim3(256), 0, Ly.dhs, h->dh0, h->d_lens2, B, Ly.H);
-      if (attn)   // the attention's gradient wrt the encoder outputs joins the bridge's
+      if (attn) {   // the attention's gradient wrt the encoder outputs joins the bridge's
+        const bool bah = c.attention == E2T_ATTN_BAHDANAU;
         LAUNCH(h, k_attn_bwd_enc, dim3((unsigned)B), dim3(256), (size_t)2 * L * T2 * sizeof(float), h->at_dctx, h->at_q,
-               h->at_alpha, h->at_dscore, h->d_lens2, Ly.dhs, L, B, T2, c.Hd, h->T2m);
-    } else if (c.rnn_dropout > 0.f) {
+               h->at_alpha, h->at_dscore, h->d_lens2, Ly.dhs, L, B, T2, c.Hd, h->T2m, bah ? h->at_kp : nullptr,
+               bah ? P + h->at_v : nullptr, h->at_dkp);
+        if (bah) {
+          // dWk [Hd, Hd] = dkp^T enc ; enc gradient through the keys: dhs += dkp Wk (packed Wk^T is the K-major B operand)
+          gemm(h, h->at_dkp, 1, c.Hd, Ly.hs, c.Hd, 1, G + h->at_wk, c.Hd, c.Hd, c.Hd, T2 * B, nullptr, 0.f);
+          gemm(h, h->at_dkp, c.Hd, 1, h->at_keysT, 1, c.Hd, Ly.dhs, c.Hd, T2 * B, c.Hd, c.Hd, nullptr, 1.f);
+        }
+      }
+    } else if (rnn_drop) {
       DropP dp = make_drop(seed, E2T_STREAM_ENC0 + l, c.rnn_dropout);
       LAUNCH(h, k_dropout_bwd, grid1(n_out), dim3(256), 0, Ly.dhs, n_out, dp);
     }
+    if (h->aux_ran && l == c.aux_layer) aux_backward(h, B, T2, train, seed);
     const float* inp; int ld_in; float* d_in; int ld_din;
     if (l == 0) { inp = h->conv_out; ld_in = c.E; d_in = h->dconv; ld_din = c.E; }
     else {
       EncLayer& Lb = h->enc[l - 1];
-      inp = (c.rnn_dropout > 0.f) ? Lb.hd : Lb.hs; ld_in = 2 * Lb.H; d_in = Lb.dhs; ld_din = 2 * Lb.H;
+      inp = rnn_drop ? Lb.hd : Lb.hs; ld_in = 2 * Lb.H; d_in = Lb.dhs; ld_din = 2 * Lb.H;
     }
     const bool top = l == nl - 1;
     const bool rec_ok = use_rec(h, Ly, B, T2);
@@ -930,7 +1091,7 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
           rec_ok ? Ly.KP[1] : P + Ly.K[1], 4 * Ly.H, 4 * Ly.H, d_in, ld_din, (int)((i64)T2 * B), Ly.In, nullptr, 0.f);
   }
   // ---- temporal conv
-  DropP dpc = make_drop(seed, E2T_STREAM_CONV, c.ff_dropout);
+  DropP dpc = make_drop(seed, E2T_STREAM_CONV, train ? c.ff_dropout : 0.f);
   LAUNCH(h, k_act_dropout_bwd, grid1((i64)T2 * B * c.E), dim3(256), 0, h->dconv, h->conv_out, (i64)T2 * B, c.E, c.E,
          c.conv_act, dpc);
   gemm_conv(h, 2, in.x, h->d_lens, B, T, C, W, T2, h->dconv, c.E, 1, G + h->conv_w[subnet], c.E, c.E, nullptr, 0.f);
@@ -940,11 +1101,11 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
 
 void read_loss(e2t_handle* h, float* loss_sum, int32_t* ntok) {
   if (!loss_sum && !ntok) return;
-  float l = 0.f; int n = 0;
-  E2T_CHECK(cudaMemcpyAsync(&l, h->d_loss, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  float l[2] = {0.f, 0.f}; int n = 0;
+  E2T_CHECK(cudaMemcpyAsync(l, h->d_loss, (h->aux_ran ? 2 : 1) * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   E2T_CHECK(cudaMemcpyAsync(&n, h->d_ntok, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   E2T_CHECK(cudaStreamSynchronize(h->stream));
-  if (loss_sum) *loss_sum = l;
+  if (loss_sum) *loss_sum = l[0] + (h->aux_ran ? l[1] : 0.f);
   if (ntok) *ntok = n;
 }
 
@@ -968,8 +1129,9 @@ void decode_step(e2t_handle* h, int rows, const int* prev, const float* h_in, co
     const EncLayer& top = h->enc.back();
     const int T2 = h->last_T2;
     gemm(h, h_out, c.Hd, 1, Wc + h->at_wq, 1, c.Hd, h->g_q, c.Hd, rows, c.Hd, c.Hd, nullptr, 0.f);
+    const bool bah = c.attention == E2T_ATTN_BAHDANAU;
     LAUNCH(h, k_attn_fwd, dim3((unsigned)rows), dim3(128), (size_t)T2 * sizeof(float), h->g_q, top.hs, h->d_lens2,
-           h->g_alpha, h->g_ctx, rows, B, beam, T2, c.Hd, h->T2m);
+           h->g_alpha, h->g_ctx, rows, B, beam, T2, c.Hd, h->T2m, bah ? h->at_kp : nullptr, bah ? Wc + h->at_v : nullptr);
     gemm2(h, h->g_ctx, c.Hd, Wc + h->at_wc, 2 * c.Hd, c.Hd, h_out, c.Hd, Wc + h->at_wc + c.Hd, 2 * c.Hd, c.Hd, h->g_ht, c.Hd,
           rows, c.Hd, Wc + h->at_bc, 0.f);
     LAUNCH(h, k_tanh_fwd, grid1((i64)rows * c.Hd), dim3(256), 0, h->g_ht, (i64)rows * c.Hd);
@@ -1127,6 +1289,7 @@ extern "C" int e2t_train_step_grads(e2t_handle* h, int subnet, const float* x, c
   E2T_REQUIRE(in.y != nullptr, "training needs targets");
   use_weights(h, false);
   encoder_forward(h, subnet, in, B, T, true, dropout_seed);
+  aux_forward(h, subnet, B, T, true, dropout_seed, true);
   decoder_forward(h, in, B, L, true, dropout_seed, true);
   backward(h, subnet, in, B, T, L, dropout_seed);
   E2T_CHECK(cudaGetLastError());
@@ -1208,10 +1371,82 @@ extern "C" int e2t_eval_loss(e2t_handle* h, int subnet, const float* x, const in
   Inputs in = stage(h, subnet, x, lens, y, loc, B, T, L);
   use_weights(h, use_ema != 0);
   encoder_forward(h, subnet, in, B, T, false, 0);
+  aux_forward(h, subnet, B, T, false, 0, false);
   decoder_forward(h, in, B, L, false, 0, false);
   E2T_CHECK(cudaGetLastError());
   release_slot(h, loc);
   read_loss(h, loss_sum, ntok);
+  API_END
+}
+
+extern "C" int e2t_set_encoder_targets(e2t_handle* h, const void* targets, int loc, int B, int T) {
+  API_BEGIN NEED_H;
+  E2T_REQUIRE(h->aux, "this model has no encoder-targets head (e2t_config.aux_F == 0)");
+  E2T_REQUIRE(targets != nullptr, "targets is NULL");
+  E2T_REQUIRE(B >= 1 && B <= h->Bm && T >= 1 && T <= h->Tm, "B / T exceed the capacities");
+  E2T_REQUIRE(loc == E2T_HOST || loc == E2T_DEVICE, "loc must be E2T_HOST or E2T_DEVICE");
+  const size_t per_frame = h->cfg.aux_kind == E2T_AUX_GAUSSIAN ? (size_t)h->cfg.aux_F : 1;
+  E2T_CHECK(cudaMemcpyAsync(h->aux_tgt, targets, (size_t)B * T * per_frame * 4,
+                            loc == E2T_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+  h->aux_tgt_B = B; h->aux_tgt_T = T; h->aux_ready = true;
+  API_END
+}
+
+extern "C" int e2t_last_losses(e2t_handle* h, float* decoder_sum, int32_t* ntok, float* aux_sum, int32_t* aux_frames) {
+  API_BEGIN NEED_H;
+  float l[2] = {0.f, 0.f}; int n[2] = {0, 0};
+  E2T_CHECK(cudaMemcpyAsync(l, h->d_loss, 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  E2T_CHECK(cudaMemcpyAsync(n, h->d_ntok, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  E2T_CHECK(cudaStreamSynchronize(h->stream));
+  if (decoder_sum) *decoder_sum = l[0];
+  if (ntok) *ntok = n[0];
+  if (aux_sum) *aux_sum = h->aux_ran ? l[1] : 0.f;
+  if (aux_frames) *aux_frames = h->aux_ran ? n[1] : 0;
+  API_END
+}
+
+// A13: restore_and_get_saliencies (trainers.py:703-732)
+extern "C" int e2t_input_saliency(e2t_handle* h, int subnet, const float* x, const int32_t* lens, const int32_t* y, int loc,
+                                  int B, int T, int L, int use_ema, float decoder_penalty, float aux_penalty, float* dx,
+                                  float* sq_norms) {
+  API_BEGIN NEED_H;
+  E2T_REQUIRE(y != nullptr && L >= 1, "saliency needs decoder targets");
+  E2T_REQUIRE(loc == E2T_HOST || loc == E2T_DEVICE, "loc must be E2T_HOST or E2T_DEVICE");
+  const e2t_config& c = h->cfg;
+  Inputs in = stage(h, subnet, x, lens, y, loc, B, T, L);
+  const int C = c.subnet_C[subnet], W = c.subnet_W[subnet], T2 = (int)cdiv(T, W), WC = W * C;
+  if (!h->sal_tmp) {
+    int maxWC = 0;
+    for (int s = 0; s < c.n_subnets; ++s) maxWC = std::max(maxWC, c.subnet_W[s] * c.subnet_C[s]);
+    h->sal_tmp = h->alloc<float>((i64)h->T2m * h->Bm * maxWC);
+    h->sal_dx = h->alloc<float>((i64)h->Bm * h->Tm * h->Cmax);
+    h->sal_sq = h->alloc<float>((i64)h->Bm * h->Cmax);
+  }
+  use_weights(h, use_ema != 0);
+  const float pd = h->pen_dec, pa = h->pen_aux;
+  h->pen_dec = decoder_penalty; h->pen_aux = aux_penalty;
+  try {
+    encoder_forward(h, subnet, in, B, T, false, 0);
+    aux_forward(h, subnet, B, T, false, 0, true);
+    decoder_forward(h, in, B, L, false, 0, true);
+    backward(h, subnet, in, B, T, L, 0, false);
+  } catch (...) { h->pen_dec = pd; h->pen_aux = pa; throw; }
+  h->pen_dec = pd; h->pen_aux = pa;
+  // gradient of every conv window: tmp [T2*B, W*C] = d(pre-activation) [T2*B, E] Wc^T ; canonical Wc [W*C, E] is the
+  // K-major B operand
+  gemm(h, h->dconv, c.E, 1, h->Wc + h->conv_w[subnet], 1, c.E, h->sal_tmp, WC, T2 * B, WC, c.E, nullptr, 0.f);
+  float* dxd = (loc == E2T_DEVICE && dx) ? dx : h->sal_dx;
+  LAUNCH(h, k_saliency_scatter, grid1((i64)B * T * C), dim3(256), 0, h->sal_tmp, (i64)WC, h->d_lens, dxd, B, T, C, W);
+  if (sq_norms) {
+    float* sqd = loc == E2T_DEVICE ? sq_norms : h->sal_sq;
+    LAUNCH(h, k_saliency_norms, dim3((unsigned)cdiv(C, 128), (unsigned)B), dim3(128), 0, dxd, sqd, B, T, C);
+  }
+  E2T_CHECK(cudaGetLastError());
+  if (loc == E2T_HOST) {
+    if (dx) E2T_CHECK(cudaMemcpyAsync(dx, h->sal_dx, (size_t)B * T * C * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (sq_norms) E2T_CHECK(cudaMemcpyAsync(sq_norms, h->sal_sq, (size_t)B * C * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    E2T_CHECK(cudaStreamSynchronize(h->stream));
+  }
   API_END
 }
 
@@ -1352,6 +1587,16 @@ extern "C" int e2t_get_activation(e2t_handle* h, const char* name, void* host_ou
   else if (s == "conv_out") { src = h->conv_out; n = T2 * B * c.E; }
   else if (s == "final_h") { src = h->h0; n = B * c.Hd; }
   else if (s == "final_c") { src = h->c0; n = B * c.Hd; }
+  else if (s == "aux_out") {
+    E2T_REQUIRE(h->aux, "no encoder-targets head");
+    n = T2 * B * c.aux_F;
+    E2T_REQUIRE(n <= n_cap, "host buffer too small");
+    E2T_CHECK(cudaStreamSynchronize(h->stream));
+    for (i64 r = 0; r < T2 * B; ++r)
+      E2T_CHECK(cudaMemcpy((float*)host_out + r * c.aux_F, h->aux_out + r * h->aux_Fp, (size_t)c.aux_F * 4, cudaMemcpyDeviceToHost));
+    if (n_out) *n_out = n;
+    return 0;
+  }
   else if (s == "logits") {
     // stored with leading dim Vp: copy row by row
     n = L * B * c.V;

@@ -301,10 +301,13 @@ __global__ void k_scatter_final(float* dhs, const float* dh0, const int* lens2, 
 // One block per decoder row r (time-major rows r = k*R + j of q / ctx / alpha; encoder batch index b = j / bdiv, so that the
 // beam rows of one utterance share its encoder outputs).  enc [T2, Benc, F] time-major.  Scores live in shared memory
 // (T2 floats); each thread keeps its F/blockDim query elements in registers; nothing but alpha and ctx goes to HBM.
+// Bahdanau ("additive") variant, kp != NULL: score[s] = sum_a v[a] tanh(q[a] + kp[s,b,a]) with kp = enc Wk^T [T2, Benc, F]
+// computed once per batch (GEMM, outside) and q = h Wq^T; softmax and context are the same.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_attn_fwd(const float* __restrict__ q, const float* __restrict__ enc, const int* __restrict__ lens2, float* alpha,
-           float* ctx, int R, int Benc, int bdiv, int T2, int F, int ld_alpha) {
+           float* ctx, int R, int Benc, int bdiv, int T2, int F, int ld_alpha, const float* __restrict__ kp,
+           const float* __restrict__ v) {
   E2T_DYN_SMEM(float, sc);                 // [T2] scores -> probabilities
   __shared__ float red[32];
   const int r = blockIdx.x;
@@ -313,9 +316,10 @@ k_attn_fwd(const float* __restrict__ q, const float* __restrict__ enc, const int
   const int len = min(lens2[b], T2);
   const float* qr = q + (i64)r * F;
   for (int s = 0; s < len; ++s) {
-    const float* er = enc + ((i64)s * Benc + b) * F;
+    const float* er = (kp ? kp : enc) + ((i64)s * Benc + b) * F;
     float a = 0.f;
-    for (int u = threadIdx.x; u < F; u += blockDim.x) a = fmaf(qr[u], er[u], a);
+    if (kp) { for (int u = threadIdx.x; u < F; u += blockDim.x) a = fmaf(v[u], tanhf(qr[u] + er[u]), a); }
+    else { for (int u = threadIdx.x; u < F; u += blockDim.x) a = fmaf(qr[u], er[u], a); }
     a = block_sum(a, red);
     if (threadIdx.x == 0) sc[s] = a;
   }
@@ -342,9 +346,12 @@ k_attn_fwd(const float* __restrict__ q, const float* __restrict__ enc, const int
 }
 // backward, phase 1 (one block per decoder row): dalpha[s] = dctx . enc[s] ; dscore = alpha * (dalpha - sum alpha dalpha)
 // (written over alpha's companion buffer dscore) ; dq[u] = sum_s dscore[s] enc[s][u]
+// Bahdanau (kp != NULL; q holds the forward queries): th = tanh(q[a] + kp[s,b,a]) is recomputed;
+// dq[a] = sum_s dscore[s] v[a] (1 - th^2) and dvrow[r, a] = sum_s dscore[s] th (column-summed over r afterwards, fixed order).
 __global__ void __launch_bounds__(128)
 k_attn_bwd_q(const float* __restrict__ dctx, const float* __restrict__ enc, const int* __restrict__ lens2,
-             const float* __restrict__ alpha, float* dscore, float* dq, int R, int Benc, int T2, int F, int ld_alpha) {
+             const float* __restrict__ alpha, float* dscore, float* dq, int R, int Benc, int T2, int F, int ld_alpha,
+             const float* __restrict__ kp, const float* __restrict__ v, const float* __restrict__ q, float* dvrow) {
   E2T_DYN_SMEM(float, sc);                 // [T2] dalpha -> dscore
   __shared__ float red[32];
   const int r = blockIdx.x;
@@ -372,16 +379,30 @@ k_attn_bwd_q(const float* __restrict__ dctx, const float* __restrict__ enc, cons
   __syncthreads();
   for (int u = threadIdx.x; u < F; u += blockDim.x) {
     float a = 0.f;
-    for (int s = 0; s < len; ++s) a = fmaf(sc[s], enc[((i64)s * Benc + b) * F + u], a);
+    if (kp) {
+      const float qu = q[(i64)r * F + u], vu = v[u];
+      float dv = 0.f;
+      for (int s = 0; s < len; ++s) {
+        const float th = tanhf(qu + kp[((i64)s * Benc + b) * F + u]);
+        a = fmaf(sc[s] * vu, 1.f - th * th, a);
+        dv = fmaf(sc[s], th, dv);
+      }
+      dvrow[(i64)r * F + u] = dv;
+    } else {
+      for (int s = 0; s < len; ++s) a = fmaf(sc[s], enc[((i64)s * Benc + b) * F + u], a);
+    }
     dq[(i64)r * F + u] = a;
   }
 }
 // backward, phase 2 (one block per utterance b; thread = feature u): denc[s,b,u] += sum_k alpha[k,b,s] dctx[k,b,u]
 // + dscore[k,b,s] q[k,b,u], the L decoder steps summed in order (deterministic, no atomics).
+// Bahdanau (kp != NULL): the score reaches the encoder through the keys instead:
+// dkp[s,b,a] = sum_k dscore[k,b,s] v[a] (1 - tanh^2(q[k,b,a] + kp[s,b,a])) (rows s >= len' get 0); dWk and the encoder
+// gradient through Wk follow as two GEMMs outside.
 __global__ void __launch_bounds__(256)
 k_attn_bwd_enc(const float* __restrict__ dctx, const float* __restrict__ q, const float* __restrict__ alpha,
                const float* __restrict__ dscore, const int* __restrict__ lens2, float* denc, int L, int B, int T2, int F,
-               int ld_alpha) {
+               int ld_alpha, const float* __restrict__ kp, const float* __restrict__ v, float* dkp) {
   E2T_DYN_SMEM(float, sm);                 // [2][L][T2]: alpha, dscore of this utterance
   const int b = blockIdx.x;
   const int len = min(lens2[b], T2);
@@ -392,14 +413,24 @@ k_attn_bwd_enc(const float* __restrict__ dctx, const float* __restrict__ q, cons
   }
   __syncthreads();
   for (int u = threadIdx.x; u < F; u += blockDim.x) {
-    for (int s = 0; s < len; ++s) {
-      float a = 0.f;
+    const float vu = kp ? v[u] : 0.f;
+    for (int s = 0; s < T2; ++s) {
+      const i64 e = ((i64)s * B + b) * F + u;
+      if (s >= len) { if (kp) dkp[e] = 0.f; continue; }
+      float a = 0.f, dk = 0.f;
+      const float kpv = kp ? kp[e] : 0.f;
       for (int k = 0; k < L; ++k) {
         const i64 row = ((i64)k * B + b) * F + u;
         a = fmaf(sm[k * T2 + s], dctx[row], a);
-        a = fmaf(sm[L * T2 + k * T2 + s], q[row], a);
+        if (kp) {
+          const float th = tanhf(q[row] + kpv);
+          dk = fmaf(sm[L * T2 + k * T2 + s] * vu, 1.f - th * th, dk);
+        } else {
+          a = fmaf(sm[L * T2 + k * T2 + s], q[row], a);
+        }
       }
-      denc[((i64)s * B + b) * F + u] += a;
+      denc[e] += a;
+      if (kp) dkp[e] = dk;
     }
   }
 }
@@ -492,6 +523,119 @@ __global__ void __launch_bounds__(256) k_reduce_loss(const float* loss_row, cons
   s = block_sum(s, red);
   n = block_sum(n, red);
   if (threadIdx.x == 0) { *loss_out = s; *ntok_out = (int)(n + 0.5f); }
+}
+
+// hi = x with the 13 low mantissa bits cleared (exactly representable in TF32), lo = x - hi: operands of a 3xTF32 product
+// (A_hi B_hi + A_lo B_hi + A_hi B_lo), which is fp32-accurate on the tf32 tensor cores.
+__global__ void k_split_tf32(const float* __restrict__ in, float* hi, float* lo, i64 n) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = in[i];
+  const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  hi[i] = h;
+  lo[i] = x - h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A6: loss of the encoder-targets head, one warp per row r = t2*B + b of out [rows, F] (leading dim ld).
+// The target of row (t2, b) is frame len_b - 1 - t2*W of the caller's [B,T,...] array: reversed within the length,
+// then every W-th frame (trainers.py:791-795).  Rows with t2 >= lens2[b] (and, categorical, pad-class rows) are masked.
+//   kind 0 (gaussian):    loss = 0.5 * sum_f (out - tgt)^2 ;  d out = out - tgt
+//   kind 1 (categorical): loss = lse(out) - out[cls]       ;  d out = softmax - onehot
+// loss_row[r] = scale * loss, cnt_row[r] = 1 if unmasked; with_grad: out <- scale * d out (0 on masked rows).
+// ------------------------------------------------------------------------------------------------
+struct AuxP {
+  float* out; int ld, F;
+  const void* tgt; int kind;
+  const int* lens; const int* lens2;
+  int B, T, W, rows;
+  float scale;
+  float* loss_row; int* cnt_row;
+  int with_grad;
+};
+__global__ void __launch_bounds__(32) k_aux_loss(AuxP p) {
+  const int r = blockIdx.x, lane = threadIdx.x;
+  const int t2 = r / p.B, b = r - t2 * p.B;
+  float* row = p.out + (i64)r * p.ld;
+  bool valid = t2 < p.lens2[b];
+  const int frame = p.lens[b] - 1 - t2 * p.W;
+  int cls = 0;
+  if (valid && p.kind == 1) {
+    cls = static_cast<const int*>(p.tgt)[(i64)b * p.T + frame];
+    valid = cls > 0 && cls < p.F;
+  }
+  if (!valid) {
+    if (p.with_grad)
+      for (int f = lane; f < p.F; f += 32) row[f] = 0.f;
+    if (lane == 0) { p.loss_row[r] = 0.f; p.cnt_row[r] = 0; }
+    return;
+  }
+  float loss;
+  if (p.kind == 0) {
+    const float* tg = static_cast<const float*>(p.tgt) + ((i64)b * p.T + frame) * p.F;
+    float s = 0.f;
+    for (int f = lane; f < p.F; f += 32) {
+      const float e = row[f] - tg[f];
+      s += e * e;
+      if (p.with_grad) row[f] = p.scale * e;
+    }
+    loss = 0.5f * warp_sum(s);
+  } else {
+    float mx = -3.0e38f;
+    for (int f = lane; f < p.F; f += 32) mx = fmaxf(mx, row[f]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int f = lane; f < p.F; f += 32) s += expf(row[f] - mx);
+    s = warp_sum(s);
+    const float lse = mx + logf(s);
+    loss = lse - row[cls];
+    if (p.with_grad) {
+      __syncwarp();
+      for (int f = lane; f < p.F; f += 32) {
+        float g = expf(row[f] - lse);
+        if (f == cls) g -= 1.f;
+        row[f] = p.scale * g;
+      }
+    }
+  }
+  if (lane == 0) { p.loss_row[r] = p.scale * loss; p.cnt_row[r] = 1; }
+}
+// deterministic single-block reduction of the per-row head losses and the unmasked-frame count
+__global__ void __launch_bounds__(256) k_reduce_aux(const float* loss_row, const int* cnt_row, int rows, float* loss_out,
+                                                    int* cnt_out) {
+  __shared__ float red[32];
+  float s = 0.f, n = 0.f;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) { s += loss_row[i]; n += (float)cnt_row[i]; }
+  s = block_sum(s, red);
+  n = block_sum(n, red);
+  if (threadIdx.x == 0) { *loss_out = s; *cnt_out = (int)(n + 0.5f); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// A13: input saliency.  tmp [T2*B, W*C] = d(conv pre-activation) Wc^T holds the gradient of every conv window; frame t of
+// utterance b is window position s = len_b - 1 - t (the reversal of A3), i.e. row (s / W)*B + b, column (s % W)*C + c.
+// tf.reverse_sequence leaves the padding where it is (s = t for t >= len_b), so the zero frames that complete the last
+// window still receive a gradient; windows past len' have none (their outputs are masked by the recurrence).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_saliency_scatter(const float* __restrict__ tmp, i64 ldt, const int* __restrict__ lens, float* dx, int B, int T,
+                                   int C, int W) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (i64)B * T * C) return;
+  const int c = (int)(i % C);
+  const i64 bt = i / C;
+  const int t = (int)(bt % T), b = (int)(bt / T);
+  const int len = lens[b];
+  const int s = t < len ? len - 1 - t : t, t2 = s / W, w = s - t2 * W;
+  dx[i] = t2 * W < len ? tmp[((i64)t2 * B + b) * ldt + (i64)w * C + c] : 0.f;
+}
+// sq[b, c] = sum_t dx[b, t, c]^2 (fixed order)
+__global__ void k_saliency_norms(const float* __restrict__ dx, float* sq, int B, int T, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (c >= C) return;
+  const float* p = dx + (i64)b * T * C + c;
+  float s = 0.f;
+  for (int t = 0; t < T; ++t) { const float v = p[(i64)t * C]; s += v * v; }
+  sq[(i64)b * C + c] = s;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -42,6 +42,12 @@ class EngineConfig:
     gemm_backend: str = "auto"
     device: int = 0
     attention: str = "none"    # "luong": optional A7 module (not in the reference model)
+    # A6 encoder-targets head ('encoder_1_targets', /root/reference/ecog2txt/trainers.py:798-799; yaml:54,68-69,81); aux_F = 0: none
+    aux_layer: int = 1
+    aux_hidden: int = 0
+    aux_F: int = 0
+    aux_kind: str = "gaussian"
+    aux_penalty: float = 1.0
 
     def to_c(self) -> L.E2TConfig:
         c = L.E2TConfig()
@@ -65,6 +71,8 @@ class EngineConfig:
         c.ema_decay, c.penalty_scale = self.ema_decay, self.penalty_scale
         c.gemm_backend, c.device = L.GEMM[self.gemm_backend], self.device
         c.attention = L.ATTN[self.attention]
+        c.aux_layer, c.aux_hidden, c.aux_F = int(self.aux_layer), int(self.aux_hidden), int(self.aux_F)
+        c.aux_kind, c.aux_penalty = L.AUX_KIND[self.aux_kind], float(self.aux_penalty)
         return c
 
 
@@ -229,6 +237,37 @@ class Engine:
             return float(loss.value), int(ntok.value)
         self._ck(self._lib.e2t_train_step_grads(self._h, subnet, None, None, None, loc, B, T, Lk, seed & 0xFFFFFFFF, None, None))
         return None
+
+    def set_encoder_targets(self, targets):
+        """A6: encoder targets of the next train_step_grads / eval_loss / input_saliency call: float32 [B,T,aux_F]
+        (gaussian) or int32 [B,T] (categorical), host (numpy) or device (torch.cuda)."""
+        p, loc = _ptr(targets)
+        want = np.float32 if self.cfg.aux_kind == "gaussian" else np.int32
+        if isinstance(targets, np.ndarray) and (targets.dtype != want or not targets.flags.c_contiguous):
+            raise TypeError(f"encoder targets must be C-contiguous {np.dtype(want).name}")
+        self._ck(self._lib.e2t_set_encoder_targets(self._h, p, loc, int(targets.shape[0]), int(targets.shape[1])))
+
+    def last_losses(self):
+        """(decoder loss sum, ntok, encoder-targets loss sum, unmasked frames) of the most recent step."""
+        ld, la, nt, nf = C.c_float(), C.c_float(), C.c_int32(), C.c_int32()
+        self._ck(self._lib.e2t_last_losses(self._h, C.byref(ld), C.byref(nt), C.byref(la), C.byref(nf)))
+        return float(ld.value), int(nt.value), float(la.value), int(nf.value)
+
+    def input_saliency(self, x, lens, y, subnet: int = 0, use_ema: bool = False, decoder_penalty: Optional[float] = None,
+                       aux_penalty: Optional[float] = None, want_dx: bool = True, want_norms: bool = True):
+        """A13: d(loss)/d(encoder_inputs) [B,T,C] and its per-electrode squared norms over time [B,C] (host inputs only)."""
+        if not isinstance(x, np.ndarray):
+            raise TypeError("input_saliency takes host (numpy) arrays")
+        px, pl, py, loc, B, T = self._inputs(x, lens, y)
+        Cc = int(x.shape[2])
+        dx = np.empty((B, T, Cc), np.float32) if want_dx else None
+        sq = np.empty((B, Cc), np.float32) if want_norms else None
+        pd = self.cfg.penalty_scale if decoder_penalty is None else decoder_penalty
+        pa = self.cfg.aux_penalty if aux_penalty is None else aux_penalty
+        self._ck(self._lib.e2t_input_saliency(self._h, subnet, px, pl, py, loc, B, T, int(y.shape[1]), int(use_ema), pd, pa,
+                                              dx.ctypes.data_as(C.c_void_p) if want_dx else None,
+                                              sq.ctypes.data_as(C.c_void_p) if want_norms else None))
+        return dx, sq
 
     def adam_ema_step(self, grad_scale: float, subnet: int = -1):
         self._ck(self._lib.e2t_adam_ema_step(self._h, subnet, float(grad_scale)))

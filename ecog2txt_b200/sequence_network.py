@@ -7,6 +7,7 @@ the reference's call sites:
 * ``fit``                      trainers.py:309-318,341-367 (train_vars_scope / reuse_vars_scope / _restore_epoch)
 * ``restore_and_assess``       trainers.py:379-380 ; plotters.py:631-636
 * ``get_weights_as_numpy_array`` trainers.py:699-700,750-751
+* ``restore_and_get_saliencies`` trainers.py:722-725
 * attributes                   checkpoint_path, N_epochs, layer_sizes, TEMPORALLY_CONVOLVE, EMA_decay, FF_dropout,
                                RNN_dropout, assessment_epoch_interval, beam_width, temperature
 
@@ -91,6 +92,22 @@ class SequenceNetwork:
         )
         if ls.get('decoder_projection'):
             raise NotImplementedError("hidden decoder_projection layers are not built (empty in the shipped manifests)")
+        # A6: an 'encoder_<n>_targets' stream puts an FF head on encoder layer n (trainers.py:791-799; yaml:54,68-69)
+        self._aux_key = None
+        for key, man in first.items():
+            m = re.fullmatch(r'encoder_(\d+)_targets', key)
+            if m:
+                if self._aux_key is not None:
+                    raise NotImplementedError("one encoder-targets stream per model")
+                n = int(m.group(1))
+                hidden = list(ls.get(f'encoder_{n}_projection', []) or [])
+                if len(hidden) > 1:
+                    raise NotImplementedError("at most one hidden layer in encoder_<n>_projection")
+                categorical = str(man.distribution).lower() == 'categorical'
+                geo.update(aux_layer=n, aux_hidden=int(hidden[0]) if hidden else 0, aux_F=int(man.num_features),
+                           aux_kind='categorical' if categorical else 'gaussian', aux_penalty=float(man.penalty_scale))
+                self._aux_key = key
+        geo['penalty_scale'] = float(first['decoder_targets'].penalty_scale)
         return geo, flist
 
     def _get_engine(self, subnets_params, max_T, max_L) -> Engine:
@@ -115,10 +132,14 @@ class SequenceNetwork:
     # -- data ----------------------------------------------------------------------------------
     @staticmethod
     def _load_partition(subject, partition):
-        """[(x [T,C] fp32, y [L] int32)] for every trial of the partition's blocks (trainers.py:891-901)."""
-        mans = {k: subject.data_manifests[k] for k in ('encoder_inputs', 'decoder_targets')}
+        """[(x [T,C] fp32, y [L] int32, encoder targets or None)] for every trial of the partition's blocks
+        (trainers.py:891-901)."""
+        keys = ['encoder_inputs', 'decoder_targets'] + [k for k in subject.data_manifests if re.fullmatch(r'encoder_\d+_targets', k)]
+        mans = {k: subject.data_manifests[k] for k in keys}
         paths = [subject.tf_record_partial_path.format(b) for b in sorted(subject.block_ids[partition])]
-        return [(ex['encoder_inputs'], ex['decoder_targets']) for ex in tfrecord.read_examples(paths, mans)]
+        aux = keys[2] if len(keys) > 2 else None
+        return [(ex['encoder_inputs'], ex['decoder_targets'], ex[aux] if aux else None)
+                for ex in tfrecord.read_examples(paths, mans)]
 
     @staticmethod
     def _batch(examples, idx, T_pad, L_pad, pad_id):
@@ -129,6 +150,20 @@ class SequenceNetwork:
             y[r, :len(t)] = t
         return x, y
 
+    @staticmethod
+    def _aux_batch(examples, idx, T_pad):
+        """Encoder targets of a minibatch: fp32 [B,T,F] (zero padded) or int32 [B,T] class indices (pad index 0)."""
+        a0 = examples[idx[0]][2]
+        if a0 is None:
+            return None
+        if a0.dtype == np.float32 or a0.dtype == np.float64:
+            return tfrecord.pad_batch_f32([np.asarray(examples[i][2], np.float32)[:T_pad] for i in idx], T_pad)
+        out = np.zeros((len(idx), T_pad), np.int32)
+        for r, i in enumerate(idx):
+            t = np.asarray(examples[i][2]).reshape(-1)[:T_pad]
+            out[r, :len(t)] = t
+        return out
+
     # -- fit -----------------------------------------------------------------------------------
     def fit(self, subnets_params, train_vars_scope='seq2seq', reuse_vars_scope=None, _restore_epoch=None):
         """Train N_epochs on the subjects jointly (one subject per minibatch, App. D item 11); every
@@ -137,8 +172,8 @@ class SequenceNetwork:
         import torch.distributed as dist
         rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
         data = {s.subnet_id: {p: self._load_partition(s, p) for p in ('training', 'validation')} for s in subnets_params}
-        max_T = max(x.shape[0] for d in data.values() for part in d.values() for x, _ in part)
-        max_L = max(len(y) for d in data.values() for part in d.values() for _, y in part)
+        max_T = max(e[0].shape[0] for d in data.values() for part in d.values() for e in part)
+        max_L = max(len(e[1]) for d in data.values() for part in d.values() for e in part)
         eng = self._get_engine(subnets_params, max_T, max_L)
         pad_id = eng.cfg.pad_id
         start_epoch = 0
@@ -174,7 +209,10 @@ class SequenceNetwork:
 
             def host_batch(k):
                 si, ids = shards[k]
-                return self._batch(data[subnets_params[si].subnet_id]['training'], ids, max_T, max_L, pad_id) if len(ids) else None
+                if not len(ids):
+                    return None
+                ex = data[subnets_params[si].subnet_id]['training']
+                return self._batch(ex, ids, max_T, max_L, pad_id) + (self._aux_batch(ex, ids, max_T),)
 
             nxt = host_batch(0) if shards else None
             if pipelined and nxt is not None:
@@ -185,6 +223,8 @@ class SequenceNetwork:
                 if pipelined and nxt is not None:
                     eng.stage_inputs((k + 1) & 1, nxt[0], None, nxt[1], subnet=shards[k + 1][0])
                 if cur is not None:
+                    if cur[2] is not None:   # A6: encoder targets of this step (copied on the compute stream)
+                        eng.set_encoder_targets(cur[2])
                     if pipelined:
                         loss, ntok = eng.train_step_grads_staged(k & 1, seed=step)
                     else:
@@ -247,11 +287,43 @@ class SequenceNetwork:
 
     def restore_and_assess(self, subnets_params, restore_epoch, WRITE=False, data_partitions=('training', 'validation')):
         data = {s.subnet_id: {p: self._load_partition(s, p) for p in data_partitions} for s in subnets_params}
-        max_T = max(x.shape[0] for d in data.values() for part in d.values() for x, _ in part)
-        max_L = max(len(y) for d in data.values() for part in d.values() for _, y in part)
+        max_T = max(e[0].shape[0] for d in data.values() for part in d.values() for e in part)
+        max_L = max(len(e[1]) for d in data.values() for part in d.values() for e in part)
         eng = self._get_engine(subnets_params, max_T, max_L)
         prm.load_checkpoint(eng, self.checkpoint_path, restore_epoch, reuse_vars_scope='seq2seq')
         return {p: self._assess(eng, subnets_params, data, p, max_T, max_L) for p in data_partitions}
+
+    def restore_and_get_saliencies(self, subnets_params, restore_epoch, data_partition='validation', assessment_type='norms'):
+        """d(loss)/d(encoder_inputs) of the last subject's `data_partition` trials with the EMA weights of checkpoint
+        `restore_epoch` (trainers.py:722-725).  The penalties in force are the manifests' `penalty_scale`s: the caller
+        (MultiSubjectTrainer.get_saliencies, trainers.py:703-732) zeroes all but the one under study.
+        assessment_type 'norms': [C] = mean over trials of the per-electrode L2 norm over time of the input gradient;
+        'sequences': list of [T_i, C] gradients, one per trial [CHOICE: the upstream definition is not in the tree]."""
+        if assessment_type not in ('norms', 'sequences'):
+            raise ValueError("assessment_type must be 'norms' or 'sequences'")
+        s = subnets_params[-1]
+        si = len(subnets_params) - 1
+        examples = self._load_partition(s, data_partition)
+        max_T = max(e[0].shape[0] for e in examples)
+        max_L = max(len(e[1]) for e in examples)
+        eng = self._get_engine(subnets_params, max_T, max_L)
+        prm.load_checkpoint(eng, self.checkpoint_path, restore_epoch, reuse_vars_scope='seq2seq')
+        mans = s.data_manifests
+        pd = float(mans['decoder_targets'].penalty_scale)
+        pa = float(mans[self._aux_key].penalty_scale) if self._aux_key else 0.0
+        norms, seqs = [], []
+        for i in range(0, len(examples), self.N_cases):
+            idx = np.arange(i, min(i + self.N_cases, len(examples)))
+            x, y = self._batch(examples, idx, max_T, max_L, eng.cfg.pad_id)
+            aux = self._aux_batch(examples, idx, max_T)
+            if aux is not None:
+                eng.set_encoder_targets(aux)
+            dx, sq = eng.input_saliency(x, None, y, subnet=si, use_ema=float(self.EMA_decay) > 0, decoder_penalty=pd,
+                                        aux_penalty=pa, want_dx=assessment_type == 'sequences')
+            norms.append(np.sqrt(sq))
+            if dx is not None:
+                seqs += [dx[r, :examples[j][0].shape[0]].copy() for r, j in enumerate(idx)]
+        return np.concatenate(norms).mean(0) if assessment_type == 'norms' else seqs
 
     def get_weights_as_numpy_array(self, full_var_name, restore_epoch):
         """The stored variable (or its `/ExponentialMovingAverage` shadow) from checkpoint `restore_epoch`."""

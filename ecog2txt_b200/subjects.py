@@ -115,19 +115,36 @@ class SyntheticDataGenerator:
     sampling_rate = 200          # mochastar_word_sequence.yaml:84
 
     def __init__(self, corpus: SyntheticCorpus, tf_record_partial_path: str, utterances_per_block: int = 50,
-                 seed: int = 0):
+                 seed: int = 0, audio_features: int = 0, n_phonemes: int = 0):
         self.corpus = corpus
         self.tf_record_partial_path = tf_record_partial_path
         self.utterances_per_block = utterances_per_block
         self.seed = seed
         self.num_ECoG_channels = corpus.C
+        # optional frame-rate streams for the encoder-targets head (canonical keys audio_sequence / phoneme_sequence,
+        # data_generators.py:515-530): fixed random read-outs of the ECoG frame, so that the head is learnable
+        self.audio_features, self.n_phonemes = int(audio_features), int(n_phonemes)
+        rs = np.random.RandomState(seed + 7919)
+        self._audio_map = rs.randn(corpus.C, max(self.audio_features, 1)).astype(np.float32) / np.sqrt(corpus.C)
+        self._phoneme_map = rs.randn(corpus.C, max(self.n_phonemes, 1)).astype(np.float32)
+
+    @property
+    def phoneme_list(self) -> List[str]:
+        """class list of the phoneme stream; index 0 is the pad class"""
+        return [pad_token] + [f"ph{i}" for i in range(1, self.n_phonemes)]
 
     def _ecog_token_generator(self, block: int):
         rs = np.random.RandomState(self.seed * 100003 + int(block))
         for _ in range(self.utterances_per_block):
             s = int(rs.randint(0, self.corpus.n_sentences))
             x, _n = self.corpus.utterance(s, rs)
-            yield {'ecog_sequence': x, 'text_sequence': [w.encode('utf-8') for w in self.corpus.words(s)]}
+            ex = {'ecog_sequence': x, 'text_sequence': [w.encode('utf-8') for w in self.corpus.words(s)]}
+            if self.audio_features:
+                ex['audio_sequence'] = (x @ self._audio_map).astype(np.float32)
+            if self.n_phonemes:
+                cls = 1 + np.argmax(x @ self._phoneme_map[:, 1:], axis=1)
+                ex['phoneme_sequence'] = [self.phoneme_list[c].encode('utf-8') for c in cls]
+            yield ex
 
     def _write_to_Protobuf(self, block: int):
         path = self.tf_record_partial_path.format(block)
@@ -219,12 +236,18 @@ class ECoGSubject:
 def make_synthetic_subject(subj_id: int, vocab: Sequence[str], out_dir: str, n_train_blocks: int = 4,
                            n_valid_blocks: int = 1, utterances_per_block: int = 50, T: int = 400, C: int = 256,
                            n_sentences: int = 50, ragged: bool = True, seed: int = 0,
-                           pretrain_all_blocks: bool = False) -> ECoGSubject:
+                           pretrain_all_blocks: bool = False, encoder_targets: Optional[str] = None,
+                           encoder_targets_features: int = 13, encoder_targets_layer: int = 1,
+                           encoder_targets_penalty_scale: float = 1.0) -> ECoGSubject:
     """A subject in the shape of block_breakdowns.json + the minimal data_mapping of the README
     ({'decoder_targets': 'text_sequence', 'encoder_inputs': 'ecog_sequence'}, /root/reference/README.md:61)."""
     corpus = SyntheticCorpus(list(vocab), n_sentences=n_sentences, T=T, C=C, ragged=ragged, seed=seed)
     path = os.path.join(out_dir, f"EFC{subj_id}_B{{0}}.tfrecord")   # mochastar_word_sequence.yaml:90
-    gen = SyntheticDataGenerator(corpus, path, utterances_per_block, seed=seed)
+    if encoder_targets not in (None, 'audio_sequence', 'phoneme_sequence'):
+        raise ValueError("encoder_targets must be None, 'audio_sequence' or 'phoneme_sequence'")
+    gen = SyntheticDataGenerator(corpus, path, utterances_per_block, seed=seed,
+                                 audio_features=encoder_targets_features if encoder_targets == 'audio_sequence' else 0,
+                                 n_phonemes=encoder_targets_features if encoder_targets == 'phoneme_sequence' else 0)
     blocks = {b + 1: {'type': 'mocha', 'default_dataset': 'training'} for b in range(n_train_blocks)}
     for b in range(n_valid_blocks):
         blocks[n_train_blocks + b + 1] = {'type': 'mocha', 'default_dataset': 'validation'}
@@ -233,4 +256,13 @@ def make_synthetic_subject(subj_id: int, vocab: Sequence[str], out_dir: str, n_t
         'encoder_inputs': SequenceDataManifest('ecog_sequence', num_features=C),
         'decoder_targets': SequenceDataManifest('text_sequence', get_feature_list=lambda: vocab_list, APPEND_EOS=True),
     }
+    key = f'encoder_{encoder_targets_layer}_targets'      # 'encoder_1_targets' in the reference (trainers.py:791-799)
+    if encoder_targets == 'audio_sequence':
+        manifests[key] = SequenceDataManifest('audio_sequence', num_features=encoder_targets_features,
+                                              num_features_raw=encoder_targets_features,
+                                              penalty_scale=encoder_targets_penalty_scale)
+    elif encoder_targets == 'phoneme_sequence':
+        plist = gen.phoneme_list
+        manifests[key] = SequenceDataManifest('phoneme_sequence', get_feature_list=lambda: plist,
+                                              penalty_scale=encoder_targets_penalty_scale)
     return ECoGSubject(subj_id, gen, blocks, manifests, pretrain_all_blocks=pretrain_all_blocks)

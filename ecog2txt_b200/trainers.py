@@ -182,6 +182,7 @@ class MultiSubjectTrainer:
         data_sizes: Dict = {}
         strides: Dict = {}
         rnn = {}
+        proj: Dict = {}
         for name, shape in var_shapes.items():
             parts = name.split('/')
             if parts[0] != 'seq2seq' or parts[-1] not in ('weights', 'kernel') or 'Adam' in name:
@@ -205,16 +206,42 @@ class MultiSubjectTrainer:
                 strides.setdefault(subnet_id, []).append(shape[1])
                 data_sizes.setdefault(subnet_id, {})['encoder_inputs'] = shape[-2]
                 layer_sizes.setdefault(subsub, []).append(shape[-1])
-            elif subsub.endswith('_projection'):                                     # transposed: trainers.py:513-520
-                data_sizes.setdefault(subnet_id, {})[subsub.replace('_projection', '_targets')] = shape[0]
-                layer_sizes.setdefault(subsub, [])
+            elif subsub.endswith('_projection'):                                     # resolved below (needs every layer)
+                proj.setdefault((subnet_id, subsub), {})[layer] = shape
             else:
                 if subsub == 'decoder_embedding':
                     data_sizes.setdefault(subnet_id, {})['decoder_targets'] = shape[0]
                 layer_sizes.setdefault(subsub, []).append(shape[-1])
+        for (subnet_id, subsub), layers in proj.items():
+            # the LAST layer of a *_projection is stored transposed and only tells the output size (trainers.py:513-520);
+            # earlier layers are ordinary hidden layers
+            layer_sizes[subsub] = [layers[k][-1] for k in sorted(layers)[:-1]]
+            data_sizes.setdefault(subnet_id, {})[subsub.replace('_projection', '_targets')] = layers[max(layers)][0]
         for key, d in rnn.items():                                                   # encoder_rnn_<n> -> one list, :543-552
             layer_sizes[key] = [d[i] for i in sorted(d)]
         return layer_sizes, data_sizes, strides, EMA
+
+    # ---- trainers.py:703-732 ---------------------------------------------------------------------
+    def get_saliencies(self, contrib_method, assessment_type='norms'):
+        """Average "saliency" of the input electrodes: error gradients of ONE output back-propagated into the inputs.
+        contrib_method = '<data_key minus _targets>_saliency_map', e.g. 'decoder_saliency_map' / 'encoder_1_saliency_map':
+        every *_targets penalty is set to 0 except that one (set to 1), as in the reference."""
+        subject = self.ecog_subjects[-1]
+        old_penalties = {}
+        for key, manifest in subject.data_manifests.items():
+            if '_targets' in key:
+                old_penalties[key] = manifest.penalty_scale
+                manifest.penalty_scale = 0.0
+        key = contrib_method.replace('saliency_map', 'targets')
+        subject.data_manifests[key].penalty_scale = 1.0
+        try:
+            return self.net.restore_and_get_saliencies([subject] if len(self.ecog_subjects) == 1 else self.ecog_subjects,
+                                                       self.restore_epoch, data_partition='validation',
+                                                       assessment_type=assessment_type)
+        finally:
+            for key, manifest in subject.data_manifests.items():
+                if '_targets' in key:
+                    manifest.penalty_scale = old_penalties[key]
 
     # ---- trainers.py:925-963 ---------------------------------------------------------------------
     def construct_online_predictor(self, subject_index: int = -1):

@@ -48,6 +48,11 @@ extern "C" {
 /* decoder attention (A7) */
 #define E2T_ATTN_NONE 0
 #define E2T_ATTN_LUONG 1    /* q = h Wq^T; alpha = softmax_s(q . enc_s); h~ = tanh(Wc [ctx; h] + bc); logits from h~ */
+#define E2T_ATTN_BAHDANAU 2 /* additive score: alpha = softmax_s(v . tanh(Wq h + Wk enc_s)); context / combine as above */
+
+/* encoder-targets head (A6) */
+#define E2T_AUX_GAUSSIAN 0     /* float targets [B,T,F], 0.5 * squared error (subjects.py:369-380: MFCC-type streams) */
+#define E2T_AUX_CATEGORICAL 1  /* int32 targets [B,T] (class index, 0 = pad), cross-entropy (phoneme streams) */
 
 /* GEMM backends */
 #define E2T_GEMM_AUTO 0     /* tcgen05 where shapes allow, SIMT otherwise */
@@ -79,8 +84,15 @@ typedef struct e2t_config {
   float penalty_scale;                   /* decoder_targets penalty_scale, subjects.py:289 */
   int32_t gemm_backend;                  /* E2T_GEMM_* */
   int32_t device;                        /* CUDA device ordinal */
-  int32_t attention;                     /* E2T_ATTN_*: optional Luong attention over the encoder outputs (not in the
+  int32_t attention;                     /* E2T_ATTN_*: optional Luong / Bahdanau attention over the encoder outputs (not in the
                                           * reference model; default NONE = reference behaviour) */
+  /* A6: auxiliary loss on the outputs of encoder layer `aux_layer` ('encoder_1_targets' -> 1: trainers.py:798-799,
+   * mochastar_word_sequence.yaml:54,68-69,81).  aux_F == 0: no head (the minimal data_mapping has none, README.md:61). */
+  int32_t aux_layer;
+  int32_t aux_hidden;                    /* layer_sizes['encoder_1_projection'][0] (225); 0 = output layer only */
+  int32_t aux_F;                         /* num_features of the encoder targets; 0 disables the head */
+  int32_t aux_kind;                      /* E2T_AUX_* */
+  float aux_penalty;                     /* encoder_1_targets_penalty_scale */
 } e2t_config;
 
 const char* e2t_last_error(void);
@@ -125,12 +137,30 @@ int e2t_train_step_grads(e2t_handle* h, int subnet, const float* x, const int32_
  * subnet / B / T / L (x, lens, y arguments are then ignored).  Host buffers should be page-locked for the copy to overlap. */
 int e2t_stage_inputs(e2t_handle* h, int slot, int subnet, const float* x, const int32_t* lens,
                      const int32_t* y, int B, int T, int L);
+/* A6: encoder targets of the NEXT e2t_train_step_grads / e2t_eval_loss / e2t_input_saliency call (consumed by it):
+ * float [B,T,aux_F] (E2T_AUX_GAUSSIAN) or int32 [B,T] (E2T_AUX_CATEGORICAL) at the input's frame rate, zero / pad-index
+ * padded.  The library reverses them within the utterance length and keeps every W-th frame (trainers.py:791-795).
+ * A step without targets skips the head (its parameters get zero gradients). */
+int e2t_set_encoder_targets(e2t_handle* h, const void* targets, int loc, int B, int T);
+/* the two terms of the most recent loss: penalty_scale * sum CE over `ntok` tokens, aux_penalty * sum over
+ * `aux_frames` frames (0 when the head did not run); loss_sum of the calls above is their sum.  Synchronises. */
+int e2t_last_losses(e2t_handle* h, float* decoder_sum, int32_t* ntok, float* aux_sum, int32_t* aux_frames);
 /* Adam + EMA on the trainable tensors of `subnet` (private) and the shared ones, using
  * grad * grad_scale (1 / global token count).  subnet < 0: every subnet. */
 int e2t_adam_ema_step(e2t_handle* h, int subnet, float grad_scale);
 /* forward only (assessment loss): same inputs, no dropout, weights = value or EMA */
 int e2t_eval_loss(e2t_handle* h, int subnet, const float* x, const int32_t* lens, const int32_t* y,
                   int loc, int B, int T, int L, int use_ema, float* loss_sum, int32_t* ntok);
+
+/* ---- saliency: replaces restore_and_get_saliencies (trainers.py:703-732) ----
+ * d(loss)/d(encoder_inputs) of one batch, dropout off, weights = value or EMA.  decoder_penalty / aux_penalty
+ * override the configured penalty scales for this call (get_saliencies sets every *_targets penalty to 0 except the
+ * one under study).  dx [B,T,C] (nullable, host or device per `loc`): the input gradient (zero past each utterance's last conv window).
+ * sq_norms [B,C] (nullable): sum over time of dx^2 per electrode (assessment_type 'norms'; the caller takes the
+ * square root / averages).  Overwrites the E2T_GRAD buffer. */
+int e2t_input_saliency(e2t_handle* h, int subnet, const float* x, const int32_t* lens, const int32_t* y, int loc,
+                       int B, int T, int L, int use_ema, float decoder_penalty, float aux_penalty, float* dx,
+                       float* sq_norms);
 
 /* ---- decoding: replaces restore_and_assess's decode and the online predictor
  * ('decoder_outputs:0', 'decoder_probs:0'; trainers.py:379,933-937) ----
@@ -147,7 +177,7 @@ int e2t_beam_decode(e2t_handle* h, int subnet, const float* x, const int32_t* le
 /* ---- introspection (get_internal_activations, trainers.py:757-859) -------------------------
  * Copies an activation of the most recent forward pass to the host.  names: "lens", "lens2"
  * (int32 [B]), "conv_out" [T',B,E], "enc<l>_out" [T',B,2H], "final_h", "final_c" [B,Hd],
- * "logits" [L,B,V].  n_cap = capacity of host_out in elements; *n_out = elements written. */
+ * "logits" [L,B,V], "aux_out" [T',B,aux_F] (A6 head outputs; in training they hold d(loss)/d(out)).  n_cap = capacity of host_out in elements; *n_out = elements written. */
 int e2t_get_activation(e2t_handle* h, const char* name, void* host_out, int64_t n_cap,
                        int64_t* n_out);
 

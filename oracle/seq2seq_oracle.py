@@ -60,7 +60,14 @@ class OracleConfig:
     beta2: float = 0.999
     eps: float = 1e-8
     ema_decay: float = 0.99                   # yaml:3
-    attention: str = "none"                   # "luong": optional A7 module [CHOICE; absent from the reference, SURVEY 0.5]
+    attention: str = "none"                   # "luong" / "bahdanau": optional A7 module [CHOICE; absent from the reference, SURVEY 0.5]
+    # A6 encoder-targets head (App. D item 12): FF head on the outputs of encoder layer `aux_layer`
+    # ("encoder_1_targets" -> 1, trainers.py:798-799; yaml:54,68-69,81); aux_layer < 0 = no head (README.md:61)
+    aux_layer: int = -1
+    aux_hidden: int = 0                       # encoder_1_projection = [225]; 0 = straight to the output layer
+    aux_F: int = 0                            # num_features of the encoder targets (13 MFCC-type / 42 phoneme classes)
+    aux_kind: str = "gaussian"                # "gaussian": float targets, squared error; "categorical": int targets, CE
+    aux_penalty: float = 1.0                  # encoder_1_targets_penalty_scale, yaml:54
 
     def __post_init__(self):
         assert self.Hd == 2 * self.H[-1], "bridge needs decoder_rnn == 2*encoder_rnn[-1]"
@@ -91,12 +98,35 @@ def param_shapes(cfg: OracleConfig) -> "Dict[str, Tuple[int, ...]]":
     base = f"seq2seq/decoder_projection_{cfg.Hd}_{cfg.V}_0"
     shapes[base + "/weights"] = (cfg.V, cfg.Hd)            # transposed, trainers.py:513-520
     shapes[base + "/biases"] = (cfg.V,)
-    if cfg.attention == "luong":
+    if cfg.attention in ("luong", "bahdanau"):
         # stored [out, in] like the projection; q = h Wq^T, h~ = tanh(Wc [ctx; h] + bc)
         shapes["seq2seq/decoder_attention/query/weights"] = (cfg.Hd, cfg.Hd)
+        if cfg.attention == "bahdanau":
+            shapes["seq2seq/decoder_attention/keys/weights"] = (cfg.Hd, cfg.Hd)
+            shapes["seq2seq/decoder_attention/score/weights"] = (1, cfg.Hd)
         shapes["seq2seq/decoder_attention/combine/weights"] = (cfg.Hd, 2 * cfg.Hd)
         shapes["seq2seq/decoder_attention/combine/biases"] = (cfg.Hd,)
+    if cfg.aux_layer >= 0:
+        n_in = 2 * cfg.H[cfg.aux_layer]
+        k = 0
+        if cfg.aux_hidden > 0:
+            base = f"seq2seq/encoder_{cfg.aux_layer}_projection_{n_in}_{cfg.aux_hidden}_0"
+            shapes[base + "/weights"] = (n_in, cfg.aux_hidden)
+            shapes[base + "/biases"] = (cfg.aux_hidden,)
+            n_in, k = cfg.aux_hidden, 1
+        base = f"seq2seq/encoder_{cfg.aux_layer}_projection_{n_in}_{cfg.aux_F}_{k}"
+        shapes[base + "/weights"] = (cfg.aux_F, n_in)      # final layer of a *_projection: transposed, trainers.py:513-520
+        shapes[base + "/biases"] = (cfg.aux_F,)
     return shapes
+
+
+def aux_names(cfg: OracleConfig):
+    """(hidden-layer base name or None, output-layer base name) of the encoder-targets head."""
+    n_in = 2 * cfg.H[cfg.aux_layer]
+    if cfg.aux_hidden > 0:
+        return (f"seq2seq/encoder_{cfg.aux_layer}_projection_{n_in}_{cfg.aux_hidden}_0",
+                f"seq2seq/encoder_{cfg.aux_layer}_projection_{cfg.aux_hidden}_{cfg.aux_F}_1")
+    return None, f"seq2seq/encoder_{cfg.aux_layer}_projection_{n_in}_{cfg.aux_F}_0"
 
 
 def init_params(cfg: OracleConfig, seed: int = 1, dtype=torch.float32) -> "Dict[str, torch.Tensor]":
@@ -110,7 +140,8 @@ def init_params(cfg: OracleConfig, seed: int = 1, dtype=torch.float32) -> "Dict[
         else:
             if len(shape) == 4:
                 fan_in, fan_out = shape[1] * shape[2], shape[3]
-            elif name.endswith("decoder_projection_%d_%d_0/weights" % (cfg.Hd, cfg.V)):
+            elif name.endswith("decoder_projection_%d_%d_0/weights" % (cfg.Hd, cfg.V)) or (
+                    cfg.aux_layer >= 0 and name == aux_names(cfg)[1] + "/weights"):
                 fan_in, fan_out = shape[1], shape[0]
             else:
                 fan_in, fan_out = shape[0], shape[1]
@@ -149,7 +180,7 @@ def dropout_keep(seed: int, stream: int, n: int, p: float) -> np.ndarray:
 
 
 # stream ids (must match csrc): conv output 0 ; encoder layer l output 1+l ; decoder embedding 64
-STREAM_CONV, STREAM_ENC0, STREAM_DEMB = 0, 1, 64
+STREAM_CONV, STREAM_ENC0, STREAM_DEMB, STREAM_AUX = 0, 1, 64, 96
 
 
 # ------------------------------------------------------------------------------------------------
@@ -268,6 +299,22 @@ def luong_attention(cfg, P, h, enc, lens2):
                       + P["seq2seq/decoder_attention/combine/biases"])
 
 
+def bahdanau_attention(cfg, P, h, enc, lens2):
+    """A7, additive variant [CHOICE, not in the reference]: score_s = v . tanh(Wq h + Wk enc_s) for s < lens2; the
+    softmax, the context and the combine layer h~ = tanh(Wc [ctx; h] + bc) are those of `luong_attention` (attention on the
+    decoder OUTPUT, no input feeding, so the recurrence is untouched)."""
+    q = h @ P["seq2seq/decoder_attention/query/weights"].T                     # [B,A]
+    kp = enc @ P["seq2seq/decoder_attention/keys/weights"].T                   # [B,T',A]
+    v = P["seq2seq/decoder_attention/score/weights"][0]
+    score = torch.tanh(q.unsqueeze(1) + kp) @ v                                # [B,T']
+    mask = torch.arange(enc.shape[1]).unsqueeze(0) < lens2.unsqueeze(1)
+    score = score.masked_fill(~mask, -1e30)
+    alpha = torch.softmax(score, dim=1) * mask.to(h.dtype)
+    ctx = torch.einsum("bs,bsf->bf", alpha, enc)
+    return torch.tanh(torch.cat([ctx, h], dim=1) @ P["seq2seq/decoder_attention/combine/weights"].T
+                      + P["seq2seq/decoder_attention/combine/biases"])
+
+
 def decoder_step(cfg, P, y_prev, h, c, emb_mask=None, enc=None, lens2=None):
     """One decoder step: Emb[y_prev] (+bias, act) -> LSTM(Hd) [-> attention] -> logits = h Wp^T + b."""
     eb = f"seq2seq/decoder_embedding_{cfg.V}_{cfg.D}_0"
@@ -279,7 +326,11 @@ def decoder_step(cfg, P, y_prev, h, c, emb_mask=None, enc=None, lens2=None):
     z = e @ K[:cfg.D] + h @ K[cfg.D:] + bias
     h, c = lstm_cell(z, c)
     pb = f"seq2seq/decoder_projection_{cfg.Hd}_{cfg.V}_0"
-    ho = luong_attention(cfg, P, h, enc, lens2) if cfg.attention == "luong" else h
+    ho = h
+    if cfg.attention == "luong":
+        ho = luong_attention(cfg, P, h, enc, lens2)
+    elif cfg.attention == "bahdanau":
+        ho = bahdanau_attention(cfg, P, h, enc, lens2)
     logits = ho @ P[pb + "/weights"].T + P[pb + "/biases"]
     return logits, h, c
 
@@ -293,16 +344,55 @@ def make_masks(cfg, seed, B, T2, L, ff_p, rnn_p, dtype):
     if ff_p > 0:
         masks["conv"] = mk(STREAM_CONV, (T2, B, cfg.E), ff_p).permute(1, 0, 2)
         masks["demb"] = mk(STREAM_DEMB, (L, B, cfg.D), ff_p).permute(1, 0, 2)
+        if cfg.aux_layer >= 0 and cfg.aux_hidden > 0:
+            masks["aux"] = mk(STREAM_AUX, (T2, B, cfg.aux_hidden), ff_p).permute(1, 0, 2)
     if rnn_p > 0:
         for l, H in enumerate(cfg.H[:-1]):
             masks[f"enc{l}"] = mk(STREAM_ENC0 + l, (T2, B, 2 * H), rnn_p).permute(1, 0, 2)
     return masks
 
 
-def train_loss(cfg, P, x, lens, y, subnet=0, masks=None):
+def prepare_encoder_targets(tgt: torch.Tensor, lens: torch.Tensor, W: int) -> torch.Tensor:
+    """A6 targets (trainers.py:791-795): reverse within length, then keep every W-th frame, `[:, 0::W]`.
+    tgt [B,T,F] float or [B,T] int at the input's frame rate -> [B,T',...].  The reference infers the
+    length from the targets' own zero padding; here the utterance length is used (same trial, same clock)."""
+    r = reverse_within_length(tgt, lens)
+    return r[:, 0::W]
+
+
+def aux_head(cfg, P, acts, aux_targets, subnet, masks=None):
+    """A6 (App. D item 12): FF head on the (un-dropped) outputs of encoder layer `aux_layer`:
+    [hidden = act(x W1 + b1), FF dropout] -> out = hidden W2^T + b2 (W2 stored transposed, trainers.py:513-520).
+    gaussian: 0.5 * sum_f (out - tgt)^2 over frames t' < len'; categorical: CE vs the class index, frames whose
+    target is the pad index 0 or t' >= len' are masked.  Returns (aux_penalty * sum, number of unmasked frames)."""
+    W = cfg.subnet_W[subnet]
+    x = acts[f"enc{cfg.aux_layer}_out"]                          # [B,T',2H]
+    hb, ob = aux_names(cfg)
+    if hb is not None:
+        x = _act(x @ P[hb + "/weights"] + P[hb + "/biases"], cfg.conv_act)
+        if masks is not None and "aux" in masks:
+            x = x * masks["aux"]
+    out = x @ P[ob + "/weights"].T + P[ob + "/biases"]           # [B,T',F]
+    tg = prepare_encoder_targets(aux_targets, acts["lens"], W)
+    T2 = out.shape[1]
+    valid = torch.arange(T2).unsqueeze(0) < acts["lens2"].unsqueeze(1)
+    acts["aux_out"] = out
+    if cfg.aux_kind == "gaussian":
+        m = valid.to(out.dtype).unsqueeze(2)
+        loss = 0.5 * (((out - tg.to(out.dtype)) ** 2) * m).sum()
+    else:
+        tg = tg.long()
+        valid = valid & (tg != 0)
+        lp = torch.log_softmax(out, dim=2)
+        loss = -(lp.gather(2, tg.unsqueeze(2)).squeeze(2) * valid.to(out.dtype)).sum()
+    return loss * cfg.aux_penalty, int(valid.sum())
+
+
+def train_loss(cfg, P, x, lens, y, subnet=0, masks=None, aux_targets=None):
     """Teacher-forced forward + masked CE (App. D items 6-7).  y [B,L] int64 with EOS appended and
-    pad_id after it.  Returns (sum of token losses * penalty_scale, n_unmasked_tokens, acts);
-    the caller divides by the *global* token count."""
+    pad_id after it.  Returns (sum of token losses * penalty_scale [+ aux_penalty * sum of the
+    encoder-targets losses], n_unmasked_tokens, acts); the caller divides by the *global* token count
+    (one common normaliser for both penalties [CHOICE], so that data-parallel training needs one scalar)."""
     acts = encoder(cfg, P, x, lens, subnet, masks)
     h, c = acts["final_h"], acts["final_c"]
     B, L = y.shape
@@ -319,13 +409,30 @@ def train_loss(cfg, P, x, lens, y, subnet=0, masks=None):
         prev = y[:, k]
     acts["logits"] = torch.stack(logits_all, dim=1)
     ntok = int((y != cfg.pad_id).sum())
-    return loss * cfg.penalty_scale, ntok, acts
+    loss = loss * cfg.penalty_scale
+    acts["decoder_loss"] = float(loss.detach())
+    if cfg.aux_layer >= 0 and aux_targets is not None:
+        la, nf = aux_head(cfg, P, acts, aux_targets, subnet, masks)
+        acts["aux_loss"], acts["aux_frames"] = float(la.detach()), nf
+        loss = loss + la
+    return loss, ntok, acts
 
 
-def loss_and_grads(cfg, P, x, lens, y, subnet=0, masks=None):
+def input_gradients(cfg, P, x, lens, y, subnet=0, aux_targets=None):
+    """A13 saliency (trainers.py:703-732): d(loss)/d(encoder_inputs) [B,T,C] with dropout off; the caller picks the
+    penalty under study by setting the others to 0 in `cfg` (get_saliencies zeroes every *_targets penalty but one)."""
+    xg = x.clone().requires_grad_(True)
+    if lens is None:
+        lens = infer_lengths(x)
+    loss, _, _ = train_loss(cfg, P, xg, lens, y, subnet, None, aux_targets)
+    loss.backward()
+    return xg.grad
+
+
+def loss_and_grads(cfg, P, x, lens, y, subnet=0, masks=None, aux_targets=None):
     """Reference gradients by autograd of `train_loss` (sum, not yet / ntok)."""
     Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
-    loss, ntok, acts = train_loss(cfg, Pg, x, lens, y, subnet, masks)
+    loss, ntok, acts = train_loss(cfg, Pg, x, lens, y, subnet, masks, aux_targets)
     loss.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in Pg.items()}
     return float(loss.detach()), ntok, grads, {k: (v.detach() if torch.is_tensor(v) else v) for k, v in acts.items()}

@@ -77,6 +77,16 @@ def test_attention_train_and_decode(gpu_lib, backend, tol):
     pc.check_decode(gpu_lib, pc.MEDIUM_ATTN, 4, 96, 6, beam=4, backend=backend)
 
 
+@pytest.mark.parametrize("backend,tol", [("simt", 2e-4), ("auto", 1e-2)])
+def test_bahdanau_attention_train_and_decode(gpu_lib, backend, tol):
+    """A7, additive (Bahdanau) score: same coverage as the Luong module."""
+    pc.check_train_step(gpu_lib, pc.MEDIUM_BAH, 16, 96, 6, backend=backend, tol=tol)
+    pc.check_train_step(gpu_lib, pc.MEDIUM_BAH, 16, 96, 6, ff=0.1, rnn=0.5, backend=backend, tol=tol)
+    pc.check_decode(gpu_lib, pc.MEDIUM_BAH, 8, 96, 6, backend=backend)
+    # temperature 0.2: at 0.7 no two beam scores of these random weights are 1e-2 apart and the token check would be vacuous
+    pc.check_decode(gpu_lib, pc.MEDIUM_BAH, 4, 96, 6, beam=4, backend=backend, temperature=0.2)
+
+
 @pytest.mark.parametrize("backend,tol", [("simt", 2e-4), ("auto", 2e-4)])
 def test_golden_vectors(gpu_lib, backend, tol):
     """The committed golden vectors (tests/golden/make_golden.py) through the CUDA path; TINY shapes stay on the fp32
@@ -254,4 +264,72 @@ def test_staged_inputs_match_host_path(gpu_lib):
     with pytest.raises(E2TError):
         eng._staged_shape[0] = (8, 96, 6, 0)        # a slot holds what was staged, not what the caller claims
         eng.train_step_grads_staged(0, seed=7)
+    eng.close()
+
+
+@pytest.mark.parametrize("backend,tol", [("simt", 2e-4), ("auto", 1e-2)])
+def test_encoder_targets_head(gpu_lib, backend, tol):
+    """A6: the encoder-targets head (FF 2H -> hidden -> F on encoder layer 1; Gaussian and categorical targets), loss and
+    every gradient -- the head's own tensors and the extra gradient that reaches layers 0-1 and the conv through it."""
+    pc.check_train_step(gpu_lib, pc.MEDIUM_AUX, 16, 96, 6, backend=backend, tol=tol)
+    pc.check_train_step(gpu_lib, pc.MEDIUM_AUX, 16, 96, 6, ff=0.1, rnn=0.5, backend=backend, tol=tol)
+    pc.check_train_step(gpu_lib, pc.MEDIUM_AUX_CAT, 16, 96, 6, backend=backend, tol=tol)
+    pc.check_train_step(gpu_lib, pc.TINY_AUX_CAT, 4, 21, 5, backend=backend, tol=tol)
+
+
+@pytest.mark.parametrize("backend,tol", [("simt", 2e-4), ("auto", 1e-2)])
+def test_input_saliency(gpu_lib, backend, tol):
+    """A13: d(loss)/d(encoder_inputs) against autograd of the oracle, decoder penalty / encoder-targets penalty, EMA weights."""
+    pc.check_saliency(gpu_lib, pc.MEDIUM, 16, 96, 6, backend=backend, tol=tol)
+    pc.check_saliency(gpu_lib, pc.MEDIUM_AUX, 16, 96, 6, backend=backend, tol=tol, which="aux")
+    pc.check_saliency(gpu_lib, pc.MEDIUM_AUX_CAT, 16, 96, 6, backend=backend, tol=tol, which="decoder", use_ema=True)
+    pc.check_saliency(gpu_lib, pc.WIDE, 40, 100, 5, backend=backend, tol=tol)
+
+
+def test_full_size_saliency_and_encoder_targets(gpu_lib):
+    """Config-2 shapes with the reference's head (encoder_1_projection = [225], 13 MFCC-type targets, yaml:68-69,81):
+    (1) linearity -- the saliency under both penalties = the sum of the two single-penalty saliencies; (2) a directional
+    finite difference of the forward-only loss along the saliency agrees with |dx|^2; (3) padding frames beyond the last
+    conv window carry no gradient; (4) the training loss is the sum of its two terms and both are finite."""
+    B = 64
+    x, lens, y = _full_size_batch(B)
+    eng = _full_size_engine(gpu_lib, B, aux_layer=1, aux_hidden=225, aux_F=13, aux_kind="gaussian", aux_penalty=0.1)
+    rs = np.random.RandomState(4)
+    aux = rs.randn(B, 400, 13).astype(np.float32)
+    for b in range(B):
+        aux[b, lens[b]:] = 0
+    eng.set_encoder_targets(aux)
+    loss, ntok = eng.train_step_grads(x, None, y, seed=3)
+    ld, nt, la, nf = eng.last_losses()
+    assert np.isfinite(loss) and abs(loss - (ld + la)) <= 1e-5 * abs(loss) and nt == ntok
+    assert nf == int(np.ceil(lens / 12).sum()) and la > 0
+    sal = {}
+    for name, (pd, pa) in dict(dec=(1.0, 0.0), aux=(0.0, 0.1), both=(1.0, 0.1)).items():
+        eng.set_encoder_targets(aux)
+        sal[name], _ = eng.input_saliency(x, None, y, decoder_penalty=pd, aux_penalty=pa, want_norms=False)
+    assert np.abs(sal["dec"]).max() > 0 and np.abs(sal["aux"]).max() > 0
+    assert pc.rel_err(sal["dec"] + sal["aux"], sal["both"]) <= 1e-3
+    for b in range(B):
+        assert (sal["both"][b, -(-lens[b] // 12) * 12:] == 0).all()
+    # the same model on the fp32 CUDA-core backend: its saliency agrees with the tensor-core one, and a central finite
+    # difference of ITS forward-only loss along the saliency direction reproduces <dx, d> (tf32 rounding of the loss
+    # would swamp the difference, hence fp32 for this leg)
+    eng_s = _full_size_engine(gpu_lib, B, gemm_backend="simt", aux_layer=1, aux_hidden=225, aux_F=13, aux_kind="gaussian",
+                              aux_penalty=0.1)
+    eng_s.set_encoder_targets(aux)
+    sal_s, _ = eng_s.input_saliency(x, None, y, want_norms=False)
+    assert pc.rel_err(sal["both"], sal_s) <= 5e-2, pc.rel_err(sal["both"], sal_s)
+    d = sal_s.copy()
+    for b in range(B):
+        d[b, lens[b]:] = 0        # keep the inferred lengths unchanged
+    d /= np.sqrt((d.astype(np.float64) ** 2).sum())
+    g_dir = float((sal_s.astype(np.float64) * d).sum())
+    eps = 5e-2
+    vals = []
+    for sgn in (1.0, -1.0):
+        eng_s.set_encoder_targets(aux)
+        vals.append(eng_s.eval_loss((x + sgn * eps * d).astype(np.float32), lens, y)[0])
+    fd = (vals[0] - vals[1]) / (2 * eps)
+    assert abs(fd - g_dir) <= 5e-2 * abs(g_dir), (fd, g_dir)
+    eng_s.close()
     eng.close()

@@ -54,3 +54,47 @@ def test_attention_train_step(emu_lib):
 def test_attention_decode(emu_lib):
     pc.check_decode(emu_lib, pc.TINY_ATTN, 6, 21, 6)
     pc.check_decode(emu_lib, pc.TINY_ATTN, 4, 21, 6, beam=4)
+
+
+def test_bahdanau_attention(emu_lib):
+    """A7, additive score v . tanh(Wq h + Wk enc_s): forward, every gradient (query / keys / score vector / combine, and
+    the encoder path through both the context and the keys), greedy and beam decode."""
+    pc.check_train_step(emu_lib, pc.TINY_BAH, 3, 19, 5)
+    pc.check_train_step(emu_lib, pc.TINY_BAH, 3, 19, 5, ff=0.1, rnn=0.5)
+    pc.check_decode(emu_lib, pc.TINY_BAH, 6, 21, 6, margin=1e-4)     # fp32 emulation: a tighter tie margin is enough
+    pc.check_decode(emu_lib, pc.TINY_BAH, 4, 21, 6, beam=4, margin=1e-4)
+
+
+def test_encoder_targets_head(emu_lib):
+    """A6: FF head on an encoder layer's outputs + gaussian / categorical loss, forward and backward."""
+    pc.check_train_step(emu_lib, pc.TINY_AUX, 3, 19, 5)
+    pc.check_train_step(emu_lib, pc.TINY_AUX, 3, 19, 5, ff=0.1, rnn=0.5)
+    pc.check_train_step(emu_lib, pc.TINY_AUX_CAT, 4, 21, 5)
+    pc.check_train_step(emu_lib, pc.TINY_AUX_CAT, 4, 21, 5, ff=0.1, rnn=0.5, give_lens=True)
+
+
+def test_encoder_targets_are_optional_per_step(emu_lib):
+    """a step without targets skips the head: zero gradients on its parameters, loss = decoder loss only"""
+    from oracle import seq2seq_oracle as O
+    ocfg = O.OracleConfig(**pc.TINY_AUX)
+    P = pc.make_params(ocfg)
+    eng = pc.engine_for(pc.TINY_AUX, emu_lib, 3, 19, 5, gemm_backend="simt")
+    eng.set_all({k: v.numpy() for k, v in P.items()})
+    x, lens, y = pc.make_batch(ocfg, 3, 19, 5)
+    import torch
+    lo, no, g, _ = O.loss_and_grads(ocfg, P, torch.from_numpy(x), None, torch.from_numpy(y).long())
+    loss, ntok = eng.train_step_grads(x, None, y)
+    assert abs(loss - lo) <= 2e-4 * abs(lo)
+    G = eng.get_all(1)
+    for k, v in G.items():
+        if "_projection" in k and "encoder_" in k:
+            assert (v == 0).all(), k
+    assert eng.last_losses()[2:] == (0.0, 0)
+    eng.close()
+
+
+def test_input_saliency(emu_lib):
+    """A13: d(loss)/d(inputs) for the decoder penalty and for the encoder-targets penalty, value and EMA weights."""
+    pc.check_saliency(emu_lib, pc.TINY, 3, 19, 5)
+    pc.check_saliency(emu_lib, pc.TINY_AUX, 3, 19, 5, which="aux")
+    pc.check_saliency(emu_lib, pc.TINY_AUX_CAT, 4, 21, 5, which="decoder", use_ema=True)

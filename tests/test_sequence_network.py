@@ -87,3 +87,40 @@ def test_transfer_learning_scopes(tmp_path, emu_lib):
     assert np.array_equal(shared_before, shared_after)
     conv_b = net.get_weights_as_numpy_array("seq2seq/subnet_401/encoder_embedding_6_5_0/weights", 20)
     assert conv_b.shape == (1, 4, 6, 5)
+
+
+@pytest.mark.parametrize("stream,F", [("audio_sequence", 4), ("phoneme_sequence", 5)])
+def test_encoder_targets_and_saliencies(tmp_path, emu_lib, stream, F):
+    """A6 + A13 through the class: an 'encoder_1_targets' stream (audio -> Gaussian, phonemes -> categorical) adds the FF
+    head under the reference's '<x>_projection' names; restore_and_get_saliencies with the penalties the caller set
+    (MultiSubjectTrainer.get_saliencies zeroes all but one, /root/reference/ecog2txt/trainers.py:703-732)."""
+    s = _subject(tmp_path, encoder_targets=stream, encoder_targets_features=F, encoder_targets_penalty_scale=0.5)
+    s.write_tf_records_maybe()
+    m = dict(MANIFEST, N_epochs=10)
+    m["layer_sizes"] = dict(m["layer_sizes"], encoder_1_projection=[7])
+    net = SequenceNetwork(m, VERBOSE=False, N_cases=6, max_hyp_length=5, learning_rate=2e-2, lib=emu_lib, gemm_backend="simt")
+    net.checkpoint_path = str(tmp_path / "aux" / "model.ckpt")
+    net.fit([s])
+    shapes = prm.variable_to_shape_map(net.checkpoint_path, 10)
+    assert shapes["seq2seq/encoder_1_projection_16_7_0/weights"] == [16, 7]
+    assert shapes[f"seq2seq/encoder_1_projection_7_{F}_1/weights"] == [F, 7]          # final layer transposed
+    trained = net.get_weights_as_numpy_array(f"seq2seq/encoder_1_projection_7_{F}_1/weights", 10)
+    net0 = SequenceNetwork(m, VERBOSE=False, N_cases=6, max_hyp_length=5, lib=emu_lib, gemm_backend="simt")
+    eng0 = net0._get_engine([s], 16, 5)
+    assert np.abs(trained - eng0.get(f"seq2seq/encoder_1_projection_7_{F}_1/weights")).max() > 1e-3   # the head trains
+    # saliencies: decoder penalty only, then the encoder-targets penalty only
+    key = "encoder_1_targets"
+    old = s.data_manifests[key].penalty_scale
+    s.data_manifests[key].penalty_scale = 0.0
+    dec = net.restore_and_get_saliencies([s], 10, data_partition="validation", assessment_type="norms")
+    s.data_manifests[key].penalty_scale, s.data_manifests["decoder_targets"].penalty_scale = 1.0, 0.0
+    aux = net.restore_and_get_saliencies([s], 10, data_partition="validation", assessment_type="norms")
+    seqs = net.restore_and_get_saliencies([s], 10, data_partition="validation", assessment_type="sequences")
+    s.data_manifests[key].penalty_scale, s.data_manifests["decoder_targets"].penalty_scale = old, 1.0
+    assert dec.shape == (6,) and aux.shape == (6,) and (dec > 0).all() and (aux > 0).all()
+    assert not np.allclose(dec, aux)
+    ex = net._load_partition(s, "validation")
+    assert len(seqs) == len(ex) and all(g.shape == e[0].shape for g, e in zip(seqs, ex))
+    ref = np.mean([np.sqrt((g ** 2).sum(0)) for g in seqs], axis=0)
+    # 'norms' also counts the gradient on the zero frames that complete each trial's last conv window
+    assert (ref <= aux * (1 + 1e-5)).all() and np.allclose(ref, aux, rtol=0.2)

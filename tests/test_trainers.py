@@ -10,8 +10,8 @@ from ecog2txt_b200 import params as prm
 from test_sequence_network import MANIFEST, VOCAB, _subject
 
 
-def _trainer(tmp_path, emu_lib, ids=(400, 401), **sn):
-    subjects = [_subject(tmp_path, sid, seed=i) for i, sid in enumerate(ids)]
+def _trainer(tmp_path, emu_lib, ids=(400, 401), subject_kw=None, **sn):
+    subjects = [_subject(tmp_path, sid, seed=i, **(subject_kw or {})) for i, sid in enumerate(ids)]
     for s in subjects:
         s.write_tf_records_maybe()
     manifest = {sid: dict(MANIFEST, token_type="word_sequence", decoder_targets_penalty_scale=1.0) for sid in ids}
@@ -48,7 +48,7 @@ def test_sequential_transfer_learn(tmp_path, emu_lib):
     assert abs(res["training"].word_error_rate - a["training"].decoder_word_error_rates[-1]) < 1e-9
     # online predictor: one utterance at a time -> sentence
     predict = tr.construct_online_predictor()
-    x, _ = tr.net._load_partition(tr.ecog_subjects[-1], "validation")[0]
+    x = tr.net._load_partition(tr.ecog_subjects[-1], "validation")[0][0]
     s1 = predict(x)
     assert isinstance(s1, str) and s1 == predict(x)
 
@@ -63,3 +63,21 @@ def test_parallel_transfer_learn_and_resume(tmp_path, emu_lib):
     assert "seq2seq/subnet_401/encoder_embedding_6_5_0/weights" in shapes
     tr.parallel_transfer_learn(RESUME=True)                                   # last subject only, from the latest epoch
     assert tr.restore_epoch == 20
+
+
+def test_get_saliencies_and_projection_sizes(tmp_path, emu_lib):
+    """get_saliencies (trainers.py:703-732) zeroes every *_targets penalty but the one named by contrib_method and restores
+    them afterwards; recover_model_sizes splits an 'encoder_1_projection' into hidden sizes + the (transposed) output size."""
+    tr = _trainer(tmp_path, emu_lib, ids=(400,), subject_kw=dict(encoder_targets="audio_sequence", encoder_targets_features=4,
+                                                                   encoder_targets_penalty_scale=0.3),
+                  N_epochs=5, assessment_epoch_interval=5)
+    tr.net.layer_sizes = dict(tr.net.layer_sizes, encoder_1_projection=[7])
+    tr.parallel_transfer_learn()
+    layer_sizes, data_sizes, _, _ = tr.recover_model_sizes()
+    assert layer_sizes["encoder_1_projection"] == [7] and data_sizes[None]["encoder_1_targets"] == 4
+    assert layer_sizes["decoder_projection"] == [] and data_sizes[None]["decoder_targets"] == len(VOCAB)
+    dec = tr.get_saliencies("decoder_saliency_map")
+    aux = tr.get_saliencies("encoder_1_saliency_map")
+    assert dec.shape == (6,) and aux.shape == (6,) and not np.allclose(dec, aux)
+    mans = tr.ecog_subjects[-1].data_manifests
+    assert mans["encoder_1_targets"].penalty_scale == 0.3 and mans["decoder_targets"].penalty_scale == 1.0
