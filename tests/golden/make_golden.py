@@ -45,6 +45,33 @@ def main():
     out["beam_tokens"], out["beam_scores"] = bt.numpy(), bs.numpy()
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "seq2seq_tiny.npz"), **out)
     print("wrote seq2seq_tiny.npz: loss", loss, "ntok", ntok)
+    make_optional()
+
+
+def make_optional():
+    """seq2seq_tiny_optional.npz: the optional rows together -- encoder-targets head (A6, Gaussian, hidden layer) +
+    Bahdanau attention (A7) + input saliency under both penalties (A13)."""
+    geo = dict(pc.TINY_AUX, attention="bahdanau")
+    ocfg = O.OracleConfig(**geo)
+    P32 = pc.make_params(ocfg, eos_bias=-1.0)
+    P = {k: v.double() for k, v in P32.items()}
+    B, T, L = 4, 19, 5
+    x, lens, y = pc.make_batch(ocfg, B, T, L, seed=12)
+    aux = pc.make_aux_targets(ocfg, lens, T, seed=6)
+    xt, yt, at = torch.from_numpy(x).double(), torch.from_numpy(y).long(), torch.from_numpy(aux).double()
+    loss, ntok, g, acts = O.loss_and_grads(ocfg, P, xt, None, yt, aux_targets=at)
+    out = {"x": x, "lens": lens, "y": y, "aux": aux, "loss": np.float64(loss), "ntok": np.int64(ntok),
+           "decoder_loss": np.float64(acts["decoder_loss"]), "aux_loss": np.float64(acts["aux_loss"]),
+           "aux_frames": np.int64(acts["aux_frames"]),
+           "dx": O.input_gradients(ocfg, P, xt, None, yt, aux_targets=at).numpy()}
+    for k, v in P32.items():
+        out["P|" + k.replace("/", "|")] = v.numpy()
+    for k, v in g.items():
+        out["G|" + k.replace("/", "|")] = v.numpy()
+    toks, logp, _ = O.greedy_decode(ocfg, P, xt, None, max_len=6, temperature=0.7)
+    out["greedy_tokens"], out["greedy_logp"] = toks.numpy(), logp.numpy()
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "seq2seq_tiny_optional.npz"), **out)
+    print("wrote seq2seq_tiny_optional.npz: loss", loss, "=", acts["decoder_loss"], "+", acts["aux_loss"])
 
 
 if __name__ == "__main__":

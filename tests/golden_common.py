@@ -42,3 +42,37 @@ def check_engine_against_golden(lib, backend="simt", tol=2e-4):
     assert np.abs(bs - z["beam_scores"]).max() < 5e-3
     assert (bt[:, 0] == z["beam_tokens"][:, 0]).all()
     eng.close()
+
+
+GOLD_OPT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "seq2seq_tiny_optional.npz")
+GEO_OPT = dict(pc.TINY_AUX, attention="bahdanau")
+
+
+def load_optional():
+    z = np.load(GOLD_OPT)
+    P = {k[2:].replace("|", "/"): z[k] for k in z.files if k.startswith("P|")}
+    return z, P
+
+
+def check_engine_against_optional_golden(lib, backend="simt", tol=2e-4):
+    """Encoder-targets head + Bahdanau attention + saliency against tests/golden/seq2seq_tiny_optional.npz."""
+    z, P = load_optional()
+    B, T, L = z["x"].shape[0], z["x"].shape[1], z["y"].shape[1]
+    eng = pc.engine_for(GEO_OPT, lib, B, T, 6, gemm_backend=backend)
+    eng.set_all(P)
+    eng.set_encoder_targets(z["aux"])
+    loss, ntok = eng.train_step_grads(z["x"], None, z["y"], seed=0)
+    ld, nt, la, nf = eng.last_losses()
+    assert ntok == int(z["ntok"]) and nf == int(z["aux_frames"])
+    for got, key in ((loss, "loss"), (ld, "decoder_loss"), (la, "aux_loss")):
+        assert abs(got - float(z[key])) <= tol * abs(float(z[key])), key
+    for k, v in eng.get_all(_lib.GRAD).items():
+        assert pc.rel_err(v, z["G|" + k.replace("/", "|")]) <= 5 * tol, k
+    eng.set_encoder_targets(z["aux"])
+    dx, sq = eng.input_saliency(z["x"], None, z["y"])
+    assert pc.rel_err(dx, z["dx"]) <= 5 * tol
+    assert pc.rel_err(sq, (z["dx"].astype(np.float64) ** 2).sum(1)) <= 10 * tol
+    toks, logp = eng.greedy_decode(z["x"], None, max_len=6, temperature=0.7)
+    assert (toks == z["greedy_tokens"]).all()
+    assert np.abs(logp - z["greedy_logp"]).max() < 2e-3
+    eng.close()

@@ -29,6 +29,21 @@ def test_emulated_engine_reproduces_golden_vectors(emu_lib):
     gc.check_engine_against_golden(emu_lib)
 
 
+def test_optional_rows_reproduce_golden_vectors(emu_lib):
+    """A6 + A7 (Bahdanau) + A13: the oracle (fp32) and the emulated engine against seq2seq_tiny_optional.npz (fp64)."""
+    z, P = gc.load_optional()
+    ocfg = O.OracleConfig(**gc.GEO_OPT)
+    Pt = {k: torch.from_numpy(v) for k, v in P.items()}
+    xt, yt, at = torch.from_numpy(z["x"]), torch.from_numpy(z["y"]).long(), torch.from_numpy(z["aux"])
+    loss, ntok, g, acts = O.loss_and_grads(ocfg, Pt, xt, None, yt, aux_targets=at)
+    assert ntok == int(z["ntok"]) and abs(loss - float(z["loss"])) < 1e-4 * abs(float(z["loss"]))
+    assert acts["aux_frames"] == int(z["aux_frames"])
+    for k, v in g.items():
+        assert pc.rel_err(v.numpy(), z["G|" + k.replace("/", "|")]) < 1e-4, k
+    assert pc.rel_err(O.input_gradients(ocfg, Pt, xt, None, yt, aux_targets=at).numpy(), z["dx"]) < 1e-4
+    gc.check_engine_against_optional_golden(emu_lib)
+
+
 def test_oracle_lstm_matches_torch_nn_lstm():
     """TF1 LSTMCell (gates i,j,f,o; forget_bias 1; kernel [In+H,4H]) == torch.nn.LSTM (gates i,f,g,o;
     weight_ih [4H,In]) after re-ordering: an implementation of the cell the oracle did not write."""

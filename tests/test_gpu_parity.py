@@ -95,6 +95,13 @@ def test_golden_vectors(gpu_lib, backend, tol):
     gc.check_engine_against_golden(gpu_lib, backend=backend, tol=tol)
 
 
+def test_optional_rows_golden_vectors(gpu_lib):
+    """A6 + A7 (Bahdanau) + A13 against tests/golden/seq2seq_tiny_optional.npz through the CUDA path."""
+    import golden_common as gc
+    gc.check_engine_against_optional_golden(gpu_lib, backend="simt")
+    gc.check_engine_against_optional_golden(gpu_lib, backend="auto")
+
+
 def test_sequence_network_fit_on_gpu(gpu_lib, tmp_path):
     """TFRecords -> SequenceNetwork.fit -> checkpoint -> restore_and_assess through libe2t.so (tensor-core path)."""
     from ecog2txt_b200 import SequenceNetwork
