@@ -137,7 +137,8 @@ def main():
     ap.add_argument("--cpu-baseline-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write the per-kernel event-time breakdown of a step to this file")
-    ap.add_argument("--decode", action="store_true", help="also report greedy / beam decode numbers")
+    ap.add_argument("--no-decode", action="store_true", help="skip the greedy / beam-8 decode legs")
+    ap.add_argument("--decode-utterances", type=int, default=10000, help="utterances decoded per leg, sharded over the ranks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -298,31 +299,71 @@ def main():
                                "algorithmic_bytes_per_launch": conv_bytes},
                 "whole_step_frac_of_tf32_peak": (fl["train"] * value / world / 1e12) / peak_tf32}
 
+    # ---- decode legs (BASELINE.json: greedy-decode ms/utterance; config 5: beam-8 throughput over 10 000 utterances sharded
+    # over the ranks).  Inference is embarrassingly parallel: rank r decodes its contiguous share, no collective on the data
+    # path; device-resident inputs from the same > L2 pool, CUDA-event time on the launching stream, max over ranks.
     decode = None
-    if args.decode and rank == 0:
-        x, _ = dev[0]
-        for _ in range(2):
-            eng.greedy_decode(x, None, max_len=20, want_logp=False)
-        t0 = time.perf_counter()
-        for _ in range(5):
-            eng.greedy_decode(x, None, max_len=20, want_logp=False)
-        g256 = (time.perf_counter() - t0) / 5
-        # online-predictor path (trainers.py:925-949): ONE host utterance in, tokens out, wall clock per call
-        x1 = np.ascontiguousarray(host[0][0][:1].numpy())
-        for _ in range(3):
-            eng.greedy_decode(x1, None, max_len=20, want_logp=False)
-        t0 = time.perf_counter()
-        for _ in range(20):
-            eng.greedy_decode(x1, None, max_len=20, want_logp=False)
-        g1 = (time.perf_counter() - t0) / 20
-        xb = x[:32].contiguous()
-        eng.beam_decode(xb, None, beam=8, max_len=20)
-        t0 = time.perf_counter()
-        for _ in range(3):
-            eng.beam_decode(xb, None, beam=8, max_len=20)
-        b8 = (time.perf_counter() - t0) / 3
-        decode = {"greedy_ms_per_utt_batch256": 1e3 * g256 / B, "greedy_ms_per_utt_batch1": 1e3 * g1, "batch1_graph_replays": eng.counter("decode_graph_replays"),
-                  "beam8_utt_per_s_batch32": 32 / b8}
+    if not args.no_decode:
+        from ecog2txt_b200.dist import shard_range
+        n_total = args.decode_utterances
+        lo, hi = shard_range(n_total, rank, world)
+        mine = hi - lo
+
+        def run_decode(beam, bsz, n_utt):
+            done, i = 0, 0
+            while done < n_utt:
+                n = min(bsz, n_utt - done)
+                x = dev[i % NPOOL][0]
+                xb = x if n == x.shape[0] else x[:n]
+                if beam:
+                    eng.beam_decode(xb, None, beam=beam, max_len=20)
+                else:
+                    eng.greedy_decode(xb, None, max_len=20, want_logp=False)
+                done += n
+                i += 1
+
+        def timed_decode(beam, bsz, n_utt):
+            run_decode(beam, bsz, min(2 * bsz, n_utt))          # warm-up
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            run_decode(beam, bsz, n_utt)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()) * 1e-3
+
+        t_greedy = timed_decode(0, B, mine)
+        # beam-8: pick the minibatch size on a short probe (same choice on every rank: rank 0's)
+        probe = {}
+        for bsz in sorted({min(32, B), min(128, B), B}):
+            try:
+                probe[bsz] = timed_decode(8, bsz, 2 * bsz) / (2 * bsz)
+            except Exception as e:   # a size the beam workspace cannot hold: skip it, keep the rest of the run
+                print(f"[bench] beam-8 probe at batch {bsz} failed: {e}", file=sys.stderr)
+        best = torch.tensor([min(probe, key=probe.get)], device="cuda")
+        if world > 1:
+            dist.broadcast(best, 0)
+        beam_bsz = int(best.item())
+        t_beam = timed_decode(8, beam_bsz, mine)
+        decode = {"utterances": n_total, "sharding": f"{world} x {mine} (contiguous shares, no collective)",
+                  "greedy_utt_per_s": n_total / t_greedy, "greedy_ms_per_utt": 1e3 * t_greedy / n_total, "greedy_batch": B,
+                  "beam8_utt_per_s": n_total / t_beam, "beam8_ms_per_utt": 1e3 * t_beam / n_total, "beam8_batch": beam_bsz,
+                  "beam8_probe_ms_per_utt": {str(k): 1e3 * v for k, v in probe.items()}, "max_len": 20}
+        if rank == 0:
+            # online-predictor path (trainers.py:925-949): ONE host utterance in, tokens out, wall clock per call
+            x1 = np.ascontiguousarray(host[0][0][:1].numpy())
+            for _ in range(3):
+                eng.greedy_decode(x1, None, max_len=20, want_logp=False)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                eng.greedy_decode(x1, None, max_len=20, want_logp=False)
+            decode["greedy_ms_per_utt_batch1_host"] = 1e3 * (time.perf_counter() - t0) / 20
+            decode["batch1_graph_replays"] = eng.counter("decode_graph_replays")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

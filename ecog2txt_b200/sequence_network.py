@@ -252,19 +252,27 @@ class SequenceNetwork:
                     prm.save_checkpoint(eng, self.checkpoint_path, epoch + 1)
         if self.checkpoint_path and rank == 0 and self.N_epochs % self.assessment_epoch_interval:
             prm.save_checkpoint(eng, self.checkpoint_path, start_epoch + self.N_epochs)
+        if world > 1:
+            dist.barrier()      # rank 0's checkpoint is complete before any rank goes on to restore it
         return assessments
 
     # -- assessment ----------------------------------------------------------------------------
     def _assess(self, eng, subnets_params, data, partition, max_T, max_L):
         """Decode (greedy if beam_width == 1, else beam) with the EMA weights; WER over the last subject's trials
         like the reference's assessor (one subnet's validation data, trainers.py:838-849)."""
+        import torch.distributed as dist
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
         s = subnets_params[-1]
         si = len(subnets_params) - 1
         examples = data[s.subnet_id][partition]
         pad_id, eos_id = eng.cfg.pad_id, eng.cfg.eos_id
         refs, hyps, n_ok, n_tok = [], [], 0, 0
         Lh = max(self.max_hyp_length, max_L)
-        for i in range(0, len(examples), self.N_cases):
+        # inference is embarrassingly parallel over utterances (SURVEY.md 8e): rank r decodes every world-th minibatch,
+        # the decoded strings are gathered at the end (no collective on the data path)
+        for bi, i in enumerate(range(0, len(examples), self.N_cases)):
+            if bi % world != rank:
+                continue
             idx = np.arange(i, min(i + self.N_cases, len(examples)))
             x, y = self._batch(examples, idx, max_T, max_L, pad_id)
             if int(self.beam_width) > 1:
@@ -280,6 +288,19 @@ class SequenceNetwork:
                 m = y[r] != pad_id
                 n_ok += int((toks[r, 0, :max_L][m] == y[r][m]).sum())
                 n_tok += int(m.sum())
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, (refs, hyps, n_ok, n_tok))
+            # rank-major order -> original minibatch order (rank r holds minibatches r, r + world, ...)
+            nb = -(-len(examples) // self.N_cases)
+            refs, hyps, cursor = [], [], [0] * world
+            for bi in range(nb):
+                r = bi % world
+                n = min(self.N_cases, len(examples) - bi * self.N_cases)
+                refs += parts[r][0][cursor[r]:cursor[r] + n]
+                hyps += parts[r][1][cursor[r]:cursor[r] + n]
+                cursor[r] += n
+            n_ok, n_tok = sum(p[2] for p in parts), sum(p[3] for p in parts)
         wers = wer_vector(refs, hyps) if refs else np.zeros(0)
         return SimpleNamespace(word_error_rate=float(wers.mean()) if len(wers) else float('nan'),
                                accuracy=n_ok / max(n_tok, 1), references=refs, hypotheses=hyps,

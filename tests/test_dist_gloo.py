@@ -78,3 +78,52 @@ def test_two_rank_step_equals_single_process(tmp_path, emu_lib):
         assert np.allclose(r0["G|" + kk], G[k], rtol=1e-5, atol=1e-6), k   # summed shard grads == full-batch grads
         assert np.allclose(r0[kk], W[k], rtol=1e-5, atol=1e-6), k
     eng.close()
+
+
+def _fit_worker(rank, world, port, tmp):
+    import ctypes
+    import pickle
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    import __graft_entry__ as ge
+    from ecog2txt_b200 import SequenceNetwork, _lib
+    from test_sequence_network import MANIFEST, _subject
+    from pathlib import Path
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = _lib.bind(ctypes.CDLL(ge.EMU_LIB))
+    s = _subject(Path(tmp))                      # TFRecords were written by the parent
+    m = dict(MANIFEST, N_epochs=10, assessment_epoch_interval=10)
+    net = SequenceNetwork(m, VERBOSE=False, N_cases=4, max_hyp_length=5, learning_rate=2e-2, lib=lib, gemm_backend="simt")
+    net.checkpoint_path = os.path.join(tmp, "ckpt", "model.ckpt")
+    a = net.fit([s])
+    res = net.restore_and_assess([s], 10)        # sharded decode: every rank ends up with every hypothesis
+    with open(os.path.join(tmp, f"fit_rank{rank}.pkl"), "wb") as f:
+        pickle.dump({"wer": a["training"].decoder_word_error_rates, "acc": a["training"].decoder_accuracies,
+                     "hyps": res["training"].hypotheses, "refs": res["training"].references,
+                     "vwer": res["validation"].word_error_rate}, f)
+    dist.destroy_process_group()
+
+
+def test_two_rank_fit_and_sharded_assessment(tmp_path, emu_lib):
+    """SequenceNetwork.fit under torch.distributed (world 2, gloo): every minibatch sharded over the ranks, one all-reduce
+    per step; assessment decodes every world-th minibatch per rank and gathers the strings.  Both ranks must report the
+    same numbers, and the sharded assessment must equal a single-process assessment of the same checkpoint."""
+    import pickle
+    from ecog2txt_b200 import SequenceNetwork
+    from test_sequence_network import MANIFEST, _subject
+    s = _subject(tmp_path)
+    s.write_tf_records_maybe()
+    port = _free_port()
+    mp.spawn(_fit_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (pickle.load(open(tmp_path / f"fit_rank{r}.pkl", "rb")) for r in range(2))
+    assert np.array_equal(r0["wer"], r1["wer"]) and np.array_equal(r0["acc"], r1["acc"])
+    assert r0["hyps"] == r1["hyps"] and r0["refs"] == r1["refs"] and r0["vwer"] == r1["vwer"]
+    m = dict(MANIFEST, N_epochs=10, assessment_epoch_interval=10)
+    net = SequenceNetwork(m, VERBOSE=False, N_cases=4, max_hyp_length=5, lib=emu_lib, gemm_backend="simt")
+    net.checkpoint_path = str(tmp_path / "ckpt" / "model.ckpt")
+    res = net.restore_and_assess([s], 10)
+    assert res["training"].hypotheses == r0["hyps"] and res["training"].references == r0["refs"]
+    assert res["validation"].word_error_rate == r0["vwer"]
