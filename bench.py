@@ -137,6 +137,8 @@ def main():
     ap.add_argument("--cpu-baseline-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write the per-kernel event-time breakdown of a step to this file")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: one all-reduce after the backward pass instead of the "
+                                                             "bucketed all-reduce overlapped with it")
     ap.add_argument("--no-decode", action="store_true", help="skip the greedy / beam-8 decode legs")
     ap.add_argument("--decode-utterances", type=int, default=10000, help="utterances decoded per leg, sharded over the ranks")
     args = ap.parse_args()
@@ -178,18 +180,30 @@ def main():
         dev.append((hx.cuda(), hy.cuda()))
     ntok_t = torch.zeros(1, device="cuda")
 
+    # N > 1: the all-reduce of the 57 MB gradient buffer runs bucket by bucket on a side stream while the backward pass is still
+    # going (ecog2txt_b200/dist.py: BucketedAllReduce); the global token count stays on the device (e2t_adam_ema_step_dev),
+    # so the timed loop has no host synchronisation
+    from ecog2txt_b200.dist import BucketedAllReduce
+    ar = BucketedAllReduce(eng) if world > 1 and not args.no_overlap else None
+    ntok_dev = [(y != 0).sum().float().reshape(1) for _, y in dev]
+    ntok_cache = [float((hy != 0).sum()) for _, hy in host]
+
+    def reduce_and_step(ntok_local_t):
+        if world == 1:
+            eng.adam_ema_step_dev(ntok_local_t)
+            return
+        ntok_t.copy_(ntok_local_t)
+        if ar is not None:
+            ar.reduce_async(ntok_t)
+        else:
+            dist.all_reduce(grads)
+            dist.all_reduce(ntok_t)
+        eng.adam_ema_step_dev(ntok_t)
+
     def step_device(i):
         x, y = dev[i % NPOOL]
         eng.train_step_grads(x, None, y, seed=i, want_loss=False)
-        ntok = float((y != 0).sum()) if world == 1 else None
-        if world > 1:
-            ntok_t[0] = (y != 0).sum()
-            dist.all_reduce(grads)
-            dist.all_reduce(ntok_t)
-            ntok = float(ntok_t.item())
-        eng.adam_ema_step(1.0 / ntok)
-
-    ntok_cache = [float((hy != 0).sum()) for _, hy in host]
+        reduce_and_step(ntok_dev[i % NPOOL])
 
     staged = {"next": None}
 
@@ -202,13 +216,9 @@ def main():
         hx, hy = host[(i + 1) % NPOOL]
         eng.stage_inputs((i + 1) & 1, hx.numpy(), None, hy.numpy())
         staged["next"] = i + 1
-        loss, ntok = eng.train_step_grads_staged(i & 1, seed=i, want_loss=True)   # D2H loss, ntok
-        if world > 1:
-            ntok_t[0] = ntok
-            dist.all_reduce(grads)
-            dist.all_reduce(ntok_t)
-            ntok = float(ntok_t.item())
-        eng.adam_ema_step(1.0 / ntok)
+        eng.train_step_grads_staged(i & 1, seed=i, want_loss=False)
+        reduce_and_step(ntok_dev[i % NPOOL])
+        loss, ntok, _, _ = eng.last_losses()                                     # D2H loss, ntok (synchronises)
         return loss
 
     def timed(fn, steps, warmup):
@@ -381,7 +391,9 @@ def main():
             "config": {"workload": "config2: T=400 C=256 3x400 BiLSTM + 800 LSTM decoder V=1806, L=11, dropout .1/.5, "
                                    "Adam+EMA, per-GPU batch %d" % B,
                        "global_batch": B * world, "cache": "pool of 4 batches x 105 MB per rank (> 126 MB L2)",
-                       "parallelism": f"dp{world}", "gemm_backend": args.backend},
+                       "parallelism": f"dp{world}", "gemm_backend": args.backend,
+                       "allreduce": None if world == 1 else ("one flat NCCL all-reduce after the backward pass" if ar is None else
+                                                              f"{len(eng.grad_buckets())} buckets on a side stream, overlapped with the backward pass")},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(hx.numel() * 4 + hy.numel() * 4),
                     "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "tcgen05_launches_total": int(tc1),

@@ -29,7 +29,7 @@
 
 static thread_local std::string g_err;
 extern "C" const char* e2t_last_error(void) { return g_err.c_str(); }
-extern "C" int e2t_abi_version(void) { return 4; }
+extern "C" int e2t_abi_version(void) { return 5; }
 
 namespace {
 
@@ -105,6 +105,13 @@ struct e2t_handle {
   bool aux_ready = false, aux_ran = false;
   int aux_tgt_B = 0, aux_tgt_T = 0;
   float pen_dec = 1.f, pen_aux = 1.f;   // penalty scales in force (e2t_input_saliency overrides them for one call)
+  // gradient buckets (e2t_set_grad_buckets): flat ranges of G in the order the backward pass completes them
+  struct Bucket { i64 off, n; int ev; };
+  bool bucketed = false;
+  std::vector<Bucket> buckets;
+#ifndef E2T_EMU
+  std::vector<cudaEvent_t> bucket_ev;
+#endif
   // A13 saliency workspace (allocated on first use)
   float *sal_tmp = nullptr, *sal_dx = nullptr, *sal_sq = nullptr;
 
@@ -967,6 +974,27 @@ void lstm_layer_wgrads(e2t_handle* h, const float* in, int ld_in, int In, int H,
   if (d_in) gemm(h, dz, 4 * H, 1, K, 1, 4 * H, d_in, ld_din, (int)rows, In, 4 * H, nullptr, beta_din);
 }
 
+// Marks the flat range [off, off + n) of the gradient buffer as final: everything deferred so far (bias column sums,
+// gate-order un-permutes) is flushed and an event is recorded, so that a data-parallel caller can start all-reducing this
+// bucket on another stream while the rest of the backward pass runs (e2t_grad_bucket_*).  Without bucketing only the last
+// call of a step does anything.
+void bucket_done(e2t_handle* h, i64 off, i64 n, bool last) {
+  if (!h->bucketed && !last) return;
+  batch_flush(h);
+  if (!h->bucketed) { off = 0; n = h->n_params; }
+  if (n <= 0) return;
+  e2t_handle::Bucket b{off, n, (int)h->buckets.size()};
+#ifndef E2T_EMU
+  if ((size_t)b.ev >= h->bucket_ev.size()) {
+    cudaEvent_t e;
+    E2T_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->bucket_ev.push_back(e);
+  }
+  E2T_CHECK(cudaEventRecord(h->bucket_ev[b.ev], h->stream));
+#endif
+  h->buckets.push_back(b);
+}
+
 // train = false: the forward pass ran without dropout (saliency), possibly on the EMA weights
 void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, uint32_t seed, bool train = true) {
   const e2t_config& c = h->cfg;
@@ -977,6 +1005,9 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
   const int T2 = (int)cdiv(T, W);
   const i64 rows = (i64)L * B;
   E2T_CHECK(cudaMemsetAsync(G, 0, (size_t)h->n_params * sizeof(float), h->stream));
+  h->buckets.clear();
+  // flat order: [conv per subject | encoder layers 0.. | decoder embedding, decoder rnn, projection, attention | aux head]
+  const i64 tail_end = h->aux ? (c.aux_hidden > 0 ? h->aux_w1 : h->aux_w2) : h->n_params;
   // ---- projection: logits already hold dlogits
   const bool attn = c.attention != E2T_ATTN_NONE;
   const float* proj_in = attn ? h->at_ht : h->hdec;
@@ -1018,6 +1049,7 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
   LAUNCH(h, k_act_dropout_bwd, grid1(rows * c.D), dim3(256), 0, h->ddemb, h->demb, rows, c.D, h->Dp, c.emb_act, dpe);
   LAUNCH(h, k_embed_bwd, grid1(rows * c.D), dim3(256), 0, h->d_prev, h->ddemb, G + h->demb_w, rows, c.D, h->Dp);
   batch_colsum(h, h->ddemb, rows, c.D, h->Dp, G + h->demb_b);
+  bucket_done(h, h->demb_w, tail_end - h->demb_w, false);      // decoder embedding / rnn / projection / attention
   // ---- encoder, top layer first
   const int nl = c.n_enc_layers;
   for (int l = nl - 1; l >= 0; --l) {
@@ -1089,6 +1121,8 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
     // d_in [rows, In] = dz_fw Wx_fw^T + dz_bw Wx_bw^T in one pass (canonical K rows [In, 4H] are the K-major B operands)
     gemm2(h, Ly.gates[0], 4 * Ly.H, rec_ok ? Ly.KP[0] : P + Ly.K[0], 4 * Ly.H, 4 * Ly.H, Ly.gates[1], 4 * Ly.H,
           rec_ok ? Ly.KP[1] : P + Ly.K[1], 4 * Ly.H, 4 * Ly.H, d_in, ld_din, (int)((i64)T2 * B), Ly.In, nullptr, 0.f);
+    bucket_done(h, Ly.K[0], (l + 1 < nl ? h->enc[l + 1].K[0] : h->demb_w) - Ly.K[0], false);
+    if (h->aux && l == c.aux_layer) bucket_done(h, tail_end, h->n_params - tail_end, false);   // the head's tensors
   }
   // ---- temporal conv
   DropP dpc = make_drop(seed, E2T_STREAM_CONV, train ? c.ff_dropout : 0.f);
@@ -1096,7 +1130,9 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
          c.conv_act, dpc);
   gemm_conv(h, 2, in.x, h->d_lens, B, T, C, W, T2, h->dconv, c.E, 1, G + h->conv_w[subnet], c.E, c.E, nullptr, 0.f);
   batch_colsum(h, h->dconv, (i64)T2 * B, c.E, c.E, G + h->conv_b[subnet]);
-  batch_flush(h);    // every bias-gradient column sum and gate-order un-permute of the step: three launches
+  // every (remaining) bias-gradient column sum and gate-order un-permute of the step: three launches; the subject-private
+  // conv tensors are the last bucket (without bucketing: the only one, covering the whole buffer)
+  bucket_done(h, 0, h->enc[0].K[0], true);
 }
 
 void read_loss(e2t_handle* h, float* loss_sum, int32_t* ntok) {
@@ -1209,6 +1245,7 @@ extern "C" int e2t_destroy(e2t_handle* h) {
 #endif
   for (void* p : h->allocs) cudaFree(p);
 #ifndef E2T_EMU
+  for (cudaEvent_t e : h->bucket_ev) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) { if (h->st_ready[i]) cudaEventDestroy(h->st_ready[i]); if (h->st_done[i]) cudaEventDestroy(h->st_done[i]); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
 #endif
@@ -1335,8 +1372,19 @@ extern "C" int e2t_stage_inputs(e2t_handle* h, int slot, int subnet, const float
   API_END
 }
 
+static void adam_ema_step(e2t_handle* h, int subnet, float grad_scale, const float* count_dev);
 extern "C" int e2t_adam_ema_step(e2t_handle* h, int subnet, float grad_scale) {
   API_BEGIN NEED_H;
+  adam_ema_step(h, subnet, grad_scale, nullptr);
+  API_END
+}
+extern "C" int e2t_adam_ema_step_dev(e2t_handle* h, int subnet, const float* token_count_dev) {
+  API_BEGIN NEED_H;
+  E2T_REQUIRE(token_count_dev != nullptr, "token_count_dev is NULL");
+  adam_ema_step(h, subnet, 0.f, token_count_dev);
+  API_END
+}
+static void adam_ema_step(e2t_handle* h, int subnet, float grad_scale, const float* count_dev) {
   const e2t_config& c = h->cfg;
   h->step += 1;
   double t = (double)h->step;
@@ -1347,7 +1395,7 @@ extern "C" int e2t_adam_ema_step(e2t_handle* h, int subnet, float grad_scale) {
     if (start < 0) return;
     i64 n = end - start;
     LAUNCH(h, k_adam_ema, grid1(n), dim3(256), 0, h->P + start, h->G + start, h->M + start, h->Vv + start,
-           h->S + start, n, grad_scale, lr_t, c.beta1, c.beta2, c.eps, c.ema_decay);
+           h->S + start, n, grad_scale, lr_t, c.beta1, c.beta2, c.eps, c.ema_decay, count_dev);
     start = -1;
   };
   for (const TensorInfo& ti : h->tensors) {
@@ -1361,7 +1409,6 @@ extern "C" int e2t_adam_ema_step(e2t_handle* h, int subnet, float grad_scale) {
   flush();
   h->packed_dirty = true;
   E2T_CHECK(cudaGetLastError());
-  API_END
 }
 
 extern "C" int e2t_eval_loss(e2t_handle* h, int subnet, const float* x, const int32_t* lens, const int32_t* y, int loc,
@@ -1376,6 +1423,30 @@ extern "C" int e2t_eval_loss(e2t_handle* h, int subnet, const float* x, const in
   E2T_CHECK(cudaGetLastError());
   release_slot(h, loc);
   read_loss(h, loss_sum, ntok);
+  API_END
+}
+
+extern "C" int e2t_set_grad_buckets(e2t_handle* h, int on) {
+  API_BEGIN NEED_H;
+  h->bucketed = on != 0;
+  API_END
+}
+extern "C" int e2t_grad_bucket_count(e2t_handle* h) { return h ? (int)h->buckets.size() : -1; }
+extern "C" int e2t_grad_bucket_info(e2t_handle* h, int i, int64_t* offset, int64_t* n) {
+  API_BEGIN NEED_H;
+  E2T_REQUIRE(i >= 0 && i < (int)h->buckets.size(), "bucket index out of range");
+  if (offset) *offset = h->buckets[i].off;
+  if (n) *n = h->buckets[i].n;
+  API_END
+}
+extern "C" int e2t_grad_bucket_wait(e2t_handle* h, int i, void* cuda_stream) {
+  API_BEGIN NEED_H;
+  E2T_REQUIRE(i >= 0 && i < (int)h->buckets.size(), "bucket index out of range");
+#ifndef E2T_EMU
+  E2T_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(cuda_stream), h->bucket_ev[h->buckets[i].ev], 0));
+#else
+  (void)cuda_stream;
+#endif
   API_END
 }
 

@@ -668,10 +668,13 @@ __global__ void __launch_bounds__(256) k_colsum(const float* X, i64 rows, int N,
 // ------------------------------------------------------------------------------------------------
 // A10: TF1 Adam (lr_t folds the bias corrections) + ExponentialMovingAverage, fused, elementwise.
 // ------------------------------------------------------------------------------------------------
+// count_dev != NULL: the gradient scale is 1 / max(*count_dev, 1) (the global token count left on the device by the
+// data-parallel all-reduce), so that the host never has to read it back.
 __global__ void k_adam_ema(float* p, const float* g, float* m, float* v, float* s, i64 n, float grad_scale,
-                           float lr_t, float b1, float b2, float eps, float ema_decay) {
+                           float lr_t, float b1, float b2, float eps, float ema_decay, const float* count_dev) {
   i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (count_dev) grad_scale = 1.0f / fmaxf(*count_dev, 1.0f);
   float gi = g[i] * grad_scale;
   float mi = b1 * m[i] + (1.f - b1) * gi;
   float vi = b2 * v[i] + (1.f - b2) * gi * gi;

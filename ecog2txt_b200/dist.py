@@ -41,3 +41,49 @@ def allreduce_grads(engine, grads_tensor, ntok_local: float):
     dist.all_reduce(grads_tensor)
     dist.all_reduce(t)
     return float(t.item())
+
+
+class BucketedAllReduce:
+    """All-reduce of the gradient buffer bucket by bucket on a side stream, started while the backward pass of the same step
+    is still running (the library completes the buffer in flat ranges and records a CUDA event after each:
+    e2t_set_grad_buckets / e2t_grad_bucket_*).  The NCCL kernels run on the SMs the persistent recurrent kernels leave idle
+    (100 of 148), so only the last, small bucket (layer 0 + the conv) is exposed.
+
+        ar = BucketedAllReduce(engine)            # once; turns bucketing on
+        engine.train_step_grads(..., want_loss=False)    # enqueue only, no host sync
+        ntok_global = ar.reduce(ntok_device_tensor)       # enqueues the per-bucket all-reduces, joins the streams
+        engine.adam_ema_step(1 / ntok_global)
+    """
+
+    def __init__(self, engine):
+        import torch
+        self.engine = engine
+        self.grads = flat_tensor(engine, L.GRAD)
+        self.emulated = getattr(engine, "emulated", False)
+        self.comm = None if self.emulated else torch.cuda.Stream(device=self.grads.device)
+        engine.set_grad_buckets(True)
+
+    def reduce_async(self, ntok_t):
+        """Enqueue the per-bucket all-reduces (side stream, each waiting on its bucket's event) and the all-reduce of the
+        1-element float32 device tensor ntok_t (this rank's unmasked-token count, summed in place); the current stream then
+        waits for both.  Nothing synchronises with the host: follow with engine.adam_ema_step_dev(ntok_t)."""
+        import torch
+        import torch.distributed as dist
+        buckets = self.engine.grad_buckets()
+        if self.emulated:
+            for off, n in buckets:
+                dist.all_reduce(self.grads[off:off + n])
+            dist.all_reduce(ntok_t)
+            return
+        main = torch.cuda.current_stream(self.grads.device)
+        for i, (off, n) in enumerate(buckets):
+            self.engine.grad_bucket_wait(i, self.comm.cuda_stream)      # device-side wait on the bucket's event
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(self.grads[off:off + n])
+        main.wait_stream(self.comm)
+        dist.all_reduce(ntok_t)
+
+    def reduce(self, ntok_t):
+        """reduce_async + read the global token count back (host synchronisation)."""
+        self.reduce_async(ntok_t)
+        return float(ntok_t.item())

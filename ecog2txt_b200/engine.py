@@ -238,6 +238,22 @@ class Engine:
         self._ck(self._lib.e2t_train_step_grads(self._h, subnet, None, None, None, loc, B, T, Lk, seed & 0xFFFFFFFF, None, None))
         return None
 
+    def set_grad_buckets(self, on: bool):
+        """complete the gradient buffer bucket by bucket (with an event each) so that the all-reduce can overlap the backward"""
+        self._ck(self._lib.e2t_set_grad_buckets(self._h, int(bool(on))))
+
+    def grad_buckets(self) -> List[Tuple[int, int]]:
+        """[(offset, n)] flat ranges of E2T_GRAD in the order the most recent train_step_grads completes them"""
+        out = []
+        off, n = C.c_int64(), C.c_int64()
+        for i in range(self._lib.e2t_grad_bucket_count(self._h)):
+            self._ck(self._lib.e2t_grad_bucket_info(self._h, i, C.byref(off), C.byref(n)))
+            out.append((int(off.value), int(n.value)))
+        return out
+
+    def grad_bucket_wait(self, i: int, cuda_stream: int):
+        self._ck(self._lib.e2t_grad_bucket_wait(self._h, i, C.c_void_p(cuda_stream)))
+
     def set_encoder_targets(self, targets):
         """A6: encoder targets of the next train_step_grads / eval_loss / input_saliency call: float32 [B,T,aux_F]
         (gaussian) or int32 [B,T] (categorical), host (numpy) or device (torch.cuda)."""
@@ -271,6 +287,12 @@ class Engine:
 
     def adam_ema_step(self, grad_scale: float, subnet: int = -1):
         self._ck(self._lib.e2t_adam_ema_step(self._h, subnet, float(grad_scale)))
+
+    def adam_ema_step_dev(self, token_count, subnet: int = -1):
+        """Adam + EMA with grad_scale = 1 / max(token_count, 1) read on the device: `token_count` is a 1-element float32
+        device tensor (numpy in the emulation build), e.g. the all-reduced token count -- no host synchronisation."""
+        p, _ = _ptr(token_count)
+        self._ck(self._lib.e2t_adam_ema_step_dev(self._h, subnet, p))
 
     def eval_loss(self, x, lens, y, subnet: int = 0, use_ema: bool = False):
         px, pl, py, loc, B, T = self._inputs(x, lens, y)

@@ -137,6 +137,17 @@ int e2t_train_step_grads(e2t_handle* h, int subnet, const float* x, const int32_
  * subnet / B / T / L (x, lens, y arguments are then ignored).  Host buffers should be page-locked for the copy to overlap. */
 int e2t_stage_inputs(e2t_handle* h, int slot, int subnet, const float* x, const int32_t* lens,
                      const int32_t* y, int B, int T, int L);
+/* Gradient buckets: lets a data-parallel caller overlap the all-reduce with the backward pass.  With
+ * bucketing on, e2t_train_step_grads completes E2T_GRAD in flat ranges -- decoder-side tensors first, then the encoder layers
+ * top to bottom, the subject-private conv last -- and records a CUDA event after each (deferred bias sums / un-permutes are
+ * flushed per bucket: a few more small launches per step, so leave it off on one GPU).  After the call has returned (work
+ * enqueued, nothing synchronised): bucket i = [offset, offset + n) of the flat buffer, final once e2t_grad_bucket_wait's
+ * event has fired; buckets are disjoint, in completion order, and cover every tensor.  Off: one bucket = the whole buffer. */
+int e2t_set_grad_buckets(e2t_handle* h, int on);
+int e2t_grad_bucket_count(e2t_handle* h);
+int e2t_grad_bucket_info(e2t_handle* h, int i, int64_t* offset, int64_t* n);
+/* make `cuda_stream` (cudaStream_t as void*) wait on the device until bucket i of the most recent step is final */
+int e2t_grad_bucket_wait(e2t_handle* h, int i, void* cuda_stream);
 /* A6: encoder targets of the NEXT e2t_train_step_grads / e2t_eval_loss / e2t_input_saliency call (consumed by it):
  * float [B,T,aux_F] (E2T_AUX_GAUSSIAN) or int32 [B,T] (E2T_AUX_CATEGORICAL) at the input's frame rate, zero / pad-index
  * padded.  The library reverses them within the utterance length and keeps every W-th frame (trainers.py:791-795).
@@ -148,6 +159,9 @@ int e2t_last_losses(e2t_handle* h, float* decoder_sum, int32_t* ntok, float* aux
 /* Adam + EMA on the trainable tensors of `subnet` (private) and the shared ones, using
  * grad * grad_scale (1 / global token count).  subnet < 0: every subnet. */
 int e2t_adam_ema_step(e2t_handle* h, int subnet, float grad_scale);
+/* same with grad_scale = 1 / max(*token_count_dev, 1) read on the device (fp32 scalar in device memory, e.g. the all-reduced
+ * token count): no host read-back between the backward pass and the optimiser */
+int e2t_adam_ema_step_dev(e2t_handle* h, int subnet, const float* token_count_dev);
 /* forward only (assessment loss): same inputs, no dropout, weights = value or EMA */
 int e2t_eval_loss(e2t_handle* h, int subnet, const float* x, const int32_t* lens, const int32_t* y,
                   int loc, int B, int T, int L, int use_ema, float* loss_sum, int32_t* ntok);

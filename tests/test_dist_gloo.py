@@ -42,8 +42,19 @@ def _worker(rank, world, port, out_dir):
     lo, hi = shard_range(B, rank, world)
     loss, ntok = eng.train_step_grads(np.ascontiguousarray(x[lo:hi]), None, np.ascontiguousarray(y[lo:hi]), seed=0)
     g = flat_tensor(eng, _lib.GRAD)
-    ntok_g = allreduce_grads(eng, g, float(ntok))
-    eng.adam_ema_step(1.0 / ntok_g)
+    if os.environ.get("E2T_TEST_BUCKETED") == "1":
+        # bucket-by-bucket all-reduce (sequential here: no streams in the emulation) + token count kept in "device" memory
+        from ecog2txt_b200.dist import BucketedAllReduce
+        ar = BucketedAllReduce(eng)
+        eng.train_step_grads(np.ascontiguousarray(x[lo:hi]), None, np.ascontiguousarray(y[lo:hi]), seed=0)   # bucketing now on
+        assert len(eng.grad_buckets()) == 1 + len(geo["H"]) + 1
+        nt = torch.tensor([float(ntok)], dtype=torch.float32)
+        ar.reduce_async(nt)
+        ntok_g = float(nt.item())
+        eng.adam_ema_step_dev(nt.numpy())
+    else:
+        ntok_g = allreduce_grads(eng, g, float(ntok))
+        eng.adam_ema_step(1.0 / ntok_g)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ntok=ntok_g, lo=lo, hi=hi,
              **{k.replace("/", "|"): v for k, v in eng.get_all(_lib.VALUE).items()},
              **{"G|" + k.replace("/", "|"): v for k, v in eng.get_all(_lib.GRAD).items()})
@@ -51,7 +62,9 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_step_equals_single_process(tmp_path, emu_lib):
+@pytest.mark.parametrize("bucketed", ["0", "1"])
+def test_two_rank_step_equals_single_process(tmp_path, emu_lib, bucketed, monkeypatch):
+    monkeypatch.setenv("E2T_TEST_BUCKETED", bucketed)
     from ecog2txt_b200 import _lib
     from ecog2txt_b200.dist import shard_range
     from oracle import seq2seq_oracle as O

@@ -340,3 +340,42 @@ def test_full_size_saliency_and_encoder_targets(gpu_lib):
     assert abs(fd - g_dir) <= 5e-2 * abs(g_dir), (fd, g_dir)
     eng_s.close()
     eng.close()
+
+
+def test_gradient_buckets_and_device_side_scale(gpu_lib):
+    """e2t_set_grad_buckets on the tensor-core path (WIDE: persistent recurrent kernels, permuted gate order un-permuted per
+    bucket): bit-identical gradients, buckets cover the buffer, a side stream can wait on every bucket event; and
+    e2t_adam_ema_step_dev (token count read on the device) updates exactly like the host-scale call."""
+    from oracle import seq2seq_oracle as O
+    ocfg = O.OracleConfig(**pc.WIDE)
+    P = pc.make_params(ocfg)
+    x, lens, y = pc.make_batch(ocfg, 64, 80, 5)
+    ntok_ref = int((y != 0).sum())
+    out = []
+    for on in (False, True):
+        eng = pc.engine_for(pc.WIDE, gpu_lib, 64, 80, 5, gemm_backend="auto", ff_dropout=0.1, rnn_dropout=0.5)
+        eng.set_all({k: v.numpy() for k, v in P.items()})
+        eng.set_grad_buckets(on)
+        loss, ntok = eng.train_step_grads(x, None, y, seed=1)
+        assert ntok == ntok_ref
+        side = torch.cuda.Stream()
+        b = eng.grad_buckets()
+        for i in range(len(b)):
+            eng.grad_bucket_wait(i, side.cuda_stream)
+        side.synchronize()
+        g = eng.get_all(_lib.GRAD)
+        if on:
+            eng.adam_ema_step_dev(torch.tensor([float(ntok)], device="cuda"))
+        else:
+            eng.adam_ema_step(1.0 / ntok)
+        out.append((loss, g, eng.get_all(_lib.VALUE), eng.get_all(_lib.EMA), b, eng.flat_buffer(_lib.GRAD)[1]))
+        eng.close()
+    (l0, g0, w0, s0, b0, total), (l1, g1, w1, s1, b1, _) = out
+    assert l0 == l1 and b0 == [(0, total)]
+    assert len(b1) == 1 + 2 + 1 and sum(n for _, n in b1) == total
+    for k in g0:
+        if "decoder_embedding" in k and k.endswith("weights"):
+            assert pc.rel_err(g1[k], g0[k]) < 1e-5      # atomicAdd scatter: order-dependent rounding
+            continue
+        assert np.array_equal(g0[k], g1[k]), k
+        assert np.allclose(w0[k], w1[k], rtol=1e-6, atol=1e-8) and np.allclose(s0[k], s1[k], rtol=1e-6, atol=1e-8), k

@@ -98,3 +98,38 @@ def test_input_saliency(emu_lib):
     pc.check_saliency(emu_lib, pc.TINY, 3, 19, 5)
     pc.check_saliency(emu_lib, pc.TINY_AUX, 3, 19, 5, which="aux")
     pc.check_saliency(emu_lib, pc.TINY_AUX_CAT, 4, 21, 5, which="decoder", use_ema=True)
+
+
+def test_gradient_buckets_cover_the_buffer_and_change_nothing(emu_lib):
+    """e2t_set_grad_buckets: the staged flush gives bit-identical gradients; the buckets are disjoint, cover every tensor and
+    come in completion order (decoder side, encoder layers top to bottom, head, conv)."""
+    import numpy as np
+    from ecog2txt_b200 import _lib
+    from oracle import seq2seq_oracle as O
+    geo = dict(pc.TINY_AUX, attention="luong")
+    ocfg = O.OracleConfig(**geo)
+    P = pc.make_params(ocfg)
+    x, lens, y = pc.make_batch(ocfg, 3, 19, 5)
+    aux = pc.make_aux_targets(ocfg, lens, 19)
+    grads, buckets = [], []
+    for on in (False, True):
+        eng = pc.engine_for(geo, emu_lib, 3, 19, 5, gemm_backend="simt", ff_dropout=0.1, rnn_dropout=0.5)
+        eng.set_all({k: v.numpy() for k, v in P.items()})
+        eng.set_grad_buckets(on)
+        eng.set_encoder_targets(aux)
+        eng.train_step_grads(x, None, y, seed=3)
+        grads.append(eng.get_all(_lib.GRAD))
+        buckets.append(eng.grad_buckets())
+        total, tensors = eng.flat_buffer(_lib.GRAD)[1], eng.tensors()
+        eng.close()
+    for k in grads[0]:
+        assert np.array_equal(grads[0][k], grads[1][k]), k
+    assert buckets[0] == [(0, total)]
+    b = buckets[1]
+    assert len(b) == 1 + 2 + 1 + 1                      # decoder side, 2 encoder layers, head, conv
+    assert sorted(b)[0][0] == 0 and sum(n for _, n in b) == total
+    ends = sorted((o, o + n) for o, n in b)
+    assert all(ends[i][1] == ends[i + 1][0] for i in range(len(ends) - 1))
+    name_at = {off: name for name, (_, off) in tensors.items()}
+    assert "decoder_embedding" in name_at[b[0][0]] and "encoder_rnn_1" in name_at[b[1][0]]
+    assert "encoder_1_projection" in name_at[b[2][0]] and "encoder_rnn_0" in name_at[b[3][0]] and b[4][0] == 0
