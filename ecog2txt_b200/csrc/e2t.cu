@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -205,13 +206,14 @@ struct CatScope {
   ~CatScope() { h->cat = old; }
 };
 
-#define LAUNCH(h, kern, grid, block, smem, ...)                       \
+#define LAUNCH_L(h, label, kern, grid, block, smem, ...)               \
   do {                                                                \
-    prof_begin(h, #kern);                                             \
+    prof_begin(h, label);                                             \
     E2T_LAUNCH(kern, grid, block, smem, (h)->stream, __VA_ARGS__);    \
     prof_end(h);                                                      \
     ++(h)->n_launch;                                                  \
   } while (0)
+#define LAUNCH(h, kern, grid, block, smem, ...) LAUNCH_L(h, #kern, kern, grid, block, smem, __VA_ARGS__)
 
 inline dim3 grid1(i64 n, int block = 256) { return dim3((unsigned)cdiv(n, block)); }
 
@@ -794,6 +796,63 @@ void encoder_forward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, 
   h->last_B = B; h->last_T2 = T2; h->last_subnet = subnet;
 }
 
+// warp-per-row attention kernels need the feature vector in a warp's registers; E2T_ATTN_BLOCK forces the general kernels (tests)
+bool attn_warp_kernels(e2t_handle* h) { return h->cfg.Hd <= 32 * kAttnNF && getenv("E2T_ATTN_BLOCK") == nullptr; }
+
+// encoder rows staged per sweep: as many as fit ~110 KB of shared memory (two blocks per SM), at most the whole utterance
+int attn_tile_rows(e2t_handle* h, int T2) {
+  int by_smem = (int)((110 * 1024) / ((size_t)h->cfg.Hd * sizeof(float)));
+  if (const char* e = getenv("E2T_ATTN_TILE_ROWS")) by_smem = std::max(1, atoi(e));   // tests: force the multi-chunk sweeps
+  return std::max(1, std::min(T2, by_smem));
+}
+size_t attn_smem_bytes(e2t_handle* h, int SC, int nw, int T2) {
+  const size_t bytes = ((size_t)SC * h->cfg.Hd + (size_t)nw * T2) * sizeof(float);
+  if (bytes > (size_t)200 * 1024) throw std::runtime_error("e2t: attention score buffer exceeds shared memory (T' too large)");
+  return bytes;
+}
+template <typename K>
+K attn_prepare(K kfn) {   // opt in to > 48 KB of dynamic shared memory, once per instantiation
+#ifndef E2T_EMU
+  static std::set<const void*> seen;
+  if (seen.insert(reinterpret_cast<const void*>(kfn)).second)
+    E2T_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+#endif
+  return kfn;
+}
+// instantiations: exact feature counts F = 32 * NF of the shipped geometries (Hd = 800 -> 25; 128, 256, 512, 1024) without
+// bounds checks, everything else through the guarded generic version
+#define E2T_ATTN_DISPATCH(KERN, BAH, F, CALL)                                             \
+  do {                                                                                    \
+    switch ((F) % 32 == 0 ? (F) / 32 : 0) {                                               \
+      case 4:  { auto kfn = attn_prepare(KERN<4, true, BAH>); CALL; } break;              \
+      case 8:  { auto kfn = attn_prepare(KERN<8, true, BAH>); CALL; } break;              \
+      case 16: { auto kfn = attn_prepare(KERN<16, true, BAH>); CALL; } break;             \
+      case 25: { auto kfn = attn_prepare(KERN<25, true, BAH>); CALL; } break;             \
+      case 32: { auto kfn = attn_prepare(KERN<32, true, BAH>); CALL; } break;             \
+      default: { auto kfn = attn_prepare(KERN<kAttnNF, false, BAH>); CALL; } break;       \
+    }                                                                                     \
+  } while (0)
+
+// A7: fused score / masked softmax / context for L * R decoder rows (rows r = k*R + j share the encoder outputs of
+// utterance j / bdiv): warp-per-row kernel when the feature vector fits a warp's registers, block-per-row otherwise
+void attn_forward(e2t_handle* h, const float* q, const float* enc, float* alpha, float* ctx, int R, int Benc, int bdiv, int L,
+                  int T2, const float* kp, const float* v) {
+  const e2t_config& c = h->cfg;
+  if (attn_warp_kernels(h)) {
+    const int nw = std::max(1, std::min(16, L * bdiv));
+    const int SC = attn_tile_rows(h, T2);
+    const size_t smem = attn_smem_bytes(h, SC, nw, T2);
+#define E2T_CALL_ LAUNCH_L(h, "k_attn_fwd_w", kfn, dim3((unsigned)Benc), dim3(32 * nw), smem, q, enc, h->d_lens2, alpha, ctx, R, Benc, bdiv, L, T2, \
+                         c.Hd, h->T2m, kp, v, SC)
+    if (kp) E2T_ATTN_DISPATCH(k_attn_fwd_w, true, c.Hd, E2T_CALL_);
+    else E2T_ATTN_DISPATCH(k_attn_fwd_w, false, c.Hd, E2T_CALL_);
+#undef E2T_CALL_
+  } else {
+    LAUNCH(h, k_attn_fwd, dim3((unsigned)(L * R)), dim3(128), (size_t)T2 * sizeof(float), q, enc, h->d_lens2, alpha, ctx, R,
+           Benc, bdiv, T2, c.Hd, h->T2m, kp, v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // decoder forward, teacher forced (A8-A9)
 // ------------------------------------------------------------------------------------------------
@@ -815,8 +874,8 @@ void decoder_forward(e2t_handle* h, const Inputs& in, int B, int L, bool train, 
     const int T2 = h->last_T2;
     gemm(h, h->hdec, c.Hd, 1, Wc + h->at_wq, 1, c.Hd, h->at_q, c.Hd, (int)rows, c.Hd, c.Hd, nullptr, 0.f);
     const bool bah = c.attention == E2T_ATTN_BAHDANAU;
-    LAUNCH(h, k_attn_fwd, dim3((unsigned)rows), dim3(128), (size_t)T2 * sizeof(float), h->at_q, top.hs, h->d_lens2,
-           h->at_alpha, h->at_ctx, B, B, 1, T2, c.Hd, h->T2m, bah ? h->at_kp : nullptr, bah ? Wc + h->at_v : nullptr);
+    attn_forward(h, h->at_q, top.hs, h->at_alpha, h->at_ctx, /*R=*/B, /*Benc=*/B, /*bdiv=*/1, /*L=*/L, T2,
+                 bah ? h->at_kp : nullptr, bah ? Wc + h->at_v : nullptr);
     gemm2(h, h->at_ctx, c.Hd, Wc + h->at_wc, 2 * c.Hd, c.Hd, h->hdec, c.Hd, Wc + h->at_wc + c.Hd, 2 * c.Hd, c.Hd, h->at_ht,
           c.Hd, (int)rows, c.Hd, Wc + h->at_bc, 0.f);
     LAUNCH(h, k_tanh_fwd, grid1(rows * c.Hd), dim3(256), 0, h->at_ht, rows * c.Hd);
@@ -1025,9 +1084,21 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
     // dctx = dpre Wc[:, :Hd]
     gemm(h, h->at_dht, c.Hd, 1, h->at_combT, 1, c.Hd, h->at_dctx, c.Hd, (int)rows, c.Hd, c.Hd, nullptr, 0.f);
     const bool bah = c.attention == E2T_ATTN_BAHDANAU;
-    LAUNCH(h, k_attn_bwd_q, dim3((unsigned)rows), dim3(128), (size_t)T2 * sizeof(float), h->at_dctx, top.hs, h->d_lens2,
-           h->at_alpha, h->at_dscore, h->at_dq, B, B, T2, c.Hd, h->T2m, bah ? h->at_kp : nullptr, bah ? P + h->at_v : nullptr,
-           h->at_q, h->at_dvrow);
+    if (attn_warp_kernels(h)) {
+      const int nw = std::max(1, std::min(16, L));
+      const int SC = attn_tile_rows(h, T2);
+      const size_t smem = attn_smem_bytes(h, SC, nw, T2);
+#define E2T_CALL_ LAUNCH_L(h, "k_attn_bwd_q_w", kfn, dim3((unsigned)B), dim3(32 * nw), smem, h->at_dctx, top.hs, h->d_lens2, h->at_alpha, h->at_dscore, \
+                         h->at_dq, B, B, L, T2, c.Hd, h->T2m, bah ? h->at_kp : nullptr, bah ? P + h->at_v : nullptr, h->at_q,         \
+                         h->at_dvrow, SC)
+      if (bah) E2T_ATTN_DISPATCH(k_attn_bwd_q_w, true, c.Hd, E2T_CALL_);
+      else E2T_ATTN_DISPATCH(k_attn_bwd_q_w, false, c.Hd, E2T_CALL_);
+#undef E2T_CALL_
+    } else {
+      LAUNCH(h, k_attn_bwd_q, dim3((unsigned)rows), dim3(128), (size_t)T2 * sizeof(float), h->at_dctx, top.hs, h->d_lens2,
+             h->at_alpha, h->at_dscore, h->at_dq, B, B, T2, c.Hd, h->T2m, bah ? h->at_kp : nullptr, bah ? P + h->at_v : nullptr,
+             h->at_q, h->at_dvrow);
+    }
     if (bah) batch_colsum(h, h->at_dvrow, rows, c.Hd, c.Hd, G + h->at_v);
     // dWq [Hd, Hd] = dq^T hdec
     gemm(h, h->at_dq, 1, c.Hd, h->hdec, c.Hd, 1, G + h->at_wq, c.Hd, c.Hd, c.Hd, (int)rows, nullptr, 0.f);
@@ -1166,8 +1237,8 @@ void decode_step(e2t_handle* h, int rows, const int* prev, const float* h_in, co
     const int T2 = h->last_T2;
     gemm(h, h_out, c.Hd, 1, Wc + h->at_wq, 1, c.Hd, h->g_q, c.Hd, rows, c.Hd, c.Hd, nullptr, 0.f);
     const bool bah = c.attention == E2T_ATTN_BAHDANAU;
-    LAUNCH(h, k_attn_fwd, dim3((unsigned)rows), dim3(128), (size_t)T2 * sizeof(float), h->g_q, top.hs, h->d_lens2,
-           h->g_alpha, h->g_ctx, rows, B, beam, T2, c.Hd, h->T2m, bah ? h->at_kp : nullptr, bah ? Wc + h->at_v : nullptr);
+    attn_forward(h, h->g_q, top.hs, h->g_alpha, h->g_ctx, /*R=*/rows, /*Benc=*/B, /*bdiv=*/beam, /*L=*/1, T2,
+                 bah ? h->at_kp : nullptr, bah ? Wc + h->at_v : nullptr);
     gemm2(h, h->g_ctx, c.Hd, Wc + h->at_wc, 2 * c.Hd, c.Hd, h_out, c.Hd, Wc + h->at_wc + c.Hd, 2 * c.Hd, c.Hd, h->g_ht, c.Hd,
           rows, c.Hd, Wc + h->at_bc, 0.f);
     LAUNCH(h, k_tanh_fwd, grid1((i64)rows * c.Hd), dim3(256), 0, h->g_ht, (i64)rows * c.Hd);

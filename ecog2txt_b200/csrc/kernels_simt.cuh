@@ -394,6 +394,266 @@ k_attn_bwd_q(const float* __restrict__ dctx, const float* __restrict__ enc, cons
     dq[(i64)r * F + u] = a;
   }
 }
+// ---- block-per-utterance versions (F <= 32 * kAttnNF) ----------------------------------------------------------------
+// One block per utterance b, one warp per decoder row of that utterance (its L teacher-forced steps, or its beams).  The
+// encoder rows (or the projected keys) of the utterance are staged ONCE per sweep in shared memory, SC rows at a time, and
+// every warp consumes them from there: L2 traffic drops from rows x T2 x F to B x T2 x F per sweep (measured at config 2:
+// the row-per-block kernels move 614 MB per launch through L2, 215 us).  A lane keeps its F/32 query / accumulator elements in
+// registers, dot products are warp-shuffle reductions, the T2 scores of a row live in that warp's slice of shared memory.
+// smem: [SC * F] tile + [warps * T2] scores.
+constexpr int kAttnNF = 32;          // register elements per lane -> F <= 1024
+__device__ __forceinline__ float attn_tanh(float x) {   // 1 - 2 / (1 + e^{2x}): saturates cleanly, ~1e-7 absolute error
+  return 1.0f - 2.0f * __fdividef(1.0f, 1.0f + __expf(2.0f * x));
+}
+// cooperative copy of rows [c0, c0 + n) of utterance b (time-major [T2, Benc, F]) into the tile
+// (four 16-byte loads in flight per thread before the first store: with one block of a dozen warps per SM a load -> store -> load
+// chain would expose one L2 latency per element -- measured 100 us per block)
+__device__ __forceinline__ void attn_stage(float* tile, const float* __restrict__ src, int c0, int n, int Benc, int b, int F) {
+  constexpr int UN = 4;
+  const int nt = blockDim.x;
+  if ((F & 3) == 0) {          // 16-byte rows
+    const int F4 = F >> 2, total = n * F4;
+    float4* t4 = reinterpret_cast<float4*>(tile);
+    for (int base = threadIdx.x; base < total; base += nt * UN) {
+      float4 val[UN];
+#pragma unroll
+      for (int j = 0; j < UN; ++j) {
+        const int i4 = base + j * nt;
+        if (i4 < total) {
+          const int rr = i4 / F4, cc = i4 - rr * F4;
+          val[j] = *reinterpret_cast<const float4*>(src + ((i64)(c0 + rr) * Benc + b) * F + 4 * cc);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < UN; ++j) {
+        const int i4 = base + j * nt;
+        if (i4 < total) t4[i4] = val[j];
+      }
+    }
+  } else {
+    const int total = n * F;
+    for (int base = threadIdx.x; base < total; base += nt * UN) {
+      float val[UN];
+#pragma unroll
+      for (int j = 0; j < UN; ++j) {
+        const int i = base + j * nt;
+        if (i < total) { const int rr = i / F, cc = i - rr * F; val[j] = src[((i64)(c0 + rr) * Benc + b) * F + cc]; }
+      }
+#pragma unroll
+      for (int j = 0; j < UN; ++j) {
+        const int i = base + j * nt;
+        if (i < total) tile[i] = val[j];
+      }
+    }
+  }
+}
+// NF = register elements per lane; EXACT: F == 32 * NF (no bounds checks, constant offsets -- the guarded generic version
+// executed 6x the instructions: 70.7 M warp instructions per launch at config 2, 220 us); BAH: additive (Bahdanau) score.
+#define E2T_ATTN_OK(i, u) (EXACT || ((i) < nf && (u) < F))
+template <int NF, bool EXACT, bool BAH>
+__global__ void __launch_bounds__(512)
+k_attn_fwd_w(const float* __restrict__ q, const float* __restrict__ enc, const int* __restrict__ lens2, float* alpha,
+             float* ctx, int R, int Benc, int bdiv, int L, int T2, int F_, int ld_alpha, const float* __restrict__ kp,
+             const float* __restrict__ v, int SC) {
+  E2T_DYN_SMEM(float, tile);               // [SC][F], then [warps][T2]
+  const int F = EXACT ? 32 * NF : F_;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int len = min(lens2[b], T2);
+  const int nf = (F + 31) >> 5;
+  (void)nf;
+  float* sc = tile + (size_t)SC * F + (size_t)warp * T2;
+  const float* src = BAH ? kp : enc;
+  const int n_rows = L * bdiv;
+  for (int g0 = 0; g0 < n_rows; g0 += nw) {
+    const int idx = g0 + warp;
+    const bool active = idx < n_rows;
+    const int k = idx / bdiv, jb = idx - k * bdiv;
+    const i64 r = (i64)k * R + (i64)b * bdiv + jb;
+    float reg[NF], vv[BAH ? NF : 1];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+      const int u = lane + 32 * i;
+      const bool ok = active && E2T_ATTN_OK(i, u);
+      reg[i] = ok ? q[r * F + u] : 0.f;
+      if (BAH) vv[i] = ok ? v[u] : 0.f;
+    }
+    // sweep 1: scores
+    for (int c0 = 0; c0 < len; c0 += SC) {
+      const int n = min(SC, len - c0);
+      __syncthreads();
+      attn_stage(tile, src, c0, n, Benc, b, F);
+      __syncthreads();
+      if (active) {
+        for (int s = 0; s < n; ++s) {
+          const float* er = tile + s * F + lane;
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < NF; ++i) {
+            if (E2T_ATTN_OK(i, lane + 32 * i)) {
+              const float t = BAH ? vv[i] * attn_tanh(reg[i] + er[32 * i]) : reg[i] * er[32 * i];
+              if (i & 1) a1 += t; else a0 += t;
+            }
+          }
+          const float a = warp_sum(a0 + a1);
+          if (lane == 0) sc[c0 + s] = a;
+        }
+      }
+    }
+    __syncwarp();
+    if (active) {
+      float m = -3.0e38f;
+      for (int s = lane; s < len; s += 32) m = fmaxf(m, sc[s]);
+      m = warp_max(m);
+      float z = 0.f;
+      for (int s = lane; s < len; s += 32) { const float e = expf(sc[s] - m); sc[s] = e; z += e; }
+      z = warp_sum(z);
+      const float inv = len > 0 ? 1.0f / z : 0.f;
+      for (int s = lane; s < T2; s += 32) {
+        const float pv = s < len ? sc[s] * inv : 0.f;
+        if (s < len) sc[s] = pv;
+        alpha[r * ld_alpha + s] = pv;
+      }
+    }
+    __syncwarp();
+    // sweep 2: context (the tile still holds the encoder rows when one chunk covers the utterance and no keys were staged)
+#pragma unroll
+    for (int i = 0; i < NF; ++i) reg[i] = 0.f;
+    const bool reuse = !BAH && len <= SC;
+    for (int c0 = 0; c0 < len; c0 += SC) {
+      const int n = min(SC, len - c0);
+      if (!reuse) {
+        __syncthreads();
+        attn_stage(tile, enc, c0, n, Benc, b, F);
+        __syncthreads();
+      }
+      if (active) {
+        for (int s = 0; s < n; ++s) {
+          const float* er = tile + s * F + lane;
+          const float pv = sc[c0 + s];
+#pragma unroll
+          for (int i = 0; i < NF; ++i)
+            if (E2T_ATTN_OK(i, lane + 32 * i)) reg[i] = fmaf(pv, er[32 * i], reg[i]);
+        }
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        const int u = lane + 32 * i;
+        if (E2T_ATTN_OK(i, u)) ctx[r * F + u] = reg[i];
+      }
+    }
+  }
+}
+// backward phase 1, same mapping (training only: bdiv = 1, rows r = k*B + b)
+template <int NF, bool EXACT, bool BAH>
+__global__ void __launch_bounds__(512)
+k_attn_bwd_q_w(const float* __restrict__ dctx, const float* __restrict__ enc, const int* __restrict__ lens2,
+               const float* __restrict__ alpha, float* dscore, float* dq, int R, int Benc, int L, int T2, int F_, int ld_alpha,
+               const float* __restrict__ kp, const float* __restrict__ v, const float* __restrict__ q, float* dvrow, int SC) {
+  E2T_DYN_SMEM(float, tile);               // [SC][F], then [warps][T2] dalpha -> dscore
+  const int F = EXACT ? 32 * NF : F_;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int len = min(lens2[b], T2);
+  const int nf = (F + 31) >> 5;
+  (void)nf;
+  float* sc = tile + (size_t)SC * F + (size_t)warp * T2;
+  for (int g0 = 0; g0 < L; g0 += nw) {
+    const int k = g0 + warp;
+    const bool active = k < L;
+    const i64 r = (i64)k * R + b;
+    const float* ar = alpha + r * ld_alpha;
+    float reg[NF];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+      const int u = lane + 32 * i;
+      reg[i] = (active && E2T_ATTN_OK(i, u)) ? dctx[r * F + u] : 0.f;
+    }
+    // sweep 1: dalpha[s] = dctx . enc[s]
+    for (int c0 = 0; c0 < len; c0 += SC) {
+      const int n = min(SC, len - c0);
+      __syncthreads();
+      attn_stage(tile, enc, c0, n, Benc, b, F);
+      __syncthreads();
+      if (active) {
+        for (int s = 0; s < n; ++s) {
+          const float* er = tile + s * F + lane;
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < NF; ++i) {
+            if (E2T_ATTN_OK(i, lane + 32 * i)) {
+              if (i & 1) a1 = fmaf(reg[i], er[32 * i], a1); else a0 = fmaf(reg[i], er[32 * i], a0);
+            }
+          }
+          const float a = warp_sum(a0 + a1);
+          if (lane == 0) sc[c0 + s] = a;
+        }
+      }
+    }
+    __syncwarp();
+    if (active) {
+      float t = 0.f;
+      for (int s = lane; s < len; s += 32) t = fmaf(ar[s], sc[s], t);
+      t = warp_sum(t);
+      for (int s = lane; s < T2; s += 32) {
+        const float dv = s < len ? ar[s] * (sc[s] - t) : 0.f;
+        if (s < len) sc[s] = dv;
+        dscore[r * ld_alpha + s] = dv;
+      }
+    }
+    __syncwarp();
+    // sweep 2: dq (Luong: over the encoder rows again; Bahdanau: over the keys, tanh recomputed)
+    float dvv[BAH ? NF : 1];
+    if (BAH) {
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        const int u = lane + 32 * i;
+        reg[i] = (active && E2T_ATTN_OK(i, u)) ? q[r * F + u] : 0.f;      // forward query
+        dvv[i] = 0.f;
+      }
+    }
+    float acc[NF];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) acc[i] = 0.f;
+    const bool reuse = !BAH && len <= SC;
+    for (int c0 = 0; c0 < len; c0 += SC) {
+      const int n = min(SC, len - c0);
+      if (!reuse) {
+        __syncthreads();
+        attn_stage(tile, BAH ? kp : enc, c0, n, Benc, b, F);
+        __syncthreads();
+      }
+      if (active) {
+        for (int s = 0; s < n; ++s) {
+          const float* er = tile + s * F + lane;
+          const float ds = sc[c0 + s];
+#pragma unroll
+          for (int i = 0; i < NF; ++i) {
+            if (E2T_ATTN_OK(i, lane + 32 * i)) {
+              if (BAH) {
+                const float th = attn_tanh(reg[i] + er[32 * i]);
+                acc[i] = fmaf(ds, 1.f - th * th, acc[i]);
+                dvv[i] = fmaf(ds, th, dvv[i]);
+              } else {
+                acc[i] = fmaf(ds, er[32 * i], acc[i]);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        const int u = lane + 32 * i;
+        if (E2T_ATTN_OK(i, u)) {
+          if (BAH) { dq[r * F + u] = acc[i] * v[u]; dvrow[r * F + u] = dvv[i]; }
+          else dq[r * F + u] = acc[i];
+        }
+      }
+    }
+  }
+}
 // backward, phase 2 (one block per utterance b; thread = feature u): denc[s,b,u] += sum_k alpha[k,b,s] dctx[k,b,u]
 // + dscore[k,b,s] q[k,b,u], the L decoder steps summed in order (deterministic, no atomics).
 // Bahdanau (kp != NULL): the score reaches the encoder through the keys instead:
@@ -412,25 +672,56 @@ k_attn_bwd_enc(const float* __restrict__ dctx, const float* __restrict__ q, cons
     sm[L * T2 + i] = dscore[((i64)k * B + b) * ld_alpha + s];
   }
   __syncthreads();
+  // the L (dctx, q) values of feature u stay in registers across the T2 encoder positions, KC decoder steps at a time
+  constexpr int KC = 12;
   for (int u = threadIdx.x; u < F; u += blockDim.x) {
     const float vu = kp ? v[u] : 0.f;
-    for (int s = 0; s < T2; ++s) {
-      const i64 e = ((i64)s * B + b) * F + u;
-      if (s >= len) { if (kp) dkp[e] = 0.f; continue; }
-      float a = 0.f, dk = 0.f;
-      const float kpv = kp ? kp[e] : 0.f;
-      for (int k = 0; k < L; ++k) {
-        const i64 row = ((i64)k * B + b) * F + u;
-        a = fmaf(sm[k * T2 + s], dctx[row], a);
-        if (kp) {
-          const float th = tanhf(q[row] + kpv);
-          dk = fmaf(sm[L * T2 + k * T2 + s] * vu, 1.f - th * th, dk);
-        } else {
-          a = fmaf(sm[L * T2 + k * T2 + s], q[row], a);
+    for (int k0 = 0; k0 < L; k0 += KC) {
+      float dc[KC], qq[KC];
+#pragma unroll
+      for (int kk = 0; kk < KC; ++kk) {
+        const bool ok = k0 + kk < L;
+        const i64 row = ((i64)(k0 + kk) * B + b) * F + u;
+        dc[kk] = ok ? dctx[row] : 0.f;
+        qq[kk] = ok ? q[row] : 0.f;
+      }
+      // eight encoder positions at a time: their denc / kp / dkp values are loaded together (independent loads in flight)
+      constexpr int SB = 8;
+      for (int s0 = 0; s0 < T2; s0 += SB) {
+        float old[SB], kpv[SB], okp[SB];
+#pragma unroll
+        for (int j = 0; j < SB; ++j) {
+          const int s = s0 + j;
+          const i64 e = ((i64)s * B + b) * F + u;
+          const bool in = s < len;
+          old[j] = in ? denc[e] : 0.f;
+          kpv[j] = (in && kp) ? kp[e] : 0.f;
+          okp[j] = (in && kp && k0 > 0) ? dkp[e] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < SB; ++j) {
+          const int s = s0 + j;
+          if (s >= T2) continue;
+          const i64 e = ((i64)s * B + b) * F + u;
+          if (s >= len) { if (kp && k0 == 0) dkp[e] = 0.f; continue; }
+          float a = 0.f, dk = 0.f;
+#pragma unroll
+          for (int kk = 0; kk < KC; ++kk) {
+            if (k0 + kk < L) {
+              a = fmaf(sm[(k0 + kk) * T2 + s], dc[kk], a);
+              const float ds = sm[L * T2 + (k0 + kk) * T2 + s];
+              if (kp) {
+                const float th = attn_tanh(qq[kk] + kpv[j]);
+                dk = fmaf(ds * vu, 1.f - th * th, dk);
+              } else {
+                a = fmaf(ds, qq[kk], a);
+              }
+            }
+          }
+          denc[e] = old[j] + a;
+          if (kp) dkp[e] = okp[j] + dk;
         }
       }
-      denc[e] += a;
-      if (kp) dkp[e] = dk;
     }
   }
 }

@@ -91,7 +91,9 @@ static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; ret
 static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 static inline int atomicMax(int* p, int v) { int o = *p; *p = std::max(o, v); return o; }
-// (__expf/__logf already exist in glibc with matching semantics)
+// fast-math intrinsics: plain libm here
+#define __expf(x) expf(x)
+#define __logf(x) logf(x)
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __ldg(const float* p) { return *p; }
 static inline int __ldg(const int* p) { return *p; }

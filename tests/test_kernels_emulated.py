@@ -133,3 +133,20 @@ def test_gradient_buckets_cover_the_buffer_and_change_nothing(emu_lib):
     name_at = {off: name for name, (_, off) in tensors.items()}
     assert "decoder_embedding" in name_at[b[0][0]] and "encoder_rnn_1" in name_at[b[1][0]]
     assert "encoder_1_projection" in name_at[b[2][0]] and "encoder_rnn_0" in name_at[b[3][0]] and b[4][0] == 0
+
+
+def test_attention_general_kernels(emu_lib, monkeypatch):
+    """the block-per-row attention kernels (used when the decoder is wider than a warp's registers hold: Hd > 1024)"""
+    monkeypatch.setenv("E2T_ATTN_BLOCK", "1")
+    pc.check_train_step(emu_lib, pc.TINY_ATTN, 3, 19, 5, ff=0.1, rnn=0.5)
+    pc.check_train_step(emu_lib, pc.TINY_BAH, 3, 19, 5)
+    pc.check_decode(emu_lib, pc.TINY_ATTN, 4, 21, 6, beam=4)
+
+
+def test_attention_multi_chunk_staging(emu_lib, monkeypatch):
+    """utterances longer than one shared-memory tile of encoder rows: the staged sweeps run chunk by chunk"""
+    monkeypatch.setenv("E2T_ATTN_TILE_ROWS", "2")
+    pc.check_train_step(emu_lib, pc.TINY_ATTN, 3, 19, 5, ff=0.1, rnn=0.5)
+    pc.check_train_step(emu_lib, pc.TINY_BAH, 3, 19, 5)
+    pc.check_decode(emu_lib, pc.TINY_ATTN, 6, 21, 6)
+    pc.check_decode(emu_lib, pc.TINY_BAH, 4, 21, 6, beam=4, margin=1e-4)

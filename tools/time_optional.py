@@ -57,4 +57,19 @@ for name, kw in (("plain", {}), ("aux_head_225_13", dict(aux_layer=1, aux_hidden
             eng.input_saliency(hx, None, hy, want_dx=False, want_norms=True)
         line += f"   saliency (host in, norms out) {timed(sal, 5):7.3f} ms"
     print(line, flush=True)
+    if "attention" in kw:
+        for env in ("", "1"):
+            if env:
+                os.environ["E2T_ATTN_BLOCK"] = "1"
+            else:
+                os.environ.pop("E2T_ATTN_BLOCK", None)
+            ms_v = timed(step, iters)
+            eng.profile_enable(True)
+            for _ in range(2):
+                step()
+            rep = eng.profile_report()
+            eng.profile_enable(False)
+            att = {k: round(1e3 * t / n, 1) for k, (n, t) in rep.items() if "attn" in k or "tanh" in k}
+            print(f"    {'block-per-row kernels' if env else 'warp-per-row kernels '}: step {ms_v:7.3f} ms; us/launch {att}", flush=True)
+        os.environ.pop("E2T_ATTN_BLOCK", None)
     eng.close()
