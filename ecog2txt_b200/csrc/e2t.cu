@@ -1142,7 +1142,8 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
       }
     } else if (rnn_drop) {
       DropP dp = make_drop(seed, E2T_STREAM_ENC0 + l, c.rnn_dropout);
-      LAUNCH(h, k_dropout_bwd, grid1(n_out), dim3(256), 0, Ly.dhs, n_out, dp);
+      if ((n_out & 3) == 0) LAUNCH(h, k_dropout_bwd4, grid1(n_out / 4), dim3(256), 0, reinterpret_cast<float4*>(Ly.dhs), n_out / 4, dp);
+      else LAUNCH(h, k_dropout_bwd, grid1(n_out), dim3(256), 0, Ly.dhs, n_out, dp);
     }
     if (h->aux_ran && l == c.aux_layer) aux_backward(h, B, T2, train, seed);
     const float* inp; int ld_in; float* d_in; int ld_din;
