@@ -86,8 +86,14 @@ def cpu_port_utt_per_s(B, steps, threads=None, warmup=1):
     import torch
     from oracle import seq2seq_oracle as O
     from ecog2txt_b200.synthetic import SyntheticCorpus, load_vocab
-    if threads:
-        torch.set_num_threads(threads)
+    # every host thread this process may use -- explicitly, because torchrun exports OMP_NUM_THREADS=1 to its workers and
+    # the CPU arm would otherwise run single-threaded under the N > 1 launch
+    if not threads:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
     ocfg = O.OracleConfig(**GEO)
     P = O.init_params(ocfg, 1)
     opt = O.AdamEMA(ocfg, P)
