@@ -385,10 +385,12 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v1, _, dt1 = cpu_port_utt_per_s(64, 1, threads=1, warmup=0)      # also a 1-thread figure
         v, cores, dt = cpu_port_utt_per_s(args.ref_batch, args.cpu_baseline_steps)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{args.cpu_baseline_steps} training steps of {args.ref_batch} utterances of the same workload "
-                         f"({dt:.2f} s/step; oracle = torch CPU fp32 port, reference TF1.15 path not runnable here)"}
+                         f"({dt:.2f} s/step; oracle = torch CPU fp32 port, reference TF1.15 path not runnable here)",
+               "value_1thread": v1, "sample_1thread": f"1 training step of 64 utterances on one thread ({dt1:.2f} s)"}
 
     if rank == 0:
         hx, hy = host[0]
