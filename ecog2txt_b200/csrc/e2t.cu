@@ -349,7 +349,10 @@ void batch_colsum(e2t_handle* h, const float* X, i64 rows, int N, int ld, float*
   if (rows >= 512 && h->colsum_pool_used + (i64)R * N <= h->colsum_pool_n) {
     float* ws = h->colsum_pool + h->colsum_pool_used;
     h->colsum_pool_used += (i64)R * N;
-    j.out = ws; j.ldo = N; j.flag = R; j.nblk = (int)cdiv(N, 32) * R;
+    // tall first pass: 16-byte loads when the rows are 16-byte aligned (K = 4 selects the 128-columns-per-block variant)
+    const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+    j.K = vec ? 4 : 0;
+    j.out = ws; j.ldo = N; j.flag = R; j.nblk = (int)cdiv(N, vec ? 128 : 32) * R;
     h->batch.push_back(j);
     BatchJob k{};
     k.type = E2T_JOB_COLSUM; k.in = ws; k.ldi = N; k.rows = R; k.N = N; k.out = out; k.ldo = 0; k.flag = 1; k.nblk = (int)cdiv(N, 32);

@@ -150,3 +150,10 @@ def test_attention_multi_chunk_staging(emu_lib, monkeypatch):
     pc.check_train_step(emu_lib, pc.TINY_BAH, 3, 19, 5)
     pc.check_decode(emu_lib, pc.TINY_ATTN, 6, 21, 6)
     pc.check_decode(emu_lib, pc.TINY_BAH, 4, 21, 6, beam=4, margin=1e-4)
+
+
+def test_tall_column_sums(emu_lib):
+    """T' * B >= 512 rows: the bias gradients go through the two-pass column sums, whose first pass reads 16 bytes per thread
+    where the rows are 16-byte aligned (full groups of 4 columns, ragged right edges, and the scalar variant for odd strides)"""
+    pc.check_train_step(emu_lib, pc.TINY_AUX, 40, 60, 5)
+    pc.check_train_step(emu_lib, pc.TINY_AUX_CAT, 36, 60, 5, ff=0.1, rnn=0.5)
