@@ -157,3 +157,39 @@ def test_tall_column_sums(emu_lib):
     where the rows are 16-byte aligned (full groups of 4 columns, ragged right edges, and the scalar variant for odd strides)"""
     pc.check_train_step(emu_lib, pc.TINY_AUX, 40, 60, 5)
     pc.check_train_step(emu_lib, pc.TINY_AUX_CAT, 36, 60, 5, ff=0.1, rnn=0.5)
+
+
+def test_api_error_paths(emu_lib):
+    """error behaviour of the optional entry points: every misuse is an int error code + message, never a crash"""
+    import numpy as np
+    import ctypes as C
+    from ecog2txt_b200 import E2TError
+    from oracle import seq2seq_oracle as O
+    ocfg = O.OracleConfig(**pc.TINY)
+    x, lens, y = pc.make_batch(ocfg, 3, 19, 5)
+    plain = pc.engine_for(pc.TINY, emu_lib, 3, 19, 5, gemm_backend="simt")
+    with pytest.raises(E2TError, match="no encoder-targets head"):
+        plain.set_encoder_targets(np.zeros((3, 19, 3), np.float32))
+    with pytest.raises(E2TError, match="bucket index"):
+        plain._ck(plain._lib.e2t_grad_bucket_info(plain._h, 0, None, None))          # no step has run yet
+    with pytest.raises(E2TError, match="NULL"):
+        plain._ck(plain._lib.e2t_adam_ema_step_dev(plain._h, -1, None))
+    with pytest.raises(E2TError, match="saliency needs decoder targets"):
+        plain._ck(plain._lib.e2t_input_saliency(plain._h, 0, x.ctypes.data_as(C.c_void_p), None, None, 0, 3, 19, 5, 0, 1.0, 0.0,
+                                                None, None))
+    with pytest.raises(E2TError, match="exceeds max_B"):
+        plain.input_saliency(np.zeros((4, 19, 6), np.float32), None, np.ones((4, 5), np.int32))
+    plain.close()
+    head = pc.engine_for(pc.TINY_AUX, emu_lib, 3, 19, 5, gemm_backend="simt")
+    with pytest.raises(TypeError):
+        head.set_encoder_targets(np.zeros((3, 19, 3), np.float64))                    # gaussian targets are float32
+    with pytest.raises(E2TError, match="exceed the capacities"):
+        head.set_encoder_targets(np.zeros((3, 40, 3), np.float32))
+    head.set_encoder_targets(np.zeros((2, 19, 3), np.float32))                         # set for B = 2 ...
+    with pytest.raises(E2TError, match="another batch shape"):
+        head.train_step_grads(x, None, y)                                              # ... consumed by a B = 3 step
+    head.close()
+    with pytest.raises(E2TError, match="aux_layer"):
+        pc.engine_for(dict(pc.TINY, aux_layer=5, aux_F=3), emu_lib, 3, 19, 5)
+    with pytest.raises(E2TError, match="categorical head"):
+        pc.engine_for(dict(pc.TINY, aux_layer=0, aux_F=1, aux_kind="categorical"), emu_lib, 3, 19, 5)
