@@ -1699,8 +1699,21 @@ extern "C" int e2t_beam_decode(e2t_handle* h, int subnet, const float* x, const 
   for (int k = 0; k < max_len; ++k) {
     int nxt = cur ^ 1;
     decode_step(h, R, h->g_prev[cur], h->g_h[cur], h->g_c[cur], h->g_h[nxt], h->g_c[nxt], B, beam);
-    LAUNCH(h, k_beam_topk, dim3(B), dim3(256), 0, h->g_logits, h->Vp, c.V, 1.0f / temperature, beam, h->g_score[cur],
-           h->g_done[cur], c.pad_id, h->g_lse, h->g_score[nxt], h->g_src, h->g_tok);
+    if (c.V <= 2048 && getenv("E2T_BEAM_BLOCK") == nullptr) {     // one pass, candidates in registers (E2T_BEAM_BLOCK: tests of the general kernel)
+      const int nwarp = std::min(8, beam);
+      if (c.V <= 256) {
+        auto kfn = k_beam_topk_w<8>;
+        LAUNCH_L(h, "k_beam_topk_w", kfn, dim3(B), dim3(32 * nwarp), 0, h->g_logits, h->Vp, c.V, 1.0f / temperature, beam,
+                 h->g_score[cur], h->g_done[cur], c.pad_id, h->g_score[nxt], h->g_src, h->g_tok);
+      } else {
+        auto kfn = k_beam_topk_w<64>;
+        LAUNCH_L(h, "k_beam_topk_w", kfn, dim3(B), dim3(32 * nwarp), 0, h->g_logits, h->Vp, c.V, 1.0f / temperature, beam,
+                 h->g_score[cur], h->g_done[cur], c.pad_id, h->g_score[nxt], h->g_src, h->g_tok);
+      }
+    } else {
+      LAUNCH(h, k_beam_topk, dim3(B), dim3(256), 0, h->g_logits, h->Vp, c.V, 1.0f / temperature, beam, h->g_score[cur],
+             h->g_done[cur], c.pad_id, h->g_lse, h->g_score[nxt], h->g_src, h->g_tok);
+    }
     BeamStepP p{};
     p.h_new = h->g_h[nxt]; p.c_new = h->g_c[nxt]; p.h_old = h->g_h[cur]; p.c_old = h->g_c[cur];
     p.h_out = h_re; p.c_out = c_re; p.Hd = c.Hd;

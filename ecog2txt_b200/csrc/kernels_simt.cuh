@@ -1253,6 +1253,94 @@ __global__ void __launch_bounds__(256) k_beam_topk(const float* logits, int ld, 
     tok_out[b * beam + n] = sel_flat[n] % V;
   }
 }
+// Same selection, one pass over the logits (V <= 32 * NV, beam <= 32): one WARP per beam row keeps the row's candidates
+// score[j] + log_softmax(logits/T)[v] in registers (NV per lane), finds the row's `beam` best by warp arg-max rounds
+// (score desc, flat index asc -- the same total order as above), and warp 0 merges the beam x beam survivors.  The
+// block-wide version above re-scans all beam x V candidates with two block reductions per selected beam: 114 us per decode
+// step at beam 8, V = 1806, 43 % of a beam-8 decode (profiles/r1u_decode_breakdown.txt).
+template <int NV>
+__global__ void __launch_bounds__(256) k_beam_topk_w(const float* __restrict__ logits, int ld, int V, float inv_temp, int beam,
+                                                     const float* __restrict__ score_in, const int* __restrict__ done_in,
+                                                     int pad_id, float* score_out, int* src_out, int* tok_out) {
+  __shared__ float cand_score[32 * 32];
+  __shared__ int cand_flat[32 * 32];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float NEG = -3.0e38f;
+  for (int j = warp; j < beam; j += nw) {
+    const int r = b * beam + j;
+    const float sc = score_in[r];
+    if (done_in[r]) {     // a finished beam contributes only (score, pad)
+      if (lane < beam) { cand_score[j * beam + lane] = lane == 0 ? sc : NEG; cand_flat[j * beam + lane] = j * V + pad_id + lane; }
+      continue;
+    }
+    const float* row = logits + (i64)r * ld;
+    float c[NV];
+    float mx = NEG;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      c[i] = v < V ? row[v] * inv_temp : NEG;
+      mx = fmaxf(mx, c[i]);
+    }
+    mx = warp_max(mx);
+    float se = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (lane + 32 * i < V) se += expf(c[i] - mx);
+    se = warp_sum(se);
+    const float off = sc - (mx + logf(se));
+#pragma unroll
+    for (int i = 0; i < NV; ++i) c[i] = (lane + 32 * i < V) ? c[i] + off : NEG;
+    for (int n = 0; n < beam; ++n) {
+      float best = NEG;
+      int bi = 0;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (c[i] > best) { best = c[i]; bi = i; }      // ascending i, strict >: lowest index on ties
+      int flat = j * V + lane + 32 * bi;
+      if (best == NEG) flat = 0x7fffffff;              // this lane has nothing left
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int of = __shfl_xor_sync(0xffffffffu, flat, o);
+        if (ob > best || (ob == best && of < flat)) { best = ob; flat = of; }
+      }
+      if (lane == 0) { cand_score[j * beam + n] = best; cand_flat[j * beam + n] = flat; }
+      const int loc = flat - j * V;                    // the owner removes the winner from its registers
+      if (flat != 0x7fffffff && (loc & 31) == lane) {
+        const int wi = loc >> 5;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (i == wi) c[i] = NEG;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nc = beam * beam;
+    for (int n = 0; n < beam; ++n) {
+      float best = NEG;
+      int flat = 0x7fffffff, pos = -1;
+      for (int p = lane; p < nc; p += 32) {
+        const float s = cand_score[p];
+        const int f = cand_flat[p];
+        if (s > best || (s == best && f < flat)) { best = s; flat = f; pos = p; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int of = __shfl_xor_sync(0xffffffffu, flat, o);
+        const int op = __shfl_xor_sync(0xffffffffu, pos, o);
+        if (ob > best || (ob == best && of < flat)) { best = ob; flat = of; pos = op; }
+      }
+      if (lane == 0) {
+        score_out[b * beam + n] = best;
+        src_out[b * beam + n] = flat / V;
+        tok_out[b * beam + n] = flat % V;
+        if (pos >= 0) { cand_score[pos] = NEG; cand_flat[pos] = 0x7fffffff; }
+      }
+      __syncwarp();
+    }
+  }
+}
 // reorder beam state after top-k: rows of (h,c) gathered from src; finished sources keep their old state
 struct BeamStepP {
   const float* h_new; const float* c_new; const float* h_old; const float* c_old;

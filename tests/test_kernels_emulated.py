@@ -62,7 +62,7 @@ def test_bahdanau_attention(emu_lib):
     pc.check_train_step(emu_lib, pc.TINY_BAH, 3, 19, 5)
     pc.check_train_step(emu_lib, pc.TINY_BAH, 3, 19, 5, ff=0.1, rnn=0.5)
     pc.check_decode(emu_lib, pc.TINY_BAH, 6, 21, 6, margin=1e-4)     # fp32 emulation: a tighter tie margin is enough
-    pc.check_decode(emu_lib, pc.TINY_BAH, 4, 21, 6, beam=4, margin=1e-4)
+    pc.check_decode(emu_lib, pc.TINY_BAH, 4, 21, 6, beam=4, margin=1e-5)
 
 
 def test_encoder_targets_head(emu_lib):
@@ -149,7 +149,7 @@ def test_attention_multi_chunk_staging(emu_lib, monkeypatch):
     pc.check_train_step(emu_lib, pc.TINY_ATTN, 3, 19, 5, ff=0.1, rnn=0.5)
     pc.check_train_step(emu_lib, pc.TINY_BAH, 3, 19, 5)
     pc.check_decode(emu_lib, pc.TINY_ATTN, 6, 21, 6)
-    pc.check_decode(emu_lib, pc.TINY_BAH, 4, 21, 6, beam=4, margin=1e-4)
+    pc.check_decode(emu_lib, pc.TINY_BAH, 4, 21, 6, beam=4, margin=1e-5)
 
 
 def test_tall_column_sums(emu_lib):
@@ -193,3 +193,13 @@ def test_api_error_paths(emu_lib):
         pc.engine_for(dict(pc.TINY, aux_layer=5, aux_F=3), emu_lib, 3, 19, 5)
     with pytest.raises(E2TError, match="categorical head"):
         pc.engine_for(dict(pc.TINY, aux_layer=0, aux_F=1, aux_kind="categorical"), emu_lib, 3, 19, 5)
+
+
+def test_beam_topk_variants(emu_lib, monkeypatch):
+    """the one-pass top-k at a vocabulary that needs the 64-per-lane instantiation, with more beams than warps, and the
+    general block-wide kernel (vocabularies > 2048) on the same inputs"""
+    big_v = dict(pc.TINY, V=300)
+    pc.check_decode(emu_lib, big_v, 4, 21, 6, beam=4, margin=1e-5)
+    pc.check_decode(emu_lib, big_v, 3, 21, 12, beam=10, margin=1e-5)      # 30 state rows fit max_L * max_B = 36
+    monkeypatch.setenv("E2T_BEAM_BLOCK", "1")
+    pc.check_decode(emu_lib, big_v, 4, 21, 6, beam=4, margin=1e-5)
