@@ -1694,11 +1694,15 @@ extern "C" int e2t_beam_decode(e2t_handle* h, int subnet, const float* x, const 
   LAUNCH(h, k_fill_int, grid1((i64)R * max_len), dim3(256), 0, h->g_tokens[0], c.pad_id, (i64)R * max_len);
   // a third state buffer for the reordered result (reuse dh0/dc0-sized scratch is too small -> use hdec/dhdec heads)
   E2T_REQUIRE((i64)R * c.Hd <= (i64)h->Lm * h->Bm * c.Hd, "beam workspace too small (max_L*max_B < B*beam)");
-  float* h_re = h->hdec; float* c_re = h->dhdec;
+  // (h, c) rotate through three buffers -- live beams, decode_step's candidates, the reordered survivors -- so that no copy
+  // back is needed; scores / tokens / flags ping-pong between their two buffers
+  float* hb[3] = {h->g_h[0], h->g_h[1], h->hdec};
+  float* cb[3] = {h->g_c[0], h->g_c[1], h->dhdec};
+  int sl = 0, sn = 1, sr = 2;      // state slots: live, new, reordered
   int cur = 0;
   for (int k = 0; k < max_len; ++k) {
     int nxt = cur ^ 1;
-    decode_step(h, R, h->g_prev[cur], h->g_h[cur], h->g_c[cur], h->g_h[nxt], h->g_c[nxt], B, beam);
+    decode_step(h, R, h->g_prev[cur], hb[sl], cb[sl], hb[sn], cb[sn], B, beam);
     if (c.V <= 2048 && getenv("E2T_BEAM_BLOCK") == nullptr) {     // one pass, candidates in registers (E2T_BEAM_BLOCK: tests of the general kernel)
       const int nwarp = std::min(8, beam);
       if (c.V <= 256) {
@@ -1715,15 +1719,14 @@ extern "C" int e2t_beam_decode(e2t_handle* h, int subnet, const float* x, const 
              h->g_done[cur], c.pad_id, h->g_lse, h->g_score[nxt], h->g_src, h->g_tok);
     }
     BeamStepP p{};
-    p.h_new = h->g_h[nxt]; p.c_new = h->g_c[nxt]; p.h_old = h->g_h[cur]; p.c_old = h->g_c[cur];
-    p.h_out = h_re; p.c_out = c_re; p.Hd = c.Hd;
+    p.h_new = hb[sn]; p.c_new = cb[sn]; p.h_old = hb[sl]; p.c_old = cb[sl];
+    p.h_out = hb[sr]; p.c_out = cb[sr]; p.Hd = c.Hd;
     p.src = h->g_src; p.tok = h->g_tok; p.done_in = h->g_done[cur]; p.prev_in = h->g_prev[cur];
     p.done_out = h->g_done[nxt]; p.prev_out = h->g_prev[nxt];
     p.toks_in = h->g_tokens[cur]; p.toks_out = h->g_tokens[nxt];
     p.beam = beam; p.k = k; p.max_len = max_len; p.pad_id = c.pad_id; p.eos_id = c.eos_id; p.rows = R;
     LAUNCH(h, k_beam_reorder, grid1((i64)R * c.Hd), dim3(256), 0, p);
-    E2T_CHECK(cudaMemcpyAsync(h->g_h[nxt], h_re, (size_t)R * c.Hd * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-    E2T_CHECK(cudaMemcpyAsync(h->g_c[nxt], c_re, (size_t)R * c.Hd * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    const int t = sl; sl = sr; sr = sn; sn = t;      // survivors become the live beams
     cur = nxt;
   }
   E2T_CHECK(cudaGetLastError());
