@@ -9,7 +9,8 @@ the reference's call sites:
 * ``get_weights_as_numpy_array`` trainers.py:699-700,750-751
 * ``restore_and_get_saliencies`` trainers.py:722-725
 * attributes                   checkpoint_path, N_epochs, layer_sizes, TEMPORALLY_CONVOLVE, EMA_decay, FF_dropout,
-                               RNN_dropout, assessment_epoch_interval, beam_width, temperature
+                               RNN_dropout, assessment_epoch_interval, beam_width, temperature,
+                               inputs_to_occlude (plotters.py:607,630,639: channels silenced at assessment)
 
 All arithmetic happens in libe2t.so (CUDA, sm_100a) behind the C-ABI; this file is the host-side epoch loop
 (the reference's tfh.GraphBuilder train/assess cadence, trainers.py:852-859), the TFRecord batch assembly and
@@ -275,6 +276,9 @@ class SequenceNetwork:
                 continue
             idx = np.arange(i, min(i + self.N_cases, len(examples)))
             x, y = self._batch(examples, idx, max_T, max_L, pad_id)
+            if self.inputs_to_occlude is not None and len(self.inputs_to_occlude):
+                # test-time occlusion (plotters.py:603-640): the listed input channels are silenced for this assessment
+                x[:, :, np.asarray(self.inputs_to_occlude, int)] = 0.0
             if int(self.beam_width) > 1:
                 toks, _ = eng.beam_decode(x, None, beam=int(self.beam_width), max_len=Lh, subnet=si, use_ema=True,
                                           temperature=float(self.temperature))

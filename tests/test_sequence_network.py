@@ -68,6 +68,13 @@ def test_fit_checkpoint_restore_assess(tmp_path, emu_lib):
     assert abs(res["training"].accuracy - tr.decoder_accuracies[-1]) < 1e-9
     sent = net2.predict(net2._load_partition(s, "validation")[0][0])
     assert isinstance(sent, str)
+    # test-time occlusion (plotters.py:603-640): an empty list changes nothing, silencing channels changes the hypotheses
+    net2.inputs_to_occlude = []
+    assert net2.restore_and_assess([s], 40)["training"].hypotheses == res["training"].hypotheses
+    net2.inputs_to_occlude = [0, 1, 2, 3, 4]
+    occ = net2.restore_and_assess([s], 40)["training"]
+    assert occ.hypotheses != res["training"].hypotheses and occ.word_error_rate >= res["training"].word_error_rate
+    net2.inputs_to_occlude = None
 
 
 def test_transfer_learning_scopes(tmp_path, emu_lib):
