@@ -350,6 +350,44 @@ class SequenceNetwork:
                 seqs += [dx[r, :examples[j][0].shape[0]].copy() for r, j in enumerate(idx)]
         return np.concatenate(norms).mean(0) if assessment_type == 'norms' else seqs
 
+    def restore_and_get_activations(self, subnets_params, restore_epoch, data_partition='validation'):
+        """Forward pass (no dropout, EMA weights of checkpoint `restore_epoch`) over the last subject's `data_partition` trials;
+        returns what MultiSubjectTrainer.get_internal_activations assembles in the reference (trainers.py:757-859):
+        convolved_inputs [N,T',E], reversed_inputs [N,T,C], decimated_reversed_targets [N,T',F] (None without an encoder-targets
+        stream), final_RNN_state [2 (c, h), 1 (last encoder layer), N, decoder units] (axes of plotters.py:1388), lengths [N]."""
+        s = subnets_params[-1]
+        si = len(subnets_params) - 1
+        W = int(s.decimation_factor)
+        examples = self._load_partition(s, data_partition)
+        max_T = max(e[0].shape[0] for e in examples)
+        max_L = max(len(e[1]) for e in examples)
+        eng = self._get_engine(subnets_params, max_T, max_L)
+        prm.load_checkpoint(eng, self.checkpoint_path, restore_epoch, reuse_vars_scope='seq2seq')
+        T2 = -(-max_T // W)
+        conv, rev, tgt, fin, lens_all = [], [], [], [], []
+        for i in range(0, len(examples), self.N_cases):
+            idx = np.arange(i, min(i + self.N_cases, len(examples)))
+            B = len(idx)
+            x, y = self._batch(examples, idx, max_T, max_L, eng.cfg.pad_id)
+            eng.eval_loss(x, None, y, subnet=si, use_ema=float(self.EMA_decay) > 0)
+            lens = eng.activation("lens", (B,), np.int32)
+            conv.append(eng.activation("conv_out", (T2, B, eng.cfg.E)).transpose(1, 0, 2))
+            fin.append(np.stack([eng.activation("final_c", (B, eng.cfg.Hd)), eng.activation("final_h", (B, eng.cfg.Hd))])[:, None])
+            r = x.copy()
+            for b in range(B):
+                r[b, :lens[b]] = x[b, :lens[b]][::-1]          # tf.reverse_sequence, trainers.py:808-810
+            rev.append(r)
+            aux = self._aux_batch(examples, idx, max_T)
+            if aux is not None:
+                ra = aux.copy()
+                for b in range(B):
+                    ra[b, :lens[b]] = aux[b, :lens[b]][::-1]
+                tgt.append(ra[:, 0::W])                        # trainers.py:791-795
+            lens_all.append(lens)
+        return SimpleNamespace(convolved_inputs=np.concatenate(conv), reversed_inputs=np.concatenate(rev),
+                               decimated_reversed_targets=np.concatenate(tgt) if tgt else None,
+                               final_RNN_state=np.concatenate(fin, axis=2), lengths=np.concatenate(lens_all))
+
     def get_weights_as_numpy_array(self, full_var_name, restore_epoch):
         """The stored variable (or its `/ExponentialMovingAverage` shadow) from checkpoint `restore_epoch`."""
         with np.load(f"{self.checkpoint_path}-{restore_epoch}.npz") as z:

@@ -9,6 +9,8 @@ Mirrors /root/reference/ecog2txt/trainers.py:41-408,444-554,925-963 for everythi
                                                            frozen and restored, then train everything)
 * ``assess_saved_model`` / ``update_net_from_saved_model`` / ``recover_model_sizes``   trainers.py:376-554
 * ``construct_online_predictor`` / ``target_inds_to_sequences``   trainers.py:925-963
+* ``_retrieve_layer_weights`` / ``get_encoder_embedding`` / ``get_saliencies`` / ``get_internal_activations`` /
+  ``tf_record_to_numpy_data``        trainers.py:680-922
 
 Out of scope here exactly as in SURVEY.md section 2: result files for the plotters, tf summaries, saliency plots,
 ``ECoGDataGenerator`` subclasses (lab-private data): subjects are passed in ready-made (``subjects.ECoGSubject``;
@@ -220,6 +222,50 @@ class MultiSubjectTrainer:
         for key, d in rnn.items():                                                   # encoder_rnn_<n> -> one list, :543-552
             layer_sizes[key] = [d[i] for i in sorted(d)]
         return layer_sizes, data_sizes, strides, EMA
+
+    # ---- trainers.py:676-701,734-751 -------------------------------------------------------------
+    def _retrieve_layer_weights(self, weights_name):
+        """The EMA copy of the first layer's weights of the sub-network called `weights_name` (e.g. 'decoder_embedding',
+        'encoder_embedding') from the restore_epoch checkpoint, found by name like the reference does."""
+        var_to_shape = prm.variable_to_shape_map(self.net.checkpoint_path, self.restore_epoch)
+        weights_full_name = None
+        for key in sorted(var_to_shape):
+            if re.match('.*{0}.*0/weights/ExponentialMovingAverage'.format(weights_name), key):
+                weights_full_name = key
+        assert weights_full_name, "Uh-oh, no such weights found! -- jgm"
+        return self.net.get_weights_as_numpy_array(weights_full_name, self.restore_epoch)
+
+    def get_encoder_embedding(self):
+        """The last subject's temporal-conv kernel [1, W, C, E] (EMA), named from the recovered model sizes."""
+        layer_sizes, data_sizes, _, _ = self.recover_model_sizes()
+        subj_id = self.ecog_subjects[-1].subnet_id
+        name = 'seq2seq/subnet_{0}/encoder_embedding_{1}_{2}_0/weights/ExponentialMovingAverage'.format(
+            subj_id, data_sizes[subj_id]['encoder_inputs'], layer_sizes['encoder_embedding'][0])
+        return self.net.get_weights_as_numpy_array(name, self.restore_epoch)
+
+    # ---- trainers.py:757-859 ---------------------------------------------------------------------
+    def get_internal_activations(self):
+        """convolved_inputs, reversed_inputs, decimated_reversed_targets, final_RNN_state of the last subject's validation data
+        with the restored (EMA) weights."""
+        return self.net.restore_and_get_activations(self.ecog_subjects, self.restore_epoch, data_partition='validation')
+
+    # ---- trainers.py:861-922 ---------------------------------------------------------------------
+    def tf_record_to_numpy_data(self, subj_id, block_id):
+        """Yields one dict per trial of the block's TFRecord: float streams reshaped to [T, num_features_raw], string streams
+        as raw byte strings [T, 1] (no index substitution) -- for inspecting the content of the records."""
+        from . import tfrecord
+        from .subjects import SequenceDataManifest
+        for subject in self.ecog_subjects:
+            if subject.subj_id == subj_id:
+                break
+        else:
+            raise ValueError('Requested subject not in this trainer')
+        raw = {}
+        for key, man in subject.data_manifests.items():
+            is_float = man.get_feature_list is None
+            raw[key] = SequenceDataManifest(man.sequence_type,
+                                            num_features_raw=man.num_features_raw if is_float else 1)
+        yield from tfrecord.read_examples([subject.tf_record_partial_path.format(block_id)], raw)
 
     # ---- trainers.py:703-732 ---------------------------------------------------------------------
     def get_saliencies(self, contrib_method, assessment_type='norms'):

@@ -81,3 +81,50 @@ def test_get_saliencies_and_projection_sizes(tmp_path, emu_lib):
     assert dec.shape == (6,) and aux.shape == (6,) and not np.allclose(dec, aux)
     mans = tr.ecog_subjects[-1].data_manifests
     assert mans["encoder_1_targets"].penalty_scale == 0.3 and mans["decoder_targets"].penalty_scale == 1.0
+
+
+def test_introspection_callers(tmp_path, emu_lib):
+    """_retrieve_layer_weights / get_encoder_embedding (trainers.py:680-751), get_internal_activations (:757-859) against the
+    oracle's encoder on the restored EMA weights, tf_record_to_numpy_data (:861-922)."""
+    import torch
+    from oracle import seq2seq_oracle as O
+    tr = _trainer(tmp_path, emu_lib, ids=(400,), subject_kw=dict(encoder_targets="audio_sequence", encoder_targets_features=4),
+                  N_epochs=5, assessment_epoch_interval=5)
+    tr.net.layer_sizes = dict(tr.net.layer_sizes, encoder_1_projection=[7])
+    tr.parallel_transfer_learn()
+    s = tr.ecog_subjects[-1]
+    Wc = tr.get_encoder_embedding()
+    assert Wc.shape == (1, 4, 6, 5)
+    assert np.array_equal(Wc, tr._retrieve_layer_weights("encoder_embedding"))
+    assert tr._retrieve_layer_weights("decoder_embedding").shape == (len(VOCAB), 6)
+    acts = tr.get_internal_activations()
+    ex = tr.net._load_partition(s, "validation")
+    N, T = len(ex), max(e[0].shape[0] for e in ex)
+    T2 = -(-T // 4)
+    assert acts.convolved_inputs.shape == (N, T2, 5) and acts.reversed_inputs.shape == (N, T, 6)
+    assert acts.final_RNN_state.shape == (2, 1, N, 16) and acts.decimated_reversed_targets.shape == (N, T2, 4)
+    # oracle on the EMA weights of the checkpoint
+    shapes = prm.variable_to_shape_map(tr.net.checkpoint_path, tr.restore_epoch)
+    ema = "/ExponentialMovingAverage"
+    P = {k[:-len(ema)]: torch.from_numpy(tr.net.get_weights_as_numpy_array(k, tr.restore_epoch)) for k in shapes if k.endswith(ema)}
+    ocfg = O.OracleConfig(subnet_ids=(400,), subnet_C=(6,), subnet_W=(4,), E=5, H=(8, 8), D=6, Hd=16, V=len(VOCAB),
+                          aux_layer=1, aux_hidden=7, aux_F=4)
+    x = np.zeros((N, T, 6), np.float32)
+    for i, e in enumerate(ex):
+        x[i, :e[0].shape[0]] = e[0]
+    ref = O.encoder(ocfg, P, torch.from_numpy(x), None, 0)
+    assert np.allclose(acts.convolved_inputs, ref["conv_out"].numpy(), atol=1e-5)
+    assert np.allclose(acts.final_RNN_state[1, 0], ref["final_h"].numpy(), atol=1e-5)
+    assert np.allclose(acts.final_RNN_state[0, 0], ref["final_c"].numpy(), atol=1e-5)
+    assert np.array_equal(acts.lengths, ref["lens"].numpy())
+    assert np.array_equal(acts.reversed_inputs, O.reverse_within_length(torch.from_numpy(x), ref["lens"]).numpy())
+    aux = np.zeros((N, T, 4), np.float32)
+    for i, e in enumerate(ex):
+        aux[i, :e[2].shape[0]] = e[2]
+    assert np.array_equal(acts.decimated_reversed_targets, O.prepare_encoder_targets(torch.from_numpy(aux), ref["lens"], 4).numpy())
+    # raw records
+    recs = list(tr.tf_record_to_numpy_data(400, 3))
+    assert len(recs) == 6 and recs[0]["encoder_inputs"].shape[1] == 6 and recs[0]["encoder_1_targets"].shape[1] == 4
+    assert recs[0]["decoder_targets"].dtype == object and recs[0]["decoder_targets"][0, 0].decode().endswith("_")
+    with np.testing.assert_raises(ValueError):
+        next(tr.tf_record_to_numpy_data(999, 3))
