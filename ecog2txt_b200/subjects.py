@@ -108,6 +108,24 @@ class SequenceDataManifest:
         self._padding_value = v
 
 
+def sentence_tokenize(token_list: Sequence[str], token_type: str = 'word_sequence') -> List[bytes]:
+    """Words of one trial -> the byte strings stored in the TFRecord (ECoGDataGenerator._sentence_tokenize,
+    /root/reference/ecog2txt/data_generators.py:445-473): lower-cased, underscore-postfixed, UTF-8; a 'trial' token type joins
+    the words of the sentence into ONE token.  ('word_piece_sequence' needs tensor2tensor's SubwordTextEncoder: out of scope.)"""
+    if token_type == 'word_piece_sequence':
+        raise NotImplementedError("word-piece tokenisation needs tensor2tensor's SubwordTextEncoder (out of scope)")
+    if token_type == 'trial':
+        return [' '.join(token.lower() + '_' for token in token_list).encode('utf-8')]
+    return [(token.lower() + '_').encode('utf-8') for token in token_list]
+
+
+def get_class_list(vocab_file_path: str) -> List[str]:
+    """The class list of a text stream = the whitespace-separated entries of its vocabulary file
+    (ECoGDataGenerator.get_class_list, data_generators.py:428-435; e.g. auxiliary/vocab.mocha-timit.1806)."""
+    with open(vocab_file_path, 'r') as f:
+        return f.read().split()
+
+
 class SyntheticDataGenerator:
     """Writes `<tf_record_partial_path>.format(block)` for each block from a SyntheticCorpus
     (ECoGDataGenerator.write_to_Protobuf_maybe, data_generators.py:382-425)."""

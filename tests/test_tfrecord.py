@@ -121,3 +121,23 @@ def test_io_library_exports_every_declared_symbol():
     for sym in declared:
         getattr(lib, sym)
     assert declared == set(tfrecord.EXPORTED_SYMBOLS)
+
+
+def test_sentence_tokenize_and_class_list(tmp_path):
+    """data_generators.py:428-473: tokens are lower-cased, underscore-postfixed UTF-8; 'trial' joins the sentence; the class list
+    is the vocabulary file; tokens written this way parse back to the indices of that list (OOV -> <OOV>, EOS appended)."""
+    from ecog2txt_b200.subjects import SequenceDataManifest, get_class_list, sentence_tokenize
+    assert sentence_tokenize(["The", "birch", "Canoe"]) == [b"the_", b"birch_", b"canoe_"]
+    assert sentence_tokenize(["The", "birch"], "trial") == [b"the_ birch_"]
+    with pytest.raises(NotImplementedError):
+        sentence_tokenize(["a"], "word_piece_sequence")
+    vf = tmp_path / "vocab.test"
+    vf.write_text("<pad>\n<EOS>\n<OOV>\nthe_\nbirch_\n")
+    classes = get_class_list(str(vf))
+    assert classes == ["<pad>", "<EOS>", "<OOV>", "the_", "birch_"]
+    path = str(tmp_path / "t_B1.tfrecord")
+    with tfrecord.TFRecordWriter(path) as w:
+        w.write_example({"ecog_sequence": np.ones((3, 2), np.float32), "text_sequence": sentence_tokenize(["The", "birch", "Canoe"])})
+    man = {"decoder_targets": SequenceDataManifest("text_sequence", get_feature_list=lambda: classes, APPEND_EOS=True)}
+    (ex,) = list(tfrecord.read_examples([path], man))
+    assert ex["decoder_targets"].tolist() == [3, 4, 2, 1]
