@@ -1606,20 +1606,8 @@ static void greedy_body(e2t_handle* h, int subnet, const Inputs& in, int B, int 
   for (int k = 0; k < max_len; ++k) {
     float* ho = h->g_h[k & 1]; float* co = h->g_c[k & 1];
     decode_step(h, B, h->g_prev[0], hin, cin, ho, co, B, 1);
-    if (c.V <= 2048 && getenv("E2T_BEAM_BLOCK") == nullptr) {      // warp per row, logits in registers
-      if (c.V <= 256) {
-        auto kfn = k_greedy_pick_w<8>;
-        LAUNCH_L(h, "k_greedy_pick_w", kfn, dim3((unsigned)cdiv(B, 8)), dim3(256), 0, h->g_logits, h->Vp, c.V, 1.0f / temperature, k,
-                 max_len, c.pad_id, c.eos_id, h->g_prev[0], h->g_done[0], h->g_tokens[0], h->g_logp, B);
-      } else {
-        auto kfn = k_greedy_pick_w<64>;
-        LAUNCH_L(h, "k_greedy_pick_w", kfn, dim3((unsigned)cdiv(B, 8)), dim3(256), 0, h->g_logits, h->Vp, c.V, 1.0f / temperature, k,
-                 max_len, c.pad_id, c.eos_id, h->g_prev[0], h->g_done[0], h->g_tokens[0], h->g_logp, B);
-      }
-    } else {
-      LAUNCH(h, k_greedy_pick, dim3(B), dim3(128), 0, h->g_logits, h->Vp, c.V, 1.0f / temperature, k, max_len, c.pad_id,
-             c.eos_id, h->g_prev[0], h->g_done[0], h->g_tokens[0], h->g_logp);
-    }
+    LAUNCH(h, k_greedy_pick, dim3(B), dim3(128), 0, h->g_logits, h->Vp, c.V, 1.0f / temperature, k, max_len, c.pad_id,
+           c.eos_id, h->g_prev[0], h->g_done[0], h->g_tokens[0], h->g_logp);
     hin = ho; cin = co;
   }
 }

@@ -1025,45 +1025,6 @@ __global__ void __launch_bounds__(128) k_greedy_pick(const float* logits, int ld
 // Gate-column permutation of the layers run by the persistent recurrent kernels (lstm_rec.cuh): canonical
 // column n = g*H + u  ->  n' = 64*(u/16) + 32*((u%16)/8) + 8*g + (u%8), so that the 4 gates x 8 units one
 // epilogue thread owns are 32 contiguous floats (one 128 B line) of a gates row and 32 contiguous TMEM columns.
-// same pick, one WARP per row with the row's logits in registers (V <= 32 * NV): no block reductions
-template <int NV>
-__global__ void __launch_bounds__(256) k_greedy_pick_w(const float* __restrict__ logits, int ld, int V, float inv_temp, int k,
-                                                       int max_len, int pad_id, int eos_id, int* prev, int* done, int* tokens,
-                                                       float* logp, int rows) {
-  const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (b >= rows) return;
-  const float* row = logits + (i64)b * ld;
-  const float NEG = -3.0e38f;
-  float c[NV];
-  float best = NEG;
-  int bi = 0;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int v = lane + 32 * i;
-    c[i] = v < V ? row[v] : NEG;
-    if (c[i] > best) { best = c[i]; bi = i; }        // ascending index, strict >: lowest index on ties
-  }
-  int idx = best == NEG ? 0x7fffffff : lane + 32 * bi;
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-    if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
-  }
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i)
-    if (lane + 32 * i < V) s += expf((c[i] - best) * inv_temp);
-  s = warp_sum(s);
-  if (lane == 0) {
-    const int was_done = done[b];
-    tokens[(i64)b * max_len + k] = was_done ? pad_id : idx;
-    if (logp) logp[(i64)b * max_len + k] = was_done ? 0.f : -logf(s);
-    if (!was_done) prev[b] = idx;
-    done[b] = was_done | (idx == eos_id);
-  }
-}
-
 #define E2T_REC_UT 8   /* hidden units per epilogue thread of the persistent kernels */
 __host__ __device__ __forceinline__ int e2t_gate_perm(int n, int H) {
   int g = n / H, u = n - g * H;

@@ -201,7 +201,5 @@ def test_beam_topk_variants(emu_lib, monkeypatch):
     big_v = dict(pc.TINY, V=300)
     pc.check_decode(emu_lib, big_v, 4, 21, 6, beam=4, margin=1e-5)
     pc.check_decode(emu_lib, big_v, 3, 21, 12, beam=10, margin=1e-5)      # 30 state rows fit max_L * max_B = 36
-    pc.check_decode(emu_lib, big_v, 9, 21, 6, margin=1e-5)                # greedy pick: warp per row, 9 rows = 2 blocks
     monkeypatch.setenv("E2T_BEAM_BLOCK", "1")
     pc.check_decode(emu_lib, big_v, 4, 21, 6, beam=4, margin=1e-5)
-    pc.check_decode(emu_lib, big_v, 9, 21, 6, margin=1e-5)
