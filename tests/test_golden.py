@@ -114,3 +114,67 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_oracle_conv_matches_torch_conv2d():
+    """App. D items 2-3 against an independent implementation: reverse within length, then tf.nn.conv2d semantics with a
+    (1, W, C, E) kernel at stride W and the tail zero-padded to a multiple of W == F.conv2d over [B, C, 1, T]."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    B, T, C, W, E = 3, 19, 6, 4, 5
+    x = torch.randn(B, T, C)
+    lens = torch.tensor([19, 7, 12])
+    for b in range(B):
+        x[b, lens[b]:] = 0
+    w4, bias = torch.randn(1, W, C, E) * 0.3, torch.randn(E) * 0.1
+    y, lens2 = O.temporal_conv(O.reverse_within_length(x, lens), lens, w4, bias, "relu")
+    xr = torch.stack([torch.cat([x[b, :lens[b]].flip(0), x[b, lens[b]:]]) for b in range(B)])
+    T2 = -(-T // W)
+    xp = F.pad(xr, (0, 0, 0, T2 * W - T)).permute(0, 2, 1).unsqueeze(2)            # [B, C, 1, T2*W]
+    ref = F.conv2d(xp, w4.permute(3, 2, 0, 1), bias, stride=(1, W)).squeeze(2).permute(0, 2, 1)
+    assert torch.allclose(y, torch.relu(ref), atol=1e-5)
+    assert lens2.tolist() == [5, 2, 3]
+
+
+def test_oracle_bilstm_matches_packed_torch_lstm():
+    """dynamic_rnn semantics on ragged batches (state frozen and outputs zero past the length, the backward direction reversed
+    within each length) == torch.nn.LSTM(bidirectional=True) on a packed sequence, after the TF -> torch gate re-ordering."""
+    from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
+    torch.manual_seed(1)
+    In, H, B, T = 5, 7, 4, 9
+    lens = torch.tensor([9, 3, 6, 1])
+    x = torch.randn(B, T, In)
+    for b in range(B):
+        x[b, lens[b]:] = 0
+    Ks = [torch.randn(In + H, 4 * H) * 0.3 for _ in range(2)]
+    bs = [torch.randn(4 * H) * 0.1 for _ in range(2)]
+    outs, hs, cs = zip(*(O.lstm_direction(x, lens, Ks[d], bs[d], reverse=bool(d)) for d in range(2)))
+    lstm = torch.nn.LSTM(In, H, batch_first=True, bidirectional=True)
+    order = [0, 2, 1, 3]                     # torch (i,f,g,o) <- TF (i,j,f,o) block indices
+    with torch.no_grad():
+        for d, sfx in enumerate(("", "_reverse")):
+            Kb = Ks[d].reshape(In + H, 4, H)[:, order].reshape(In + H, 4 * H)
+            bb = bs[d].clone().reshape(4, H)
+            bb[2] += 1.0                     # forget_bias
+            getattr(lstm, "weight_ih_l0" + sfx).copy_(Kb[:In].T)
+            getattr(lstm, "weight_hh_l0" + sfx).copy_(Kb[In:].T)
+            getattr(lstm, "bias_ih_l0" + sfx).copy_(bb[order].reshape(-1))
+            getattr(lstm, "bias_hh_l0" + sfx).zero_()
+        packed = pack_padded_sequence(x, lens, batch_first=True, enforce_sorted=False)
+        ref, (hn, cn) = lstm(packed)
+        ref, _ = pad_packed_sequence(ref, batch_first=True, total_length=T)
+    assert torch.allclose(torch.cat(outs, dim=2), ref, atol=1e-5)
+    for d in range(2):
+        assert torch.allclose(hs[d], hn[d], atol=1e-5) and torch.allclose(cs[d], cn[d], atol=1e-5)
+
+
+def test_oracle_loss_matches_torch_cross_entropy():
+    """App. D item 7: the masked, summed CE of train_loss == F.cross_entropy(ignore_index=pad, reduction='sum') on its logits."""
+    import torch.nn.functional as F
+    ocfg = O.OracleConfig(**pc.TINY)
+    P = pc.make_params(ocfg)
+    x, lens, y = pc.make_batch(ocfg, 4, 19, 5)
+    yt = torch.from_numpy(y).long()
+    loss, ntok, acts = O.train_loss(ocfg, P, torch.from_numpy(x), None, yt)
+    ref = F.cross_entropy(acts["logits"].reshape(-1, ocfg.V), yt.reshape(-1), ignore_index=ocfg.pad_id, reduction="sum")
+    assert abs(float(loss) - float(ref)) < 1e-4 * float(ref) and ntok == int((y != 0).sum())
