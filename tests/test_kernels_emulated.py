@@ -203,3 +203,10 @@ def test_beam_topk_variants(emu_lib, monkeypatch):
     pc.check_decode(emu_lib, big_v, 3, 21, 12, beam=10, margin=1e-5)      # 30 state rows fit max_L * max_B = 36
     monkeypatch.setenv("E2T_BEAM_BLOCK", "1")
     pc.check_decode(emu_lib, big_v, 4, 21, 6, beam=4, margin=1e-5)
+
+
+def test_maximum_utterance_length(emu_lib):
+    """the longest trial the reference's generators emit (max_samples = 1250 frames, data_generators.py:35-42) next to a short
+    one in the same batch: 313 recurrent steps per layer and direction; and the decode of such a batch"""
+    pc.check_train_step(emu_lib, pc.TINY, 2, 1250, 3)
+    pc.check_decode(emu_lib, pc.TINY, 2, 1250, 4, margin=1e-4)
