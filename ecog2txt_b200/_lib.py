@@ -17,7 +17,7 @@ ACT = {"linear": 0, "relu": 1}
 GEMM = {"auto": 0, "simt": 1, "tcgen05": 2}
 ATTN = {"none": 0, "luong": 1, "bahdanau": 2}
 AUX_KIND = {"gaussian": 0, "categorical": 1}
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class E2TConfig(C.Structure):
@@ -82,6 +82,8 @@ _SIGNATURES = {
     "e2t_train_step_grads": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                        C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "e2t_stage_inputs": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
+    "e2t_host_alloc": (C.c_int, [C.POINTER(_P), C.c_int64]),
+    "e2t_host_free": (C.c_int, [_P]),
     "e2t_set_grad_buckets": (C.c_int, [_P, C.c_int]),
     "e2t_grad_bucket_count": (C.c_int, [_P]),
     "e2t_grad_bucket_info": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -30,7 +30,7 @@
 
 static thread_local std::string g_err;
 extern "C" const char* e2t_last_error(void) { return g_err.c_str(); }
-extern "C" int e2t_abi_version(void) { return 5; }
+extern "C" int e2t_abi_version(void) { return 6; }
 
 namespace {
 
@@ -667,18 +667,16 @@ Inputs stage(e2t_handle* h, int subnet, const float* x, const int32_t* lens, con
       in.y = h->d_y;
     }
   } else if (loc == E2T_STAGED0 || loc == E2T_STAGED1) {
-#ifdef E2T_EMU
-    throw std::runtime_error("e2t: staged inputs are not available in the emulation build");
-#else
     const int slot = loc - E2T_STAGED0;
-    E2T_REQUIRE(h->st_ready[slot] != nullptr, "slot was never staged (e2t_stage_inputs)");
+    E2T_REQUIRE(h->st_x[slot] != nullptr && h->st_B[slot] > 0, "slot was never staged (e2t_stage_inputs)");
     E2T_REQUIRE(h->st_B[slot] == B && h->st_T[slot] == T && h->st_L[slot] == L && h->st_subnet[slot] == subnet,
                 "staged slot holds a batch of another shape / subject");
+#ifndef E2T_EMU
     E2T_CHECK(cudaStreamWaitEvent(h->stream, h->st_ready[slot], 0));
+#endif
     in.x = h->st_x[slot];
     in.lens_in = h->st_has_lens[slot] ? h->st_lens[slot] : nullptr;
     in.y = h->st_has_y[slot] ? h->st_y[slot] : nullptr;
-#endif
   } else {
     E2T_REQUIRE(loc == E2T_DEVICE, "loc must be E2T_HOST, E2T_DEVICE or E2T_STAGED0/1");
     in.x = x; in.lens_in = lens; in.y = y;
@@ -1413,14 +1411,26 @@ extern "C" int e2t_train_step_grads(e2t_handle* h, int subnet, const float* x, c
 extern "C" int e2t_stage_inputs(e2t_handle* h, int slot, int subnet, const float* x, const int32_t* lens, const int32_t* y,
                                 int B, int T, int L) {
   API_BEGIN NEED_H;
-#ifdef E2T_EMU
-  (void)slot; (void)subnet; (void)x; (void)lens; (void)y; (void)B; (void)T; (void)L;
-  throw std::runtime_error("e2t: staged inputs are not available in the emulation build");
-#else
   const e2t_config& c = h->cfg;
   E2T_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
   E2T_REQUIRE(subnet >= 0 && subnet < c.n_subnets, "subnet index out of range");
   E2T_REQUIRE(x != nullptr && B >= 1 && B <= h->Bm && T >= 1 && T <= h->Tm && L >= 0 && L <= h->Lm, "bad staging arguments");
+#ifdef E2T_EMU
+  // emulation build (tests): same slots and bookkeeping, synchronous copies, no streams / events
+  if (!h->st_x[slot]) {
+    if (slot == 0) { h->st_x[0] = h->d_x; h->st_lens[0] = h->d_lens_in; h->st_y[0] = h->d_y; }
+    else {
+      h->st_x[1] = h->alloc<float>((i64)h->Bm * h->Tm * h->Cmax);
+      h->st_lens[1] = h->alloc<int>(h->Bm);
+      h->st_y[1] = h->alloc<int>((i64)h->Bm * h->Lm);
+    }
+  }
+  memcpy(h->st_x[slot], x, (size_t)B * T * c.subnet_C[subnet] * sizeof(float));
+  if (lens) memcpy(h->st_lens[slot], lens, (size_t)B * sizeof(int));
+  if (y) memcpy(h->st_y[slot], y, (size_t)B * L * sizeof(int));
+  h->st_has_lens[slot] = lens != nullptr; h->st_has_y[slot] = y != nullptr;
+  h->st_B[slot] = B; h->st_T[slot] = T; h->st_L[slot] = L; h->st_subnet[slot] = subnet;
+#else
   if (!h->copy_stream) E2T_CHECK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   if (!h->st_ready[slot]) {
     E2T_CHECK(cudaEventCreateWithFlags(&h->st_ready[slot], cudaEventDisableTiming));
@@ -1498,6 +1508,19 @@ extern "C" int e2t_eval_loss(e2t_handle* h, int subnet, const float* x, const in
   E2T_CHECK(cudaGetLastError());
   release_slot(h, loc);
   read_loss(h, loss_sum, ntok);
+  API_END
+}
+
+// page-locked host memory for the caller's staging buffers (so that e2t_stage_inputs' copies are truly asynchronous)
+extern "C" int e2t_host_alloc(void** out, int64_t bytes) {
+  API_BEGIN
+  E2T_REQUIRE(out != nullptr && bytes > 0, "bad arguments");
+  E2T_CHECK(cudaMallocHost(out, (size_t)bytes));
+  API_END
+}
+extern "C" int e2t_host_free(void* p) {
+  API_BEGIN
+  if (p) E2T_CHECK(cudaFreeHost(p));
   API_END
 }
 

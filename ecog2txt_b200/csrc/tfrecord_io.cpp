@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -117,7 +118,7 @@ struct e2t_example_builder {
 extern "C" {
 
 const char* e2t_io_last_error(void) { return g_io_err.c_str(); }
-int e2t_io_abi_version(void) { return 1; }
+int e2t_io_abi_version(void) { return 2; }
 
 uint32_t e2t_io_masked_crc32c(const void* data, uint64_t n) { return mask_crc(crc32c((const uint8_t*)data, (size_t)n)); }
 
@@ -433,6 +434,33 @@ int e2t_pad_batch_f32(float* dst, int64_t B, int64_t T_pad, int64_t C, const flo
     if (lens[i]) memcpy(d, src[i], (size_t)(lens[i] * C) * sizeof(float));
     memset(d + lens[i] * C, 0, (size_t)((T_pad - lens[i]) * C) * sizeof(float));
   }
+  return 0;
+}
+
+// Same with the utterances split over n_threads worker threads (a 256-utterance batch of config 2 is 105 MB: one thread
+// copies it in ~20 ms, five times the GPU step; the destination is typically a page-locked staging buffer).
+int e2t_pad_batch_f32_mt(float* dst, int64_t B, int64_t T_pad, int64_t C, const float* const* src, const int64_t* lens,
+                         int n_threads) {
+  if (!dst || !src || !lens) { g_io_err = "e2t_io: NULL argument"; return -1; }
+  for (int64_t i = 0; i < B; ++i)
+    if (lens[i] < 0 || lens[i] > T_pad) { g_io_err = "e2t_io: sequence longer than the padded length"; return -3; }
+  if (n_threads > B) n_threads = (int)B;
+  if (n_threads <= 1) return e2t_pad_batch_f32(dst, B, T_pad, C, src, lens);
+  auto work = [&](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; ++i) {
+      float* d = dst + i * T_pad * C;
+      if (lens[i]) memcpy(d, src[i], (size_t)(lens[i] * C) * sizeof(float));
+      memset(d + lens[i] * C, 0, (size_t)((T_pad - lens[i]) * C) * sizeof(float));
+    }
+  };
+  std::vector<std::thread> pool;
+  const int64_t per = (B + n_threads - 1) / n_threads;
+  for (int t = 1; t < n_threads; ++t) {
+    const int64_t lo = t * per, hi = lo + per < B ? lo + per : B;
+    if (lo < hi) pool.emplace_back(work, lo, hi);
+  }
+  work(0, per < B ? per : B);
+  for (auto& th : pool) th.join();
   return 0;
 }
 

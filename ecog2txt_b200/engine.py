@@ -115,6 +115,10 @@ class Engine:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
+            self._lib.e2t_sync(self._h)
+            for p in getattr(self, "_host_bufs", []):
+                self._lib.e2t_host_free(p)
+            self._host_bufs = []
             self._lib.e2t_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -237,6 +241,17 @@ class Engine:
             return float(loss.value), int(ntok.value)
         self._ck(self._lib.e2t_train_step_grads(self._h, subnet, None, None, None, loc, B, T, Lk, seed & 0xFFFFFFFF, None, None))
         return None
+
+    def host_buffer(self, shape, dtype=np.float32) -> np.ndarray:
+        """numpy array over page-locked host memory (e2t_host_alloc), freed when the engine is closed: a staging buffer from
+        which stage_inputs copies asynchronously."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._ck(self._lib.e2t_host_alloc(C.byref(p), n))
+        self._host_bufs = getattr(self, "_host_bufs", [])
+        self._host_bufs.append(p)
+        buf = (C.c_char * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
     def set_grad_buckets(self, on: bool):
         """complete the gradient buffer bucket by bucket (with an event each) so that the all-reduce can overlap the backward"""

@@ -41,7 +41,7 @@ _MANIFEST_KEYS = dict(layer_sizes=None, FF_dropout=0.0, RNN_dropout=0.0, TEMPORA
 class SequenceNetwork:
     def __init__(self, manifest, EOS_token=_EOS, pad_token=_PAD, OOV_token=_OOV, training_GPUs=(0,),
                  TARGETS_ARE_SEQUENCES=True, VERBOSE=True, N_cases=256, max_hyp_length=20, learning_rate=5e-4,
-                 seed=1, gemm_backend="auto", attention="none", lib=None, **kwargs):
+                 seed=1, gemm_backend="auto", attention="none", lib=None, loader_threads=None, **kwargs):
         # utils_jgm.auto_attribute(CHECK_MANIFEST=True): a keyword wins, else manifest[key] (README.md:42)
         for key, default in _MANIFEST_KEYS.items():
             if key in kwargs and kwargs[key] is not None:
@@ -65,6 +65,8 @@ class SequenceNetwork:
         self.VERBOSE = VERBOSE
         self.N_cases, self.max_hyp_length, self.learning_rate, self.seed = N_cases, max_hyp_length, learning_rate, seed
         self.gemm_backend = gemm_backend
+        # native threads assembling a minibatch (the tf.data num_parallel_calls of the reference, subjects.py:618)
+        self.loader_threads = int(loader_threads) if loader_threads else max(1, min(8, (os.cpu_count() or 2) // 2))
         self.attention = attention       # "luong": optional A7 module (default "none" = the reference model)
         self.checkpoint_path: Optional[str] = None
         self.inputs_to_occlude = None
@@ -151,6 +153,21 @@ class SequenceNetwork:
             y[r, :len(t)] = t
         return x, y
 
+    def _ring_view(self, eng, k, B, T_pad, Cs):
+        """[B, T_pad, Cs] view of slot k % 3 of the page-locked staging ring (allocated with the engine; three slots: the batch
+        being consumed by the running step, the one being copied, the one being assembled).  Falls back to pageable memory
+        if page-locked memory cannot be had."""
+        if getattr(self, "_ring_owner", None) is not eng:
+            self._ring_owner, self._ring = eng, None
+            n = self.N_cases * eng.cfg.max_T * max(eng.cfg.subnet_C)
+            try:
+                self._ring = [eng.host_buffer((n,), np.float32) for _ in range(3)]
+            except Exception as e:      # noqa: BLE001 -- any allocation failure: pageable staging still works, only slower
+                self.vprint(f"page-locked staging ring unavailable ({e}); using pageable buffers")
+        if self._ring is None:
+            return None
+        return self._ring[k % 3][:B * T_pad * Cs].reshape(B, T_pad, Cs)
+
     @staticmethod
     def _aux_batch(examples, idx, T_pad):
         """Encoder targets of a minibatch: fp32 [B,T,F] (zero padded) or int32 [B,T] class indices (pad index 0)."""
@@ -199,37 +216,45 @@ class SequenceNetwork:
                 plan += [(si, order[i:i + self.N_cases]) for i in range(0, len(order), self.N_cases)]
             order = rs.permutation(len(plan))
             ep_loss, ep_tok = 0.0, 0
-            # this rank's shard of every minibatch of the epoch; the host->device copy of minibatch k+1 is started
-            # (e2t_stage_inputs, library copy stream) before minibatch k is trained -- the tf.data prefetch of the reference
+            # this rank's shard of every minibatch of the epoch.  Input pipeline (the tf.data prefetch of the reference,
+            # trainers.py:891-901): minibatch k+1 is assembled on the host (native threads, into a page-locked ring buffer) and
+            # its host->device copy is started (e2t_stage_inputs, library copy stream) WHILE minibatch k trains; the host only
+            # waits for step k when it reads the loss
             shards = []
             for pi in order:
                 si, idx = plan[pi]
                 lo, hi = shard_range(len(idx), rank, world)
                 shards.append((si, idx[lo:hi]))
-            pipelined = not eng.emulated
 
             def host_batch(k):
                 si, ids = shards[k]
                 if not len(ids):
                     return None
                 ex = data[subnets_params[si].subnet_id]['training']
-                return self._batch(ex, ids, max_T, max_L, pad_id) + (self._aux_batch(ex, ids, max_T),)
+                Cs = int(ex[ids[0]][0].shape[1])
+                out = self._ring_view(eng, k, len(ids), max_T, Cs)
+                x = tfrecord.pad_batch_f32([ex[i][0] for i in ids], max_T, out=out, threads=self.loader_threads)
+                y = np.full((len(ids), max_L), pad_id, np.int32)
+                for r, i in enumerate(ids):
+                    y[r, :len(ex[i][1])] = ex[i][1]
+                return x, y, self._aux_batch(ex, ids, max_T)
 
             nxt = host_batch(0) if shards else None
-            if pipelined and nxt is not None:
+            if nxt is not None:
                 eng.stage_inputs(0, nxt[0], None, nxt[1], subnet=shards[0][0])
             for k, (si, ids) in enumerate(shards):
                 cur = nxt
-                nxt = host_batch(k + 1) if k + 1 < len(shards) else None
-                if pipelined and nxt is not None:
-                    eng.stage_inputs((k + 1) & 1, nxt[0], None, nxt[1], subnet=shards[k + 1][0])
                 if cur is not None:
                     if cur[2] is not None:   # A6: encoder targets of this step (copied on the compute stream)
                         eng.set_encoder_targets(cur[2])
-                    if pipelined:
-                        loss, ntok = eng.train_step_grads_staged(k & 1, seed=step)
-                    else:
-                        loss, ntok = eng.train_step_grads(cur[0], None, cur[1], subnet=si, seed=step)
+                    eng.train_step_grads_staged(k & 1, seed=step, want_loss=False)      # enqueue only
+                # assemble and stage the next minibatch while this one computes
+                nxt = host_batch(k + 1) if k + 1 < len(shards) else None
+                if nxt is not None:
+                    eng.stage_inputs((k + 1) & 1, nxt[0], None, nxt[1], subnet=shards[k + 1][0])
+                if cur is not None:
+                    loss, ntok, aux_loss, _ = eng.last_losses()                         # waits for step k
+                    loss += aux_loss
                 else:   # fewer utterances than ranks: contribute zero gradients
                     flat_tensor(eng, _lib.GRAD).zero_()
                     loss, ntok = 0.0, 0

@@ -20,7 +20,7 @@ from typing import Dict, Iterable, Iterator, List, Optional, Sequence
 import numpy as np
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libe2t_io.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 _P = C.c_void_p
 _U8P = C.POINTER(C.c_uint8)
 _SIGNATURES = {
@@ -47,6 +47,7 @@ _SIGNATURES = {
     "e2t_example_builder_add_int64s": (C.c_int, [_P, C.c_char_p, _P, C.c_uint64]),
     "e2t_example_builder_finish": (C.c_int, [_P, C.POINTER(_U8P), C.POINTER(C.c_uint64)]),
     "e2t_pad_batch_f32": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_P), _P]),
+    "e2t_pad_batch_f32_mt": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_P), _P, C.c_int]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 _lib = None
@@ -221,8 +222,10 @@ def read_examples(paths: Iterable[str], manifests: Dict[str, "object"], check_cr
             yield parse_example(rec, manifests, cache)
 
 
-def pad_batch_f32(seqs: List[np.ndarray], T_pad: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
-    """Zero-padded [B, T_pad, C] batch of variable-length [T_i, C] fp32 sequences (padding_value 0.0)."""
+def pad_batch_f32(seqs: List[np.ndarray], T_pad: Optional[int] = None, out: Optional[np.ndarray] = None,
+                  threads: int = 1) -> np.ndarray:
+    """Zero-padded [B, T_pad, C] batch of variable-length [T_i, C] fp32 sequences (padding_value 0.0).  `out`: write into this
+    buffer (e.g. a page-locked staging buffer); `threads` > 1 splits the utterances over native worker threads."""
     lib = load()
     B = len(seqs)
     C_ = int(seqs[0].shape[1])
@@ -233,5 +236,8 @@ def pad_batch_f32(seqs: List[np.ndarray], T_pad: Optional[int] = None, out: Opti
     assert out.shape == (B, T_pad, C_) and out.dtype == np.float32 and out.flags.c_contiguous
     keep = [np.ascontiguousarray(s, np.float32) for s in seqs]
     ptrs = (_P * B)(*[k.ctypes.data for k in keep])
-    _ck(lib.e2t_pad_batch_f32(out.ctypes.data_as(_P), B, T_pad, C_, ptrs, lens.ctypes.data_as(_P)))
+    if threads > 1:
+        _ck(lib.e2t_pad_batch_f32_mt(out.ctypes.data_as(_P), B, T_pad, C_, ptrs, lens.ctypes.data_as(_P), int(threads)))
+    else:
+        _ck(lib.e2t_pad_batch_f32(out.ctypes.data_as(_P), B, T_pad, C_, ptrs, lens.ctypes.data_as(_P)))
     return out

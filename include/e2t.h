@@ -156,6 +156,10 @@ int e2t_set_encoder_targets(e2t_handle* h, const void* targets, int loc, int B, 
 /* the two terms of the most recent loss: penalty_scale * sum CE over `ntok` tokens, aux_penalty * sum over
  * `aux_frames` frames (0 when the head did not run); loss_sum of the calls above is their sum.  Synchronises. */
 int e2t_last_losses(e2t_handle* h, float* decoder_sum, int32_t* ntok, float* aux_sum, int32_t* aux_frames);
+/* page-locked host memory for the caller's staging buffers: e2t_stage_inputs copies from it without an intermediate
+ * pageable -> pinned bounce, i.e. asynchronously with respect to the host and to the compute stream */
+int e2t_host_alloc(void** out, int64_t bytes);
+int e2t_host_free(void* p);
 /* Adam + EMA on the trainable tensors of `subnet` (private) and the shared ones, using
  * grad * grad_scale (1 / global token count).  subnet < 0: every subnet. */
 int e2t_adam_ema_step(e2t_handle* h, int subnet, float grad_scale);

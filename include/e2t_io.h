@@ -61,6 +61,9 @@ int e2t_example_builder_add_int64s(e2t_example_builder* b, const char* key, cons
 int e2t_example_builder_finish(e2t_example_builder* b, const uint8_t** out, uint64_t* len);
 
 int e2t_pad_batch_f32(float* dst, int64_t B, int64_t T_pad, int64_t C, const float* const* src, const int64_t* lens);
+/* the same with the utterances split over n_threads worker threads (dst is typically a page-locked staging buffer) */
+int e2t_pad_batch_f32_mt(float* dst, int64_t B, int64_t T_pad, int64_t C, const float* const* src, const int64_t* lens,
+                         int n_threads);
 
 #ifdef __cplusplus
 }

@@ -210,3 +210,37 @@ def test_maximum_utterance_length(emu_lib):
     one in the same batch: 313 recurrent steps per layer and direction; and the decode of such a batch"""
     pc.check_train_step(emu_lib, pc.TINY, 2, 1250, 3)
     pc.check_decode(emu_lib, pc.TINY, 2, 1250, 4, margin=1e-4)
+
+
+def test_staged_inputs_and_host_buffers(emu_lib):
+    """e2t_stage_inputs / E2T_STAGED* (synchronous in the emulation build, same slots and bookkeeping) from page-locked-style
+    host buffers (e2t_host_alloc): same loss / gradients as the plain host path, shape mix-ups are errors"""
+    import numpy as np
+    from ecog2txt_b200 import E2TError, _lib
+    from oracle import seq2seq_oracle as O
+    ocfg = O.OracleConfig(**pc.TINY)
+    P = pc.make_params(ocfg)
+    eng = pc.engine_for(pc.TINY, emu_lib, 4, 19, 5, gemm_backend="simt")
+    eng.set_all({k: v.numpy() for k, v in P.items()})
+    batches = [pc.make_batch(ocfg, 4, 19, 5, seed=s) for s in range(3)]
+    ref = []
+    for x, _, y in batches:
+        loss, ntok = eng.train_step_grads(x, None, y, seed=7)
+        ref.append((loss, ntok, eng.get_all(_lib.GRAD)))
+    ring = [eng.host_buffer((4, 19, 6), np.float32) for _ in range(3)]
+    with pytest.raises(E2TError, match="never staged"):
+        eng._staged_shape = {1: (4, 19, 5, 0)}
+        eng.train_step_grads_staged(1)
+    for i, (x, _, y) in enumerate(batches):
+        ring[i % 3][...] = x
+        eng.stage_inputs(i & 1, ring[i % 3], None, y)
+        eng.train_step_grads_staged(i & 1, seed=7, want_loss=False)
+        ld, nt, la, nf = eng.last_losses()
+        assert (ld, nt, la, nf) == (ref[i][0], ref[i][1], 0.0, 0)
+        g = eng.get_all(_lib.GRAD)
+        for k in g:
+            assert np.array_equal(g[k], ref[i][2][k]), k
+    with pytest.raises(E2TError, match="another shape"):
+        eng._staged_shape[0] = (3, 19, 5, 0)
+        eng.train_step_grads_staged(0, seed=7)
+    eng.close()

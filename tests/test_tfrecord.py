@@ -141,3 +141,17 @@ def test_sentence_tokenize_and_class_list(tmp_path):
     man = {"decoder_targets": SequenceDataManifest("text_sequence", get_feature_list=lambda: classes, APPEND_EOS=True)}
     (ex,) = list(tfrecord.read_examples([path], man))
     assert ex["decoder_targets"].tolist() == [3, 4, 2, 1]
+
+
+def test_multithreaded_batch_assembly_matches_single_thread():
+    """e2t_pad_batch_f32_mt: utterances split over native threads, written into a caller-provided buffer"""
+    rs = np.random.RandomState(0)
+    seqs = [rs.randn(int(n), 7).astype(np.float32) for n in rs.randint(0, 40, size=37)]
+    seqs[3] = np.zeros((0, 7), np.float32)                       # an empty utterance
+    ref = tfrecord.pad_batch_f32(seqs, 40)
+    for threads in (2, 5, 64):
+        out = np.full((37, 40, 7), np.nan, np.float32)
+        got = tfrecord.pad_batch_f32(seqs, 40, out=out, threads=threads)
+        assert got is out and np.array_equal(out, ref)
+    with pytest.raises(tfrecord.TFRecordError):
+        tfrecord.pad_batch_f32(seqs, 20, threads=4)              # longer than the padded length
