@@ -244,3 +244,19 @@ def test_staged_inputs_and_host_buffers(emu_lib):
         eng._staged_shape[0] = (3, 19, 5, 0)
         eng.train_step_grads_staged(0, seed=7)
     eng.close()
+
+
+def test_attention_long_targets(emu_lib):
+    """more decoder steps than the encoder-gradient kernel keeps in registers at once (12) and than a block has warps (16):
+    the chunked accumulation over decoder steps and the row-group loop of the attention kernels"""
+    pc.check_train_step(emu_lib, pc.TINY_ATTN, 2, 19, 14)
+    pc.check_train_step(emu_lib, pc.TINY_BAH, 2, 19, 14)
+    pc.check_train_step(emu_lib, pc.TINY_BAH, 2, 19, 19, ff=0.1, rnn=0.5)
+
+
+def test_attention_odd_width(emu_lib):
+    """decoder width not a multiple of 4 (scalar staging of the encoder rows, ragged last register of a lane)"""
+    odd = dict(pc.TINY, H=(8, 7), Hd=14)
+    pc.check_train_step(emu_lib, dict(odd, attention="luong"), 3, 19, 5)
+    pc.check_train_step(emu_lib, dict(odd, attention="bahdanau"), 3, 19, 5, ff=0.1, rnn=0.5)
+    pc.check_decode(emu_lib, dict(odd, attention="bahdanau"), 4, 21, 6, beam=3, margin=1e-5)
