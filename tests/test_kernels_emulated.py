@@ -260,3 +260,27 @@ def test_attention_odd_width(emu_lib):
     pc.check_train_step(emu_lib, dict(odd, attention="luong"), 3, 19, 5)
     pc.check_train_step(emu_lib, dict(odd, attention="bahdanau"), 3, 19, 5, ff=0.1, rnn=0.5)
     pc.check_decode(emu_lib, dict(odd, attention="bahdanau"), 4, 21, 6, beam=3, margin=1e-5)
+
+
+def test_input_saliency_device_buffers(emu_lib):
+    """loc = E2T_DEVICE: inputs used in place, dx / sq_norms written straight into the caller's device buffers (plain host
+    memory in the emulation build) -- same numbers as the host-buffer call"""
+    import ctypes as C
+    import numpy as np
+    from ecog2txt_b200 import _lib
+    from oracle import seq2seq_oracle as O
+    ocfg = O.OracleConfig(**pc.TINY)
+    P = pc.make_params(ocfg)
+    eng = pc.engine_for(pc.TINY, emu_lib, 3, 19, 5, gemm_backend="simt")
+    eng.set_all({k: v.numpy() for k, v in P.items()})
+    x, lens, y = pc.make_batch(ocfg, 3, 19, 5)
+    dx_h, sq_h = eng.input_saliency(x, None, y)
+    dx_d, sq_d = np.full_like(dx_h, np.nan), np.full_like(sq_h, np.nan)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
+    eng._ck(eng._lib.e2t_input_saliency(eng._h, 0, vp(x), None, vp(y), _lib.DEVICE, 3, 19, 5, 0, 1.0, 0.0, vp(dx_d), vp(sq_d)))
+    eng.sync()
+    assert np.array_equal(dx_d, dx_h) and np.array_equal(sq_d, sq_h)
+    eng._ck(eng._lib.e2t_input_saliency(eng._h, 0, vp(x), vp(lens), vp(y), _lib.DEVICE, 3, 19, 5, 0, 1.0, 0.0, None, vp(sq_d)))
+    eng.sync()
+    assert np.array_equal(sq_d, sq_h)             # explicit lengths, norms only
+    eng.close()
