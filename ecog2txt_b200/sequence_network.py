@@ -145,8 +145,8 @@ class SequenceNetwork:
                 for ex in tfrecord.read_examples(paths, mans)]
 
     @staticmethod
-    def _batch(examples, idx, T_pad, L_pad, pad_id):
-        x = tfrecord.pad_batch_f32([examples[i][0] for i in idx], T_pad)
+    def _batch(examples, idx, T_pad, L_pad, pad_id, threads=1):
+        x = tfrecord.pad_batch_f32([examples[i][0] for i in idx], T_pad, threads=threads)
         y = np.full((len(idx), L_pad), pad_id, np.int32)
         for r, i in enumerate(idx):
             t = examples[i][1]
@@ -300,7 +300,7 @@ class SequenceNetwork:
             if bi % world != rank:
                 continue
             idx = np.arange(i, min(i + self.N_cases, len(examples)))
-            x, y = self._batch(examples, idx, max_T, max_L, pad_id)
+            x, y = self._batch(examples, idx, max_T, max_L, pad_id, threads=self.loader_threads)
             if self.inputs_to_occlude is not None and len(self.inputs_to_occlude):
                 # test-time occlusion (plotters.py:603-640): the listed input channels are silenced for this assessment
                 x[:, :, np.asarray(self.inputs_to_occlude, int)] = 0.0
@@ -364,7 +364,7 @@ class SequenceNetwork:
         norms, seqs = [], []
         for i in range(0, len(examples), self.N_cases):
             idx = np.arange(i, min(i + self.N_cases, len(examples)))
-            x, y = self._batch(examples, idx, max_T, max_L, eng.cfg.pad_id)
+            x, y = self._batch(examples, idx, max_T, max_L, eng.cfg.pad_id, threads=self.loader_threads)
             aux = self._aux_batch(examples, idx, max_T)
             if aux is not None:
                 eng.set_encoder_targets(aux)
@@ -393,7 +393,7 @@ class SequenceNetwork:
         for i in range(0, len(examples), self.N_cases):
             idx = np.arange(i, min(i + self.N_cases, len(examples)))
             B = len(idx)
-            x, y = self._batch(examples, idx, max_T, max_L, eng.cfg.pad_id)
+            x, y = self._batch(examples, idx, max_T, max_L, eng.cfg.pad_id, threads=self.loader_threads)
             eng.eval_loss(x, None, y, subnet=si, use_ema=float(self.EMA_decay) > 0)
             lens = eng.activation("lens", (B,), np.int32)
             conv.append(eng.activation("conv_out", (T2, B, eng.cfg.E)).transpose(1, 0, 2))
