@@ -284,3 +284,36 @@ def test_input_saliency_device_buffers(emu_lib):
     eng.sync()
     assert np.array_equal(sq_d, sq_h)             # explicit lengths, norms only
     eng.close()
+
+
+def test_size_independent_properties(emu_lib):
+    """the properties the full-size GPU test pins, on the emulated kernels: zero-padding invariance (lengths are inferred from
+    the padding), batch additivity of the summed-loss gradient, eval loss == training loss without dropout, determinism"""
+    import numpy as np
+    from ecog2txt_b200 import _lib
+    from oracle import seq2seq_oracle as O
+    ocfg = O.OracleConfig(**pc.SMALL)
+    P = pc.make_params(ocfg)
+    x, lens, y = pc.make_batch(ocfg, 6, 50, 6)
+    eng = pc.engine_for(pc.SMALL, emu_lib, 6, 62, 6, gemm_backend="simt")
+    eng.set_all({k: v.numpy() for k, v in P.items()})
+    loss, ntok = eng.train_step_grads(x, None, y, seed=3)
+    g1 = eng.get_all(_lib.GRAD)
+    loss_b, _ = eng.train_step_grads(x, None, y, seed=3)
+    g2 = eng.get_all(_lib.GRAD)
+    assert loss == loss_b and all(np.array_equal(g1[k], g2[k]) for k in g1)
+    le, ne = eng.eval_loss(x, None, y)
+    assert ne == ntok and abs(le - loss) <= 1e-5 * abs(loss)
+    xp = np.zeros((6, 62, 32), np.float32)
+    xp[:, :50] = x
+    loss_p, _ = eng.train_step_grads(xp, None, y, seed=3)
+    gp = eng.get_all(_lib.GRAD)
+    assert abs(loss_p - loss) <= 1e-5 * abs(loss) and all(pc.rel_err(gp[k], g1[k]) <= 1e-4 for k in g1)
+    acc, ltot = None, 0.0
+    for lo in (0, 3):
+        l_h, _ = eng.train_step_grads(np.ascontiguousarray(x[lo:lo + 3]), None, np.ascontiguousarray(y[lo:lo + 3]), seed=3)
+        gh = eng.get_all(_lib.GRAD)
+        ltot += l_h
+        acc = gh if acc is None else {k: acc[k] + gh[k] for k in gh}
+    assert abs(ltot - loss) <= 1e-4 * abs(loss) and all(pc.rel_err(acc[k], g1[k]) <= 1e-4 for k in g1)
+    eng.close()
