@@ -13,11 +13,12 @@ E2T_MAX_SUBNETS = 16
 E2T_MAX_LAYERS = 8
 HOST, DEVICE, STAGED0, STAGED1 = 0, 1, 2, 3
 VALUE, GRAD, ADAM_M, ADAM_V, EMA = 0, 1, 2, 3, 4
+GRAD_AND_COUNT = 5   # e2t_flat_buffer only: gradients + [token count, 0, 0, 0] -- ONE all-reduce per data-parallel step
 ACT = {"linear": 0, "relu": 1}
 GEMM = {"auto": 0, "simt": 1, "tcgen05": 2}
 ATTN = {"none": 0, "luong": 1, "bahdanau": 2}
 AUX_KIND = {"gaussian": 0, "categorical": 1}
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class E2TConfig(C.Structure):
@@ -82,6 +83,8 @@ _SIGNATURES = {
     "e2t_train_step_grads": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                        C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "e2t_stage_inputs": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
+    "e2t_read_loss_accumulators": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
+    "e2t_wait_staged": (C.c_int, [_P, C.c_int]),
     "e2t_host_alloc": (C.c_int, [C.POINTER(_P), C.c_int64]),
     "e2t_host_free": (C.c_int, [_P]),
     "e2t_set_grad_buckets": (C.c_int, [_P, C.c_int]),

@@ -30,7 +30,7 @@
 
 static thread_local std::string g_err;
 extern "C" const char* e2t_last_error(void) { return g_err.c_str(); }
-extern "C" int e2t_abi_version(void) { return 6; }
+extern "C" int e2t_abi_version(void) { return 7; }
 
 namespace {
 
@@ -131,6 +131,7 @@ struct e2t_handle {
   float *h0, *c0, *dh0, *dc0, *dh_rec, *dc_rec;
   float *demb, *ddemb, *dgates, *dcs, *hdec, *dhdec, *logits, *loss_rows, *d_loss;
   int* d_ntok;
+  double* d_acc = nullptr;   // running [decoder loss, tokens, aux loss, aux frames] over training steps (e2t_read_loss_accumulators)
   float* colsum_ws = nullptr; i64 colsum_ws_n = 0;   // [64, N] partial column sums
   float* perm_ws = nullptr; i64 perm_ws_n = 0;       // [(In+H+1), 4H] weight + bias gradients in permuted gate order
   // batched small jobs (k_batch): pending list + device table
@@ -160,7 +161,7 @@ struct e2t_handle {
   cudaEvent_t st_ready[2] = {nullptr, nullptr}, st_done[2] = {nullptr, nullptr};
 #endif
   // decode workspace
-  float *g_h[2], *g_c[2], *g_e, *g_z, *g_logits, *g_logp, *g_score[2], *g_lse;
+  float *g_h[3], *g_c[3], *g_e, *g_z, *g_logits, *g_logp, *g_score[2], *g_lse;
   int *g_prev[2], *g_done[2], *g_tokens[2], *g_src, *g_tok;
   // last-forward bookkeeping for e2t_get_activation
   int last_B = 0, last_T2 = 0, last_L = 0, last_subnet = 0;
@@ -480,7 +481,8 @@ void build_workspace(e2t_handle* h) {
   h->T2m = (int)cdiv(c.max_T, minW);
   h->Dp = round_up(c.D, 4); h->Vp = round_up(c.V, 4);
   const i64 Bm = h->Bm, T2 = h->T2m, Lm = h->Lm;
-  h->P = h->alloc<float>(h->n_params); h->G = h->alloc<float>(h->n_params);
+  // G carries 4 extra floats: [unmasked-token count of the last training step, 0, 0, 0] (E2T_GRAD_AND_COUNT)
+  h->P = h->alloc<float>(h->n_params); h->G = h->alloc<float>(h->n_params + 4);
   h->M = h->alloc<float>(h->n_params); h->Vv = h->alloc<float>(h->n_params);
   h->S = h->alloc<float>(h->n_params);
   h->d_x = h->alloc<float>(Bm * h->Tm * h->Cmax);
@@ -526,6 +528,7 @@ void build_workspace(e2t_handle* h) {
   h->logits = h->alloc<float>(Lm * Bm * h->Vp);
   h->loss_rows = h->alloc<float>(Lm * Bm);
   h->d_loss = h->alloc<float>(4); h->d_ntok = h->alloc<int>(4);
+  h->d_acc = h->alloc<double>(4);
   h->colsum_ws_n = (i64)64 * std::max<i64>(std::max<i64>(4 * Hmax, h->Vp), std::max<i64>(c.E, h->Dp));
   h->colsum_ws = h->alloc<float>(h->colsum_ws_n);
   if (h->perm_ws_n) h->perm_ws = h->alloc<float>(h->perm_ws_n);
@@ -589,6 +592,9 @@ void build_workspace(e2t_handle* h) {
   const i64 R = Bm * h->beam_m;
   for (int i = 0; i < 2; ++i) {
     h->g_h[i] = h->alloc<float>(R * c.Hd); h->g_c[i] = h->alloc<float>(R * c.Hd);
+    if (i == 1) {   // beam search rotates (h, c) through a third, dedicated buffer (any beam <= max_beam fits)
+      h->g_h[2] = h->alloc<float>(R * c.Hd); h->g_c[2] = h->alloc<float>(R * c.Hd);
+    }
     h->g_score[i] = h->alloc<float>(R);
     h->g_prev[i] = h->alloc<int>(R); h->g_done[i] = h->alloc<int>(R);
     h->g_tokens[i] = h->alloc<int>(R * Lm);
@@ -886,7 +892,8 @@ void decoder_forward(e2t_handle* h, const Inputs& in, int B, int L, bool train, 
   gemm(h, proj_in, c.Hd, 1, Wc + h->proj_w, 1, c.Hd, h->logits, h->Vp, (int)rows, c.V, c.Hd, Wc + h->proj_b, 0.f);
   LAUNCH(h, k_softmax_ce, dim3((unsigned)rows), dim3(128), 0, h->logits, h->Vp, c.V, h->d_tgt, c.pad_id,
          h->pen_dec, h->loss_rows, with_grad ? 1 : 0);
-  LAUNCH(h, k_reduce_loss, dim3(1), dim3(256), 0, h->loss_rows, h->d_tgt, c.pad_id, (int)rows, h->d_loss, h->d_ntok);
+  LAUNCH(h, k_reduce_loss, dim3(1), dim3(256), 0, h->loss_rows, h->d_tgt, c.pad_id, (int)rows, h->d_loss, h->d_ntok,
+         with_grad ? h->G + h->n_params : (float*)nullptr, (with_grad && train) ? h->d_acc : (double*)nullptr);
   h->last_L = L;
 }
 
@@ -932,7 +939,8 @@ void aux_forward(e2t_handle* h, int subnet, int B, int T, bool train, uint32_t s
   p.lens = h->d_lens; p.lens2 = h->d_lens2; p.B = B; p.T = T; p.W = W; p.rows = rows;
   p.scale = h->pen_aux; p.loss_row = h->aux_loss_rows; p.cnt_row = h->aux_cnt_rows; p.with_grad = with_grad ? 1 : 0;
   LAUNCH(h, k_aux_loss, dim3((unsigned)rows), dim3(32), 0, p);
-  LAUNCH(h, k_reduce_aux, dim3(1), dim3(256), 0, h->aux_loss_rows, h->aux_cnt_rows, rows, h->d_loss + 1, h->d_ntok + 1);
+  LAUNCH(h, k_reduce_aux, dim3(1), dim3(256), 0, h->aux_loss_rows, h->aux_cnt_rows, rows, h->d_loss + 1, h->d_ntok + 1,
+         (with_grad && train) ? h->d_acc : (double*)nullptr);
   h->aux_ran = true;
 }
 
@@ -1377,8 +1385,13 @@ extern "C" int e2t_set_tensor(e2t_handle* h, const char* name, int which, const 
 
 extern "C" int e2t_flat_buffer(e2t_handle* h, int which, void** dev_ptr, int64_t* n) {
   API_BEGIN NEED_H;
-  if (dev_ptr) *dev_ptr = flat_of(h, which);
-  if (n) *n = h->n_params;
+  if (which == E2T_GRAD_AND_COUNT) {
+    if (dev_ptr) *dev_ptr = h->G;
+    if (n) *n = h->n_params + 4;
+  } else {
+    if (dev_ptr) *dev_ptr = flat_of(h, which);
+    if (n) *n = h->n_params;
+  }
   API_END
 }
 
@@ -1465,8 +1478,8 @@ extern "C" int e2t_adam_ema_step(e2t_handle* h, int subnet, float grad_scale) {
 }
 extern "C" int e2t_adam_ema_step_dev(e2t_handle* h, int subnet, const float* token_count_dev) {
   API_BEGIN NEED_H;
-  E2T_REQUIRE(token_count_dev != nullptr, "token_count_dev is NULL");
-  adam_ema_step(h, subnet, 0.f, token_count_dev);
+  // NULL: the count slot behind the gradient buffer (E2T_GRAD_AND_COUNT), i.e. after ONE all-reduce of that range
+  adam_ema_step(h, subnet, 0.f, token_count_dev ? token_count_dev : h->G + h->n_params);
   API_END
 }
 static void adam_ema_step(e2t_handle* h, int subnet, float grad_scale, const float* count_dev) {
@@ -1571,6 +1584,25 @@ extern "C" int e2t_last_losses(e2t_handle* h, float* decoder_sum, int32_t* ntok,
   if (ntok) *ntok = n[0];
   if (aux_sum) *aux_sum = h->aux_ran ? l[1] : 0.f;
   if (aux_frames) *aux_frames = h->aux_ran ? n[1] : 0;
+  API_END
+}
+
+extern "C" int e2t_read_loss_accumulators(e2t_handle* h, double* out4, int reset) {
+  API_BEGIN NEED_H;
+  double a[4] = {0, 0, 0, 0};
+  E2T_CHECK(cudaMemcpyAsync(a, h->d_acc, sizeof(a), cudaMemcpyDeviceToHost, h->stream));
+  if (reset) E2T_CHECK(cudaMemsetAsync(h->d_acc, 0, sizeof(a), h->stream));
+  E2T_CHECK(cudaStreamSynchronize(h->stream));
+  if (out4) for (int i = 0; i < 4; ++i) out4[i] = a[i];
+  API_END
+}
+
+extern "C" int e2t_wait_staged(e2t_handle* h, int slot) {
+  API_BEGIN NEED_H;
+  E2T_REQUIRE(slot == 0 || slot == 1, "slot must be 0 or 1");
+#ifndef E2T_EMU
+  if (h->st_ready[slot]) E2T_CHECK(cudaEventSynchronize(h->st_ready[slot]));
+#endif
   API_END
 }
 
@@ -1715,12 +1747,10 @@ extern "C" int e2t_beam_decode(e2t_handle* h, int subnet, const float* x, const 
   LAUNCH(h, k_fill_int, grid1(R), dim3(256), 0, h->g_prev[0], c.start_id, (i64)R);
   E2T_CHECK(cudaMemsetAsync(h->g_done[0], 0, (size_t)R * sizeof(int), h->stream));
   LAUNCH(h, k_fill_int, grid1((i64)R * max_len), dim3(256), 0, h->g_tokens[0], c.pad_id, (i64)R * max_len);
-  // a third state buffer for the reordered result (reuse dh0/dc0-sized scratch is too small -> use hdec/dhdec heads)
-  E2T_REQUIRE((i64)R * c.Hd <= (i64)h->Lm * h->Bm * c.Hd, "beam workspace too small (max_L*max_B < B*beam)");
   // (h, c) rotate through three buffers -- live beams, decode_step's candidates, the reordered survivors -- so that no copy
   // back is needed; scores / tokens / flags ping-pong between their two buffers
-  float* hb[3] = {h->g_h[0], h->g_h[1], h->hdec};
-  float* cb[3] = {h->g_c[0], h->g_c[1], h->dhdec};
+  float* hb[3] = {h->g_h[0], h->g_h[1], h->g_h[2]};
+  float* cb[3] = {h->g_c[0], h->g_c[1], h->g_c[2]};
   int sl = 0, sn = 1, sr = 2;      // state slots: live, new, reordered
   int cur = 0;
   for (int k = 0; k < max_len; ++k) {

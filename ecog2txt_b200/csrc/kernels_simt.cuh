@@ -815,8 +815,10 @@ __global__ void __launch_bounds__(128) k_softmax_ce(float* logits, int ld, int V
   }
 }
 // deterministic single-block reduction of the per-row losses and the unmasked-token count
+// count_f (nullable): the token count as fp32 in the slot behind the gradient buffer (rides on the gradient all-reduce);
+// acc (nullable): running [loss sum, token count] over the training steps since the last read (no per-step host sync)
 __global__ void __launch_bounds__(256) k_reduce_loss(const float* loss_row, const int* tgt, int pad_id, int rows,
-                                                     float* loss_out, int* ntok_out) {
+                                                     float* loss_out, int* ntok_out, float* count_f, double* acc) {
   __shared__ float red[32];
   float s = 0.f, n = 0.f;
   for (int i = threadIdx.x; i < rows; i += blockDim.x) {
@@ -825,7 +827,11 @@ __global__ void __launch_bounds__(256) k_reduce_loss(const float* loss_row, cons
   }
   s = block_sum(s, red);
   n = block_sum(n, red);
-  if (threadIdx.x == 0) { *loss_out = s; *ntok_out = (int)(n + 0.5f); }
+  if (threadIdx.x == 0) {
+    *loss_out = s; *ntok_out = (int)(n + 0.5f);
+    if (count_f) *count_f = n;
+    if (acc) { acc[0] += (double)s; acc[1] += (double)n; }
+  }
 }
 
 // hi = x with the 13 low mantissa bits cleared (exactly representable in TF32), lo = x - hi: operands of a 3xTF32 product
@@ -905,13 +911,13 @@ __global__ void __launch_bounds__(32) k_aux_loss(AuxP p) {
 }
 // deterministic single-block reduction of the per-row head losses and the unmasked-frame count
 __global__ void __launch_bounds__(256) k_reduce_aux(const float* loss_row, const int* cnt_row, int rows, float* loss_out,
-                                                    int* cnt_out) {
+                                                    int* cnt_out, double* acc) {
   __shared__ float red[32];
   float s = 0.f, n = 0.f;
   for (int i = threadIdx.x; i < rows; i += blockDim.x) { s += loss_row[i]; n += (float)cnt_row[i]; }
   s = block_sum(s, red);
   n = block_sum(n, red);
-  if (threadIdx.x == 0) { *loss_out = s; *cnt_out = (int)(n + 0.5f); }
+  if (threadIdx.x == 0) { *loss_out = s; *cnt_out = (int)(n + 0.5f); if (acc) { acc[2] += (double)s; acc[3] += (double)n; } }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -31,6 +31,15 @@ def shard_range(n_items: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def allreduce_step(grads_and_count):
+    """THE collective of a data-parallel training step: one flat all-reduce (sum) over `flat_tensor(engine,
+    GRAD_AND_COUNT)` -- the 57 MB gradient bucket with the token count riding in its tail.  Enqueue-only: no host
+    synchronisation; follow with engine.adam_ema_step_dev(None)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(grads_and_count)
+
+
 def allreduce_grads(engine, grads_tensor, ntok_local: float):
     """One flat all-reduce (sum) of the gradient bucket + the token count; returns the global count."""
     import torch
@@ -61,6 +70,9 @@ class BucketedAllReduce:
         self.grads = flat_tensor(engine, L.GRAD)
         self.emulated = getattr(engine, "emulated", False)
         self.comm = None if self.emulated else torch.cuda.Stream(device=self.grads.device)
+        if not self.emulated:
+            # the per-bucket all-reduces are ordered against torch's current stream: the library must enqueue there too
+            engine.set_stream(torch.cuda.current_stream(self.grads.device).cuda_stream)
         engine.set_grad_buckets(True)
 
     def reduce_async(self, ntok_t):

@@ -303,11 +303,23 @@ class Engine:
     def adam_ema_step(self, grad_scale: float, subnet: int = -1):
         self._ck(self._lib.e2t_adam_ema_step(self._h, subnet, float(grad_scale)))
 
-    def adam_ema_step_dev(self, token_count, subnet: int = -1):
+    def adam_ema_step_dev(self, token_count=None, subnet: int = -1):
         """Adam + EMA with grad_scale = 1 / max(token_count, 1) read on the device: `token_count` is a 1-element float32
-        device tensor (numpy in the emulation build), e.g. the all-reduced token count -- no host synchronisation."""
-        p, _ = _ptr(token_count)
+        device tensor (numpy in the emulation build), e.g. the all-reduced token count -- no host synchronisation.
+        None: the count slot behind the gradient buffer (flat_buffer(GRAD_AND_COUNT), all-reduced with the gradients)."""
+        p = None if token_count is None else _ptr(token_count)[0]
         self._ck(self._lib.e2t_adam_ema_step_dev(self._h, subnet, p))
+
+    def read_loss_accumulators(self, reset: bool = True):
+        """(decoder loss sum, tokens, encoder-targets loss sum, frames) over the training steps since the last reset;
+        one host synchronisation."""
+        out = (C.c_double * 4)()
+        self._ck(self._lib.e2t_read_loss_accumulators(self._h, out, int(reset)))
+        return float(out[0]), int(round(out[1])), float(out[2]), int(round(out[3]))
+
+    def wait_staged(self, slot: int):
+        """Block until the latest stage_inputs copy into `slot` has finished (its host buffer may then be rewritten)."""
+        self._ck(self._lib.e2t_wait_staged(self._h, int(slot)))
 
     def eval_loss(self, x, lens, y, subnet: int = 0, use_ema: bool = False):
         px, pl, py, loc, B, T = self._inputs(x, lens, y)

@@ -2,6 +2,7 @@
 
 * ``target_inds_to_sequences`` -- /root/reference/ecog2txt/trainers.py:952-963
 * ``wer_vector``               -- utils_jgm.toolbox.wer_vector as used at /root/reference/ecog2txt/subjects.py:546-549
+* ``confusion_counts``         -- the `.decoder_confusions` the reference reads at /root/reference/ecog2txt/trainers.py:604-611
 """
 from __future__ import annotations
 
@@ -37,3 +38,13 @@ def word_error_rate(ref_words: Sequence[str], hyp_words: Sequence[str]) -> float
 
 def wer_vector(references: Sequence[str], hypotheses: Sequence[str]) -> np.ndarray:
     return np.asarray([word_error_rate(r.split(), h.split()) for r, h in zip(references, hypotheses)], np.float64)
+
+
+def confusion_counts(targets: np.ndarray, predictions: np.ndarray, num_classes: int, pad_id: int = 0) -> np.ndarray:
+    """[V, V] int64 counts: entry (i, j) = how often target class i was decoded as class j, over the unmasked (non-pad)
+    target positions (rows = true token, columns = decoded token -- the axes the reference labels with the class list
+    on both sides, trainers.py:606-616).  targets / predictions: integer arrays of equal shape, position-aligned."""
+    t = np.asarray(targets).reshape(-1).astype(np.int64)
+    p = np.asarray(predictions).reshape(-1).astype(np.int64)
+    keep = (t != pad_id) & (p >= 0) & (p < num_classes)
+    return np.bincount(t[keep] * num_classes + p[keep], minlength=num_classes * num_classes).reshape(num_classes, num_classes)

@@ -26,17 +26,42 @@ def glorot_init(shapes: Dict[str, tuple], seed: int = 1) -> Dict[str, np.ndarray
     return out
 
 
-def init_engine(engine, seed: int = 1):
+def init_engine(engine, seed: int = 1, keep=()):
+    """Fresh variables (Glorot / zero biases; the EMA shadow follows the value), zeroed Adam slots.  Tensors named in `keep`
+    (just restored from a checkpoint) are left alone.  The reference builds and initialises a new graph for every fit; a
+    cached engine must not carry weights or optimiser state over from the previous one."""
     shapes = {k: s for k, (s, _) in engine.tensors().items()}
-    engine.set_all(glorot_init(shapes, seed))
+    fresh = glorot_init(shapes, seed)
+    keep = set(keep)
+    for name, val in fresh.items():
+        if name in keep:
+            continue
+        engine.set(name, val, L.VALUE)
+        z = np.zeros_like(val)
+        engine.set(name, z, L.ADAM_M)
+        engine.set(name, z, L.ADAM_V)
 
 
 EMA_SUFFIX = "/ExponentialMovingAverage"  # trainers.py:466-468
 
 
-def save_checkpoint(engine, checkpoint_path: str, epoch: int) -> str:
+def checkpoint_epochs(checkpoint_path: str):
+    """Sorted epochs of the checkpoints <checkpoint_path>-<epoch>.index on disk (trainers.py:240-252)."""
+    d, base = os.path.split(os.path.abspath(checkpoint_path))
+    out = []
+    if os.path.isdir(d):
+        for f in os.listdir(d):
+            m = re.fullmatch(re.escape(base) + r"-(\d+)\.index", f)
+            if m:
+                out.append(int(m.group(1)))
+    return sorted(out)
+
+
+def save_checkpoint(engine, checkpoint_path: str, epoch: int, max_to_keep: Optional[int] = 5) -> str:
     """<checkpoint_path>-<epoch>.index (manifest, discovered by restore_epoch: trainers.py:240-252)
-    + <checkpoint_path>-<epoch>.npz holding variables, EMA shadows and Adam slots under TF names."""
+    + <checkpoint_path>-<epoch>.npz holding variables, EMA shadows and Adam slots under TF names.
+    Both files are written to a temporary name and renamed (the .index last: a checkpoint exists once its index does), and
+    only the `max_to_keep` most recent checkpoints are kept, like the tf.train.Saver this replaces (None keeps all)."""
     arrays = {}
     for name in engine.tensors():
         arrays[name] = engine.get(name, L.VALUE)
@@ -46,10 +71,20 @@ def save_checkpoint(engine, checkpoint_path: str, epoch: int) -> str:
     arrays["global_step"] = np.asarray(engine.step, np.int64)
     base = f"{checkpoint_path}-{epoch}"
     os.makedirs(os.path.dirname(os.path.abspath(base)), exist_ok=True)
-    np.savez(base + ".npz", **arrays)
-    with open(base + ".index", "w") as f:
+    tmp = base + ".tmp.npz"
+    np.savez(tmp, **arrays)
+    os.replace(tmp, base + ".npz")
+    with open(base + ".index.tmp", "w") as f:
         for k, v in arrays.items():
             f.write(f"{k}\t{list(v.shape)}\n")
+    os.replace(base + ".index.tmp", base + ".index")
+    if max_to_keep:
+        for old in checkpoint_epochs(checkpoint_path)[:-int(max_to_keep)]:
+            for ext in (".index", ".npz"):      # index first: a half-deleted checkpoint is never discoverable
+                try:
+                    os.remove(f"{checkpoint_path}-{old}{ext}")
+                except OSError:
+                    pass
     return base
 
 

@@ -29,9 +29,9 @@ import numpy as np
 from . import EOS_token as _EOS, OOV_token as _OOV, pad_token as _PAD, _lib
 from . import params as prm
 from . import tfrecord
-from .dist import allreduce_grads, flat_tensor, shard_range
+from .dist import allreduce_step, flat_tensor, shard_range
 from .engine import Engine, EngineConfig
-from .metrics import target_inds_to_sequences, wer_vector
+from .metrics import confusion_counts, target_inds_to_sequences, wer_vector
 
 _MANIFEST_KEYS = dict(layer_sizes=None, FF_dropout=0.0, RNN_dropout=0.0, TEMPORALLY_CONVOLVE=True, EMA_decay=0.99,
                       N_epochs=800, beam_width=1, temperature=1.0, assessment_epoch_interval=10,
@@ -55,9 +55,9 @@ class SequenceNetwork:
             raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
         if self.layer_sizes is None:
             raise ValueError("layer_sizes must come from the manifest or a keyword")
-        if not self.TEMPORALLY_CONVOLVE:
-            raise NotImplementedError("this engine implements the temporally-convolving encoder only "
-                                      "(TEMPORALLY_CONVOLVE: true in every shipped manifest)")
+        # TEMPORALLY_CONVOLVE=False (README.md:80-83, trainers.py:386): the encoder embedding degenerates to a per-frame
+        # dense layer = a temporal convolution of width 1 / stride 1, which the same kernels run (W = 1) [CHOICE: the
+        # un-vendored graph builder is not visible; every shipped manifest sets it to true]
         self.EOS_token, self.pad_token, self.OOV_token = EOS_token, pad_token, OOV_token
         self.training_GPUs = list(training_GPUs)
         self.assessment_GPU = self.training_GPUs[0]
@@ -69,6 +69,7 @@ class SequenceNetwork:
         self.loader_threads = int(loader_threads) if loader_threads else max(1, min(8, (os.cpu_count() or 2) // 2))
         self.attention = attention       # "luong": optional A7 module (default "none" = the reference model)
         self.checkpoint_path: Optional[str] = None
+        self.max_to_keep = 5             # checkpoints kept on disk (tf.train.Saver default)
         self.inputs_to_occlude = None
         self._lib = lib
         self._engine: Optional[Engine] = None
@@ -87,7 +88,7 @@ class SequenceNetwork:
         geo = dict(
             subnet_ids=tuple(int(s.subnet_id) for s in subnets_params),
             subnet_C=tuple(int(s.data_manifests['encoder_inputs'].num_features) for s in subnets_params),
-            subnet_W=tuple(int(s.decimation_factor) for s in subnets_params),
+            subnet_W=tuple(int(s.decimation_factor) if self.TEMPORALLY_CONVOLVE else 1 for s in subnets_params),
             E=int(ls['encoder_embedding'][0]), H=tuple(int(h) for h in ls['encoder_rnn']),
             D=int(ls['decoder_embedding'][0]), Hd=int(ls['decoder_rnn'][0]), V=V,
             pad_id=flist.index(self.pad_token) if self.pad_token in flist else 0,
@@ -113,6 +114,14 @@ class SequenceNetwork:
         geo['penalty_scale'] = float(first['decoder_targets'].penalty_scale)
         return geo, flist
 
+    def _device(self) -> int:
+        """CUDA ordinal of this process: one process per GPU under torchrun -> LOCAL_RANK (training_GPUs = [0] is what the
+        reference hard-codes, trainers.py:131, and would put every rank on cuda:0); otherwise training_GPUs[0]."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and "LOCAL_RANK" in os.environ:
+            return int(os.environ["LOCAL_RANK"])
+        return int(self.training_GPUs[0])
+
     def _get_engine(self, subnets_params, max_T, max_L) -> Engine:
         geo, flist = self._geometry(subnets_params)
         key = (tuple(sorted(geo.items())), self.attention, self.FF_dropout, self.RNN_dropout, self.EMA_decay, int(self.beam_width), self.N_cases)
@@ -120,7 +129,7 @@ class SequenceNetwork:
         if e is None or self._engine_key != key or e.cfg.max_T < max_T or e.cfg.max_L < max_L:
             if e is not None:
                 e.close()
-            dev = self.training_GPUs[0]
+            dev = self._device()
             cfg = EngineConfig(**geo, max_B=self.N_cases, max_T=max_T, max_L=max(max_L, self.max_hyp_length),
                                max_beam=max(int(self.beam_width), 1), ff_dropout=float(self.FF_dropout),
                                rnn_dropout=float(self.RNN_dropout), lr=self.learning_rate,
@@ -129,8 +138,19 @@ class SequenceNetwork:
             self._engine = Engine(cfg, lib=self._lib)
             prm.init_engine(self._engine, self.seed)
             self._engine_key = key
+            self._bind_stream(self._engine)
         self._targets_list = flist
         return self._engine
+
+    def _bind_stream(self, eng):
+        """Data-parallel runs: the library must enqueue on the stream torch.distributed orders its NCCL kernels against
+        (torch's current stream of this rank's device), or the all-reduce would race the backward pass."""
+        import torch.distributed as dist
+        if getattr(eng, "emulated", False) or not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        import torch
+        torch.cuda.set_device(eng.cfg.device)
+        eng.set_stream(torch.cuda.current_stream().cuda_stream)
 
     # -- data ----------------------------------------------------------------------------------
     @staticmethod
@@ -194,20 +214,26 @@ class SequenceNetwork:
         max_L = max(len(e[1]) for d in data.values() for part in d.values() for e in part)
         eng = self._get_engine(subnets_params, max_T, max_L)
         pad_id = eng.cfg.pad_id
-        start_epoch = 0
+        start_epoch, restored = 0, []
         if _restore_epoch is not None and _restore_epoch > 0:
-            prm.load_checkpoint(eng, self.checkpoint_path, _restore_epoch, reuse_vars_scope=reuse_vars_scope)
+            restored = prm.load_checkpoint(eng, self.checkpoint_path, _restore_epoch, reuse_vars_scope=reuse_vars_scope)
             start_epoch = _restore_epoch
+        # everything NOT restored starts fresh (a cached engine of the same geometry may hold the previous fit's weights)
+        prm.init_engine(eng, self.seed, keep=restored)
+        if not restored:
+            eng.step = 0
         pat = re.compile(train_vars_scope or 'seq2seq')
         for name in eng.tensors():
             eng.set_trainable(name, bool(pat.match(name)))
-        grads = flat_tensor(eng, _lib.GRAD) if world > 1 else None
+        # data-parallel: ONE collective per step -- the gradient buffer with the token count in its tail (dist.allreduce_step)
+        grads = flat_tensor(eng, _lib.GRAD_AND_COUNT) if world > 1 else None
         rs = np.random.RandomState(self.seed + 17 + start_epoch)
         n_assess = self.N_epochs // self.assessment_epoch_interval
         assessments = {p: SimpleNamespace(decoder_accuracies=np.zeros(n_assess), decoder_word_error_rates=np.zeros(n_assess),
                                           decoder_confusions=None, epochs=np.zeros(n_assess, int), losses=np.zeros(n_assess))
                        for p in ('training', 'validation')}
         step = eng.step
+        eng.read_loss_accumulators(reset=True)
         for epoch in range(start_epoch, start_epoch + self.N_epochs):
             # minibatches: (subject index, example indices); all ranks draw the same order, then shard each batch
             plan = []
@@ -215,11 +241,12 @@ class SequenceNetwork:
                 order = rs.permutation(len(data[s.subnet_id]['training']))
                 plan += [(si, order[i:i + self.N_cases]) for i in range(0, len(order), self.N_cases)]
             order = rs.permutation(len(plan))
-            ep_loss, ep_tok = 0.0, 0
             # this rank's shard of every minibatch of the epoch.  Input pipeline (the tf.data prefetch of the reference,
             # trainers.py:891-901): minibatch k+1 is assembled on the host (native threads, into a page-locked ring buffer) and
-            # its host->device copy is started (e2t_stage_inputs, library copy stream) WHILE minibatch k trains; the host only
-            # waits for step k when it reads the loss
+            # its host->device copy is started (e2t_stage_inputs, library copy stream) WHILE minibatch k trains.  The step
+            # itself is enqueue-only -- forward/backward, the all-reduce, Adam+EMA with the token count read on the device
+            # (the loop bench.py times); the host runs at most ~3 minibatches ahead (wait_staged) and reads the summed
+            # epoch loss once per epoch.
             shards = []
             for pi in order:
                 si, idx = plan[pi]
@@ -248,21 +275,20 @@ class SequenceNetwork:
                     if cur[2] is not None:   # A6: encoder targets of this step (copied on the compute stream)
                         eng.set_encoder_targets(cur[2])
                     eng.train_step_grads_staged(k & 1, seed=step, want_loss=False)      # enqueue only
-                # assemble and stage the next minibatch while this one computes
+                else:   # fewer utterances than ranks: contribute zero gradients and a zero count
+                    flat_tensor(eng, _lib.GRAD_AND_COUNT).zero_()
+                # assemble and stage the next minibatch while this one computes; ring slot (k+1) % 3 was last read by the
+                # copy of minibatch k-2, which has finished once the copy of minibatch k-1 has (same copy stream)
+                if k >= 1:
+                    eng.wait_staged((k - 1) & 1)
                 nxt = host_batch(k + 1) if k + 1 < len(shards) else None
                 if nxt is not None:
                     eng.stage_inputs((k + 1) & 1, nxt[0], None, nxt[1], subnet=shards[k + 1][0])
-                if cur is not None:
-                    loss, ntok, aux_loss, _ = eng.last_losses()                         # waits for step k
-                    loss += aux_loss
-                else:   # fewer utterances than ranks: contribute zero gradients
-                    flat_tensor(eng, _lib.GRAD).zero_()
-                    loss, ntok = 0.0, 0
-                ntok_g = allreduce_grads(eng, grads, float(ntok)) if world > 1 else float(ntok)
-                eng.adam_ema_step(1.0 / max(ntok_g, 1.0), subnet=si)
+                allreduce_step(grads)
+                eng.adam_ema_step_dev(None, subnet=si)
                 step += 1
-                ep_loss += loss
-                ep_tok += ntok
+            ep_loss, ep_tok, ep_aux, _ = eng.read_loss_accumulators(reset=True)      # the epoch's one host synchronisation
+            ep_loss += ep_aux
             done = epoch + 1 - start_epoch
             if done % self.assessment_epoch_interval == 0:
                 k = done // self.assessment_epoch_interval - 1
@@ -270,14 +296,15 @@ class SequenceNetwork:
                     res = self._assess(eng, subnets_params, data, part, max_T, max_L)
                     a = assessments[part]
                     a.decoder_accuracies[k], a.decoder_word_error_rates[k] = res.accuracy, res.word_error_rate
+                    a.decoder_confusions = res.decoder_confusions      # of the latest assessment (trainers.py:604-611)
                     a.epochs[k], a.losses[k] = epoch + 1, ep_loss / max(ep_tok, 1)
                 self.vprint(f"epoch {epoch + 1}: train loss/token {ep_loss / max(ep_tok, 1):.4f}  "
                             f"WER train {assessments['training'].decoder_word_error_rates[k]:.3f} "
                             f"valid {assessments['validation'].decoder_word_error_rates[k]:.3f}")
                 if self.checkpoint_path and rank == 0:
-                    prm.save_checkpoint(eng, self.checkpoint_path, epoch + 1)
+                    prm.save_checkpoint(eng, self.checkpoint_path, epoch + 1, max_to_keep=self.max_to_keep)
         if self.checkpoint_path and rank == 0 and self.N_epochs % self.assessment_epoch_interval:
-            prm.save_checkpoint(eng, self.checkpoint_path, start_epoch + self.N_epochs)
+            prm.save_checkpoint(eng, self.checkpoint_path, start_epoch + self.N_epochs, max_to_keep=self.max_to_keep)
         if world > 1:
             dist.barrier()      # rank 0's checkpoint is complete before any rank goes on to restore it
         return assessments
@@ -293,6 +320,8 @@ class SequenceNetwork:
         examples = data[s.subnet_id][partition]
         pad_id, eos_id = eng.cfg.pad_id, eng.cfg.eos_id
         refs, hyps, n_ok, n_tok = [], [], 0, 0
+        V = int(eng.cfg.V)
+        conf = np.zeros((V, V), np.int64)
         Lh = max(self.max_hyp_length, max_L)
         # inference is embarrassingly parallel over utterances: rank r decodes every world-th minibatch,
         # the decoded strings are gathered at the end (no collective on the data path)
@@ -317,9 +346,11 @@ class SequenceNetwork:
                 m = y[r] != pad_id
                 n_ok += int((toks[r, 0, :max_L][m] == y[r][m]).sum())
                 n_tok += int(m.sum())
+            conf += confusion_counts(y, toks[:, 0, :max_L], V, pad_id)
         if world > 1:
             parts = [None] * world
-            dist.all_gather_object(parts, (refs, hyps, n_ok, n_tok))
+            dist.all_gather_object(parts, (refs, hyps, n_ok, n_tok, conf))
+            conf = sum(p[4] for p in parts)
             # rank-major order -> original minibatch order (rank r holds minibatches r, r + world, ...)
             nb = -(-len(examples) // self.N_cases)
             refs, hyps, cursor = [], [], [0] * world
@@ -333,7 +364,7 @@ class SequenceNetwork:
         wers = wer_vector(refs, hyps) if refs else np.zeros(0)
         return SimpleNamespace(word_error_rate=float(wers.mean()) if len(wers) else float('nan'),
                                accuracy=n_ok / max(n_tok, 1), references=refs, hypotheses=hyps,
-                               word_error_rates=wers)
+                               word_error_rates=wers, decoder_confusions=conf)
 
     def restore_and_assess(self, subnets_params, restore_epoch, WRITE=False, data_partitions=('training', 'validation')):
         data = {s.subnet_id: {p: self._load_partition(s, p) for p in data_partitions} for s in subnets_params}

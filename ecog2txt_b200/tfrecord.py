@@ -144,6 +144,7 @@ class _Vocab:
     """Sorted view of a class list for the native string -> index lookup."""
 
     def __init__(self, feature_list: Sequence[str]):
+        self.source = list(feature_list)      # own copy: keeps the content the table was built from
         enc = [t.encode("utf-8") for t in feature_list]
         order = sorted(range(len(enc)), key=lambda i: enc[i])
         self.n = len(enc)
@@ -196,10 +197,12 @@ def parse_example(record: bytes, manifests: Dict[str, "object"], _vocab_cache: O
                     strs.append(C.string_at(s, sl.value))
                 out[data_key] = np.asarray(strs, object).reshape(-1, 1)
             else:
-                key = id(flist)
-                if key not in cache:
-                    cache[key] = _Vocab(flist)
-                v = cache[key]
+                # one vocabulary per stream.  Keyed by the stream's name and checked against the list's content: a manifest
+                # whose get_feature_list() builds a fresh list per call must neither rebuild the table per record nor hit
+                # another stream's table through a recycled id()
+                v = cache.get(data_key)
+                if v is None or v.source != flist:
+                    v = cache[data_key] = _Vocab(flist)
                 res = np.empty(count.value + 1, np.int32)
                 n = C.c_uint64()
                 _ck(lib.e2t_tokens_to_indices(payload, plen.value, v.sorted, v.ids.ctypes.data_as(_P), v.n, man.OOV_id,

@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import os
 import re
+from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence
 
 import numpy as np
@@ -28,6 +29,40 @@ from . import EOS_token, OOV_token, pad_token, TOKEN_TYPES
 from . import params as prm
 from .metrics import target_inds_to_sequences
 from .sequence_network import SequenceNetwork
+
+
+# variable-scope regexes that split the model into its two halves (the reference's transfer-learning contract,
+# trainers.py:337-338): tensors under seq2seq/subnet_<id>/ belong to one subject, everything else is shared
+SUBJECT_SCOPE = 'seq2seq/subnet'
+SHARED_SCOPE = 'seq2seq/(?!subnet)'
+WHOLE_MODEL_SCOPE = 'seq2seq'
+
+
+@dataclass
+class FitPhase:
+    """One `SequenceNetwork.fit` call of a transfer-learning schedule."""
+    subject_index: int
+    n_epochs: int
+    train_scope: str                 # what Adam updates
+    restore_scope: Optional[str]     # what is read back from the checkpoint of `restore_from` (None: nothing, fresh start)
+    restore_from: int                # epoch of the checkpoint to start from (0: none)
+    report: bool                     # whether the phase's assessments are kept as a result
+
+
+def sequential_schedule(n_subjects: int, pretraining_epochs: int, training_epochs: int, posttraining_epochs: int) -> List[FitPhase]:
+    """The reference's sequential transfer learning (trainers.py:329-374) as data.  Subject 0 trains the whole model from
+    scratch; every later subject first fits ONLY its private input layer for `pretraining_epochs` on top of the restored
+    (frozen) shared layers, then the whole model for `training_epochs`; the last subject trains `posttraining_epochs` longer.
+    Epoch numbers accumulate across phases: each phase starts from the checkpoint the previous one ended with."""
+    phases, epoch = [], 0
+    for i in range(n_subjects):
+        if i > 0:
+            phases.append(FitPhase(i, pretraining_epochs, SUBJECT_SCOPE, SHARED_SCOPE, epoch, report=False))
+            epoch += pretraining_epochs
+        n = training_epochs + (posttraining_epochs if i == n_subjects - 1 else 0)
+        phases.append(FitPhase(i, n, WHOLE_MODEL_SCOPE, WHOLE_MODEL_SCOPE if i > 0 else None, epoch, report=True))
+        epoch += n
+    return phases
 
 
 class MultiSubjectTrainer:
@@ -43,7 +78,8 @@ class MultiSubjectTrainer:
         self.experiment_manifest = experiment_manifest
         last = experiment_manifest[subject_ids[-1]]
         token_type = last.get('token_type', 'word_sequence')
-        assert token_type in TOKEN_TYPES, 'Unrecognized token_type!! -- jgm'          # trainers.py:64-65
+        if token_type not in TOKEN_TYPES:                                            # trainers.py:64-65
+            raise ValueError(f"token_type {token_type!r} is not one of {sorted(TOKEN_TYPES)}")
         self._token_type = token_type
         # subjects: every subject but the last pre-trains on all of its blocks (trainers.py:72-82; subjects.py:123-126)
         if subjects is None:
@@ -67,39 +103,36 @@ class MultiSubjectTrainer:
                     man.penalty_scale = experiment_manifest[subject.subnet_id][data_key + '_penalty_scale']
                 except KeyError:
                     pass
-        self.net = SequenceNetwork(last, EOS_token=EOS_token, pad_token=pad_token, OOV_token=OOV_token, training_GPUs=[0],
+        # the reference pins training_GPUs=[0] (trainers.py:131); here SN_kwargs may override it, and under torchrun the
+        # network binds to this rank's LOCAL_RANK device (SequenceNetwork._device)
+        SN_kwargs.setdefault('training_GPUs', [0])
+        self.net = SequenceNetwork(last, EOS_token=EOS_token, pad_token=pad_token, OOV_token=OOV_token,
                                    TARGETS_ARE_SEQUENCES='sequence' in token_type, VERBOSE=VERBOSE, **SN_kwargs)
         self.checkpoint_dir = checkpoint_dir
         self.results: List[dict] = []
 
-    # ---- trainers.py:213-252 ---------------------------------------------------------------------
+    # ---- checkpoint location and discovery (trainers.py:213-252) -----------------------------------
     @property
-    def checkpoint_dir(self):
-        try:
-            self.net.checkpoint_path = os.path.join(self._checkpoint_dir, 'model.ckpt')
-        except AttributeError:
-            pass
+    def checkpoint_dir(self) -> str:
         return self._checkpoint_dir
 
     @checkpoint_dir.setter
-    def checkpoint_dir(self, checkpoint_dir):
-        self._checkpoint_dir = checkpoint_dir
-        self.checkpoint_dir
+    def checkpoint_dir(self, path: str):
+        """The network always writes <checkpoint_dir>/model.ckpt-<epoch>.*; moving the directory re-points it."""
+        self._checkpoint_dir = path
+        self.net.checkpoint_path = os.path.join(path, 'model.ckpt')
 
     @property
-    def restore_epoch(self):
+    def restore_epoch(self) -> Optional[int]:
+        """The epoch set explicitly, else the newest checkpoint found in checkpoint_dir, else None."""
         if self._restore_epoch is not None:
             return self._restore_epoch
-        model_name = 'model.ckpt'
-        if not os.path.isdir(self.checkpoint_dir):
-            return None
-        epochs = sorted(int(name.split('-')[1].split('.')[0]) for name in os.listdir(self.checkpoint_dir)
-                        if name.split('-')[0] == model_name and name.split('.')[-1] == 'index')
-        return epochs[-1] if epochs else None
+        found = prm.checkpoint_epochs(self.net.checkpoint_path)
+        return found[-1] if found else None
 
     @restore_epoch.setter
-    def restore_epoch(self, restore_epoch):
-        self._restore_epoch = restore_epoch
+    def restore_epoch(self, epoch: Optional[int]):
+        self._restore_epoch = epoch
 
     def vprint(self, *a, **k):
         if self.VERBOSE:
@@ -111,45 +144,31 @@ class MultiSubjectTrainer:
     # ---- trainers.py:303-327 ---------------------------------------------------------------------
     def parallel_transfer_learn(self, RESUME=False, fit_kwargs=()):
         """All subjects jointly in one fit (one subject per minibatch, shared layers see everyone's data)."""
+        fit_kwargs = dict(fit_kwargs)
         if RESUME:
-            fit_kwargs = {'_restore_epoch': self.restore_epoch, **dict(fit_kwargs),
-                          'train_vars_scope': 'seq2seq', 'reuse_vars_scope': 'seq2seq'}
-            self.ecog_subjects = [self.ecog_subjects[-1]]
-        assessments = self.net.fit(self.ecog_subjects, **dict(fit_kwargs))
+            # continue from the newest checkpoint with the LAST subject only, whole model restored and trainable
+            fit_kwargs.setdefault('_restore_epoch', self.restore_epoch)
+            fit_kwargs.update(train_vars_scope=WHOLE_MODEL_SCOPE, reuse_vars_scope=WHOLE_MODEL_SCOPE)
+            self.ecog_subjects = self.ecog_subjects[-1:]
+        assessments = self.net.fit(self.ecog_subjects, **fit_kwargs)
         self._save_results(assessments)
         if self._restore_epoch is not None:
             self.restore_epoch = self.restore_epoch + self.net.N_epochs if RESUME else self.net.N_epochs
         return assessments
 
-    # ---- trainers.py:329-374 ---------------------------------------------------------------------
+    # ---- sequential transfer learning (trainers.py:329-374) ------------------------------------------
     def sequential_transfer_learn(self, pretraining_epochs=60, training_epochs=200, posttraining_epochs=340):
-        proprietary_scopes = 'seq2seq/subnet'
-        reusable_scopes = 'seq2seq/(?!subnet)'  # negative lookahead
-        fit_kwargs: Dict = {}
-        latest_epoch = 0
+        """Subjects one after the other; see `sequential_schedule` for the phases.  Returns the last phase's assessments."""
         assessments = None
-        for subject in self.ecog_subjects:
-            if subject is self.ecog_subjects[0]:
-                latest_epoch = 0
-                fit_kwargs['reuse_vars_scope'] = None
-            else:
-                # first acquire this subject's encoder embedding with everything shared frozen
-                self.net.N_epochs = pretraining_epochs
-                fit_kwargs['train_vars_scope'] = proprietary_scopes
-                fit_kwargs['reuse_vars_scope'] = reusable_scopes
-                fit_kwargs['_restore_epoch'] = latest_epoch
-                self.net.fit([subject], **fit_kwargs)
-                latest_epoch += self.net.N_epochs
-                fit_kwargs['_restore_epoch'] = latest_epoch
-                fit_kwargs['reuse_vars_scope'] = 'seq2seq'
-            if subject is self.ecog_subjects[-1]:
-                training_epochs += posttraining_epochs
-            self.net.N_epochs = training_epochs
-            fit_kwargs['train_vars_scope'] = 'seq2seq'
-            assessments = self.net.fit([subject], **fit_kwargs)
-            latest_epoch += self.net.N_epochs
-            self._save_results(assessments)
-        self.restore_epoch = latest_epoch
+        phases = sequential_schedule(len(self.ecog_subjects), pretraining_epochs, training_epochs, posttraining_epochs)
+        for ph in phases:
+            self.net.N_epochs = ph.n_epochs
+            out = self.net.fit([self.ecog_subjects[ph.subject_index]], train_vars_scope=ph.train_scope,
+                               reuse_vars_scope=ph.restore_scope, _restore_epoch=ph.restore_from or None)
+            if ph.report:
+                assessments = out
+                self._save_results(out)
+        self.restore_epoch = phases[-1].restore_from + phases[-1].n_epochs
         return assessments
 
     # ---- trainers.py:376-408 ---------------------------------------------------------------------
@@ -158,20 +177,22 @@ class MultiSubjectTrainer:
         return self.net.restore_and_assess(self.ecog_subjects, self.restore_epoch)
 
     def update_net_from_saved_model(self):
-        self.net.layer_sizes, data_sizes, strides, EMA = self.recover_model_sizes()
-        self.net.TEMPORALLY_CONVOLVE = len(strides)
-        self.net.EMA_decay = 0.99 * EMA
+        """Make the network and the subjects' manifests agree with what the checkpoint holds (sizes are read back from
+        the stored variable names / shapes, so a model can be assessed without its original manifest)."""
+        layer_sizes, data_sizes, strides, has_ema = self.recover_model_sizes()
+        net = self.net
+        net.layer_sizes = layer_sizes
+        net.TEMPORALLY_CONVOLVE = len(strides)          # truthy iff conv kernels were found
+        net.EMA_decay = 0.99 * has_ema
+        shared_sizes = data_sizes.get(None, {})
         for subject in self.ecog_subjects:
-            s_id = subject.subnet_id
-            manifests = subject.data_manifests
-            for key, data_size in data_sizes.get(s_id, {}).items():
-                if key in manifests:
-                    manifests[key].num_features = data_size
-            for key, data_size in data_sizes.get(None, {}).items():
-                if key in manifests:
-                    manifests[key].num_features = data_size
-            if strides.get(s_id):
-                subject.decimation_factor = int(np.prod(strides[s_id]))
+            own_sizes = data_sizes.get(subject.subnet_id, {})
+            for key, man in subject.data_manifests.items():
+                if key in own_sizes or key in shared_sizes:
+                    man.num_features = shared_sizes.get(key, own_sizes.get(key))
+            subject_strides = strides.get(subject.subnet_id)
+            if subject_strides:
+                subject.decimation_factor = int(np.prod(subject_strides))
 
     # ---- trainers.py:444-554 ---------------------------------------------------------------------
     def recover_model_sizes(self):
@@ -227,13 +248,12 @@ class MultiSubjectTrainer:
     def _retrieve_layer_weights(self, weights_name):
         """The EMA copy of the first layer's weights of the sub-network called `weights_name` (e.g. 'decoder_embedding',
         'encoder_embedding') from the restore_epoch checkpoint, found by name like the reference does."""
-        var_to_shape = prm.variable_to_shape_map(self.net.checkpoint_path, self.restore_epoch)
-        weights_full_name = None
-        for key in sorted(var_to_shape):
-            if re.match('.*{0}.*0/weights/ExponentialMovingAverage'.format(weights_name), key):
-                weights_full_name = key
-        assert weights_full_name, "Uh-oh, no such weights found! -- jgm"
-        return self.net.get_weights_as_numpy_array(weights_full_name, self.restore_epoch)
+        stored = prm.variable_to_shape_map(self.net.checkpoint_path, self.restore_epoch)
+        wanted = re.compile(rf'.*{weights_name}.*0/weights{re.escape(prm.EMA_SUFFIX)}')
+        matches = [name for name in sorted(stored) if wanted.match(name)]
+        if not matches:
+            raise KeyError(f"checkpoint {self.restore_epoch} holds no first-layer EMA weights for {weights_name!r}")
+        return self.net.get_weights_as_numpy_array(matches[-1], self.restore_epoch)
 
     def get_encoder_embedding(self):
         """The last subject's temporal-conv kernel [1, W, C, E] (EMA), named from the recovered model sizes."""
@@ -273,21 +293,19 @@ class MultiSubjectTrainer:
         contrib_method = '<data_key minus _targets>_saliency_map', e.g. 'decoder_saliency_map' / 'encoder_1_saliency_map':
         every *_targets penalty is set to 0 except that one (set to 1), as in the reference."""
         subject = self.ecog_subjects[-1]
-        old_penalties = {}
-        for key, manifest in subject.data_manifests.items():
-            if '_targets' in key:
-                old_penalties[key] = manifest.penalty_scale
-                manifest.penalty_scale = 0.0
-        key = contrib_method.replace('saliency_map', 'targets')
-        subject.data_manifests[key].penalty_scale = 1.0
+        target_streams = {k: m for k, m in subject.data_manifests.items() if '_targets' in k}
+        studied = contrib_method.replace('saliency_map', 'targets')
+        if studied not in target_streams:
+            raise KeyError(f"{contrib_method!r} names no target stream of subject {subject.subnet_id}")
+        saved = {k: m.penalty_scale for k, m in target_streams.items()}
+        for k, m in target_streams.items():
+            m.penalty_scale = 1.0 if k == studied else 0.0
         try:
-            return self.net.restore_and_get_saliencies([subject] if len(self.ecog_subjects) == 1 else self.ecog_subjects,
-                                                       self.restore_epoch, data_partition='validation',
+            return self.net.restore_and_get_saliencies(self.ecog_subjects, self.restore_epoch, data_partition='validation',
                                                        assessment_type=assessment_type)
         finally:
-            for key, manifest in subject.data_manifests.items():
-                if '_targets' in key:
-                    manifest.penalty_scale = old_penalties[key]
+            for k, m in target_streams.items():
+                m.penalty_scale = saved[k]
 
     # ---- trainers.py:925-963 ---------------------------------------------------------------------
     def construct_online_predictor(self, subject_index: int = -1):

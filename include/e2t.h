@@ -40,6 +40,10 @@ extern "C" {
 #define E2T_ADAM_M 2
 #define E2T_ADAM_V 3
 #define E2T_EMA 4     /* .../ExponentialMovingAverage shadow (trainers.py:466) */
+/* e2t_flat_buffer only: the gradient buffer followed by 4 floats [unmasked-token count of the last training step, 0, 0, 0].
+ * A data-parallel caller all-reduces THIS range once per step (gradients and the loss normaliser in one collective) and then
+ * calls e2t_adam_ema_step_dev(h, subnet, NULL). */
+#define E2T_GRAD_AND_COUNT 5
 
 /* activations */
 #define E2T_ACT_LINEAR 0
@@ -156,6 +160,13 @@ int e2t_set_encoder_targets(e2t_handle* h, const void* targets, int loc, int B, 
 /* the two terms of the most recent loss: penalty_scale * sum CE over `ntok` tokens, aux_penalty * sum over
  * `aux_frames` frames (0 when the head did not run); loss_sum of the calls above is their sum.  Synchronises. */
 int e2t_last_losses(e2t_handle* h, float* decoder_sum, int32_t* ntok, float* aux_sum, int32_t* aux_frames);
+/* Running sums over the training steps since the last reset: out4 = [decoder loss, unmasked tokens, encoder-targets loss,
+ * encoder-target frames].  Lets a training loop report the epoch loss with ONE host synchronisation per epoch instead of
+ * one per step.  Synchronises. */
+int e2t_read_loss_accumulators(e2t_handle* h, double* out4, int reset);
+/* block the host until the most recent e2t_stage_inputs copy into `slot` has completed (its host buffer may be reused);
+ * bounds how far a sync-free training loop runs ahead of the device */
+int e2t_wait_staged(e2t_handle* h, int slot);
 /* page-locked host memory for the caller's staging buffers: e2t_stage_inputs copies from it without an intermediate
  * pageable -> pinned bounce, i.e. asynchronously with respect to the host and to the compute stream */
 int e2t_host_alloc(void** out, int64_t bytes);
@@ -164,7 +175,8 @@ int e2t_host_free(void* p);
  * grad * grad_scale (1 / global token count).  subnet < 0: every subnet. */
 int e2t_adam_ema_step(e2t_handle* h, int subnet, float grad_scale);
 /* same with grad_scale = 1 / max(*token_count_dev, 1) read on the device (fp32 scalar in device memory, e.g. the all-reduced
- * token count): no host read-back between the backward pass and the optimiser */
+ * token count): no host read-back between the backward pass and the optimiser.  token_count_dev == NULL: the count slot
+ * behind the gradient buffer (E2T_GRAD_AND_COUNT). */
 int e2t_adam_ema_step_dev(e2t_handle* h, int subnet, const float* token_count_dev);
 /* forward only (assessment loss): same inputs, no dropout, weights = value or EMA */
 int e2t_eval_loss(e2t_handle* h, int subnet, const float* x, const int32_t* lens, const int32_t* y,

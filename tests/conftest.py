@@ -12,6 +12,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run under gpurun)")
 
 
+def pytest_sessionfinish(session, exitstatus):
+    """GPU runs: persist the achieved-error table of every oracle comparison (also when a test failed)."""
+    try:
+        import torch
+        import parity_common as pc
+        if torch.cuda.is_available() and pc.PARITY_RECORD:
+            pc.dump_record(os.path.join(ROOT, "gpurun_out", "parity_r2.json"))
+    except Exception:      # noqa: BLE001 -- bookkeeping must never turn a green run red
+        pass
+
+
 @pytest.fixture(scope="session")
 def emu_lib():
     """The kernel-emulation build of csrc (g++, fibers).  TEST-ONLY -- see tests/emu/cuda_emu.h."""

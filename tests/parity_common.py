@@ -24,6 +24,38 @@ TINY_AUX_CAT = dict(TINY, aux_layer=0, aux_hidden=0, aux_F=5, aux_kind="categori
 MEDIUM_AUX = dict(MEDIUM, aux_layer=1, aux_hidden=36, aux_F=13, aux_kind="gaussian", aux_penalty=0.5)
 MEDIUM_AUX_CAT = dict(MEDIUM, aux_layer=1, aux_hidden=36, aux_F=42, aux_kind="categorical", aux_penalty=1.0)
 TWO_SUBJ = dict(subnet_ids=(400, 401), subnet_C=(6, 10), subnet_W=(4, 3), E=5, H=(8,), D=6, Hd=16, V=11)
+# BASELINE.json config 2 exactly (mochastar_word_sequence.yaml:62-75,84-85,89): the geometry bench.py is quoted on
+FULL = dict(subnet_ids=(400,), subnet_C=(256,), subnet_W=(12,), E=100, H=(400, 400, 400), D=150, Hd=800, V=1806)
+
+# Tolerances at config 2, tensor-core backend (set to <= 10x the errors measured on B200, profiles/parity_r2.json)
+FULL_TOL = dict(loss=1e-2, state=1e-2, grad=5e-2, logp=5e-3, beam_score=1e-2)
+
+# ---- achieved-error record -------------------------------------------------------------------------------------
+# Every oracle comparison appends its measured errors here; tests/test_gpu_zz_fit.py's last test (or the session
+# teardown in conftest.py) writes the table to gpurun_out/parity_r2.json, which is committed as profiles/parity_r2.json.
+# Tolerances in the tests are <= 10x the errors recorded there.
+PARITY_RECORD = {}
+
+
+def record(name, **errs):
+    PARITY_RECORD.setdefault(name, {}).update({k: (float(v) if not isinstance(v, (dict, list, str)) else v) for k, v in errs.items()})
+
+
+def dump_record(path):
+    import json
+    import os
+    if not PARITY_RECORD:
+        return
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    old = {}
+    if os.path.exists(path):
+        try:
+            old = json.load(open(path))
+        except Exception:      # noqa: BLE001 -- a truncated file from a killed run is simply replaced
+            old = {}
+    old.update(PARITY_RECORD)
+    with open(path, "w") as f:
+        json.dump(old, f, indent=1, sort_keys=True)
 
 
 def make_params(ocfg, seed=1, bias_scale=0.1, eos_bias=None):
@@ -78,12 +110,16 @@ def rel_err(a, ref):
 
 
 def check_train_step(lib, geo, B, T, L, ff=0.0, rnn=0.0, seed=3, tol=2e-4, backend="simt", give_lens=False,
-                     subnet=0):
+                     subnet=0, grad_tol=None, name=None, batch=None):
+    """One training step through the C-ABI against O.loss_and_grads.  tol bounds the relative error of the loss and of
+    the final encoder state, grad_tol (default 5 * tol) the error of every gradient tensor relative to that tensor's
+    largest entry.  The achieved errors are recorded under `name` (PARITY_RECORD)."""
     ocfg = O.OracleConfig(**geo)
     P = make_params(ocfg)
     eng = engine_for(geo, lib, B, T, L, ff_dropout=ff, rnn_dropout=rnn, gemm_backend=backend)
     eng.set_all({k: v.numpy() for k, v in P.items()})
-    x, lens, y = make_batch(ocfg, B, T, L, subnet=subnet)
+    x, lens, y = batch if batch is not None else make_batch(ocfg, B, T, L, subnet=subnet)
+    grad_tol = 5 * tol if grad_tol is None else grad_tol
     W = ocfg.subnet_W[subnet]
     T2 = -(-T // W)
     masks = O.make_masks(ocfg, seed, B, T2, L, ff, rnn, torch.float32) if (ff > 0 or rnn > 0) else None
@@ -100,16 +136,20 @@ def check_train_step(lib, geo, B, T, L, ff=0.0, rnn=0.0, seed=3, tol=2e-4, backe
         assert abs(la - acts["aux_loss"]) <= tol * max(abs(acts["aux_loss"]), 1.0), (la, acts["aux_loss"])
         assert abs(ld - acts["decoder_loss"]) <= tol * max(abs(acts["decoder_loss"]), 1.0)
     assert ntok == no
-    assert abs(loss - lo) <= tol * max(abs(lo), 1.0), (loss, lo)
+    e_loss = abs(loss - lo) / max(abs(lo), 1.0)
     assert (eng.activation("lens", (B,), np.int32) == lens).all()
-    e_top = eng.activation("final_h", (B, ocfg.Hd))
-    assert rel_err(e_top, acts["final_h"].numpy()) <= tol
+    e_h = rel_err(eng.activation("final_h", (B, ocfg.Hd)), acts["final_h"].numpy())
+    e_c = rel_err(eng.activation("final_c", (B, ocfg.Hd)), acts["final_c"].numpy()) if "final_c" in acts else 0.0
     G = eng.get_all(_lib.GRAD)
-    worst = 0.0
-    for k, v in G.items():
-        e = rel_err(v, g[k].numpy())
-        worst = max(worst, e)
-        assert e <= 5 * tol, (k, e)
+    errs = {k: rel_err(v, g[k].numpy()) for k, v in G.items()}
+    worst = max(errs.values())
+    rec_name = name or f"train_step/{backend}/E{ocfg.E}_H{'x'.join(map(str, ocfg.H))}_V{ocfg.V}_C{ocfg.subnet_C[subnet]}" \
+                       f"/B{B}_T{T}_L{L}_ff{ff}_rnn{rnn}"
+    record(rec_name, loss=e_loss, final_h=e_h, final_c=e_c, worst_grad=worst, grads=errs, tol=tol, grad_tol=grad_tol)
+    assert e_loss <= tol, (loss, lo)
+    assert e_h <= tol and e_c <= tol, (e_h, e_c)
+    for k, e in errs.items():
+        assert e <= grad_tol, (k, e)
     eng._last_counters = {k: eng.counter(k) for k in ("launches", "tcgen05_launches", "persistent_rnn_launches")}
     counters = eng._last_counters
     eng.close()
@@ -145,13 +185,21 @@ def check_saliency(lib, geo, B, T, L, tol=2e-4, backend="simt", which="decoder",
     return e
 
 
-def check_decode(lib, geo, B, T, max_len, beam=0, backend="simt", temperature=0.7, use_ema=False, margin=1e-3):
+def check_decode(lib, geo, B, T, max_len, beam=0, backend="simt", temperature=0.7, use_ema=False, margin=1e-3,
+                 logp_tol=2e-3, score_tol=5e-3, name=None, x=None, eng=None):
+    """Greedy (beam = 0) or beam decode through the C-ABI against the oracle.  Margin-aware: rows whose oracle top-2
+    logit gap at some live step is below `margin` may legitimately pick the other token; all others must be IDENTICAL
+    (north_star: "decoded token sequences identical under greedy decode").  Achieved errors are recorded under `name`."""
     ocfg = O.OracleConfig(**geo)
     P = make_params(ocfg, eos_bias=-1.0)
-    eng = engine_for(geo, lib, B, T, max_len, max_beam=max(beam, 1), gemm_backend=backend)
-    eng.set_all({k: v.numpy() for k, v in P.items()})
-    x, lens, _ = make_batch(ocfg, B, T, 4)
+    own = eng is None
+    if own:
+        eng = engine_for(geo, lib, B, T, max_len, max_beam=max(beam, 1), gemm_backend=backend)
+    eng.set_all({k: v.numpy() for k, v in P.items()}, _lib.EMA if use_ema else _lib.VALUE)
+    if x is None:
+        x, lens, _ = make_batch(ocfg, B, T, 4)
     xt = torch.from_numpy(x)
+    rec_name = name or f"decode/{backend}/beam{beam}/E{ocfg.E}_H{'x'.join(map(str, ocfg.H))}_V{ocfg.V}/B{B}_T{T}_len{max_len}"
     if beam == 0:
         t_ref, lp_ref, logits = O.greedy_decode(ocfg, P, xt, None, max_len=max_len, temperature=temperature)
         toks, logp = eng.greedy_decode(x, None, max_len=max_len, temperature=temperature, use_ema=use_ema)
@@ -165,22 +213,30 @@ def check_decode(lib, geo, B, T, max_len, beam=0, backend="simt", temperature=0.
             if len(ends):
                 live[b, ends[0] + 1:] = False
         safe = np.all((gap > margin) | ~live, axis=1)
+        e_logp = float(np.abs(logp[safe] - lp_ref.numpy()[safe]).max()) if safe.any() else 0.0
+        record(rec_name, safe_rows=float(safe.mean()), rows_identical=float((toks == tr).all(1).mean()),
+               safe_rows_identical=float((toks[safe] == tr[safe]).all(1).mean()) if safe.any() else 1.0,
+               logp_abs=e_logp, min_live_gap=float(gap[live].min()), logp_tol=logp_tol, margin=margin)
         assert safe.mean() > 0.5
         assert (toks[safe] == tr[safe]).all()
-        assert np.abs(logp[safe] - lp_ref.numpy()[safe]).max() < 2e-3
+        assert e_logp < logp_tol
         assert (tr != ocfg.pad_id).sum(1).max() > 1, "test params should give multi-token hypotheses"
     else:
         t_ref, s_ref = O.beam_decode(ocfg, P, xt, None, beam=beam, max_len=max_len, temperature=temperature)
-        toks, scores = eng.beam_decode(x, None, beam=beam, max_len=max_len, temperature=temperature)
+        toks, scores = eng.beam_decode(x, None, beam=beam, max_len=max_len, temperature=temperature, use_ema=use_ema)
         s_ref = s_ref.numpy()
         tscale = max(1.0, 0.7 / temperature)       # logit errors enter the scores divided by the temperature
-        assert np.abs(scores - s_ref).max() < 5e-3 * tscale
+        e_score = float(np.abs(scores - s_ref).max())
         # beams whose score is well separated from their neighbours must hold identical tokens
         sep = np.ones_like(s_ref, bool)
         d = np.abs(np.diff(s_ref, axis=1)) > 10 * margin * tscale
         sep[:, 1:] &= d
         sep[:, :-1] &= d
+        record(rec_name, score_abs=e_score, separated_beams=float(sep.mean()),
+               beams_identical=float((toks == t_ref.numpy()).all(2).mean()), score_tol=score_tol * tscale)
+        assert e_score < score_tol * tscale
         assert sep.any()
         assert (toks[sep] == t_ref.numpy()[sep]).all()
         assert (np.diff(scores, axis=1) <= 1e-6).all(), "beams must be best-first"
-    eng.close()
+    if own:
+        eng.close()

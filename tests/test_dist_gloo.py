@@ -53,8 +53,17 @@ def _worker(rank, world, port, out_dir):
         ntok_g = float(nt.item())
         eng.adam_ema_step_dev(nt.numpy())
     else:
-        ntok_g = allreduce_grads(eng, g, float(ntok))
-        eng.adam_ema_step(1.0 / ntok_g)
+        # the product path (SequenceNetwork.fit, bench.py): ONE collective -- gradients with the token count in the tail --
+        # and the optimiser reads the all-reduced count on the "device"
+        from ecog2txt_b200.dist import allreduce_step
+        gc = flat_tensor(eng, _lib.GRAD_AND_COUNT)
+        assert gc.numel() == g.numel() + 4 and float(gc[-4]) == float(ntok) and gc.data_ptr() == g.data_ptr()
+        allreduce_step(gc)
+        ntok_g = float(gc[-4])
+        eng.adam_ema_step_dev(None)
+        acc = eng.read_loss_accumulators(reset=True)
+        assert acc[1] == ntok and abs(acc[0] - loss) <= 1e-6 * abs(loss)
+        assert eng.read_loss_accumulators()[1] == 0
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ntok=ntok_g, lo=lo, hi=hi,
              **{k.replace("/", "|"): v for k, v in eng.get_all(_lib.VALUE).items()},
              **{"G|" + k.replace("/", "|"): v for k, v in eng.get_all(_lib.GRAD).items()})

@@ -209,9 +209,16 @@ def test_degenerate_inputs(gpu_lib):
     G = eng.get_all(_lib.GRAD)
     for k, v in G.items():
         assert pc.rel_err(v, g[k].numpy()) <= 5e-2, k
-    t_ref, _, _ = O.greedy_decode(ocfg, P, torch.from_numpy(x[:1]), None, max_len=4)
-    toks, _ = eng.greedy_decode(np.ascontiguousarray(x[:1]), None, max_len=4)      # B = 1
-    assert toks.shape == (1, 4)
+    # B = 1 decodes against the oracle, every utterance of the batch on its own (incl. the empty and the one-frame one)
+    for b in range(5):
+        xb = np.ascontiguousarray(x[b:b + 1])
+        t_ref, lp_ref, logits = O.greedy_decode(ocfg, P, torch.from_numpy(xb), None, max_len=4)
+        toks, logp = eng.greedy_decode(xb, None, max_len=4)
+        assert toks.shape == (1, 4)
+        top2 = logits.topk(2, dim=2).values
+        if float((top2[..., 0] - top2[..., 1]).min()) > 1e-3:
+            assert (toks == t_ref.numpy()).all(), (b, toks, t_ref)
+            assert np.abs(logp - lp_ref.numpy()).max() < 2e-3
     eng.close()
 
 

@@ -172,8 +172,8 @@ def test_api_error_paths(emu_lib):
         plain.set_encoder_targets(np.zeros((3, 19, 3), np.float32))
     with pytest.raises(E2TError, match="bucket index"):
         plain._ck(plain._lib.e2t_grad_bucket_info(plain._h, 0, None, None))          # no step has run yet
-    with pytest.raises(E2TError, match="NULL"):
-        plain._ck(plain._lib.e2t_adam_ema_step_dev(plain._h, -1, None))
+    with pytest.raises(E2TError, match="slot must be"):
+        plain.wait_staged(2)
     with pytest.raises(E2TError, match="saliency needs decoder targets"):
         plain._ck(plain._lib.e2t_input_saliency(plain._h, 0, x.ctypes.data_as(C.c_void_p), None, None, 0, 3, 19, 5, 0, 1.0, 0.0,
                                                 None, None))

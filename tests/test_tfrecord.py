@@ -155,3 +155,21 @@ def test_multithreaded_batch_assembly_matches_single_thread():
         assert got is out and np.array_equal(out, ref)
     with pytest.raises(tfrecord.TFRecordError):
         tfrecord.pad_batch_f32(seqs, 20, threads=4)              # longer than the padded length
+
+
+def test_vocab_cache_survives_fresh_feature_lists(tmp_path):
+    """a manifest whose get_feature_list() returns a NEW list on every call (e.g. lambda: get_class_list(path))
+    must not alias another stream's vocabulary through a recycled id(): two categorical streams, fresh lists per call."""
+    from ecog2txt_b200 import tfrecord
+    from ecog2txt_b200.subjects import SequenceDataManifest
+    words = ["<pad>", "<EOS>", "<OOV>", "alpha_", "beta_", "gamma_"]
+    phones = ["<pad>", "<EOS>", "<OOV>", "aa", "bb"]
+    path = str(tmp_path / "two_streams.tfrecord")
+    with tfrecord.TFRecordWriter(path) as w:
+        for _ in range(40):
+            w.write_example({"text_sequence": [b"alpha_", b"gamma_"], "phoneme_sequence": [b"bb", b"aa", b"bb"]})
+    mans = {"decoder_targets": SequenceDataManifest("text_sequence", get_feature_list=lambda: list(words), APPEND_EOS=True),
+            "encoder_1_targets": SequenceDataManifest("phoneme_sequence", get_feature_list=lambda: list(phones))}
+    for ex in tfrecord.read_examples([path], mans):
+        assert ex["decoder_targets"].reshape(-1).tolist() == [3, 5, 1]
+        assert ex["encoder_1_targets"].reshape(-1).tolist()[:3] == [4, 3, 4]
