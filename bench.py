@@ -81,31 +81,45 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_utt_per_s(B, steps, threads=None, warmup=1):
-    """The oracle's training step (forward, autograd backward, Adam+EMA) on the host cores."""
+WORKLOAD = "config2: T=400 C=256 3x400 BiLSTM + 800 LSTM decoder V=1806, L=11, dropout .1/.5, Adam+EMA"
+
+
+def _host_threads():
+    # every host thread this process may use -- explicitly, because torchrun exports OMP_NUM_THREADS=1 to its workers and
+    # the CPU arm would otherwise run single-threaded under the N > 1 launch
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_port_utt_per_s(B, steps, threads=None, warmup=1, mode="speed"):
+    """One full training step (forward, backward, Adam+EMA) of the CPU oracle on the host cores, masks / dropout included.
+    mode "speed": oracle/speed_mode.py -- recurrences on torch.nn.LSTM (oneDNN), the fastest CPU restatement available here
+    (BASELINE.md section 3); mode "loops": oracle/seq2seq_oracle.py -- one LSTM step per Python iteration + autograd."""
     import torch
     from oracle import seq2seq_oracle as O
     from ecog2txt_b200.synthetic import SyntheticCorpus, load_vocab
-    # every host thread this process may use -- explicitly, because torchrun exports OMP_NUM_THREADS=1 to its workers and
-    # the CPU arm would otherwise run single-threaded under the N > 1 launch
-    if not threads:
-        try:
-            threads = len(os.sched_getaffinity(0))
-        except AttributeError:
-            threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
+    torch.set_num_threads(threads or _host_threads())
     ocfg = O.OracleConfig(**GEO)
     P = O.init_params(ocfg, 1)
-    opt = O.AdamEMA(ocfg, P)
     corpus = SyntheticCorpus(load_vocab(size=GEO["V"]), T=T_FRAMES, C=256, seed=0)
+    if mode == "speed":
+        from oracle import speed_mode as S
+        trainer = S.SpeedTrainer(ocfg, P)
+    else:
+        opt = O.AdamEMA(ocfg, P)
     times = []
     for s in range(warmup + steps):
         b = corpus.batch(B, seed=s, L=L_TGT)
         x, y = torch.from_numpy(b["encoder_inputs"]), torch.from_numpy(b["decoder_targets"]).long()
         t0 = time.perf_counter()
-        masks = O.make_masks(ocfg, s, B, 34, L_TGT, FF_DROPOUT, RNN_DROPOUT, torch.float32)
-        _, ntok, g, _ = O.loss_and_grads(ocfg, P, x, None, y, masks=masks)
-        opt.step(P, g, 1.0 / ntok)
+        if mode == "speed":
+            trainer.step(x, y, FF_DROPOUT, RNN_DROPOUT)
+        else:
+            masks = O.make_masks(ocfg, s, B, 34, L_TGT, FF_DROPOUT, RNN_DROPOUT, torch.float32)
+            _, ntok, g, _ = O.loss_and_grads(ocfg, P, x, None, y, masks=masks)
+            opt.step(P, g, 1.0 / ntok)
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
@@ -113,22 +127,45 @@ def cpu_port_utt_per_s(B, steps, threads=None, warmup=1):
 
 
 def run_reference(args, rank, world):
+    """The reference arm: the reference's own TF1.15 path cannot be installed here, so this times the CPU oracle
+    in speed mode -- same workload, metric, steps and warm-up as the GPU arm, every host thread."""
     if rank != 0:
         return
     B = args.ref_batch
-    v, cores, dt = cpu_port_utt_per_s(B, args.steps, warmup=min(args.warmup, 1))
+    warm = max(args.warmup, 3)
+    v, cores, dt = cpu_port_utt_per_s(B, args.steps, warmup=warm, mode="speed")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config2: T=400 C=256 3x400 BiLSTM + 800 LSTM decoder V=1806, L=11, dropout .1/.5",
-                   "batch_per_step": B},
+        "config": {"workload": WORKLOAD, "batch_per_step": B},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} training steps of {B} utterances (oracle: torch CPU fp32; the reference's "
-                                   "TF1.15 + machine_learning path is not installable here)"},
+                         "sample": f"{args.steps} training steps of {B} utterances (oracle speed mode: torch CPU fp32, "
+                                   "torch.nn.LSTM / oneDNN; the reference's TF1.15 + machine_learning path is not installable here)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def measure_cublas_tflops(torch, dtype, tf32, n=8192, iters=20):
+    """Dense n^3 GEMM through cuBLAS (torch.matmul), random operands, CUDA events -- a measured tensor peak for the roofline."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    try:
+        a = torch.rand(n, n, device="cuda", dtype=dtype) - 0.5
+        b = torch.rand(n, n, device="cuda", dtype=dtype) - 0.5
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        return 2.0 * n ** 3 * iters / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 def main():
@@ -137,7 +174,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="utterances per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="utterances per GPU per step (weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch utterances per GPU (global batch grows with N); strong: --global-batch utterances per "
+                         "step in total, sharded over the N GPUs (north_star: the per-subject minibatch sharded across the GPUs)")
+    ap.add_argument("--global-batch", type=int, default=256, help="utterances per step over all GPUs (strong scaling)")
     ap.add_argument("--ref-batch", type=int, default=256, help="utterances per CPU step (the GPU arm's per-GPU batch)")
     ap.add_argument("--backend", default="auto")
     ap.add_argument("--cpu-baseline-steps", type=int, default=8)
@@ -168,13 +209,17 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    B = args.batch
+    if args.scaling == "strong":
+        assert args.global_batch % world == 0, "--global-batch must be divisible by the number of GPUs"
+        B = args.global_batch // world
+    else:
+        B = args.batch
     eng = Engine(EngineConfig(**GEO, max_B=B, max_T=T_FRAMES, max_L=20, max_beam=8, ff_dropout=FF_DROPOUT,
                               rnn_dropout=RNN_DROPOUT, gemm_backend=args.backend, device=local))
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     init_engine(eng, seed=1)
-    grads = flat_tensor(eng, _lib.GRAD)
+    grads = flat_tensor(eng, _lib.GRAD_AND_COUNT)      # gradients + token count: ONE collective per step
 
     # ---- synthetic pool: 4 distinct batches per rank, 105 MB each -> 420 MB > 126 MB L2
     corpus = SyntheticCorpus(load_vocab(size=GEO["V"]), T=T_FRAMES, C=256, seed=0)
@@ -187,6 +232,7 @@ def main():
         host.append((hx, hy))
         dev.append((hx.cuda(), hy.cuda()))
     ntok_t = torch.zeros(1, device="cuda")
+    # the token count of a step sits behind the gradients in the same buffer (written by the backward pass)
 
     # N > 1: ONE flat NCCL all-reduce of the 57 MB gradient buffer per step; --overlap-allreduce runs it bucket by
     # bucket on a side stream while the backward pass is still going (ecog2txt_b200/dist.py: BucketedAllReduce).  Either way
@@ -197,16 +243,14 @@ def main():
     ntok_cache = [float((hy != 0).sum()) for _, hy in host]
 
     def reduce_and_step(ntok_local_t):
-        if world == 1:
-            eng.adam_ema_step_dev(ntok_local_t)
-            return
-        ntok_t.copy_(ntok_local_t)
         if ar is not None:
+            ntok_t.copy_(ntok_local_t)
             ar.reduce_async(ntok_t)
-        else:
-            dist.all_reduce(grads)
-            dist.all_reduce(ntok_t)
-        eng.adam_ema_step_dev(ntok_t)
+            eng.adam_ema_step_dev(ntok_t)
+            return
+        if world > 1:
+            dist.all_reduce(grads)          # 57.4 MB of gradients + the token count in the tail: one NCCL all-reduce
+        eng.adam_ema_step_dev(None)         # 1 / global token count read from the tail, on the device
 
     def step_device(i):
         x, y = dev[i % NPOOL]
@@ -271,6 +315,13 @@ def main():
             pass
         peak_tf = peaks.get("bf16_tflops_sustained", 1590.0 * 0.88)
         psrc = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback"
+        # measured tf32 peak of THIS box: cuBLAS tf32 at 8192^3 with random operands (the analogue of the driver's cuBLAS
+        # bf16 figure); the larger of it and bf16_sustained / 2 is the denominator, so no kernel of ours can beat its "peak"
+        try:
+            tf32_meas = measure_cublas_tflops(torch, torch.float32, True)
+        except Exception as e:      # noqa: BLE001 -- a box without a usable cuBLAS still gets a bench line
+            print(f"[bench] cuBLAS tf32 measurement failed: {e}", file=sys.stderr)
+            tf32_meas = 0.0
         eng.profile_enable(True)
         nprof = 3
         for i in range(nprof):     # rank-local steps: no collective may be issued by rank 0 alone
@@ -292,7 +343,7 @@ def main():
         n_f, n_b = cat_ms[4][1], cat_ms[5][1]
         rec_ms = cat_ms[4][0] + cat_ms[5][0]
         tot = sum(v[0] for v in cat_ms.values())
-        peak_tf32 = peak_tf / 2.0
+        peak_tf32 = max(peak_tf / 2.0, tf32_meas)
         achieved = flops_launch * (n_f + n_b) / (rec_ms * 1e-3) / 1e12 if rec_ms > 0 else 0.0
         traffic = None
         try:
@@ -304,8 +355,7 @@ def main():
         conv_gbs = 2 * conv_bytes * nprof / (cat_ms[2][0] * 1e-3) / 1e9 if cat_ms[2][0] > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "k_lstm_rec<fwd> + k_lstm_bptt (persistent whole-layer recurrent kernels, tcgen05 kind::tf32)",
                 "achieved": achieved, "peak": peak_tf32, "unit": "TFLOP/s", "frac": achieved / peak_tf32, "traffic": traffic,
-                "peak_source": psrc + " / 2: operands are tf32 (fp32 in HBM, 10-bit mantissa in the tensor core); dense tf32 "
-                               "runs at half the bf16 rate",
+                "peak_source": f"max(cuBLAS tf32 8192^3 measured live with random operands = {tf32_meas:.1f}, {psrc} / 2 = {peak_tf / 2:.1f})",
                 "algorithmic_flops_per_launch": flops_launch, "launches_per_step": (n_f + n_b) // nprof,
                 "avg_launch_us": 1e3 * rec_ms / max(n_f + n_b, 1), "share_of_step": rec_ms / tot if tot > 0 else None,
                 "us_per_launch": {"fwd": 1e3 * cat_ms[4][0] / max(n_f, 1), "bptt": 1e3 * cat_ms[5][0] / max(n_b, 1)},
@@ -385,27 +435,31 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v1, _, dt1 = cpu_port_utt_per_s(64, 1, threads=1, warmup=0)      # also a 1-thread figure
-        v, cores, dt = cpu_port_utt_per_s(args.ref_batch, args.cpu_baseline_steps)
+        v, cores, dt = cpu_port_utt_per_s(args.ref_batch, args.cpu_baseline_steps, warmup=2, mode="speed")
+        vl, _, dtl = cpu_port_utt_per_s(args.ref_batch, 3, warmup=1, mode="loops")
+        v1, _, dt1 = cpu_port_utt_per_s(64, 2, threads=1, warmup=1, mode="speed")      # also a 1-thread figure
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{args.cpu_baseline_steps} training steps of {args.ref_batch} utterances of the same workload "
-                         f"({dt:.2f} s/step; oracle = torch CPU fp32 port, reference TF1.15 path not runnable here)",
-               "value_1thread": v1, "sample_1thread": f"1 training step of 64 utterances on one thread ({dt1:.2f} s)"}
+                         f"({dt:.2f} s/step; oracle speed mode = torch CPU fp32 with torch.nn.LSTM / oneDNN; the reference's "
+                         "TF1.15 path is not runnable here)",
+               "value_explicit_loops": vl, "sample_explicit_loops": f"3 steps of {args.ref_batch} utterances, one LSTM step per "
+                                                                    f"Python iteration + autograd ({dtl:.2f} s/step)",
+               "value_1thread": v1, "sample_1thread": f"2 steps of 64 utterances on one thread, speed mode ({dt1:.2f} s/step)"}
 
     if rank == 0:
         hx, hy = host[0]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "tf32" if eng.launch_counts()[1] > 0 else "f32", "data": "synthetic",
-            "config": {"workload": "config2: T=400 C=256 3x400 BiLSTM + 800 LSTM decoder V=1806, L=11, dropout .1/.5, "
-                                   "Adam+EMA, per-GPU batch %d" % B,
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B,
                        "global_batch": B * world, "cache": "pool of 4 batches x 105 MB per rank (> 126 MB L2)",
                        "parallelism": f"dp{world}", "gemm_backend": args.backend,
-                       "allreduce": None if world == 1 else ("one flat NCCL all-reduce after the backward pass" if ar is None else
+                       "allreduce": None if world == 1 else ("ONE flat NCCL all-reduce per step (57.4 MB of gradients + the token count in its tail)" if ar is None else
                                                               f"{len(eng.grad_buckets())} buckets on a side stream, overlapped with the backward pass")},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(hx.numel() * 4 + hy.numel() * 4),
-                    "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_gbs_per_rank": (hx.numel() * 4 + hy.numel() * 4) / (ms_e2e / args.steps * 1e-3) / 1e9},
             "gpu_launches": int(launches), "tcgen05_launches_total": int(tc1),
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         }

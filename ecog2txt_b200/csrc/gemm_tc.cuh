@@ -617,12 +617,27 @@ static inline void tc_gemm_tn(cudaStream_t st, const float* A, i64 lda, const fl
 }
 
 // times `iters` back-to-back launches of one GEMM shape on zero-filled operands (diagnostic; e2t_bench_gemm)
+// uniform(-0.5, 0.5) operands for the GEMM timing (all-zero operands do not toggle the datapath: the tensor pipe then runs
+// at a power / clock point no real GEMM sees, which is how an 8192^3 "1033 TFLOP/s" was once measured)
+__global__ void k_fill_uniform(float* p, size_t n, uint32_t seed) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t x = (uint32_t)i * 2654435761u + seed;
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  p[i] = (float)(x >> 8) * (1.0f / 16777216.0f) - 0.5f;
+}
+
 static inline float tc_gemm_bench(cudaStream_t st, int M, int N, int K, bool tn, float beta, int iters) {
   const i64 lda = tn ? (M + 3) / 4 * 4 : (K + 3) / 4 * 4, ldb = tn ? (N + 3) / 4 * 4 : (K + 3) / 4 * 4, ldc = (N + 3) / 4 * 4;
   float *dA, *dB, *dC;
   const size_t na = (size_t)(tn ? K : M) * lda, nb = (size_t)(tn ? K : N) * ldb, nc = (size_t)M * ldc;
   E2T_CHECK(cudaMalloc(&dA, na * 4)); E2T_CHECK(cudaMalloc(&dB, nb * 4)); E2T_CHECK(cudaMalloc(&dC, nc * 4));
-  E2T_CHECK(cudaMemsetAsync(dA, 0, na * 4, st)); E2T_CHECK(cudaMemsetAsync(dB, 0, nb * 4, st));
+  if (getenv("E2T_BENCH_ZERO_OPERANDS")) {
+    E2T_CHECK(cudaMemsetAsync(dA, 0, na * 4, st)); E2T_CHECK(cudaMemsetAsync(dB, 0, nb * 4, st));
+  } else {
+    k_fill_uniform<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(dA, na, 1u);
+    k_fill_uniform<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(dB, nb, 2u);
+  }
   E2T_CHECK(cudaMemsetAsync(dC, 0, nc * 4, st));
   cudaEvent_t e0, e1;
   E2T_CHECK(cudaEventCreate(&e0)); E2T_CHECK(cudaEventCreate(&e1));

@@ -20,8 +20,8 @@ import this module.  The product package (ecog2txt_b200) never does.
 
 Everything is plain torch on CPU; `dtype` selects fp32 (parity tolerance) or fp64 (to measure
 how far fp32 itself is from exact).  Loops are explicit (one LSTM step per python iteration) so
-that each line can be read against Appendix D; `speed=True` variants used for the CPU baseline
-call the same cell but through batched matmuls only (no oneDNN fused LSTM), i.e. a "port".
+that each line can be read against Appendix D.  The CPU baseline bench.py quotes is oracle/speed_mode.py: the
+same model with the recurrences on torch.nn.LSTM (oneDNN), checked against this file in tests/test_golden.py.
 """
 from __future__ import annotations
 

@@ -178,3 +178,34 @@ def test_oracle_loss_matches_torch_cross_entropy():
     loss, ntok, acts = O.train_loss(ocfg, P, torch.from_numpy(x), None, yt)
     ref = F.cross_entropy(acts["logits"].reshape(-1, ocfg.V), yt.reshape(-1), ignore_index=ocfg.pad_id, reduction="sum")
     assert abs(float(loss) - float(ref)) < 1e-4 * float(ref) and ntok == int((y != 0).sum())
+
+
+def test_speed_mode_oracle_matches_explicit_loops():
+    """oracle/speed_mode.py (torch.nn.LSTM / oneDNN, packed sequences -- the CPU baseline bench.py times) against the
+    explicit-loop oracle on a ragged batch that includes an empty utterance: loss and every gradient, fp32 tolerance."""
+    import parity_common as pc
+    from oracle import speed_mode as S
+    ocfg = O.OracleConfig(**pc.SMALL)
+    P = pc.make_params(ocfg)
+    x, lens, y = pc.make_batch(ocfg, 9, 50, 6)
+    x[4] = 0.0
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y).long()
+    lo, no, g, _ = O.loss_and_grads(ocfg, P, xt, None, yt)
+    m = S.SpeedModel(ocfg, P)
+    m.eval()
+    loss, ntok = m(xt, yt)
+    loss.backward()
+    assert ntok == no and abs(float(loss) - lo) <= 1e-5 * abs(lo)
+    gs = m.canonical_grads()
+    assert set(gs) == set(g)
+    for k in g:
+        assert pc.rel_err(gs[k].numpy(), g[k].numpy()) <= 2e-4, k
+    # one optimiser step of the trainer = the explicit oracle's Adam + EMA
+    tr = S.SpeedTrainer(ocfg, P)
+    tr.model.eval()
+    tr.step(xt, yt, 0.0, 0.0)
+    opt = O.AdamEMA(ocfg, dict(P))
+    P2 = dict(P)
+    opt.step(P2, g, 1.0 / no)
+    pb = f"seq2seq/decoder_projection_{ocfg.Hd}_{ocfg.V}_0/weights"
+    assert pc.rel_err(tr.model.proj_w.detach().numpy(), P2[pb].numpy()) <= 1e-5
