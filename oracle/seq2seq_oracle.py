@@ -211,9 +211,14 @@ def _act(z, kind):
     return z
 
 
-def temporal_conv(xr, lens, w4, bias, act):
+def temporal_conv(xr, lens, w4, bias, act, relu_mask=None, want_preact=False):
     """App. D item 3: kernel (1,W,C,E), stride W, zero-pad tail to a multiple of W.
-    Returns y [B,T',E] and lens' = ceil(len/W) (trainers.py:813-818,534-541)."""
+    Returns y [B,T',E] and lens' = ceil(len/W) (trainers.py:813-818,534-541).
+    relu_mask [B,T',E] (tests only): impose this activation pattern instead of (z > 0).  A ReLU is discontinuous in its
+    derivative: ONE pre-activation within rounding distance of zero that lands on the other side changes the whole
+    weight gradient by a few per cent at config 2 (measured: the fp32 and the fp64 oracle differ by 3.8e-2 of the
+    largest entry through a single flip among 217 600), so gradient parity is stated for a common pattern, and the
+    patterns themselves are compared separately (they may differ only where |z| is within rounding distance of 0)."""
     B, T, C = xr.shape
     _, W, C2, E = w4.shape
     assert C == C2
@@ -221,9 +226,10 @@ def temporal_conv(xr, lens, w4, bias, act):
     xp = torch.zeros(B, T2 * W, C, dtype=xr.dtype)
     xp[:, :T] = xr
     a = xp.reshape(B, T2, W * C)
-    y = _act(a @ w4.reshape(W * C, E) + bias, act)
+    z = a @ w4.reshape(W * C, E) + bias
+    y = z * relu_mask.to(z.dtype) if (relu_mask is not None and act == "relu") else _act(z, act)
     lens2 = (lens + W - 1) // W
-    return y, lens2
+    return (y, lens2, z) if want_preact else (y, lens2)
 
 
 def lstm_cell(z, c_prev):
@@ -256,15 +262,15 @@ def lstm_direction(x, lens, K, bias, reverse):
     return out, h, c
 
 
-def encoder(cfg, P, x, lens, subnet, train_masks=None):
+def encoder(cfg, P, x, lens, subnet, train_masks=None, conv_relu_mask=None):
     """A2-A5: lengths -> reverse -> conv -> stacked BiLSTM.  Returns dict of activations."""
     sid, C, W = cfg.subnet_ids[subnet], cfg.subnet_C[subnet], cfg.subnet_W[subnet]
     if lens is None:
         lens = infer_lengths(x)
     xr = reverse_within_length(x, lens)
     base = f"seq2seq/subnet_{sid}/encoder_embedding_{C}_{cfg.E}_0"
-    y, lens2 = temporal_conv(xr, lens, P[base + "/weights"], P[base + "/biases"], cfg.conv_act)
-    acts = {"lens": lens, "lens2": lens2, "conv_out_nodrop": y}
+    y, lens2, z = temporal_conv(xr, lens, P[base + "/weights"], P[base + "/biases"], cfg.conv_act, conv_relu_mask, True)
+    acts = {"lens": lens, "lens2": lens2, "conv_out_nodrop": y, "conv_preact": z}
     if train_masks is not None and "conv" in train_masks:
         y = y * train_masks["conv"]
     acts["conv_out"] = y
@@ -388,12 +394,12 @@ def aux_head(cfg, P, acts, aux_targets, subnet, masks=None):
     return loss * cfg.aux_penalty, int(valid.sum())
 
 
-def train_loss(cfg, P, x, lens, y, subnet=0, masks=None, aux_targets=None):
+def train_loss(cfg, P, x, lens, y, subnet=0, masks=None, aux_targets=None, conv_relu_mask=None):
     """Teacher-forced forward + masked CE (App. D items 6-7).  y [B,L] int64 with EOS appended and
     pad_id after it.  Returns (sum of token losses * penalty_scale [+ aux_penalty * sum of the
     encoder-targets losses], n_unmasked_tokens, acts); the caller divides by the *global* token count
     (one common normaliser for both penalties [CHOICE], so that data-parallel training needs one scalar)."""
-    acts = encoder(cfg, P, x, lens, subnet, masks)
+    acts = encoder(cfg, P, x, lens, subnet, masks, conv_relu_mask)
     h, c = acts["final_h"], acts["final_c"]
     B, L = y.shape
     prev = torch.full((B,), cfg.start_id, dtype=torch.int64)
@@ -429,10 +435,10 @@ def input_gradients(cfg, P, x, lens, y, subnet=0, aux_targets=None):
     return xg.grad
 
 
-def loss_and_grads(cfg, P, x, lens, y, subnet=0, masks=None, aux_targets=None):
+def loss_and_grads(cfg, P, x, lens, y, subnet=0, masks=None, aux_targets=None, conv_relu_mask=None):
     """Reference gradients by autograd of `train_loss` (sum, not yet / ntok)."""
     Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
-    loss, ntok, acts = train_loss(cfg, Pg, x, lens, y, subnet, masks, aux_targets)
+    loss, ntok, acts = train_loss(cfg, Pg, x, lens, y, subnet, masks, aux_targets, conv_relu_mask)
     loss.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in Pg.items()}
     return float(loss.detach()), ntok, grads, {k: (v.detach() if torch.is_tensor(v) else v) for k, v in acts.items()}

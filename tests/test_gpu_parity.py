@@ -13,15 +13,13 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("backend", ["simt", "auto"])
 @pytest.mark.parametrize("geo,B,T,L", [(pc.TINY, 3, 19, 5), (pc.SMALL, 8, 50, 6), (pc.MEDIUM, 32, 120, 7)])
 def test_train_step_matches_oracle(gpu_lib, backend, geo, B, T, L):
-    # fp32 SIMT: 2e-4 relative; tcgen05 kind::tf32 (10-bit mantissa operands, fp32 accumulate): 1e-2
-    tol = 2e-4 if backend == "simt" else 1e-2
-    pc.check_train_step(gpu_lib, geo, B, T, L, backend=backend, tol=tol)
+    # tolerances: parity_common.SIMT_TOL / TC_TOL (<= 10x the errors measured on B200, profiles/parity_r2.json)
+    pc.check_train_step(gpu_lib, geo, B, T, L, backend=backend)
 
 
 @pytest.mark.parametrize("backend", ["simt", "auto"])
 def test_train_step_with_dropout(gpu_lib, backend):
-    tol = 2e-4 if backend == "simt" else 1e-2
-    pc.check_train_step(gpu_lib, pc.MEDIUM, 16, 96, 6, ff=0.1, rnn=0.5, backend=backend, tol=tol)
+    pc.check_train_step(gpu_lib, pc.MEDIUM, 16, 96, 6, ff=0.1, rnn=0.5, backend=backend)
 
 
 def test_train_step_explicit_lengths_and_second_subject(gpu_lib):
@@ -42,7 +40,7 @@ def test_beam_decode(gpu_lib, backend):
 def test_persistent_recurrent_kernels_full_width(gpu_lib, B, T, ff, rnn):
     """H=400 BiLSTM layers through the whole-sequence tcgen05 kernels (1-2 batch tiles, ragged lengths,
     dropout copies), against the oracle; tolerance = tf32 operands (10-bit mantissa), fp32 accumulate."""
-    pc.check_train_step(gpu_lib, pc.WIDE, B, T, 5, ff=ff, rnn=rnn, backend="auto", tol=1e-2)
+    pc.check_train_step(gpu_lib, pc.WIDE, B, T, 5, ff=ff, rnn=rnn, backend="auto")
     c = pc.check_train_step.last_counters
     assert c["persistent_rnn_launches"] == 4, c   # 2 layers x (forward + backward)
 
@@ -71,8 +69,8 @@ def test_persistent_kernels_are_deterministic(gpu_lib):
 def test_attention_train_and_decode(gpu_lib, backend, tol):
     """A7 (optional Luong attention): training step (loss, every gradient incl. the attention tensors and the encoder
     path through the attention), greedy and beam decode, CUDA-core and tensor-core GEMM backends."""
-    pc.check_train_step(gpu_lib, pc.MEDIUM_ATTN, 16, 96, 6, backend=backend, tol=tol)
-    pc.check_train_step(gpu_lib, pc.MEDIUM_ATTN, 16, 96, 6, ff=0.1, rnn=0.5, backend=backend, tol=tol)
+    pc.check_train_step(gpu_lib, pc.MEDIUM_ATTN, 16, 96, 6, backend=backend)
+    pc.check_train_step(gpu_lib, pc.MEDIUM_ATTN, 16, 96, 6, ff=0.1, rnn=0.5, backend=backend)
     pc.check_decode(gpu_lib, pc.MEDIUM_ATTN, 8, 96, 6, backend=backend)
     pc.check_decode(gpu_lib, pc.MEDIUM_ATTN, 4, 96, 6, beam=4, backend=backend)
 
@@ -80,8 +78,8 @@ def test_attention_train_and_decode(gpu_lib, backend, tol):
 @pytest.mark.parametrize("backend,tol", [("simt", 2e-4), ("auto", 1e-2)])
 def test_bahdanau_attention_train_and_decode(gpu_lib, backend, tol):
     """A7, additive (Bahdanau) score: same coverage as the Luong module."""
-    pc.check_train_step(gpu_lib, pc.MEDIUM_BAH, 16, 96, 6, backend=backend, tol=tol)
-    pc.check_train_step(gpu_lib, pc.MEDIUM_BAH, 16, 96, 6, ff=0.1, rnn=0.5, backend=backend, tol=tol)
+    pc.check_train_step(gpu_lib, pc.MEDIUM_BAH, 16, 96, 6, backend=backend)
+    pc.check_train_step(gpu_lib, pc.MEDIUM_BAH, 16, 96, 6, ff=0.1, rnn=0.5, backend=backend)
     pc.check_decode(gpu_lib, pc.MEDIUM_BAH, 8, 96, 6, backend=backend)
     # temperature 0.2: at 0.7 no two beam scores of these random weights are 1e-2 apart and the token check would be vacuous
     pc.check_decode(gpu_lib, pc.MEDIUM_BAH, 4, 96, 6, beam=4, backend=backend, temperature=0.2)
@@ -257,10 +255,10 @@ def test_staged_inputs_match_host_path(gpu_lib):
 def test_encoder_targets_head(gpu_lib, backend, tol):
     """A6: the encoder-targets head (FF 2H -> hidden -> F on encoder layer 1; Gaussian and categorical targets), loss and
     every gradient -- the head's own tensors and the extra gradient that reaches layers 0-1 and the conv through it."""
-    pc.check_train_step(gpu_lib, pc.MEDIUM_AUX, 16, 96, 6, backend=backend, tol=tol)
-    pc.check_train_step(gpu_lib, pc.MEDIUM_AUX, 16, 96, 6, ff=0.1, rnn=0.5, backend=backend, tol=tol)
-    pc.check_train_step(gpu_lib, pc.MEDIUM_AUX_CAT, 16, 96, 6, backend=backend, tol=tol)
-    pc.check_train_step(gpu_lib, pc.TINY_AUX_CAT, 4, 21, 5, backend=backend, tol=tol)
+    pc.check_train_step(gpu_lib, pc.MEDIUM_AUX, 16, 96, 6, backend=backend)
+    pc.check_train_step(gpu_lib, pc.MEDIUM_AUX, 16, 96, 6, ff=0.1, rnn=0.5, backend=backend)
+    pc.check_train_step(gpu_lib, pc.MEDIUM_AUX_CAT, 16, 96, 6, backend=backend)
+    pc.check_train_step(gpu_lib, pc.TINY_AUX_CAT, 4, 21, 5, backend=backend)
 
 
 @pytest.mark.parametrize("backend,tol", [("simt", 2e-4), ("auto", 1e-2)])
