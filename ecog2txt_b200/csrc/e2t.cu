@@ -25,6 +25,9 @@
 #ifndef E2T_EMU
 #include "gemm_tc.cuh"
 #include "lstm_rec.cuh"
+#ifndef E2T_EMU
+#include "lstm_rec16.cuh"
+#endif
 #include "conv_tc.cuh"
 #endif
 
@@ -56,6 +59,9 @@ struct EncLayer {
   float* KP[2] = {nullptr, nullptr};
   float* bP[2] = {nullptr, nullptr};
   float* dKP[2] = {nullptr, nullptr};  // [(In+H+1), 4H] weight + bias gradients in permuted gate order (un-permuted in one batch)
+  // rec16 = the forward recurrence runs on k_lstm_fwd16 (lstm_rec16.cuh): fp16 copies of Wh^T [4H (permuted), round_up(H, 8)]
+  bool rec16 = false;
+  void* WhT16[2] = {nullptr, nullptr};
 };
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -141,6 +147,7 @@ struct e2t_handle {
   std::vector<BatchJob> batch2;       // second pass of the two-pass column sums (runs after `batch`)
   std::vector<BatchJob> batch3;       // un-permutes that consume column sums (run after `batch2`)
   float* rec_pws = nullptr; i64 rec_pws_n = 0;       // partial-dh workspace of the reduce-scatter BPTT kernel
+  void* rec_hx16 = nullptr; i64 rec_hx16_n = 0;      // fp16 h exchange buffer of k_lstm_fwd16 [2][T'][Bp][Hp]
   int* rec_counters = nullptr;   // arrival counters of the persistent recurrent kernels [2][n_bt][T2m]
   int64_t n_launch_rec = 0, n_graph_replays = 0;
 #ifndef E2T_EMU
@@ -516,6 +523,12 @@ void build_workspace(e2t_handle* h) {
     if (L.rec) h->perm_ws_n = std::max<i64>(h->perm_ws_n, (i64)(L.In + L.H + 1) * 4 * L.H);
 #ifndef E2T_EMU
     if (L.rec && rec::bptt_supported((int)Bm, L.H)) h->rec_pws_n = std::max<i64>(h->rec_pws_n, (i64)rec::bptt_ws_floats((int)Bm, L.H));
+    static const bool rec_v1 = getenv("E2T_REC_V1") != nullptr;      // A/B switch: first-generation forward kernel
+    L.rec16 = L.rec && !rec_v1 && rec16::fwd16_supported((int)Bm, L.H);
+    if (L.rec16) {
+      for (int d = 0; d < 2; ++d) L.WhT16[d] = h->alloc<uint16_t>((i64)4 * L.H * rec16::hp16(L.H));
+      h->rec_hx16_n = std::max<i64>(h->rec_hx16_n, (i64)rec16::hx16_halves((int)Bm, L.H, (int)T2));
+    }
 #endif
   }
   h->h0 = h->alloc<float>(Bm * c.Hd); h->c0 = h->alloc<float>(Bm * c.Hd);
@@ -541,6 +554,7 @@ void build_workspace(e2t_handle* h) {
     h->d_batch = reinterpret_cast<BatchJob*>(h->alloc<char>((i64)h->d_batch_cap * sizeof(BatchJob)));
   }
   if (h->rec_pws_n) h->rec_pws = h->alloc<float>(h->rec_pws_n);
+  if (h->rec_hx16_n) h->rec_hx16 = h->alloc<uint16_t>(h->rec_hx16_n);
   h->rec_counters = h->alloc<int>((i64)2 * cdiv(Bm, 128) * std::max<i64>(T2, Lm));
   h->ld_dec_kt = h->Dp + round_up(c.Hd, 4);
   h->dec_KT = h->alloc<float>((i64)4 * c.Hd * h->ld_dec_kt);
@@ -639,6 +653,24 @@ void repack(e2t_handle* h, const float* src, int src_id) {
     tr(src + h->conv_w[s], c.E, h->conv_wT[s], round_up(WC, 4), WC, c.E, 0, h->conv_wT_lo[s]);
   }
   batch_flush(h);
+#ifndef E2T_EMU
+  {   // 16-bit copies of Wh^T for the second-generation forward recurrence: one launch for all layers / directions
+    rec16::PackJobs jobs{};
+    i64 biggest = 0;
+    for (auto& L : h->enc)
+      if (L.rec16)
+        for (int d = 0; d < 2; ++d) {
+          rec16::PackJob& jb = jobs.j[jobs.n++];
+          jb.src = L.KT[d] + L.In4; jb.dst = static_cast<__half*>(L.WhT16[d]);
+          jb.rows = 4 * L.H; jb.cols = L.H; jb.ld_src = L.ldkt; jb.ld_dst = rec16::hp16(L.H);
+          biggest = std::max<i64>(biggest, (i64)jb.rows * jb.ld_dst);
+        }
+    if (jobs.n) {
+      auto kfn = rec16::k_pack_f16;
+      LAUNCH_L(h, "k_pack_f16", kfn, dim3((unsigned)std::min<i64>(cdiv(biggest, 256), 512), (unsigned)jobs.n), dim3(256), 0, jobs);
+    }
+  }
+#endif
   h->packed_dirty = false;
   h->packed_src = src_id;
 }
@@ -782,8 +814,14 @@ void encoder_forward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, 
 #ifndef E2T_EMU
       CatScope cs_(h, E2T_CAT_REC_FWD);
       prof_begin(h, "rec_forward", B, L.H, T2);
-      rec::rec_forward(h->stream, L.gates, L.cs, L.hs, drop ? L.hd : nullptr, L.KT, L.ldkt, L.In4, h->d_lens2,
-                       h->rec_counters, T2, B, L.H, dp, 2 * L.H);
+      if (L.rec16) {
+        const __half* w16[2] = {static_cast<const __half*>(L.WhT16[0]), static_cast<const __half*>(L.WhT16[1])};
+        rec16::rec_forward16(h->stream, L.gates, L.cs, L.hs, drop ? L.hd : nullptr, w16, static_cast<__half*>(h->rec_hx16),
+                             h->d_lens2, T2, B, L.H, dp, 2 * L.H);
+      } else {
+        rec::rec_forward(h->stream, L.gates, L.cs, L.hs, drop ? L.hd : nullptr, L.KT, L.ldkt, L.In4, h->d_lens2,
+                         h->rec_counters, T2, B, L.H, dp, 2 * L.H);
+      }
       prof_end(h);
       ++h->n_launch; ++h->n_launch_tc; ++h->n_launch_rec;
 #endif

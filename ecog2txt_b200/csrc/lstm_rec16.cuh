@@ -1,0 +1,388 @@
+// lstm_rec16.cuh -- persistent BiLSTM forward recurrence, second generation (A5 of SURVEY.md section 8a).
+//
+// Same decomposition as k_lstm_rec<false> (lstm_rec.cuh): grid = 2 directions x batch tiles of 128 rows x H/16 unit slices,
+// one cooperative launch runs ALL time steps, the CTA's recurrent weight slice stays in shared memory for the whole
+// sequence, accumulators live in TMEM, gate non-linearities + cell update come straight out of tcgen05.ld registers.
+// What changed, and why (B200 timelines of the first generation, profiles/r1p_rec_timeline.txt: 8.5 us per step of which
+// 2.65 us were 52 MMA issues, 0.7 us the release and 3.4 us the counter hand-off between the 25 CTAs of a chain):
+//
+//  * 16-bit operands.  h is a product of a sigmoid and a tanh, |h| < 1, and the recurrent weights are O(0.1): both are
+//    exactly representable in fp16 with the SAME 11-bit significand the tensor core keeps of a tf32 operand (range
+//    6e-5 .. 65504 normal, absolute error < 3e-8 below).  kind::f16 consumes K = 16 per instruction instead of 8: 25 MMAs
+//    per step instead of 52, half the shared memory for the weights (56 KB) and half the bytes of h through L2.
+//  * No flags, no counters, no fences on the critical path: the DATA is its own flag.  The exchange buffer
+//    hx [dir][t][b][H] (fp16) is filled with the bit pattern 0xFFFF before the launch (a NaN that the epilogue can never
+//    produce: cvt.rn.f16.f32 canonicalises NaN to 0x7FFF); every step writes its own time slot exactly once, so a consumer
+//    simply re-loads a 16-byte piece until none of its words is the fill pattern.  One L2 round trip replaces
+//    store -> release -> counter -> poll -> acquire -> TMA.
+//  * The 256 epilogue threads are also the loaders: they would otherwise idle while the step's h arrives.  Each pulls its
+//    pieces with 16-byte ld.relaxed.gpu, writes them into the 128B-swizzled K-major operand tile, fences the async proxy and
+//    arrives on the k-chunk's mbarrier; the MMA warp issues chunk by chunk as they complete.
+//
+// 8 warps, all loader + epilogue (thread = batch row x 8 hidden units); warp 0 also loads the weights (TMA, once), owns the
+// TMEM allocation and issues the MMAs once its own pieces are in place (a ninth warp would cap every thread at 168 registers --
+// ptxas budgets for 384 threads -- and spill the 28 outstanding 16-byte loads).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "lstm_rec.cuh"
+
+namespace rec16 {
+
+using namespace tc;
+using rec::kU;
+using rec::kBM;
+using rec::kUT;
+
+constexpr int kWorkThreads = 256;
+constexpr int kThreads16 = kWorkThreads;
+constexpr int kKC = 64;                         // fp16 elements per 128-byte swizzle row = one k-chunk
+constexpr uint32_t kAChunk = kBM * 128;         // 16 KB: 128 rows x 128 B
+constexpr uint32_t kWChunk = 4 * kU * 128;      // 8 KB: 64 gate rows x 128 B
+constexpr uint32_t kFill32 = 0xFFFFFFFFu;       // two fp16 fill patterns
+
+// cute::UMMA::InstrDescriptor for kind::f16: c_format F32=1 [4,6) | a_format F16=0 [7,10) | b_format F16=0 [10,13)
+// | a_major / b_major = K (0) | N>>3 [17,23) | M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_v4(void* p, uint4 v) {
+  asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ bool has_fill(const uint4& v) {
+  return v.x == kFill32 || v.y == kFill32 || v.z == kFill32 || v.w == kFill32;
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);      // NaN -> 0x7FFF, never the 0xFFFF fill pattern
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+struct Fwd16P {
+  float* gates[2];        // [T', B, 4H] x-projection (+bias) in, gate activations out (permuted gate order)
+  float* cs[2];           // [T', B, H]
+  float* hs;              // [T', B, 2H]   fwd half | bwd half (fp32: what the next layer / the backward pass read)
+  float* hd;              // dropped copy of hs (nullable)
+  __half* hx;             // [2][T'][Bp][Hp] fp16 exchange buffer, pre-filled with 0xFFFF
+  const int* lens2;       // [B] (nullable: all steps valid)
+  int steps, B, Bp, H, Hp, n_bt, n_slices;
+  DropP dp; int drop_F;
+  long long* dbg;         // E2T_REC_DEBUG: per-step clock64 stamps of CTA 0 ([steps][8]), else NULL
+};
+
+template <int NKC>
+__global__ void __launch_bounds__(kThreads16, 1)
+k_lstm_fwd16(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1, Fwd16P p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem_w = smem;                                   // [NKC][64 rows][128 B]
+  unsigned char* smem_a = smem + (size_t)NKC * kWChunk;           // [NKC][128 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)NKC * kAChunk);
+  uint64_t* w_bar = bars;
+  uint64_t* acc_full = bars + 1;
+  uint64_t* a_full = bars + 2;                                    // [NKC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + NKC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x % p.n_slices;
+  const int bt = (blockIdx.x / p.n_slices) % p.n_bt;
+  const int d = blockIdx.x / (p.n_slices * p.n_bt);
+  const bool reverse = d == 1;
+  const int steps = p.steps, B = p.B, H = p.H;
+  long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(w_bar), 1);
+    mbar_init(smem_u32(acc_full), 1);
+    for (int k = 0; k < NKC; ++k) mbar_init(smem_u32(&a_full[k]), kWorkThreads / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 64);
+  // the operand tile starts as zeros: rows past B are never loaded, and the accumulator rows they feed stay finite
+  for (uint32_t i = threadIdx.x; i < (uint32_t)NKC * kAChunk / 16; i += kWorkThreads)
+    reinterpret_cast<uint4*>(smem_a)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
+  const __half* hx_dir = p.hx + (size_t)d * steps * p.Bp * p.Hp;
+
+  constexpr uint32_t idesc = make_idesc_f16(kBM, 4 * kU);
+  const uint64_t desc_a0 = make_smem_desc(smem_u32(smem_a));
+  const uint64_t desc_w0 = make_smem_desc(smem_u32(smem_w));
+  if (warp == 0) {
+    // weights, once: 64 permuted gate rows of Wh^T (fp16) x 64 k columns per chunk; the K tail is zero-filled
+    const CUtensorMap* map_w = d ? &map_w1 : &map_w0;
+    if (elect_one()) {
+      const uint32_t wb = smem_u32(w_bar);
+      mbar_expect_tx(wb, (uint32_t)NKC * kWChunk);
+      for (int kc = 0; kc < NKC; ++kc)
+        tma_load_2d(smem_u32(smem_w + (size_t)kc * kWChunk), map_w, wb, kc * kKC, j * 4 * kU);
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(w_bar), 0);
+    fence_after_sync();
+  }
+  {
+    // ================= loader + epilogue: thread = (batch row, 8 hidden units) =================
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int ug = warp >> 2;                        // unit group (8 units)
+    const int r = quad * 32 + lane;
+    const int b = bt * kBM + r;
+    const bool row_ok = b < B;
+    const int u0 = j * kU + ug * kUT;
+    const int z0 = j * 4 * kU + ug * 4 * kUT;        // 32 contiguous gate columns [gate][8] in the permuted layout
+    const int len2 = row_ok ? (p.lens2 ? p.lens2[b] : steps) : 0;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ug * 4 * kUT);
+    float* gates = d ? p.gates[1] : p.gates[0];
+    float* cs = d ? p.cs[1] : p.cs[0];
+    const int col0 = d * H;
+    float carry[kUT];
+#pragma unroll
+    for (int i = 0; i < kUT; ++i) carry[i] = 0.f;
+    // loader geometry: k-chunk kc holds 128 rows x 8 pieces of 16 B; piece m * 256 + tid -> row (>> 3), column (& 7)
+    const int lrow0 = threadIdx.x >> 3, lc = threadIdx.x & 7;       // rows lrow0 + 32 m, m = 0..3
+    const uint32_t a_base = smem_u32(smem_a);
+
+    for (int s = 0; s < steps; ++s) {
+      const int t = reverse ? steps - 1 - s : s;
+      const bool valid = row_ok && t < len2;
+      float* zrow = gates + ((i64)t * B + b) * 4 * H + z0;
+      float z[4 * kUT];
+      float acc[4 * kUT];
+      if (s == 0 && valid) rec::ldv8<4 * kUT>(z, zrow);
+      if (s > 0) {
+        const int t_src = reverse ? t + 1 : t - 1;
+        const __half* src = hx_dir + (size_t)t_src * p.Bp * p.Hp + (size_t)(bt * kBM) * p.Hp;
+        if (dbg && threadIdx.x == 0) dbg[s * 8 + 0] = clock64();
+        uint4 v[NKC][4];
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc)
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int row = lrow0 + 32 * m, col = kc * kKC + lc * 8;
+            if (col < H && bt * kBM + row < B) v[kc][m] = ld_relaxed_v4(src + (size_t)row * p.Hp + col);
+          }
+        const long long t0 = clock64();
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc) {
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int row = lrow0 + 32 * m, col = kc * kKC + lc * 8;
+            if (col < H && bt * kBM + row < B) {
+              while (has_fill(v[kc][m])) {
+                if (clock64() - t0 > 4000000000LL) __trap();        // a lost producer must trap, not hang the GPU
+                v[kc][m] = ld_relaxed_v4(src + (size_t)row * p.Hp + col);
+              }
+              const uint32_t dst = a_base + (uint32_t)kc * kAChunk + (uint32_t)row * 128 + (uint32_t)((lc ^ (row & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[kc][m].x), "r"(v[kc][m].y),
+                           "r"(v[kc][m].z), "r"(v[kc][m].w) : "memory");
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (kc == 0) fence_before_sync();        // this thread's tcgen05.ld of the previous step precede the next MMAs
+          __syncwarp();
+          if (lane == 0) rec::mbar_arrive(smem_u32(&a_full[kc]));
+        }
+        if (warp == 0) {
+          // MMA issue (warp-convergent, one elected lane): chunk by chunk as the other warps' pieces land
+          const uint32_t ph = (uint32_t)(s - 1) & 1u;
+#pragma unroll
+          for (int kc = 0; kc < NKC; ++kc) {
+            mbar_wait(smem_u32(&a_full[kc]), ph);
+            fence_after_sync();
+            if (elect_one()) {
+              const int nk = min(4, (H - kc * kKC) / 16);       // K = 16 per instruction; H % 16 == 0
+              for (int k = 0; k < nk; ++k)
+                umma_f16(tmem_base, desc_a0 + (uint64_t)((kc * kAChunk + k * 32) >> 4),
+                         desc_w0 + (uint64_t)((kc * kWChunk + k * 32) >> 4), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+              if (kc == NKC - 1) umma_commit(smem_u32(acc_full));
+            }
+            __syncwarp();
+          }
+        }
+        if (dbg && threadIdx.x == 0) dbg[s * 8 + 1] = clock64();
+        // the x-projection of this step: its latency hides behind the MMAs (loading it before the poll would keep 32 more
+        // registers live across the 28 outstanding 16-byte loads of the h tile)
+        if (valid) rec::ldv8<4 * kUT>(z, zrow);
+        mbar_wait(smem_u32(acc_full), (uint32_t)(s - 1) & 1u);
+        fence_after_sync();
+        if (dbg && threadIdx.x == 0) dbg[s * 8 + 2] = clock64();
+        rec::tmem_ld_cols<4 * kUT>(taddr, acc);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4 * kUT; ++i) acc[i] = 0.f;
+      }
+      float hv[kUT];
+      if (valid) {
+#pragma unroll
+        for (int e = 0; e < kUT; ++e) {
+          const float gi = rec::sigm(z[e] + acc[e]);
+          const float gj = rec::tanh_fast(z[kUT + e] + acc[kUT + e]);
+          const float gf = rec::sigm(z[2 * kUT + e] + acc[2 * kUT + e] + 1.0f);
+          const float go = rec::sigm(z[3 * kUT + e] + acc[3 * kUT + e]);
+          const float c = gf * carry[e] + gi * gj;
+          carry[e] = c;
+          hv[e] = go * rec::tanh_fast(c);
+          z[e] = gi; z[kUT + e] = gj; z[2 * kUT + e] = gf; z[3 * kUT + e] = go;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < kUT; ++e) { carry[e] = 0.f; hv[e] = 0.f; }
+      }
+      // 1) what the other CTAs of the chain wait for: this thread's 8 units of h as ONE 16-byte store (zeros past the length)
+      if (row_ok) {
+        uint4 hp;
+        hp.x = pack_h2(hv[0], hv[1]); hp.y = pack_h2(hv[2], hv[3]); hp.z = pack_h2(hv[4], hv[5]); hp.w = pack_h2(hv[6], hv[7]);
+        st_relaxed_v4(const_cast<__half*>(hx_dir) + (size_t)t * p.Bp * p.Hp + (size_t)b * p.Hp + u0, hp);
+      }
+      if (dbg && threadIdx.x == 0) dbg[s * 8 + 3] = clock64();
+      // 2) everything the next layer / the backward pass read goes out behind it
+      if (row_ok) {
+        rec::stv8<kUT>(p.hs + ((i64)t * B + b) * 2 * H + col0 + u0, hv);
+        if (valid) rec::stv8<4 * kUT>(zrow, z);
+        rec::stv8<kUT>(cs + ((i64)t * B + b) * H + u0, carry);
+        if (p.hd) {
+          const uint32_t idx0 = (uint32_t)(((i64)t * B + b) * p.drop_F + col0 + u0);
+          const uint32_t key = p.dp.key, thresh = p.dp.thresh;
+          const float inv = p.dp.inv;
+          float o[kUT];
+#pragma unroll
+          for (int e = 0; e < kUT; ++e) o[e] = (valid && e2t_keep(key, idx0 + e, thresh)) ? hv[e] * inv : 0.f;
+          rec::stv8<kUT>(p.hd + ((i64)t * B + b) * 2 * H + col0 + u0, o);
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// fp32 [rows, ld_src] -> fp16 [rows, ld_dst] (columns [0, cols); the padding columns up to ld_dst are zeroed), several
+// matrices per launch: the 16-bit copies of Wh^T the recurrence multiplies with
+struct PackJob { const float* src; __half* dst; int rows, cols, ld_src, ld_dst; };
+struct PackJobs { PackJob j[16]; int n; };
+__global__ void k_pack_f16(PackJobs jobs) {
+  const PackJob& jb = jobs.j[blockIdx.y];
+  const i64 n = (i64)jb.rows * jb.ld_dst;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    const int r = (int)(i / jb.ld_dst), c = (int)(i % jb.ld_dst);
+    float v = c < jb.cols ? jb.src[(i64)r * jb.ld_src + c] : 0.f;
+    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    jb.dst[i] = __float2half_rn(v);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+inline CUtensorMap make_map_f16(const __half* ptr, i64 rows, i64 cols, i64 ld, int box_rows, int box_cols) {
+  CUtensorMap m;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t bx[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) throw std::runtime_error("e2t: cuTensorMapEncodeTiled entry point not found");
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), gdim, gstr, bx, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("e2t: cuTensorMapEncodeTiled (f16) failed with code " + std::to_string((int)r));
+  return m;
+}
+
+inline int nkc16(int H) { return (H + kKC - 1) / kKC; }
+inline size_t fwd16_smem_bytes(int H) { return (size_t)nkc16(H) * (kWChunk + kAChunk) + (2 + 8) * 8 + 16 + 1024; }
+inline int hp16(int H) { return (H + 7) / 8 * 8; }
+inline int bp16(int B) { return (B + kBM - 1) / kBM * kBM; }
+inline size_t hx16_halves(int B, int H, int steps) { return (size_t)2 * steps * bp16(B) * hp16(H); }
+
+inline bool fwd16_supported(int B, int H) {
+  if (H % kU != 0 || H < kU || H > 512 || B < 1) return false;
+  const int n_bt = (B + kBM - 1) / kBM, n_slices = H / kU;
+  if (2 * n_bt * n_slices > rec::sm_count()) return false;
+  return fwd16_smem_bytes(H) <= 227 * 1024;
+}
+
+template <int NKC>
+inline void fwd16_launch_t(cudaStream_t st, const CUtensorMap& w0, const CUtensorMap& w1, Fwd16P& p) {
+  auto kfn = k_lstm_fwd16<NKC>;
+  const size_t smem = fwd16_smem_bytes(p.H);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    E2T_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * p.n_bt * p.n_slices)); cfg.blockDim = dim3(kThreads16);
+  cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeCooperative; attrs[0].val.cooperative = 1;   // all CTAs co-resident
+  cfg.attrs = attrs; cfg.numAttrs = 1;
+  E2T_CHECK(cudaLaunchKernelEx(&cfg, kfn, w0, w1, p));
+}
+
+// Forward of one BiLSTM layer.  WhT16[d]: fp16 copies of Wh^T [4H (permuted gate rows), Hp]; hx: exchange buffer of at
+// least hx16_halves(B, H, steps) halves.
+inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const cs[2], float* hs, float* hd,
+                          const __half* const WhT16[2], __half* hx, const int* lens2, int steps, int B, int H, DropP dp,
+                          int drop_F) {
+  Fwd16P p{};
+  for (int d = 0; d < 2; ++d) { p.gates[d] = gates[d]; p.cs[d] = cs[d]; }
+  p.hs = hs; p.hd = hd; p.hx = hx; p.lens2 = lens2;
+  p.steps = steps; p.B = B; p.Bp = bp16(B); p.H = H; p.Hp = hp16(H);
+  p.n_bt = (B + kBM - 1) / kBM; p.n_slices = H / kU;
+  p.dp = dp; p.drop_F = drop_F;
+  CUtensorMap mw[2];
+  for (int d = 0; d < 2; ++d) mw[d] = make_map_f16(WhT16[d], 4 * (i64)H, H, p.Hp, 4 * kU, kKC);
+  E2T_CHECK(cudaMemsetAsync(hx, 0xFF, hx16_halves(B, H, steps) * sizeof(__half), st));
+  static int dbg_left = getenv("E2T_REC_DEBUG") ? atoi(getenv("E2T_REC_DEBUG")) : 0;
+  p.dbg = nullptr;
+  if (dbg_left > 0) {
+    E2T_CHECK(cudaMalloc(&p.dbg, (size_t)steps * 8 * sizeof(long long)));
+    E2T_CHECK(cudaMemsetAsync(p.dbg, 0, (size_t)steps * 8 * sizeof(long long), st));
+  }
+  switch (nkc16(H)) {
+    case 1: fwd16_launch_t<1>(st, mw[0], mw[1], p); break;
+    case 2: fwd16_launch_t<2>(st, mw[0], mw[1], p); break;
+    case 3: fwd16_launch_t<3>(st, mw[0], mw[1], p); break;
+    case 4: fwd16_launch_t<4>(st, mw[0], mw[1], p); break;
+    case 5: fwd16_launch_t<5>(st, mw[0], mw[1], p); break;
+    case 6: fwd16_launch_t<6>(st, mw[0], mw[1], p); break;
+    case 7: fwd16_launch_t<7>(st, mw[0], mw[1], p); break;
+    case 8: fwd16_launch_t<8>(st, mw[0], mw[1], p); break;
+    default: throw std::runtime_error("e2t: rec_forward16 needs H <= 512");
+  }
+  if (p.dbg) {
+    --dbg_left;
+    std::vector<long long> hst((size_t)steps * 8);
+    E2T_CHECK(cudaStreamSynchronize(st));
+    E2T_CHECK(cudaMemcpy(hst.data(), p.dbg, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.dbg);
+    fprintf(stderr, "[rec fwd16] steps=%d B=%d H=%d grid=%d (cycles of CTA 0 thread 0, rel. to the start of the step's poll)\n"
+                    "  step  ->h_in_smem  ->acc_seen  ->h_stored | step_total\n", steps, B, H, 2 * p.n_bt * p.n_slices);
+    for (int s = 1; s < steps; ++s) {
+      const long long* e = &hst[(size_t)s * 8];
+      const long long prev = s > 1 ? hst[(size_t)(s - 1) * 8] : 0;
+      fprintf(stderr, "  %4d  %8lld %8lld %8lld | %8lld\n", s, e[1] - e[0], e[2] - e[0], e[3] - e[0], prev ? e[0] - prev : 0);
+    }
+  }
+}
+
+}  // namespace rec16
