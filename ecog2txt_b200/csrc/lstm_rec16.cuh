@@ -164,30 +164,41 @@ k_lstm_fwd16(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__
       float* zrow = gates + ((i64)t * B + b) * 4 * H + z0;
       float z[4 * kUT];
       float acc[4 * kUT];
-      if (s == 0 && valid) rec::ldv8<4 * kUT>(z, zrow);
+      if (valid) rec::ldv8<4 * kUT>(z, zrow);                        // in flight while h arrives
       if (s > 0) {
         const int t_src = reverse ? t + 1 : t - 1;
         const __half* src = hx_dir + (size_t)t_src * p.Bp * p.Hp + (size_t)(bt * kBM) * p.Hp;
         if (dbg && threadIdx.x == 0) dbg[s * 8 + 0] = clock64();
+        // Pull this thread's pieces of h_{t-1}: every round re-issues ALL loads that still showed the fill pattern (they
+        // are in flight together: one L2 round trip per round, not one per piece), until none is left.
         uint4 v[NKC][4];
+        uint32_t pending = 0;
 #pragma unroll
         for (int kc = 0; kc < NKC; ++kc)
 #pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const int row = lrow0 + 32 * m, col = kc * kKC + lc * 8;
-            if (col < H && bt * kBM + row < B) v[kc][m] = ld_relaxed_v4(src + (size_t)row * p.Hp + col);
-          }
+          for (int m = 0; m < 4; ++m)
+            if (kc * kKC + lc * 8 < H && bt * kBM + lrow0 + 32 * m < B) pending |= 1u << (kc * 4 + m);
         const long long t0 = clock64();
+        while (pending) {
+#pragma unroll
+          for (int kc = 0; kc < NKC; ++kc)
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+              if (pending & (1u << (kc * 4 + m)))
+                v[kc][m] = ld_relaxed_v4(src + (size_t)(lrow0 + 32 * m) * p.Hp + kc * kKC + lc * 8);
+#pragma unroll
+          for (int kc = 0; kc < NKC; ++kc)
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+              if ((pending & (1u << (kc * 4 + m))) && !has_fill(v[kc][m])) pending &= ~(1u << (kc * 4 + m));
+          if (pending && clock64() - t0 > 4000000000LL) __trap();      // a lost producer must trap, not hang the GPU
+        }
 #pragma unroll
         for (int kc = 0; kc < NKC; ++kc) {
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
             const int row = lrow0 + 32 * m, col = kc * kKC + lc * 8;
             if (col < H && bt * kBM + row < B) {
-              while (has_fill(v[kc][m])) {
-                if (clock64() - t0 > 4000000000LL) __trap();        // a lost producer must trap, not hang the GPU
-                v[kc][m] = ld_relaxed_v4(src + (size_t)row * p.Hp + col);
-              }
               const uint32_t dst = a_base + (uint32_t)kc * kAChunk + (uint32_t)row * 128 + (uint32_t)((lc ^ (row & 7)) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[kc][m].x), "r"(v[kc][m].y),
                            "r"(v[kc][m].z), "r"(v[kc][m].w) : "memory");
@@ -216,9 +227,6 @@ k_lstm_fwd16(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__
           }
         }
         if (dbg && threadIdx.x == 0) dbg[s * 8 + 1] = clock64();
-        // the x-projection of this step: its latency hides behind the MMAs (loading it before the poll would keep 32 more
-        // registers live across the 28 outstanding 16-byte loads of the h tile)
-        if (valid) rec::ldv8<4 * kUT>(z, zrow);
         mbar_wait(smem_u32(acc_full), (uint32_t)(s - 1) & 1u);
         fence_after_sync();
         if (dbg && threadIdx.x == 0) dbg[s * 8 + 2] = clock64();
