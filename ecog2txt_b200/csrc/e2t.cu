@@ -148,6 +148,9 @@ struct e2t_handle {
   std::vector<BatchJob> batch3;       // un-permutes that consume column sums (run after `batch2`)
   float* rec_pws = nullptr; i64 rec_pws_n = 0;       // partial-dh workspace of the reduce-scatter BPTT kernel
   void* rec_hx16 = nullptr; i64 rec_hx16_n = 0;      // fp16 h exchange buffer of k_lstm_fwd16 [2][T'][Bp][Hp]
+#ifndef E2T_EMU
+  rec16::BpttTags bptt_tags{{0, 0}, -1, -1};         // tag state of rec_pws (k_lstm_bptt2)
+#endif
   int* rec_counters = nullptr;   // arrival counters of the persistent recurrent kernels [2][n_bt][T2m]
   int64_t n_launch_rec = 0, n_graph_replays = 0;
 #ifndef E2T_EMU
@@ -1208,7 +1211,11 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
       const float* csd[2] = {Ly.cs[0], Ly.cs[1]};
       prof_begin(h, "rec_backward", B, Ly.H, T2);
       static const bool use_allgather = getenv("E2T_REC_BWD_ALLGATHER") != nullptr;
-      if (!use_allgather && h->rec_pws && rec::bptt_supported(h->Bm, Ly.H))
+      static const bool bptt_v1 = getenv("E2T_REC_V1") != nullptr || getenv("E2T_BPTT_V1") != nullptr;
+      if (!use_allgather && !bptt_v1 && h->rec_pws && rec::bptt_supported(h->Bm, Ly.H))
+        rec16::rec_backward_rs2(h->stream, Ly.gates, csd, Ly.dhs, Kd, Ly.In, h->d_lens2, top ? h->dc0 : nullptr, c.Hd,
+                                top ? h->d_tlast : nullptr, h->rec_pws, (size_t)h->rec_pws_n, h->bptt_tags, T2, B, Ly.H);
+      else if (!use_allgather && h->rec_pws && rec::bptt_supported(h->Bm, Ly.H))
         rec::rec_backward_rs(h->stream, Ly.gates, csd, Ly.dhs, Kd, Ly.In, h->d_lens2, top ? h->dc0 : nullptr, c.Hd,
                              top ? h->d_tlast : nullptr, h->rec_counters, h->rec_pws, T2, B, Ly.H);
       else

@@ -192,7 +192,9 @@ k_lstm_fwd16(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__
             for (int m = 0; m < 4; ++m)
               if ((pending & (1u << (kc * 4 + m))) && !has_fill(v[kc][m])) pending &= ~(1u << (kc * 4 + m));
           if (pending && clock64() - t0 > 4000000000LL) __trap();      // a lost producer must trap, not hang the GPU
+          if (dbg && threadIdx.x == 0) dbg[s * 8 + 7] += 1;             // poll rounds
         }
+        if (dbg && threadIdx.x == 0) dbg[s * 8 + 4] = clock64();
 #pragma unroll
         for (int kc = 0; kc < NKC; ++kc) {
 #pragma unroll
@@ -209,6 +211,7 @@ k_lstm_fwd16(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__
           __syncwarp();
           if (lane == 0) rec::mbar_arrive(smem_u32(&a_full[kc]));
         }
+        if (dbg && threadIdx.x == 0) dbg[s * 8 + 5] = clock64();
         if (warp == 0) {
           // MMA issue (warp-convergent, one elected lane): chunk by chunk as the other warps' pieces land
           const uint32_t ph = (uint32_t)(s - 1) & 1u;
@@ -216,6 +219,7 @@ k_lstm_fwd16(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__
           for (int kc = 0; kc < NKC; ++kc) {
             mbar_wait(smem_u32(&a_full[kc]), ph);
             fence_after_sync();
+            if (kc == NKC - 1 && dbg && threadIdx.x == 0) dbg[s * 8 + 6] = clock64();     // every warp's pieces are in
             if (elect_one()) {
               const int nk = min(4, (H - kc * kKC) / 16);       // K = 16 per instruction; H % 16 == 0
               for (int k = 0; k < nk; ++k)
@@ -384,11 +388,355 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
     E2T_CHECK(cudaMemcpy(hst.data(), p.dbg, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(p.dbg);
     fprintf(stderr, "[rec fwd16] steps=%d B=%d H=%d grid=%d (cycles of CTA 0 thread 0, rel. to the start of the step's poll)\n"
-                    "  step  ->h_in_smem  ->acc_seen  ->h_stored | step_total\n", steps, B, H, 2 * p.n_bt * p.n_slices);
+                    "  step  rounds ->polled ->deposited ->all_warps_in ->mma_issued ->acc_seen ->h_stored | step_total\n",
+            steps, B, H, 2 * p.n_bt * p.n_slices);
     for (int s = 1; s < steps; ++s) {
       const long long* e = &hst[(size_t)s * 8];
       const long long prev = s > 1 ? hst[(size_t)(s - 1) * 8] : 0;
-      fprintf(stderr, "  %4d  %8lld %8lld %8lld | %8lld\n", s, e[1] - e[0], e[2] - e[0], e[3] - e[0], prev ? e[0] - prev : 0);
+      fprintf(stderr, "  %4d  %4lld %8lld %8lld %8lld %8lld %8lld %8lld | %8lld\n", s, e[7], e[4] - e[0], e[5] - e[0], e[6] - e[0],
+              e[1] - e[0], e[2] - e[0], e[3] - e[0], prev ? e[0] - prev : 0);
+    }
+  }
+}
+
+
+// ================================================================================================
+// BPTT, second generation (k_lstm_bptt2): the reduce-scatter formulation of k_lstm_bptt (lstm_rec.cuh) -- every CTA multiplies
+// only its own 64 dz columns with the matching columns of Wh for all H units and the [128, H] partial dh goes through an
+// L2-resident workspace -- with the counter / release / acquire hand-off replaced by TAGGED DATA:
+//   * every fp32 word of a partial carries, in its least-significant mantissa bit, the parity of the number of times its
+//     workspace slot has been written (the slot of (step parity, direction, batch tile, writer) is rewritten every second
+//     step).  A reader re-loads a 16-byte piece until all four tag bits show the value it expects; stale data from two steps
+//     earlier carries the other value.  No flags, no fences, no resets; one bit (6e-8 relative) of the partial is given up.
+//   * a writer drains its accumulator owner by owner in the order the owners sum (owner j-1 first), and an owner sums its
+//     n partials starting with writer j+1: the hand-off pipelines, and the summation order is a fixed function of the
+//     slice index (bit-identical gradients run to run).
+// The workspace must hold consistent tags: the host memsets it whenever (batch tiles, H) change and tracks the write counts
+// per step parity (BpttTags).
+// ================================================================================================
+struct BpttTags { uint32_t epoch[2]; int n_bt, H; };
+
+struct Bptt2P {
+  rec::RecBptt r;
+  uint32_t epoch0, epoch1;       // writes so far to the parity-0 / parity-1 slots
+};
+
+__device__ __forceinline__ uint4 ld_relaxed_v4f(const float* p) { return ld_relaxed_v4(p); }
+__device__ __forceinline__ bool tags_ok(const uint4& v, uint32_t tw) {
+  return ((((v.x ^ tw) | (v.y ^ tw) | (v.z ^ tw) | (v.w ^ tw)) & 1u) == 0u);
+}
+
+__global__ void __launch_bounds__(rec::kBpttThreads, 1)
+k_lstm_bptt2(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1, Bptt2P pp) {
+  using namespace rec;
+  const RecBptt& p = pp.r;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int H = p.H, steps = p.steps, B = p.B;
+  const uint32_t WCH = (uint32_t)H * 128;                 // one 32-column chunk of the resident weights [H rows x 128 B]
+  unsigned char* smem_w = smem;                           // [2 chunks][H][32] K-major, 128B swizzle
+  unsigned char* smem_a = smem + 2 * (size_t)WCH;         // [2 chunks][128][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + 2 * A_STAGE_BYTES);
+  uint64_t* w_bar = bars;
+  uint64_t* acc_full = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = p.n_slices;
+  const int j = blockIdx.x % n;
+  const int bt = (blockIdx.x / n) % p.n_bt;
+  const int d = blockIdx.x / (n * p.n_bt);
+  const bool reverse = d == 1;
+  const CUtensorMap* map_w = d ? &map_w1 : &map_w0;
+  long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(smem_u32(w_bar), 1);
+    mbar_init(smem_u32(acc_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t wb = smem_u32(w_bar);
+      mbar_expect_tx(wb, 2 * WCH);
+      for (int c = 0; c < 2; ++c)
+        for (int r0 = 0; r0 < H; r0 += p.wbox_rows)
+          tma_load_2d(smem_u32(smem_w + (size_t)c * WCH + (size_t)r0 * 128), map_w, wb, j * 64 + c * 32, r0);
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(w_bar), 0);
+  }
+  const uint64_t desc_a0 = make_smem_desc(smem_u32(smem_a));
+  const uint64_t desc_w0 = make_smem_desc(smem_u32(smem_w));
+
+  const int quad = warp & 3;
+  const int sg = warp >> 2;                        // unit sub-group (8 units)
+  const int r = quad * 32 + lane;
+  const int b = bt * kBM + r;
+  const bool row_ok = b < B;
+  const int u0 = j * kU + sg * kBUT;
+  const int z0 = j * 4 * kU + sg * 4 * kBUT;
+  const int len2 = row_ok ? (p.lens2 ? p.lens2[b] : steps) : 0;
+  float* gates = d ? p.gates[1] : p.gates[0];
+  const float* cs = d ? p.cs[1] : p.cs[0];
+  const int col0 = d * H;
+  const bool t0thread = threadIdx.x == 0;
+  const size_t chain_sz = (size_t)n * kBM * H;
+  float* pws_chain = p.pws + (size_t)(d * p.n_bt + bt) * chain_sz;
+  const size_t par_stride = (size_t)2 * p.n_bt * chain_sz;
+  const uint32_t a_row = smem_u32(smem_a) + (uint32_t)sg * A_STAGE_BYTES + (uint32_t)r * 128;
+  const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
+  float carry[kBUT];
+#pragma unroll
+  for (int i = 0; i < kBUT; ++i) carry[i] = 0.f;
+
+  for (int q = 0; q < steps; ++q) {
+    const int sf = steps - 1 - q;
+    const int t = reverse ? steps - 1 - sf : sf;
+    const int tp = reverse ? t + 1 : t - 1;
+    const bool valid = row_ok && t < len2;
+    float* zrow = gates + ((i64)t * B + b) * 4 * H + z0;
+    float gz[4 * kBUT], cv[kBUT], cpv[kBUT], dhv[kBUT];
+#pragma unroll
+    for (int e = 0; e < kBUT; ++e) { cv[e] = 0.f; cpv[e] = 0.f; dhv[e] = 0.f; }
+    if (valid) {
+      ldv8<4 * kBUT>(gz, zrow);
+      ldv8<kBUT>(cv, cs + ((i64)t * B + b) * H + u0);
+      if (sf > 0) ldv8<kBUT>(cpv, cs + ((i64)tp * B + b) * H + u0);
+      if (p.dhs) ldv8<kBUT>(dhv, p.dhs + ((i64)t * B + b) * 2 * H + col0 + u0);
+    }
+    float acc[kBUT];
+#pragma unroll
+    for (int i = 0; i < kBUT; ++i) acc[i] = 0.f;
+    if (q > 0) {
+      if (t0thread && dbg) dbg[q * 8 + 0] = clock64();
+      if (row_ok) {
+        // partial dh of step q-1 from every writer, summed in the order j+1, j+2, ..., j (mod n); two halves of <= 13
+        // writers, all pieces of a half in flight together, re-polled until their tags say "written at step q-1".
+        // Rows past their length poll too (and discard): seeing step q-1 of EVERY writer is what keeps this CTA from
+        // running two steps ahead and overwriting a slot another owner has not read yet.
+        const int pq = (q - 1) & 1;
+        const uint32_t tw = ((pq ? pp.epoch1 : pp.epoch0) + (uint32_t)((q - 1) >> 1)) & 1u;
+        const float* src = pws_chain + (size_t)pq * par_stride + ((size_t)(u0 / 4) * kBM + r) * 4;
+        constexpr int KB = 13;
+        const long long t0 = clock64();
+        for (int k0 = 1; k0 <= n; k0 += KB) {
+          uint4 v[KB][2];
+          uint32_t pending = 0;
+#pragma unroll
+          for (int kk = 0; kk < KB; ++kk)
+            if (k0 + kk <= n) pending |= 3u << (2 * kk);
+          while (pending) {
+#pragma unroll
+            for (int kk = 0; kk < KB; ++kk) {
+              int i = j + k0 + kk;
+              i -= (i >= n) ? n : 0;
+              i -= (i >= n) ? n : 0;
+#pragma unroll
+              for (int h4 = 0; h4 < 2; ++h4)
+                if (pending & (1u << (2 * kk + h4)))
+                  v[kk][h4] = ld_relaxed_v4f(src + (size_t)i * kBM * H + (size_t)h4 * kBM * 4);
+            }
+#pragma unroll
+            for (int kk = 0; kk < KB; ++kk)
+#pragma unroll
+              for (int h4 = 0; h4 < 2; ++h4)
+                if ((pending & (1u << (2 * kk + h4))) && tags_ok(v[kk][h4], tw)) pending &= ~(1u << (2 * kk + h4));
+            if (pending && clock64() - t0 > 4000000000LL) __trap();
+          }
+#pragma unroll
+          for (int kk = 0; kk < KB; ++kk)
+            if (k0 + kk <= n) {
+#pragma unroll
+              for (int h4 = 0; h4 < 2; ++h4) {
+                acc[4 * h4] += __uint_as_float(v[kk][h4].x & ~1u); acc[4 * h4 + 1] += __uint_as_float(v[kk][h4].y & ~1u);
+                acc[4 * h4 + 2] += __uint_as_float(v[kk][h4].z & ~1u); acc[4 * h4 + 3] += __uint_as_float(v[kk][h4].w & ~1u);
+              }
+            }
+        }
+      }
+      if (t0thread && dbg) dbg[q * 8 + 1] = clock64();
+    }
+    if (valid) {
+      bool inject = false;
+      if (p.dc_inject) {
+        const int ti = (d == 0 && p.inject_t) ? p.inject_t[b] : 0;
+        inject = ti == t;
+      }
+#pragma unroll
+      for (int e = 0; e < kBUT; ++e) {
+        const float gi = gz[e], gj = gz[kBUT + e], gf = gz[2 * kBUT + e], go = gz[3 * kBUT + e];
+        const float dh = dhv[e] + acc[e];
+        float dc = carry[e];
+        if (inject) dc += p.dc_inject[(i64)b * p.ldi + col0 + u0 + e];
+        const float tc_ = tanh_fast(cv[e]);
+        gz[3 * kBUT + e] = dh * tc_ * go * (1.f - go);
+        dc += dh * go * (1.f - tc_ * tc_);
+        gz[e] = dc * gj * gi * (1.f - gi);
+        gz[kBUT + e] = dc * gi * (1.f - gj * gj);
+        gz[2 * kBUT + e] = dc * cpv[e] * gf * (1.f - gf);
+        carry[e] = dc * gf;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4 * kBUT; ++i) gz[i] = 0.f;
+#pragma unroll
+      for (int e = 0; e < kBUT; ++e) carry[e] = 0.f;
+    }
+    if (q + 1 < steps) {
+      // dz -> swizzled A tile (rows past B are zero), visible to the tensor core, then warp 0 issues the MMAs
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t addr = a_row + (uint32_t)((c ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(gz[4 * c]), "f"(gz[4 * c + 1]),
+                     "f"(gz[4 * c + 2]), "f"(gz[4 * c + 3]) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      fence_before_sync();                 // this thread's tcgen05.ld of the previous step precede the next MMAs
+      named_bar_sync(2, kBComputeThreads);
+      if (warp == 0) {
+        fence_after_sync();
+        if (t0thread && dbg) dbg[q * 8 + 2] = clock64();
+        if (elect_one()) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = desc_a0 + (uint64_t)((c * A_STAGE_BYTES + k * UMMA_K * 4) >> 4);
+              for (int pt = 0; pt < p.n_parts; ++pt) {
+                const int nn = min(p.part, H - pt * p.part);
+                const uint64_t dw = desc_w0 + (uint64_t)((c * WCH + (uint32_t)(pt * p.part) * 128 + k * UMMA_K * 4) >> 4);
+                umma_tf32(tmem_base + (uint32_t)(pt * p.part), da, dw, make_idesc_tf32(kBM, nn, 0), (c > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+          umma_commit(smem_u32(acc_full));
+        }
+        __syncwarp();
+      }
+    }
+    // dz to HBM for the weight-gradient GEMMs (off the inter-CTA critical path: overlaps the MMA)
+    if (row_ok) stv8<4 * kBUT>(zrow, gz);
+    if (q + 1 < steps) {
+      mbar_wait(smem_u32(acc_full), q & 1);
+      fence_after_sync();
+      if (t0thread && dbg) dbg[q * 8 + 3] = clock64();
+      // drain the accumulator owner by owner: owner o = j - k sums this writer at position k, so k = 1 goes out first;
+      // this thread takes every second owner (k = 1 + sg, 3 + sg, ...); each owner = 16 columns = 4 unit quads
+      const int pq = q & 1;
+      const uint32_t tw = ((pq ? pp.epoch1 : pp.epoch0) + (uint32_t)(q >> 1)) & 1u;
+      float* dstw = pws_chain + (size_t)pq * par_stride + (size_t)j * kBM * H + (size_t)r * 4;
+      float va[16], vb[16];
+      int k = 1 + sg;
+      int o = j - k; o += (o < 0) ? n : 0;
+      if (k <= n) tmem_ld16_nowait(tlane + (uint32_t)(16 * o), va);
+      while (k <= n) {
+        tmem_ld_wait();
+        const int k2 = k + 2;
+        int o2 = j - k2; o2 += (o2 < 0) ? n : 0; o2 += (o2 < 0) ? n : 0;
+        if (k2 <= n) tmem_ld16_nowait(tlane + (uint32_t)(16 * o2), vb);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 w;
+          w.x = (__float_as_uint(va[4 * g]) & ~1u) | tw; w.y = (__float_as_uint(va[4 * g + 1]) & ~1u) | tw;
+          w.z = (__float_as_uint(va[4 * g + 2]) & ~1u) | tw; w.w = (__float_as_uint(va[4 * g + 3]) & ~1u) | tw;
+          st_relaxed_v4(dstw + (size_t)(4 * o + g) * kBM * 4, w);
+        }
+        if (k2 > n) break;
+        tmem_ld_wait();
+        const int k3 = k2 + 2;
+        int o3 = j - k3; o3 += (o3 < 0) ? n : 0; o3 += (o3 < 0) ? n : 0;
+        if (k3 <= n) tmem_ld16_nowait(tlane + (uint32_t)(16 * o3), va);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 w;
+          w.x = (__float_as_uint(vb[4 * g]) & ~1u) | tw; w.y = (__float_as_uint(vb[4 * g + 1]) & ~1u) | tw;
+          w.z = (__float_as_uint(vb[4 * g + 2]) & ~1u) | tw; w.w = (__float_as_uint(vb[4 * g + 3]) & ~1u) | tw;
+          st_relaxed_v4(dstw + (size_t)(4 * o2 + g) * kBM * 4, w);
+        }
+        k = k3; o = o3;
+      }
+      if (t0thread && dbg) dbg[q * 8 + 4] = clock64();
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// BPTT of one BiLSTM layer (second generation).  Arguments as rec::rec_backward_rs; `tags` is the persistent tag state of `pws`.
+inline void rec_backward_rs2(cudaStream_t st, float* const gates[2], const float* const cs[2], const float* dhs,
+                             const float* const K[2], int In, const int* lens2, const float* dc_inject, int ldi,
+                             const int* inject_t, float* pws, size_t pws_floats, BpttTags& tags, int steps, int B, int H) {
+  using namespace rec;
+  Bptt2P pp{};
+  RecBptt& p = pp.r;
+  for (int d = 0; d < 2; ++d) { p.gates[d] = gates[d]; p.cs[d] = cs[d]; }
+  p.dhs = dhs; p.lens2 = lens2; p.dc_inject = dc_inject; p.ldi = ldi; p.inject_t = inject_t; p.counters = nullptr;
+  p.pws = pws; p.steps = steps; p.B = B; p.H = H;
+  p.n_bt = (B + kBM - 1) / kBM; p.n_slices = H / kU;
+  p.n_parts = (H + 255) / 256;
+  p.part = (((H + p.n_parts - 1) / p.n_parts) + 15) / 16 * 16;
+  CUtensorMap mw[2];
+  for (int d = 0; d < 2; ++d) {
+    const i64 wdims[2] = {4 * (i64)H, H}, wstr[2] = {1, 4 * (i64)H};
+    p.wbox_rows = H <= 256 ? H : H / 2;
+    const int wbox[2] = {BK, p.wbox_rows};
+    mw[d] = make_map_nd(K[d] + (i64)In * 4 * H, 2, wdims, wstr, wbox);
+  }
+  if (tags.n_bt != p.n_bt || tags.H != H) {
+    // new geometry: the slots hold tags of another layout -- start from all-zero tags, next expected tag = 1
+    E2T_CHECK(cudaMemsetAsync(pws, 0, pws_floats * sizeof(float), st));
+    tags.epoch[0] = tags.epoch[1] = 1;
+    tags.n_bt = p.n_bt; tags.H = H;
+  }
+  pp.epoch0 = tags.epoch[0]; pp.epoch1 = tags.epoch[1];
+  // steps - 1 partials are written (q = 0 .. steps-2): parity 0 gets ceil, parity 1 floor of (steps - 1) / 2
+  tags.epoch[0] += (uint32_t)(steps / 2);
+  tags.epoch[1] += (uint32_t)((steps - 1) / 2);
+  auto kfn = k_lstm_bptt2;
+  const size_t smem = bptt_smem_bytes(H);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    E2T_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  static int dbg_left = getenv("E2T_REC_DEBUG") ? atoi(getenv("E2T_REC_DEBUG")) : 0;
+  p.dbg = nullptr;
+  if (dbg_left > 0) {
+    E2T_CHECK(cudaMalloc(&p.dbg, (size_t)steps * 8 * sizeof(long long)));
+    E2T_CHECK(cudaMemsetAsync(p.dbg, 0, (size_t)steps * 8 * sizeof(long long), st));
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * p.n_bt * p.n_slices)); cfg.blockDim = dim3(kBpttThreads);
+  cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeCooperative; attrs[0].val.cooperative = 1;   // all CTAs co-resident
+  cfg.attrs = attrs; cfg.numAttrs = 1;
+  E2T_CHECK(cudaLaunchKernelEx(&cfg, kfn, mw[0], mw[1], pp));
+  if (p.dbg) {
+    --dbg_left;
+    std::vector<long long> hst((size_t)steps * 8);
+    E2T_CHECK(cudaStreamSynchronize(st));
+    E2T_CHECK(cudaMemcpy(hst.data(), p.dbg, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.dbg);
+    fprintf(stderr, "[rec bptt2] steps=%d B=%d H=%d grid=%u (cycles of CTA 0 thread 0, rel. to the start of the step's poll)\n"
+                    "  step  ->partials_summed  ->dz_in_smem  ->acc_seen  ->partial_stored | step_total\n",
+            steps, B, H, cfg.gridDim.x);
+    for (int q = 1; q + 1 < steps; ++q) {
+      const long long* e = &hst[(size_t)q * 8];
+      const long long prev = q > 1 ? hst[(size_t)(q - 1) * 8] : 0;
+      fprintf(stderr, "  %4d  %8lld %8lld %8lld %8lld | %8lld\n", q, e[1] - e[0], e[2] - e[0], e[3] - e[0], e[4] - e[0],
+              prev ? e[0] - prev : 0);
     }
   }
 }
