@@ -1211,7 +1211,9 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
       const float* csd[2] = {Ly.cs[0], Ly.cs[1]};
       prof_begin(h, "rec_backward", B, Ly.H, T2);
       static const bool use_allgather = getenv("E2T_REC_BWD_ALLGATHER") != nullptr;
-      static const bool bptt_v1 = getenv("E2T_REC_V1") != nullptr || getenv("E2T_BPTT_V1") != nullptr;
+      // second-generation BPTT (tag-in-data hand-off): opt-in -- polling 205 KB of partials per step through the LSU was
+      // measured slower (13.4 vs 11.2 us per step, profiles/r2d_*) than the counter hand-off of the first generation
+      static const bool bptt_v1 = getenv("E2T_BPTT_V2") == nullptr;
       if (!use_allgather && !bptt_v1 && h->rec_pws && rec::bptt_supported(h->Bm, Ly.H))
         rec16::rec_backward_rs2(h->stream, Ly.gates, csd, Ly.dhs, Kd, Ly.In, h->d_lens2, top ? h->dc0 : nullptr, c.Hd,
                                 top ? h->d_tlast : nullptr, h->rec_pws, (size_t)h->rec_pws_n, h->bptt_tags, T2, B, Ly.H);

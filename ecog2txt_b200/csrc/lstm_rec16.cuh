@@ -35,7 +35,7 @@ using rec::kBM;
 using rec::kUT;
 
 constexpr int kWorkThreads = 256;
-constexpr int kThreads16 = kWorkThreads;
+constexpr int kThreads16 = kWorkThreads + 32;
 constexpr int kKC = 64;                         // fp16 elements per 128-byte swizzle row = one k-chunk
 constexpr uint32_t kAChunk = kBM * 128;         // 16 KB: 128 rows x 128 B
 constexpr uint32_t kWChunk = 4 * kU * 128;      // 8 KB: 64 gate rows x 128 B
@@ -56,11 +56,21 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 }
 __device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
   uint4 v;
+  // E2T_STRONG_POLL: ld.relaxed.gpu (LDG.STRONG.GPU) -- measured far slower than L1-bypassing weak loads (ld.cg), which
+  // read the same L2 copy; asm volatile keeps the compiler from caching the value across poll rounds
+#ifdef E2T_STRONG_POLL
   asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+#else
+  asm volatile("ld.global.cg.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+#endif
   return v;
 }
 __device__ __forceinline__ void st_relaxed_v4(void* p, uint4 v) {
+#ifdef E2T_STRONG_POLL
   asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#else
+  asm volatile("st.global.cg.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#endif
 }
 __device__ __forceinline__ bool has_fill(const uint4& v) {
   return v.x == kFill32 || v.y == kFill32 || v.z == kFill32 || v.w == kFill32;
@@ -72,24 +82,51 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 
 struct Fwd16P {
   float* gates[2];        // [T', B, 4H] x-projection (+bias) in, gate activations out (permuted gate order)
-  float* cs[2];           // [T', B, H]
-  float* hs;              // [T', B, 2H]   fwd half | bwd half (fp32: what the next layer / the backward pass read)
-  float* hd;              // dropped copy of hs (nullable)
   __half* hx;             // [2][T'][Bp][Hp] fp16 exchange buffer, pre-filled with 0xFFFF
   const int* lens2;       // [B] (nullable: all steps valid)
   int steps, B, Bp, H, Hp, n_bt, n_slices;
+  int has_hd;
   DropP dp; int drop_F;
   long long* dbg;         // E2T_REC_DEBUG: per-step clock64 stamps of CTA 0 ([steps][8]), else NULL
 };
+// tensor maps of one launch (one kernel parameter: TMA descriptors must live in param / const space)
+struct Fwd16Maps {
+  CUtensorMap w[2];       // Wh^T fp16 [4H, Hp], box 64 x 64, 128B swizzle (load, once)
+  CUtensorMap hx;         // exchange buffer as [2 T' Bp, Hp] fp16, box 64 x 128, 128B swizzle (load, every step)
+  CUtensorMap gates[2];   // [T', B, 4H] fp32, box 32 x 128 x 1, 128B swizzle (store)
+  CUtensorMap cs[2];      // [T', B, H] fp32, box 16 x 128 x 1 (store)
+  CUtensorMap hs, hd;     // [T', B, 2H] fp32, box 16 x 128 x 1 (store)
+};
 
+constexpr uint32_t kStageGates = 2 * kBM * 128;   // two swizzled [128 x 32 fp32] sub-tiles (unit group 0 / 1)
+constexpr uint32_t kStageSmall = kBM * 64;        // dense [128 x 16 fp32]
+constexpr uint32_t kStageBytes = kStageGates + 3 * kStageSmall;
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_cg_u32(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Per step and CTA: 102 KB of h in (TMA), 56 KB of results out (TMA bulk stores from a staging tile), 4 KB of fp16 h and
+// 32 KB of x-projection through the LSU.  (First cut of this kernel pulled h with 16-byte LSU loads: 15-25 B/clk per SM,
+// 6500 cycles per step -- profiles/r2d_rec_timeline.txt; TMA ingests the same tile at ~92 B/clk.)
 template <int NKC>
 __global__ void __launch_bounds__(kThreads16, 1)
-k_lstm_fwd16(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1, Fwd16P p) {
+k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* smem_w = smem;                                   // [NKC][64 rows][128 B]
   unsigned char* smem_a = smem + (size_t)NKC * kWChunk;           // [NKC][128 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)NKC * kAChunk);
+  unsigned char* smem_o = smem_a + (size_t)NKC * kAChunk;         // staging: gates | cs | hs | hd
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + kStageBytes);
   uint64_t* w_bar = bars;
   uint64_t* acc_full = bars + 1;
   uint64_t* a_full = bars + 2;                                    // [NKC]
@@ -106,39 +143,87 @@ k_lstm_fwd16(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(w_bar), 1);
     mbar_init(smem_u32(acc_full), 1);
-    for (int k = 0; k < NKC; ++k) mbar_init(smem_u32(&a_full[k]), kWorkThreads / 32);
+    for (int k = 0; k < NKC; ++k) mbar_init(smem_u32(&a_full[k]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 64);
-  // the operand tile starts as zeros: rows past B are never loaded, and the accumulator rows they feed stay finite
-  for (uint32_t i = threadIdx.x; i < (uint32_t)NKC * kAChunk / 16; i += kWorkThreads)
-    reinterpret_cast<uint4*>(smem_a)[i] = make_uint4(0, 0, 0, 0);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 64);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
-  const __half* hx_dir = p.hx + (size_t)d * steps * p.Bp * p.Hp;
+  __half* hx_dir = p.hx + (size_t)d * steps * p.Bp * p.Hp;
+  const int hx_row0 = d * steps * p.Bp + bt * kBM;                // + t * Bp: first row of this CTA's tile in map hx
 
-  constexpr uint32_t idesc = make_idesc_f16(kBM, 4 * kU);
-  const uint64_t desc_a0 = make_smem_desc(smem_u32(smem_a));
-  const uint64_t desc_w0 = make_smem_desc(smem_u32(smem_w));
-  if (warp == 0) {
-    // weights, once: 64 permuted gate rows of Wh^T (fp16) x 64 k columns per chunk; the K tail is zero-filled
-    const CUtensorMap* map_w = d ? &map_w1 : &map_w0;
+  if (warp == 8) {
+    // ================= issue warp: weight TMA (once); per step: h tile TMA, fill-pattern check, MMAs =================
     if (elect_one()) {
       const uint32_t wb = smem_u32(w_bar);
       mbar_expect_tx(wb, (uint32_t)NKC * kWChunk);
-      for (int kc = 0; kc < NKC; ++kc)
-        tma_load_2d(smem_u32(smem_w + (size_t)kc * kWChunk), map_w, wb, kc * kKC, j * 4 * kU);
+      for (int kc = 0; kc < NKC; ++kc)     // 64 permuted gate rows of Wh^T (fp16), 64 k columns; the K tail is zero-filled
+        tma_load_2d(smem_u32(smem_w + (size_t)kc * kWChunk), &maps.w[d], wb, kc * kKC, j * 4 * kU);
     }
     __syncwarp();
     mbar_wait(smem_u32(w_bar), 0);
     fence_after_sync();
-  }
-  {
-    // ================= loader + epilogue: thread = (batch row, 8 hidden units) =================
+    constexpr uint32_t idesc = make_idesc_f16(kBM, 4 * kU);
+    const uint64_t desc_a0 = make_smem_desc(smem_u32(smem_a));
+    const uint64_t desc_w0 = make_smem_desc(smem_u32(smem_w));
+    uint32_t phases = 0;                             // bit kc = parity the next completion of a_full[kc] will have
+    for (int s = 1; s < steps; ++s) {
+      const int t = reverse ? steps - 1 - s : s;
+      const int t_src = reverse ? t + 1 : t - 1;
+      // the epilogue threads have seen one piece of every producer warp's store of step s-1 (probe): the tile is (almost
+      // surely) complete in L2.  Pull it; what the check below still finds unwritten is pulled again.
+      rec::named_bar_sync(1, kThreads16);
+      if (dbg && lane == 0) dbg[s * 8 + 1] = clock64();
+      if (elect_one()) {
+        for (int kc = 0; kc < NKC; ++kc) {
+          const uint32_t fb = smem_u32(&a_full[kc]);
+          mbar_expect_tx(fb, kAChunk);
+          tma_load_2d(smem_u32(smem_a + (size_t)kc * kAChunk), &maps.hx, fb, kc * kKC, hx_row0 + t_src * p.Bp);
+        }
+      }
+      __syncwarp();
+      const long long t0 = clock64();
+#pragma unroll
+      for (int kc = 0; kc < NKC; ++kc) {
+        for (;;) {
+          mbar_wait(smem_u32(&a_full[kc]), (phases >> kc) & 1u);
+          phases ^= 1u << kc;
+          // lane l checks the first word of all 8 pieces of rows l, l+32, l+64, l+96 (a 16-byte piece is one store)
+          bool bad = false;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int row = lane + 32 * m;
+            const unsigned char* rp = smem_a + (size_t)kc * kAChunk + (size_t)row * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) bad |= *reinterpret_cast<const volatile uint32_t*>(rp + ((c ^ (row & 7)) << 4)) == kFill32;
+          }
+          if (!__any_sync(0xffffffffu, bad)) break;
+          if (clock64() - t0 > 4000000000LL) __trap();        // a lost producer must trap, not hang the GPU
+          if (dbg && lane == 0) dbg[s * 8 + 7] += 1;           // re-pulled chunks
+          if (elect_one()) {
+            const uint32_t fb = smem_u32(&a_full[kc]);
+            mbar_expect_tx(fb, kAChunk);
+            tma_load_2d(smem_u32(smem_a + (size_t)kc * kAChunk), &maps.hx, fb, kc * kKC, hx_row0 + t_src * p.Bp);
+          }
+          __syncwarp();
+        }
+        fence_after_sync();
+        if (elect_one()) {
+          const int nk = min(4, (H - kc * kKC) / 16);       // K = 16 per instruction; H % 16 == 0
+          for (int k = 0; k < nk; ++k)
+            umma_f16(tmem_base, desc_a0 + (uint64_t)((kc * kAChunk + k * 32) >> 4), desc_w0 + (uint64_t)((kc * kWChunk + k * 32) >> 4),
+                     idesc, (kc > 0 || k > 0) ? 1u : 0u);
+          if (kc == NKC - 1) umma_commit(smem_u32(acc_full));
+        }
+        __syncwarp();
+      }
+      if (dbg && lane == 0) dbg[s * 8 + 2] = clock64();
+    }
+  } else {
+    // ================= epilogue: thread = (batch row, 8 hidden units) =================
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may read
     const int ug = warp >> 2;                        // unit group (8 units)
     const int r = quad * 32 + lane;
@@ -148,93 +233,41 @@ k_lstm_fwd16(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__
     const int z0 = j * 4 * kU + ug * 4 * kUT;        // 32 contiguous gate columns [gate][8] in the permuted layout
     const int len2 = row_ok ? (p.lens2 ? p.lens2[b] : steps) : 0;
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ug * 4 * kUT);
-    float* gates = d ? p.gates[1] : p.gates[0];
-    float* cs = d ? p.cs[1] : p.cs[0];
+    const float* gates = d ? p.gates[1] : p.gates[0];
     const int col0 = d * H;
     float carry[kUT];
 #pragma unroll
     for (int i = 0; i < kUT; ++i) carry[i] = 0.f;
-    // loader geometry: k-chunk kc holds 128 rows x 8 pieces of 16 B; piece m * 256 + tid -> row (>> 3), column (& 7)
-    const int lrow0 = threadIdx.x >> 3, lc = threadIdx.x & 7;       // rows lrow0 + 32 m, m = 0..3
-    const uint32_t a_base = smem_u32(smem_a);
+    // probe: thread i watches the store of producer slice i / 8, warp i % 8 (its lane 0: row 32 (w & 3), unit group w >> 2)
+    const bool prober = (int)threadIdx.x < p.n_slices * 8;
+    const size_t probe_off = (size_t)(bt * kBM + 32 * ((int)threadIdx.x & 3)) * p.Hp + (size_t)((int)threadIdx.x >> 3) * kU +
+                             (size_t)(((int)threadIdx.x >> 2) & 1) * kUT;
+    const uint32_t st_g = smem_u32(smem_o) + (uint32_t)ug * (kBM * 128) + (uint32_t)r * 128;
+    const uint32_t st_s = smem_u32(smem_o) + kStageGates + (uint32_t)r * 64 + (uint32_t)ug * 32;
 
     for (int s = 0; s < steps; ++s) {
       const int t = reverse ? steps - 1 - s : s;
       const bool valid = row_ok && t < len2;
-      float* zrow = gates + ((i64)t * B + b) * 4 * H + z0;
       float z[4 * kUT];
       float acc[4 * kUT];
-      if (valid) rec::ldv8<4 * kUT>(z, zrow);                        // in flight while h arrives
+#pragma unroll
+      for (int i = 0; i < 4 * kUT; ++i) z[i] = 0.f;
+      if (valid) rec::ldv8<4 * kUT>(z, gates + ((i64)t * B + b) * 4 * H + z0);       // in flight while h arrives
       if (s > 0) {
         const int t_src = reverse ? t + 1 : t - 1;
-        const __half* src = hx_dir + (size_t)t_src * p.Bp * p.Hp + (size_t)(bt * kBM) * p.Hp;
         if (dbg && threadIdx.x == 0) dbg[s * 8 + 0] = clock64();
-        // Pull this thread's pieces of h_{t-1}: every round re-issues ALL loads that still showed the fill pattern (they
-        // are in flight together: one L2 round trip per round, not one per piece), until none is left.
-        uint4 v[NKC][4];
-        uint32_t pending = 0;
-#pragma unroll
-        for (int kc = 0; kc < NKC; ++kc)
-#pragma unroll
-          for (int m = 0; m < 4; ++m)
-            if (kc * kKC + lc * 8 < H && bt * kBM + lrow0 + 32 * m < B) pending |= 1u << (kc * 4 + m);
-        const long long t0 = clock64();
-        while (pending) {
-#pragma unroll
-          for (int kc = 0; kc < NKC; ++kc)
-#pragma unroll
-            for (int m = 0; m < 4; ++m)
-              if (pending & (1u << (kc * 4 + m)))
-                v[kc][m] = ld_relaxed_v4(src + (size_t)(lrow0 + 32 * m) * p.Hp + kc * kKC + lc * 8);
-#pragma unroll
-          for (int kc = 0; kc < NKC; ++kc)
-#pragma unroll
-            for (int m = 0; m < 4; ++m)
-              if ((pending & (1u << (kc * 4 + m))) && !has_fill(v[kc][m])) pending &= ~(1u << (kc * 4 + m));
-          if (pending && clock64() - t0 > 4000000000LL) __trap();      // a lost producer must trap, not hang the GPU
-          if (dbg && threadIdx.x == 0) dbg[s * 8 + 7] += 1;             // poll rounds
+        if (prober) {
+          const __half* pp = hx_dir + (size_t)t_src * p.Bp * p.Hp + probe_off;
+          const long long t0 = clock64();
+          while (ld_cg_u32(pp) == kFill32)
+            if (clock64() - t0 > 4000000000LL) __trap();
         }
-        if (dbg && threadIdx.x == 0) dbg[s * 8 + 4] = clock64();
-#pragma unroll
-        for (int kc = 0; kc < NKC; ++kc) {
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const int row = lrow0 + 32 * m, col = kc * kKC + lc * 8;
-            if (col < H && bt * kBM + row < B) {
-              const uint32_t dst = a_base + (uint32_t)kc * kAChunk + (uint32_t)row * 128 + (uint32_t)((lc ^ (row & 7)) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[kc][m].x), "r"(v[kc][m].y),
-                           "r"(v[kc][m].z), "r"(v[kc][m].w) : "memory");
-            }
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          if (kc == 0) fence_before_sync();        // this thread's tcgen05.ld of the previous step precede the next MMAs
-          __syncwarp();
-          if (lane == 0) rec::mbar_arrive(smem_u32(&a_full[kc]));
-        }
-        if (dbg && threadIdx.x == 0) dbg[s * 8 + 5] = clock64();
-        if (warp == 0) {
-          // MMA issue (warp-convergent, one elected lane): chunk by chunk as the other warps' pieces land
-          const uint32_t ph = (uint32_t)(s - 1) & 1u;
-#pragma unroll
-          for (int kc = 0; kc < NKC; ++kc) {
-            mbar_wait(smem_u32(&a_full[kc]), ph);
-            fence_after_sync();
-            if (kc == NKC - 1 && dbg && threadIdx.x == 0) dbg[s * 8 + 6] = clock64();     // every warp's pieces are in
-            if (elect_one()) {
-              const int nk = min(4, (H - kc * kKC) / 16);       // K = 16 per instruction; H % 16 == 0
-              for (int k = 0; k < nk; ++k)
-                umma_f16(tmem_base, desc_a0 + (uint64_t)((kc * kAChunk + k * 32) >> 4),
-                         desc_w0 + (uint64_t)((kc * kWChunk + k * 32) >> 4), idesc, (kc > 0 || k > 0) ? 1u : 0u);
-              if (kc == NKC - 1) umma_commit(smem_u32(acc_full));
-            }
-            __syncwarp();
-          }
-        }
-        if (dbg && threadIdx.x == 0) dbg[s * 8 + 1] = clock64();
+        named_bar_arrive(1, kThreads16);              // -> issue warp: pull the tile
         mbar_wait(smem_u32(acc_full), (uint32_t)(s - 1) & 1u);
         fence_after_sync();
-        if (dbg && threadIdx.x == 0) dbg[s * 8 + 2] = clock64();
+        if (dbg && threadIdx.x == 0) dbg[s * 8 + 3] = clock64();
         rec::tmem_ld_cols<4 * kUT>(taddr, acc);
+        fence_before_sync();                           // the next step's MMAs are ordered behind these reads by barrier 1
       } else {
 #pragma unroll
         for (int i = 0; i < 4 * kUT; ++i) acc[i] = 0.f;
@@ -256,33 +289,56 @@ k_lstm_fwd16(const __grid_constant__ CUtensorMap map_w0, const __grid_constant__
 #pragma unroll
         for (int e = 0; e < kUT; ++e) { carry[e] = 0.f; hv[e] = 0.f; }
       }
-      // 1) what the other CTAs of the chain wait for: this thread's 8 units of h as ONE 16-byte store (zeros past the length)
-      if (row_ok) {
+      // 1) what the other CTAs of the chain wait for: this thread's 8 units of h as ONE 16-byte store (zeros past the
+      //    length, and for the padding rows of the last batch tile: every row of the tile must leave the fill pattern)
+      {
         uint4 hp;
         hp.x = pack_h2(hv[0], hv[1]); hp.y = pack_h2(hv[2], hv[3]); hp.z = pack_h2(hv[4], hv[5]); hp.w = pack_h2(hv[6], hv[7]);
-        st_relaxed_v4(const_cast<__half*>(hx_dir) + (size_t)t * p.Bp * p.Hp + (size_t)b * p.Hp + u0, hp);
+        st_relaxed_v4(hx_dir + (size_t)t * p.Bp * p.Hp + (size_t)b * p.Hp + u0, hp);
       }
-      if (dbg && threadIdx.x == 0) dbg[s * 8 + 3] = clock64();
-      // 2) everything the next layer / the backward pass read goes out behind it
-      if (row_ok) {
-        rec::stv8<kUT>(p.hs + ((i64)t * B + b) * 2 * H + col0 + u0, hv);
-        if (valid) rec::stv8<4 * kUT>(zrow, z);
-        rec::stv8<kUT>(cs + ((i64)t * B + b) * H + u0, carry);
-        if (p.hd) {
-          const uint32_t idx0 = (uint32_t)(((i64)t * B + b) * p.drop_F + col0 + u0);
-          const uint32_t key = p.dp.key, thresh = p.dp.thresh;
-          const float inv = p.dp.inv;
-          float o[kUT];
+      if (dbg && threadIdx.x == 0) dbg[s * 8 + 4] = clock64();
+      // 2) everything the next layer / the backward pass read: staged in shared memory, written by TMA bulk stores
+      //    (rows past B are clipped by the tensor maps).  The previous step's stores must have finished reading first.
+      if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      rec::named_bar_sync(2, kWorkThreads);
 #pragma unroll
-          for (int e = 0; e < kUT; ++e) o[e] = (valid && e2t_keep(key, idx0 + e, thresh)) ? hv[e] * inv : 0.f;
-          rec::stv8<kUT>(p.hd + ((i64)t * B + b) * 2 * H + col0 + u0, o);
-        }
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t addr = st_g + (uint32_t)((c ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(z[4 * c]), "f"(z[4 * c + 1]), "f"(z[4 * c + 2]),
+                     "f"(z[4 * c + 3]) : "memory");
+      }
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s), "f"(carry[0]), "f"(carry[1]), "f"(carry[2]), "f"(carry[3]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + 16), "f"(carry[4]), "f"(carry[5]), "f"(carry[6]), "f"(carry[7]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + kStageSmall), "f"(hv[0]), "f"(hv[1]), "f"(hv[2]), "f"(hv[3]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + kStageSmall + 16), "f"(hv[4]), "f"(hv[5]), "f"(hv[6]), "f"(hv[7]) : "memory");
+      if (p.has_hd) {
+        const uint32_t idx0 = (uint32_t)(((i64)t * B + b) * p.drop_F + col0 + u0);
+        const uint32_t key = p.dp.key, thresh = p.dp.thresh;
+        const float inv = p.dp.inv;
+        float o[kUT];
+#pragma unroll
+        for (int e = 0; e < kUT; ++e) o[e] = (valid && e2t_keep(key, idx0 + e, thresh)) ? hv[e] * inv : 0.f;
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + 2 * kStageSmall), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + 2 * kStageSmall + 16), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      rec::named_bar_sync(3, kWorkThreads);
+      if (threadIdx.x == 0) {
+        const uint32_t so = smem_u32(smem_o);
+        tma_store_3d(&maps.gates[d], so, j * 4 * kU, bt * kBM, t);
+        tma_store_3d(&maps.gates[d], so + kBM * 128, j * 4 * kU + 4 * kUT, bt * kBM, t);
+        tma_store_3d(&maps.cs[d], so + kStageGates, j * kU, bt * kBM, t);
+        tma_store_3d(&maps.hs, so + kStageGates + kStageSmall, col0 + j * kU, bt * kBM, t);
+        if (p.has_hd) tma_store_3d(&maps.hd, so + kStageGates + 2 * kStageSmall, col0 + j * kU, bt * kBM, t);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (dbg) dbg[s * 8 + 5] = clock64();
       }
     }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 8) {
     fence_after_sync();
     tmem_dealloc(tmem_base, 64);
   }
@@ -319,8 +375,24 @@ inline CUtensorMap make_map_f16(const __half* ptr, i64 rows, i64 cols, i64 ld, i
   return m;
 }
 
+inline CUtensorMap make_map_f32_3d(const float* ptr, const i64* dims, const i64* strides_elems, const int* box, bool swizzle128) {
+  CUtensorMap m;
+  cuuint64_t gdim[3]; cuuint64_t gstr[2]; cuuint32_t bx[3]; cuuint32_t estr[3] = {1, 1, 1};
+  for (int i = 0; i < 3; ++i) { gdim[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; }
+  for (int i = 1; i < 3; ++i) gstr[i - 1] = (cuuint64_t)strides_elems[i] * 4;
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) throw std::runtime_error("e2t: cuTensorMapEncodeTiled entry point not found");
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("e2t: cuTensorMapEncodeTiled (3d) failed with code " + std::to_string((int)r));
+  return m;
+}
+
 inline int nkc16(int H) { return (H + kKC - 1) / kKC; }
-inline size_t fwd16_smem_bytes(int H) { return (size_t)nkc16(H) * (kWChunk + kAChunk) + (2 + 8) * 8 + 16 + 1024; }
+inline size_t fwd16_smem_bytes(int H) {
+  return (size_t)nkc16(H) * (kWChunk + kAChunk) + kStageBytes + (2 + 8) * 8 + 16 + 1024;
+}
 inline int hp16(int H) { return (H + 7) / 8 * 8; }
 inline int bp16(int B) { return (B + kBM - 1) / kBM * kBM; }
 inline size_t hx16_halves(int B, int H, int steps) { return (size_t)2 * steps * bp16(B) * hp16(H); }
@@ -329,11 +401,12 @@ inline bool fwd16_supported(int B, int H) {
   if (H % kU != 0 || H < kU || H > 512 || B < 1) return false;
   const int n_bt = (B + kBM - 1) / kBM, n_slices = H / kU;
   if (2 * n_bt * n_slices > rec::sm_count()) return false;
+  if (n_slices * 8 > kWorkThreads) return false;            // one probe thread per (producer slice, warp)
   return fwd16_smem_bytes(H) <= 227 * 1024;
 }
 
 template <int NKC>
-inline void fwd16_launch_t(cudaStream_t st, const CUtensorMap& w0, const CUtensorMap& w1, Fwd16P& p) {
+inline void fwd16_launch_t(cudaStream_t st, const Fwd16Maps& maps, Fwd16P& p) {
   auto kfn = k_lstm_fwd16<NKC>;
   const size_t smem = fwd16_smem_bytes(p.H);
   static size_t attr_smem = 0;
@@ -347,7 +420,7 @@ inline void fwd16_launch_t(cudaStream_t st, const CUtensorMap& w0, const CUtenso
   cudaLaunchAttribute attrs[1];
   attrs[0].id = cudaLaunchAttributeCooperative; attrs[0].val.cooperative = 1;   // all CTAs co-resident
   cfg.attrs = attrs; cfg.numAttrs = 1;
-  E2T_CHECK(cudaLaunchKernelEx(&cfg, kfn, w0, w1, p));
+  E2T_CHECK(cudaLaunchKernelEx(&cfg, kfn, maps, p));
 }
 
 // Forward of one BiLSTM layer.  WhT16[d]: fp16 copies of Wh^T [4H (permuted gate rows), Hp]; hx: exchange buffer of at
@@ -356,13 +429,24 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
                           const __half* const WhT16[2], __half* hx, const int* lens2, int steps, int B, int H, DropP dp,
                           int drop_F) {
   Fwd16P p{};
-  for (int d = 0; d < 2; ++d) { p.gates[d] = gates[d]; p.cs[d] = cs[d]; }
-  p.hs = hs; p.hd = hd; p.hx = hx; p.lens2 = lens2;
+  for (int d = 0; d < 2; ++d) p.gates[d] = gates[d];
+  p.hx = hx; p.lens2 = lens2; p.has_hd = hd != nullptr;
   p.steps = steps; p.B = B; p.Bp = bp16(B); p.H = H; p.Hp = hp16(H);
   p.n_bt = (B + kBM - 1) / kBM; p.n_slices = H / kU;
   p.dp = dp; p.drop_F = drop_F;
-  CUtensorMap mw[2];
-  for (int d = 0; d < 2; ++d) mw[d] = make_map_f16(WhT16[d], 4 * (i64)H, H, p.Hp, 4 * kU, kKC);
+  Fwd16Maps maps;
+  maps.hx = make_map_f16(hx, (i64)2 * steps * p.Bp, H, p.Hp, kBM, kKC);
+  const i64 dg[3] = {4 * (i64)H, B, steps}, sg[3] = {1, 4 * (i64)H, (i64)B * 4 * H};
+  const i64 dc[3] = {H, B, steps}, sc[3] = {1, H, (i64)B * H};
+  const i64 dh[3] = {2 * (i64)H, B, steps}, sh[3] = {1, 2 * (i64)H, (i64)B * 2 * H};
+  const int bg[3] = {4 * kUT, kBM, 1}, bs[3] = {kU, kBM, 1};
+  for (int d = 0; d < 2; ++d) {
+    maps.w[d] = make_map_f16(WhT16[d], 4 * (i64)H, H, p.Hp, 4 * kU, kKC);
+    maps.gates[d] = make_map_f32_3d(gates[d], dg, sg, bg, true);
+    maps.cs[d] = make_map_f32_3d(cs[d], dc, sc, bs, false);
+  }
+  maps.hs = make_map_f32_3d(hs, dh, sh, bs, false);
+  maps.hd = make_map_f32_3d(hd ? hd : hs, dh, sh, bs, false);
   E2T_CHECK(cudaMemsetAsync(hx, 0xFF, hx16_halves(B, H, steps) * sizeof(__half), st));
   static int dbg_left = getenv("E2T_REC_DEBUG") ? atoi(getenv("E2T_REC_DEBUG")) : 0;
   p.dbg = nullptr;
@@ -371,15 +455,14 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
     E2T_CHECK(cudaMemsetAsync(p.dbg, 0, (size_t)steps * 8 * sizeof(long long), st));
   }
   switch (nkc16(H)) {
-    case 1: fwd16_launch_t<1>(st, mw[0], mw[1], p); break;
-    case 2: fwd16_launch_t<2>(st, mw[0], mw[1], p); break;
-    case 3: fwd16_launch_t<3>(st, mw[0], mw[1], p); break;
-    case 4: fwd16_launch_t<4>(st, mw[0], mw[1], p); break;
-    case 5: fwd16_launch_t<5>(st, mw[0], mw[1], p); break;
-    case 6: fwd16_launch_t<6>(st, mw[0], mw[1], p); break;
-    case 7: fwd16_launch_t<7>(st, mw[0], mw[1], p); break;
-    case 8: fwd16_launch_t<8>(st, mw[0], mw[1], p); break;
-    default: throw std::runtime_error("e2t: rec_forward16 needs H <= 512");
+    case 1: fwd16_launch_t<1>(st, maps, p); break;
+    case 2: fwd16_launch_t<2>(st, maps, p); break;
+    case 3: fwd16_launch_t<3>(st, maps, p); break;
+    case 4: fwd16_launch_t<4>(st, maps, p); break;
+    case 5: fwd16_launch_t<5>(st, maps, p); break;
+    case 6: fwd16_launch_t<6>(st, maps, p); break;
+    case 7: fwd16_launch_t<7>(st, maps, p); break;
+    default: throw std::runtime_error("e2t: rec_forward16 needs H <= 448");
   }
   if (p.dbg) {
     --dbg_left;
@@ -387,18 +470,17 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
     E2T_CHECK(cudaStreamSynchronize(st));
     E2T_CHECK(cudaMemcpy(hst.data(), p.dbg, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(p.dbg);
-    fprintf(stderr, "[rec fwd16] steps=%d B=%d H=%d grid=%d (cycles of CTA 0 thread 0, rel. to the start of the step's poll)\n"
-                    "  step  rounds ->polled ->deposited ->all_warps_in ->mma_issued ->acc_seen ->h_stored | step_total\n",
+    fprintf(stderr, "[rec fwd16] steps=%d B=%d H=%d grid=%d (cycles of CTA 0, rel. to the start of the step's probe)\n"
+                    "  step  repulls ->probed(tma_issued) ->mma_issued ->acc_seen ->h_stored ->stores_issued | step_total\n",
             steps, B, H, 2 * p.n_bt * p.n_slices);
     for (int s = 1; s < steps; ++s) {
       const long long* e = &hst[(size_t)s * 8];
       const long long prev = s > 1 ? hst[(size_t)(s - 1) * 8] : 0;
-      fprintf(stderr, "  %4d  %4lld %8lld %8lld %8lld %8lld %8lld %8lld | %8lld\n", s, e[7], e[4] - e[0], e[5] - e[0], e[6] - e[0],
-              e[1] - e[0], e[2] - e[0], e[3] - e[0], prev ? e[0] - prev : 0);
+      fprintf(stderr, "  %4d  %4lld %8lld %8lld %8lld %8lld %8lld | %8lld\n", s, e[7], e[1] - e[0], e[2] - e[0], e[3] - e[0],
+              e[4] - e[0], e[5] - e[0], prev ? e[0] - prev : 0);
     }
   }
 }
-
 
 // ================================================================================================
 // BPTT, second generation (k_lstm_bptt2): the reduce-scatter formulation of k_lstm_bptt (lstm_rec.cuh) -- every CTA multiplies
