@@ -88,7 +88,34 @@ struct Fwd16P {
   int has_hd;
   DropP dp; int drop_F;
   long long* dbg;         // E2T_REC_DEBUG: per-step clock64 stamps of CTA 0 ([steps][8]), else NULL
+  int* trap_rec;          // mapped host memory (nullable): who timed out where, written right before the trap
 };
+// A wait that ran out of patience records (site, block, thread, step, chunk, extra) for the host, then traps.
+__device__ __noinline__ void timeout_trap(int* rec, int site, int s, int kc, int extra) {
+  if (rec && atomicCAS(rec, 0, site) == 0) {
+    rec[1] = (int)blockIdx.x; rec[2] = (int)threadIdx.x; rec[3] = s; rec[4] = kc; rec[5] = extra;
+    __threadfence_system();
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait_rec(uint32_t bar, uint32_t parity, int* rec, int site, int s, int kc) {
+  // bounded by TIME (2^31 cycles ~ 1 s), not by a try count: how long one try_wait parks the thread is up to the hardware,
+  // and 2^14 tries (gemm_tc.cuh: mbar_wait) were measured to run out on healthy launches of this kernel
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(1000000u)
+        : "memory");
+    if (done) return;
+    if (clock64() - t0 > (1LL << 31)) break;
+  }
+  timeout_trap(rec, site, s, kc, (int)parity);
+}
 // tensor maps of one launch (one kernel parameter: TMA descriptors must live in param / const space)
 struct Fwd16Maps {
   CUtensorMap w[2];       // Wh^T fp16 [4H, Hp], box 64 x 64, 128B swizzle (load, once)
@@ -164,7 +191,7 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
         tma_load_2d(smem_u32(smem_w + (size_t)kc * kWChunk), &maps.w[d], wb, kc * kKC, j * 4 * kU);
     }
     __syncwarp();
-    mbar_wait(smem_u32(w_bar), 0);
+    mbar_wait_rec(smem_u32(w_bar), 0, p.trap_rec, 5, 0, 0);
     fence_after_sync();
     constexpr uint32_t idesc = make_idesc_f16(kBM, 4 * kU);
     const uint64_t desc_a0 = make_smem_desc(smem_u32(smem_a));
@@ -175,6 +202,7 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
       const int t_src = reverse ? t + 1 : t - 1;
       // the epilogue threads have seen one piece of every producer warp's store of step s-1 (probe): the tile is (almost
       // surely) complete in L2.  Pull it; what the check below still finds unwritten is pulled again.
+      __syncwarp();
       rec::named_bar_sync(1, kThreads16);
       if (dbg && lane == 0) dbg[s * 8 + 1] = clock64();
       if (elect_one()) {
@@ -189,7 +217,7 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
 #pragma unroll
       for (int kc = 0; kc < NKC; ++kc) {
         for (;;) {
-          mbar_wait(smem_u32(&a_full[kc]), (phases >> kc) & 1u);
+          mbar_wait_rec(smem_u32(&a_full[kc]), (phases >> kc) & 1u, p.trap_rec, 3, s, kc);
           phases ^= 1u << kc;
           // lane l checks the first word of all 8 pieces of rows l, l+32, l+64, l+96 (a 16-byte piece is one store)
           bool bad = false;
@@ -201,7 +229,7 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
             for (int c = 0; c < 8; ++c) bad |= *reinterpret_cast<const volatile uint32_t*>(rp + ((c ^ (row & 7)) << 4)) == kFill32;
           }
           if (!__any_sync(0xffffffffu, bad)) break;
-          if (clock64() - t0 > 4000000000LL) __trap();        // a lost producer must trap, not hang the GPU
+          if (clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 4, s, kc, (int)__ballot_sync(0xffffffffu, bad));   // a lost producer must trap, not hang the GPU
           if (dbg && lane == 0) dbg[s * 8 + 7] += 1;           // re-pulled chunks
           if (elect_one()) {
             const uint32_t fb = smem_u32(&a_full[kc]);
@@ -260,10 +288,11 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
           const __half* pp = hx_dir + (size_t)t_src * p.Bp * p.Hp + probe_off;
           const long long t0 = clock64();
           while (ld_cg_u32(pp) == kFill32)
-            if (clock64() - t0 > 4000000000LL) __trap();
+            if (clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 1, s, 0, 0);
         }
+        __syncwarp();                                 // bar.arrive is warp-aligned: the probe loop must have reconverged
         named_bar_arrive(1, kThreads16);              // -> issue warp: pull the tile
-        mbar_wait(smem_u32(acc_full), (uint32_t)(s - 1) & 1u);
+        mbar_wait_rec(smem_u32(acc_full), (uint32_t)(s - 1) & 1u, p.trap_rec, 2, s, 0);
         fence_after_sync();
         if (dbg && threadIdx.x == 0) dbg[s * 8 + 3] = clock64();
         rec::tmem_ld_cols<4 * kUT>(taddr, acc);
@@ -300,6 +329,7 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
       // 2) everything the next layer / the backward pass read: staged in shared memory, written by TMA bulk stores
       //    (rows past B are clipped by the tensor maps).  The previous step's stores must have finished reading first.
       if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
       rec::named_bar_sync(2, kWorkThreads);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -322,6 +352,7 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + 2 * kStageSmall + 16), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
       rec::named_bar_sync(3, kWorkThreads);
       if (threadIdx.x == 0) {
         const uint32_t so = smem_u32(smem_o);
@@ -333,6 +364,7 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         if (dbg) dbg[s * 8 + 5] = clock64();
       }
+      __syncwarp();
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -454,6 +486,17 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
     E2T_CHECK(cudaMalloc(&p.dbg, (size_t)steps * 8 * sizeof(long long)));
     E2T_CHECK(cudaMemsetAsync(p.dbg, 0, (size_t)steps * 8 * sizeof(long long), st));
   }
+  // E2T_REC_TRAPINFO=1: a wait that times out leaves a record in mapped host memory before it traps (the launch is then
+  // synchronised here so that the record can be printed: diagnostics only)
+  static int* trap_host = nullptr;
+  static int* trap_dev = nullptr;
+  static const bool trapinfo = getenv("E2T_REC_TRAPINFO") != nullptr;
+  if (trapinfo && !trap_host) {
+    E2T_CHECK(cudaHostAlloc(&trap_host, 64, cudaHostAllocMapped));
+    memset(trap_host, 0, 64);
+    E2T_CHECK(cudaHostGetDevicePointer(&trap_dev, trap_host, 0));
+  }
+  p.trap_rec = trapinfo ? trap_dev : nullptr;
   switch (nkc16(H)) {
     case 1: fwd16_launch_t<1>(st, maps, p); break;
     case 2: fwd16_launch_t<2>(st, maps, p); break;
@@ -463,6 +506,14 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
     case 6: fwd16_launch_t<6>(st, maps, p); break;
     case 7: fwd16_launch_t<7>(st, maps, p); break;
     default: throw std::runtime_error("e2t: rec_forward16 needs H <= 448");
+  }
+  if (trapinfo) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess)
+      fprintf(stderr, "[rec fwd16 TRAP] %s: site=%d (1 probe, 2 acc_full, 3 a_full, 4 check, 5 weights) block=%d thread=%d step=%d chunk=%d extra=0x%x "
+                      "(steps=%d B=%d H=%d has_hd=%d)\n", cudaGetErrorString(e), trap_host[0], trap_host[1], trap_host[2], trap_host[3],
+              trap_host[4], (unsigned)trap_host[5], steps, B, H, p.has_hd);
+    E2T_CHECK(e);
   }
   if (p.dbg) {
     --dbg_left;
