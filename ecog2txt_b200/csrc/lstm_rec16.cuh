@@ -157,7 +157,8 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
   uint64_t* w_bar = bars;
   uint64_t* acc_full = bars + 1;
   uint64_t* a_full = bars + 2;                                    // [NKC]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + NKC);
+  uint64_t* probe_bar = bars + 2 + NKC;                           // epilogue warps -> issue warp: "h of the step is out there"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + NKC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x % p.n_slices;
@@ -170,6 +171,7 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(w_bar), 1);
     mbar_init(smem_u32(acc_full), 1);
+    mbar_init(smem_u32(probe_bar), kWorkThreads / 32);
     for (int k = 0; k < NKC; ++k) mbar_init(smem_u32(&a_full[k]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -202,8 +204,8 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
       const int t_src = reverse ? t + 1 : t - 1;
       // the epilogue threads have seen one piece of every producer warp's store of step s-1 (probe): the tile is (almost
       // surely) complete in L2.  Pull it; what the check below still finds unwritten is pulled again.
-      __syncwarp();
-      rec::named_bar_sync(1, kThreads16);
+      mbar_wait_rec(smem_u32(probe_bar), (uint32_t)(s - 1) & 1u, p.trap_rec, 6, s, 0);
+      fence_after_sync();                              // the epilogue's tcgen05.ld of the previous step are behind us
       if (dbg && lane == 0) dbg[s * 8 + 1] = clock64();
       if (elect_one()) {
         for (int kc = 0; kc < NKC; ++kc) {
@@ -273,30 +275,26 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
     const uint32_t st_g = smem_u32(smem_o) + (uint32_t)ug * (kBM * 128) + (uint32_t)r * 128;
     const uint32_t st_s = smem_u32(smem_o) + kStageGates + (uint32_t)r * 64 + (uint32_t)ug * 32;
 
+    float zn[4 * kUT];                                 // x-projection of the NEXT step, prefetched a step ahead
+#pragma unroll
+    for (int i = 0; i < 4 * kUT; ++i) zn[i] = 0.f;
+    {
+      const int t0s = reverse ? steps - 1 : 0;
+      if (row_ok && t0s < len2) rec::ldv8<4 * kUT>(zn, gates + ((i64)t0s * B + b) * 4 * H + z0);
+    }
     for (int s = 0; s < steps; ++s) {
       const int t = reverse ? steps - 1 - s : s;
       const bool valid = row_ok && t < len2;
       float z[4 * kUT];
       float acc[4 * kUT];
 #pragma unroll
-      for (int i = 0; i < 4 * kUT; ++i) z[i] = 0.f;
-      if (valid) rec::ldv8<4 * kUT>(z, gates + ((i64)t * B + b) * 4 * H + z0);       // in flight while h arrives
+      for (int i = 0; i < 4 * kUT; ++i) z[i] = zn[i];
       if (s > 0) {
-        const int t_src = reverse ? t + 1 : t - 1;
-        if (dbg && threadIdx.x == 0) dbg[s * 8 + 0] = clock64();
-        if (prober) {
-          const __half* pp = hx_dir + (size_t)t_src * p.Bp * p.Hp + probe_off;
-          const long long t0 = clock64();
-          while (ld_cg_u32(pp) == kFill32)
-            if (clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 1, s, 0, 0);
-        }
-        __syncwarp();                                 // bar.arrive is warp-aligned: the probe loop must have reconverged
-        named_bar_arrive(1, kThreads16);              // -> issue warp: pull the tile
         mbar_wait_rec(smem_u32(acc_full), (uint32_t)(s - 1) & 1u, p.trap_rec, 2, s, 0);
         fence_after_sync();
         if (dbg && threadIdx.x == 0) dbg[s * 8 + 3] = clock64();
         rec::tmem_ld_cols<4 * kUT>(taddr, acc);
-        fence_before_sync();                           // the next step's MMAs are ordered behind these reads by barrier 1
+        fence_before_sync();                           // the next step's MMAs are ordered behind these reads by probe_bar
       } else {
 #pragma unroll
         for (int i = 0; i < 4 * kUT; ++i) acc[i] = 0.f;
@@ -316,6 +314,8 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
         }
       } else {
 #pragma unroll
+        for (int i = 0; i < 4 * kUT; ++i) z[i] = 0.f;
+#pragma unroll
         for (int e = 0; e < kUT; ++e) { carry[e] = 0.f; hv[e] = 0.f; }
       }
       // 1) what the other CTAs of the chain wait for: this thread's 8 units of h as ONE 16-byte store (zeros past the
@@ -326,7 +326,24 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
         st_relaxed_v4(hx_dir + (size_t)t * p.Bp * p.Hp + (size_t)b * p.Hp + u0, hp);
       }
       if (dbg && threadIdx.x == 0) dbg[s * 8 + 4] = clock64();
-      // 2) everything the next layer / the backward pass read: staged in shared memory, written by TMA bulk stores
+      // 2) the next step's inputs: its x-projection (LSU, in flight behind everything below) and the probe -- one word of
+      //    every producer warp's store of THIS step; once all are seen the issue warp pulls the tile while we stage 3)
+      if (s + 1 < steps) {
+        const int tn = reverse ? t - 1 : t + 1;
+#pragma unroll
+        for (int i = 0; i < 4 * kUT; ++i) zn[i] = 0.f;
+        if (row_ok && tn < len2) rec::ldv8<4 * kUT>(zn, gates + ((i64)tn * B + b) * 4 * H + z0);
+        if (prober) {
+          const __half* pp = hx_dir + (size_t)t * p.Bp * p.Hp + probe_off;
+          const long long t0 = clock64();
+          while (ld_cg_u32(pp) == kFill32)
+            if (clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 1, s, 0, 0);
+        }
+        __syncwarp();
+        if (lane == 0) rec::mbar_arrive(smem_u32(probe_bar));
+        if (dbg && threadIdx.x == 0) dbg[(s + 1) * 8 + 0] = clock64();
+      }
+      // 3) everything the next layer / the backward pass read: staged in shared memory, written by TMA bulk stores
       //    (rows past B are clipped by the tensor maps).  The previous step's stores must have finished reading first.
       if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
@@ -423,7 +440,7 @@ inline CUtensorMap make_map_f32_3d(const float* ptr, const i64* dims, const i64*
 
 inline int nkc16(int H) { return (H + kKC - 1) / kKC; }
 inline size_t fwd16_smem_bytes(int H) {
-  return (size_t)nkc16(H) * (kWChunk + kAChunk) + kStageBytes + (2 + 8) * 8 + 16 + 1024;
+  return (size_t)nkc16(H) * (kWChunk + kAChunk) + kStageBytes + (3 + 8) * 8 + 16 + 1024;
 }
 inline int hp16(int H) { return (H + 7) / 8 * 8; }
 inline int bp16(int B) { return (B + kBM - 1) / kBM * kBM; }
@@ -510,7 +527,7 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
   if (trapinfo) {
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess)
-      fprintf(stderr, "[rec fwd16 TRAP] %s: site=%d (1 probe, 2 acc_full, 3 a_full, 4 check, 5 weights) block=%d thread=%d step=%d chunk=%d extra=0x%x "
+      fprintf(stderr, "[rec fwd16 TRAP] %s: site=%d (1 probe, 2 acc_full, 3 a_full, 4 check, 5 weights, 6 probe_bar) block=%d thread=%d step=%d chunk=%d extra=0x%x "
                       "(steps=%d B=%d H=%d has_hd=%d)\n", cudaGetErrorString(e), trap_host[0], trap_host[1], trap_host[2], trap_host[3],
               trap_host[4], (unsigned)trap_host[5], steps, B, H, p.has_hd);
     E2T_CHECK(e);
