@@ -35,7 +35,7 @@ using rec::kBM;
 using rec::kUT;
 
 constexpr int kWorkThreads = 256;
-constexpr int kThreads16 = kWorkThreads + 32;
+constexpr int kThreads16 = kWorkThreads + 64;     // + MMA warp (8) + load / check warp (9)
 constexpr int kKC = 64;                         // fp16 elements per 128-byte swizzle row = one k-chunk
 constexpr uint32_t kAChunk = kBM * 128;         // 16 KB: 128 rows x 128 B
 constexpr uint32_t kWChunk = 4 * kU * 128;      // 8 KB: 64 gate rows x 128 B
@@ -86,6 +86,7 @@ struct Fwd16P {
   const int* lens2;       // [B] (nullable: all steps valid)
   int steps, B, Bp, H, Hp, n_bt, n_slices;
   int has_hd;
+  int dual_acc;           // alternate k-chunks between two TMEM accumulators (E2T_REC_DUAL, experiment)
   DropP dp; int drop_F;
   long long* dbg;         // E2T_REC_DEBUG: per-step clock64 stamps of CTA 0 ([steps][8]), else NULL
   int* trap_rec;          // mapped host memory (nullable): who timed out where, written right before the trap
@@ -157,8 +158,9 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
   uint64_t* w_bar = bars;
   uint64_t* acc_full = bars + 1;
   uint64_t* a_full = bars + 2;                                    // [NKC]
-  uint64_t* probe_bar = bars + 2 + NKC;                           // epilogue warps -> issue warp: "h of the step is out there"
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + NKC);
+  uint64_t* probe_bar = bars + 2 + NKC;                           // epilogue warps -> load warp: "h of the step is out there"
+  uint64_t* chk_bar = bars + 3 + NKC;                             // [NKC] load warp -> MMA warp: chunk landed and is complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + 2 * NKC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x % p.n_slices;
@@ -172,11 +174,11 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
     mbar_init(smem_u32(w_bar), 1);
     mbar_init(smem_u32(acc_full), 1);
     mbar_init(smem_u32(probe_bar), kWorkThreads / 32);
-    for (int k = 0; k < NKC; ++k) mbar_init(smem_u32(&a_full[k]), 1);
+    for (int k = 0; k < NKC; ++k) { mbar_init(smem_u32(&a_full[k]), 1); mbar_init(smem_u32(&chk_bar[k]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 64);
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 128);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -185,7 +187,7 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
   const int hx_row0 = d * steps * p.Bp + bt * kBM;                // + t * Bp: first row of this CTA's tile in map hx
 
   if (warp == 8) {
-    // ================= issue warp: weight TMA (once); per step: h tile TMA, fill-pattern check, MMAs =================
+    // ================= MMA warp: weight TMA (once); per step the MMAs of every chunk the load warp has released =================
     if (elect_one()) {
       const uint32_t wb = smem_u32(w_bar);
       mbar_expect_tx(wb, (uint32_t)NKC * kWChunk);
@@ -198,6 +200,27 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
     constexpr uint32_t idesc = make_idesc_f16(kBM, 4 * kU);
     const uint64_t desc_a0 = make_smem_desc(smem_u32(smem_a));
     const uint64_t desc_w0 = make_smem_desc(smem_u32(smem_w));
+    const bool dual = p.dual_acc && NKC >= 2;
+    for (int s = 1; s < steps; ++s) {
+      const uint32_t ph = (uint32_t)(s - 1) & 1u;
+#pragma unroll
+      for (int kc = 0; kc < NKC; ++kc) {
+        mbar_wait_rec(smem_u32(&chk_bar[kc]), ph, p.trap_rec, 7, s, kc);
+        fence_after_sync();
+        if (elect_one()) {
+          const int nk = min(4, (H - kc * kKC) / 16);       // K = 16 per instruction; H % 16 == 0
+          const uint32_t tacc = tmem_base + ((dual && (kc & 1)) ? 64u : 0u);
+          for (int k = 0; k < nk; ++k)
+            umma_f16(tacc, desc_a0 + (uint64_t)((kc * kAChunk + k * 32) >> 4), desc_w0 + (uint64_t)((kc * kWChunk + k * 32) >> 4),
+                     idesc, (kc > (dual ? 1 : 0) || k > 0) ? 1u : 0u);
+          if (kc == NKC - 1) umma_commit(smem_u32(acc_full));
+        }
+        __syncwarp();
+      }
+      if (dbg && lane == 0) dbg[s * 8 + 2] = clock64();
+    }
+  } else if (warp == 9) {
+    // ================= load warp: per step the h tile by TMA, then the fill-pattern check chunk by chunk =================
     uint32_t phases = 0;                             // bit kc = parity the next completion of a_full[kc] will have
     for (int s = 1; s < steps; ++s) {
       const int t = reverse ? steps - 1 - s : s;
@@ -205,7 +228,6 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
       // the epilogue threads have seen one piece of every producer warp's store of step s-1 (probe): the tile is (almost
       // surely) complete in L2.  Pull it; what the check below still finds unwritten is pulled again.
       mbar_wait_rec(smem_u32(probe_bar), (uint32_t)(s - 1) & 1u, p.trap_rec, 6, s, 0);
-      fence_after_sync();                              // the epilogue's tcgen05.ld of the previous step are behind us
       if (dbg && lane == 0) dbg[s * 8 + 1] = clock64();
       if (elect_one()) {
         for (int kc = 0; kc < NKC; ++kc) {
@@ -226,12 +248,16 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
             const int row = lane + 32 * m;
-            const unsigned char* rp = smem_a + (size_t)kc * kAChunk + (size_t)row * 128;
+            const uint32_t rp = smem_u32(smem_a) + (uint32_t)kc * kAChunk + (uint32_t)row * 128;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) bad |= *reinterpret_cast<const volatile uint32_t*>(rp + ((c ^ (row & 7)) << 4)) == kFill32;
+            for (int c = 0; c < 8; ++c) {
+              uint32_t w;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(rp + (uint32_t)((c ^ (row & 7)) << 4)) : "memory");
+              bad |= w == kFill32;
+            }
           }
           if (!__any_sync(0xffffffffu, bad)) break;
-          if (clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 4, s, kc, (int)__ballot_sync(0xffffffffu, bad));   // a lost producer must trap, not hang the GPU
+          if (clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 4, s, kc, (int)__ballot_sync(0xffffffffu, bad));
           if (dbg && lane == 0) dbg[s * 8 + 7] += 1;           // re-pulled chunks
           if (elect_one()) {
             const uint32_t fb = smem_u32(&a_full[kc]);
@@ -240,17 +266,10 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
           }
           __syncwarp();
         }
-        fence_after_sync();
-        if (elect_one()) {
-          const int nk = min(4, (H - kc * kKC) / 16);       // K = 16 per instruction; H % 16 == 0
-          for (int k = 0; k < nk; ++k)
-            umma_f16(tmem_base, desc_a0 + (uint64_t)((kc * kAChunk + k * 32) >> 4), desc_w0 + (uint64_t)((kc * kWChunk + k * 32) >> 4),
-                     idesc, (kc > 0 || k > 0) ? 1u : 0u);
-          if (kc == NKC - 1) umma_commit(smem_u32(acc_full));
-        }
         __syncwarp();
+        if (lane == 0) rec::mbar_arrive(smem_u32(&chk_bar[kc]));
+        if (kc == 0 && dbg && lane == 0) dbg[s * 8 + 6] = clock64();
       }
-      if (dbg && lane == 0) dbg[s * 8 + 2] = clock64();
     }
   } else {
     // ================= epilogue: thread = (batch row, 8 hidden units) =================
@@ -294,6 +313,11 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
         fence_after_sync();
         if (dbg && threadIdx.x == 0) dbg[s * 8 + 3] = clock64();
         rec::tmem_ld_cols<4 * kUT>(taddr, acc);
+        if (p.dual_acc && NKC >= 2) {                  // odd k-chunks were accumulated 64 columns further on
+#pragma unroll
+          for (int i = 0; i < 4 * kUT; ++i) z[i] += acc[i];
+          rec::tmem_ld_cols<4 * kUT>(taddr + 64u, acc);
+        }
         fence_before_sync();                           // the next step's MMAs are ordered behind these reads by probe_bar
       } else {
 #pragma unroll
@@ -389,7 +413,7 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
   __syncthreads();
   if (warp == 8) {
     fence_after_sync();
-    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_base, 128);
   }
 }
 
@@ -440,7 +464,7 @@ inline CUtensorMap make_map_f32_3d(const float* ptr, const i64* dims, const i64*
 
 inline int nkc16(int H) { return (H + kKC - 1) / kKC; }
 inline size_t fwd16_smem_bytes(int H) {
-  return (size_t)nkc16(H) * (kWChunk + kAChunk) + kStageBytes + (3 + 8) * 8 + 16 + 1024;
+  return (size_t)nkc16(H) * (kWChunk + kAChunk) + kStageBytes + (3 + 16) * 8 + 16 + 1024;
 }
 inline int hp16(int H) { return (H + 7) / 8 * 8; }
 inline int bp16(int B) { return (B + kBM - 1) / kBM * kBM; }
@@ -483,6 +507,8 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
   p.steps = steps; p.B = B; p.Bp = bp16(B); p.H = H; p.Hp = hp16(H);
   p.n_bt = (B + kBM - 1) / kBM; p.n_slices = H / kU;
   p.dp = dp; p.drop_F = drop_F;
+  static const int dual = getenv("E2T_REC_DUAL") ? atoi(getenv("E2T_REC_DUAL")) : 0;
+  p.dual_acc = dual;
   Fwd16Maps maps;
   maps.hx = make_map_f16(hx, (i64)2 * steps * p.Bp, H, p.Hp, kBM, kKC);
   const i64 dg[3] = {4 * (i64)H, B, steps}, sg[3] = {1, 4 * (i64)H, (i64)B * 4 * H};
@@ -527,7 +553,7 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
   if (trapinfo) {
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess)
-      fprintf(stderr, "[rec fwd16 TRAP] %s: site=%d (1 probe, 2 acc_full, 3 a_full, 4 check, 5 weights, 6 probe_bar) block=%d thread=%d step=%d chunk=%d extra=0x%x "
+      fprintf(stderr, "[rec fwd16 TRAP] %s: site=%d (1 probe, 2 acc_full, 3 a_full, 4 check, 5 weights, 6 probe_bar, 7 chk_bar) block=%d thread=%d step=%d chunk=%d extra=0x%x "
                       "(steps=%d B=%d H=%d has_hd=%d)\n", cudaGetErrorString(e), trap_host[0], trap_host[1], trap_host[2], trap_host[3],
               trap_host[4], (unsigned)trap_host[5], steps, B, H, p.has_hd);
     E2T_CHECK(e);
@@ -539,13 +565,13 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
     E2T_CHECK(cudaMemcpy(hst.data(), p.dbg, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(p.dbg);
     fprintf(stderr, "[rec fwd16] steps=%d B=%d H=%d grid=%d (cycles of CTA 0, rel. to the start of the step's probe)\n"
-                    "  step  repulls ->probed(tma_issued) ->mma_issued ->acc_seen ->h_stored ->stores_issued | step_total\n",
+                    "  step  repulls ->tma_issued ->chunk0_checked ->mma_issued ->acc_seen ->h_stored ->stores_issued | step_total\n",
             steps, B, H, 2 * p.n_bt * p.n_slices);
     for (int s = 1; s < steps; ++s) {
       const long long* e = &hst[(size_t)s * 8];
       const long long prev = s > 1 ? hst[(size_t)(s - 1) * 8] : 0;
-      fprintf(stderr, "  %4d  %4lld %8lld %8lld %8lld %8lld %8lld | %8lld\n", s, e[7], e[1] - e[0], e[2] - e[0], e[3] - e[0],
-              e[4] - e[0], e[5] - e[0], prev ? e[0] - prev : 0);
+      fprintf(stderr, "  %4d  %4lld %8lld %8lld %8lld %8lld %8lld %8lld | %8lld\n", s, e[7], e[1] - e[0], e[6] - e[0], e[2] - e[0],
+              e[3] - e[0], e[4] - e[0], e[5] - e[0], prev ? e[0] - prev : 0);
     }
   }
 }
