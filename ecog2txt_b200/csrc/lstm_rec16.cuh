@@ -87,6 +87,7 @@ struct Fwd16P {
   int steps, B, Bp, H, Hp, n_bt, n_slices;
   int has_hd;
   int dual_acc;           // alternate k-chunks between two TMEM accumulators (E2T_REC_DUAL, experiment)
+  int dbg_skip;           // timing experiments only (results are WRONG): bit 0 skip the TMA stores, bit 1 skip the z prefetch
   DropP dp; int drop_F;
   long long* dbg;         // E2T_REC_DEBUG: per-step clock64 stamps of CTA 0 ([steps][8]), else NULL
   int* trap_rec;          // mapped host memory (nullable): who timed out where, written right before the trap
@@ -217,18 +218,18 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
         }
         __syncwarp();
       }
-      if (dbg && lane == 0) dbg[s * 8 + 2] = clock64();
+      if (dbg && lane == 0) dbg[s * 16 + 2] = clock64();
     }
   } else if (warp == 9) {
     // ================= load warp: per step the h tile by TMA, then the fill-pattern check chunk by chunk =================
     uint32_t phases = 0;                             // bit kc = parity the next completion of a_full[kc] will have
     for (int s = 1; s < steps; ++s) {
       const int t = reverse ? steps - 1 - s : s;
-      const int t_src = reverse ? t + 1 : t - 1;
+      const int t_src = (p.dbg_skip & 4) ? (reverse ? steps - 1 : 0) : (reverse ? t + 1 : t - 1);   // bit 2: always the oldest tile
       // the epilogue threads have seen one piece of every producer warp's store of step s-1 (probe): the tile is (almost
       // surely) complete in L2.  Pull it; what the check below still finds unwritten is pulled again.
       mbar_wait_rec(smem_u32(probe_bar), (uint32_t)(s - 1) & 1u, p.trap_rec, 6, s, 0);
-      if (dbg && lane == 0) dbg[s * 8 + 1] = clock64();
+      if (dbg && lane == 0) dbg[s * 16 + 1] = clock64();
       if (elect_one()) {
         for (int kc = 0; kc < NKC; ++kc) {
           const uint32_t fb = smem_u32(&a_full[kc]);
@@ -238,27 +239,36 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
       }
       __syncwarp();
       const long long t0 = clock64();
+      if (p.dbg_skip & 8) {      // timing experiment: when does the LAST chunk land, independent of the checks?
+        uint32_t done = 0;
+        while (!done) {
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(done) : "r"(smem_u32(&a_full[NKC - 1])), "r"((phases >> (NKC - 1)) & 1u) : "memory");
+        }
+        if (dbg && lane == 0) dbg[s * 16 + 14] = clock64();
+      }
 #pragma unroll
       for (int kc = 0; kc < NKC; ++kc) {
         for (;;) {
           mbar_wait_rec(smem_u32(&a_full[kc]), (phases >> kc) & 1u, p.trap_rec, 3, s, kc);
           phases ^= 1u << kc;
           // lane l checks the first word of all 8 pieces of rows l, l+32, l+64, l+96 (a 16-byte piece is one store)
-          bool bad = false;
+          // (all 32 loads are issued before the first compare: a load -> compare chain costs one smem latency per word)
+          uint32_t w[32];
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
             const int row = lane + 32 * m;
             const uint32_t rp = smem_u32(smem_a) + (uint32_t)kc * kAChunk + (uint32_t)row * 128;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              uint32_t w;
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(rp + (uint32_t)((c ^ (row & 7)) << 4)) : "memory");
-              bad |= w == kFill32;
-            }
+            for (int c = 0; c < 8; ++c)
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[m * 8 + c]) : "r"(rp + (uint32_t)((c ^ (row & 7)) << 4)));
           }
+          bool bad = false;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) bad |= w[i] == kFill32;
           if (!__any_sync(0xffffffffu, bad)) break;
           if (clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 4, s, kc, (int)__ballot_sync(0xffffffffu, bad));
-          if (dbg && lane == 0) dbg[s * 8 + 7] += 1;           // re-pulled chunks
+          if (dbg && lane == 0) dbg[s * 16 + 7] += 1;           // re-pulled chunks
           if (elect_one()) {
             const uint32_t fb = smem_u32(&a_full[kc]);
             mbar_expect_tx(fb, kAChunk);
@@ -268,7 +278,8 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
         }
         __syncwarp();
         if (lane == 0) rec::mbar_arrive(smem_u32(&chk_bar[kc]));
-        if (kc == 0 && dbg && lane == 0) dbg[s * 8 + 6] = clock64();
+        if (kc == 0 && dbg && lane == 0) dbg[s * 16 + 6] = clock64();
+        if (kc == NKC - 1 && dbg && lane == 0) dbg[s * 16 + 8] = clock64();
       }
     }
   } else {
@@ -311,7 +322,7 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
       if (s > 0) {
         mbar_wait_rec(smem_u32(acc_full), (uint32_t)(s - 1) & 1u, p.trap_rec, 2, s, 0);
         fence_after_sync();
-        if (dbg && threadIdx.x == 0) dbg[s * 8 + 3] = clock64();
+        if (dbg && threadIdx.x == 0) dbg[s * 16 + 3] = clock64();
         rec::tmem_ld_cols<4 * kUT>(taddr, acc);
         if (p.dual_acc && NKC >= 2) {                  // odd k-chunks were accumulated 64 columns further on
 #pragma unroll
@@ -349,29 +360,22 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
         hp.x = pack_h2(hv[0], hv[1]); hp.y = pack_h2(hv[2], hv[3]); hp.z = pack_h2(hv[4], hv[5]); hp.w = pack_h2(hv[6], hv[7]);
         st_relaxed_v4(hx_dir + (size_t)t * p.Bp * p.Hp + (size_t)b * p.Hp + u0, hp);
       }
-      if (dbg && threadIdx.x == 0) dbg[s * 8 + 4] = clock64();
+      if (dbg && threadIdx.x == 0) dbg[s * 16 + 4] = clock64();
       // 2) the next step's inputs: its x-projection (LSU, in flight behind everything below) and the probe -- one word of
       //    every producer warp's store of THIS step; once all are seen the issue warp pulls the tile while we stage 3)
       if (s + 1 < steps) {
         const int tn = reverse ? t - 1 : t + 1;
 #pragma unroll
         for (int i = 0; i < 4 * kUT; ++i) zn[i] = 0.f;
-        if (row_ok && tn < len2) rec::ldv8<4 * kUT>(zn, gates + ((i64)tn * B + b) * 4 * H + z0);
-        if (prober) {
-          const __half* pp = hx_dir + (size_t)t * p.Bp * p.Hp + probe_off;
-          const long long t0 = clock64();
-          while (ld_cg_u32(pp) == kFill32)
-            if (clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 1, s, 0, 0);
-        }
-        __syncwarp();
-        if (lane == 0) rec::mbar_arrive(smem_u32(probe_bar));
-        if (dbg && threadIdx.x == 0) dbg[(s + 1) * 8 + 0] = clock64();
+        if (row_ok && tn < len2 && !(p.dbg_skip & 2)) rec::ldv8<4 * kUT>(zn, gates + ((i64)tn * B + b) * 4 * H + z0);
       }
       // 3) everything the next layer / the backward pass read: staged in shared memory, written by TMA bulk stores
       //    (rows past B are clipped by the tensor maps).  The previous step's stores must have finished reading first.
       if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (dbg && threadIdx.x == 0) dbg[s * 16 + 10] = clock64();
       __syncwarp();
       rec::named_bar_sync(2, kWorkThreads);
+      if (dbg && threadIdx.x == 0) dbg[s * 16 + 11] = clock64();
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const uint32_t addr = st_g + (uint32_t)((c ^ (r & 7)) << 4);
@@ -392,10 +396,13 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + 2 * kStageSmall), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + 2 * kStageSmall + 16), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
       }
+      if (dbg && threadIdx.x == 0) dbg[s * 16 + 12] = clock64();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (dbg && threadIdx.x == 0) dbg[s * 16 + 13] = clock64();
       __syncwarp();
       rec::named_bar_sync(3, kWorkThreads);
-      if (threadIdx.x == 0) {
+      if (dbg && threadIdx.x == 0) dbg[s * 16 + 9] = clock64();
+      if (threadIdx.x == 0 && !(p.dbg_skip & 1)) {
         const uint32_t so = smem_u32(smem_o);
         tma_store_3d(&maps.gates[d], so, j * 4 * kU, bt * kBM, t);
         tma_store_3d(&maps.gates[d], so + kBM * 128, j * 4 * kU + 4 * kUT, bt * kBM, t);
@@ -403,7 +410,19 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
         tma_store_3d(&maps.hs, so + kStageGates + kStageSmall, col0 + j * kU, bt * kBM, t);
         if (p.has_hd) tma_store_3d(&maps.hd, so + kStageGates + 2 * kStageSmall, col0 + j * kU, bt * kBM, t);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        if (dbg) dbg[s * 8 + 5] = clock64();
+        if (dbg) dbg[s * 16 + 5] = clock64();
+      }
+      __syncwarp();
+      if (s + 1 < steps) {
+        if (prober) {
+          const __half* pp = hx_dir + (size_t)t * p.Bp * p.Hp + probe_off;
+          const long long t0 = clock64();
+          while (ld_cg_u32(pp) == kFill32)
+            if (clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 1, s, 0, 0);
+        }
+        __syncwarp();
+        if (lane == 0) rec::mbar_arrive(smem_u32(probe_bar));
+        if (dbg && threadIdx.x == 0) dbg[(s + 1) * 16 + 0] = clock64();
       }
       __syncwarp();
     }
@@ -467,8 +486,11 @@ inline size_t fwd16_smem_bytes(int H) {
   return (size_t)nkc16(H) * (kWChunk + kAChunk) + kStageBytes + (3 + 16) * 8 + 16 + 1024;
 }
 inline int hp16(int H) { return (H + 7) / 8 * 8; }
+// row pitch of the exchange buffer: a multiple of 64 halves = 128 bytes, so that every 128-byte row of a TMA box is ONE
+// L2 line (at H = 400 an 800-byte pitch made most rows straddle two lines: 28 B/clk instead of ~90, profiles/r2l_*)
+inline int hpx16(int H) { return (H + 63) / 64 * 64; }
 inline int bp16(int B) { return (B + kBM - 1) / kBM * kBM; }
-inline size_t hx16_halves(int B, int H, int steps) { return (size_t)2 * steps * bp16(B) * hp16(H); }
+inline size_t hx16_halves(int B, int H, int steps) { return (size_t)2 * steps * bp16(B) * hpx16(H); }
 
 inline bool fwd16_supported(int B, int H) {
   if (H % kU != 0 || H < kU || H > 512 || B < 1) return false;
@@ -504,11 +526,13 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
   Fwd16P p{};
   for (int d = 0; d < 2; ++d) p.gates[d] = gates[d];
   p.hx = hx; p.lens2 = lens2; p.has_hd = hd != nullptr;
-  p.steps = steps; p.B = B; p.Bp = bp16(B); p.H = H; p.Hp = hp16(H);
+  p.steps = steps; p.B = B; p.Bp = bp16(B); p.H = H; p.Hp = hpx16(H);
   p.n_bt = (B + kBM - 1) / kBM; p.n_slices = H / kU;
   p.dp = dp; p.drop_F = drop_F;
   static const int dual = getenv("E2T_REC_DUAL") ? atoi(getenv("E2T_REC_DUAL")) : 0;
   p.dual_acc = dual;
+  static const int skip = getenv("E2T_REC_DBGSKIP") ? atoi(getenv("E2T_REC_DBGSKIP")) : 0;
+  p.dbg_skip = skip;
   Fwd16Maps maps;
   maps.hx = make_map_f16(hx, (i64)2 * steps * p.Bp, H, p.Hp, kBM, kKC);
   const i64 dg[3] = {4 * (i64)H, B, steps}, sg[3] = {1, 4 * (i64)H, (i64)B * 4 * H};
@@ -516,7 +540,7 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
   const i64 dh[3] = {2 * (i64)H, B, steps}, sh[3] = {1, 2 * (i64)H, (i64)B * 2 * H};
   const int bg[3] = {4 * kUT, kBM, 1}, bs[3] = {kU, kBM, 1};
   for (int d = 0; d < 2; ++d) {
-    maps.w[d] = make_map_f16(WhT16[d], 4 * (i64)H, H, p.Hp, 4 * kU, kKC);
+    maps.w[d] = make_map_f16(WhT16[d], 4 * (i64)H, H, hp16(H), 4 * kU, kKC);
     maps.gates[d] = make_map_f32_3d(gates[d], dg, sg, bg, true);
     maps.cs[d] = make_map_f32_3d(cs[d], dc, sc, bs, false);
   }
@@ -526,8 +550,8 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
   static int dbg_left = getenv("E2T_REC_DEBUG") ? atoi(getenv("E2T_REC_DEBUG")) : 0;
   p.dbg = nullptr;
   if (dbg_left > 0) {
-    E2T_CHECK(cudaMalloc(&p.dbg, (size_t)steps * 8 * sizeof(long long)));
-    E2T_CHECK(cudaMemsetAsync(p.dbg, 0, (size_t)steps * 8 * sizeof(long long), st));
+    E2T_CHECK(cudaMalloc(&p.dbg, (size_t)(steps + 1) * 16 * sizeof(long long)));
+    E2T_CHECK(cudaMemsetAsync(p.dbg, 0, (size_t)(steps + 1) * 16 * sizeof(long long), st));
   }
   // E2T_REC_TRAPINFO=1: a wait that times out leaves a record in mapped host memory before it traps (the launch is then
   // synchronised here so that the record can be printed: diagnostics only)
@@ -560,18 +584,19 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
   }
   if (p.dbg) {
     --dbg_left;
-    std::vector<long long> hst((size_t)steps * 8);
+    std::vector<long long> hst((size_t)(steps + 1) * 16);
     E2T_CHECK(cudaStreamSynchronize(st));
     E2T_CHECK(cudaMemcpy(hst.data(), p.dbg, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(p.dbg);
-    fprintf(stderr, "[rec fwd16] steps=%d B=%d H=%d grid=%d (cycles of CTA 0, rel. to the start of the step's probe)\n"
-                    "  step  repulls ->tma_issued ->chunk0_checked ->mma_issued ->acc_seen ->h_stored ->stores_issued | step_total\n",
+    fprintf(stderr, "[rec fwd16] steps=%d B=%d H=%d grid=%d (cycles of CTA 0, rel. to the end of the step's probe)\n"
+                    "  step  repulls ->tma_issued ->chunk0_checked ->last_checked ->mma_issued ->acc_seen ->h_stored [->wait_read ->bar2 ->sts ->fence ->bar3] ->stores_issued | step_total\n",
             steps, B, H, 2 * p.n_bt * p.n_slices);
     for (int s = 1; s < steps; ++s) {
-      const long long* e = &hst[(size_t)s * 8];
-      const long long prev = s > 1 ? hst[(size_t)(s - 1) * 8] : 0;
-      fprintf(stderr, "  %4d  %4lld %8lld %8lld %8lld %8lld %8lld %8lld | %8lld\n", s, e[7], e[1] - e[0], e[6] - e[0], e[2] - e[0],
-              e[3] - e[0], e[4] - e[0], e[5] - e[0], prev ? e[0] - prev : 0);
+      const long long* e = &hst[(size_t)s * 16];
+      const long long prev = s > 1 ? hst[(size_t)(s - 1) * 16] : 0;
+      if (e[14]) fprintf(stderr, "        (last chunk landed %lld)\n", e[14] - e[0]);
+      fprintf(stderr, "  %4d  %4lld %8lld %8lld %8lld %8lld %8lld %8lld [%6lld %6lld %6lld %6lld %6lld] %8lld | %8lld\n", s, e[7], e[1] - e[0], e[6] - e[0], e[8] - e[0],
+              e[2] - e[0], e[3] - e[0], e[4] - e[0], e[10] - e[0], e[11] - e[0], e[12] - e[0], e[13] - e[0], e[9] - e[0], e[5] - e[0], prev ? e[0] - prev : 0);
     }
   }
 }
