@@ -40,6 +40,8 @@ constexpr int kKC = 64;                         // fp16 elements per 128-byte sw
 constexpr uint32_t kAChunk = kBM * 128;         // 16 KB: 128 rows x 128 B
 constexpr uint32_t kWChunk = 4 * kU * 128;      // 8 KB: 64 gate rows x 128 B
 constexpr uint32_t kFill32 = 0xFFFFFFFFu;       // two fp16 fill patterns
+constexpr int kMaxRedo = 3;                     // bounded re-pulls of a tile whose accumulator came out NaN
+constexpr int kDbg = 32;                        // timeline slots per step (E2T_REC_DEBUG)
 
 // cute::UMMA::InstrDescriptor for kind::f16: c_format F32=1 [4,6) | a_format F16=0 [7,10) | b_format F16=0 [10,13)
 // | a_major / b_major = K (0) | N>>3 [17,23) | M>>4 [24,29)
@@ -82,12 +84,12 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 
 struct Fwd16P {
   float* gates[2];        // [T', B, 4H] x-projection (+bias) in, gate activations out (permuted gate order)
-  __half* hx;             // [2][T'][Bp][Hp] fp16 exchange buffer, pre-filled with 0xFFFF
+  __half* hx;             // fp16 exchange buffer [2][T'][n_bt][NKC][128 rows][64] = the operand tile's shared-memory image
+                          // (128B swizzle applied by the writers), pre-filled with 0xFFFF
   const int* lens2;       // [B] (nullable: all steps valid)
-  int steps, B, Bp, H, Hp, n_bt, n_slices;
+  int steps, B, H, n_bt, n_slices;
   int has_hd;
-  int dual_acc;           // alternate k-chunks between two TMEM accumulators (E2T_REC_DUAL, experiment)
-  int dbg_skip;           // timing experiments only (results are WRONG): bit 0 skip the TMA stores, bit 1 skip the z prefetch
+  int dbg_skip;           // E2T_REC_DBGSKIP, timing experiments only (results are WRONG): bit 0 no result stores, bit 1 no x-projection loads; bit 2 (results stay right) forces re-pulls
   DropP dp; int drop_F;
   long long* dbg;         // E2T_REC_DEBUG: per-step clock64 stamps of CTA 0 ([steps][8]), else NULL
   int* trap_rec;          // mapped host memory (nullable): who timed out where, written right before the trap
@@ -121,10 +123,9 @@ __device__ __forceinline__ void mbar_wait_rec(uint32_t bar, uint32_t parity, int
 // tensor maps of one launch (one kernel parameter: TMA descriptors must live in param / const space)
 struct Fwd16Maps {
   CUtensorMap w[2];       // Wh^T fp16 [4H, Hp], box 64 x 64, 128B swizzle (load, once)
-  CUtensorMap hx;         // exchange buffer as [2 T' Bp, Hp] fp16, box 64 x 128, 128B swizzle (load, every step)
   CUtensorMap gates[2];   // [T', B, 4H] fp32, box 32 x 128 x 1, 128B swizzle (store)
-  CUtensorMap cs[2];      // [T', B, H] fp32, box 16 x 128 x 1 (store)
-  CUtensorMap hs, hd;     // [T', B, 2H] fp32, box 16 x 128 x 1 (store)
+  CUtensorMap cs[2];      // [T', B, H] fp32, box 16 x 128 x 1, 64B swizzle (store)
+  CUtensorMap hs, hd;     // [T', B, 2H] fp32, box 16 x 128 x 1, 64B swizzle (store)
 };
 
 constexpr uint32_t kStageGates = 2 * kBM * 128;   // two swizzled [128 x 32 fp32] sub-tiles (unit group 0 / 1)
@@ -135,6 +136,14 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// contiguous global -> shared bulk copy (no tensor map: one request, not one per box row)
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -144,9 +153,29 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const void* p) {
   return v;
 }
 
-// Per step and CTA: 102 KB of h in (TMA), 56 KB of results out (TMA bulk stores from a staging tile), 4 KB of fp16 h and
-// 32 KB of x-projection through the LSU.  (First cut of this kernel pulled h with 16-byte LSU loads: 15-25 B/clk per SM,
-// 6500 cycles per step -- profiles/r2d_rec_timeline.txt; TMA ingests the same tile at ~92 B/clk.)
+__device__ __forceinline__ bool bar_red_or(int id, int nthreads, bool pred) {
+  uint32_t out;
+  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(out) : "r"((uint32_t)pred), "r"(id), "r"(nthreads) : "memory");
+  return out != 0;
+}
+
+// Per step and CTA: 112 KB of h in (7 contiguous bulk copies of the tile's shared-memory image), 32 KB of x-projection in
+// (TMA), 24 KB of c / h / dropped h out (TMA bulk stores from swizzled stages), 32 KB of gate activations and 4 KB of fp16
+// h out through the LSU.  History (profiles/r2*_timeline.txt, cycles per step at 1.965 GHz):
+//  * h pulled with 16-byte LSU loads: 15-25 B/clk per SM, 6500 cycles; TMA / bulk copies ingest the tile in ~1800;
+//  * x-projection prefetched into registers with 32-byte LSU loads at a 6400-byte row stride: 2400 cycles of LSU queueing
+//    in front of the staging stores of the same threads;
+//  * probe by the epilogue threads after their staging: the whole staging phase (5-6 k cycles) sat on the critical path;
+//  * explicit fill-pattern check of the landed tile by one warp: 32 ld.shared per lane and chunk = ~630 cycles per chunk,
+//    4400 per step, although all seven chunks had landed after ~1800 (r2q/r2r).
+// Now: warps 0-7 epilogue (thread = batch row x 8 units), warp 8 MMA issue, warp 9 probe + copies.
+//  * The load warp polls one word of every producer warp's h store of the previous step (the probe); when all are there the
+//    tile is almost surely complete in L2 and is pulled.  No check of what landed: the fill pattern 0xFFFF is an fp16 NaN,
+//    so a piece that was not there yet turns the whole accumulator row into NaN.  The epilogue threads test one accumulator
+//    word of their row, agree with one bar.red.or, and in the (never yet observed) bad case the step's copies and MMAs are
+//    simply repeated (at most kMaxRedo times, so that a genuinely diverged model cannot hang the kernel).
+//  * The x-projection tile of step s+1 is requested as soon as every thread has read the tile of step s into registers.
 template <int NKC>
 __global__ void __launch_bounds__(kThreads16, 1)
 k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
@@ -154,14 +183,15 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* smem_w = smem;                                   // [NKC][64 rows][128 B]
   unsigned char* smem_a = smem + (size_t)NKC * kWChunk;           // [NKC][128 rows][128 B]
-  unsigned char* smem_o = smem_a + (size_t)NKC * kAChunk;         // staging: gates | cs | hs | hd
+  unsigned char* smem_o = smem_a + (size_t)NKC * kAChunk;         // x-projection tile (2 x 16 KB) | stages cs | hs | hd
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + kStageBytes);
   uint64_t* w_bar = bars;
   uint64_t* acc_full = bars + 1;
   uint64_t* a_full = bars + 2;                                    // [NKC]
-  uint64_t* probe_bar = bars + 2 + NKC;                           // epilogue warps -> load warp: "h of the step is out there"
-  uint64_t* chk_bar = bars + 3 + NKC;                             // [NKC] load warp -> MMA warp: chunk landed and is complete
+  uint64_t* z_bar = bars + 2 + NKC;                               // x-projection tile of the step has landed
+  uint64_t* verdict_bar = bars + 3 + NKC;                         // epilogue -> MMA / load warp: accumulator accepted or redo
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 + 2 * NKC);
+  volatile uint32_t* verdict = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x % p.n_slices;
@@ -174,8 +204,9 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(w_bar), 1);
     mbar_init(smem_u32(acc_full), 1);
-    mbar_init(smem_u32(probe_bar), kWorkThreads / 32);
-    for (int k = 0; k < NKC; ++k) { mbar_init(smem_u32(&a_full[k]), 1); mbar_init(smem_u32(&chk_bar[k]), 1); }
+    mbar_init(smem_u32(z_bar), 1);
+    mbar_init(smem_u32(verdict_bar), 1);
+    for (int k = 0; k < NKC; ++k) mbar_init(smem_u32(&a_full[k]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -184,11 +215,14 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
-  __half* hx_dir = p.hx + (size_t)d * steps * p.Bp * p.Hp;
-  const int hx_row0 = d * steps * p.Bp + bt * kBM;                // + t * Bp: first row of this CTA's tile in map hx
+  // this chain's tiles: tile of step t at hx_chain + t * tile_stride (bytes); piece (row, k) of a tile at
+  // (k / 64) * 16 KB + row * 128 + (((k % 64) / 8) ^ (row & 7)) * 16
+  const size_t tile_bytes = (size_t)NKC * kAChunk;
+  const size_t tile_stride = (size_t)p.n_bt * tile_bytes;
+  unsigned char* hx_chain = reinterpret_cast<unsigned char*>(p.hx) + ((size_t)d * steps * p.n_bt + bt) * tile_bytes;
 
   if (warp == 8) {
-    // ================= MMA warp: weight TMA (once); per step the MMAs of every chunk the load warp has released =================
+    // ================= MMA warp: weight TMA (once); per step the MMAs of every chunk as it lands =================
     if (elect_one()) {
       const uint32_t wb = smem_u32(w_bar);
       mbar_expect_tx(wb, (uint32_t)NKC * kWChunk);
@@ -201,85 +235,81 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
     constexpr uint32_t idesc = make_idesc_f16(kBM, 4 * kU);
     const uint64_t desc_a0 = make_smem_desc(smem_u32(smem_a));
     const uint64_t desc_w0 = make_smem_desc(smem_u32(smem_w));
-    const bool dual = p.dual_acc && NKC >= 2;
+    uint32_t round = 0;                                // tiles pulled so far = phase of a_full / verdict_bar
     for (int s = 1; s < steps; ++s) {
-      const uint32_t ph = (uint32_t)(s - 1) & 1u;
+      for (;;) {
 #pragma unroll
-      for (int kc = 0; kc < NKC; ++kc) {
-        mbar_wait_rec(smem_u32(&chk_bar[kc]), ph, p.trap_rec, 7, s, kc);
-        fence_after_sync();
-        if (elect_one()) {
-          const int nk = min(4, (H - kc * kKC) / 16);       // K = 16 per instruction; H % 16 == 0
-          const uint32_t tacc = tmem_base + ((dual && (kc & 1)) ? 64u : 0u);
-          for (int k = 0; k < nk; ++k)
-            umma_f16(tacc, desc_a0 + (uint64_t)((kc * kAChunk + k * 32) >> 4), desc_w0 + (uint64_t)((kc * kWChunk + k * 32) >> 4),
-                     idesc, (kc > (dual ? 1 : 0) || k > 0) ? 1u : 0u);
-          if (kc == NKC - 1) umma_commit(smem_u32(acc_full));
-        }
-        __syncwarp();
-      }
-      if (dbg && lane == 0) dbg[s * 16 + 2] = clock64();
-    }
-  } else if (warp == 9) {
-    // ================= load warp: per step the h tile by TMA, then the fill-pattern check chunk by chunk =================
-    uint32_t phases = 0;                             // bit kc = parity the next completion of a_full[kc] will have
-    for (int s = 1; s < steps; ++s) {
-      const int t = reverse ? steps - 1 - s : s;
-      const int t_src = (p.dbg_skip & 4) ? (reverse ? steps - 1 : 0) : (reverse ? t + 1 : t - 1);   // bit 2: always the oldest tile
-      // the epilogue threads have seen one piece of every producer warp's store of step s-1 (probe): the tile is (almost
-      // surely) complete in L2.  Pull it; what the check below still finds unwritten is pulled again.
-      mbar_wait_rec(smem_u32(probe_bar), (uint32_t)(s - 1) & 1u, p.trap_rec, 6, s, 0);
-      if (dbg && lane == 0) dbg[s * 16 + 1] = clock64();
-      if (elect_one()) {
         for (int kc = 0; kc < NKC; ++kc) {
-          const uint32_t fb = smem_u32(&a_full[kc]);
-          mbar_expect_tx(fb, kAChunk);
-          tma_load_2d(smem_u32(smem_a + (size_t)kc * kAChunk), &maps.hx, fb, kc * kKC, hx_row0 + t_src * p.Bp);
-        }
-      }
-      __syncwarp();
-      const long long t0 = clock64();
-      if (p.dbg_skip & 8) {      // timing experiment: when does the LAST chunk land, independent of the checks?
-        uint32_t done = 0;
-        while (!done) {
-          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                       : "=r"(done) : "r"(smem_u32(&a_full[NKC - 1])), "r"((phases >> (NKC - 1)) & 1u) : "memory");
-        }
-        if (dbg && lane == 0) dbg[s * 16 + 14] = clock64();
-      }
-#pragma unroll
-      for (int kc = 0; kc < NKC; ++kc) {
-        for (;;) {
-          mbar_wait_rec(smem_u32(&a_full[kc]), (phases >> kc) & 1u, p.trap_rec, 3, s, kc);
-          phases ^= 1u << kc;
-          // lane l checks the first word of all 8 pieces of rows l, l+32, l+64, l+96 (a 16-byte piece is one store)
-          // (all 32 loads are issued before the first compare: a load -> compare chain costs one smem latency per word)
-          uint32_t w[32];
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const int row = lane + 32 * m;
-            const uint32_t rp = smem_u32(smem_a) + (uint32_t)kc * kAChunk + (uint32_t)row * 128;
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[m * 8 + c]) : "r"(rp + (uint32_t)((c ^ (row & 7)) << 4)));
-          }
-          bool bad = false;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) bad |= w[i] == kFill32;
-          if (!__any_sync(0xffffffffu, bad)) break;
-          if (clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 4, s, kc, (int)__ballot_sync(0xffffffffu, bad));
-          if (dbg && lane == 0) dbg[s * 16 + 7] += 1;           // re-pulled chunks
+          mbar_wait_rec(smem_u32(&a_full[kc]), round & 1u, p.trap_rec, 7, s, kc);
+          fence_after_sync();
           if (elect_one()) {
-            const uint32_t fb = smem_u32(&a_full[kc]);
-            mbar_expect_tx(fb, kAChunk);
-            tma_load_2d(smem_u32(smem_a + (size_t)kc * kAChunk), &maps.hx, fb, kc * kKC, hx_row0 + t_src * p.Bp);
+            const int nk = min(4, (H - kc * kKC) / 16);       // K = 16 per instruction; H % 16 == 0
+            for (int k = 0; k < nk; ++k)
+              umma_f16(tmem_base, desc_a0 + (uint64_t)((kc * kAChunk + k * 32) >> 4), desc_w0 + (uint64_t)((kc * kWChunk + k * 32) >> 4),
+                       idesc, (kc > 0 || k > 0) ? 1u : 0u);
+            if (kc == NKC - 1) umma_commit(smem_u32(acc_full));
           }
           __syncwarp();
+          if (dbg && lane == 0) dbg[s * kDbg + 16 + kc] = clock64();
+        }
+        if (dbg && lane == 0) dbg[s * kDbg + 2] = clock64();
+        mbar_wait_rec(smem_u32(verdict_bar), round & 1u, p.trap_rec, 9, s, 0);
+        ++round;
+        if (*verdict == 0u) break;
+      }
+    }
+  } else if (warp == 9) {
+    // ================= load warp: probe, then the h tile as NKC contiguous bulk copies =================
+    // probe word idx = 32 k + lane: producer slice idx / 8, its epilogue warp idx % 8 (lane 0 of that warp: row 32 (w & 3),
+    // unit group w >> 2)
+    constexpr int kProbes = (kWorkThreads + 31) / 32;      // n_slices * 8 <= kWorkThreads words
+    const int n_probe = p.n_slices * 8;
+    uint32_t probe_off[kProbes];
+#pragma unroll
+    for (int k = 0; k < kProbes; ++k) {
+      const int idx = 32 * k + lane;
+      const int prow = 32 * (idx & 3), pk = (idx >> 3) * kU + ((idx >> 2) & 1) * kUT;
+      probe_off[k] = (uint32_t)(pk / kKC) * kAChunk + (uint32_t)prow * 128 + (uint32_t)((((pk % kKC) / 8) ^ (prow & 7)) << 4);
+    }
+    uint32_t round = 0;
+    for (int s = 1; s < steps; ++s) {
+      const int t = reverse ? steps - 1 - s : s;
+      const int t_src = reverse ? t + 1 : t - 1;
+      const unsigned char* base = hx_chain + (size_t)t_src * tile_stride;
+      {
+        uint32_t pending = 0;
+#pragma unroll
+        for (int k = 0; k < kProbes; ++k)
+          if (32 * k + lane < n_probe) pending |= 1u << k;
+        const long long t0 = clock64();
+        while (pending) {
+          uint32_t v[kProbes];
+#pragma unroll
+          for (int k = 0; k < kProbes; ++k)
+            if (pending & (1u << k)) v[k] = ld_cg_u32(base + probe_off[k]);
+#pragma unroll
+          for (int k = 0; k < kProbes; ++k)
+            if ((pending & (1u << k)) && v[k] != kFill32) pending &= ~(1u << k);
+          if (pending && clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 1, s, 0, (int)pending);
         }
         __syncwarp();
-        if (lane == 0) rec::mbar_arrive(smem_u32(&chk_bar[kc]));
-        if (kc == 0 && dbg && lane == 0) dbg[s * 16 + 6] = clock64();
-        if (kc == NKC - 1 && dbg && lane == 0) dbg[s * 16 + 8] = clock64();
+      }
+      if (dbg && lane == 0) dbg[s * kDbg + 0] = clock64();
+      for (;;) {
+        // (the previous tile's MMAs are done and its accumulator has been read: the verdict said so)
+        if (elect_one()) {
+          for (int kc = 0; kc < NKC; ++kc) {
+            const uint32_t fb = smem_u32(&a_full[kc]);
+            mbar_expect_tx(fb, kAChunk);
+            bulk_load(smem_u32(smem_a + (size_t)kc * kAChunk), base + (size_t)kc * kAChunk, kAChunk, fb);
+          }
+        }
+        __syncwarp();
+        if (dbg && lane == 0) dbg[s * kDbg + 1] = clock64();
+        mbar_wait_rec(smem_u32(verdict_bar), round & 1u, p.trap_rec, 6, s, 0);
+        ++round;
+        if (*verdict == 0u) break;
+        if (dbg && lane == 0) dbg[s * kDbg + 7] += 1;           // tiles pulled again
       }
     }
   } else {
@@ -293,43 +323,76 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
     const int z0 = j * 4 * kU + ug * 4 * kUT;        // 32 contiguous gate columns [gate][8] in the permuted layout
     const int len2 = row_ok ? (p.lens2 ? p.lens2[b] : steps) : 0;
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ug * 4 * kUT);
-    const float* gates = d ? p.gates[1] : p.gates[0];
+    float* gates = d ? p.gates[1] : p.gates[0];
     const int col0 = d * H;
     float carry[kUT];
 #pragma unroll
     for (int i = 0; i < kUT; ++i) carry[i] = 0.f;
-    // probe: thread i watches the store of producer slice i / 8, warp i % 8 (its lane 0: row 32 (w & 3), unit group w >> 2)
-    const bool prober = (int)threadIdx.x < p.n_slices * 8;
-    const size_t probe_off = (size_t)(bt * kBM + 32 * ((int)threadIdx.x & 3)) * p.Hp + (size_t)((int)threadIdx.x >> 3) * kU +
-                             (size_t)(((int)threadIdx.x >> 2) & 1) * kUT;
+    // this thread's 32 gate columns [gate][8] of its row in the swizzled x-projection tile
     const uint32_t st_g = smem_u32(smem_o) + (uint32_t)ug * (kBM * 128) + (uint32_t)r * 128;
-    const uint32_t st_s = smem_u32(smem_o) + kStageGates + (uint32_t)r * 64 + (uint32_t)ug * 32;
+    // small stages [128 rows][16 fp32], 64B swizzle: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)
+    const uint32_t st_s0 = smem_u32(smem_o) + kStageGates + (uint32_t)r * 64 + (uint32_t)(((2 * ug) ^ ((r >> 1) & 3)) << 4);
+    const uint32_t st_s1 = smem_u32(smem_o) + kStageGates + (uint32_t)r * 64 + (uint32_t)(((2 * ug + 1) ^ ((r >> 1) & 3)) << 4);
+    // this thread's 16-byte piece of the exchange tile (8 units of h, fp16)
+    const uint32_t hx_off = (uint32_t)(u0 / kKC) * kAChunk + (uint32_t)r * 128 + (uint32_t)((((u0 % kKC) / 8) ^ (r & 7)) << 4);
+    const uint32_t so = smem_u32(smem_o);
+    const uint32_t zb = smem_u32(z_bar);
+    uint32_t acc_round = 0;
 
-    float zn[4 * kUT];                                 // x-projection of the NEXT step, prefetched a step ahead
-#pragma unroll
-    for (int i = 0; i < 4 * kUT; ++i) zn[i] = 0.f;
-    {
+    if (threadIdx.x == 0) {                            // x-projection tile of the first step
       const int t0s = reverse ? steps - 1 : 0;
-      if (row_ok && t0s < len2) rec::ldv8<4 * kUT>(zn, gates + ((i64)t0s * B + b) * 4 * H + z0);
+      mbar_expect_tx(zb, kStageGates);
+      rec::tma_load_3d(so, &maps.gates[d], zb, j * 4 * kU, bt * kBM, t0s);
+      rec::tma_load_3d(so + kBM * 128, &maps.gates[d], zb, j * 4 * kU + 4 * kUT, bt * kBM, t0s);
     }
     for (int s = 0; s < steps; ++s) {
       const int t = reverse ? steps - 1 - s : s;
       const bool valid = row_ok && t < len2;
       float z[4 * kUT];
       float acc[4 * kUT];
+      mbar_wait_rec(zb, (uint32_t)s & 1u, p.trap_rec, 8, s, 0);
 #pragma unroll
-      for (int i = 0; i < 4 * kUT; ++i) z[i] = zn[i];
-      if (s > 0) {
-        mbar_wait_rec(smem_u32(acc_full), (uint32_t)(s - 1) & 1u, p.trap_rec, 2, s, 0);
-        fence_after_sync();
-        if (dbg && threadIdx.x == 0) dbg[s * 16 + 3] = clock64();
-        rec::tmem_ld_cols<4 * kUT>(taddr, acc);
-        if (p.dual_acc && NKC >= 2) {                  // odd k-chunks were accumulated 64 columns further on
-#pragma unroll
-          for (int i = 0; i < 4 * kUT; ++i) z[i] += acc[i];
-          rec::tmem_ld_cols<4 * kUT>(taddr + 64u, acc);
+      for (int c = 0; c < 8; ++c)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(z[4 * c]), "=f"(z[4 * c + 1]), "=f"(z[4 * c + 2]), "=f"(z[4 * c + 3])
+                     : "r"(st_g + (uint32_t)((c ^ (r & 7)) << 4)) : "memory");
+      // the previous step's bulk stores must have finished reading the small stages before anyone writes them again
+      if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      rec::named_bar_sync(2, kWorkThreads);           // every thread holds its x-projection: the tile can be refilled
+      if (threadIdx.x == 0 && s + 1 < steps) {
+        const int tn = reverse ? t - 1 : t + 1;
+        if (p.dbg_skip & 2) rec::mbar_arrive(zb);
+        else {
+          mbar_expect_tx(zb, kStageGates);
+          rec::tma_load_3d(so, &maps.gates[d], zb, j * 4 * kU, bt * kBM, tn);
+          rec::tma_load_3d(so + kBM * 128, &maps.gates[d], zb, j * 4 * kU + 4 * kUT, bt * kBM, tn);
+          if (s + 2 < steps) {                         // and the one after that is asked into L2
+            const int tnn = reverse ? t - 2 : t + 2;
+            tma_prefetch_3d(&maps.gates[d], j * 4 * kU, bt * kBM, tnn);
+            tma_prefetch_3d(&maps.gates[d], j * 4 * kU + 4 * kUT, bt * kBM, tnn);
+          }
         }
-        fence_before_sync();                           // the next step's MMAs are ordered behind these reads by probe_bar
+      }
+      __syncwarp();
+      if (s > 0) {
+        for (int tries = 0;; ++tries) {
+          mbar_wait_rec(smem_u32(acc_full), acc_round & 1u, p.trap_rec, 2, s, 0);
+          ++acc_round;
+          fence_after_sync();
+          if (dbg && threadIdx.x == 0) dbg[s * kDbg + 3] = clock64();
+          rec::tmem_ld_cols<4 * kUT>(taddr, acc);
+          fence_before_sync();
+          // a piece of h that had not arrived (fill pattern = NaN) makes every accumulator word of its row NaN
+          const bool nan_row = (__float_as_uint(acc[0]) & 0x7fffffffu) > 0x7f800000u;
+          // (E2T_REC_DBGSKIP bit 2: tests force a redo on every fifth step to exercise the path)
+          const bool redo = (bar_red_or(3, kWorkThreads, nan_row) || ((p.dbg_skip & 4) && s % 5 == 0 && tries == 0)) && tries < kMaxRedo;
+          if (threadIdx.x == 0) {
+            *verdict = redo ? 1u : 0u;
+            rec::mbar_arrive(smem_u32(verdict_bar));
+          }
+          __syncwarp();
+          if (!redo) break;
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < 4 * kUT; ++i) acc[i] = 0.f;
@@ -358,34 +421,17 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
       {
         uint4 hp;
         hp.x = pack_h2(hv[0], hv[1]); hp.y = pack_h2(hv[2], hv[3]); hp.z = pack_h2(hv[4], hv[5]); hp.w = pack_h2(hv[6], hv[7]);
-        st_relaxed_v4(hx_dir + (size_t)t * p.Bp * p.Hp + (size_t)b * p.Hp + u0, hp);
+        st_relaxed_v4(hx_chain + (size_t)t * tile_stride + hx_off, hp);
       }
-      if (dbg && threadIdx.x == 0) dbg[s * 16 + 4] = clock64();
-      // 2) the next step's inputs: its x-projection (LSU, in flight behind everything below) and the probe -- one word of
-      //    every producer warp's store of THIS step; once all are seen the issue warp pulls the tile while we stage 3)
-      if (s + 1 < steps) {
-        const int tn = reverse ? t - 1 : t + 1;
-#pragma unroll
-        for (int i = 0; i < 4 * kUT; ++i) zn[i] = 0.f;
-        if (row_ok && tn < len2 && !(p.dbg_skip & 2)) rec::ldv8<4 * kUT>(zn, gates + ((i64)tn * B + b) * 4 * H + z0);
-      }
-      // 3) everything the next layer / the backward pass read: staged in shared memory, written by TMA bulk stores
-      //    (rows past B are clipped by the tensor maps).  The previous step's stores must have finished reading first.
-      if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      if (dbg && threadIdx.x == 0) dbg[s * 16 + 10] = clock64();
-      __syncwarp();
-      rec::named_bar_sync(2, kWorkThreads);
-      if (dbg && threadIdx.x == 0) dbg[s * 16 + 11] = clock64();
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t addr = st_g + (uint32_t)((c ^ (r & 7)) << 4);
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(z[4 * c]), "f"(z[4 * c + 1]), "f"(z[4 * c + 2]),
-                     "f"(z[4 * c + 3]) : "memory");
-      }
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s), "f"(carry[0]), "f"(carry[1]), "f"(carry[2]), "f"(carry[3]) : "memory");
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + 16), "f"(carry[4]), "f"(carry[5]), "f"(carry[6]), "f"(carry[7]) : "memory");
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + kStageSmall), "f"(hv[0]), "f"(hv[1]), "f"(hv[2]), "f"(hv[3]) : "memory");
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + kStageSmall + 16), "f"(hv[4]), "f"(hv[5]), "f"(hv[6]), "f"(hv[7]) : "memory");
+      if (dbg && threadIdx.x == 0) dbg[s * kDbg + 4] = clock64();
+      // 2) what the backward pass and the next layer read.  Gate activations: 128 contiguous bytes per thread, straight from
+      //    registers (the shared-memory tile they came from is already being refilled).  c / h / dropped h: small swizzled
+      //    stages, written out by TMA bulk stores (rows past B are clipped by the tensor maps).
+      if (row_ok && !(p.dbg_skip & 1)) rec::stv8<4 * kUT>(gates + ((i64)t * B + b) * 4 * H + z0, z);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s0), "f"(carry[0]), "f"(carry[1]), "f"(carry[2]), "f"(carry[3]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s1), "f"(carry[4]), "f"(carry[5]), "f"(carry[6]), "f"(carry[7]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s0 + kStageSmall), "f"(hv[0]), "f"(hv[1]), "f"(hv[2]), "f"(hv[3]) : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s1 + kStageSmall), "f"(hv[4]), "f"(hv[5]), "f"(hv[6]), "f"(hv[7]) : "memory");
       if (p.has_hd) {
         const uint32_t idx0 = (uint32_t)(((i64)t * B + b) * p.drop_F + col0 + u0);
         const uint32_t key = p.dp.key, thresh = p.dp.thresh;
@@ -393,36 +439,21 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
         float o[kUT];
 #pragma unroll
         for (int e = 0; e < kUT; ++e) o[e] = (valid && e2t_keep(key, idx0 + e, thresh)) ? hv[e] * inv : 0.f;
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + 2 * kStageSmall), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + 2 * kStageSmall + 16), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s0 + 2 * kStageSmall), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(st_s1 + 2 * kStageSmall), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
       }
-      if (dbg && threadIdx.x == 0) dbg[s * 16 + 12] = clock64();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if (dbg && threadIdx.x == 0) dbg[s * 16 + 13] = clock64();
       __syncwarp();
-      rec::named_bar_sync(3, kWorkThreads);
-      if (dbg && threadIdx.x == 0) dbg[s * 16 + 9] = clock64();
-      if (threadIdx.x == 0 && !(p.dbg_skip & 1)) {
-        const uint32_t so = smem_u32(smem_o);
-        tma_store_3d(&maps.gates[d], so, j * 4 * kU, bt * kBM, t);
-        tma_store_3d(&maps.gates[d], so + kBM * 128, j * 4 * kU + 4 * kUT, bt * kBM, t);
-        tma_store_3d(&maps.cs[d], so + kStageGates, j * kU, bt * kBM, t);
-        tma_store_3d(&maps.hs, so + kStageGates + kStageSmall, col0 + j * kU, bt * kBM, t);
-        if (p.has_hd) tma_store_3d(&maps.hd, so + kStageGates + 2 * kStageSmall, col0 + j * kU, bt * kBM, t);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        if (dbg) dbg[s * 16 + 5] = clock64();
-      }
-      __syncwarp();
-      if (s + 1 < steps) {
-        if (prober) {
-          const __half* pp = hx_dir + (size_t)t * p.Bp * p.Hp + probe_off;
-          const long long t0 = clock64();
-          while (ld_cg_u32(pp) == kFill32)
-            if (clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 1, s, 0, 0);
+      rec::named_bar_sync(4, kWorkThreads);
+      if (threadIdx.x == 0) {
+        if (dbg) dbg[s * kDbg + 9] = clock64();
+        if (!(p.dbg_skip & 1)) {
+          tma_store_3d(&maps.cs[d], so + kStageGates, j * kU, bt * kBM, t);
+          tma_store_3d(&maps.hs, so + kStageGates + kStageSmall, col0 + j * kU, bt * kBM, t);
+          if (p.has_hd) tma_store_3d(&maps.hd, so + kStageGates + 2 * kStageSmall, col0 + j * kU, bt * kBM, t);
         }
-        __syncwarp();
-        if (lane == 0) rec::mbar_arrive(smem_u32(probe_bar));
-        if (dbg && threadIdx.x == 0) dbg[(s + 1) * 16 + 0] = clock64();
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (dbg) dbg[s * kDbg + 5] = clock64();
       }
       __syncwarp();
     }
@@ -467,7 +498,7 @@ inline CUtensorMap make_map_f16(const __half* ptr, i64 rows, i64 cols, i64 ld, i
   return m;
 }
 
-inline CUtensorMap make_map_f32_3d(const float* ptr, const i64* dims, const i64* strides_elems, const int* box, bool swizzle128) {
+inline CUtensorMap make_map_f32_3d(const float* ptr, const i64* dims, const i64* strides_elems, const int* box, int swizzle_bytes) {
   CUtensorMap m;
   cuuint64_t gdim[3]; cuuint64_t gstr[2]; cuuint32_t bx[3]; cuuint32_t estr[3] = {1, 1, 1};
   for (int i = 0; i < 3; ++i) { gdim[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; }
@@ -475,7 +506,8 @@ inline CUtensorMap make_map_f32_3d(const float* ptr, const i64* dims, const i64*
   EncodeTiledFn fn = encode_fn();
   if (!fn) throw std::runtime_error("e2t: cuTensorMapEncodeTiled entry point not found");
   CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("e2t: cuTensorMapEncodeTiled (3d) failed with code " + std::to_string((int)r));
   return m;
@@ -486,11 +518,9 @@ inline size_t fwd16_smem_bytes(int H) {
   return (size_t)nkc16(H) * (kWChunk + kAChunk) + kStageBytes + (3 + 16) * 8 + 16 + 1024;
 }
 inline int hp16(int H) { return (H + 7) / 8 * 8; }
-// row pitch of the exchange buffer: a multiple of 64 halves = 128 bytes, so that every 128-byte row of a TMA box is ONE
-// L2 line (at H = 400 an 800-byte pitch made most rows straddle two lines: 28 B/clk instead of ~90, profiles/r2l_*)
-inline int hpx16(int H) { return (H + 63) / 64 * 64; }
+// exchange buffer: one shared-memory image of the operand tile (NKC chunks of 16 KB) per direction, step and batch tile
 inline int bp16(int B) { return (B + kBM - 1) / kBM * kBM; }
-inline size_t hx16_halves(int B, int H, int steps) { return (size_t)2 * steps * bp16(B) * hpx16(H); }
+inline size_t hx16_halves(int B, int H, int steps) { return (size_t)2 * steps * (bp16(B) / kBM) * nkc16(H) * (kAChunk / 2); }
 
 inline bool fwd16_supported(int B, int H) {
   if (H % kU != 0 || H < kU || H > 512 || B < 1) return false;
@@ -526,32 +556,29 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
   Fwd16P p{};
   for (int d = 0; d < 2; ++d) p.gates[d] = gates[d];
   p.hx = hx; p.lens2 = lens2; p.has_hd = hd != nullptr;
-  p.steps = steps; p.B = B; p.Bp = bp16(B); p.H = H; p.Hp = hpx16(H);
+  p.steps = steps; p.B = B; p.H = H;
   p.n_bt = (B + kBM - 1) / kBM; p.n_slices = H / kU;
   p.dp = dp; p.drop_F = drop_F;
-  static const int dual = getenv("E2T_REC_DUAL") ? atoi(getenv("E2T_REC_DUAL")) : 0;
-  p.dual_acc = dual;
   static const int skip = getenv("E2T_REC_DBGSKIP") ? atoi(getenv("E2T_REC_DBGSKIP")) : 0;
   p.dbg_skip = skip;
   Fwd16Maps maps;
-  maps.hx = make_map_f16(hx, (i64)2 * steps * p.Bp, H, p.Hp, kBM, kKC);
   const i64 dg[3] = {4 * (i64)H, B, steps}, sg[3] = {1, 4 * (i64)H, (i64)B * 4 * H};
   const i64 dc[3] = {H, B, steps}, sc[3] = {1, H, (i64)B * H};
   const i64 dh[3] = {2 * (i64)H, B, steps}, sh[3] = {1, 2 * (i64)H, (i64)B * 2 * H};
   const int bg[3] = {4 * kUT, kBM, 1}, bs[3] = {kU, kBM, 1};
   for (int d = 0; d < 2; ++d) {
     maps.w[d] = make_map_f16(WhT16[d], 4 * (i64)H, H, hp16(H), 4 * kU, kKC);
-    maps.gates[d] = make_map_f32_3d(gates[d], dg, sg, bg, true);
-    maps.cs[d] = make_map_f32_3d(cs[d], dc, sc, bs, false);
+    maps.gates[d] = make_map_f32_3d(gates[d], dg, sg, bg, 128);
+    maps.cs[d] = make_map_f32_3d(cs[d], dc, sc, bs, 64);
   }
-  maps.hs = make_map_f32_3d(hs, dh, sh, bs, false);
-  maps.hd = make_map_f32_3d(hd ? hd : hs, dh, sh, bs, false);
+  maps.hs = make_map_f32_3d(hs, dh, sh, bs, 64);
+  maps.hd = make_map_f32_3d(hd ? hd : hs, dh, sh, bs, 64);
   E2T_CHECK(cudaMemsetAsync(hx, 0xFF, hx16_halves(B, H, steps) * sizeof(__half), st));
   static int dbg_left = getenv("E2T_REC_DEBUG") ? atoi(getenv("E2T_REC_DEBUG")) : 0;
   p.dbg = nullptr;
   if (dbg_left > 0) {
-    E2T_CHECK(cudaMalloc(&p.dbg, (size_t)(steps + 1) * 16 * sizeof(long long)));
-    E2T_CHECK(cudaMemsetAsync(p.dbg, 0, (size_t)(steps + 1) * 16 * sizeof(long long), st));
+    E2T_CHECK(cudaMalloc(&p.dbg, (size_t)(steps + 1) * kDbg * sizeof(long long)));
+    E2T_CHECK(cudaMemsetAsync(p.dbg, 0, (size_t)(steps + 1) * kDbg * sizeof(long long), st));
   }
   // E2T_REC_TRAPINFO=1: a wait that times out leaves a record in mapped host memory before it traps (the launch is then
   // synchronised here so that the record can be printed: diagnostics only)
@@ -584,19 +611,20 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
   }
   if (p.dbg) {
     --dbg_left;
-    std::vector<long long> hst((size_t)(steps + 1) * 16);
+    std::vector<long long> hst((size_t)(steps + 1) * kDbg);
     E2T_CHECK(cudaStreamSynchronize(st));
     E2T_CHECK(cudaMemcpy(hst.data(), p.dbg, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(p.dbg);
+    const int nkc = nkc16(H);
     fprintf(stderr, "[rec fwd16] steps=%d B=%d H=%d grid=%d (cycles of CTA 0, rel. to the end of the step's probe)\n"
-                    "  step  repulls ->tma_issued ->chunk0_checked ->last_checked ->mma_issued ->acc_seen ->h_stored [->wait_read ->bar2 ->sts ->fence ->bar3] ->stores_issued | step_total\n",
+                    "  step  repulls ->copies_issued [chunk's MMAs issued ...] ->acc_seen ->h_stored ->staged ->stores_issued | step_total\n",
             steps, B, H, 2 * p.n_bt * p.n_slices);
-    for (int s = 1; s < steps; ++s) {
-      const long long* e = &hst[(size_t)s * 16];
-      const long long prev = s > 1 ? hst[(size_t)(s - 1) * 16] : 0;
-      if (e[14]) fprintf(stderr, "        (last chunk landed %lld)\n", e[14] - e[0]);
-      fprintf(stderr, "  %4d  %4lld %8lld %8lld %8lld %8lld %8lld %8lld [%6lld %6lld %6lld %6lld %6lld] %8lld | %8lld\n", s, e[7], e[1] - e[0], e[6] - e[0], e[8] - e[0],
-              e[2] - e[0], e[3] - e[0], e[4] - e[0], e[10] - e[0], e[11] - e[0], e[12] - e[0], e[13] - e[0], e[9] - e[0], e[5] - e[0], prev ? e[0] - prev : 0);
+    for (int s = 1; s + 1 < steps; ++s) {
+      const long long* e = &hst[(size_t)s * kDbg];
+      const long long prev = s > 1 ? hst[(size_t)(s - 1) * kDbg] : 0;
+      fprintf(stderr, "  %4d  %4lld %6lld [", s, e[7], e[1] - e[0]);
+      for (int kc = 0; kc < nkc; ++kc) fprintf(stderr, " %lld", e[16 + kc] - e[0]);
+      fprintf(stderr, "] %6lld %6lld %6lld %6lld | %6lld\n", e[3] - e[0], e[4] - e[0], e[9] - e[0], e[5] - e[0], prev ? e[0] - prev : 0);
     }
   }
 }
