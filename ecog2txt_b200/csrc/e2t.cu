@@ -27,6 +27,7 @@
 #include "lstm_rec.cuh"
 #ifndef E2T_EMU
 #include "lstm_rec16.cuh"
+#include "lstm_bptt3.cuh"
 #endif
 #include "conv_tc.cuh"
 #endif
@@ -62,6 +63,11 @@ struct EncLayer {
   // rec16 = the forward recurrence runs on k_lstm_fwd16 (lstm_rec16.cuh): fp16 copies of Wh^T [4H (permuted), round_up(H, 8)]
   bool rec16 = false;
   void* WhT16[2] = {nullptr, nullptr};
+  // bptt3 = the backward recurrence runs on k_lstm_bptt3 (lstm_bptt3.cuh): fp16 copies of Wh [H, 4H (permuted)] and the
+  // layer's dz scale state
+  bool bptt3 = false;
+  void* Wh16[2] = {nullptr, nullptr};
+  int* bptt3_scale = nullptr; int bptt3_scale_cur = 0;
 };
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -150,6 +156,9 @@ struct e2t_handle {
   void* rec_hx16 = nullptr; i64 rec_hx16_n = 0;      // fp16 h exchange buffer of k_lstm_fwd16 [2][T'][Bp][Hp]
 #ifndef E2T_EMU
   rec16::BpttTags bptt_tags{{0, 0}, -1, -1};         // tag state of rec_pws (k_lstm_bptt2)
+  rec16::BpttTags bptt3_tags{{0, 0}, -1, -1};        // tag state of rec_pws3 (k_lstm_bptt3)
+  float* rec_pws3 = nullptr; i64 rec_pws3_n = 0;     // partial pieces of k_lstm_bptt3
+  unsigned char* rec_dzx = nullptr; i64 rec_dzx_n = 0;   // fp16 dz exchange slots of k_lstm_bptt3
 #endif
   int* rec_counters = nullptr;   // arrival counters of the persistent recurrent kernels [2][n_bt][T2m]
   int64_t n_launch_rec = 0, n_graph_replays = 0;
@@ -532,6 +541,16 @@ void build_workspace(e2t_handle* h) {
       for (int d = 0; d < 2; ++d) L.WhT16[d] = h->alloc<uint16_t>((i64)4 * L.H * rec16::hp16(L.H));
       h->rec_hx16_n = std::max<i64>(h->rec_hx16_n, (i64)rec16::hx16_halves((int)Bm, L.H, (int)T2));
     }
+    static const bool bptt_old = getenv("E2T_BPTT_V1") != nullptr;   // A/B switch: first-generation BPTT kernel
+    L.bptt3 = L.rec && !bptt_old && rec16::bptt3_supported((int)Bm, L.H);
+    if (L.bptt3) {
+      for (int d = 0; d < 2; ++d) L.Wh16[d] = h->alloc<uint16_t>((i64)L.H * 4 * L.H);
+      L.bptt3_scale = h->alloc<int>(4);
+      const int init[4] = {0, 8, 0, 8};
+      E2T_CHECK(cudaMemcpy(L.bptt3_scale, init, sizeof(init), cudaMemcpyHostToDevice));
+      h->rec_dzx_n = std::max<i64>(h->rec_dzx_n, (i64)rec16::bptt3_dzx_bytes((int)Bm, L.H, (int)T2));
+      h->rec_pws3_n = std::max<i64>(h->rec_pws3_n, (i64)rec16::bptt3_pws_floats((int)Bm, L.H));
+    }
 #endif
   }
   h->h0 = h->alloc<float>(Bm * c.Hd); h->c0 = h->alloc<float>(Bm * c.Hd);
@@ -558,6 +577,8 @@ void build_workspace(e2t_handle* h) {
   }
   if (h->rec_pws_n) h->rec_pws = h->alloc<float>(h->rec_pws_n);
   if (h->rec_hx16_n) h->rec_hx16 = h->alloc<uint16_t>(h->rec_hx16_n);
+  if (h->rec_dzx_n) h->rec_dzx = h->alloc<unsigned char>(h->rec_dzx_n);
+  if (h->rec_pws3_n) h->rec_pws3 = h->alloc<float>(h->rec_pws3_n);
   h->rec_counters = h->alloc<int>((i64)2 * cdiv(Bm, 128) * std::max<i64>(T2, Lm));
   h->ld_dec_kt = h->Dp + round_up(c.Hd, 4);
   h->dec_KT = h->alloc<float>((i64)4 * c.Hd * h->ld_dec_kt);
@@ -666,6 +687,15 @@ void repack(e2t_handle* h, const float* src, int src_id) {
           rec16::PackJob& jb = jobs.j[jobs.n++];
           jb.src = L.KT[d] + L.In4; jb.dst = static_cast<__half*>(L.WhT16[d]);
           jb.rows = 4 * L.H; jb.cols = L.H; jb.ld_src = L.ldkt; jb.ld_dst = rec16::hp16(L.H);
+          biggest = std::max<i64>(biggest, (i64)jb.rows * jb.ld_dst);
+        }
+    for (auto& L : h->enc)
+      if (L.bptt3)
+        for (int d = 0; d < 2; ++d) {
+          E2T_REQUIRE(jobs.n < 16, "too many recurrent layers for one pack launch");
+          rec16::PackJob& jb = jobs.j[jobs.n++];     // Wh = rows [In, In+H) of the canonical kernel with permuted gate columns
+          jb.src = L.KP[d] + (i64)L.In * 4 * L.H; jb.dst = static_cast<__half*>(L.Wh16[d]);
+          jb.rows = L.H; jb.cols = 4 * L.H; jb.ld_src = 4 * L.H; jb.ld_dst = 4 * L.H;
           biggest = std::max<i64>(biggest, (i64)jb.rows * jb.ld_dst);
         }
     if (jobs.n) {
@@ -1214,7 +1244,13 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
       // second-generation BPTT (tag-in-data hand-off): opt-in -- polling 205 KB of partials per step through the LSU was
       // measured slower (13.4 vs 11.2 us per step, profiles/r2d_*) than the counter hand-off of the first generation
       static const bool bptt_v1 = getenv("E2T_BPTT_V2") == nullptr;
-      if (!use_allgather && !bptt_v1 && h->rec_pws && rec::bptt_supported(h->Bm, Ly.H))
+      if (Ly.bptt3) {
+        const __half* w16[2] = {static_cast<const __half*>(Ly.Wh16[0]), static_cast<const __half*>(Ly.Wh16[1])};
+        rec16::Bptt3Scale sc{Ly.bptt3_scale, Ly.bptt3_scale_cur};
+        rec16::rec_backward3(h->stream, Ly.gates, csd, Ly.dhs, w16, h->d_lens2, top ? h->dc0 : nullptr, c.Hd,
+                             top ? h->d_tlast : nullptr, h->rec_dzx, h->rec_pws3, (size_t)h->rec_pws3_n, h->bptt3_tags, sc, T2, B, Ly.H);
+        Ly.bptt3_scale_cur = sc.cur;
+      } else if (!use_allgather && !bptt_v1 && h->rec_pws && rec::bptt_supported(h->Bm, Ly.H))
         rec16::rec_backward_rs2(h->stream, Ly.gates, csd, Ly.dhs, Kd, Ly.In, h->d_lens2, top ? h->dc0 : nullptr, c.Hd,
                                 top ? h->d_tlast : nullptr, h->rec_pws, (size_t)h->rec_pws_n, h->bptt_tags, T2, B, Ly.H);
       else if (!use_allgather && h->rec_pws && rec::bptt_supported(h->Bm, Ly.H))

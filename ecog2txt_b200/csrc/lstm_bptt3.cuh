@@ -1,0 +1,590 @@
+// lstm_bptt3.cuh -- persistent BiLSTM BPTT, third generation (A10 of SURVEY.md section 8a): a two-hop exchange.
+//
+// Per step the recurrent part of dh is dz [B, 4H] x Wh^T [4H, H].  With the chain of n = H/16 CTAs that share a batch tile
+//   * all-gathering dz (first generation) moves 128 x 4H values INTO every CTA per step (819 KB in fp32),
+//   * reduce-scattering the [128, H] partials (k_lstm_bptt / k_lstm_bptt2) moves 205 KB out of and 205 KB into every CTA:
+//     41 MB through L2 per step chip-wide, ~6500 cycles at the measured ~6300 B/clk -- the floor of that formulation.
+// Here the chain is a G x R grid (n = R G; 5 x 5 at H = 400).  CTA j = a G + m (row group a, member m)
+//   hop 1: all-gathers the fp16 dz chunks [128 x 64] of the G members of ITS ROW GROUP (80 KB in, 16 KB out) -- the K-slice
+//          of 64 G permuted gate columns starting at 64 G a -- and multiplies them with Wh[units 16 R m .. 16 R (m+1), that
+//          K-slice] (resident in shared memory, fp16): a [128 x 16 R] partial, 4 G MMAs of K = 16;
+//   hop 2: cuts the partial into R pieces [128 x 16] for the owners R m + i of those units (40 KB out) and, as the owner of
+//          units 16 j .., sums the R pieces the row groups a' = 0 .. R-1 wrote for it (40 KB in), in that fixed order.
+// 176 KB per CTA and step through L2 instead of 410 KB, 20 MMAs instead of 200 (all-gather) -- and two hand-offs per step,
+// both without flags or fences, as in k_lstm_fwd16:
+//   * dz chunks are written as 16-byte pieces into per-step slots pre-filled with 0xFFFF (an fp16 NaN): the load warp polls
+//     one word per producer warp, then pulls the chunks with contiguous bulk copies; a piece that was not there yet poisons
+//     its accumulator row with NaN, which the drain detects (bar.red.or) and answers by pulling again;
+//   * partial pieces carry, in the least-significant mantissa bit of every fp32 word, the parity of the number of times
+//     their slot (double-buffered by step parity) has been written; they leave through bulk stores from a swizzled stage
+//     and are pulled back by ONE bulk copy per owner (its R pieces are contiguous); every consumed word's tag is checked.
+// dz is exchanged in fp16 (the 11-bit significand a tf32 operand keeps) times a power-of-two scale 2^e that is carried from
+// launch to launch per layer: e is re-centred (largest |dz| of the previous launch -> 2^10) only when that maximum, scaled,
+// left [2^4, 2^13]; conversions saturate, so a sudden 32-fold growth clips for one step instead of producing infinities.
+// The fp32 dz the weight-gradient GEMMs read is written unscaled, straight from registers.
+//
+// warps 0-7: compute (thread = batch row x 8 units: gate derivatives, drain), warp 8: MMA issue, warp 9: probes + pulls.
+#pragma once
+#include "lstm_rec16.cuh"
+
+namespace rec16 {
+
+constexpr uint32_t kPiece = kBM * 64;             // [128 rows x 16 fp32] = 8 KB, 64B-swizzled
+constexpr uint32_t kInGates = 2 * kBM * 128;      // gate activations of the step: two swizzled [128 x 32 fp32] sub-tiles
+constexpr uint32_t kInBytes = kInGates + 2 * kPiece;   // + c of the previous time step + dh from the layer above
+constexpr int kMaxG = 8;
+
+struct Bptt3Maps {
+  CUtensorMap w[2];       // Wh fp16 [H units, 4H permuted gate columns], box 64 columns x 16 R rows, 128B swizzle (load, once)
+  CUtensorMap gates[2];   // [T', B, 4H] fp32, box 32 x 128 x 1, 128B swizzle (load)
+  CUtensorMap cs[2];      // [T', B, H] fp32, box 16 x 128 x 1, 64B swizzle (load)
+  CUtensorMap dhs;        // [T', B, 2H] fp32, box 16 x 128 x 1, 64B swizzle (load)
+};
+
+struct Bptt3P {
+  float* gates[2];        // gate activations in, dz out (in place), permuted gate columns
+  const int* lens2;
+  const float* dc_inject; int ldi;
+  const int* inject_t;
+  unsigned char* dzx;     // fp16 dz exchange [2 dir][steps][n_bt][n slices] x 16 KB chunk images, pre-filled with 0xFF
+  float* pws;             // partial pieces [2 parity][2 dir][n_bt][owner n][row group R] x 8 KB
+  const int* scale_in;    // {bits of the largest |dz| of the previous launch, exponent e it ran with}
+  int* scale_out;         // same for this launch (max zeroed by the host, e written by block 0)
+  int has_dhs;
+  int steps, B, H, n_bt, n, G, R;
+  uint32_t epoch0, epoch1;   // writes so far to the parity-0 / parity-1 partial slots
+  int dbg_force;          // tests: force one re-pull of either hop on every fifth step
+  long long* dbg;
+  int* trap_rec;
+};
+
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ void lds_v4(float* v, uint32_t addr) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, const float* v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+// scale exponent of this launch from the previous launch's {max bits, exponent}
+__device__ __forceinline__ int bptt3_scale_exp(const int* in) {
+  const float pm = __int_as_float(in[0]);
+  int e = in[1];
+  if (pm > 0.f && pm < 3.0e38f) {
+    const int me = ilogbf(pm);
+    if (me + e > 13 || me + e < 4) e = 10 - me;
+  }
+  return max(-60, min(60, e));
+}
+
+__global__ void __launch_bounds__(kThreads16, 1)
+k_lstm_bptt3(const __grid_constant__ Bptt3Maps maps, Bptt3P p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int H = p.H, steps = p.steps, B = p.B, G = p.G, R = p.R, n = p.n;
+  const uint32_t WCH = (uint32_t)(16 * R) * 128;          // one 64-column chunk of the resident weights [16 R rows x 128 B]
+  unsigned char* smem_w = smem;                           // [G][16 R][128 B]
+  unsigned char* smem_a = smem_w + (size_t)G * WCH;       // [G][128][128 B]  dz chunks of the row group
+  unsigned char* smem_in = smem_a + (size_t)G * kAChunk;  // gate activations | c(t_prev) | dh from above
+  unsigned char* smem_p = smem_in + kInBytes;             // [R] partial pieces: drained out of TMEM, then the owner's pieces in
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + (size_t)R * kPiece);
+  uint64_t* w_bar = bars;
+  uint64_t* acc_full = bars + 1;
+  uint64_t* in_bar = bars + 2;
+  uint64_t* p_bar = bars + 3;         // the owner's pieces have landed
+  uint64_t* pfree_bar = bars + 4;     // the bulk stores of this CTA's pieces have read the stage
+  uint64_t* vbar1 = bars + 5;         // compute -> MMA / load warp: accumulator accepted or pull again
+  uint64_t* vbar2 = bars + 6;         // compute -> load warp: pieces accepted or pull again
+  uint64_t* a_full = bars + 7;        // [G]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7 + kMaxG);
+  volatile uint32_t* verdict1 = tmem_slot + 1;
+  volatile uint32_t* verdict2 = tmem_slot + 2;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x % n;
+  const int bt = (blockIdx.x / n) % p.n_bt;
+  const int d = blockIdx.x / (n * p.n_bt);
+  const bool reverse = d == 1;
+  const int a = j / G, m = j % G;
+  long long* dbg = (blockIdx.x == 0) ? p.dbg : nullptr;
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(w_bar), 1);
+    mbar_init(smem_u32(acc_full), 1);
+    mbar_init(smem_u32(in_bar), 1);
+    mbar_init(smem_u32(p_bar), 1);
+    mbar_init(smem_u32(pfree_bar), 1);
+    mbar_init(smem_u32(vbar1), 1);
+    mbar_init(smem_u32(vbar2), 1);
+    for (int k = 0; k < G; ++k) mbar_init(smem_u32(&a_full[k]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 256);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
+
+  // dz chunk of writer jj at step q: dzx + (((d steps + q) n_bt + bt) n + jj) * 16 KB; this CTA's row group = G contiguous chunks
+  const size_t dz_step = (size_t)p.n_bt * n * kAChunk;
+  unsigned char* dz_chain = p.dzx + ((size_t)d * steps * p.n_bt + bt) * n * kAChunk;      // + q * dz_step
+  // piece (owner jo, row group aa) of parity pq: pws + ((((pq 2 + d) n_bt + bt) n + jo) R + aa) * 2048 floats
+  const size_t par_stride = (size_t)2 * p.n_bt * n * R * (kPiece / 4);
+  float* pw_chain = p.pws + (size_t)(d * p.n_bt + bt) * n * R * (kPiece / 4);              // + pq * par_stride
+
+  if (warp == 8) {
+    // ================= MMA warp =================
+    if (elect_one()) {
+      const uint32_t wb = smem_u32(w_bar);
+      mbar_expect_tx(wb, (uint32_t)G * WCH);
+      for (int c = 0; c < G; ++c)
+        tma_load_2d(smem_u32(smem_w + (size_t)c * WCH), &maps.w[d], wb, 64 * (G * a + c), 16 * R * m);
+    }
+    __syncwarp();
+    mbar_wait_rec(smem_u32(w_bar), 0, p.trap_rec, 5, 0, 0);
+    fence_after_sync();
+    const uint32_t idesc = make_idesc_f16(kBM, 16 * R);
+    const uint64_t desc_a0 = make_smem_desc(smem_u32(smem_a));
+    const uint64_t desc_w0 = make_smem_desc(smem_u32(smem_w));
+    uint32_t round = 0;
+    for (int q = 0; q + 1 < steps; ++q) {
+      for (;;) {
+        for (int c = 0; c < G; ++c) {
+          mbar_wait_rec(smem_u32(&a_full[c]), round & 1u, p.trap_rec, 7, q, c);
+          fence_after_sync();
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tmem_base, desc_a0 + (uint64_t)((c * kAChunk + k * 32) >> 4), desc_w0 + (uint64_t)((c * WCH + k * 32) >> 4),
+                       idesc, (c > 0 || k > 0) ? 1u : 0u);
+            if (c == G - 1) umma_commit(smem_u32(acc_full));
+          }
+          __syncwarp();
+        }
+        if (dbg && lane == 0) dbg[q * kDbg + 2] = clock64();
+        mbar_wait_rec(smem_u32(vbar1), round & 1u, p.trap_rec, 9, q, 0);
+        ++round;
+        if (*verdict1 == 0u) break;
+      }
+    }
+  } else if (warp == 9) {
+    // ================= load warp: per step hop 1 (dz chunks of the row group), then hop 2 (this owner's pieces) =================
+    uint32_t off1[2], off2[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int idx = 32 * k + lane;
+      // hop 1: member idx / 8, its compute warp w = idx % 8 (lane 0: row 32 (w & 3), first piece 4 (w >> 2))
+      const int prow = 32 * (idx & 3), pc = 4 * ((idx >> 2) & 1);
+      off1[k] = (uint32_t)(idx >> 3) * kAChunk + (uint32_t)prow * 128 + (uint32_t)((pc ^ (prow & 7)) << 4);
+      // hop 2: piece idx / 8, the last word of its KB idx % 8
+      off2[k] = (uint32_t)(idx >> 3) * kPiece + (uint32_t)(idx & 7) * 1024 + 1020;
+    }
+    const int n1 = 8 * G, n2 = 8 * R;
+    uint32_t round1 = 0, round2 = 0;
+    for (int q = 0; q + 1 < steps; ++q) {
+      {
+        const unsigned char* base = dz_chain + (size_t)q * dz_step + (size_t)(a * G) * kAChunk;
+        uint32_t pending = (lane < n1 ? 1u : 0u) | (32 + lane < n1 ? 2u : 0u);
+        const long long t0 = clock64();
+        while (pending) {
+          uint32_t v[2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            if (pending & (1u << k)) v[k] = ld_cg_u32(base + off1[k]);
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            if ((pending & (1u << k)) && v[k] != kFill32) pending &= ~(1u << k);
+          if (pending && clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 1, q, 0, (int)pending);
+        }
+        __syncwarp();
+        if (dbg && lane == 0) dbg[q * kDbg + 0] = clock64();
+        for (;;) {
+          if (elect_one()) {
+            for (int c = 0; c < G; ++c) {
+              const uint32_t fb = smem_u32(&a_full[c]);
+              mbar_expect_tx(fb, kAChunk);
+              bulk_load(smem_u32(smem_a + (size_t)c * kAChunk), base + (size_t)c * kAChunk, kAChunk, fb);
+            }
+          }
+          __syncwarp();
+          if (dbg && lane == 0) dbg[q * kDbg + 1] = clock64();
+          mbar_wait_rec(smem_u32(vbar1), round1 & 1u, p.trap_rec, 6, q, 0);
+          ++round1;
+          if (*verdict1 == 0u) break;
+          if (dbg && lane == 0) dbg[q * kDbg + 9] += 1;
+        }
+      }
+      {
+        const int pq = q & 1;
+        const uint32_t tw = ((pq ? p.epoch1 : p.epoch0) + (uint32_t)(q >> 1)) & 1u;
+        const unsigned char* base = reinterpret_cast<const unsigned char*>(pw_chain + (size_t)pq * par_stride + (size_t)j * R * (kPiece / 4));
+        uint32_t pending = (lane < n2 ? 1u : 0u) | (32 + lane < n2 ? 2u : 0u);
+        const long long t0 = clock64();
+        while (pending) {
+          uint32_t v[2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            if (pending & (1u << k)) v[k] = ld_cg_u32(base + off2[k]);
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            if ((pending & (1u << k)) && (v[k] & 1u) == tw) pending &= ~(1u << k);
+          if (pending && clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 10, q, 0, (int)pending);
+        }
+        __syncwarp();
+        if (dbg && lane == 0) dbg[q * kDbg + 5] = clock64();
+        // this CTA's own pieces of the step have left the stage
+        mbar_wait_rec(smem_u32(pfree_bar), (uint32_t)q & 1u, p.trap_rec, 11, q, 0);
+        for (;;) {
+          if (elect_one()) {
+            const uint32_t fb = smem_u32(p_bar);
+            mbar_expect_tx(fb, (uint32_t)R * kPiece);
+            bulk_load(smem_u32(smem_p), base, (uint32_t)R * kPiece, fb);
+          }
+          __syncwarp();
+          if (dbg && lane == 0) dbg[q * kDbg + 6] = clock64();
+          mbar_wait_rec(smem_u32(vbar2), round2 & 1u, p.trap_rec, 12, q, 0);
+          ++round2;
+          if (*verdict2 == 0u) break;
+          if (dbg && lane == 0) dbg[q * kDbg + 9] += 1;
+        }
+      }
+    }
+  } else {
+    // ================= compute threads: (batch row, 8 hidden units) =================
+    const int quad = warp & 3;
+    const int ug = warp >> 2;
+    const int r = quad * 32 + lane;
+    const int b = bt * kBM + r;
+    const bool row_ok = b < B;
+    const int u0 = j * kU + ug * kUT;
+    const int z0 = j * 4 * kU + ug * 4 * kUT;
+    const int len2 = row_ok ? (p.lens2 ? p.lens2[b] : steps) : 0;
+    float* gates = d ? p.gates[1] : p.gates[0];
+    const int col0 = d * H;
+    const int inject_at = (row_ok && p.dc_inject) ? ((d == 0 && p.inject_t) ? p.inject_t[b] : 0) : -1;
+    const uint32_t sin = smem_u32(smem_in), sp = smem_u32(smem_p);
+    const uint32_t in_g = sin + (uint32_t)ug * (kBM * 128) + (uint32_t)r * 128;                       // + ((c ^ (r & 7)) << 4)
+    const uint32_t sw0 = (uint32_t)r * 64 + (uint32_t)(((2 * ug) ^ ((r >> 1) & 3)) << 4);             // 64B-swizzled [128][16] tiles
+    const uint32_t sw1 = (uint32_t)r * 64 + (uint32_t)(((2 * ug + 1) ^ ((r >> 1) & 3)) << 4);
+    const uint32_t dz_off = (uint32_t)r * 128;                                                       // + (((4 ug + g) ^ (r & 7)) << 4)
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ug * kUT);
+    const int e_scale = bptt3_scale_exp(p.scale_in);
+    const float S = exp2f((float)e_scale), invS = exp2f((float)-e_scale);
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.scale_out[1] = e_scale;
+    float amax = 0.f;
+    float carry[kUT], cv[kUT];
+#pragma unroll
+    for (int i = 0; i < kUT; ++i) carry[i] = 0.f;
+    uint32_t acc_round = 0, p_round = 0;
+
+    if (threadIdx.x == 0) {
+      // inputs of the first step; its c(t) rides in the (still unused) piece stage
+      const int t0s = reverse ? 0 : steps - 1;
+      const int tp0 = reverse ? 1 : steps - 2;
+      const uint32_t ib = smem_u32(in_bar);
+      mbar_expect_tx(ib, kInGates + 2 * kPiece + (p.has_dhs ? kPiece : 0));
+      rec::tma_load_3d(sin, &maps.gates[d], ib, j * 4 * kU, bt * kBM, t0s);
+      rec::tma_load_3d(sin + kBM * 128, &maps.gates[d], ib, j * 4 * kU + 4 * kUT, bt * kBM, t0s);
+      rec::tma_load_3d(sin + kInGates, &maps.cs[d], ib, j * kU, bt * kBM, tp0);
+      rec::tma_load_3d(sp, &maps.cs[d], ib, j * kU, bt * kBM, t0s);
+      if (p.has_dhs) rec::tma_load_3d(sin + kInGates + kPiece, &maps.dhs, ib, col0 + j * kU, bt * kBM, t0s);
+    }
+    for (int q = 0; q < steps; ++q) {
+      const int t = reverse ? q : steps - 1 - q;
+      const bool valid = row_ok && t < len2;
+      const bool more = q + 1 < steps;
+      float gz[4 * kUT], cpv[kUT], dhv[kUT], acc[kUT];
+      // ---- inputs of the step: shared memory -> registers, then the stage is refilled for the next step
+      mbar_wait_rec(smem_u32(in_bar), (uint32_t)q & 1u, p.trap_rec, 8, q, 0);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) lds_v4(gz + 4 * c, in_g + (uint32_t)((c ^ (r & 7)) << 4));
+      lds_v4(cpv, sin + kInGates + sw0); lds_v4(cpv + 4, sin + kInGates + sw1);
+      if (p.has_dhs) { lds_v4(dhv, sin + kInGates + kPiece + sw0); lds_v4(dhv + 4, sin + kInGates + kPiece + sw1); }
+      else {
+#pragma unroll
+        for (int e = 0; e < kUT; ++e) dhv[e] = 0.f;
+      }
+      if (q == 0) { lds_v4(cv, sp + sw0); lds_v4(cv + 4, sp + sw1); }
+      __syncwarp();
+      rec::named_bar_sync(2, kWorkThreads);
+      if (threadIdx.x == 0 && more) {
+        const int tn = reverse ? t + 1 : t - 1;
+        const int tpn = reverse ? t + 2 : t - 2;          // out of range on the last step: the box is zero-filled
+        const uint32_t ib = smem_u32(in_bar);
+        mbar_expect_tx(ib, kInGates + kPiece + (p.has_dhs ? kPiece : 0));
+        rec::tma_load_3d(sin, &maps.gates[d], ib, j * 4 * kU, bt * kBM, tn);
+        rec::tma_load_3d(sin + kBM * 128, &maps.gates[d], ib, j * 4 * kU + 4 * kUT, bt * kBM, tn);
+        rec::tma_load_3d(sin + kInGates, &maps.cs[d], ib, j * kU, bt * kBM, tpn);
+        if (p.has_dhs) rec::tma_load_3d(sin + kInGates + kPiece, &maps.dhs, ib, col0 + j * kU, bt * kBM, tn);
+      }
+      __syncwarp();
+      // ---- recurrent part of dh: the R pieces written for this owner at the previous step, summed in row-group order
+#pragma unroll
+      for (int e = 0; e < kUT; ++e) acc[e] = 0.f;
+      if (q > 0) {
+        const uint32_t tw = ((((q - 1) & 1) ? p.epoch1 : p.epoch0) + (uint32_t)((q - 1) >> 1)) & 1u;
+        for (int tries = 0;; ++tries) {
+          mbar_wait_rec(smem_u32(p_bar), p_round & 1u, p.trap_rec, 13, q, 0);
+          ++p_round;
+          if (dbg && threadIdx.x == 0) dbg[q * kDbg + 7] = clock64();
+          uint32_t tagbad = 0;
+#pragma unroll
+          for (int e = 0; e < kUT; ++e) acc[e] = 0.f;
+          for (int aa = 0; aa < R; ++aa) {
+            float v[8];
+            lds_v4(v, sp + (uint32_t)aa * kPiece + sw0); lds_v4(v + 4, sp + (uint32_t)aa * kPiece + sw1);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint32_t w = __float_as_uint(v[e]);
+              tagbad |= (w ^ tw);
+              acc[e] += __uint_as_float(w & ~1u);
+            }
+          }
+          const bool force = p.dbg_force && q % 5 == 0 && tries == 0;
+          const bool redo = (bar_red_or(3, kWorkThreads, (tagbad & 1u) != 0u) || force) && tries < kMaxRedo;
+          if (threadIdx.x == 0) {
+            *verdict2 = redo ? 1u : 0u;
+            rec::mbar_arrive(smem_u32(vbar2));
+          }
+          __syncwarp();
+          if (!redo) break;
+        }
+#pragma unroll
+        for (int e = 0; e < kUT; ++e) acc[e] *= invS;
+      }
+      // ---- gate derivatives
+      if (valid) {
+        const bool inject = inject_at == t;
+#pragma unroll
+        for (int e = 0; e < kUT; ++e) {
+          const float gi = gz[e], gj = gz[kUT + e], gf = gz[2 * kUT + e], go = gz[3 * kUT + e];
+          const float dh = dhv[e] + acc[e];
+          float dc = carry[e];
+          if (inject) dc += p.dc_inject[(i64)b * p.ldi + col0 + u0 + e];
+          const float tc_ = rec::tanh_fast(cv[e]);
+          gz[3 * kUT + e] = dh * tc_ * go * (1.f - go);
+          dc += dh * go * (1.f - tc_ * tc_);
+          gz[e] = dc * gj * gi * (1.f - gi);
+          gz[kUT + e] = dc * gi * (1.f - gj * gj);
+          gz[2 * kUT + e] = dc * cpv[e] * gf * (1.f - gf);
+          carry[e] = dc * gf;
+        }
+#pragma unroll
+        for (int i = 0; i < 4 * kUT; ++i) amax = fmaxf(amax, fabsf(gz[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4 * kUT; ++i) gz[i] = 0.f;
+#pragma unroll
+        for (int e = 0; e < kUT; ++e) carry[e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < kUT; ++e) cv[e] = cpv[e];         // c(t_prev) is the next step's c(t)
+      // ---- hop 1: this thread's four 16-byte pieces of the CTA's dz chunk (zeros for padding rows: the fill must go)
+      if (more) {
+        unsigned char* dst = dz_chain + (size_t)q * dz_step + (size_t)j * kAChunk + dz_off;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 w;
+          w.x = pack_h2_sat(gz[8 * g] * S, gz[8 * g + 1] * S); w.y = pack_h2_sat(gz[8 * g + 2] * S, gz[8 * g + 3] * S);
+          w.z = pack_h2_sat(gz[8 * g + 4] * S, gz[8 * g + 5] * S); w.w = pack_h2_sat(gz[8 * g + 6] * S, gz[8 * g + 7] * S);
+          st_relaxed_v4(dst + (uint32_t)(((4 * ug + g) ^ (r & 7)) << 4), w);
+        }
+        if (dbg && threadIdx.x == 0) dbg[q * kDbg + 8] = clock64();
+      }
+      // dz to HBM for the weight-gradient GEMMs (off the inter-CTA critical path)
+      if (row_ok) rec::stv8<4 * kUT>(gates + ((i64)t * B + b) * 4 * H + z0, gz);
+      // ---- hop 2: drain the partial of the step, piece by piece, tagged, through the stage
+      if (more) {
+        const uint32_t tw = (((q & 1) ? p.epoch1 : p.epoch0) + (uint32_t)(q >> 1)) & 1u;
+        float v[8];
+        for (int tries = 0;; ++tries) {
+          mbar_wait_rec(smem_u32(acc_full), acc_round & 1u, p.trap_rec, 2, q, 0);
+          ++acc_round;
+          fence_after_sync();
+          if (dbg && threadIdx.x == 0) dbg[q * kDbg + 3] = clock64();
+          rec::tmem_ld_cols<8>(tlane, v);
+          const bool nan_row = (__float_as_uint(v[0]) & 0x7fffffffu) > 0x7f800000u;
+          const bool force = p.dbg_force && q % 5 == 2 && tries == 0;
+          const bool redo = (bar_red_or(4, kWorkThreads, nan_row) || force) && tries < kMaxRedo;
+          if (redo) fence_before_sync();
+          if (threadIdx.x == 0) {
+            *verdict1 = redo ? 1u : 0u;
+            rec::mbar_arrive(smem_u32(vbar1));
+          }
+          __syncwarp();
+          if (!redo) break;
+        }
+        for (int i = 0; i < R; ++i) {
+          if (i > 0) rec::tmem_ld_cols<8>(tlane + (uint32_t)(16 * i), v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float((__float_as_uint(v[e]) & ~1u) | tw);
+          sts_v4(sp + (uint32_t)i * kPiece + sw0, v); sts_v4(sp + (uint32_t)i * kPiece + sw1, v + 4);
+        }
+        fence_before_sync();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        rec::named_bar_sync(5, kWorkThreads);
+        if (threadIdx.x == 0) {
+          float* dstp = pw_chain + (size_t)(q & 1) * par_stride;
+          for (int i = 0; i < R; ++i)
+            bulk_store(dstp + ((size_t)(R * m + i) * R + a) * (kPiece / 4), sp + (uint32_t)i * kPiece, kPiece);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (dbg) dbg[q * kDbg + 4] = clock64();
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          rec::mbar_arrive(smem_u32(pfree_bar));
+        }
+        __syncwarp();
+      }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // largest |dz| of the launch: the next launch's scale
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0 && amax < 3.0e38f) atomicMax(reinterpret_cast<unsigned int*>(p.scale_out), __float_as_uint(amax));
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 8) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+struct Bptt3Geo { int G, R; };
+inline Bptt3Geo bptt3_geo(int H) {
+  const int n = H / kU;
+  Bptt3Geo g{0, 0};
+  // members per row group: the divisor of n closest to sqrt(n) (5 x 5 at H = 400), at most kMaxG; R pieces of 16 columns
+  int best = 0;
+  for (int G = 1; G <= kMaxG && G <= n; ++G)
+    if (n % G == 0 && (best == 0 || abs(G * G - n) < abs(best * best - n))) best = G;
+  if (best) { g.G = best; g.R = n / best; }
+  return g;
+}
+inline size_t bptt3_smem_bytes(int H) {
+  const Bptt3Geo g = bptt3_geo(H);
+  return (size_t)g.G * ((size_t)16 * g.R * 128 + kAChunk) + kInBytes + (size_t)g.R * kPiece + (7 + kMaxG) * 8 + 16 + 1024;
+}
+inline bool bptt3_supported(int B, int H) {
+  if (H % kU != 0 || H < 4 * kU || H > 512 || B < 1) return false;
+  const Bptt3Geo g = bptt3_geo(H);
+  if (g.G < 2 || g.R < 1 || 16 * g.R > 256 || 8 * g.G > 64 || 8 * g.R > 64) return false;
+  const int n_bt = (B + kBM - 1) / kBM;
+  if (2 * n_bt * (H / kU) > rec::sm_count()) return false;
+  return bptt3_smem_bytes(H) <= 227 * 1024;
+}
+inline size_t bptt3_dzx_bytes(int B, int H, int steps) { return (size_t)2 * steps * (bp16(B) / kBM) * (H / kU) * kAChunk; }
+inline size_t bptt3_pws_floats(int B, int H) {
+  const Bptt3Geo g = bptt3_geo(H);
+  return (size_t)2 * 2 * (bp16(B) / kBM) * (H / kU) * g.R * (kPiece / 4);
+}
+
+// persistent per-engine state of the kernel: tags of the partial workspace, per-layer dz scale
+struct Bptt3Scale { int* dev = nullptr; int cur = 0; };      // dev: [2][2] ints {max bits, exponent}
+
+// BPTT of one BiLSTM layer.  Wh16[d]: fp16 copies of Wh [H units, 4H permuted gate columns]; dzx / pws: workspaces of at
+// least bptt3_dzx_bytes / bptt3_pws_floats; tags / scale: state carried between launches.
+inline void rec_backward3(cudaStream_t st, float* const gates[2], const float* const cs[2], const float* dhs,
+                          const __half* const Wh16[2], const int* lens2, const float* dc_inject, int ldi, const int* inject_t,
+                          unsigned char* dzx, float* pws, size_t pws_floats, BpttTags& tags, Bptt3Scale& scale, int steps, int B,
+                          int H) {
+  Bptt3P p{};
+  const Bptt3Geo g = bptt3_geo(H);
+  for (int d = 0; d < 2; ++d) p.gates[d] = gates[d];
+  p.lens2 = lens2; p.dc_inject = dc_inject; p.ldi = ldi; p.inject_t = inject_t;
+  p.dzx = dzx; p.pws = pws; p.has_dhs = dhs != nullptr;
+  p.steps = steps; p.B = B; p.H = H; p.n_bt = (B + kBM - 1) / kBM; p.n = H / kU; p.G = g.G; p.R = g.R;
+  static const int force = getenv("E2T_REC_DBGSKIP") ? (atoi(getenv("E2T_REC_DBGSKIP")) & 4) : 0;
+  p.dbg_force = force;
+  Bptt3Maps maps;
+  const i64 dg[3] = {4 * (i64)H, B, steps}, sg[3] = {1, 4 * (i64)H, (i64)B * 4 * H};
+  const i64 dc[3] = {H, B, steps}, sc[3] = {1, H, (i64)B * H};
+  const i64 dh[3] = {2 * (i64)H, B, steps}, sh[3] = {1, 2 * (i64)H, (i64)B * 2 * H};
+  const int bg[3] = {4 * kUT, kBM, 1}, bs[3] = {kU, kBM, 1};
+  for (int d = 0; d < 2; ++d) {
+    maps.w[d] = make_map_f16(Wh16[d], H, 4 * (i64)H, 4 * (i64)H, 16 * g.R, kKC);
+    maps.gates[d] = make_map_f32_3d(gates[d], dg, sg, bg, 128);
+    maps.cs[d] = make_map_f32_3d(cs[d], dc, sc, bs, 64);
+  }
+  maps.dhs = make_map_f32_3d(dhs ? dhs : cs[0], dhs ? dh : dc, dhs ? sh : sc, bs, 64);
+  if (tags.n_bt != p.n_bt || tags.H != H) {
+    // new geometry: the slots hold tags of another layout -- start from all-zero tags, next expected tag = 1
+    E2T_CHECK(cudaMemsetAsync(pws, 0, pws_floats * sizeof(float), st));
+    tags.epoch[0] = tags.epoch[1] = 1;
+    tags.n_bt = p.n_bt; tags.H = H;
+  }
+  p.epoch0 = tags.epoch[0]; p.epoch1 = tags.epoch[1];
+  tags.epoch[0] += (uint32_t)(steps / 2);            // steps - 1 partials: ceil on parity 0, floor on parity 1
+  tags.epoch[1] += (uint32_t)((steps - 1) / 2);
+  p.scale_in = scale.dev + 2 * scale.cur;
+  p.scale_out = scale.dev + 2 * (scale.cur ^ 1);
+  scale.cur ^= 1;
+  E2T_CHECK(cudaMemsetAsync(p.scale_out, 0, sizeof(int), st));
+  E2T_CHECK(cudaMemsetAsync(dzx, 0xFF, bptt3_dzx_bytes(B, H, steps), st));
+  static int dbg_left = getenv("E2T_REC_DEBUG") ? atoi(getenv("E2T_REC_DEBUG")) : 0;
+  p.dbg = nullptr;
+  if (dbg_left > 0) {
+    E2T_CHECK(cudaMalloc(&p.dbg, (size_t)(steps + 1) * kDbg * sizeof(long long)));
+    E2T_CHECK(cudaMemsetAsync(p.dbg, 0, (size_t)(steps + 1) * kDbg * sizeof(long long), st));
+  }
+  static int* trap_host = nullptr;
+  static int* trap_dev = nullptr;
+  static const bool trapinfo = getenv("E2T_REC_TRAPINFO") != nullptr;
+  if (trapinfo && !trap_host) {
+    E2T_CHECK(cudaHostAlloc(&trap_host, 64, cudaHostAllocMapped));
+    memset(trap_host, 0, 64);
+    E2T_CHECK(cudaHostGetDevicePointer(&trap_dev, trap_host, 0));
+  }
+  p.trap_rec = trapinfo ? trap_dev : nullptr;
+  auto kfn = k_lstm_bptt3;
+  const size_t smem = bptt3_smem_bytes(H);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    E2T_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * p.n_bt * p.n)); cfg.blockDim = dim3(kThreads16);
+  cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeCooperative; attrs[0].val.cooperative = 1;   // all CTAs co-resident
+  cfg.attrs = attrs; cfg.numAttrs = 1;
+  E2T_CHECK(cudaLaunchKernelEx(&cfg, kfn, maps, p));
+  if (trapinfo) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess)
+      fprintf(stderr, "[rec bptt3 TRAP] %s: site=%d (1 probe1, 2 acc_full, 5 weights, 6/9 vbar1, 7 a_full, 8 in_bar, 10 probe2, 11 pfree, 12 vbar2, "
+                      "13 p_bar) block=%d thread=%d step=%d chunk=%d extra=0x%x (steps=%d B=%d H=%d G=%d R=%d)\n",
+              cudaGetErrorString(e), trap_host[0], trap_host[1], trap_host[2], trap_host[3], trap_host[4], (unsigned)trap_host[5], steps, B, H,
+              g.G, g.R);
+    E2T_CHECK(e);
+  }
+  if (p.dbg) {
+    --dbg_left;
+    std::vector<long long> hst((size_t)(steps + 1) * kDbg);
+    E2T_CHECK(cudaStreamSynchronize(st));
+    E2T_CHECK(cudaMemcpy(hst.data(), p.dbg, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.dbg);
+    fprintf(stderr, "[rec bptt3] steps=%d B=%d H=%d grid=%u G=%d R=%d (cycles of CTA 0, rel. to the end of the step's dz probe)\n"
+                    "  step  repulls ->chunks_asked ->mma_issued ->acc_seen ->pieces_stored ->piece_probe_done ->pieces_asked "
+                    "->pieces_seen(next) ->dz_published(next) | step_total\n",
+            steps, B, H, cfg.gridDim.x, g.G, g.R);
+    for (int q = 1; q + 2 < steps; ++q) {
+      const long long* e = &hst[(size_t)q * kDbg];
+      const long long* nx = e + kDbg;
+      const long long prev = q > 1 ? hst[(size_t)(q - 1) * kDbg] : 0;
+      fprintf(stderr, "  %4d  %4lld %8lld %8lld %8lld %8lld %8lld %8lld %8lld %8lld | %8lld\n", q, e[9], e[1] - e[0], e[2] - e[0], e[3] - e[0],
+              e[4] - e[0], e[5] - e[0], e[6] - e[0], nx[7] - e[0], nx[8] - e[0], prev ? e[0] - prev : 0);
+    }
+  }
+}
+
+}  // namespace rec16

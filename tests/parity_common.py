@@ -28,12 +28,14 @@ TWO_SUBJ = dict(subnet_ids=(400, 401), subnet_C=(6, 10), subnet_W=(4, 3), E=5, H
 FULL = dict(subnet_ids=(400,), subnet_C=(256,), subnet_W=(12,), E=100, H=(400, 400, 400), D=150, Hd=800, V=1806)
 
 # Tolerances = <= 10x the errors measured on B200 (profiles/parity_r2.json), relative to each tensor's largest entry:
-#   fp32 CUDA-core backend ("simt"): measured loss <= 1.2e-7, state <= 5.5e-7, gradients <= 6e-7
+#   fp32 CUDA-core backend ("simt"): measured loss <= 1.2e-7, state <= 5.5e-7, gradients <= 6e-7 (attention: 4.1e-5 on the
+#   Bahdanau query weights with dropout .1/.5, 7.9e-6 without)
 #   tensor-core backend ("auto"; 11-bit-significand operands, fp32 accumulate), small geometries: loss <= 1.0e-5,
 #   state <= 1.3e-3, gradients <= 3.0e-3; config 2 (3 layers x 34 steps, K up to 3072): see FULL_TOL
-SIMT_TOL = dict(loss=1e-6, state=5e-6, grad=2e-5)      # attention tensors reach 7.9e-6
+SIMT_TOL = dict(loss=1e-6, state=5e-6, grad=2e-4)
 TC_TOL = dict(loss=1e-4, state=1e-2, grad=3e-2)
-FULL_TOL = dict(loss=2e-5, state=1e-2, grad=3e-2, logp=5e-3, beam_score=1e-2)
+# (log-probabilities of the TRAINED model: logits an order of magnitude larger than with random weights, measured 8.1e-3)
+FULL_TOL = dict(loss=2e-5, state=1e-2, grad=3e-2, logp=5e-3, logp_trained=3e-2, beam_score=1e-2)
 
 
 def tols(backend):
@@ -216,7 +218,7 @@ def check_saliency(lib, geo, B, T, L, tol=2e-4, backend="simt", which="decoder",
 
 
 def check_decode(lib, geo, B, T, max_len, beam=0, backend="simt", temperature=0.7, use_ema=False, margin=1e-3,
-                 logp_tol=2e-3, score_tol=5e-3, name=None, x=None, eng=None):
+                 logp_tol=2e-3, score_tol=5e-3, name=None, x=None, eng=None, require_separated=True):
     """Greedy (beam = 0) or beam decode through the C-ABI against the oracle.  Margin-aware: rows whose oracle top-2
     logit gap at some live step is below `margin` may legitimately pick the other token; all others must be IDENTICAL
     (north_star: "decoded token sequences identical under greedy decode").  Achieved errors are recorded under `name`."""
@@ -265,7 +267,7 @@ def check_decode(lib, geo, B, T, max_len, beam=0, backend="simt", temperature=0.
         record(rec_name, score_abs=e_score, separated_beams=float(sep.mean()),
                beams_identical=float((toks == t_ref.numpy()).all(2).mean()), score_tol=score_tol * tscale)
         assert e_score < score_tol * tscale
-        assert sep.any()
+        assert sep.any() or not require_separated
         assert (toks[sep] == t_ref.numpy()[sep]).all()
         assert (np.diff(scores, axis=1) <= 1e-6).all(), "beams must be best-first"
     if own:

@@ -71,7 +71,7 @@ def test_config2_decode_random_weights(gpu_lib):
     pc.check_decode(gpu_lib, pc.FULL, B, T, 12, backend="auto", temperature=0.384, name="config2/greedy/random_weights/B256",
                     logp_tol=pc.FULL_TOL["logp"])
     pc.check_decode(gpu_lib, pc.FULL, 32, T, 12, beam=8, backend="auto", temperature=0.384,
-                    name="config2/beam8/random_weights/B32", score_tol=pc.FULL_TOL["beam_score"])
+                    name="config2/beam8/random_weights/B32", score_tol=pc.FULL_TOL["beam_score"], require_separated=False)
 
 
 def test_config2_trained_weights_greedy_identical(gpu_lib):
@@ -108,11 +108,11 @@ def test_config2_trained_weights_greedy_identical(gpu_lib):
     e_logp = float(np.abs(logp[safe] - lp_ref.numpy()[safe]).max())
     pc.record("config2/greedy/trained_weights/B256", safe_rows=float(safe.mean()), rows_identical=float((toks == tr).all(1).mean()),
               logp_abs=e_logp, median_live_gap=float(np.median(gap[live])), oracle_token_accuracy=token_acc,
-              logp_tol=pc.FULL_TOL["logp"])
+              logp_tol=pc.FULL_TOL["logp_trained"])
     assert token_acc > 0.5, token_acc
     assert safe.mean() > 0.9, safe.mean()
     assert (toks[safe] == tr[safe]).all()
-    assert e_logp < pc.FULL_TOL["logp"]
+    assert e_logp < pc.FULL_TOL["logp_trained"]
     # B = 1: eager twice, then CUDA-graph replays -- every call must return the oracle's row
     rows = [int(r) for r in np.where(safe)[0][:6]]
     n0 = eng.counter("decode_graph_replays")
@@ -121,7 +121,7 @@ def test_config2_trained_weights_greedy_identical(gpu_lib):
         for _ in range(3):
             t1, lp1 = eng.greedy_decode(np.ascontiguousarray(x[r:r + 1]), None, max_len=12, temperature=temperature, use_ema=True)
             same.append(bool((t1[0] == tr[r]).all()))
-            assert np.abs(lp1[0] - lp_ref.numpy()[r]).max() < pc.FULL_TOL["logp"]
+            assert np.abs(lp1[0] - lp_ref.numpy()[r]).max() < pc.FULL_TOL["logp_trained"]
     pc.record("config2/greedy/trained_weights/B1_graph", rows=len(rows), calls=len(same), identical=float(np.mean(same)),
               graph_replays=float(eng.counter("decode_graph_replays") - n0))
     assert all(same)
