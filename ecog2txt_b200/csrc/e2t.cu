@@ -1079,7 +1079,7 @@ void lstm_layer_backward(e2t_handle* h, int H, const float* K, int In, float* ga
 // weight / bias / input gradients of one LSTM direction after its dz is known.
 void lstm_layer_wgrads(e2t_handle* h, const float* in, int ld_in, int In, int H, const float* K, float* dK, float* db,
                        const float* dz, const float* hs, int ldh, int col0, int steps, int B, bool reverse,
-                       const float* h_init, float* d_in, int ld_din, float beta_din) {
+                       const float* h_init, float* d_in, int ld_din, float beta_din, const float* db_part = nullptr, int n_part = 0) {
   const i64 rows = (i64)steps * B;
   // dWx [In,4H] = in^T dz
   gemm(h, in, 1, ld_in, dz, 4 * H, 1, dK, 4 * H, In, 4 * H, (int)rows, nullptr, 0.f);
@@ -1108,7 +1108,9 @@ void lstm_layer_wgrads(e2t_handle* h, const float* in, int ld_in, int In, int H,
     if (h_init)   // decoder: first step's previous state is the bridge state
       gemm(h, h_init, 1, H, dz0, 4 * H, 1, dWh, 4 * H, H, 4 * H, B, nullptr, 1.f);
   }
-  batch_colsum(h, dz, rows, 4 * H, 4 * H, db);
+  // bias gradient: column sums of dz (or of the per-batch-tile partials the persistent BPTT kernel left)
+  if (db_part) batch_colsum(h, db_part, n_part, 4 * H, 4 * H, db);
+  else batch_colsum(h, dz, rows, 4 * H, 4 * H, db);
   // d_in [rows, In] (+)= dz Wx^T ; canonical K rows [In,4H] are the K-major B operand
   if (d_in) gemm(h, dz, 4 * H, 1, K, 1, 4 * H, d_in, ld_din, (int)rows, In, 4 * H, nullptr, beta_din);
 }

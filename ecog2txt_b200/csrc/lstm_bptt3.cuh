@@ -83,6 +83,9 @@ __device__ __forceinline__ int bptt3_scale_exp(const int* in) {
   return max(-60, min(60, e));
 }
 
+// (10 warps are allocated as 12 -- registers come in units of 4 warps -- so 168 registers per thread is all there is;
+// __maxnreg__(192) compiles without spills but is refused by the cooperative launch.  Summing the bias gradient in 32 more
+// registers per thread therefore spills: measured 9.6 instead of 8.1 us per step, more than the column sums it saves)
 __global__ void __launch_bounds__(kThreads16, 1)
 k_lstm_bptt3(const __grid_constant__ Bptt3Maps maps, Bptt3P p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -191,30 +194,35 @@ k_lstm_bptt3(const __grid_constant__ Bptt3Maps maps, Bptt3P p) {
     for (int q = 0; q + 1 < steps; ++q) {
       {
         const unsigned char* base = dz_chain + (size_t)q * dz_step + (size_t)(a * G) * kAChunk;
-        uint32_t pending = (lane < n1 ? 1u : 0u) | (32 + lane < n1 ? 2u : 0u);
-        const long long t0 = clock64();
-        while (pending) {
-          uint32_t v[2];
+        // words 8 c .. 8 c + 7 belong to member c: its chunk is pulled as soon as they are in
+        for (bool first = true;; first = false) {
+          uint32_t pending = first ? ((lane < n1 ? 1u : 0u) | (32 + lane < n1 ? 2u : 0u)) : 0u;
+          uint32_t pulled = 0;
+          const long long t0 = clock64();
+          while (pulled != (1u << G) - 1u) {
+            uint32_t v[2];
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            if (pending & (1u << k)) v[k] = ld_cg_u32(base + off1[k]);
+            for (int k = 0; k < 2; ++k)
+              if (pending & (1u << k)) v[k] = ld_cg_u32(base + off1[k]);
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            if ((pending & (1u << k)) && v[k] != kFill32) pending &= ~(1u << k);
-          if (pending && clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 1, q, 0, (int)pending);
-        }
-        __syncwarp();
-        if (dbg && lane == 0) dbg[q * kDbg + 0] = clock64();
-        for (;;) {
-          if (elect_one()) {
+            for (int k = 0; k < 2; ++k)
+              if ((pending & (1u << k)) && v[k] != kFill32) pending &= ~(1u << k);
+            const uint32_t seen0 = __ballot_sync(0xffffffffu, !(pending & 1u)), seen1 = __ballot_sync(0xffffffffu, !(pending & 2u));
             for (int c = 0; c < G; ++c) {
-              const uint32_t fb = smem_u32(&a_full[c]);
-              mbar_expect_tx(fb, kAChunk);
-              bulk_load(smem_u32(smem_a + (size_t)c * kAChunk), base + (size_t)c * kAChunk, kAChunk, fb);
+              if (pulled & (1u << c)) continue;
+              if ((((c < 4 ? seen0 : seen1) >> (8 * (c & 3))) & 0xFFu) != 0xFFu) continue;
+              if (dbg && lane == 0 && pulled == 0) dbg[q * kDbg + 1] = clock64();
+              pulled |= 1u << c;
+              if (elect_one()) {
+                const uint32_t fb = smem_u32(&a_full[c]);
+                mbar_expect_tx(fb, kAChunk);
+                bulk_load(smem_u32(smem_a + (size_t)c * kAChunk), base + (size_t)c * kAChunk, kAChunk, fb);
+              }
+              __syncwarp();
             }
+            if (clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 1, q, 0, (int)pending);
           }
-          __syncwarp();
-          if (dbg && lane == 0) dbg[q * kDbg + 1] = clock64();
+          if (dbg && lane == 0 && first) dbg[q * kDbg + 0] = clock64();
           mbar_wait_rec(smem_u32(vbar1), round1 & 1u, p.trap_rec, 6, q, 0);
           ++round1;
           if (*verdict1 == 0u) break;
@@ -225,30 +233,34 @@ k_lstm_bptt3(const __grid_constant__ Bptt3Maps maps, Bptt3P p) {
         const int pq = q & 1;
         const uint32_t tw = ((pq ? p.epoch1 : p.epoch0) + (uint32_t)(q >> 1)) & 1u;
         const unsigned char* base = reinterpret_cast<const unsigned char*>(pw_chain + (size_t)pq * par_stride + (size_t)j * R * (kPiece / 4));
-        uint32_t pending = (lane < n2 ? 1u : 0u) | (32 + lane < n2 ? 2u : 0u);
-        const long long t0 = clock64();
-        while (pending) {
-          uint32_t v[2];
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-            if (pending & (1u << k)) v[k] = ld_cg_u32(base + off2[k]);
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-            if ((pending & (1u << k)) && (v[k] & 1u) == tw) pending &= ~(1u << k);
-          if (pending && clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 10, q, 0, (int)pending);
-        }
-        __syncwarp();
-        if (dbg && lane == 0) dbg[q * kDbg + 5] = clock64();
-        // this CTA's own pieces of the step have left the stage
+        // this CTA's own pieces of the step must have left the stage before anything lands in it
         mbar_wait_rec(smem_u32(pfree_bar), (uint32_t)q & 1u, p.trap_rec, 11, q, 0);
-        for (;;) {
-          if (elect_one()) {
-            const uint32_t fb = smem_u32(p_bar);
-            mbar_expect_tx(fb, (uint32_t)R * kPiece);
-            bulk_load(smem_u32(smem_p), base, (uint32_t)R * kPiece, fb);
-          }
+        for (bool first = true;; first = false) {
+          uint32_t pending = first ? ((lane < n2 ? 1u : 0u) | (32 + lane < n2 ? 2u : 0u)) : 0u;
+          uint32_t pulled = 0;
+          if (elect_one()) mbar_expect_tx(smem_u32(p_bar), (uint32_t)R * kPiece);
           __syncwarp();
-          if (dbg && lane == 0) dbg[q * kDbg + 6] = clock64();
+          const long long t0 = clock64();
+          while (pulled != (1u << R) - 1u) {
+            uint32_t v[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              if (pending & (1u << k)) v[k] = ld_cg_u32(base + off2[k]);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              if ((pending & (1u << k)) && (v[k] & 1u) == tw) pending &= ~(1u << k);
+            const uint32_t seen0 = __ballot_sync(0xffffffffu, !(pending & 1u)), seen1 = __ballot_sync(0xffffffffu, !(pending & 2u));
+            for (int c = 0; c < R; ++c) {
+              if (pulled & (1u << c)) continue;
+              if ((((c < 4 ? seen0 : seen1) >> (8 * (c & 3))) & 0xFFu) != 0xFFu) continue;
+              if (dbg && lane == 0 && pulled == 0) dbg[q * kDbg + 6] = clock64();
+              pulled |= 1u << c;
+              if (elect_one()) bulk_load(smem_u32(smem_p) + (uint32_t)c * kPiece, base + (size_t)c * kPiece, kPiece, smem_u32(p_bar));
+              __syncwarp();
+            }
+            if (clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 10, q, 0, (int)pending);
+          }
+          if (dbg && lane == 0 && first) dbg[q * kDbg + 5] = clock64();
           mbar_wait_rec(smem_u32(vbar2), round2 & 1u, p.trap_rec, 12, q, 0);
           ++round2;
           if (*verdict2 == 0u) break;
@@ -348,7 +360,9 @@ k_lstm_bptt3(const __grid_constant__ Bptt3Maps maps, Bptt3P p) {
             }
           }
           const bool force = p.dbg_force && q % 5 == 0 && tries == 0;
+          if (dbg && threadIdx.x == 0) dbg[q * kDbg + 10] = clock64();
           const bool redo = (bar_red_or(3, kWorkThreads, (tagbad & 1u) != 0u) || force) && tries < kMaxRedo;
+          if (dbg && threadIdx.x == 0) dbg[q * kDbg + 11] = clock64();
           if (threadIdx.x == 0) {
             *verdict2 = redo ? 1u : 0u;
             rec::mbar_arrive(smem_u32(vbar2));
@@ -384,6 +398,7 @@ k_lstm_bptt3(const __grid_constant__ Bptt3Maps maps, Bptt3P p) {
 #pragma unroll
         for (int e = 0; e < kUT; ++e) carry[e] = 0.f;
       }
+      if (dbg && threadIdx.x == 0) dbg[q * kDbg + 12] = clock64();
 #pragma unroll
       for (int e = 0; e < kUT; ++e) cv[e] = cpv[e];         // c(t_prev) is the next step's c(t)
       // ---- hop 1: this thread's four 16-byte pieces of the CTA's dz chunk (zeros for padding rows: the fill must go)
@@ -476,7 +491,7 @@ inline size_t bptt3_smem_bytes(int H) {
 inline bool bptt3_supported(int B, int H) {
   if (H % kU != 0 || H < 4 * kU || H > 512 || B < 1) return false;
   const Bptt3Geo g = bptt3_geo(H);
-  if (g.G < 2 || g.R < 1 || 16 * g.R > 256 || 8 * g.G > 64 || 8 * g.R > 64) return false;
+  if (g.G < 2 || g.R < 1 || 16 * g.R > 256 || g.G > 8 || g.R > 8) return false;
   const int n_bt = (B + kBM - 1) / kBM;
   if (2 * n_bt * (H / kU) > rec::sm_count()) return false;
   return bptt3_smem_bytes(H) <= 227 * 1024;
@@ -574,15 +589,16 @@ inline void rec_backward3(cudaStream_t st, float* const gates[2], const float* c
     E2T_CHECK(cudaMemcpy(hst.data(), p.dbg, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(p.dbg);
     fprintf(stderr, "[rec bptt3] steps=%d B=%d H=%d grid=%u G=%d R=%d (cycles of CTA 0, rel. to the end of the step's dz probe)\n"
-                    "  step  repulls ->chunks_asked ->mma_issued ->acc_seen ->pieces_stored ->piece_probe_done ->pieces_asked "
-                    "->pieces_seen(next) ->dz_published(next) | step_total\n",
+                    "  step  repulls first_chunk_asked ->mma_issued ->acc_seen ->pieces_stored ->first_piece_asked ->last_piece_asked "
+                    "->pieces_seen(next) ->summed ->agreed ->gates_done ->dz_published(next) | step_total\n",
             steps, B, H, cfg.gridDim.x, g.G, g.R);
     for (int q = 1; q + 2 < steps; ++q) {
       const long long* e = &hst[(size_t)q * kDbg];
       const long long* nx = e + kDbg;
       const long long prev = q > 1 ? hst[(size_t)(q - 1) * kDbg] : 0;
-      fprintf(stderr, "  %4d  %4lld %8lld %8lld %8lld %8lld %8lld %8lld %8lld %8lld | %8lld\n", q, e[9], e[1] - e[0], e[2] - e[0], e[3] - e[0],
-              e[4] - e[0], e[5] - e[0], e[6] - e[0], nx[7] - e[0], nx[8] - e[0], prev ? e[0] - prev : 0);
+      fprintf(stderr, "  %4d  %4lld %8lld %8lld %8lld %8lld %8lld %8lld %8lld %8lld %8lld %8lld %8lld | %8lld\n", q, e[9], e[1] - e[0], e[2] - e[0],
+              e[3] - e[0], e[4] - e[0], e[6] - e[0], e[5] - e[0], nx[7] - e[0], nx[10] - e[0], nx[11] - e[0], nx[12] - e[0], nx[8] - e[0],
+              prev ? e[0] - prev : 0);
     }
   }
 }

@@ -276,13 +276,17 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
       const int t = reverse ? steps - 1 - s : s;
       const int t_src = reverse ? t + 1 : t - 1;
       const unsigned char* base = hx_chain + (size_t)t_src * tile_stride;
-      {
-        uint32_t pending = 0;
+      // words 32 kc .. 32 kc + 31 belong to the four producer slices of chunk kc: a chunk is pulled as soon as ITS producers
+      // are in, so that when the slowest CTA of the chain arrives only one chunk (and its MMAs) is still outstanding
+      for (bool first = true;; first = false) {
+        uint32_t pending = 0, pulled = 0;
+        if (first) {
 #pragma unroll
-        for (int k = 0; k < kProbes; ++k)
-          if (32 * k + lane < n_probe) pending |= 1u << k;
+          for (int k = 0; k < kProbes; ++k)
+            if (32 * k + lane < n_probe) pending |= 1u << k;
+        }
         const long long t0 = clock64();
-        while (pending) {
+        while (pulled != (1u << NKC) - 1u) {
           uint32_t v[kProbes];
 #pragma unroll
           for (int k = 0; k < kProbes; ++k)
@@ -290,22 +294,22 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
 #pragma unroll
           for (int k = 0; k < kProbes; ++k)
             if ((pending & (1u << k)) && v[k] != kFill32) pending &= ~(1u << k);
-          if (pending && clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 1, s, 0, (int)pending);
-        }
-        __syncwarp();
-      }
-      if (dbg && lane == 0) dbg[s * kDbg + 0] = clock64();
-      for (;;) {
-        // (the previous tile's MMAs are done and its accumulator has been read: the verdict said so)
-        if (elect_one()) {
+#pragma unroll
           for (int kc = 0; kc < NKC; ++kc) {
-            const uint32_t fb = smem_u32(&a_full[kc]);
-            mbar_expect_tx(fb, kAChunk);
-            bulk_load(smem_u32(smem_a + (size_t)kc * kAChunk), base + (size_t)kc * kAChunk, kAChunk, fb);
+            if (pulled & (1u << kc)) continue;
+            if (!__all_sync(0xffffffffu, kc >= kProbes || !(pending & (1u << kc)))) continue;
+            if (dbg && lane == 0 && pulled == 0) dbg[s * kDbg + 1] = clock64();
+            pulled |= 1u << kc;
+            if (elect_one()) {
+              const uint32_t fb = smem_u32(&a_full[kc]);
+              mbar_expect_tx(fb, kAChunk);
+              bulk_load(smem_u32(smem_a + (size_t)kc * kAChunk), base + (size_t)kc * kAChunk, kAChunk, fb);
+            }
+            __syncwarp();
           }
+          if (clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 1, s, 0, (int)pending);
         }
-        __syncwarp();
-        if (dbg && lane == 0) dbg[s * kDbg + 1] = clock64();
+        if (dbg && lane == 0 && first) dbg[s * kDbg + 0] = clock64();
         mbar_wait_rec(smem_u32(verdict_bar), round & 1u, p.trap_rec, 6, s, 0);
         ++round;
         if (*verdict == 0u) break;
@@ -616,8 +620,8 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
     E2T_CHECK(cudaMemcpy(hst.data(), p.dbg, hst.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(p.dbg);
     const int nkc = nkc16(H);
-    fprintf(stderr, "[rec fwd16] steps=%d B=%d H=%d grid=%d (cycles of CTA 0, rel. to the end of the step's probe)\n"
-                    "  step  repulls ->copies_issued [chunk's MMAs issued ...] ->acc_seen ->h_stored ->staged ->stores_issued | step_total\n",
+    fprintf(stderr, "[rec fwd16] steps=%d B=%d H=%d grid=%d (cycles of CTA 0, rel. to the request of the step's LAST chunk)\n"
+                    "  step  repulls first_chunk_asked [chunk's MMAs issued ...] ->acc_seen ->h_stored ->staged ->stores_issued | step_total\n",
             steps, B, H, 2 * p.n_bt * p.n_slices);
     for (int s = 1; s + 1 < steps; ++s) {
       const long long* e = &hst[(size_t)s * kDbg];
