@@ -46,6 +46,15 @@ struct TensorInfo {
   bool trainable = true;
 };
 
+// Exchange buffer of a persistent recurrent kernel (training path): must be all 0xFF when the kernel starts.  Instead of a
+// memset in front of every launch (54 MB for the BPTT kernel: ~15 us on the critical stream, three times per step), the
+// bytes a launch dirtied are wiped on a side stream while the main stream goes on; the next launch waits for that event.
+struct XBuf {
+  unsigned char* p = nullptr; size_t bytes = 0;
+  cudaEvent_t used = nullptr, clean = nullptr;
+  bool pending = false;
+};
+
 struct EncLayer {
   int In, H;
   i64 K[2], b[2];           // offsets into the flat parameter buffers
@@ -67,6 +76,7 @@ struct EncLayer {
   // layer's dz scale state
   bool bptt3 = false;
   void* Wh16[2] = {nullptr, nullptr};
+  XBuf hx_train, dzx_train;            // per-layer exchange buffers of the training path (cleaned on the side stream)
   int* bptt3_scale = nullptr; int bptt3_scale_cur = 0;
 };
 
@@ -158,7 +168,6 @@ struct e2t_handle {
   rec16::BpttTags bptt_tags{{0, 0}, -1, -1};         // tag state of rec_pws (k_lstm_bptt2)
   rec16::BpttTags bptt3_tags{{0, 0}, -1, -1};        // tag state of rec_pws3 (k_lstm_bptt3)
   float* rec_pws3 = nullptr; i64 rec_pws3_n = 0;     // partial pieces of k_lstm_bptt3
-  unsigned char* rec_dzx = nullptr; i64 rec_dzx_n = 0;   // fp16 dz exchange slots of k_lstm_bptt3
 #endif
   int* rec_counters = nullptr;   // arrival counters of the persistent recurrent kernels [2][n_bt][T2m]
   int64_t n_launch_rec = 0, n_graph_replays = 0;
@@ -173,6 +182,7 @@ struct e2t_handle {
 #endif
   // double-buffered input staging (e2t_stage_inputs): slot 0 aliases d_x / d_lens_in / d_y
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t clean_stream = nullptr;   // wipes the exchange buffers of the recurrent kernels behind their launches
   float* st_x[2] = {nullptr, nullptr}; int* st_lens[2] = {nullptr, nullptr}; int* st_y[2] = {nullptr, nullptr};
   bool st_has_lens[2] = {false, false}, st_has_y[2] = {false, false};
   int st_B[2] = {0, 0}, st_T[2] = {0, 0}, st_L[2] = {0, 0}, st_subnet[2] = {0, 0};
@@ -200,6 +210,28 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // launches
 // ------------------------------------------------------------------------------------------------
+#ifndef E2T_EMU
+void xbuf_alloc(e2t_handle* h, XBuf& x, size_t bytes) {
+  x.p = h->alloc<unsigned char>((i64)bytes); x.bytes = bytes;
+  E2T_CHECK(cudaMemset(x.p, 0xFF, bytes));
+  E2T_CHECK(cudaEventCreateWithFlags(&x.used, cudaEventDisableTiming));
+  E2T_CHECK(cudaEventCreateWithFlags(&x.clean, cudaEventDisableTiming));
+}
+// before the launch: the wipe of the previous launch's bytes must have finished
+void xbuf_acquire(e2t_handle* h, XBuf& x) {
+  if (x.pending) E2T_CHECK(cudaStreamWaitEvent(h->stream, x.clean, 0));
+}
+// behind the launch: wipe what it wrote, off the main stream
+void xbuf_release(e2t_handle* h, XBuf& x, size_t dirtied) {
+  if (!h->clean_stream) E2T_CHECK(cudaStreamCreateWithFlags(&h->clean_stream, cudaStreamNonBlocking));
+  E2T_CHECK(cudaEventRecord(x.used, h->stream));
+  E2T_CHECK(cudaStreamWaitEvent(h->clean_stream, x.used, 0));
+  E2T_CHECK(cudaMemsetAsync(x.p, 0xFF, std::min(dirtied, x.bytes), h->clean_stream));
+  E2T_CHECK(cudaEventRecord(x.clean, h->clean_stream));
+  x.pending = true;
+}
+#endif
+
 #ifndef E2T_EMU
 inline void prof_begin(e2t_handle* h, const char* label = "", int M = 0, int N = 0, int K = 0) {
   if (!h->prof) return;
@@ -540,6 +572,7 @@ void build_workspace(e2t_handle* h) {
     if (L.rec16) {
       for (int d = 0; d < 2; ++d) L.WhT16[d] = h->alloc<uint16_t>((i64)4 * L.H * rec16::hp16(L.H));
       h->rec_hx16_n = std::max<i64>(h->rec_hx16_n, (i64)rec16::hx16_halves((int)Bm, L.H, (int)T2));
+      xbuf_alloc(h, L.hx_train, rec16::hx16_halves((int)Bm, L.H, (int)T2) * 2);
     }
     static const bool bptt_old = getenv("E2T_BPTT_V1") != nullptr;   // A/B switch: first-generation BPTT kernel
     L.bptt3 = L.rec && !bptt_old && rec16::bptt3_supported((int)Bm, L.H);
@@ -548,7 +581,7 @@ void build_workspace(e2t_handle* h) {
       L.bptt3_scale = h->alloc<int>(4);
       const int init[4] = {0, 8, 0, 8};
       E2T_CHECK(cudaMemcpy(L.bptt3_scale, init, sizeof(init), cudaMemcpyHostToDevice));
-      h->rec_dzx_n = std::max<i64>(h->rec_dzx_n, (i64)rec16::bptt3_dzx_bytes((int)Bm, L.H, (int)T2));
+      xbuf_alloc(h, L.dzx_train, rec16::bptt3_dzx_bytes((int)Bm, L.H, (int)T2));
       h->rec_pws3_n = std::max<i64>(h->rec_pws3_n, (i64)rec16::bptt3_pws_floats((int)Bm, L.H));
     }
 #endif
@@ -577,7 +610,6 @@ void build_workspace(e2t_handle* h) {
   }
   if (h->rec_pws_n) h->rec_pws = h->alloc<float>(h->rec_pws_n);
   if (h->rec_hx16_n) h->rec_hx16 = h->alloc<uint16_t>(h->rec_hx16_n);
-  if (h->rec_dzx_n) h->rec_dzx = h->alloc<unsigned char>(h->rec_dzx_n);
   if (h->rec_pws3_n) h->rec_pws3 = h->alloc<float>(h->rec_pws3_n);
   h->rec_counters = h->alloc<int>((i64)2 * cdiv(Bm, 128) * std::max<i64>(T2, Lm));
   h->ld_dec_kt = h->Dp + round_up(c.Hd, 4);
@@ -849,8 +881,15 @@ void encoder_forward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, 
       prof_begin(h, "rec_forward", B, L.H, T2);
       if (L.rec16) {
         const __half* w16[2] = {static_cast<const __half*>(L.WhT16[0]), static_cast<const __half*>(L.WhT16[1])};
-        rec16::rec_forward16(h->stream, L.gates, L.cs, L.hs, drop ? L.hd : nullptr, w16, static_cast<__half*>(h->rec_hx16),
-                             h->d_lens2, T2, B, L.H, dp, 2 * L.H);
+        if (train) {     // per-layer exchange buffer, wiped behind the launch on the side stream
+          xbuf_acquire(h, L.hx_train);
+          rec16::rec_forward16(h->stream, L.gates, L.cs, L.hs, drop ? L.hd : nullptr, w16, reinterpret_cast<__half*>(L.hx_train.p),
+                               h->d_lens2, T2, B, L.H, dp, 2 * L.H, false);
+          xbuf_release(h, L.hx_train, rec16::hx16_halves(B, L.H, T2) * 2);
+        } else {         // inference (may be under CUDA-graph capture): one shared buffer, filled in stream order
+          rec16::rec_forward16(h->stream, L.gates, L.cs, L.hs, drop ? L.hd : nullptr, w16, static_cast<__half*>(h->rec_hx16),
+                               h->d_lens2, T2, B, L.H, dp, 2 * L.H, true);
+        }
       } else {
         rec::rec_forward(h->stream, L.gates, L.cs, L.hs, drop ? L.hd : nullptr, L.KT, L.ldkt, L.In4, h->d_lens2,
                          h->rec_counters, T2, B, L.H, dp, 2 * L.H);
@@ -1247,11 +1286,13 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
       // measured slower (13.4 vs 11.2 us per step, profiles/r2d_*) than the counter hand-off of the first generation
       static const bool bptt_v1 = getenv("E2T_BPTT_V2") == nullptr;
       if (Ly.bptt3) {
+        xbuf_acquire(h, Ly.dzx_train);
         const __half* w16[2] = {static_cast<const __half*>(Ly.Wh16[0]), static_cast<const __half*>(Ly.Wh16[1])};
         rec16::Bptt3Scale sc{Ly.bptt3_scale, Ly.bptt3_scale_cur};
         rec16::rec_backward3(h->stream, Ly.gates, csd, Ly.dhs, w16, h->d_lens2, top ? h->dc0 : nullptr, c.Hd,
-                             top ? h->d_tlast : nullptr, h->rec_dzx, h->rec_pws3, (size_t)h->rec_pws3_n, h->bptt3_tags, sc, T2, B, Ly.H);
+                             top ? h->d_tlast : nullptr, Ly.dzx_train.p, h->rec_pws3, (size_t)h->rec_pws3_n, h->bptt3_tags, sc, T2, B, Ly.H);
         Ly.bptt3_scale_cur = sc.cur;
+        xbuf_release(h, Ly.dzx_train, rec16::bptt3_dzx_bytes(B, Ly.H, T2));
       } else if (!use_allgather && !bptt_v1 && h->rec_pws && rec::bptt_supported(h->Bm, Ly.H))
         rec16::rec_backward_rs2(h->stream, Ly.gates, csd, Ly.dhs, Kd, Ly.In, h->d_lens2, top ? h->dc0 : nullptr, c.Hd,
                                 top ? h->d_tlast : nullptr, h->rec_pws, (size_t)h->rec_pws_n, h->bptt_tags, T2, B, Ly.H);
@@ -1414,6 +1455,9 @@ extern "C" int e2t_destroy(e2t_handle* h) {
   for (cudaEvent_t e : h->bucket_ev) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) { if (h->st_ready[i]) cudaEventDestroy(h->st_ready[i]); if (h->st_done[i]) cudaEventDestroy(h->st_done[i]); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->clean_stream) cudaStreamDestroy(h->clean_stream);
+  for (auto& L : h->enc)
+    for (XBuf* x : {&L.hx_train, &L.dzx_train}) { if (x->used) cudaEventDestroy(x->used); if (x->clean) cudaEventDestroy(x->clean); }
 #endif
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;

@@ -506,7 +506,8 @@ inline size_t bptt3_pws_floats(int B, int H) {
 struct Bptt3Scale { int* dev = nullptr; int cur = 0; };      // dev: [2][2] ints {max bits, exponent}
 
 // BPTT of one BiLSTM layer.  Wh16[d]: fp16 copies of Wh [H units, 4H permuted gate columns]; dzx / pws: workspaces of at
-// least bptt3_dzx_bytes / bptt3_pws_floats; tags / scale: state carried between launches.
+// least bptt3_dzx_bytes / bptt3_pws_floats, dzx ALL 0xFF on entry (the caller wipes it behind the launch, e2t.cu: XBuf);
+// tags / scale: state carried between launches.
 inline void rec_backward3(cudaStream_t st, float* const gates[2], const float* const cs[2], const float* dhs,
                           const __half* const Wh16[2], const int* lens2, const float* dc_inject, int ldi, const int* inject_t,
                           unsigned char* dzx, float* pws, size_t pws_floats, BpttTags& tags, Bptt3Scale& scale, int steps, int B,
@@ -543,7 +544,6 @@ inline void rec_backward3(cudaStream_t st, float* const gates[2], const float* c
   p.scale_out = scale.dev + 2 * (scale.cur ^ 1);
   scale.cur ^= 1;
   E2T_CHECK(cudaMemsetAsync(p.scale_out, 0, sizeof(int), st));
-  E2T_CHECK(cudaMemsetAsync(dzx, 0xFF, bptt3_dzx_bytes(B, H, steps), st));
   static int dbg_left = getenv("E2T_REC_DEBUG") ? atoi(getenv("E2T_REC_DEBUG")) : 0;
   p.dbg = nullptr;
   if (dbg_left > 0) {
@@ -571,7 +571,8 @@ inline void rec_backward3(cudaStream_t st, float* const gates[2], const float* c
   cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attrs[1];
   attrs[0].id = cudaLaunchAttributeCooperative; attrs[0].val.cooperative = 1;   // all CTAs co-resident
-  cfg.attrs = attrs; cfg.numAttrs = 1;
+  static const bool coop = getenv("E2T_REC_NOCOOP") == nullptr;      // A/B: plain launch (the grid fits one wave by construction)
+  cfg.attrs = attrs; cfg.numAttrs = coop ? 1 : 0;
   E2T_CHECK(cudaLaunchKernelEx(&cfg, kfn, maps, p));
   if (trapinfo) {
     cudaError_t e = cudaStreamSynchronize(st);

@@ -402,6 +402,8 @@ k_lstm_fwd16(const __grid_constant__ Fwd16Maps maps, Fwd16P p) {
         for (int i = 0; i < 4 * kUT; ++i) acc[i] = 0.f;
       }
       float hv[kUT];
+      // (one reciprocal for the product of several denominators -- 7 instead of 10 SFU results per unit -- was measured:
+      //  the epilogue of CTA 0 shrank by 270 cycles, the launch got 3 % SLOWER, gpurun_out/r2y; the plain form stays)
       if (valid) {
 #pragma unroll
         for (int e = 0; e < kUT; ++e) {
@@ -548,7 +550,8 @@ inline void fwd16_launch_t(cudaStream_t st, const Fwd16Maps& maps, Fwd16P& p) {
   cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attrs[1];
   attrs[0].id = cudaLaunchAttributeCooperative; attrs[0].val.cooperative = 1;   // all CTAs co-resident
-  cfg.attrs = attrs; cfg.numAttrs = 1;
+  static const bool coop = getenv("E2T_REC_NOCOOP") == nullptr;      // A/B: plain launch (the grid fits one wave by construction)
+  cfg.attrs = attrs; cfg.numAttrs = coop ? 1 : 0;
   E2T_CHECK(cudaLaunchKernelEx(&cfg, kfn, maps, p));
 }
 
@@ -556,7 +559,7 @@ inline void fwd16_launch_t(cudaStream_t st, const Fwd16Maps& maps, Fwd16P& p) {
 // least hx16_halves(B, H, steps) halves.
 inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const cs[2], float* hs, float* hd,
                           const __half* const WhT16[2], __half* hx, const int* lens2, int steps, int B, int H, DropP dp,
-                          int drop_F) {
+                          int drop_F, bool fill_hx = true) {
   Fwd16P p{};
   for (int d = 0; d < 2; ++d) p.gates[d] = gates[d];
   p.hx = hx; p.lens2 = lens2; p.has_hd = hd != nullptr;
@@ -577,7 +580,8 @@ inline void rec_forward16(cudaStream_t st, float* const gates[2], float* const c
   }
   maps.hs = make_map_f32_3d(hs, dh, sh, bs, 64);
   maps.hd = make_map_f32_3d(hd ? hd : hs, dh, sh, bs, 64);
-  E2T_CHECK(cudaMemsetAsync(hx, 0xFF, hx16_halves(B, H, steps) * sizeof(__half), st));
+  // (fill_hx = false: the caller keeps the buffer all-0xFF between launches, e2t.cu: XBuf)
+  if (fill_hx) E2T_CHECK(cudaMemsetAsync(hx, 0xFF, hx16_halves(B, H, steps) * sizeof(__half), st));
   static int dbg_left = getenv("E2T_REC_DEBUG") ? atoi(getenv("E2T_REC_DEBUG")) : 0;
   p.dbg = nullptr;
   if (dbg_left > 0) {
