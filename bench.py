@@ -257,7 +257,7 @@ def main():
         eng.train_step_grads(x, None, y, seed=i, want_loss=False)
         reduce_and_step(ntok_dev[i % NPOOL])
 
-    staged = {"next": None}
+    staged = {"next": None, "posted": None, "loss": None}
 
     def step_host(i):
         # end to end through the public API with HOST buffers: the H2D copy of THIS step's batch was started (pinned
@@ -270,10 +270,20 @@ def main():
         staged["next"] = i + 1
         eng.train_step_grads_staged(i & 1, seed=i, want_loss=False)
         reduce_and_step(ntok_dev[i % NPOOL])
-        loss, ntok, _, _ = eng.last_losses()                                     # D2H loss, ntok (synchronises)
-        return loss
+        # D2H of this step's loss + token count: posted behind the step (page-locked ring), read by the host one step
+        # later -- every step's result reaches the host inside the timed region, the device is never left idle for it
+        eng.post_losses(i & 3)
+        if staged["posted"] is not None:
+            staged["loss"] = eng.fetch_losses(staged["posted"])[0]
+        staged["posted"] = i & 3
+        return staged["loss"]
 
-    def timed(fn, steps, warmup):
+    def drain_host():
+        if staged["posted"] is not None:
+            staged["loss"] = eng.fetch_losses(staged["posted"])[0]
+            staged["posted"] = None
+
+    def timed(fn, steps, warmup, drain=None):
         for i in range(warmup):
             fn(i)
         if world > 1:
@@ -283,6 +293,8 @@ def main():
         e0.record(stream)
         for i in range(steps):
             fn(warmup + i)
+        if drain is not None:
+            drain()                          # the last step's loss is on the host before the clock stops
         e1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
@@ -299,7 +311,7 @@ def main():
     ms = timed(step_device, args.steps, max(args.warmup, 3))
     l1, tc1 = eng.launch_counts()
     launches = (l1 - l0) * args.steps // (args.steps + max(args.warmup, 3))
-    ms_e2e = timed(step_host, args.steps, 3)
+    ms_e2e = timed(step_host, args.steps, 3, drain_host)
     clocks = sampler.stop() if rank == 0 else None     # sampled over both timed regions
     value = B * world * args.steps / (ms * 1e-3)
     e2e = B * world * args.steps / (ms_e2e * 1e-3)
@@ -468,7 +480,9 @@ def main():
                        "allreduce": None if world == 1 else ("ONE flat NCCL all-reduce per step (57.4 MB of gradients + the token count in its tail)" if ar is None else
                                                               f"{len(eng.grad_buckets())} buckets on a side stream, overlapped with the backward pass")},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(hx.numel() * 4 + hy.numel() * 4),
-                    "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps,
+                    "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps,
+                    "d2h": "loss + token count of every step, copied into page-locked memory behind the step (e2t_post_losses) and "
+                           "read by the host one step later (e2t_fetch_losses); the last one before the clock stops",
                     "h2d_gbs_per_rank": (hx.numel() * 4 + hy.numel() * 4) / (ms_e2e / args.steps * 1e-3) / 1e9},
             "gpu_launches": int(launches), "tcgen05_launches_total": int(tc1),
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,

@@ -18,7 +18,7 @@ ACT = {"linear": 0, "relu": 1}
 GEMM = {"auto": 0, "simt": 1, "tcgen05": 2}
 ATTN = {"none": 0, "luong": 1, "bahdanau": 2}
 AUX_KIND = {"gaussian": 0, "categorical": 1}
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class E2TConfig(C.Structure):
@@ -93,6 +93,8 @@ _SIGNATURES = {
     "e2t_grad_bucket_wait": (C.c_int, [_P, C.c_int, _P]),
     "e2t_set_encoder_targets": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
     "e2t_last_losses": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "e2t_post_losses": (C.c_int, [_P, C.c_int]),
+    "e2t_fetch_losses": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "e2t_input_saliency": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                      C.c_float, _P, _P]),
     "e2t_adam_ema_step": (C.c_int, [_P, C.c_int, C.c_float]),

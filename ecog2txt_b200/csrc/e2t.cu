@@ -34,7 +34,7 @@
 
 static thread_local std::string g_err;
 extern "C" const char* e2t_last_error(void) { return g_err.c_str(); }
-extern "C" int e2t_abi_version(void) { return 7; }
+extern "C" int e2t_abi_version(void) { return 8; }
 
 namespace {
 
@@ -182,6 +182,11 @@ struct e2t_handle {
 #endif
   // double-buffered input staging (e2t_stage_inputs): slot 0 aliases d_x / d_lens_in / d_y
   cudaStream_t copy_stream = nullptr;
+  // e2t_post_losses / e2t_fetch_losses: the step's losses travel to page-locked host memory behind the step, the host
+  // picks them up later (no synchronisation inside the step loop)
+  struct LossSlot { float l[2]; int n[2]; int aux_ran; };
+  LossSlot* loss_ring = nullptr;       // [4], page-locked
+  cudaEvent_t loss_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t clean_stream = nullptr;   // wipes the exchange buffers of the recurrent kernels behind their launches
   float* st_x[2] = {nullptr, nullptr}; int* st_lens[2] = {nullptr, nullptr}; int* st_y[2] = {nullptr, nullptr};
   bool st_has_lens[2] = {false, false}, st_has_y[2] = {false, false};
@@ -610,7 +615,9 @@ void build_workspace(e2t_handle* h) {
   }
   if (h->rec_pws_n) h->rec_pws = h->alloc<float>(h->rec_pws_n);
   if (h->rec_hx16_n) h->rec_hx16 = h->alloc<uint16_t>(h->rec_hx16_n);
+#ifndef E2T_EMU
   if (h->rec_pws3_n) h->rec_pws3 = h->alloc<float>(h->rec_pws3_n);
+#endif
   h->rec_counters = h->alloc<int>((i64)2 * cdiv(Bm, 128) * std::max<i64>(T2, Lm));
   h->ld_dec_kt = h->Dp + round_up(c.Hd, 4);
   h->dec_KT = h->alloc<float>((i64)4 * c.Hd * h->ld_dec_kt);
@@ -1456,6 +1463,8 @@ extern "C" int e2t_destroy(e2t_handle* h) {
   for (int i = 0; i < 2; ++i) { if (h->st_ready[i]) cudaEventDestroy(h->st_ready[i]); if (h->st_done[i]) cudaEventDestroy(h->st_done[i]); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->clean_stream) cudaStreamDestroy(h->clean_stream);
+  if (h->loss_ring) cudaFreeHost(h->loss_ring);
+  for (int i = 0; i < 4; ++i) if (h->loss_ev[i]) cudaEventDestroy(h->loss_ev[i]);
   for (auto& L : h->enc)
     for (XBuf* x : {&L.hx_train, &L.dzx_train}) { if (x->used) cudaEventDestroy(x->used); if (x->clean) cudaEventDestroy(x->clean); }
 #endif
@@ -1713,6 +1722,46 @@ extern "C" int e2t_last_losses(e2t_handle* h, float* decoder_sum, int32_t* ntok,
   if (ntok) *ntok = n[0];
   if (aux_sum) *aux_sum = h->aux_ran ? l[1] : 0.f;
   if (aux_frames) *aux_frames = h->aux_ran ? n[1] : 0;
+  API_END
+}
+
+extern "C" int e2t_post_losses(e2t_handle* h, int slot) {
+  API_BEGIN NEED_H;
+  E2T_REQUIRE(slot >= 0 && slot < 4, "slot must be 0..3");
+#ifndef E2T_EMU
+  if (!h->loss_ring) {
+    E2T_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&h->loss_ring), 4 * sizeof(e2t_handle::LossSlot), cudaHostAllocDefault));
+    memset(h->loss_ring, 0, 4 * sizeof(e2t_handle::LossSlot));
+    for (int i = 0; i < 4; ++i) E2T_CHECK(cudaEventCreateWithFlags(&h->loss_ev[i], cudaEventDisableTiming));
+  }
+  e2t_handle::LossSlot& s = h->loss_ring[slot];
+  E2T_CHECK(cudaMemcpyAsync(s.l, h->d_loss, 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  E2T_CHECK(cudaMemcpyAsync(s.n, h->d_ntok, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  s.aux_ran = h->aux_ran ? 1 : 0;
+  E2T_CHECK(cudaEventRecord(h->loss_ev[slot], h->stream));
+#else
+  if (!h->loss_ring) h->loss_ring = new e2t_handle::LossSlot[4]();
+  e2t_handle::LossSlot& s = h->loss_ring[slot];
+  E2T_CHECK(cudaMemcpyAsync(s.l, h->d_loss, 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  E2T_CHECK(cudaMemcpyAsync(s.n, h->d_ntok, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  E2T_CHECK(cudaStreamSynchronize(h->stream));
+  s.aux_ran = h->aux_ran ? 1 : 0;
+#endif
+  API_END
+}
+
+extern "C" int e2t_fetch_losses(e2t_handle* h, int slot, float* decoder_sum, int32_t* ntok, float* aux_sum, int32_t* aux_frames) {
+  API_BEGIN NEED_H;
+  E2T_REQUIRE(slot >= 0 && slot < 4, "slot must be 0..3");
+  E2T_REQUIRE(h->loss_ring != nullptr, "e2t_fetch_losses before any e2t_post_losses");
+#ifndef E2T_EMU
+  E2T_CHECK(cudaEventSynchronize(h->loss_ev[slot]));
+#endif
+  const e2t_handle::LossSlot& s = h->loss_ring[slot];
+  if (decoder_sum) *decoder_sum = s.l[0];
+  if (ntok) *ntok = s.n[0];
+  if (aux_sum) *aux_sum = s.aux_ran ? s.l[1] : 0.f;
+  if (aux_frames) *aux_frames = s.aux_ran ? s.n[1] : 0;
   API_END
 }
 

@@ -18,10 +18,13 @@
 //   * partial pieces carry, in the least-significant mantissa bit of every fp32 word, the parity of the number of times
 //     their slot (double-buffered by step parity) has been written; they leave through bulk stores from a swizzled stage
 //     and are pulled back by ONE bulk copy per owner (its R pieces are contiguous); every consumed word's tag is checked.
-// dz is exchanged in fp16 (the 11-bit significand a tf32 operand keeps) times a power-of-two scale 2^e that is carried from
-// launch to launch per layer: e is re-centred (largest |dz| of the previous launch -> 2^10) only when that maximum, scaled,
-// left [2^4, 2^13]; conversions saturate, so a sudden 32-fold growth clips for one step instead of producing infinities.
-// The fp32 dz the weight-gradient GEMMs read is written unscaled, straight from registers.
+// dz is exchanged in fp16 (the 11-bit significand a tf32 operand keeps) times a power-of-two scale 2^e.  e is a function of
+// the launch's INPUTS only (k_absmax over the gradient arriving from the layer above and the injected final-state gradient:
+// their largest magnitude maps to [2^9, 2^10)), so the result does not depend on what ran before -- a scale carried over
+// from the previous launch made the first step after start-up lose precision (default scale, dz of 1e-6 landed in fp16
+// subnormals) and two identical steps differ in their last bits.  |dz| <= |dc| / 4 with |dc| accumulating at most a few
+// |dh|: the 2^6 head-room has never been used up; conversions saturate, so even a gradient explosion clips instead of
+// producing infinities.  The fp32 dz the weight-gradient GEMMs read is written unscaled, straight from registers.
 //
 // warps 0-7: compute (thread = batch row x 8 units: gate derivatives, drain), warp 8: MMA issue, warp 9: probes + pulls.
 #pragma once
@@ -48,8 +51,8 @@ struct Bptt3P {
   const int* inject_t;
   unsigned char* dzx;     // fp16 dz exchange [2 dir][steps][n_bt][n slices] x 16 KB chunk images, pre-filled with 0xFF
   float* pws;             // partial pieces [2 parity][2 dir][n_bt][owner n][row group R] x 8 KB
-  const int* scale_in;    // {bits of the largest |dz| of the previous launch, exponent e it ran with}
-  int* scale_out;         // same for this launch (max zeroed by the host, e written by block 0)
+  const int* scale_in;    // bits of the largest |incoming gradient| of this launch (k_absmax)
+  int* scale_out;         // diagnostics: {bits of the largest |dz| of this launch, exponent e it ran with}
   int has_dhs;
   int steps, B, H, n_bt, n, G, R;
   uint32_t epoch0, epoch1;   // writes so far to the parity-0 / parity-1 partial slots
@@ -72,15 +75,29 @@ __device__ __forceinline__ void lds_v4(float* v, uint32_t addr) {
 __device__ __forceinline__ void sts_v4(uint32_t addr, const float* v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
 }
-// scale exponent of this launch from the previous launch's {max bits, exponent}
+// scale exponent of the launch: the largest incoming gradient magnitude lands in [2^9, 2^10)
 __device__ __forceinline__ int bptt3_scale_exp(const int* in) {
   const float pm = __int_as_float(in[0]);
-  int e = in[1];
-  if (pm > 0.f && pm < 3.0e38f) {
-    const int me = ilogbf(pm);
-    if (me + e > 13 || me + e < 4) e = 10 - me;
+  int e = 0;
+  if (pm > 0.f && pm < 3.0e38f) e = 9 - ilogbf(pm);
+  return max(-100, min(100, e));
+}
+// largest |a[i]|, |b[i]| as float bits (non-negative floats order like unsigned integers); *out zeroed by the caller
+__global__ void __launch_bounds__(256) k_absmax(const float4* __restrict__ a, long long n4a, const float4* __restrict__ b, long long n4b,
+                                                int* __restrict__ out) {
+  float m = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4a; i += stride) {
+    const float4 v = a[i];
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
   }
-  return max(-60, min(60, e));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4b; i += stride) {
+    const float4 v = b[i];
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m < 3.0e38f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
 }
 
 // (10 warps are allocated as 12 -- registers come in units of 4 warps -- so 168 registers per thread is all there is;
@@ -503,7 +520,7 @@ inline size_t bptt3_pws_floats(int B, int H) {
 }
 
 // persistent per-engine state of the kernel: tags of the partial workspace, per-layer dz scale
-struct Bptt3Scale { int* dev = nullptr; int cur = 0; };      // dev: [2][2] ints {max bits, exponent}
+struct Bptt3Scale { int* dev = nullptr; int cur = 0; };      // dev: 4 ints {max |incoming gradient| bits, -, max |dz| bits, exponent}
 
 // BPTT of one BiLSTM layer.  Wh16[d]: fp16 copies of Wh [H units, 4H permuted gate columns]; dzx / pws: workspaces of at
 // least bptt3_dzx_bytes / bptt3_pws_floats, dzx ALL 0xFF on entry (the caller wipes it behind the launch, e2t.cu: XBuf);
@@ -540,10 +557,15 @@ inline void rec_backward3(cudaStream_t st, float* const gates[2], const float* c
   p.epoch0 = tags.epoch[0]; p.epoch1 = tags.epoch[1];
   tags.epoch[0] += (uint32_t)(steps / 2);            // steps - 1 partials: ceil on parity 0, floor on parity 1
   tags.epoch[1] += (uint32_t)((steps - 1) / 2);
-  p.scale_in = scale.dev + 2 * scale.cur;
-  p.scale_out = scale.dev + 2 * (scale.cur ^ 1);
-  scale.cur ^= 1;
-  E2T_CHECK(cudaMemsetAsync(p.scale_out, 0, sizeof(int), st));
+  // scale of the exchange: from the largest |gradient| entering this launch (dhs: [steps, B, 2H]; dc_inject: [B, ldi])
+  p.scale_in = scale.dev; p.scale_out = scale.dev + 2;
+  E2T_CHECK(cudaMemsetAsync(scale.dev, 0, 4 * sizeof(int), st));
+  {
+    const long long na = dhs ? (long long)steps * B * 2 * H : 0, nb = dc_inject ? (long long)B * ldi : 0;
+    if ((na | nb) & 3) throw std::runtime_error("e2t: rec_backward3 needs 4-float aligned gradient buffers");
+    k_absmax<<<296, 256, 0, st>>>(reinterpret_cast<const float4*>(dhs), na / 4, reinterpret_cast<const float4*>(dc_inject), nb / 4, scale.dev);
+    E2T_CHECK(cudaGetLastError());
+  }
   static int dbg_left = getenv("E2T_REC_DEBUG") ? atoi(getenv("E2T_REC_DEBUG")) : 0;
   p.dbg = nullptr;
   if (dbg_left > 0) {

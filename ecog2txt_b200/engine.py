@@ -284,6 +284,16 @@ class Engine:
         self._ck(self._lib.e2t_last_losses(self._h, C.byref(ld), C.byref(nt), C.byref(la), C.byref(nf)))
         return float(ld.value), int(nt.value), float(la.value), int(nf.value)
 
+    def post_losses(self, slot: int):
+        """Enqueue the copy of the most recent step's losses into page-locked ring slot 0..3 (no synchronisation)."""
+        self._ck(self._lib.e2t_post_losses(self._h, int(slot)))
+
+    def fetch_losses(self, slot: int):
+        """Wait for the copy posted into `slot` and return (decoder loss sum, ntok, encoder-targets loss sum, frames)."""
+        ld, la, nt, nf = C.c_float(), C.c_float(), C.c_int32(), C.c_int32()
+        self._ck(self._lib.e2t_fetch_losses(self._h, int(slot), C.byref(ld), C.byref(nt), C.byref(la), C.byref(nf)))
+        return float(ld.value), int(nt.value), float(la.value), int(nf.value)
+
     def input_saliency(self, x, lens, y, subnet: int = 0, use_ema: bool = False, decoder_penalty: Optional[float] = None,
                        aux_penalty: Optional[float] = None, want_dx: bool = True, want_norms: bool = True):
         """A13: d(loss)/d(encoder_inputs) [B,T,C] and its per-electrode squared norms over time [B,C] (host inputs only)."""

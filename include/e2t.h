@@ -160,6 +160,12 @@ int e2t_set_encoder_targets(e2t_handle* h, const void* targets, int loc, int B, 
 /* the two terms of the most recent loss: penalty_scale * sum CE over `ntok` tokens, aux_penalty * sum over
  * `aux_frames` frames (0 when the head did not run); loss_sum of the calls above is their sum.  Synchronises. */
 int e2t_last_losses(e2t_handle* h, float* decoder_sum, int32_t* ntok, float* aux_sum, int32_t* aux_frames);
+/* The same four numbers without a synchronisation inside the step loop: e2t_post_losses enqueues their copy into
+ * page-locked host memory (ring slot 0..3) behind the step just enqueued; e2t_fetch_losses waits for THAT copy only and
+ * returns them -- typically one step later, while the device already works on the next step (the reference fetches the
+ * loss with every session.run, trainers.py:806-823; a pipelined loop reads it with a lag of one step). */
+int e2t_post_losses(e2t_handle* h, int slot);
+int e2t_fetch_losses(e2t_handle* h, int slot, float* decoder_sum, int32_t* ntok, float* aux_sum, int32_t* aux_frames);
 /* Running sums over the training steps since the last reset: out4 = [decoder loss, unmasked tokens, encoder-targets loss,
  * encoder-target frames].  Lets a training loop report the epoch loss with ONE host synchronisation per epoch instead of
  * one per step.  Synchronises. */

@@ -237,12 +237,16 @@ def test_staged_inputs_and_host_buffers(emu_lib):
         eng.train_step_grads_staged(i & 1, seed=7, want_loss=False)
         ld, nt, la, nf = eng.last_losses()
         assert (ld, nt, la, nf) == (ref[i][0], ref[i][1], 0.0, 0)
+        eng.post_losses(i & 3)                         # the pipelined read returns the same numbers
+        assert eng.fetch_losses(i & 3) == (ld, nt, la, nf)
         g = eng.get_all(_lib.GRAD)
         for k in g:
             assert np.array_equal(g[k], ref[i][2][k]), k
     with pytest.raises(E2TError, match="another shape"):
         eng._staged_shape[0] = (3, 19, 5, 0)
         eng.train_step_grads_staged(0, seed=7)
+    with pytest.raises(E2TError, match="slot must be"):
+        eng.post_losses(4)
     eng.close()
 
 
