@@ -28,6 +28,7 @@
 #ifndef E2T_EMU
 #include "lstm_rec16.cuh"
 #include "lstm_bptt3.cuh"
+#include "lstm_dec16.cuh"
 #endif
 #include "conv_tc.cuh"
 #endif
@@ -167,6 +168,9 @@ struct e2t_handle {
 #ifndef E2T_EMU
   rec16::BpttTags bptt_tags{{0, 0}, -1, -1};         // tag state of rec_pws (k_lstm_bptt2)
   rec16::BpttTags bptt3_tags{{0, 0}, -1, -1};        // tag state of rec_pws3 (k_lstm_bptt3)
+  bool dec16 = false;                                // teacher-forced decoder recurrence on k_dec_fwd16 (lstm_dec16.cuh)
+  void* dec_WhT16 = nullptr;                         // fp16 copy of the decoder's Wh^T [4Hd, round_up(Hd, 8)]
+  XBuf dec_hx;                                       // its exchange buffer
   float* rec_pws3 = nullptr; i64 rec_pws3_n = 0;     // partial pieces of k_lstm_bptt3
 #endif
   int* rec_counters = nullptr;   // arrival counters of the persistent recurrent kernels [2][n_bt][T2m]
@@ -591,6 +595,16 @@ void build_workspace(e2t_handle* h) {
     }
 #endif
   }
+#ifndef E2T_EMU
+  {
+    static const bool dec_old = getenv("E2T_DEC_V1") != nullptr;      // A/B switch: per-step decoder kernels
+    h->dec16 = !dec_old && c.gemm_backend != E2T_GEMM_SIMT && rec16::dec16_supported((int)Bm, c.Hd);
+    if (h->dec16) {
+      h->dec_WhT16 = h->alloc<uint16_t>((i64)4 * c.Hd * rec16::hp16(c.Hd));
+      xbuf_alloc(h, h->dec_hx, rec16::dec16_hx_bytes((int)Bm, c.Hd, (int)Lm));
+    }
+  }
+#endif
   h->h0 = h->alloc<float>(Bm * c.Hd); h->c0 = h->alloc<float>(Bm * c.Hd);
   h->dh0 = h->alloc<float>(Bm * c.Hd); h->dc0 = h->alloc<float>(Bm * c.Hd);
   h->dh_rec = h->alloc<float>(Bm * Hmax); h->dc_rec = h->alloc<float>(Bm * Hmax);
@@ -737,6 +751,13 @@ void repack(e2t_handle* h, const float* src, int src_id) {
           jb.rows = L.H; jb.cols = 4 * L.H; jb.ld_src = 4 * L.H; jb.ld_dst = 4 * L.H;
           biggest = std::max<i64>(biggest, (i64)jb.rows * jb.ld_dst);
         }
+    if (h->dec16) {
+      E2T_REQUIRE(jobs.n < 16, "too many recurrent layers for one pack launch");
+      rec16::PackJob& jb = jobs.j[jobs.n++];       // decoder Wh^T: columns [Dp, Dp + Hd) of the transposed kernel
+      jb.src = h->dec_KT + h->Dp; jb.dst = static_cast<__half*>(h->dec_WhT16);
+      jb.rows = 4 * h->cfg.Hd; jb.cols = h->cfg.Hd; jb.ld_src = h->ld_dec_kt; jb.ld_dst = rec16::hp16(h->cfg.Hd);
+      biggest = std::max<i64>(biggest, (i64)jb.rows * jb.ld_dst);
+    }
     if (jobs.n) {
       auto kfn = rec16::k_pack_f16;
       LAUNCH_L(h, "k_pack_f16", kfn, dim3((unsigned)std::min<i64>(cdiv(biggest, 256), 512), (unsigned)jobs.n), dim3(256), 0, jobs);
@@ -989,8 +1010,25 @@ void decoder_forward(e2t_handle* h, const Inputs& in, int B, int L, bool train, 
   LAUNCH(h, k_embed_fwd, grid1(rows * c.D), dim3(256), 0, h->d_prev, Wc + h->demb_w, Wc + h->demb_b, h->demb, rows,
          c.D, h->Dp, c.emb_act, dpe);
   DropP none = make_drop(0, 0, 0.f);
-  lstm_layer_forward(h, h->demb, h->Dp, c.D, c.Hd, h->dec_KT, h->ld_dec_kt, Wc + h->dec_b, h->dgates, h->dcs, h->hdec, nullptr,
-                     c.Hd, 0, nullptr, L, B, false, h->h0, h->c0, none, 0);
+  bool persistent = false;
+#ifndef E2T_EMU
+  if (h->dec16) {
+    // x-projection of all L steps in one GEMM, then ONE launch for the recurrence (lstm_dec16.cuh)
+    lstm_xproj(h, h->demb, h->Dp, c.D, c.Hd, h->dec_KT, h->ld_dec_kt, Wc + h->dec_b, h->dgates, L, B);
+    CatScope cs_(h, E2T_CAT_RECURRENT);
+    prof_begin(h, "dec_forward", B, c.Hd, L);
+    xbuf_acquire(h, h->dec_hx);
+    rec16::dec_forward16(h->stream, h->dgates, h->dcs, h->hdec, static_cast<const __half*>(h->dec_WhT16), h->dec_hx.p, h->h0, h->c0,
+                         L, B, c.Hd);
+    xbuf_release(h, h->dec_hx, rec16::dec16_hx_bytes(B, c.Hd, L));
+    prof_end(h);
+    ++h->n_launch; ++h->n_launch_tc; ++h->n_launch_rec;
+    persistent = true;
+  }
+#endif
+  if (!persistent)
+    lstm_layer_forward(h, h->demb, h->Dp, c.D, c.Hd, h->dec_KT, h->ld_dec_kt, Wc + h->dec_b, h->dgates, h->dcs, h->hdec, nullptr,
+                       c.Hd, 0, nullptr, L, B, false, h->h0, h->c0, none, 0);
   const float* proj_in = h->hdec;
   if (c.attention != E2T_ATTN_NONE) {
     // A7: q = hdec Wq^T ; fused score/softmax/context over the last encoder layer ; h~ = tanh([ctx, hdec] Wc^T + bc)
@@ -1467,6 +1505,8 @@ extern "C" int e2t_destroy(e2t_handle* h) {
   for (int i = 0; i < 4; ++i) if (h->loss_ev[i]) cudaEventDestroy(h->loss_ev[i]);
   for (auto& L : h->enc)
     for (XBuf* x : {&L.hx_train, &L.dzx_train}) { if (x->used) cudaEventDestroy(x->used); if (x->clean) cudaEventDestroy(x->clean); }
+  if (h->dec_hx.used) cudaEventDestroy(h->dec_hx.used);
+  if (h->dec_hx.clean) cudaEventDestroy(h->dec_hx.clean);
 #endif
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
