@@ -171,6 +171,10 @@ struct e2t_handle {
   bool dec16 = false;                                // teacher-forced decoder recurrence on k_dec_fwd16 (lstm_dec16.cuh)
   void* dec_WhT16 = nullptr;                         // fp16 copy of the decoder's Wh^T [4Hd, round_up(Hd, 8)]
   XBuf dec_hx;                                       // its exchange buffer
+  bool decbwd16 = false;                             // ... and its BPTT on k_dec_bwd16
+  void* dec_Wh16 = nullptr;                          // fp16 copy of the decoder's Wh [Hd, 4Hd]
+  XBuf dec_dzx;
+  int* dec_scale = nullptr;
   float* rec_pws3 = nullptr; i64 rec_pws3_n = 0;     // partial pieces of k_lstm_bptt3
 #endif
   int* rec_counters = nullptr;   // arrival counters of the persistent recurrent kernels [2][n_bt][T2m]
@@ -603,6 +607,13 @@ void build_workspace(e2t_handle* h) {
       h->dec_WhT16 = h->alloc<uint16_t>((i64)4 * c.Hd * rec16::hp16(c.Hd));
       xbuf_alloc(h, h->dec_hx, rec16::dec16_hx_bytes((int)Bm, c.Hd, (int)Lm));
     }
+    static const bool decbwd_old = getenv("E2T_DECBWD_V1") != nullptr;      // A/B switch: per-step decoder BPTT
+    h->decbwd16 = h->dec16 && !decbwd_old && rec16::decbwd_supported((int)Bm, c.Hd);
+    if (h->decbwd16) {
+      h->dec_Wh16 = h->alloc<uint16_t>((i64)c.Hd * 4 * c.Hd);
+      h->dec_scale = h->alloc<int>(4);
+      xbuf_alloc(h, h->dec_dzx, rec16::decbwd_dzx_bytes((int)Bm, c.Hd, (int)Lm));
+    }
   }
 #endif
   h->h0 = h->alloc<float>(Bm * c.Hd); h->c0 = h->alloc<float>(Bm * c.Hd);
@@ -756,6 +767,13 @@ void repack(e2t_handle* h, const float* src, int src_id) {
       rec16::PackJob& jb = jobs.j[jobs.n++];       // decoder Wh^T: columns [Dp, Dp + Hd) of the transposed kernel
       jb.src = h->dec_KT + h->Dp; jb.dst = static_cast<__half*>(h->dec_WhT16);
       jb.rows = 4 * h->cfg.Hd; jb.cols = h->cfg.Hd; jb.ld_src = h->ld_dec_kt; jb.ld_dst = rec16::hp16(h->cfg.Hd);
+      biggest = std::max<i64>(biggest, (i64)jb.rows * jb.ld_dst);
+    }
+    if (h->decbwd16) {
+      E2T_REQUIRE(jobs.n < 16, "too many recurrent layers for one pack launch");
+      rec16::PackJob& jb = jobs.j[jobs.n++];       // decoder Wh: rows [D, D + Hd) of the canonical kernel
+      jb.src = src + h->dec_K + (i64)h->cfg.D * 4 * h->cfg.Hd; jb.dst = static_cast<__half*>(h->dec_Wh16);
+      jb.rows = h->cfg.Hd; jb.cols = 4 * h->cfg.Hd; jb.ld_src = 4 * h->cfg.Hd; jb.ld_dst = 4 * h->cfg.Hd;
       biggest = std::max<i64>(biggest, (i64)jb.rows * jb.ld_dst);
     }
     if (jobs.n) {
@@ -1273,12 +1291,29 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
           c.Hd, (int)rows, c.Hd, nullptr, 0.f);
   }
   // ---- decoder recurrence
-  lstm_layer_backward(h, c.Hd, P + h->dec_K, c.D, h->dgates, h->dcs, h->dhdec, c.Hd, 0, nullptr, L, B, false, h->c0,
-                      nullptr, 0, nullptr, -1);
-  // grads wrt the bridge state: dh0 = dz[0] Wh^T, dc0 = dc_rec
-  gemm(h, h->dgates, 4 * c.Hd, 1, P + h->dec_K + (i64)c.D * 4 * c.Hd, 1, 4 * c.Hd, h->dh0, c.Hd, B, c.Hd, 4 * c.Hd,
-       nullptr, 0.f);
-  E2T_CHECK(cudaMemcpyAsync(h->dc0, h->dc_rec, (size_t)B * c.Hd * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  bool dec_persistent = false;
+#ifndef E2T_EMU
+  if (h->decbwd16 && P == h->Wc) {      // (the fp16 weight copies follow the weights in use)
+    // the L steps, the bridge-state gradient dh0 = dz[0] Wh^T and dc0 in ONE launch (lstm_dec16.cuh)
+    CatScope cs_(h, E2T_CAT_RECURRENT);
+    prof_begin(h, "dec_backward", B, c.Hd, L);
+    xbuf_acquire(h, h->dec_dzx);
+    rec16::dec_backward16(h->stream, h->dgates, h->dcs, h->c0, h->dhdec, static_cast<const __half*>(h->dec_Wh16), h->dec_dzx.p,
+                          h->dec_scale, h->dh0, h->dc0, L, B, c.Hd);
+    xbuf_release(h, h->dec_dzx, rec16::decbwd_dzx_bytes(B, c.Hd, L));
+    prof_end(h);
+    ++h->n_launch; ++h->n_launch_tc; ++h->n_launch_rec;
+    dec_persistent = true;
+  }
+#endif
+  if (!dec_persistent) {
+    lstm_layer_backward(h, c.Hd, P + h->dec_K, c.D, h->dgates, h->dcs, h->dhdec, c.Hd, 0, nullptr, L, B, false, h->c0,
+                        nullptr, 0, nullptr, -1);
+    // grads wrt the bridge state: dh0 = dz[0] Wh^T, dc0 = dc_rec
+    gemm(h, h->dgates, 4 * c.Hd, 1, P + h->dec_K + (i64)c.D * 4 * c.Hd, 1, 4 * c.Hd, h->dh0, c.Hd, B, c.Hd, 4 * c.Hd,
+         nullptr, 0.f);
+    E2T_CHECK(cudaMemcpyAsync(h->dc0, h->dc_rec, (size_t)B * c.Hd * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  }
   lstm_layer_wgrads(h, h->demb, h->Dp, c.D, c.Hd, P + h->dec_K, G + h->dec_K, G + h->dec_b, h->dgates, h->hdec, c.Hd, 0,
                     L, B, false, h->h0, h->ddemb, h->Dp, 0.f);
   // ---- decoder embedding
@@ -1507,6 +1542,8 @@ extern "C" int e2t_destroy(e2t_handle* h) {
     for (XBuf* x : {&L.hx_train, &L.dzx_train}) { if (x->used) cudaEventDestroy(x->used); if (x->clean) cudaEventDestroy(x->clean); }
   if (h->dec_hx.used) cudaEventDestroy(h->dec_hx.used);
   if (h->dec_hx.clean) cudaEventDestroy(h->dec_hx.clean);
+  if (h->dec_dzx.used) cudaEventDestroy(h->dec_dzx.used);
+  if (h->dec_dzx.clean) cudaEventDestroy(h->dec_dzx.clean);
 #endif
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;

@@ -9,6 +9,7 @@ E2T_REC_DEBUG=1 timeout 300 python tools/one_step.py 1 > gpurun_out/${TAG}_timel
 grep -A10 "rec fwd16\]" gpurun_out/${TAG}_timeline.txt | head -13 | cut -c1-200
 grep -A8 "rec bptt3\]" gpurun_out/${TAG}_timeline.txt | head -12 | cut -c1-200
 grep -A11 "dec fwd16\]" gpurun_out/${TAG}_timeline.txt | head -13 | cut -c1-200
+grep -A11 "dec bwd16\]" gpurun_out/${TAG}_timeline.txt | head -13 | cut -c1-200
 timeout 600 python bench.py --steps 20 --warmup 5 --no-decode --no-cpu-baseline --breakdown gpurun_out/${TAG}_breakdown.txt > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 tail -c 600 gpurun_out/${TAG}_bench.err
 python - <<PY
