@@ -77,6 +77,7 @@ struct EncLayer {
   // layer's dz scale state
   bool bptt3 = false;
   void* Wh16[2] = {nullptr, nullptr};
+  float* db_part = nullptr;            // [2 dir][batch tiles][4H] bias-gradient partials written by k_lstm_bptt3
   XBuf hx_train, dzx_train;            // per-layer exchange buffers of the training path (cleaned on the side stream)
   int* bptt3_scale = nullptr; int bptt3_scale_cur = 0;
 };
@@ -592,6 +593,7 @@ void build_workspace(e2t_handle* h) {
     if (L.bptt3) {
       for (int d = 0; d < 2; ++d) L.Wh16[d] = h->alloc<uint16_t>((i64)L.H * 4 * L.H);
       L.bptt3_scale = h->alloc<int>(4);
+      L.db_part = h->alloc<float>((i64)2 * ((Bm + 127) / 128) * 4 * L.H);
       const int init[4] = {0, 8, 0, 8};
       E2T_CHECK(cudaMemcpy(L.bptt3_scale, init, sizeof(init), cudaMemcpyHostToDevice));
       xbuf_alloc(h, L.dzx_train, rec16::bptt3_dzx_bytes((int)Bm, L.H, (int)T2));
@@ -1370,7 +1372,8 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
         const __half* w16[2] = {static_cast<const __half*>(Ly.Wh16[0]), static_cast<const __half*>(Ly.Wh16[1])};
         rec16::Bptt3Scale sc{Ly.bptt3_scale, Ly.bptt3_scale_cur};
         rec16::rec_backward3(h->stream, Ly.gates, csd, Ly.dhs, w16, h->d_lens2, top ? h->dc0 : nullptr, c.Hd,
-                             top ? h->d_tlast : nullptr, Ly.dzx_train.p, h->rec_pws3, (size_t)h->rec_pws3_n, h->bptt3_tags, sc, T2, B, Ly.H);
+                             top ? h->d_tlast : nullptr, Ly.dzx_train.p, h->rec_pws3, (size_t)h->rec_pws3_n, h->bptt3_tags, sc, Ly.db_part, T2, B,
+                             Ly.H);
         Ly.bptt3_scale_cur = sc.cur;
         xbuf_release(h, Ly.dzx_train, rec16::bptt3_dzx_bytes(B, Ly.H, T2));
       } else if (!use_allgather && !bptt_v1 && h->rec_pws && rec::bptt_supported(h->Bm, Ly.H))
@@ -1395,8 +1398,9 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
         // dz is in the permuted gate order: gradients land in a scratch and are un-permuted into the flat buffer
         float* dKp = Ly.dKP[d];
         float* dbp = Ly.dKP[d] + (i64)(Ly.In + Ly.H) * 4 * Ly.H;
+        const int n_bt = (B + 127) / 128;
         lstm_layer_wgrads(h, inp, ld_in, Ly.In, Ly.H, Ly.KP[d], dKp, dbp, Ly.gates[d], Ly.hs, 2 * Ly.H, d * Ly.H, T2, B,
-                          d == 1, nullptr, nullptr, ld_din, 0.f);
+                          d == 1, nullptr, nullptr, ld_din, 0.f, Ly.bptt3 ? Ly.db_part + (i64)d * n_bt * 4 * Ly.H : nullptr, n_bt);
         const i64 rows = Ly.In + Ly.H;
         batch_permute(h, h->batch3, dKp, G + Ly.K[d], rows, 4 * Ly.H, Ly.H, 0);
         batch_permute(h, h->batch3, dbp, G + Ly.b[d], (i64)1, 4 * Ly.H, Ly.H, 0);

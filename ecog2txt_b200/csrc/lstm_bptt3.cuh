@@ -49,6 +49,7 @@ struct Bptt3P {
   const int* lens2;
   const float* dc_inject; int ldi;
   const int* inject_t;
+  float* db_part;         // [2 dir][n_bt][4H] bias-gradient partials: column sums of dz over this batch tile's rows and all steps
   unsigned char* dzx;     // fp16 dz exchange [2 dir][steps][n_bt][n slices] x 16 KB chunk images, pre-filled with 0xFF
   float* pws;             // partial pieces [2 parity][2 dir][n_bt][owner n][row group R] x 8 KB
   const int* scale_in;    // bits of the largest |incoming gradient| of this launch (k_absmax)
@@ -101,8 +102,7 @@ __global__ void __launch_bounds__(256) k_absmax(const float4* __restrict__ a, lo
 }
 
 // (10 warps are allocated as 12 -- registers come in units of 4 warps -- so 168 registers per thread is all there is;
-// __maxnreg__(192) compiles without spills but is refused by the cooperative launch.  Summing the bias gradient in 32 more
-// registers per thread therefore spills: measured 9.6 instead of 8.1 us per step, more than the column sums it saves)
+// __maxnreg__(192) compiles without spills but is refused by the cooperative launch)
 __global__ void __launch_bounds__(kThreads16, 1)
 k_lstm_bptt3(const __grid_constant__ Bptt3Maps maps, Bptt3P p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -308,6 +308,7 @@ k_lstm_bptt3(const __grid_constant__ Bptt3Maps maps, Bptt3P p) {
     const float S = exp2f((float)e_scale), invS = exp2f((float)-e_scale);
     if (blockIdx.x == 0 && threadIdx.x == 0) p.scale_out[1] = e_scale;
     float amax = 0.f;
+    float dbsum = 0.f;            // bias gradient: lane l accumulates column l of the warp's 32 gate columns (32 rows x all steps)
     float carry[kUT], cv[kUT];
 #pragma unroll
     for (int i = 0; i < kUT; ++i) carry[i] = 0.f;
@@ -432,6 +433,21 @@ k_lstm_bptt3(const __grid_constant__ Bptt3Maps maps, Bptt3P p) {
       }
       // dz to HBM for the weight-gradient GEMMs (off the inter-CTA critical path)
       if (row_ok) rec::stv8<4 * kUT>(gates + ((i64)t * B + b) * 4 * H + z0, gz);
+      // bias gradient: the warp's [32 rows x 32 columns] of dz summed over the rows by a butterfly (gz is dead afterwards),
+      // behind the hand-off; one accumulator register (32 of them, reduced once at the end, spilled: 9.6 vs 8.1 us per step)
+      {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < off; ++i) {
+            const float send = upper ? gz[i] : gz[i + off];
+            const float keep = upper ? gz[i + off] : gz[i];
+            gz[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        dbsum += gz[0];
+      }
       // ---- hop 2: drain the partial of the step, piece by piece, tagged, through the stage
       if (more) {
         const uint32_t tw = (((q & 1) ? p.epoch1 : p.epoch0) + (uint32_t)(q >> 1)) & 1u;
@@ -476,6 +492,17 @@ k_lstm_bptt3(const __grid_constant__ Bptt3Maps maps, Bptt3P p) {
       }
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    {
+      // the four row quadrants of a unit group (warps 4 ug .. 4 ug + 3) through shared memory, in a fixed order
+      rec::named_bar_sync(2, kWorkThreads);                 // every thread is done with the piece stage
+      float* red = reinterpret_cast<float*>(smem_p);
+      red[warp * 32 + lane] = dbsum;
+      rec::named_bar_sync(2, kWorkThreads);
+      if (warp < 2) {
+        const float sum = ((red[(4 * warp) * 32 + lane] + red[(4 * warp + 1) * 32 + lane]) + red[(4 * warp + 2) * 32 + lane]) + red[(4 * warp + 3) * 32 + lane];
+        p.db_part[((size_t)(d * p.n_bt + bt) * 4 * H) + j * 4 * kU + warp * 32 + lane] = sum;
+      }
+    }
     // largest |dz| of the launch: the next launch's scale
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -527,13 +554,13 @@ struct Bptt3Scale { int* dev = nullptr; int cur = 0; };      // dev: 4 ints {max
 // tags / scale: state carried between launches.
 inline void rec_backward3(cudaStream_t st, float* const gates[2], const float* const cs[2], const float* dhs,
                           const __half* const Wh16[2], const int* lens2, const float* dc_inject, int ldi, const int* inject_t,
-                          unsigned char* dzx, float* pws, size_t pws_floats, BpttTags& tags, Bptt3Scale& scale, int steps, int B,
-                          int H) {
+                          unsigned char* dzx, float* pws, size_t pws_floats, BpttTags& tags, Bptt3Scale& scale, float* db_part,
+                          int steps, int B, int H) {
   Bptt3P p{};
   const Bptt3Geo g = bptt3_geo(H);
   for (int d = 0; d < 2; ++d) p.gates[d] = gates[d];
   p.lens2 = lens2; p.dc_inject = dc_inject; p.ldi = ldi; p.inject_t = inject_t;
-  p.dzx = dzx; p.pws = pws; p.has_dhs = dhs != nullptr;
+  p.dzx = dzx; p.pws = pws; p.has_dhs = dhs != nullptr; p.db_part = db_part;
   p.steps = steps; p.B = B; p.H = H; p.n_bt = (B + kBM - 1) / kBM; p.n = H / kU; p.G = g.G; p.R = g.R;
   static const int force = getenv("E2T_REC_DBGSKIP") ? (atoi(getenv("E2T_REC_DBGSKIP")) & 4) : 0;
   p.dbg_force = force;
