@@ -479,6 +479,22 @@ struct PackJob { const float* src; __half* dst; int rows, cols, ld_src, ld_dst; 
 struct PackJobs { PackJob j[16]; int n; };
 __global__ void k_pack_f16(PackJobs jobs) {
   const PackJob& jb = jobs.j[blockIdx.y];
+  if (((jb.cols | jb.ld_src | jb.ld_dst) & 3) == 0 && (reinterpret_cast<uintptr_t>(jb.src) & 15) == 0) {
+    // four elements per thread: one 16-byte load, one 8-byte store
+    const int q = jb.ld_dst / 4;
+    const i64 n4 = (i64)jb.rows * q;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (i64)gridDim.x * blockDim.x) {
+      const int r = (int)(i / q), c = (int)(i % q) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < jb.cols) v = *reinterpret_cast<const float4*>(jb.src + (i64)r * jb.ld_src + c);
+      const __half2 lo = __floats2half2_rn(fminf(fmaxf(v.x, -65504.f), 65504.f), fminf(fmaxf(v.y, -65504.f), 65504.f));
+      const __half2 hi = __floats2half2_rn(fminf(fmaxf(v.z, -65504.f), 65504.f), fminf(fmaxf(v.w, -65504.f), 65504.f));
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(jb.dst + (i64)r * jb.ld_dst + c) = o;
+    }
+    return;
+  }
   const i64 n = (i64)jb.rows * jb.ld_dst;
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
     const int r = (int)(i / jb.ld_dst), c = (int)(i % jb.ld_dst);
