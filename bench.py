@@ -184,10 +184,10 @@ def main():
     ap.add_argument("--cpu-baseline-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write the per-kernel event-time breakdown of a step to this file")
-    ap.add_argument("--overlap-allreduce", action="store_true",
+    ap.add_argument("--overlap-allreduce", default="auto", nargs="?", const="on", choices=["auto", "on", "off"],
                     help="N > 1: bucketed all-reduce on a side stream, overlapped with the backward pass, instead of one flat "
-                         "all-reduce after it (measured at N = 2: 113.7 k vs 114.3 k utt/s -- the per-bucket flushes cost what "
-                         "the overlap hides, so flat is the default)")
+                         "all-reduce after it.  Measured: N = 2 113.7 k vs 114.3 k utt/s flat (the per-bucket flushes cost what the "
+                         "overlap hides), N = 8 572.2 k vs 561.9 k (profiles/r2_bench_8gpu_*.json); auto = on from 4 ranks")
     ap.add_argument("--no-decode", action="store_true", help="skip the greedy / beam-8 decode legs")
     ap.add_argument("--decode-utterances", type=int, default=10000, help="utterances decoded per leg, sharded over the ranks")
     args = ap.parse_args()
@@ -238,7 +238,8 @@ def main():
     # bucket on a side stream while the backward pass is still going (ecog2txt_b200/dist.py: BucketedAllReduce).  Either way
     # the global token count stays on the device (e2t_adam_ema_step_dev): the timed loop has no host synchronisation
     from ecog2txt_b200.dist import BucketedAllReduce
-    ar = BucketedAllReduce(eng) if world > 1 and args.overlap_allreduce else None
+    overlap = args.overlap_allreduce == "on" or (args.overlap_allreduce == "auto" and world >= 4)
+    ar = BucketedAllReduce(eng) if world > 1 and overlap else None
     ntok_dev = [(y != 0).sum().float().reshape(1) for _, y in dev]
     ntok_cache = [float((hy != 0).sum()) for _, hy in host]
 
@@ -368,13 +369,16 @@ def main():
         achieved = flops_launch * (n_f + n_b) / (rec_ms * 1e-3) / 1e12 if rec_ms > 0 else 0.0
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_lstm_rec_fwd"]["dram_bytes_per_launch"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            # per launch like `achieved`: mean of the forward and the BPTT kernel of one layer (ncu --set full, one launch each)
+            traffic = (tj["k_lstm_fwd16"]["dram_bytes_per_launch"] + tj["k_lstm_bptt3"]["dram_bytes_per_launch"]) // 2
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         conv_bytes = B * T_FRAMES * 256 * 4
         conv_gbs = 2 * conv_bytes * nprof / (cat_ms[2][0] * 1e-3) / 1e9 if cat_ms[2][0] > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "k_lstm_rec<fwd> + k_lstm_bptt (persistent whole-layer recurrent kernels, tcgen05 kind::tf32)",
+        roof = {"bound": "tensor", "kernel": "k_lstm_fwd16 + k_lstm_bptt3 (persistent whole-layer recurrent kernels of the encoder, tcgen05 "
+                                            "kind::f16 on fp16 operands with the 11-bit significand of tf32, fp32 accumulate)",
                 "achieved": achieved, "peak": peak_tf32, "unit": "TFLOP/s", "frac": achieved / peak_tf32, "traffic": traffic,
                 "peak_source": f"max(cuBLAS tf32 8192^3 measured live with random operands = {tf32_meas:.1f}, this repo's tcgen05 tf32 GEMM at "
                                f"8192^3 measured live = {tf32_own:.1f}, {psrc} / 2 = {peak_tf / 2:.1f})",
