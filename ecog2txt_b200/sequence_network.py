@@ -41,7 +41,8 @@ _MANIFEST_KEYS = dict(layer_sizes=None, FF_dropout=0.0, RNN_dropout=0.0, TEMPORA
 class SequenceNetwork:
     def __init__(self, manifest, EOS_token=_EOS, pad_token=_PAD, OOV_token=_OOV, training_GPUs=(0,),
                  TARGETS_ARE_SEQUENCES=True, VERBOSE=True, N_cases=256, max_hyp_length=20, learning_rate=5e-4,
-                 seed=1, gemm_backend="auto", attention="none", lib=None, loader_threads=None, **kwargs):
+                 seed=1, gemm_backend="auto", attention="none", lib=None, loader_threads=None, device_cache_bytes=16 << 30,
+                 **kwargs):
         # utils_jgm.auto_attribute(CHECK_MANIFEST=True): a keyword wins, else manifest[key] (README.md:42)
         for key, default in _MANIFEST_KEYS.items():
             if key in kwargs and kwargs[key] is not None:
@@ -70,6 +71,9 @@ class SequenceNetwork:
         self.attention = attention       # "luong": optional A7 module (default "none" = the reference model)
         self.checkpoint_path: Optional[str] = None
         self.max_to_keep = 5             # checkpoints kept on disk (tf.train.Saver default)
+        # fit(): keep the padded training set of every subject on the device (uploaded once per fit) when it fits this many
+        # bytes; a step then moves only its example indices over PCIe instead of 105 MB of ECoG.  0 disables.
+        self.device_cache_bytes = int(device_cache_bytes or 0)
         self.inputs_to_occlude = None
         self._lib = lib
         self._engine: Optional[Engine] = None
@@ -234,6 +238,9 @@ class SequenceNetwork:
                        for p in ('training', 'validation')}
         step = eng.step
         eng.read_loss_accumulators(reset=True)
+        cache = self._device_cache(eng, subnets_params, data, max_T, max_L, pad_id)
+        if cache is not None:
+            import torch
         for epoch in range(start_epoch, start_epoch + self.N_epochs):
             # minibatches: (subject index, example indices); all ranks draw the same order, then shard each batch
             plan = []
@@ -266,6 +273,20 @@ class SequenceNetwork:
                     y[r, :len(ex[i][1])] = ex[i][1]
                 return x, y, self._aux_batch(ex, ids, max_T)
 
+            if cache is not None:
+                # device-resident path: gather the minibatch out of the cached training set on the device
+                for k, (si, ids) in enumerate(shards):
+                    if len(ids):
+                        cx, cy = cache[subnets_params[si].subnet_id]
+                        it = torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int64)).to(cx.device, non_blocking=True)
+                        eng.train_step_grads(cx.index_select(0, it), None, cy.index_select(0, it), subnet=si, seed=step,
+                                             want_loss=False)
+                    else:
+                        flat_tensor(eng, _lib.GRAD_AND_COUNT).zero_()
+                    allreduce_step(grads)
+                    eng.adam_ema_step_dev(None, subnet=si)
+                    step += 1
+                shards = []
             nxt = host_batch(0) if shards else None
             if nxt is not None:
                 eng.stage_inputs(0, nxt[0], None, nxt[1], subnet=shards[0][0])
@@ -308,6 +329,34 @@ class SequenceNetwork:
         if world > 1:
             dist.barrier()      # rank 0's checkpoint is complete before any rank goes on to restore it
         return assessments
+
+    def _device_cache(self, eng, subnets_params, data, max_T, max_L, pad_id):
+        """{subnet_id: (x [N, max_T, C] fp32, y [N, max_L] int32)} as CUDA tensors, or None (emulation build, encoder targets
+        in play, or the padded training sets exceed device_cache_bytes).  The library is bound to torch's current stream so
+        that the gathers and the library's kernels are ordered."""
+        if getattr(eng, "emulated", False) or not self.device_cache_bytes:
+            return None
+        total = 0
+        for s in subnets_params:
+            ex = data[s.subnet_id]['training']
+            if not len(ex) or any(e[2] is not None for e in ex[:1]):
+                return None
+            total += len(ex) * max_T * int(ex[0][0].shape[1]) * 4
+        if total > self.device_cache_bytes:
+            return None
+        import torch
+        dev = torch.device("cuda", eng.cfg.device)
+        torch.cuda.set_device(dev)
+        eng.set_stream(torch.cuda.current_stream().cuda_stream)
+        cache = {}
+        for s in subnets_params:
+            ex = data[s.subnet_id]['training']
+            x = tfrecord.pad_batch_f32([e[0] for e in ex], max_T, threads=self.loader_threads)
+            y = np.full((len(ex), max_L), pad_id, np.int32)
+            for r, e in enumerate(ex):
+                y[r, :len(e[1])] = e[1]
+            cache[s.subnet_id] = (torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev))
+        return cache
 
     # -- assessment ----------------------------------------------------------------------------
     def _assess(self, eng, subnets_params, data, partition, max_T, max_L):

@@ -35,6 +35,32 @@ def test_sequence_network_fit_on_gpu(gpu_lib, tmp_path):
     assert res_b["training"].word_error_rate <= wer[-1] + 0.05
 
 
+def test_fit_device_cache_equals_staged_pipeline(gpu_lib, tmp_path):
+    """fit() with the training set resident on the device (minibatches gathered there, only indices cross PCIe) must train
+    exactly like the staged host pipeline (native padding threads -> page-locked ring -> copy stream): same minibatches,
+    same dropout seeds -> the same weights up to the one atomic reduction (embedding scatter)."""
+    from ecog2txt_b200 import SequenceNetwork, _lib
+    from ecog2txt_b200.subjects import make_synthetic_subject
+    vocab = ["<pad>", "<EOS>", "<OOV>"] + [f"w{i:02d}_" for i in range(37)]
+    s = make_synthetic_subject(400, vocab, str(tmp_path / "tf"), n_train_blocks=2, n_valid_blocks=1,
+                               utterances_per_block=32, T=96, C=64, n_sentences=10, ragged=True, seed=0)
+    s.data_generator.corpus.max_words = 6
+    s.write_tf_records_maybe()
+    manifest = {"layer_sizes": {"encoder_embedding": [32], "encoder_rnn": [64, 64], "decoder_embedding": [24],
+                                "decoder_rnn": [128], "decoder_projection": []},
+                "FF_dropout": 0.1, "RNN_dropout": 0.3, "TEMPORALLY_CONVOLVE": True, "EMA_decay": 0.9, "N_epochs": 3,
+                "beam_width": 1, "temperature": 0.384, "assessment_epoch_interval": 3}
+    out = []
+    for cache_bytes in (16 << 30, 0):
+        net = SequenceNetwork(manifest, VERBOSE=False, N_cases=32, max_hyp_length=8, learning_rate=5e-3,
+                              device_cache_bytes=cache_bytes)
+        net.checkpoint_path = None
+        net.fit([s])
+        out.append(net._engine.get_all(_lib.VALUE))
+    for k in out[0]:
+        np.testing.assert_allclose(out[0][k], out[1][k], rtol=2e-4, atol=2e-6, err_msg=k)
+
+
 def _gpu_trainer(tmp_path, ids=(400, 401), C=(64, 48), **sn):
     from ecog2txt_b200 import MultiSubjectTrainer
     from ecog2txt_b200.subjects import make_synthetic_subject
