@@ -216,7 +216,12 @@ def main():
         B = args.batch
     eng = Engine(EngineConfig(**GEO, max_B=B, max_T=T_FRAMES, max_L=20, max_beam=8, ff_dropout=FF_DROPOUT,
                               rnn_dropout=RNN_DROPOUT, gemm_backend=args.backend, device=local))
-    stream = torch.cuda.current_stream()
+    # everything runs on ONE high-priority torch stream (the library's kernels, NCCL, the timing events): the library hands the
+    # weight-gradient GEMMs of encoder layer l to its own lowest-priority side stream while layer l - 1 runs its BPTT, and the
+    # block scheduler must prefer the main stream's kernels (torch's default stream has the LOWEST priority)
+    stream = torch.cuda.Stream(priority=-1)
+    stream.wait_stream(torch.cuda.current_stream())
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     init_engine(eng, seed=1)
     grads = flat_tensor(eng, _lib.GRAD_AND_COUNT)      # gradients + token count: ONE collective per step

@@ -197,6 +197,12 @@ struct e2t_handle {
   LossSlot* loss_ring = nullptr;       // [4], page-locked
   cudaEvent_t loss_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t clean_stream = nullptr;   // wipes the exchange buffers of the recurrent kernels behind their launches
+  // weight-gradient GEMMs of encoder layer l run here (lowest priority, short-lived CTAs) beside the BPTT of layer l - 1,
+  // which occupies only 100 of the 148 SMs; side_ev[l]: their completion, main_ev: "dz of the layer is final"
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t main_ev = nullptr;
+  std::vector<cudaEvent_t> side_ev;
+  std::vector<int> side_pending;
   float* st_x[2] = {nullptr, nullptr}; int* st_lens[2] = {nullptr, nullptr}; int* st_y[2] = {nullptr, nullptr};
   bool st_has_lens[2] = {false, false}, st_has_y[2] = {false, false};
   int st_B[2] = {0, 0}, st_T[2] = {0, 0}, st_L[2] = {0, 0}, st_subnet[2] = {0, 0};
@@ -1241,6 +1247,41 @@ void bucket_done(e2t_handle* h, i64 off, i64 n, bool last) {
 }
 
 // train = false: the forward pass ran without dropout (saliency), possibly on the EMA weights
+#ifndef E2T_EMU
+// Everything enqueued while a SideScope lives goes to the side stream, behind "what the main stream has enqueued so far".
+struct SideScope {
+  e2t_handle* h; cudaStream_t saved; int slot;
+  SideScope(e2t_handle* h_, int slot_) : h(h_), saved(h_->stream), slot(slot_) {
+    if (!h->side_stream) {
+      int lo = 0, hi = 0;
+      E2T_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      E2T_CHECK(cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, lo));
+      E2T_CHECK(cudaEventCreateWithFlags(&h->main_ev, cudaEventDisableTiming));
+    }
+    while ((int)h->side_ev.size() <= slot) {
+      cudaEvent_t e;
+      E2T_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->side_ev.push_back(e);
+    }
+    E2T_CHECK(cudaEventRecord(h->main_ev, saved));
+    E2T_CHECK(cudaStreamWaitEvent(h->side_stream, h->main_ev, 0));
+    h->stream = h->side_stream;
+    tc::short_lived_ctas() = true;
+  }
+  ~SideScope() {
+    tc::short_lived_ctas() = false;
+    cudaEventRecord(h->side_ev[slot], h->side_stream);
+    h->side_pending.push_back(slot);
+    h->stream = saved;
+  }
+};
+// the main stream goes on only after everything the side stream was given
+void side_join(e2t_handle* h) {
+  for (int s : h->side_pending) E2T_CHECK(cudaStreamWaitEvent(h->stream, h->side_ev[s], 0));
+  h->side_pending.clear();
+}
+#endif
+
 void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, uint32_t seed, bool train = true) {
   const e2t_config& c = h->cfg;
   const float* P = h->Wc;
@@ -1389,30 +1430,52 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
       ++h->n_launch; ++h->n_launch_tc; ++h->n_launch_rec;
 #endif
     }
-    for (int d = 0; d < 2; ++d) {
-      if (!rec_ok)
+    // d_in [rows, In] = dz_fw Wx_fw^T + dz_bw Wx_bw^T in one pass (canonical K rows [In, 4H] are the K-major B operands)
+    auto input_grad = [&]() {
+      gemm2(h, Ly.gates[0], 4 * Ly.H, rec_ok ? Ly.KP[0] : P + Ly.K[0], 4 * Ly.H, 4 * Ly.H, Ly.gates[1], 4 * Ly.H,
+            rec_ok ? Ly.KP[1] : P + Ly.K[1], 4 * Ly.H, 4 * Ly.H, d_in, ld_din, (int)((i64)T2 * B), Ly.In, nullptr, 0.f);
+    };
+    auto weight_grads = [&]() {
+      for (int d = 0; d < 2; ++d) {
+        if (rec_ok) {
+          // dz is in the permuted gate order: gradients land in a scratch and are un-permuted into the flat buffer
+          float* dKp = Ly.dKP[d];
+          float* dbp = Ly.dKP[d] + (i64)(Ly.In + Ly.H) * 4 * Ly.H;
+          const int n_bt = (B + 127) / 128;
+          lstm_layer_wgrads(h, inp, ld_in, Ly.In, Ly.H, Ly.KP[d], dKp, dbp, Ly.gates[d], Ly.hs, 2 * Ly.H, d * Ly.H, T2, B,
+                            d == 1, nullptr, nullptr, ld_din, 0.f, Ly.bptt3 ? Ly.db_part + (i64)d * n_bt * 4 * Ly.H : nullptr, n_bt);
+          const i64 rows = Ly.In + Ly.H;
+          batch_permute(h, h->batch3, dKp, G + Ly.K[d], rows, 4 * Ly.H, Ly.H, 0);
+          batch_permute(h, h->batch3, dbp, G + Ly.b[d], (i64)1, 4 * Ly.H, Ly.H, 0);
+        } else {
+          lstm_layer_wgrads(h, inp, ld_in, Ly.In, Ly.H, P + Ly.K[d], G + Ly.K[d], G + Ly.b[d], Ly.gates[d], Ly.hs, 2 * Ly.H,
+                            d * Ly.H, T2, B, d == 1, nullptr, nullptr, ld_din, 0.f);
+        }
+      }
+      bucket_done(h, Ly.K[0], (l + 1 < nl ? h->enc[l + 1].K[0] : h->demb_w) - Ly.K[0], false);
+    };
+    if (!rec_ok)
+      for (int d = 0; d < 2; ++d)
         lstm_layer_backward(h, Ly.H, P + Ly.K[d], Ly.In, Ly.gates[d], Ly.cs[d], Ly.dhs, 2 * Ly.H, d * Ly.H, h->d_lens2,
                             T2, B, d == 1, nullptr, top ? h->dc0 + d * Ly.H : nullptr, c.Hd,
                             (top && d == 0) ? h->d_tlast : nullptr, 0);
-      if (rec_ok) {
-        // dz is in the permuted gate order: gradients land in a scratch and are un-permuted into the flat buffer
-        float* dKp = Ly.dKP[d];
-        float* dbp = Ly.dKP[d] + (i64)(Ly.In + Ly.H) * 4 * Ly.H;
-        const int n_bt = (B + 127) / 128;
-        lstm_layer_wgrads(h, inp, ld_in, Ly.In, Ly.H, Ly.KP[d], dKp, dbp, Ly.gates[d], Ly.hs, 2 * Ly.H, d * Ly.H, T2, B,
-                          d == 1, nullptr, nullptr, ld_din, 0.f, Ly.bptt3 ? Ly.db_part + (i64)d * n_bt * 4 * Ly.H : nullptr, n_bt);
-        const i64 rows = Ly.In + Ly.H;
-        batch_permute(h, h->batch3, dKp, G + Ly.K[d], rows, 4 * Ly.H, Ly.H, 0);
-        batch_permute(h, h->batch3, dbp, G + Ly.b[d], (i64)1, 4 * Ly.H, Ly.H, 0);
-      } else {
-        lstm_layer_wgrads(h, inp, ld_in, Ly.In, Ly.H, P + Ly.K[d], G + Ly.K[d], G + Ly.b[d], Ly.gates[d], Ly.hs, 2 * Ly.H,
-                          d * Ly.H, T2, B, d == 1, nullptr, nullptr, ld_din, 0.f);
-      }
+    bool on_side = false;
+#ifndef E2T_EMU
+    // The weight gradients of this layer are off the critical path (only the optimiser needs them); the layer below starts
+    // its BPTT as soon as d_in is there and leaves 48 SMs idle for ~270 us: the weight-gradient GEMMs (and, with gradient
+    // buckets, the bucket's flush) go to the low-priority side stream.  Not for the bottom layer (nothing left to hide behind).
+    static const bool no_side = getenv("E2T_NO_SIDE") != nullptr;
+    on_side = rec_ok && l > 0 && use_rec(h, h->enc[l - 1], B, T2) && !no_side && !h->prof && !(h->aux && l == c.aux_layer);
+    if (on_side) {
+      input_grad();
+      SideScope side(h, l);
+      weight_grads();
     }
-    // d_in [rows, In] = dz_fw Wx_fw^T + dz_bw Wx_bw^T in one pass (canonical K rows [In, 4H] are the K-major B operands)
-    gemm2(h, Ly.gates[0], 4 * Ly.H, rec_ok ? Ly.KP[0] : P + Ly.K[0], 4 * Ly.H, 4 * Ly.H, Ly.gates[1], 4 * Ly.H,
-          rec_ok ? Ly.KP[1] : P + Ly.K[1], 4 * Ly.H, 4 * Ly.H, d_in, ld_din, (int)((i64)T2 * B), Ly.In, nullptr, 0.f);
-    bucket_done(h, Ly.K[0], (l + 1 < nl ? h->enc[l + 1].K[0] : h->demb_w) - Ly.K[0], false);
+#endif
+    if (!on_side) {
+      weight_grads();      // (bucket_done inside: before d_in, as ever)
+      input_grad();
+    }
     if (h->aux && l == c.aux_layer) bucket_done(h, tail_end, h->n_params - tail_end, false);   // the head's tensors
   }
   // ---- temporal conv
@@ -1423,6 +1486,9 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
   batch_colsum(h, h->dconv, (i64)T2 * B, c.E, c.E, G + h->conv_b[subnet]);
   // every (remaining) bias-gradient column sum and gate-order un-permute of the step: three launches; the subject-private
   // conv tensors are the last bucket (without bucketing: the only one, covering the whole buffer)
+#ifndef E2T_EMU
+  side_join(h);
+#endif
   bucket_done(h, 0, h->enc[0].K[0], true);
 }
 
@@ -1513,7 +1579,11 @@ extern "C" int e2t_create(const e2t_config* cfg, e2t_handle** out) {
     E2T_CHECK(cudaSetDevice(cfg->device));
     h = new e2t_handle();
     h->cfg = *cfg;
-    E2T_CHECK(cudaStreamCreate(&h->own_stream));
+    {   // the library's own stream gets the highest priority: its kernels go first when the side stream has work pending
+      int lo = 0, hi = 0;
+      E2T_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      E2T_CHECK(cudaStreamCreateWithPriority(&h->own_stream, cudaStreamDefault, hi));
+    }
     h->stream = h->own_stream;
     build_params(h);
     build_workspace(h);
@@ -1540,6 +1610,9 @@ extern "C" int e2t_destroy(e2t_handle* h) {
   for (int i = 0; i < 2; ++i) { if (h->st_ready[i]) cudaEventDestroy(h->st_ready[i]); if (h->st_done[i]) cudaEventDestroy(h->st_done[i]); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->clean_stream) cudaStreamDestroy(h->clean_stream);
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->main_ev) cudaEventDestroy(h->main_ev);
+  for (cudaEvent_t e : h->side_ev) cudaEventDestroy(e);
   if (h->loss_ring) cudaFreeHost(h->loss_ring);
   for (int i = 0; i < 4; ++i) if (h->loss_ev[i]) cudaEventDestroy(h->loss_ev[i]);
   for (auto& L : h->enc)

@@ -457,6 +457,12 @@ inline int sm_count_() {
   return n;
 }
 
+// Launches made while this is set are NOT persistent: one CTA per (tile, k-split) instead of min(work, SMs) CTAs looping over
+// their share.  Used for the GEMMs that run on a low-priority side stream beside a persistent recurrent kernel (e2t.cu:
+// SideScope): short-lived CTAs give the SMs back every few microseconds, so the high-priority kernel's CTAs are never held up
+// for the duration of a whole GEMM.
+inline bool& short_lived_ctas() { static thread_local bool v = false; return v; }
+
 constexpr size_t kSmemCap = 227 * 1024;
 inline size_t gemm_fixed_smem() { return (size_t)4 * 32 * kEpiPad * 4 + (2 * 8 + 4 + 1) * 8 + 1024; }
 inline size_t gemm_smem_bytes(int BN, int stages) { return (size_t)stages * (BM * BK * 4 + (size_t)BN * BK * 4) + gemm_fixed_smem(); }
@@ -560,11 +566,11 @@ inline void launch_gemm(cudaStream_t st, const float* A, i64 lda, const float* B
   tiles = p.tiles_m * p.tiles_n;
   const size_t smem_bytes = gemm_smem_bytes(bn_local, p.stages);
   if (!two) {
-    const int grid = std::min(tiles * p.ksplit, nsm);
+    const int grid = short_lived_ctas() ? tiles * p.ksplit : std::min(tiles * p.ksplit, nsm);
     k_gemm_tc<TN, false><<<grid, kGemmThreads, smem_bytes, st>>>(ma, mb, ma2, mb2, p);
   } else {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(2 * std::min(tiles * p.ksplit, nsm / 2)));
+    cfg.gridDim = dim3((unsigned)(2 * (short_lived_ctas() ? tiles * p.ksplit : std::min(tiles * p.ksplit, nsm / 2))));
     cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;

@@ -13,7 +13,8 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 eng = Engine(EngineConfig(**Bn.GEO, max_B=B, max_T=Bn.T_FRAMES, max_L=20, max_beam=8, ff_dropout=Bn.FF_DROPOUT,
                           rnn_dropout=Bn.RNN_DROPOUT))
-eng.set_stream(torch.cuda.current_stream().cuda_stream)
+_st = torch.cuda.Stream(priority=-1); torch.cuda.set_stream(_st)
+eng.set_stream(_st.cuda_stream)
 init_engine(eng, seed=1)
 corpus = SyntheticCorpus(load_vocab(size=Bn.GEO["V"]), T=Bn.T_FRAMES, C=256, seed=0)
 b = corpus.batch(B, seed=0, L=Bn.L_TGT)
