@@ -1297,7 +1297,21 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
   // ---- projection: logits already hold dlogits
   const bool attn = c.attention != E2T_ATTN_NONE;
   const float* proj_in = attn ? h->at_ht : h->hdec;
-  gemm(h, h->logits, 1, h->Vp, proj_in, c.Hd, 1, G + h->proj_w, c.Hd, c.V, c.Hd, (int)rows, nullptr, 0.f);
+  // (without attention the persistent decoder BPTT below leaves 48 SMs idle: the projection's weight gradient runs beside it
+  //  on the side stream, the decoder's own weight / embedding gradients beside the top encoder layer's BPTT)
+  bool dec_side = false;
+#ifndef E2T_EMU
+  {
+    static const bool no_side = getenv("E2T_NO_SIDE") != nullptr;
+    dec_side = !attn && !no_side && !h->prof && h->decbwd16 && P == h->Wc && c.n_enc_layers > 0 &&
+               use_rec(h, h->enc.back(), B, T2);
+  }
+  if (dec_side) {
+    SideScope side(h, c.n_enc_layers + 1);
+    gemm(h, h->logits, 1, h->Vp, proj_in, c.Hd, 1, G + h->proj_w, c.Hd, c.V, c.Hd, (int)rows, nullptr, 0.f);
+  }
+#endif
+  if (!dec_side) gemm(h, h->logits, 1, h->Vp, proj_in, c.Hd, 1, G + h->proj_w, c.Hd, c.V, c.Hd, (int)rows, nullptr, 0.f);
   batch_colsum(h, h->logits, rows, c.V, h->Vp, G + h->proj_b);
   // d(proj input) [rows,Hd] = dlogits Wp ; B operand (k=v, n=u) = Wp[v*Hd+u] -> packed transpose is the K-major form
   gemm(h, h->logits, h->Vp, 1, h->proj_wT, 1, h->Vp, attn ? h->at_dht : h->dhdec, c.Hd, (int)rows, c.Hd, c.V, nullptr, 0.f);
@@ -1357,14 +1371,23 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
          nullptr, 0.f);
     E2T_CHECK(cudaMemcpyAsync(h->dc0, h->dc_rec, (size_t)B * c.Hd * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
   }
-  lstm_layer_wgrads(h, h->demb, h->Dp, c.D, c.Hd, P + h->dec_K, G + h->dec_K, G + h->dec_b, h->dgates, h->hdec, c.Hd, 0,
-                    L, B, false, h->h0, h->ddemb, h->Dp, 0.f);
-  // ---- decoder embedding
-  DropP dpe = make_drop(seed, E2T_STREAM_DEMB, train ? c.ff_dropout : 0.f);
-  LAUNCH(h, k_act_dropout_bwd, grid1(rows * c.D), dim3(256), 0, h->ddemb, h->demb, rows, c.D, h->Dp, c.emb_act, dpe);
-  LAUNCH(h, k_embed_bwd, grid1(rows * c.D), dim3(256), 0, h->d_prev, h->ddemb, G + h->demb_w, rows, c.D, h->Dp);
-  batch_colsum(h, h->ddemb, rows, c.D, h->Dp, G + h->demb_b);
-  bucket_done(h, h->demb_w, tail_end - h->demb_w, false);      // decoder embedding / rnn / projection / attention
+  auto decoder_param_grads = [&]() {
+    lstm_layer_wgrads(h, h->demb, h->Dp, c.D, c.Hd, P + h->dec_K, G + h->dec_K, G + h->dec_b, h->dgates, h->hdec, c.Hd, 0,
+                      L, B, false, h->h0, h->ddemb, h->Dp, 0.f);
+    // ---- decoder embedding
+    DropP dpe = make_drop(seed, E2T_STREAM_DEMB, train ? c.ff_dropout : 0.f);
+    LAUNCH(h, k_act_dropout_bwd, grid1(rows * c.D), dim3(256), 0, h->ddemb, h->demb, rows, c.D, h->Dp, c.emb_act, dpe);
+    LAUNCH(h, k_embed_bwd, grid1(rows * c.D), dim3(256), 0, h->d_prev, h->ddemb, G + h->demb_w, rows, c.D, h->Dp);
+    batch_colsum(h, h->ddemb, rows, c.D, h->Dp, G + h->demb_b);
+    bucket_done(h, h->demb_w, tail_end - h->demb_w, false);      // decoder embedding / rnn / projection / attention
+  };
+#ifndef E2T_EMU
+  if (dec_side) {
+    SideScope side(h, c.n_enc_layers);
+    decoder_param_grads();
+  }
+#endif
+  if (!dec_side) decoder_param_grads();
   // ---- encoder, top layer first
   const int nl = c.n_enc_layers;
   for (int l = nl - 1; l >= 0; --l) {
