@@ -219,7 +219,7 @@ def main():
     # everything runs on ONE high-priority torch stream (the library's kernels, NCCL, the timing events): the library hands the
     # weight-gradient GEMMs of encoder layer l to its own lowest-priority side stream while layer l - 1 runs its BPTT, and the
     # block scheduler must prefer the main stream's kernels (torch's default stream has the LOWEST priority)
-    stream = torch.cuda.Stream(priority=-1)
+    stream = torch.cuda.Stream(priority=0 if os.environ.get("E2T_BENCH_PRIO0") else -1)
     stream.wait_stream(torch.cuda.current_stream())
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)

@@ -35,7 +35,8 @@ FULL = dict(subnet_ids=(400,), subnet_C=(256,), subnet_W=(12,), E=100, H=(400, 4
 SIMT_TOL = dict(loss=1e-6, state=5e-6, grad=2e-4)
 TC_TOL = dict(loss=1e-4, state=1e-2, grad=3e-2)
 # (log-probabilities of the TRAINED model: logits an order of magnitude larger than with random weights, measured 8.1e-3)
-FULL_TOL = dict(loss=2e-5, state=1e-2, grad=3e-2, logp=5e-3, logp_trained=3e-2, beam_score=1e-2)
+# (beam-8 scores of the trained model -- sums of up to 12 such log-probabilities: 3.3e-2 measured, all beams identical)
+FULL_TOL = dict(loss=2e-5, state=1e-2, grad=3e-2, logp=5e-3, logp_trained=3e-2, beam_score=1e-2, beam_score_trained=1e-1)
 
 
 def tols(backend):
