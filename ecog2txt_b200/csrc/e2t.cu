@@ -1027,7 +1027,10 @@ void attn_forward(e2t_handle* h, const float* q, const float* enc, float* alpha,
 // ------------------------------------------------------------------------------------------------
 // decoder forward, teacher forced (A8-A9)
 // ------------------------------------------------------------------------------------------------
-void decoder_forward(e2t_handle* h, const Inputs& in, int B, int L, bool train, uint32_t seed, bool with_grad) {
+// What the teacher-forced decoder needs BEFORE the encoder's final state: shifted targets, their embeddings and (persistent
+// decoder kernel) the x-projection of all L steps.  None of it depends on the encoder, so a training step runs it on the
+// side stream beside the first encoder layer's recurrence (which leaves 48 SMs idle).
+void decoder_inputs(e2t_handle* h, const Inputs& in, int B, int L, bool train, uint32_t seed) {
   const e2t_config& c = h->cfg;
   const float* Wc = h->Wc;
   const i64 rows = (i64)L * B;
@@ -1035,12 +1038,22 @@ void decoder_forward(e2t_handle* h, const Inputs& in, int B, int L, bool train, 
   DropP dpe = make_drop(seed, E2T_STREAM_DEMB, train ? c.ff_dropout : 0.f);
   LAUNCH(h, k_embed_fwd, grid1(rows * c.D), dim3(256), 0, h->d_prev, Wc + h->demb_w, Wc + h->demb_b, h->demb, rows,
          c.D, h->Dp, c.emb_act, dpe);
+#ifndef E2T_EMU
+  if (h->dec16)   // x-projection of all L steps in one GEMM (the recurrence is ONE launch, lstm_dec16.cuh)
+    lstm_xproj(h, h->demb, h->Dp, c.D, c.Hd, h->dec_KT, h->ld_dec_kt, Wc + h->dec_b, h->dgates, L, B);
+#endif
+}
+
+void decoder_forward(e2t_handle* h, const Inputs& in, int B, int L, bool train, uint32_t seed, bool with_grad,
+                     bool inputs_done = false) {
+  const e2t_config& c = h->cfg;
+  const float* Wc = h->Wc;
+  const i64 rows = (i64)L * B;
+  if (!inputs_done) decoder_inputs(h, in, B, L, train, seed);
   DropP none = make_drop(0, 0, 0.f);
   bool persistent = false;
 #ifndef E2T_EMU
   if (h->dec16) {
-    // x-projection of all L steps in one GEMM, then ONE launch for the recurrence (lstm_dec16.cuh)
-    lstm_xproj(h, h->demb, h->Dp, c.D, c.Hd, h->dec_KT, h->ld_dec_kt, Wc + h->dec_b, h->dgates, L, B);
     CatScope cs_(h, E2T_CAT_RECURRENT);
     prof_begin(h, "dec_forward", B, c.Hd, L);
     xbuf_acquire(h, h->dec_hx);
@@ -1726,9 +1739,25 @@ extern "C" int e2t_train_step_grads(e2t_handle* h, int subnet, const float* x, c
   Inputs in = stage(h, subnet, x, lens, y, loc, B, T, L);
   E2T_REQUIRE(in.y != nullptr, "training needs targets");
   use_weights(h, false);
+  bool dec_hoist = false;
+#ifndef E2T_EMU
+  {
+    // the decoder's embeddings and x-projection do not depend on the encoder: side stream, beside the first recurrence
+    static const bool no_side = getenv("E2T_NO_SIDE") != nullptr;
+    const int T2 = (int)cdiv(T, h->cfg.subnet_W[subnet]);
+    if (!no_side && !h->prof && h->dec16 && h->cfg.n_enc_layers > 0 && use_rec(h, h->enc[0], B, T2)) {
+      SideScope side(h, h->cfg.n_enc_layers + 2);
+      decoder_inputs(h, in, B, L, true, dropout_seed);
+      dec_hoist = true;
+    }
+  }
+#endif
   encoder_forward(h, subnet, in, B, T, true, dropout_seed);
   aux_forward(h, subnet, B, T, true, dropout_seed, true);
-  decoder_forward(h, in, B, L, true, dropout_seed, true);
+#ifndef E2T_EMU
+  if (dec_hoist) side_join(h);
+#endif
+  decoder_forward(h, in, B, L, true, dropout_seed, true, dec_hoist);
   backward(h, subnet, in, B, T, L, dropout_seed);
   E2T_CHECK(cudaGetLastError());
   release_slot(h, loc);
