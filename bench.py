@@ -187,7 +187,9 @@ def main():
     ap.add_argument("--overlap-allreduce", default="auto", nargs="?", const="on", choices=["auto", "on", "off"],
                     help="N > 1: bucketed all-reduce on a side stream, overlapped with the backward pass, instead of one flat "
                          "all-reduce after it.  Measured: N = 2 113.7 k vs 114.3 k utt/s flat (the per-bucket flushes cost what the "
-                         "overlap hides), N = 8 572.2 k vs 561.9 k (profiles/r2_bench_8gpu_*.json); auto = on from 4 ranks")
+                         "overlap hides); N = 8 before the side stream took the weight-gradient GEMMs 572.2 k vs 561.9 k, with it "
+                         "618.8 k vs 620.8 k flat (profiles/r2_bench_8gpu_*.json: the buckets now complete on the side stream, late) "
+                         "-- auto = flat")
     ap.add_argument("--no-decode", action="store_true", help="skip the greedy / beam-8 decode legs")
     ap.add_argument("--decode-utterances", type=int, default=10000, help="utterances decoded per leg, sharded over the ranks")
     args = ap.parse_args()
@@ -243,7 +245,7 @@ def main():
     # bucket on a side stream while the backward pass is still going (ecog2txt_b200/dist.py: BucketedAllReduce).  Either way
     # the global token count stays on the device (e2t_adam_ema_step_dev): the timed loop has no host synchronisation
     from ecog2txt_b200.dist import BucketedAllReduce
-    overlap = args.overlap_allreduce == "on" or (args.overlap_allreduce == "auto" and world >= 4)
+    overlap = args.overlap_allreduce == "on"
     ar = BucketedAllReduce(eng) if world > 1 and overlap else None
     ntok_dev = [(y != 0).sum().float().reshape(1) for _, y in dev]
     ntok_cache = [float((hy != 0).sum()) for _, hy in host]

@@ -45,6 +45,24 @@ def test_persistent_recurrent_kernels_full_width(gpu_lib, B, T, ff, rnn):
     assert c["persistent_rnn_launches"] == 6, c   # 2 layers x (forward + backward) + the decoder (Hd = 800) forward + backward
 
 
+def test_persistent_kernels_recover_from_incomplete_tiles(gpu_lib):
+    """The persistent recurrent kernels pull a tile when one word per producer warp has arrived and detect a piece that was
+    not there yet by the NaN it leaves in the accumulator (or by its tag); the step is then pulled again.  That path almost
+    never runs by itself (once in ~3000 steps), so E2T_REC_DBGSKIP=4 forces a re-pull on every fifth step of every kernel
+    (forward, both BPTT hand-offs, decoder forward / backward): the results must still match the oracle.  The switch is read
+    once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, 'tests'); import parity_common as pc; from ecog2txt_b200 import _lib; "
+            "lib = _lib.load(); pc.check_train_step(lib, pc.WIDE, 160, 60, 5, ff=0.1, rnn=0.5, backend='auto'); "
+            "pc.check_train_step(lib, pc.WIDE, 40, 100, 5, backend='auto'); print('REPULL_OK')")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, E2T_REC_DBGSKIP="4")
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "REPULL_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
 def test_persistent_kernels_are_deterministic(gpu_lib):
     import numpy as np
     from ecog2txt_b200 import _lib
