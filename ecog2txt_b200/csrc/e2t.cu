@@ -1316,7 +1316,9 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
 #ifndef E2T_EMU
   {
     static const bool no_side = getenv("E2T_NO_SIDE") != nullptr;
-    dec_side = !attn && !no_side && !h->prof && h->decbwd16 && P == h->Wc && c.n_enc_layers > 0 &&
+    // (not with gradient buckets: a bucket's flush would run on the side stream and share the batch-job table and the
+    //  column-sum pool with the main stream's flushes)
+    dec_side = !attn && !no_side && !h->prof && !h->bucketed && h->decbwd16 && P == h->Wc && c.n_enc_layers > 0 &&
                use_rec(h, h->enc.back(), B, T2);
   }
   if (dec_side) {
@@ -1501,7 +1503,8 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
     // its BPTT as soon as d_in is there and leaves 48 SMs idle for ~270 us: the weight-gradient GEMMs (and, with gradient
     // buckets, the bucket's flush) go to the low-priority side stream.  Not for the bottom layer (nothing left to hide behind).
     static const bool no_side = getenv("E2T_NO_SIDE") != nullptr;
-    on_side = rec_ok && l > 0 && use_rec(h, h->enc[l - 1], B, T2) && !no_side && !h->prof && !(h->aux && l == c.aux_layer);
+    on_side = rec_ok && l > 0 && use_rec(h, h->enc[l - 1], B, T2) && !no_side && !h->prof && !h->bucketed &&
+              !(h->aux && l == c.aux_layer);
     if (on_side) {
       input_grad();
       SideScope side(h, l);

@@ -416,6 +416,8 @@ struct DecBwdP {
 };
 
 constexpr uint32_t kDecBwdW = 16 * 128;      // one 64-column chunk of the resident weights: 16 unit rows x 128 B
+constexpr int kBwdPair = 2;                  // chunks per ring slot of k_dec_bwd16
+constexpr int kBwdSlots = kDecRing / kBwdPair;
 
 __global__ void __launch_bounds__(kThreads16, 1)
 k_dec_bwd16(const __grid_constant__ DecBwdMaps maps, DecBwdP p) {
@@ -474,20 +476,24 @@ k_dec_bwd16(const __grid_constant__ DecBwdMaps maps, DecBwdP p) {
     constexpr uint32_t idesc = make_idesc_f16(kBM, kU);
     const uint64_t desc_a0 = make_smem_desc(smem_u32(smem_a));
     const uint64_t desc_w0 = make_smem_desc(smem_u32(smem_w));
+    // the ring is handed over in slots of kBwdPair chunks (one barrier round trip, fence and commit per 8 MMAs instead of
+    // per 4: the per-chunk overhead was ~150 of ~570 cycles)
     uint32_t q = 0, round = 0;
     for (int s = 0; s < L; ++s) {
       for (;;) {
-        for (int kc = 0; kc < NKC; ++kc, ++q) {
-          const uint32_t slot = q % kDecRing;
-          mbar_wait_rec(smem_u32(&a_full[slot]), (q / kDecRing) & 1u, p.trap_rec, 7, s, kc);
+        for (int kc = 0; kc < NKC; kc += kBwdPair, ++q) {
+          const uint32_t slot = q % kBwdSlots;
+          mbar_wait_rec(smem_u32(&a_full[slot]), (q / kBwdSlots) & 1u, p.trap_rec, 7, s, kc);
           fence_after_sync();
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(tmem_base, desc_a0 + (uint64_t)((slot * kAChunk + k * 32) >> 4), desc_w0 + (uint64_t)((kc * kDecBwdW + k * 32) >> 4),
-                       idesc, (kc > 0 || k > 0) ? 1u : 0u);
+            for (int c2 = 0; c2 < kBwdPair; ++c2)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(tmem_base, desc_a0 + (uint64_t)(((slot * kBwdPair + c2) * kAChunk + k * 32) >> 4),
+                         desc_w0 + (uint64_t)(((kc + c2) * kDecBwdW + k * 32) >> 4), idesc, (kc > 0 || c2 > 0 || k > 0) ? 1u : 0u);
             umma_commit(smem_u32(&a_free[slot]));
-            if (kc == NKC - 1) umma_commit(smem_u32(acc_full));
+            if (kc + kBwdPair >= NKC) umma_commit(smem_u32(acc_full));
           }
           __syncwarp();
         }
@@ -509,7 +515,7 @@ k_dec_bwd16(const __grid_constant__ DecBwdMaps maps, DecBwdP p) {
         int seen_upto = first ? 0 : NKC;      // chunks [0, seen_upto) are known complete (after a verdict: all)
         const long long t0 = clock64();
         while (next < NKC) {
-          // poll the window [seen_upto, min(NKC, next + ring depth))
+          // poll the window [seen_upto, min(NKC, next + ring depth in chunks))
           const int hi = min(NKC, next + kDecRing);
           uint32_t v[kDecRing];
 #pragma unroll
@@ -520,17 +526,17 @@ k_dec_bwd16(const __grid_constant__ DecBwdMaps maps, DecBwdP p) {
           for (int k = 0; k < kDecRing; ++k)
             if (seen_upto + k < hi && adv == k && __all_sync(0xffffffffu, v[k] != kFill32)) adv = k + 1;
           seen_upto += adv;
-          while (next < seen_upto) {
-            const uint32_t slot = q % kDecRing;
-            if (q >= (uint32_t)kDecRing) mbar_wait_rec(smem_u32(&a_free[slot]), ((q / kDecRing) - 1u) & 1u, p.trap_rec, 3, s, next);
+          while (next + kBwdPair <= seen_upto) {          // a slot = kBwdPair consecutive chunks = one contiguous 32 KB copy
+            const uint32_t slot = q % kBwdSlots;
+            if (q >= (uint32_t)kBwdSlots) mbar_wait_rec(smem_u32(&a_free[slot]), ((q / kBwdSlots) - 1u) & 1u, p.trap_rec, 3, s, next);
             if (dbg && lane == 0 && next == 0) dbg[s * kDbg + 1] = clock64();
             if (elect_one()) {
               const uint32_t fb = smem_u32(&a_full[slot]);
-              mbar_expect_tx(fb, kAChunk);
-              bulk_load(smem_u32(smem_a + (size_t)slot * kAChunk), base + (size_t)next * kAChunk, kAChunk, fb);
+              mbar_expect_tx(fb, kBwdPair * kAChunk);
+              bulk_load(smem_u32(smem_a + (size_t)slot * kBwdPair * kAChunk), base + (size_t)next * kAChunk, kBwdPair * kAChunk, fb);
             }
             __syncwarp();
-            ++next; ++q;
+            next += kBwdPair; ++q;
           }
           if (clock64() - t0 > (1LL << 31)) timeout_trap(p.trap_rec, 1, s, next, seen_upto);
         }
@@ -669,7 +675,7 @@ inline size_t decbwd_smem_bytes(int H) {
 }
 inline size_t decbwd_dzx_bytes(int B, int H, int L) { return (size_t)L * (bp16(B) / kBM) * (4 * H / kKC) * kAChunk; }
 inline bool decbwd_supported(int B, int H) {
-  if (H % kU != 0 || H < 8 * kU || B < 1) return false;
+  if (H % kU != 0 || H < 8 * kU || B < 1 || (4 * H / kKC) % kBwdPair != 0) return false;
   const int n_bt = (B + kBM - 1) / kBM, n_slices = H / kU;
   if (n_bt * n_slices > rec::sm_count()) return false;
   return decbwd_smem_bytes(H) <= 227 * 1024;
