@@ -161,6 +161,9 @@ struct e2t_handle {
   // batched small jobs (k_batch): pending list + device table
   std::vector<BatchJob> batch;
   BatchJob* d_batch = nullptr; int d_batch_cap = 0;
+  BatchJob* d_batch_side = nullptr;   // job table of flushes that run on the side stream (a table is reused per flush)
+  bool pool_keep = false;             // backward pass with gradient buckets: flushes on two streams -> the column-sum pool is
+                                      // handed out once per step (reset at the start of backward), not once per flush
   float* colsum_pool = nullptr; i64 colsum_pool_n = 0, colsum_pool_used = 0;   // [64][N] partial sums of deferred colsums
   std::vector<BatchJob> batch2;       // second pass of the two-pass column sums (runs after `batch`)
   std::vector<BatchJob> batch3;       // un-permutes that consume column sums (run after `batch2`)
@@ -390,15 +393,19 @@ void batch_flush_list(e2t_handle* h, std::vector<BatchJob>& jobs) {
   for (auto& j : jobs) { j.blk0 = blk; blk += j.nblk; }
   if ((int)jobs.size() > h->d_batch_cap) throw std::runtime_error("e2t: batch job table overflow");
   // pageable source: the runtime stages the bytes before returning, so `jobs` may be reused at once
-  E2T_CHECK(cudaMemcpyAsync(h->d_batch, jobs.data(), jobs.size() * sizeof(BatchJob), cudaMemcpyHostToDevice, h->stream));
-  LAUNCH(h, k_batch, dim3((unsigned)blk), dim3(256), 0, h->d_batch, (int)jobs.size());
+  BatchJob* table = h->d_batch;
+#ifndef E2T_EMU
+  if (h->side_stream && h->stream == h->side_stream) table = h->d_batch_side;
+#endif
+  E2T_CHECK(cudaMemcpyAsync(table, jobs.data(), jobs.size() * sizeof(BatchJob), cudaMemcpyHostToDevice, h->stream));
+  LAUNCH(h, k_batch, dim3((unsigned)blk), dim3(256), 0, table, (int)jobs.size());
   jobs.clear();
 }
 void batch_flush(e2t_handle* h) {
   batch_flush_list(h, h->batch);
   batch_flush_list(h, h->batch2);
   batch_flush_list(h, h->batch3);
-  h->colsum_pool_used = 0;
+  if (!h->pool_keep) h->colsum_pool_used = 0;
 }
 void batch_transpose(e2t_handle* h, const float* in, i64 ldi, float* out, i64 ldo, int K, int N, int permH = 0,
                      float* out_lo = nullptr) {
@@ -645,6 +652,7 @@ void build_workspace(e2t_handle* h) {
     h->colsum_pool = h->alloc<float>(h->colsum_pool_n);
     h->d_batch_cap = 256;
     h->d_batch = reinterpret_cast<BatchJob*>(h->alloc<char>((i64)h->d_batch_cap * sizeof(BatchJob)));
+    h->d_batch_side = reinterpret_cast<BatchJob*>(h->alloc<char>((i64)h->d_batch_cap * sizeof(BatchJob)));
   }
   if (h->rec_pws_n) h->rec_pws = h->alloc<float>(h->rec_pws_n);
   if (h->rec_hx16_n) h->rec_hx16 = h->alloc<uint16_t>(h->rec_hx16_n);
@@ -1305,6 +1313,8 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
   const i64 rows = (i64)L * B;
   E2T_CHECK(cudaMemsetAsync(G, 0, (size_t)h->n_params * sizeof(float), h->stream));
   h->buckets.clear();
+  h->colsum_pool_used = 0;
+  h->pool_keep = h->bucketed;
   // flat order: [conv per subject | encoder layers 0.. | decoder embedding, decoder rnn, projection, attention | aux head]
   const i64 tail_end = h->aux ? (c.aux_hidden > 0 ? h->aux_w1 : h->aux_w2) : h->n_params;
   // ---- projection: logits already hold dlogits
@@ -1316,9 +1326,7 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
 #ifndef E2T_EMU
   {
     static const bool no_side = getenv("E2T_NO_SIDE") != nullptr;
-    // (not with gradient buckets: a bucket's flush would run on the side stream and share the batch-job table and the
-    //  column-sum pool with the main stream's flushes)
-    dec_side = !attn && !no_side && !h->prof && !h->bucketed && h->decbwd16 && P == h->Wc && c.n_enc_layers > 0 &&
+    dec_side = !attn && !no_side && !h->prof && h->decbwd16 && P == h->Wc && c.n_enc_layers > 0 &&
                use_rec(h, h->enc.back(), B, T2);
   }
   if (dec_side) {
@@ -1503,8 +1511,7 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
     // its BPTT as soon as d_in is there and leaves 48 SMs idle for ~270 us: the weight-gradient GEMMs (and, with gradient
     // buckets, the bucket's flush) go to the low-priority side stream.  Not for the bottom layer (nothing left to hide behind).
     static const bool no_side = getenv("E2T_NO_SIDE") != nullptr;
-    on_side = rec_ok && l > 0 && use_rec(h, h->enc[l - 1], B, T2) && !no_side && !h->prof && !h->bucketed &&
-              !(h->aux && l == c.aux_layer);
+    on_side = rec_ok && l > 0 && use_rec(h, h->enc[l - 1], B, T2) && !no_side && !h->prof && !(h->aux && l == c.aux_layer);
     if (on_side) {
       input_grad();
       SideScope side(h, l);
@@ -1529,6 +1536,8 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
   side_join(h);
 #endif
   bucket_done(h, 0, h->enc[0].K[0], true);
+  h->pool_keep = false;
+  h->colsum_pool_used = 0;
 }
 
 void read_loss(e2t_handle* h, float* loss_sum, int32_t* ntok) {
@@ -1618,11 +1627,15 @@ extern "C" int e2t_create(const e2t_config* cfg, e2t_handle** out) {
     E2T_CHECK(cudaSetDevice(cfg->device));
     h = new e2t_handle();
     h->cfg = *cfg;
+#ifndef E2T_EMU
     {   // the library's own stream gets the highest priority: its kernels go first when the side stream has work pending
       int lo = 0, hi = 0;
       E2T_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
       E2T_CHECK(cudaStreamCreateWithPriority(&h->own_stream, cudaStreamDefault, hi));
     }
+#else
+    E2T_CHECK(cudaStreamCreate(&h->own_stream));
+#endif
     h->stream = h->own_stream;
     build_params(h);
     build_workspace(h);
