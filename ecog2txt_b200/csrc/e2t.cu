@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <set>
 #include <string>
 #include <vector>
@@ -99,6 +100,13 @@ struct e2t_handle {
   int64_t n_launch = 0, n_launch_tc = 0;
   bool packed_dirty = true;
   int packed_src = -1;
+  // one-shot request to the next weight-gradient GEMM (gemm(), TN form): its columns are in the recurrent kernels' gate order
+  // and `unperm_dst` is the canonical tensor -- a split-K reduction writes there directly (unperm_applied), see gemm_tc.cuh
+  bool repack_on_side = false;      // part of the last re-pack is still running on the side stream (slot repack_slot())
+  int repack_slot() const { return cfg.n_enc_layers + 3; }
+  float* unperm_dst = nullptr;
+  int unperm_H = 0;
+  bool unperm_applied = false;
   // per-category event timing (e2t_profile_*)
   bool prof = false;
   int cat = E2T_CAT_OTHER;
@@ -295,6 +303,8 @@ inline dim3 grid1(i64 n, int block = 256) { return dim3((unsigned)cdiv(n, block)
 // C[M,N] = A(m,k) B(k,n) + bias + beta*C with arbitrary strides; dispatches to tcgen05 when possible.
 void gemm(e2t_handle* h, const float* A, i64 sam, i64 sak, const float* B, i64 sbk, i64 sbn, float* C, i64 ldc,
           int M, int N, int K, const float* bias, float beta) {
+  h->unperm_applied = false;
+  if (M <= 0 || N <= 0 || K <= 0) h->unperm_dst = nullptr;
   if (M <= 0 || N <= 0) return;
   if (K <= 0) {
     E2T_REQUIRE(beta == 1.f && !bias, "empty-K gemm must be a no-op");
@@ -305,6 +315,7 @@ void gemm(e2t_handle* h, const float* A, i64 sam, i64 sak, const float* B, i64 s
   if (h->cfg.gemm_backend != E2T_GEMM_SIMT && sak == 1 && sbk == 1 &&
       tc_gemm_nt_supported(A, sam, B, sbn, C, ldc, M, N, K)) {
     prof_begin(h, "tc_gemm_nt", M, N, K);
+    h->unperm_dst = nullptr;
     tc_gemm_nt(h->stream, A, sam, B, sbn, C, ldc, M, N, K, bias, beta);
     prof_end(h);
     ++h->n_launch;
@@ -313,13 +324,15 @@ void gemm(e2t_handle* h, const float* A, i64 sam, i64 sak, const float* B, i64 s
   }
   if (h->cfg.gemm_backend != E2T_GEMM_SIMT && sam == 1 && sbn == 1 && tc_gemm_tn_supported(A, sak, B, sbk, M, N, K)) {
     prof_begin(h, "tc_gemm_tn", M, N, K);
-    tc_gemm_tn(h->stream, A, sak, B, sbk, C, ldc, M, N, K, bias, beta);
+    h->unperm_applied = tc_gemm_tn(h->stream, A, sak, B, sbk, C, ldc, M, N, K, bias, beta, h->unperm_dst, h->unperm_H);
+    h->unperm_dst = nullptr;
     prof_end(h);
     ++h->n_launch;
     ++h->n_launch_tc;
     return;
   }
 #endif
+  h->unperm_dst = nullptr; h->unperm_applied = false;
   CatScope cs_(h, h->cat == E2T_CAT_RECURRENT ? E2T_CAT_RECURRENT : E2T_CAT_BULK_GEMM);
   GemmP p{};
   p.A = A; p.sam = sam; p.sak = sak;
@@ -722,15 +735,25 @@ void build_workspace(e2t_handle* h) {
   h->g_lse = h->alloc<float>(R); h->g_src = h->alloc<int>(R); h->g_tok = h->alloc<int>(R);
 }
 
+#ifndef E2T_EMU
+struct SideScope;
+void side_join_slot(e2t_handle* h, int slot);
+SideScope* side_scope_open(e2t_handle* h, int slot);
+void side_scope_close(SideScope* s);
+#endif
+
 // Re-pack the derived (transposed) weight copies from `src` (P for training, S for EMA decoding).
-void repack(e2t_handle* h, const float* src, int src_id) {
+// side_ok (training step): only the conv and the bottom encoder layer are needed at once; everything else (and the 16-bit
+// copies) is re-packed on the side stream while the conv and the first x-projection run -- the caller joins slot
+// `repack_slot` before the first recurrence (h->repack_on_side).
+void repack(e2t_handle* h, const float* src, int src_id, bool side_ok = false) {
   if (!h->packed_dirty && h->packed_src == src_id) return;
   const e2t_config& c = h->cfg;
   // all re-packs of a step go out as ONE k_batch launch
   auto tr = [&](const float* in, i64 ldi, float* out, i64 ldo, int K, int N, int permH = 0, float* out_lo = nullptr) {
     batch_transpose(h, in, ldi, out, ldo, K, N, permH, out_lo);
   };
-  for (auto& L : h->enc)
+  auto enc_layer = [&](EncLayer& L) {
     for (int d = 0; d < 2; ++d) {
       const int pH = L.rec ? L.H : 0;
       tr(src + L.K[d], 4 * L.H, L.KT[d], L.ldkt, L.In, 4 * L.H, pH);
@@ -741,6 +764,28 @@ void repack(e2t_handle* h, const float* src, int src_id) {
         batch_permute(h, h->batch, src + L.b[d], L.bP[d], (i64)1, 4 * L.H, L.H, 1);
       }
     }
+  };
+#ifndef E2T_EMU
+  std::unique_ptr<SideScope, void (*)(SideScope*)> side(nullptr, side_scope_close);   // closes on every way out
+  static const bool no_side = getenv("E2T_NO_SIDE") != nullptr || getenv("E2T_NO_SIDE_REPACK") != nullptr;
+  const bool split = side_ok && !no_side && !h->prof && c.n_enc_layers > 0 && h->enc[0].rec;
+#else
+  const bool split = false;
+#endif
+  for (int s = 0; s < c.n_subnets; ++s) {
+    int WC = c.subnet_W[s] * c.subnet_C[s];
+    // tensor-core conv: Wc^T split into its tf32-exact part and the remainder (3xTF32 forward, conv_tc.cuh)
+    tr(src + h->conv_w[s], c.E, h->conv_wT[s], round_up(WC, 4), WC, c.E, 0, h->conv_wT_lo[s]);
+  }
+  for (size_t l = 0; l < h->enc.size(); ++l) {
+    enc_layer(h->enc[l]);
+#ifndef E2T_EMU
+    if (l == 0 && split) {
+      batch_flush(h);
+      side.reset(side_scope_open(h, h->repack_slot()));
+    }
+#endif
+  }
   tr(src + h->dec_K, 4 * c.Hd, h->dec_KT, h->ld_dec_kt, c.D, 4 * c.Hd);
   tr(src + h->dec_K + (i64)c.D * 4 * c.Hd, 4 * c.Hd, h->dec_KT + h->Dp, h->ld_dec_kt, c.Hd, 4 * c.Hd);
   tr(src + h->proj_w, c.Hd, h->proj_wT, h->Vp, c.V, c.Hd);
@@ -751,11 +796,6 @@ void repack(e2t_handle* h, const float* src, int src_id) {
   }
   if (h->aux && c.aux_hidden > 0)   // W1 [In, P] -> W1^T [P, In]: the K-major B operand of the head's first GEMM
     tr(src + h->aux_w1, c.aux_hidden, h->aux_w1T, h->aux_In, h->aux_In, c.aux_hidden, 0, h->aux_w1T_lo);
-  for (int s = 0; s < c.n_subnets; ++s) {
-    int WC = c.subnet_W[s] * c.subnet_C[s];
-    // tensor-core conv: Wc^T split into its tf32-exact part and the remainder (3xTF32 forward, conv_tc.cuh)
-    tr(src + h->conv_w[s], c.E, h->conv_wT[s], round_up(WC, 4), WC, c.E, 0, h->conv_wT_lo[s]);
-  }
   batch_flush(h);
 #ifndef E2T_EMU
   {   // 16-bit copies of Wh^T for the second-generation forward recurrence: one launch for all layers / directions
@@ -798,14 +838,17 @@ void repack(e2t_handle* h, const float* src, int src_id) {
     }
   }
 #endif
+#ifndef E2T_EMU
+  if (side) { side.reset(); h->repack_on_side = true; }
+#endif
   h->packed_dirty = false;
   h->packed_src = src_id;
 }
 
-void use_weights(e2t_handle* h, bool ema) {
+void use_weights(e2t_handle* h, bool ema, bool side_ok = false) {
   bool e = ema && h->cfg.ema_decay > 0.f;
   h->Wc = e ? h->S : h->P;
-  repack(h, h->Wc, e ? 1 : 0);
+  repack(h, h->Wc, e ? 1 : 0, side_ok && !e);
 }
 
 // stage inputs; returns device pointers
@@ -939,6 +982,10 @@ void encoder_forward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, 
       lstm_xproj(h, inp, ld_in, L.In, L.H, L.KT[d], L.ldkt, L.rec ? L.bP[d] : Wc + L.b[d], L.gates[d], T2, B);
     if (use_rec(h, L, B, T2)) {
 #ifndef E2T_EMU
+      if (h->repack_on_side) {     // the upper layers' / decoder's re-packs and every 16-bit copy (repack, side_ok)
+        side_join_slot(h, h->repack_slot());
+        h->repack_on_side = false;
+      }
       CatScope cs_(h, E2T_CAT_REC_FWD);
       prof_begin(h, "rec_forward", B, L.H, T2);
       if (L.rec16) {
@@ -1210,10 +1257,16 @@ void lstm_layer_backward(e2t_handle* h, int H, const float* K, int In, float* ga
 // weight / bias / input gradients of one LSTM direction after its dz is known.
 void lstm_layer_wgrads(e2t_handle* h, const float* in, int ld_in, int In, int H, const float* K, float* dK, float* db,
                        const float* dz, const float* hs, int ldh, int col0, int steps, int B, bool reverse,
-                       const float* h_init, float* d_in, int ld_din, float beta_din, const float* db_part = nullptr, int n_part = 0) {
+                       const float* h_init, float* d_in, int ld_din, float beta_din, const float* db_part = nullptr, int n_part = 0,
+                       float* dK_canon = nullptr, int* canon_done = nullptr) {
   const i64 rows = (i64)steps * B;
+  // dK_canon: dz is in the permuted gate order and dK_canon is the canonical gradient tensor; products whose split-K
+  // reduction wrote there directly are reported in *canon_done (bit 0: dWx, bit 1: dWh), the others are left in dK
+  if (canon_done) *canon_done = 0;
   // dWx [In,4H] = in^T dz
+  if (dK_canon) { h->unperm_dst = dK_canon; h->unperm_H = H; }
   gemm(h, in, 1, ld_in, dz, 4 * H, 1, dK, 4 * H, In, 4 * H, (int)rows, nullptr, 0.f);
+  if (canon_done && h->unperm_applied) *canon_done |= 1;
   // dWh [H,4H] = hprev^T dz : forward direction pairs hs[t-1] with dz[t]; backward pairs hs[t+1] with dz[t]
   float* dWh = dK + (i64)In * 4 * H;
   const float* hp = reverse ? hs + (i64)B * ldh + col0 : hs + col0;
@@ -1234,7 +1287,11 @@ void lstm_layer_wgrads(e2t_handle* h, const float* in, int ld_in, int In, int H,
   }
 #endif
   if (!fused) {
-    if (steps > 1) gemm(h, hp, 1, ldh, dzp, 4 * H, 1, dWh, 4 * H, H, 4 * H, Krec, nullptr, 0.f);
+    if (steps > 1) {
+      if (dK_canon && !h_init) { h->unperm_dst = dK_canon + (i64)In * 4 * H; h->unperm_H = H; }
+      gemm(h, hp, 1, ldh, dzp, 4 * H, 1, dWh, 4 * H, H, 4 * H, Krec, nullptr, 0.f);
+      if (canon_done && h->unperm_applied) *canon_done |= 2;
+    }
     else E2T_CHECK(cudaMemsetAsync(dWh, 0, (size_t)H * 4 * H * sizeof(float), h->stream));
     if (h_init)   // decoder: first step's previous state is the bridge state
       gemm(h, h_init, 1, H, dz0, 4 * H, 1, dWh, 4 * H, H, 4 * H, B, nullptr, 1.f);
@@ -1251,7 +1308,14 @@ void lstm_layer_wgrads(e2t_handle* h, const float* in, int ld_in, int In, int H,
 // bucket on another stream while the rest of the backward pass runs (e2t_grad_bucket_*).  Without bucketing only the last
 // call of a step does anything.
 void bucket_done(e2t_handle* h, i64 off, i64 n, bool last) {
-  if (!h->bucketed && !last) return;
+  if (!h->bucketed && !last) {
+#ifndef E2T_EMU
+    // inside a side scope the deferred column sums / un-permutes run right here, beside a persistent recurrent kernel,
+    // instead of at the end of the step on the main stream (the 20 MB + 36 MB column sums of dlogits and the decoder's dz)
+    if (h->side_stream && h->stream == h->side_stream) batch_flush(h);
+#endif
+    return;
+  }
   batch_flush(h);
   if (!h->bucketed) { off = 0; n = h->n_params; }
   if (n <= 0) return;
@@ -1296,6 +1360,17 @@ struct SideScope {
     h->stream = saved;
   }
 };
+SideScope* side_scope_open(e2t_handle* h, int slot) { return new SideScope(h, slot); }
+void side_scope_close(SideScope* s) { delete s; }
+// the main stream waits for ONE scope (the side stream is in order: scopes opened later are not waited for)
+void side_join_slot(e2t_handle* h, int slot) {
+  for (size_t i = 0; i < h->side_pending.size(); ++i)
+    if (h->side_pending[i] == slot) {
+      E2T_CHECK(cudaStreamWaitEvent(h->stream, h->side_ev[slot], 0));
+      h->side_pending.erase(h->side_pending.begin() + (long)i);
+      return;
+    }
+}
 // the main stream goes on only after everything the side stream was given
 void side_join(e2t_handle* h) {
   for (int s : h->side_pending) E2T_CHECK(cudaStreamWaitEvent(h->stream, h->side_ev[s], 0));
@@ -1314,7 +1389,7 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
   E2T_CHECK(cudaMemsetAsync(G, 0, (size_t)h->n_params * sizeof(float), h->stream));
   h->buckets.clear();
   h->colsum_pool_used = 0;
-  h->pool_keep = h->bucketed;
+  h->pool_keep = true;      // flushes may run on both streams (bucket_done): column-sum scratch is handed out once per step
   // flat order: [conv per subject | encoder layers 0.. | decoder embedding, decoder rnn, projection, attention | aux head]
   const i64 tail_end = h->aux ? (c.aux_hidden > 0 ? h->aux_w1 : h->aux_w2) : h->n_params;
   // ---- projection: logits already hold dlogits
@@ -1488,10 +1563,14 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
           float* dKp = Ly.dKP[d];
           float* dbp = Ly.dKP[d] + (i64)(Ly.In + Ly.H) * 4 * Ly.H;
           const int n_bt = (B + 127) / 128;
+          int canon = 0;
           lstm_layer_wgrads(h, inp, ld_in, Ly.In, Ly.H, Ly.KP[d], dKp, dbp, Ly.gates[d], Ly.hs, 2 * Ly.H, d * Ly.H, T2, B,
-                            d == 1, nullptr, nullptr, ld_din, 0.f, Ly.bptt3 ? Ly.db_part + (i64)d * n_bt * 4 * Ly.H : nullptr, n_bt);
-          const i64 rows = Ly.In + Ly.H;
-          batch_permute(h, h->batch3, dKp, G + Ly.K[d], rows, 4 * Ly.H, Ly.H, 0);
+                            d == 1, nullptr, nullptr, ld_din, 0.f, Ly.bptt3 ? Ly.db_part + (i64)d * n_bt * 4 * Ly.H : nullptr, n_bt,
+                            G + Ly.K[d], &canon);
+          // (products that did not split K stay in the scratch and are un-permuted by the batched job)
+          const i64 wx = (i64)Ly.In * 4 * Ly.H;
+          if (!(canon & 1)) batch_permute(h, h->batch3, dKp, G + Ly.K[d], (i64)Ly.In, 4 * Ly.H, Ly.H, 0);
+          if (!(canon & 2)) batch_permute(h, h->batch3, dKp + wx, G + Ly.K[d] + wx, (i64)Ly.H, 4 * Ly.H, Ly.H, 0);
           batch_permute(h, h->batch3, dbp, G + Ly.b[d], (i64)1, 4 * Ly.H, Ly.H, 0);
         } else {
           lstm_layer_wgrads(h, inp, ld_in, Ly.In, Ly.H, P + Ly.K[d], G + Ly.K[d], G + Ly.b[d], Ly.gates[d], Ly.hs, 2 * Ly.H,
@@ -1754,7 +1833,7 @@ extern "C" int e2t_train_step_grads(e2t_handle* h, int subnet, const float* x, c
   E2T_REQUIRE((y != nullptr || loc == E2T_STAGED0 || loc == E2T_STAGED1) && L >= 1, "training needs targets");
   Inputs in = stage(h, subnet, x, lens, y, loc, B, T, L);
   E2T_REQUIRE(in.y != nullptr, "training needs targets");
-  use_weights(h, false);
+  use_weights(h, false, true);
   bool dec_hoist = false;
 #ifndef E2T_EMU
   {

@@ -410,6 +410,41 @@ __global__ void k_splitk_reduce(const float* __restrict__ ws, int ksplit, int M,
   if (beta != 0.f) a += beta * (*c);
   *c = a;
 }
+// The same sum (same order, so bit-identical) with 16-byte accesses and four partial loads in flight; N % 4 == 0, 16-byte
+// aligned rows of C.  unpermH > 0: the GEMM's columns are in the gate order of the persistent recurrent kernels
+// (e2t_gate_perm) and C is the canonical tensor -- column n' = 64 (u/16) + 32 ((u%16)/8) + 8 g + u%8 lands at g H + u, so a
+// weight gradient goes straight into the flat gradient buffer (runs of 8 columns stay contiguous: float4 stores).
+__global__ void __launch_bounds__(256) k_splitk_reduce4(const float4* __restrict__ ws, int ksplit, int M, int N4, float* C,
+                                                        i64 ldc, const float* __restrict__ bias, float beta, int unpermH) {
+  const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 total = (i64)M * N4;
+  if (i >= total) return;
+  const int m = (int)(i / N4), n = (int)(i - (i64)m * N4) * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* w = ws + i;
+  int s = 0;
+  for (; s + 4 <= ksplit; s += 4) {
+    const float4 v0 = w[(size_t)s * total], v1 = w[(size_t)(s + 1) * total];
+    const float4 v2 = w[(size_t)(s + 2) * total], v3 = w[(size_t)(s + 3) * total];
+    a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
+    a.x += v1.x; a.y += v1.y; a.z += v1.z; a.w += v1.w;
+    a.x += v2.x; a.y += v2.y; a.z += v2.z; a.w += v2.w;
+    a.x += v3.x; a.y += v3.y; a.z += v3.z; a.w += v3.w;
+  }
+  for (; s < ksplit; ++s) {
+    const float4 v = w[(size_t)s * total];
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  if (bias) { a.x += bias[n]; a.y += bias[n + 1]; a.z += bias[n + 2]; a.w += bias[n + 3]; }
+  int nn = n;
+  if (unpermH > 0) {
+    const int r = n & 63;
+    nn = ((r & 31) >> 3) * unpermH + (n >> 6) * 16 + (r >> 5) * 8 + (r & 7);
+  }
+  float4* c = reinterpret_cast<float4*>(C + (i64)m * ldc + nn);
+  if (beta != 0.f) { const float4 o = *c; a.x += beta * o.x; a.y += beta * o.y; a.z += beta * o.z; a.w += beta * o.w; }
+  *c = a;
+}
 
 // ---- host side ------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -509,10 +544,13 @@ inline void pick_tiling(int M, int N, int num_kb, bool tn, int nsm, int* bn_out,
 
 // Optional second operand pair (A2, B2, K2): C = A B^T + A2 B2^T (+bias, +beta C) in ONE pass over C -- the two LSTM
 // directions' contributions to d(input), or [x_t, h_{t-1}] [Wx; Wh] of a decoder step, without a read-modify-write of C.
+// C_unperm / unpermH: the product's columns are in the recurrent kernels' gate order and `C_unperm` (leading dimension N) is
+// the canonical tensor; when the launch splits K, its reduction writes there directly (returns true) and C is not touched;
+// otherwise C holds the permuted product as usual (returns false) and the caller un-permutes.
 template <bool TN>
-inline void launch_gemm(cudaStream_t st, const float* A, i64 lda, const float* B, i64 ldb, float* C, i64 ldc, int M, int N,
+inline bool launch_gemm(cudaStream_t st, const float* A, i64 lda, const float* B, i64 ldb, float* C, i64 ldc, int M, int N,
                         int K, const float* bias, float beta, const float* A2 = nullptr, i64 lda2 = 0,
-                        const float* B2 = nullptr, i64 ldb2 = 0, int K2 = 0) {
+                        const float* B2 = nullptr, i64 ldb2 = 0, int K2 = 0, float* C_unperm = nullptr, int unpermH = 0) {
   const int nsm = sm_count_();
   TcGemmP p{};
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.beta = beta;
@@ -580,8 +618,19 @@ inline void launch_gemm(cudaStream_t st, const float* A, i64 lda, const float* B
   }
   if (p.ksplit > 1) {
     const i64 n = (i64)M * N;
-    k_splitk_reduce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.ws, p.ksplit, M, N, C, ldc, bias, beta);
+    static const bool scalar_reduce = getenv("E2T_SPLITK_SCALAR") != nullptr;
+    const bool unperm = C_unperm != nullptr && unpermH > 0 && (unpermH & 3) == 0 && (N & 63) == 0 && N == 4 * unpermH &&
+                        (reinterpret_cast<uintptr_t>(C_unperm) & 15) == 0 && !scalar_reduce;
+    float* Co = unperm ? C_unperm : C;
+    const i64 ldo = unperm ? (i64)N : ldc;
+    if (!scalar_reduce && (N & 3) == 0 && (ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(Co) & 15) == 0)
+      k_splitk_reduce4<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(p.ws), p.ksplit, M, N / 4,
+                                                                         Co, ldo, bias, beta, unperm ? unpermH : 0);
+    else
+      k_splitk_reduce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.ws, p.ksplit, M, N, C, ldc, bias, beta);
+    return unperm;
   }
+  return false;
 }
 
 }  // namespace tc
@@ -617,9 +666,9 @@ static inline bool tc_gemm_tn_supported(const float* A, i64 lda, const float* B,
   if ((i64)M * N * K < (i64)64 * 64 * 64) return false;
   return true;
 }
-static inline void tc_gemm_tn(cudaStream_t st, const float* A, i64 lda, const float* B, i64 ldb, float* C, i64 ldc, int M,
-                              int N, int K, const float* bias, float beta) {
-  tc::launch_gemm<true>(st, A, lda, B, ldb, C, ldc, M, N, K, bias, beta);
+static inline bool tc_gemm_tn(cudaStream_t st, const float* A, i64 lda, const float* B, i64 ldb, float* C, i64 ldc, int M,
+                              int N, int K, const float* bias, float beta, float* C_unperm = nullptr, int unpermH = 0) {
+  return tc::launch_gemm<true>(st, A, lda, B, ldb, C, ldc, M, N, K, bias, beta, nullptr, 0, nullptr, 0, 0, C_unperm, unpermH);
 }
 
 // times `iters` back-to-back launches of one GEMM shape on zero-filled operands (diagnostic; e2t_bench_gemm)
