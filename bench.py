@@ -192,7 +192,13 @@ def main():
                          "-- auto = flat")
     ap.add_argument("--no-decode", action="store_true", help="skip the greedy / beam-8 decode legs")
     ap.add_argument("--decode-utterances", type=int, default=10000, help="utterances decoded per leg, sharded over the ranks")
+    ap.add_argument("--watchdog", type=int, default=int(os.environ.get("E2T_BENCH_WATCHDOG", "900")),
+                    help="seconds after which a run that has not finished dumps every thread's Python stack to stderr and "
+                         "exits non-zero (0 = off): a wedged GPU or collective must not hang the caller")
     args = ap.parse_args()
+    if args.watchdog > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))

@@ -83,6 +83,42 @@ def test_persistent_kernels_are_deterministic(gpu_lib):
         assert np.array_equal(outs[0][k], outs[1][k]), k
 
 
+def test_side_stream_steps_equal_single_stream(gpu_lib):
+    """K optimiser steps with everything the side stream takes (weight gradients, re-packs, the upper tensors' Adam step,
+    deferred column sums; joined lazily: DESIGN.md 3.2b) against the same K steps in profiling mode, which keeps every
+    launch on ONE stream: weights, EMA shadows and Adam moments must be BIT-identical, read both through the tensor API
+    and right behind the last optimiser step (param_join)."""
+    import numpy as np
+    from ecog2txt_b200 import _lib
+    from oracle import seq2seq_oracle as O
+    ocfg = O.OracleConfig(**pc.WIDE)
+    P = pc.make_params(ocfg)
+    batches = [pc.make_batch(ocfg, 64, 80, 5, seed=s) for s in range(3)]
+    res = []
+    for single_stream in (False, True):
+        eng = pc.engine_for(pc.WIDE, gpu_lib, 64, 80, 5, gemm_backend="auto")
+        eng.set_all({k: v.numpy() for k, v in P.items()})
+        if single_stream:
+            eng.profile_enable(True)
+        for i, (x, lens, y) in enumerate(batches):
+            _, ntok = eng.train_step_grads(x, None, y, seed=i)
+            eng.adam_ema_step(1.0 / ntok)
+        out = {w: eng.get_all(w) for w in (_lib.VALUE, _lib.EMA, _lib.ADAM_M, _lib.ADAM_V)}   # right behind the step
+        # ... and a decode right behind another step sees the updated weights too
+        x, lens, y = batches[0]
+        _, ntok = eng.train_step_grads(x, None, y, seed=7)
+        eng.adam_ema_step(1.0 / ntok)
+        toks, _ = eng.greedy_decode(x[:8], None, max_len=5, use_ema=False)
+        res.append((out, toks))
+        eng.close()
+    for w in res[0][0]:
+        for k in res[0][0][w]:
+            if "decoder_embedding" in k and k.endswith("weights"):
+                continue   # atomicAdd scatter: order-dependent rounding
+            assert np.array_equal(res[0][0][w][k], res[1][0][w][k]), (w, k)
+    assert np.array_equal(res[0][1], res[1][1])
+
+
 @pytest.mark.parametrize("backend,tol", [("simt", 2e-4), ("auto", 1e-2)])
 def test_attention_train_and_decode(gpu_lib, backend, tol):
     """A7 (optional Luong attention): training step (loss, every gradient incl. the attention tensors and the encoder

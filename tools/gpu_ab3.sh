@@ -1,9 +1,10 @@
 #!/bin/bash
 # one gpurun call: the full GPU suite, then the bench line under several environment settings (same box, alternating).
+# PYTEST_K="expr" restricts the suite.
 # usage: gpu_ab3.sh TAG "ENV1=a ENV2=b" "ENV3=c" ...   (each argument is one setting; "-" = defaults)
 mkdir -p gpurun_out
 TAG=${1:-ab3}; shift
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -x -q ${PYTEST_K:+-k "$PYTEST_K"} > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -4 gpurun_out/pytest_gpu.log
 for rep in 1 2; do
 i=0
