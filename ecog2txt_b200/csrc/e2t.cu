@@ -223,6 +223,7 @@ struct e2t_handle {
   // decode workspace
   float *g_h[3], *g_c[3], *g_e, *g_z, *g_logits, *g_logp, *g_score[2], *g_lse;
   int *g_prev[2], *g_done[2], *g_tokens[2], *g_src, *g_tok;
+  float* g_small_ws = nullptr; int* g_small_cnt = nullptr;   // k_dec_small_pick: per-block partials, ticket counter
   // last-forward bookkeeping for e2t_get_activation
   int last_B = 0, last_T2 = 0, last_L = 0, last_subnet = 0;
 
@@ -733,6 +734,8 @@ void build_workspace(e2t_handle* h) {
   h->g_e = h->alloc<float>(R * h->Dp); h->g_z = h->alloc<float>(R * 4 * c.Hd);
   h->g_logits = h->alloc<float>(R * h->Vp); h->g_logp = h->alloc<float>(R * Lm);
   h->g_lse = h->alloc<float>(R); h->g_src = h->alloc<int>(R); h->g_tok = h->alloc<int>(R);
+  h->g_small_ws = h->alloc<float>((i64)cdiv(c.V, 8) * kDecSmallRows * 3);
+  h->g_small_cnt = h->alloc<int>(4);
 }
 
 #ifndef E2T_EMU
@@ -2137,11 +2140,35 @@ static void greedy_body(e2t_handle* h, int subnet, const Inputs& in, int B, int 
   LAUNCH(h, k_fill_int, grid1(B), dim3(256), 0, h->g_prev[0], c.start_id, (i64)B);
   E2T_CHECK(cudaMemsetAsync(h->g_done[0], 0, (size_t)B * sizeof(int), h->stream));
   const float* hin = h->h0; const float* cin = h->c0;
+  // online-predictor regime (a handful of utterances): two matrix-vector launches per step instead of five batched ones
+  // (measured at config 2 through the graph replay, tools/time_b1.py: B = 1 0.90 vs 1.14 ms per call, B = 4 1.13 vs 1.27,
+  //  B = 8 1.46 vs 1.40 -- the kernels take up to kDecSmallRows rows, the dispatch stops at 4)
+  static const bool no_small = getenv("E2T_NO_SMALL_DECODE") != nullptr;
+  static const int small_rows = getenv("E2T_SMALL_DECODE_ROWS") ? std::max(0, std::min(kDecSmallRows, atoi(getenv("E2T_SMALL_DECODE_ROWS")))) : 4;
+  const size_t smem_cell = ((size_t)B * (h->Dp + c.Hd) + 4 * kDecSmallUnits * B) * sizeof(float);
+  const size_t smem_pick = ((size_t)B * c.Hd + 8 * B) * sizeof(float);
+  const bool small = B <= small_rows && c.attention == E2T_ATTN_NONE && (c.Hd & 3) == 0 && (h->ld_dec_kt & 3) == 0 &&
+                     smem_cell <= 48 * 1024 && smem_pick <= 48 * 1024 && !no_small;
   for (int k = 0; k < max_len; ++k) {
     float* ho = h->g_h[k & 1]; float* co = h->g_c[k & 1];
-    decode_step(h, B, h->g_prev[0], hin, cin, ho, co, B, 1);
-    LAUNCH(h, k_greedy_pick, dim3(B), dim3(128), 0, h->g_logits, h->Vp, c.V, 1.0f / temperature, k, max_len, c.pad_id,
-           c.eos_id, h->g_prev[0], h->g_done[0], h->g_tokens[0], h->g_logp);
+    if (small) {
+      const float* Wc = h->Wc;
+      DecSmallP a{};
+      a.prev = h->g_prev[0]; a.emb = Wc + h->demb_w; a.emb_b = Wc + h->demb_b; a.act = c.emb_act;
+      a.KT = h->dec_KT; a.ldk = h->ld_dec_kt; a.bias = Wc + h->dec_b;
+      a.h_in = hin; a.c_in = cin; a.h_out = ho; a.c_out = co; a.R = B; a.D = c.D; a.Dp = h->Dp; a.Hd = c.Hd;
+      LAUNCH(h, k_dec_small_cell, dim3((unsigned)cdiv(c.Hd, kDecSmallUnits)), dim3(256), smem_cell, a);
+      DecPickP q{};
+      q.h = ho; q.Wp = Wc + h->proj_w; q.bp = Wc + h->proj_b; q.V = c.V; q.Hd = c.Hd; q.R = B;
+      q.inv_temp = 1.0f / temperature; q.k = k; q.max_len = max_len; q.pad_id = c.pad_id; q.eos_id = c.eos_id;
+      q.prev = h->g_prev[0]; q.done = h->g_done[0]; q.tokens = h->g_tokens[0]; q.logp = h->g_logp;
+      q.ws = h->g_small_ws; q.counter = h->g_small_cnt;
+      LAUNCH(h, k_dec_small_pick, dim3((unsigned)cdiv(c.V, 8)), dim3(256), smem_pick, q);
+    } else {
+      decode_step(h, B, h->g_prev[0], hin, cin, ho, co, B, 1);
+      LAUNCH(h, k_greedy_pick, dim3(B), dim3(128), 0, h->g_logits, h->Vp, c.V, 1.0f / temperature, k, max_len, c.pad_id,
+             c.eos_id, h->g_prev[0], h->g_done[0], h->g_tokens[0], h->g_logp);
+    }
     hin = ho; cin = co;
   }
 }

@@ -1026,6 +1026,166 @@ __global__ void __launch_bounds__(128) k_greedy_pick(const float* logits, int ld
 }
 
 // ------------------------------------------------------------------------------------------------
+// A11 / N3, the online-predictor regime (construct_online_predictor, trainers.py:925-949: one utterance at a time).  With
+// R <= 8 state rows a decoder step is two matrix-VECTOR products over 18 MB of weights that sit in L2 after the first
+// step; the batched path runs it as 5 launches (embedding, a 128-row tensor-core GEMM that is 127/128 padding, cell,
+// projection GEMM, pick).  Here it is two:
+//   k_dec_small_cell  z = [act(Emb[prev] + b_e), h] [Wx; Wh] + b (rows of the transposed kernel are contiguous: one warp
+//                     per gate row, 16-byte loads, the R input vectors staged once per block in shared memory in the
+//                     row's own layout), then the cell update of the block's units -- fp32 CUDA cores
+//   k_dec_small_pick  logits = h Wp^T + b_p (one warp per vocabulary row), per-block (max, lowest arg-max, sum of exp)
+//                     partials, and the LAST block to arrive (ticket counter) merges them and does what k_greedy_pick
+//                     does: token, log-probability under softmax(logits / temperature), done flags
+// ------------------------------------------------------------------------------------------------
+constexpr int kDecSmallRows = 8;      // state rows handled by the small-batch decode kernels
+constexpr int kDecSmallUnits = 2;     // hidden units per block of k_dec_small_cell (4 gates x 2 units = 8 warps)
+struct DecSmallP {
+  const int* prev; const float* emb; const float* emb_b; int act;
+  const float* KT; int ldk; const float* bias;          // transposed decoder kernel [4Hd][ldk]: [0, D) embedding part, [Dp, Dp + Hd) state part
+  const float* h_in; const float* c_in; float* h_out; float* c_out;
+  int R, D, Dp, Hd;
+};
+__global__ void __launch_bounds__(256) k_dec_small_cell(DecSmallP p) {
+  E2T_DYN_SMEM(float, v);                   // [R][Kp] input vectors in the layout of a kernel row, then zs [8][R]
+  const int Kp = p.Dp + p.Hd, R = p.R;
+  for (int i = threadIdx.x; i < R * Kp; i += blockDim.x) {
+    const int r = i / Kp, k = i - r * Kp;
+    float x = 0.f;
+    if (k < p.D) {
+      x = p.emb[(i64)p.prev[r] * p.D + k] + p.emb_b[k];
+      if (p.act == 1) x = fmaxf(x, 0.f);
+    } else if (k >= p.Dp) x = p.h_in[(i64)r * p.Hd + (k - p.Dp)];
+    v[i] = x;
+  }
+  __syncthreads();
+  float* zs = v + R * Kp;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = w / kDecSmallUnits, uu = w - g * kDecSmallUnits;
+  const int u = blockIdx.x * kDecSmallUnits + uu;
+  if (u < p.Hd) {
+    const int n = g * p.Hd + u;
+    const float4* wrow = reinterpret_cast<const float4*>(p.KT + (i64)n * p.ldk);
+    const float4* v4 = reinterpret_cast<const float4*>(v);
+    const int K4 = Kp >> 2;
+    float acc[kDecSmallRows];
+#pragma unroll
+    for (int r = 0; r < kDecSmallRows; ++r) acc[r] = 0.f;
+    for (int k4 = lane; k4 < K4; k4 += 32) {
+      const float4 a = wrow[k4];
+#pragma unroll
+      for (int r = 0; r < kDecSmallRows; ++r)
+        if (r < R) {
+          const float4 x = v4[r * K4 + k4];
+          acc[r] += a.x * x.x + a.y * x.y + a.z * x.z + a.w * x.w;
+        }
+    }
+    const float bn = p.bias[n];
+#pragma unroll
+    for (int r = 0; r < kDecSmallRows; ++r)
+      if (r < R) {
+        const float t = warp_sum(acc[r]);
+        if (lane == 0) zs[w * R + r] = t + bn;
+      }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < kDecSmallUnits * R) {
+    const int uu2 = threadIdx.x / R, r = threadIdx.x - uu2 * R;
+    const int u2 = blockIdx.x * kDecSmallUnits + uu2;
+    if (u2 < p.Hd) {      // TF1 LSTMCell: gates i, j, f, o; forget bias 1 (k_lstm_fwd)
+      const float gi = sigmoidf_(zs[(0 * kDecSmallUnits + uu2) * R + r]);
+      const float gj = tanhf(zs[(1 * kDecSmallUnits + uu2) * R + r]);
+      const float gf = sigmoidf_(zs[(2 * kDecSmallUnits + uu2) * R + r] + 1.0f);
+      const float go = sigmoidf_(zs[(3 * kDecSmallUnits + uu2) * R + r]);
+      const float c = gf * p.c_in[(i64)r * p.Hd + u2] + gi * gj;
+      p.c_out[(i64)r * p.Hd + u2] = c;
+      p.h_out[(i64)r * p.Hd + u2] = go * tanhf(c);
+    }
+  }
+}
+struct DecPickP {
+  const float* h; const float* Wp; const float* bp;     // state rows [R][Hd], canonical projection [V][Hd], bias [V]
+  int V, Hd, R; float inv_temp; int k, max_len, pad_id, eos_id;
+  int* prev; int* done; int* tokens; float* logp;
+  float* ws; int* counter;                              // [gridDim.x][R][3] partials; ticket counter (0 between launches)
+};
+__global__ void __launch_bounds__(256) k_dec_small_pick(DecPickP p) {
+  E2T_DYN_SMEM(float, hs);                  // [R][Hd] state rows, then lg [8][R]
+  __shared__ int is_last;
+  const int R = p.R, Hd = p.Hd;
+  for (int i = threadIdx.x; i < R * Hd; i += blockDim.x) hs[i] = p.h[i];
+  __syncthreads();
+  float* lg = hs + R * Hd;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int vrow = blockIdx.x * 8 + w;
+  if (vrow < p.V) {
+    const float4* wrow = reinterpret_cast<const float4*>(p.Wp + (i64)vrow * Hd);
+    const float4* h4 = reinterpret_cast<const float4*>(hs);
+    const int K4 = Hd >> 2;
+    float acc[kDecSmallRows];
+#pragma unroll
+    for (int r = 0; r < kDecSmallRows; ++r) acc[r] = 0.f;
+    for (int k4 = lane; k4 < K4; k4 += 32) {
+      const float4 a = wrow[k4];
+#pragma unroll
+      for (int r = 0; r < kDecSmallRows; ++r)
+        if (r < R) {
+          const float4 x = h4[r * K4 + k4];
+          acc[r] += a.x * x.x + a.y * x.y + a.z * x.z + a.w * x.w;
+        }
+    }
+    const float bv = p.bp[vrow];
+#pragma unroll
+    for (int r = 0; r < kDecSmallRows; ++r)
+      if (r < R) {
+        const float t = warp_sum(acc[r]);
+        if (lane == 0) lg[w * R + r] = t + bv;
+      }
+  } else if (lane < R) lg[w * R + lane] = -3.0e38f;
+  __syncthreads();
+  if ((int)threadIdx.x < R) {
+    const int r = threadIdx.x;
+    float mx = -3.0e38f; int wi = 0;
+    for (int i = 0; i < 8; ++i)
+      if (lg[i * R + r] > mx) { mx = lg[i * R + r]; wi = i; }       // strict >: the lowest index wins ties
+    float sum = 0.f;
+    for (int i = 0; i < 8; ++i)
+      if (blockIdx.x * 8 + i < (unsigned)p.V) sum += expf((lg[i * R + r] - mx) * p.inv_temp);
+    float* o = p.ws + ((i64)blockIdx.x * R + r) * 3;
+    o[0] = mx; o[1] = (float)(blockIdx.x * 8 + wi); o[2] = sum;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(p.counter, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (w < R) {        // one warp per state row merges the blocks' partials (blocks cover ascending vocabulary ranges)
+    const int r = w;
+    const volatile float* ws = p.ws;
+    float mx = -3.0e38f;
+    for (int b = lane; b < (int)gridDim.x; b += 32) mx = fmaxf(mx, ws[((i64)b * R + r) * 3]);
+    mx = warp_max(mx);
+    float bi = -3.0e38f, sum = 0.f;
+    for (int b = lane; b < (int)gridDim.x; b += 32) {
+      const float bm = ws[((i64)b * R + r) * 3];
+      if (bm == mx) bi = fmaxf(bi, -ws[((i64)b * R + r) * 3 + 1]);       // lowest index attaining the max
+      sum += ws[((i64)b * R + r) * 3 + 2] * expf((bm - mx) * p.inv_temp);
+    }
+    bi = warp_max(bi);
+    sum = warp_sum(sum);
+    if (lane == 0) {
+      const int best = (int)(-bi + 0.5f);
+      const int was_done = p.done[r];
+      p.tokens[(i64)r * p.max_len + p.k] = was_done ? p.pad_id : best;
+      if (p.logp) p.logp[(i64)r * p.max_len + p.k] = was_done ? 0.f : -logf(sum);
+      if (!was_done) p.prev[r] = best;
+      p.done[r] = was_done | (best == p.eos_id);
+    }
+  }
+  if (threadIdx.x == 0) *p.counter = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // tiled transpose: out[n*ldo + k] = in[k*ldi + n] for k < K, n < N  (weight re-packing)
 // ------------------------------------------------------------------------------------------------
 // Gate-column permutation of the layers run by the persistent recurrent kernels (lstm_rec.cuh): canonical

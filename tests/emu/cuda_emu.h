@@ -90,6 +90,7 @@ static inline int __shfl_sync(unsigned, int v, int s) {
 static inline float atomicAdd(float* p, float v) { float o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+static inline void __threadfence() {}
 static inline int atomicMax(int* p, int v) { int o = *p; *p = std::max(o, v); return o; }
 // fast-math intrinsics: plain libm here
 #define __expf(x) expf(x)

@@ -119,6 +119,31 @@ def test_side_stream_steps_equal_single_stream(gpu_lib):
     assert np.array_equal(res[0][1], res[1][1])
 
 
+@pytest.mark.parametrize("backend", ["simt", "auto"])
+def test_small_batch_greedy_decode(gpu_lib, backend):
+    """N3: k_dec_small_cell / k_dec_small_pick (at most 4 utterances) against the oracle at the decoder width of config 2
+    (Hd = 800; batches whose oracle top-2 gaps are >= 6e-3 at every live step), and -- fp32 backend, where both paths are
+    fp32 -- against the batched decode step on the same utterances."""
+    import numpy as np
+    from oracle import seq2seq_oracle as O
+    for B in (1, 3):
+        pc.check_decode(gpu_lib, pc.WIDE, B, 100, 8, backend=backend, name=f"decode/{backend}/small_batch/B{B}")
+    if backend != "simt":
+        return
+    ocfg = O.OracleConfig(**pc.WIDE)
+    P = pc.make_params(ocfg, eos_bias=-1.0)
+    x, _, _ = pc.make_batch(ocfg, 5, 100, 4)
+    eng = pc.engine_for(pc.WIDE, gpu_lib, 5, 100, 8, gemm_backend=backend)
+    eng.set_all({k: v.numpy() for k, v in P.items()})
+    t5, lp5 = eng.greedy_decode(x, None, max_len=8, temperature=0.5)
+    t4, lp4 = eng.greedy_decode(np.ascontiguousarray(x[:4]), None, max_len=8, temperature=0.5)
+    eng.close()
+    d = float(np.abs(lp4 - lp5[:4]).max())
+    pc.record(f"decode/{backend}/small_batch_vs_batched", logp_abs=d, rows_identical=float((t4 == t5[:4]).all(1).mean()))
+    assert (t4 == t5[:4]).all()
+    assert d < 1e-4
+
+
 @pytest.mark.parametrize("backend,tol", [("simt", 2e-4), ("auto", 1e-2)])
 def test_attention_train_and_decode(gpu_lib, backend, tol):
     """A7 (optional Luong attention): training step (loss, every gradient incl. the attention tensors and the encoder

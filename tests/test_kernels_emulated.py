@@ -321,3 +321,28 @@ def test_size_independent_properties(emu_lib):
         acc = gh if acc is None else {k: acc[k] + gh[k] for k in gh}
     assert abs(ltot - loss) <= 1e-4 * abs(loss) and all(pc.rel_err(acc[k], g1[k]) <= 1e-4 for k in g1)
     eng.close()
+
+
+@pytest.mark.parametrize("geo,B,T", [(pc.TINY, 1, 21), (pc.TINY, 3, 21), (pc.SMALL, 4, 50)])
+def test_small_batch_greedy_decode(emu_lib, geo, B, T):
+    """N3 (online predictor): with at most 4 utterances the decode steps run as k_dec_small_cell / k_dec_small_pick (two
+    matrix-vector launches per step, arg-max merged by the last block to arrive) -- against the oracle, one utterance, the
+    4-row dispatch boundary, a vocabulary that is not a multiple of the 8 rows per block, D not a multiple of 4."""
+    pc.check_decode(emu_lib, geo, B, T, 6, name=f"emu/small_decode/B{B}")
+    pc.check_decode(emu_lib, geo, B, T, 6, temperature=0.3, use_ema=True, name=f"emu/small_decode/B{B}_ema")
+
+
+def test_small_batch_decode_equals_batched_path(emu_lib):
+    """The same utterances through the small-batch kernels (B = 4) and the batched decode step (B = 5: GEMM + cell +
+    projection + k_greedy_pick): identical tokens, log-probabilities to fp32 rounding."""
+    from oracle import seq2seq_oracle as O
+    ocfg = O.OracleConfig(**pc.SMALL)
+    P = pc.make_params(ocfg, eos_bias=-1.0)
+    x, _, _ = pc.make_batch(ocfg, 5, 50, 4)
+    eng = pc.engine_for(pc.SMALL, emu_lib, 5, 50, 6, gemm_backend="simt")
+    eng.set_all({k: v.numpy() for k, v in P.items()})
+    t5, lp5 = eng.greedy_decode(x, None, max_len=6, temperature=0.5)
+    t4, lp4 = eng.greedy_decode(np.ascontiguousarray(x[:4]), None, max_len=6, temperature=0.5)
+    eng.close()
+    assert (t4 == t5[:4]).all()
+    assert np.abs(lp4 - lp5[:4]).max() < 1e-5
