@@ -18,7 +18,7 @@ ACT = {"linear": 0, "relu": 1}
 GEMM = {"auto": 0, "simt": 1, "tcgen05": 2}
 ATTN = {"none": 0, "luong": 1, "bahdanau": 2}
 AUX_KIND = {"gaussian": 0, "categorical": 1}
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class E2TConfig(C.Structure):
@@ -58,6 +58,7 @@ class E2TConfig(C.Structure):
         ("aux_F", C.c_int32),
         ("aux_kind", C.c_int32),
         ("aux_penalty", C.c_float),
+        ("proj_hidden", C.c_int32),
     ]
 
 

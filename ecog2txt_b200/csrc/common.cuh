@@ -52,7 +52,7 @@ static inline uint32_t e2t_thresh(float p) {
   return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
 }
 // dropout stream ids (oracle: STREAM_CONV, STREAM_ENC0 + l, STREAM_DEMB)
-enum { E2T_STREAM_CONV = 0, E2T_STREAM_ENC0 = 1, E2T_STREAM_DEMB = 64, E2T_STREAM_AUX = 96 };
+enum { E2T_STREAM_CONV = 0, E2T_STREAM_ENC0 = 1, E2T_STREAM_DEMB = 64, E2T_STREAM_AUX = 96, E2T_STREAM_PROJ = 112 };
 
 struct DropP {  // p == 0 <=> thresh == 0 && inv == 1
   uint32_t key, thresh;

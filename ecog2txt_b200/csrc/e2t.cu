@@ -36,7 +36,7 @@
 
 static thread_local std::string g_err;
 extern "C" const char* e2t_last_error(void) { return g_err.c_str(); }
-extern "C" int e2t_abi_version(void) { return 8; }
+extern "C" int e2t_abi_version(void) { return 9; }
 
 namespace {
 
@@ -152,7 +152,12 @@ struct e2t_handle {
   int Bm, Tm, Lm, T2m, Cmax, Dp, Vp, beam_m;
   // packed decoder weights
   float* dec_KT = nullptr; int ld_dec_kt = 0;   // [4Hd, D+Hd (padded)]
-  float* proj_wT = nullptr;                      // [Hd, Vp]
+  float* proj_wT = nullptr;                      // [PI, Vp], PI = width of the final projection's input (Hd, or proj_hidden)
+  // optional hidden decoder_projection layer (cfg.proj_hidden > 0): parameter offsets, K-major copy of W1, activations
+  i64 proj_w1 = 0, proj_b1 = 0;
+  int Pp = 0;                                    // round_up(proj_hidden, 4): row pitch of pz1 / dpz1 / g_pz
+  float *proj_w1T = nullptr, *pz1 = nullptr, *dpz1 = nullptr, *g_pz = nullptr;
+  int proj_in_width() const { return cfg.proj_hidden > 0 ? cfg.proj_hidden : cfg.Hd; }
   float* conv_wT[E2T_MAX_SUBNETS];               // [E, W*C]
   float* conv_wT_lo[E2T_MAX_SUBNETS];            // tf32 remainder of conv_wT (conv_wT then holds the tf32-exact part)
 
@@ -510,8 +515,16 @@ void build_params(e2t_handle* h) {
   const char* rb = "seq2seq/decoder_rnn/multi_rnn_cell/cell_0/lstm_cell";
   h->dec_K = h->n_params; add_tensor(h, std::string(rb) + "/kernel", {c.D + c.Hd, 4 * c.Hd}, -1);
   h->dec_b = h->n_params; add_tensor(h, std::string(rb) + "/bias", {4 * c.Hd}, -1);
-  snprintf(buf, sizeof buf, "seq2seq/decoder_projection_%d_%d_0", c.Hd, c.V);
-  h->proj_w = h->n_params; add_tensor(h, std::string(buf) + "/weights", {c.V, c.Hd}, -1);
+  if (c.proj_hidden > 0) {
+    // '<x>_projection' scopes number their layers; only the LAST layer's weight is stored transposed (trainers.py:488-520)
+    snprintf(buf, sizeof buf, "seq2seq/decoder_projection_%d_%d_0", c.Hd, c.proj_hidden);
+    h->proj_w1 = h->n_params; add_tensor(h, std::string(buf) + "/weights", {c.Hd, c.proj_hidden}, -1);
+    h->proj_b1 = h->n_params; add_tensor(h, std::string(buf) + "/biases", {c.proj_hidden}, -1);
+    snprintf(buf, sizeof buf, "seq2seq/decoder_projection_%d_%d_1", c.proj_hidden, c.V);
+  } else {
+    snprintf(buf, sizeof buf, "seq2seq/decoder_projection_%d_%d_0", c.Hd, c.V);
+  }
+  h->proj_w = h->n_params; add_tensor(h, std::string(buf) + "/weights", {c.V, h->proj_in_width()}, -1);
   h->proj_b = h->n_params; add_tensor(h, std::string(buf) + "/biases", {c.V}, -1);
   if (c.attention != E2T_ATTN_NONE) {
     // stored [out, in] like the projection (trainers.py:513-520), i.e. already the K-major B operand of the forward GEMMs
@@ -557,6 +570,7 @@ void validate(const e2t_config& c) {
   E2T_REQUIRE(c.attention == E2T_ATTN_NONE || c.attention == E2T_ATTN_LUONG || c.attention == E2T_ATTN_BAHDANAU,
               "attention must be E2T_ATTN_NONE, E2T_ATTN_LUONG or E2T_ATTN_BAHDANAU");
   E2T_REQUIRE(c.aux_F >= 0 && c.aux_hidden >= 0, "aux_F / aux_hidden must be >= 0");
+  E2T_REQUIRE(c.proj_hidden >= 0, "proj_hidden must be >= 0");
   if (c.aux_F > 0) {
     E2T_REQUIRE(c.aux_layer >= 0 && c.aux_layer < c.n_enc_layers, "aux_layer must name an encoder layer");
     E2T_REQUIRE(c.aux_kind == E2T_AUX_GAUSSIAN || c.aux_kind == E2T_AUX_CATEGORICAL, "aux_kind must be E2T_AUX_*");
@@ -660,7 +674,8 @@ void build_workspace(e2t_handle* h) {
   h->colsum_ws = h->alloc<float>(h->colsum_ws_n);
   if (h->perm_ws_n) h->perm_ws = h->alloc<float>(h->perm_ws_n);
   {
-    i64 ncols = h->Vp + 4 * c.Hd + h->Dp + c.E + 3 * c.Hd + round_up(c.aux_F, 4) + round_up(c.aux_hidden, 4);
+    i64 ncols = h->Vp + 4 * c.Hd + h->Dp + c.E + 3 * c.Hd + round_up(c.aux_F, 4) + round_up(c.aux_hidden, 4) +
+                round_up(c.proj_hidden, 4);
     for (auto& L : h->enc) ncols += 2 * 4 * L.H;
     h->colsum_pool_n = 64 * ncols;
     h->colsum_pool = h->alloc<float>(h->colsum_pool_n);
@@ -676,7 +691,13 @@ void build_workspace(e2t_handle* h) {
   h->rec_counters = h->alloc<int>((i64)2 * cdiv(Bm, 128) * std::max<i64>(T2, Lm));
   h->ld_dec_kt = h->Dp + round_up(c.Hd, 4);
   h->dec_KT = h->alloc<float>((i64)4 * c.Hd * h->ld_dec_kt);
-  h->proj_wT = h->alloc<float>((i64)c.Hd * h->Vp);
+  h->proj_wT = h->alloc<float>((i64)h->proj_in_width() * h->Vp);
+  if (c.proj_hidden > 0) {
+    h->Pp = (int)round_up(c.proj_hidden, 4);
+    h->proj_w1T = h->alloc<float>((i64)c.proj_hidden * round_up(c.Hd, 4));
+    h->pz1 = h->alloc<float>(Lm * Bm * h->Pp); h->dpz1 = h->alloc<float>(Lm * Bm * h->Pp);
+    h->g_pz = h->alloc<float>(Bm * h->beam_m * h->Pp);
+  }
   for (int s = 0; s < c.n_subnets; ++s) {
     h->conv_wT[s] = h->alloc<float>((i64)c.E * round_up(c.subnet_W[s] * c.subnet_C[s], 4));
     h->conv_wT_lo[s] = nullptr;
@@ -791,7 +812,9 @@ void repack(e2t_handle* h, const float* src, int src_id, bool side_ok = false) {
   }
   tr(src + h->dec_K, 4 * c.Hd, h->dec_KT, h->ld_dec_kt, c.D, 4 * c.Hd);
   tr(src + h->dec_K + (i64)c.D * 4 * c.Hd, 4 * c.Hd, h->dec_KT + h->Dp, h->ld_dec_kt, c.Hd, 4 * c.Hd);
-  tr(src + h->proj_w, c.Hd, h->proj_wT, h->Vp, c.V, c.Hd);
+  tr(src + h->proj_w, h->proj_in_width(), h->proj_wT, h->Vp, c.V, h->proj_in_width());
+  if (c.proj_hidden > 0)   // W1 [Hd, P] -> W1^T [P, Hd]: the K-major B operand of the hidden layer's forward GEMM
+    tr(src + h->proj_w1, c.proj_hidden, h->proj_w1T, round_up(c.Hd, 4), c.Hd, c.proj_hidden);
   if (c.attention != E2T_ATTN_NONE) {
     tr(src + h->at_wc, 2 * c.Hd, h->at_combT, c.Hd, c.Hd, 2 * c.Hd);      // [Hd, 2Hd] -> [2Hd, Hd]
     tr(src + h->at_wq, c.Hd, h->at_queryT, c.Hd, c.Hd, c.Hd);
@@ -1140,8 +1163,17 @@ void decoder_forward(e2t_handle* h, const Inputs& in, int B, int L, bool train, 
     LAUNCH(h, k_tanh_fwd, grid1(rows * c.Hd), dim3(256), 0, h->at_ht, rows * c.Hd);
     proj_in = h->at_ht;
   }
-  // logits = h Wp^T + b ; Wp canonical [V,Hd] is already the K-major B operand
-  gemm(h, proj_in, c.Hd, 1, Wc + h->proj_w, 1, c.Hd, h->logits, h->Vp, (int)rows, c.V, c.Hd, Wc + h->proj_b, 0.f);
+  int ld_pi = c.Hd;
+  if (c.proj_hidden > 0) {
+    // optional hidden layer of the projection: pz1 = dropout(relu(proj_in W1 + b1))
+    gemm(h, proj_in, c.Hd, 1, h->proj_w1T, 1, round_up(c.Hd, 4), h->pz1, h->Pp, (int)rows, c.proj_hidden, c.Hd, Wc + h->proj_b1, 0.f);
+    DropP dpp = make_drop(seed, E2T_STREAM_PROJ, train ? c.ff_dropout : 0.f);
+    LAUNCH(h, k_act_dropout, grid1(rows * c.proj_hidden), dim3(256), 0, h->pz1, rows, c.proj_hidden, h->Pp, E2T_ACT_RELU, dpp);
+    proj_in = h->pz1; ld_pi = h->Pp;
+  }
+  // logits = h Wp^T + b ; Wp canonical [V,PI] is already the K-major B operand
+  const int PI = h->proj_in_width();
+  gemm(h, proj_in, ld_pi, 1, Wc + h->proj_w, 1, PI, h->logits, h->Vp, (int)rows, c.V, PI, Wc + h->proj_b, 0.f);
   LAUNCH(h, k_softmax_ce, dim3((unsigned)rows), dim3(128), 0, h->logits, h->Vp, c.V, h->d_tgt, c.pad_id,
          h->pen_dec, h->loss_rows, with_grad ? 1 : 0);
   LAUNCH(h, k_reduce_loss, dim3(1), dim3(256), 0, h->loss_rows, h->d_tgt, c.pad_id, (int)rows, h->d_loss, h->d_ntok,
@@ -1400,6 +1432,10 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
   const float* proj_in = attn ? h->at_ht : h->hdec;
   // (without attention the persistent decoder BPTT below leaves 48 SMs idle: the projection's weight gradient runs beside it
   //  on the side stream, the decoder's own weight / embedding gradients beside the top encoder layer's BPTT)
+  // (with a hidden projection layer the final layer reads pz1 [rows, P] instead of the decoder output)
+  const int PH = c.proj_hidden, PI = h->proj_in_width();
+  const float* fin = PH > 0 ? h->pz1 : proj_in;
+  const int ld_fin = PH > 0 ? h->Pp : c.Hd;
   bool dec_side = false;
 #ifndef E2T_EMU
   {
@@ -1409,13 +1445,25 @@ void backward(e2t_handle* h, int subnet, const Inputs& in, int B, int T, int L, 
   }
   if (dec_side) {
     SideScope side(h, c.n_enc_layers + 1);
-    gemm(h, h->logits, 1, h->Vp, proj_in, c.Hd, 1, G + h->proj_w, c.Hd, c.V, c.Hd, (int)rows, nullptr, 0.f);
+    gemm(h, h->logits, 1, h->Vp, fin, ld_fin, 1, G + h->proj_w, PI, c.V, PI, (int)rows, nullptr, 0.f);
   }
 #endif
-  if (!dec_side) gemm(h, h->logits, 1, h->Vp, proj_in, c.Hd, 1, G + h->proj_w, c.Hd, c.V, c.Hd, (int)rows, nullptr, 0.f);
+  if (!dec_side) gemm(h, h->logits, 1, h->Vp, fin, ld_fin, 1, G + h->proj_w, PI, c.V, PI, (int)rows, nullptr, 0.f);
   batch_colsum(h, h->logits, rows, c.V, h->Vp, G + h->proj_b);
-  // d(proj input) [rows,Hd] = dlogits Wp ; B operand (k=v, n=u) = Wp[v*Hd+u] -> packed transpose is the K-major form
-  gemm(h, h->logits, h->Vp, 1, h->proj_wT, 1, h->Vp, attn ? h->at_dht : h->dhdec, c.Hd, (int)rows, c.Hd, c.V, nullptr, 0.f);
+  float* d_pin = attn ? h->at_dht : h->dhdec;       // gradient wrt the projection's input (decoder output or attention output)
+  if (PH > 0) {
+    // dpz1 [rows,P] = dlogits Wp ; through the dropout / relu ; dW1 [Hd,P] = proj_in^T dpz1 ; db1 ; d(proj input) = dpz1 W1^T
+    gemm(h, h->logits, h->Vp, 1, h->proj_wT, 1, h->Vp, h->dpz1, h->Pp, (int)rows, PH, c.V, nullptr, 0.f);
+    DropP dpp = make_drop(seed, E2T_STREAM_PROJ, train ? c.ff_dropout : 0.f);
+    LAUNCH(h, k_act_dropout_bwd, grid1(rows * PH), dim3(256), 0, h->dpz1, h->pz1, rows, PH, h->Pp, E2T_ACT_RELU, dpp);
+    gemm(h, proj_in, 1, c.Hd, h->dpz1, h->Pp, 1, G + h->proj_w1, PH, c.Hd, PH, (int)rows, nullptr, 0.f);
+    batch_colsum(h, h->dpz1, rows, PH, h->Pp, G + h->proj_b1);
+    // canonical W1 [Hd,P] is the K-major B operand (n = u, k = p)
+    gemm(h, h->dpz1, h->Pp, 1, P + h->proj_w1, 1, PH, d_pin, c.Hd, (int)rows, c.Hd, PH, nullptr, 0.f);
+  } else {
+    // d(proj input) [rows,Hd] = dlogits Wp ; B operand (k=v, n=u) = Wp[v*Hd+u] -> packed transpose is the K-major form
+    gemm(h, h->logits, h->Vp, 1, h->proj_wT, 1, h->Vp, d_pin, c.Hd, (int)rows, c.Hd, c.V, nullptr, 0.f);
+  }
   if (attn) {
     const EncLayer& top = h->enc.back();
     LAUNCH(h, k_tanh_bwd, grid1(rows * c.Hd), dim3(256), 0, h->at_dht, h->at_ht, rows * c.Hd);      // -> d(pre-tanh)
@@ -1660,7 +1708,14 @@ void decode_step(e2t_handle* h, int rows, const int* prev, const float* h_in, co
     LAUNCH(h, k_tanh_fwd, grid1((i64)rows * c.Hd), dim3(256), 0, h->g_ht, (i64)rows * c.Hd);
     proj_in = h->g_ht;
   }
-  gemm(h, proj_in, c.Hd, 1, Wc + h->proj_w, 1, c.Hd, h->g_logits, h->Vp, rows, c.V, c.Hd, Wc + h->proj_b, 0.f);
+  int ld_pi = c.Hd;
+  if (c.proj_hidden > 0) {
+    gemm(h, proj_in, c.Hd, 1, h->proj_w1T, 1, round_up(c.Hd, 4), h->g_pz, h->Pp, rows, c.proj_hidden, c.Hd, Wc + h->proj_b1, 0.f);
+    LAUNCH(h, k_act_dropout, grid1((i64)rows * c.proj_hidden), dim3(256), 0, h->g_pz, (i64)rows, c.proj_hidden, h->Pp, E2T_ACT_RELU, none);
+    proj_in = h->g_pz; ld_pi = h->Pp;
+  }
+  const int PI = h->proj_in_width();
+  gemm(h, proj_in, ld_pi, 1, Wc + h->proj_w, 1, PI, h->g_logits, h->Vp, rows, c.V, PI, Wc + h->proj_b, 0.f);
 }
 
 TensorInfo& find_tensor(e2t_handle* h, const char* name) {
@@ -2147,7 +2202,7 @@ static void greedy_body(e2t_handle* h, int subnet, const Inputs& in, int B, int 
   static const int small_rows = getenv("E2T_SMALL_DECODE_ROWS") ? std::max(0, std::min(kDecSmallRows, atoi(getenv("E2T_SMALL_DECODE_ROWS")))) : 4;
   const size_t smem_cell = ((size_t)B * (h->Dp + c.Hd) + 4 * kDecSmallUnits * B) * sizeof(float);
   const size_t smem_pick = ((size_t)B * c.Hd + 8 * B) * sizeof(float);
-  const bool small = B <= small_rows && c.attention == E2T_ATTN_NONE && (c.Hd & 3) == 0 && (h->ld_dec_kt & 3) == 0 &&
+  const bool small = B <= small_rows && c.attention == E2T_ATTN_NONE && c.proj_hidden == 0 && (c.Hd & 3) == 0 && (h->ld_dec_kt & 3) == 0 &&
                      smem_cell <= 48 * 1024 && smem_pick <= 48 * 1024 && !no_small;
   for (int k = 0; k < max_len; ++k) {
     float* ho = h->g_h[k & 1]; float* co = h->g_c[k & 1];

@@ -48,6 +48,8 @@ class EngineConfig:
     aux_F: int = 0
     aux_kind: str = "gaussian"
     aux_penalty: float = 1.0
+    # layer_sizes['decoder_projection'] (yaml:65, empty in the shipped manifests): one optional hidden FF layer; 0 = none
+    proj_hidden: int = 0
 
     def to_c(self) -> L.E2TConfig:
         c = L.E2TConfig()
@@ -73,6 +75,7 @@ class EngineConfig:
         c.attention = L.ATTN[self.attention]
         c.aux_layer, c.aux_hidden, c.aux_F = int(self.aux_layer), int(self.aux_hidden), int(self.aux_F)
         c.aux_kind, c.aux_penalty = L.AUX_KIND[self.aux_kind], float(self.aux_penalty)
+        c.proj_hidden = int(self.proj_hidden)
         return c
 
 

@@ -98,8 +98,12 @@ class SequenceNetwork:
             pad_id=flist.index(self.pad_token) if self.pad_token in flist else 0,
             eos_id=flist.index(self.EOS_token), start_id=flist.index(self.EOS_token),
         )
-        if ls.get('decoder_projection'):
-            raise NotImplementedError("hidden decoder_projection layers are not built (empty in the shipped manifests)")
+        # hidden layers of the vocabulary projection (mochastar_word_sequence.yaml:65; empty in every shipped manifest)
+        proj_hidden = list(ls.get('decoder_projection') or [])
+        if len(proj_hidden) > 1:
+            raise NotImplementedError("at most one hidden layer in decoder_projection")
+        if proj_hidden:
+            geo['proj_hidden'] = int(proj_hidden[0])
         # A6: an 'encoder_<n>_targets' stream puts an FF head on encoder layer n (trainers.py:791-799; yaml:54,68-69)
         self._aux_key = None
         for key, man in first.items():

@@ -97,6 +97,9 @@ typedef struct e2t_config {
   int32_t aux_F;                         /* num_features of the encoder targets; 0 disables the head */
   int32_t aux_kind;                      /* E2T_AUX_* */
   float aux_penalty;                     /* encoder_1_targets_penalty_scale */
+  /* layer_sizes['decoder_projection'] (mochastar_word_sequence.yaml:65; empty in every shipped manifest): width of ONE optional
+   * hidden FF layer (relu + FF dropout) between the decoder output and the vocabulary projection; 0 = none. */
+  int32_t proj_hidden;
 } e2t_config;
 
 const char* e2t_last_error(void);

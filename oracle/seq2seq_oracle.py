@@ -68,6 +68,9 @@ class OracleConfig:
     aux_F: int = 0                            # num_features of the encoder targets (13 MFCC-type / 42 phoneme classes)
     aux_kind: str = "gaussian"                # "gaussian": float targets, squared error; "categorical": int targets, CE
     aux_penalty: float = 1.0                  # encoder_1_targets_penalty_scale, yaml:54
+    # layer_sizes['decoder_projection'] (yaml:65, empty in every shipped manifest): one optional hidden FF layer between the
+    # decoder state and the vocabulary projection -- relu + FF dropout like the other FF layers [CHOICE]
+    proj_hidden: int = 0
 
     def __post_init__(self):
         assert self.Hd == 2 * self.H[-1], "bridge needs decoder_rnn == 2*encoder_rnn[-1]"
@@ -95,9 +98,12 @@ def param_shapes(cfg: OracleConfig) -> "Dict[str, Tuple[int, ...]]":
     base = "seq2seq/decoder_rnn/multi_rnn_cell/cell_0/lstm_cell"
     shapes[base + "/kernel"] = (cfg.D + cfg.Hd, 4 * cfg.Hd)
     shapes[base + "/bias"] = (4 * cfg.Hd,)
-    base = f"seq2seq/decoder_projection_{cfg.Hd}_{cfg.V}_0"
-    shapes[base + "/weights"] = (cfg.V, cfg.Hd)            # transposed, trainers.py:513-520
-    shapes[base + "/biases"] = (cfg.V,)
+    hid, out = proj_names(cfg)
+    if hid is not None:                                    # '<x>_projection' scopes number their layers, trainers.py:488-520
+        shapes[hid + "/weights"] = (cfg.Hd, cfg.proj_hidden)
+        shapes[hid + "/biases"] = (cfg.proj_hidden,)
+    shapes[out + "/weights"] = (cfg.V, cfg.proj_hidden or cfg.Hd)   # final layer: transposed, trainers.py:513-520
+    shapes[out + "/biases"] = (cfg.V,)
     if cfg.attention in ("luong", "bahdanau"):
         # stored [out, in] like the projection; q = h Wq^T, h~ = tanh(Wc [ctx; h] + bc)
         shapes["seq2seq/decoder_attention/query/weights"] = (cfg.Hd, cfg.Hd)
@@ -118,6 +124,14 @@ def param_shapes(cfg: OracleConfig) -> "Dict[str, Tuple[int, ...]]":
         shapes[base + "/weights"] = (cfg.aux_F, n_in)      # final layer of a *_projection: transposed, trainers.py:513-520
         shapes[base + "/biases"] = (cfg.aux_F,)
     return shapes
+
+
+def proj_names(cfg: OracleConfig):
+    """(hidden-layer base name or None, output-layer base name) of the decoder projection."""
+    if cfg.proj_hidden > 0:
+        return (f"seq2seq/decoder_projection_{cfg.Hd}_{cfg.proj_hidden}_0",
+                f"seq2seq/decoder_projection_{cfg.proj_hidden}_{cfg.V}_1")
+    return None, f"seq2seq/decoder_projection_{cfg.Hd}_{cfg.V}_0"
 
 
 def aux_names(cfg: OracleConfig):
@@ -180,7 +194,7 @@ def dropout_keep(seed: int, stream: int, n: int, p: float) -> np.ndarray:
 
 
 # stream ids (must match csrc): conv output 0 ; encoder layer l output 1+l ; decoder embedding 64
-STREAM_CONV, STREAM_ENC0, STREAM_DEMB, STREAM_AUX = 0, 1, 64, 96
+STREAM_CONV, STREAM_ENC0, STREAM_DEMB, STREAM_AUX, STREAM_PROJ = 0, 1, 64, 96, 112
 
 
 # ------------------------------------------------------------------------------------------------
@@ -321,8 +335,9 @@ def bahdanau_attention(cfg, P, h, enc, lens2):
                       + P["seq2seq/decoder_attention/combine/biases"])
 
 
-def decoder_step(cfg, P, y_prev, h, c, emb_mask=None, enc=None, lens2=None):
-    """One decoder step: Emb[y_prev] (+bias, act) -> LSTM(Hd) [-> attention] -> logits = h Wp^T + b."""
+def decoder_step(cfg, P, y_prev, h, c, emb_mask=None, enc=None, lens2=None, proj_mask=None):
+    """One decoder step: Emb[y_prev] (+bias, act) -> LSTM(Hd) [-> attention] [-> relu(. W1 + b1), FF dropout] ->
+    logits = . Wp^T + b."""
     eb = f"seq2seq/decoder_embedding_{cfg.V}_{cfg.D}_0"
     e = _act(P[eb + "/weights"][y_prev] + P[eb + "/biases"], cfg.emb_act)
     if emb_mask is not None:
@@ -331,12 +346,16 @@ def decoder_step(cfg, P, y_prev, h, c, emb_mask=None, enc=None, lens2=None):
     K, bias = P[rb + "/kernel"], P[rb + "/bias"]
     z = e @ K[:cfg.D] + h @ K[cfg.D:] + bias
     h, c = lstm_cell(z, c)
-    pb = f"seq2seq/decoder_projection_{cfg.Hd}_{cfg.V}_0"
+    hid, pb = proj_names(cfg)
     ho = h
     if cfg.attention == "luong":
         ho = luong_attention(cfg, P, h, enc, lens2)
     elif cfg.attention == "bahdanau":
         ho = bahdanau_attention(cfg, P, h, enc, lens2)
+    if hid is not None:
+        ho = torch.relu(ho @ P[hid + "/weights"] + P[hid + "/biases"])
+        if proj_mask is not None:
+            ho = ho * proj_mask
     logits = ho @ P[pb + "/weights"].T + P[pb + "/biases"]
     return logits, h, c
 
@@ -350,6 +369,8 @@ def make_masks(cfg, seed, B, T2, L, ff_p, rnn_p, dtype):
     if ff_p > 0:
         masks["conv"] = mk(STREAM_CONV, (T2, B, cfg.E), ff_p).permute(1, 0, 2)
         masks["demb"] = mk(STREAM_DEMB, (L, B, cfg.D), ff_p).permute(1, 0, 2)
+        if cfg.proj_hidden > 0:
+            masks["proj"] = mk(STREAM_PROJ, (L, B, cfg.proj_hidden), ff_p).permute(1, 0, 2)
         if cfg.aux_layer >= 0 and cfg.aux_hidden > 0:
             masks["aux"] = mk(STREAM_AUX, (T2, B, cfg.aux_hidden), ff_p).permute(1, 0, 2)
     if rnn_p > 0:
@@ -407,7 +428,8 @@ def train_loss(cfg, P, x, lens, y, subnet=0, masks=None, aux_targets=None, conv_
     logits_all = []
     for k in range(L):
         em = None if masks is None or "demb" not in masks else masks["demb"][:, k]
-        logits, h, c = decoder_step(cfg, P, prev, h, c, em, acts[f"enc{len(cfg.H) - 1}_out"], acts["lens2"])
+        pm = None if masks is None or "proj" not in masks else masks["proj"][:, k]
+        logits, h, c = decoder_step(cfg, P, prev, h, c, em, acts[f"enc{len(cfg.H) - 1}_out"], acts["lens2"], pm)
         logits_all.append(logits)
         lp = torch.log_softmax(logits, dim=1)
         m = (y[:, k] != cfg.pad_id).to(x.dtype)

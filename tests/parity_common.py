@@ -14,6 +14,9 @@ MEDIUM = dict(subnet_ids=(400,), subnet_C=(64,), subnet_W=(12,), E=32, H=(64, 64
 # persistent tcgen05 recurrent kernels at the config-2 layer shape while the oracle still runs in seconds
 WIDE = dict(subnet_ids=(400,), subnet_C=(32,), subnet_W=(12,), E=100, H=(400, 400), D=24, Hd=800, V=200)
 # optional Luong attention (A7) on top of the same geometries
+# one hidden layer in the vocabulary projection (layer_sizes['decoder_projection'], yaml:65)
+TINY_PROJ = dict(TINY, proj_hidden=7)
+MEDIUM_PROJ = dict(MEDIUM, proj_hidden=96)
 TINY_ATTN = dict(TINY, attention="luong")
 MEDIUM_ATTN = dict(MEDIUM, attention="luong")
 TINY_BAH = dict(TINY, attention="bahdanau")
@@ -77,7 +80,7 @@ def make_params(ocfg, seed=1, bias_scale=0.1, eos_bias=None):
         if P[k].ndim == 1:
             P[k] = (torch.randn(P[k].shape, generator=g) * bias_scale).float()
     if eos_bias is not None:  # make greedy hypotheses longer than one token
-        pb = f"seq2seq/decoder_projection_{ocfg.Hd}_{ocfg.V}_0/biases"
+        pb = O.proj_names(ocfg)[1] + "/biases"
         P[pb][ocfg.eos_id] = eos_bias
         P[pb][ocfg.pad_id] = -20.0
     return P

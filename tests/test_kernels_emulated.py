@@ -346,3 +346,19 @@ def test_small_batch_decode_equals_batched_path(emu_lib):
     eng.close()
     assert (t4 == t5[:4]).all()
     assert np.abs(lp4 - lp5[:4]).max() < 1e-5
+
+
+def test_hidden_decoder_projection_layer(emu_lib):
+    """layer_sizes['decoder_projection'] = [P] (mochastar_word_sequence.yaml:65): a relu + FF-dropout layer between the decoder
+    output and the vocabulary projection -- loss, every gradient (incl. the layer's own tensors under their numbered
+    '<x>_projection' names, trainers.py:488-520) and greedy / beam decode against the oracle."""
+    pc.check_train_step(emu_lib, pc.TINY_PROJ, 3, 19, 5)
+    pc.check_train_step(emu_lib, pc.TINY_PROJ, 3, 19, 5, ff=0.1, rnn=0.5)
+    pc.check_decode(emu_lib, pc.TINY_PROJ, 6, 21, 6)
+    pc.check_decode(emu_lib, pc.TINY_PROJ, 4, 21, 6, beam=4)
+    eng = pc.engine_for(pc.TINY_PROJ, emu_lib, 3, 19, 5)
+    names = eng.tensors()
+    assert names["seq2seq/decoder_projection_16_7_0/weights"][0] == (16, 7)
+    assert names["seq2seq/decoder_projection_7_11_1/weights"][0] == (11, 7)      # last layer: stored transposed
+    assert "seq2seq/decoder_projection_16_11_0/weights" not in names
+    eng.close()

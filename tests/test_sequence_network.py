@@ -131,3 +131,24 @@ def test_encoder_targets_and_saliencies(tmp_path, emu_lib, stream, F):
     ref = np.mean([np.sqrt((g ** 2).sum(0)) for g in seqs], axis=0)
     # 'norms' also counts the gradient on the zero frames that complete each trial's last conv window
     assert (ref <= aux * (1 + 1e-5)).all() and np.allclose(ref, aux, rtol=0.2)
+
+
+def test_hidden_decoder_projection_from_the_manifest(tmp_path, emu_lib):
+    """layer_sizes['decoder_projection'] = [P] (mochastar_word_sequence.yaml:65 ships it empty): the hidden layer is built,
+    trained and check-pointed under the numbered '<x>_projection' names recover_model_sizes parses (trainers.py:488-520)."""
+    s = _subject(tmp_path)
+    s.write_tf_records_maybe()
+    man = dict(MANIFEST, layer_sizes=dict(MANIFEST["layer_sizes"], decoder_projection=[9]), N_epochs=20)
+    net = SequenceNetwork(man, VERBOSE=False, N_cases=6, max_hyp_length=5, learning_rate=2e-2, lib=emu_lib, gemm_backend="simt")
+    net.checkpoint_path = str(tmp_path / "ckpt_proj" / "model.ckpt")
+    tr = net.fit([s])["training"]
+    assert tr.losses[-1] < tr.losses[0], tr.losses
+    shapes = prm.variable_to_shape_map(net.checkpoint_path, 20)
+    assert shapes["seq2seq/decoder_projection_16_9_0/weights"] == [16, 9]
+    assert shapes[f"seq2seq/decoder_projection_9_{len(VOCAB)}_1/weights"] == [len(VOCAB), 9]      # last layer: transposed
+    assert f"seq2seq/decoder_projection_16_{len(VOCAB)}_0/weights" not in shapes
+    two = dict(MANIFEST, layer_sizes=dict(MANIFEST["layer_sizes"], decoder_projection=[9, 9]))
+    net2 = SequenceNetwork(two, VERBOSE=False, N_cases=6, max_hyp_length=5, lib=emu_lib, gemm_backend="simt")
+    net2.checkpoint_path = str(tmp_path / "ckpt_proj2" / "model.ckpt")
+    with pytest.raises(NotImplementedError):
+        net2.fit([s])

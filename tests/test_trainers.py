@@ -128,3 +128,14 @@ def test_introspection_callers(tmp_path, emu_lib):
     assert recs[0]["decoder_targets"].dtype == object and recs[0]["decoder_targets"][0, 0].decode().endswith("_")
     with np.testing.assert_raises(ValueError):
         next(tr.tf_record_to_numpy_data(999, 3))
+
+
+def test_recover_model_sizes_with_hidden_decoder_projection(tmp_path, emu_lib):
+    """A checkpoint of a model with layer_sizes['decoder_projection'] = [9] parses back to that list and the vocabulary
+    size under the reference's rules (numbered '<x>_projection' layers, the last one transposed: trainers.py:488-520)."""
+    tr = _trainer(tmp_path, emu_lib, ids=(400,), N_epochs=5, assessment_epoch_interval=5)
+    tr.net.layer_sizes = dict(tr.net.layer_sizes, decoder_projection=[9])
+    tr.parallel_transfer_learn()
+    layer_sizes, data_sizes, _, _ = tr.recover_model_sizes()
+    assert layer_sizes["decoder_projection"] == [9] and data_sizes[None]["decoder_targets"] == len(VOCAB)
+    assert layer_sizes["decoder_rnn"] == [16]
