@@ -46,7 +46,8 @@ class SpeedModel(nn.Module):
 
     def __init__(self, cfg: O.OracleConfig, P: Dict[str, torch.Tensor], subnet: int = 0):
         super().__init__()
-        assert cfg.attention == "none" and cfg.aux_layer < 0, "speed mode covers the reference model (no optional rows)"
+        assert cfg.attention == "none" and cfg.aux_layer < 0 and cfg.proj_hidden == 0, \
+            "speed mode covers the reference model (no optional rows)"
         self.cfg, self.subnet = cfg, subnet
         sid, C, W = cfg.subnet_ids[subnet], cfg.subnet_C[subnet], cfg.subnet_W[subnet]
         self.W, self.C = W, C

@@ -147,16 +147,13 @@ def test_small_batch_greedy_decode(gpu_lib, backend):
 @pytest.mark.parametrize("backend", ["simt", "auto"])
 def test_hidden_decoder_projection_layer(gpu_lib, backend):
     """layer_sizes['decoder_projection'] = [P] (mochastar_word_sequence.yaml:65): the optional relu + FF-dropout layer in front
-    of the vocabulary projection, forward / backward / decode against the oracle.  On the tensor-core backend the hidden
-    pre-activations are tf32 products: a pre-activation within ~1e-3 of zero may land on the other side of the relu and
-    move a whole column of its gradients (the effect measured for the encoder-targets head), so the
-    per-tensor gradient bound there is the loose one; loss, state and the decode are held to the usual bounds."""
+    of the vocabulary projection, forward / backward / decode against the oracle on both GEMM backends (measured on B200,
+    profiles/parity_r2.json: worst gradient tensor 9.5e-3 of its largest entry on the tensor-core backend -- the layer's own
+    W1 / b1, whose relu sees tf32 products -- against the backend's usual 3e-2 bound)."""
+    pc.check_train_step(gpu_lib, pc.MEDIUM_PROJ, 16, 96, 6, backend=backend,
+                        name="train_step/auto/hidden_projection" if backend == "auto" else None)
     if backend == "simt":
-        pc.check_train_step(gpu_lib, pc.MEDIUM_PROJ, 16, 96, 6, backend=backend)
         pc.check_train_step(gpu_lib, pc.MEDIUM_PROJ, 16, 96, 6, ff=0.1, rnn=0.5, backend=backend)
-    else:
-        pc.check_train_step(gpu_lib, pc.MEDIUM_PROJ, 16, 96, 6, backend=backend, grad_tol=0.25,
-                            name="train_step/auto/hidden_projection")
     pc.check_decode(gpu_lib, pc.MEDIUM_PROJ, 8, 96, 6, backend=backend)
     pc.check_decode(gpu_lib, pc.MEDIUM_PROJ, 4, 96, 6, beam=4, backend=backend)
 
