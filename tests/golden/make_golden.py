@@ -46,6 +46,7 @@ def main():
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "seq2seq_tiny.npz"), **out)
     print("wrote seq2seq_tiny.npz: loss", loss, "ntok", ntok)
     make_optional()
+    make_hidden_projection()
 
 
 def make_optional():
@@ -74,5 +75,37 @@ def make_optional():
     print("wrote seq2seq_tiny_optional.npz: loss", loss, "=", acts["decoder_loss"], "+", acts["aux_loss"])
 
 
+def make_hidden_projection(only=True):
+    """seq2seq_tiny_proj.npz: the model with one hidden decoder_projection layer (layer_sizes['decoder_projection'] = [7],
+    mochastar_word_sequence.yaml:65): loss, every gradient, one Adam+EMA step, greedy and beam decode."""
+    ocfg = O.OracleConfig(**pc.TINY_PROJ)
+    P32 = pc.make_params(ocfg, eos_bias=-1.0)
+    P = {k: v.double() for k, v in P32.items()}
+    B, T, L = 5, 19, 5
+    x, lens, y = pc.make_batch(ocfg, B, T, L, seed=13)
+    xt, yt = torch.from_numpy(x).double(), torch.from_numpy(y).long()
+    loss, ntok, g, acts = O.loss_and_grads(ocfg, P, xt, None, yt)
+    out = {"x": x, "lens": lens, "y": y, "loss": np.float64(loss), "ntok": np.int64(ntok)}
+    for k, v in P32.items():
+        out["P|" + k.replace("/", "|")] = v.numpy()
+    for k, v in g.items():
+        out["G|" + k.replace("/", "|")] = v.numpy()
+    opt = O.AdamEMA(ocfg, P)
+    P2 = dict(P)
+    opt.step(P2, g, 1.0 / ntok)
+    for k in P2:
+        out["W1|" + k.replace("/", "|")] = P2[k].numpy()
+        out["S1|" + k.replace("/", "|")] = opt.ema[k].numpy()
+    toks, logp, _ = O.greedy_decode(ocfg, P, xt, None, max_len=6, temperature=0.7)
+    out["greedy_tokens"], out["greedy_logp"] = toks.numpy(), logp.numpy()
+    bt, bs = O.beam_decode(ocfg, P, xt, None, beam=3, max_len=6, temperature=0.7)
+    out["beam_tokens"], out["beam_scores"] = bt.numpy(), bs.numpy()
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "seq2seq_tiny_proj.npz"), **out)
+    print("wrote seq2seq_tiny_proj.npz: loss", loss, "ntok", ntok)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "proj":      # add the newer fixture without touching the committed ones
+        make_hidden_projection()
+    else:
+        main()

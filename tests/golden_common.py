@@ -76,3 +76,38 @@ def check_engine_against_optional_golden(lib, backend="simt", tol=2e-4):
     assert (toks == z["greedy_tokens"]).all()
     assert np.abs(logp - z["greedy_logp"]).max() < 2e-3
     eng.close()
+
+
+GOLD_PROJ = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "seq2seq_tiny_proj.npz")
+
+
+def load_proj():
+    z = np.load(GOLD_PROJ)
+    P = {k[2:].replace("|", "/"): z[k] for k in z.files if k.startswith("P|")}
+    return z, P
+
+
+def check_engine_against_proj_golden(lib, backend="simt", tol=2e-4):
+    """The model with a hidden decoder_projection layer against tests/golden/seq2seq_tiny_proj.npz."""
+    z, P = load_proj()
+    B, T = z["x"].shape[0], z["x"].shape[1]
+    eng = pc.engine_for(pc.TINY_PROJ, lib, B, T, 6, max_beam=3, gemm_backend=backend)
+    eng.set_all(P)
+    loss, ntok = eng.train_step_grads(z["x"], None, z["y"], seed=0)
+    assert ntok == int(z["ntok"])
+    assert abs(loss - float(z["loss"])) <= tol * abs(float(z["loss"]))
+    for k, v in eng.get_all(_lib.GRAD).items():
+        assert pc.rel_err(v, z["G|" + k.replace("/", "|")]) <= 5 * tol, k
+    eng.adam_ema_step(1.0 / ntok)
+    for k, v in eng.get_all(_lib.VALUE).items():
+        assert np.allclose(v, z["W1|" + k.replace("/", "|")], rtol=1e-4, atol=1e-6), k
+    for k, v in eng.get_all(_lib.EMA).items():
+        assert np.allclose(v, z["S1|" + k.replace("/", "|")], rtol=1e-4, atol=1e-6), k
+    eng.set_all(P)
+    toks, logp = eng.greedy_decode(z["x"], None, max_len=6, temperature=0.7)
+    assert (toks == z["greedy_tokens"]).all()
+    assert np.abs(logp - z["greedy_logp"]).max() < 2e-3
+    bt, bs = eng.beam_decode(z["x"], None, beam=3, max_len=6, temperature=0.7)
+    assert np.abs(bs - z["beam_scores"]).max() < 5e-3
+    assert (bt[:, 0] == z["beam_tokens"][:, 0]).all()
+    eng.close()

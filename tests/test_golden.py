@@ -29,6 +29,20 @@ def test_emulated_engine_reproduces_golden_vectors(emu_lib):
     gc.check_engine_against_golden(emu_lib)
 
 
+def test_hidden_projection_reproduces_golden_vectors(emu_lib):
+    """layer_sizes['decoder_projection'] = [7]: the oracle (fp32) and the emulated engine against seq2seq_tiny_proj.npz (fp64)."""
+    z, P = gc.load_proj()
+    ocfg = O.OracleConfig(**pc.TINY_PROJ)
+    Pt = {k: torch.from_numpy(v) for k, v in P.items()}
+    loss, ntok, g, acts = O.loss_and_grads(ocfg, Pt, torch.from_numpy(z["x"]), None, torch.from_numpy(z["y"]).long())
+    assert ntok == int(z["ntok"]) and abs(loss - float(z["loss"])) < 1e-4 * abs(float(z["loss"]))
+    for k, v in g.items():
+        assert pc.rel_err(v.numpy(), z["G|" + k.replace("/", "|")]) < 1e-4, k
+    toks, _, _ = O.greedy_decode(ocfg, Pt, torch.from_numpy(z["x"]), None, max_len=6, temperature=0.7)
+    assert (toks.numpy() == z["greedy_tokens"]).all()
+    gc.check_engine_against_proj_golden(emu_lib)
+
+
 def test_optional_rows_reproduce_golden_vectors(emu_lib):
     """A6 + A7 (Bahdanau) + A13: the oracle (fp32) and the emulated engine against seq2seq_tiny_optional.npz (fp64)."""
     z, P = gc.load_optional()

@@ -186,6 +186,13 @@ def test_golden_vectors(gpu_lib, backend, tol):
     gc.check_engine_against_golden(gpu_lib, backend=backend, tol=tol)
 
 
+def test_hidden_projection_golden_vectors(gpu_lib):
+    """The model with a hidden decoder_projection layer against tests/golden/seq2seq_tiny_proj.npz through the CUDA path
+    (TINY shapes stay on the fp32 CUDA cores)."""
+    import golden_common as gc
+    gc.check_engine_against_proj_golden(gpu_lib, backend="simt")
+
+
 def test_optional_rows_golden_vectors(gpu_lib):
     """A6 + A7 (Bahdanau) + A13 against tests/golden/seq2seq_tiny_optional.npz through the CUDA path."""
     import golden_common as gc
